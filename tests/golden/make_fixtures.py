@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Regenerate tests/golden/ from the reference checkout (run in the build container only).
+
+The reference is C++ and cannot be imported; what this script does is
+  * copy the sample frames the reference's own tests use (data, not source) from
+    /root/reference/samples (sz3/cimbar-samples) and record the SHA-256 of their decoded RGB pixels,
+  * record the reference's golden SHA-256s with the file:line they come from,
+  * record cv2-derived pins for the OpenCV arithmetic the oracle restates
+    (cvtColor / adaptiveThreshold / filter2D), so a cv2 change is detected rather than silently followed.
+"""
+import hashlib, json, os, shutil, sys
+import cv2, numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+SAMPLES = [
+    "b/tr_0.png", "b/tr_1.png", "b/tr_2.png", "b/tr_3.png", "b/ex2434.jpg",
+    "6bit/4color_ecc30_fountain_0.png", "6bit/4_30_f0_627_extract.jpg", "mycell.png",
+]
+
+GOLDENS = [  # (sample, mode, ecc, bytes, sha256, source)
+    ("b/tr_0.png", 68, False, 9300, "ddcb6cd47751df1402dcf2cffdace212bc9e4a4b6ef097ad4828913086309469", "src/lib/encoder/test/DecoderTest.cpp:26-36"),
+    ("b/tr_0.png", 68, True, 7500, "a0e9fff8cd5b13807fae215b8b07e38091d3f533ff46243b53ee7f74fbbee0d5", "src/lib/encoder/test/DecoderTest.cpp:38-48"),
+    ("6bit/4color_ecc30_fountain_0.png", 4, False, 9300, "7e1919b1210ccc332fc56e8b35cccd622d980f03c6c3b32338bb00aa4b6a22a2", "src/lib/encoder/test/DecoderTest.cpp:64-77"),
+    ("6bit/4color_ecc30_fountain_0.png", 4, True, 7500, "382c76644a4dff475c5793c5fe061e35e47be252010d29aeaf8d93ee6a3f7045", "src/lib/encoder/test/DecoderTest.cpp:79-90"),
+    ("6bit/4_30_f0_627_extract.jpg", 4, False, 9300, "2040c157884c476def842f7854621a7655182e5f11a34ade563616d93cb93455", "src/lib/encoder/test/DecoderTest.cpp:92-106"),
+    ("b/scan2434.jpg", 68, False, 9300, "ccb39ac3511a8974a8e98d3ea321d576d974d28f0b9373fc611ce6a4c83b561c", "src/lib/encoder/test/DecoderTest.cpp:50-62"),
+]
+
+
+def load_rgb(path):
+    img = cv2.imread(path, cv2.IMREAD_COLOR)  # TestHelpers.h:8-18: imread + BGR2RGB
+    return np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_BGR2RGB))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit("needs /root/reference")
+    manifest = {"cv2": cv2.__version__, "samples": {}, "goldens": [], "cv_pins": {}}
+    for s in SAMPLES:
+        dst = os.path.join(HERE, s.replace("/", "__"))
+        shutil.copyfile(os.path.join(REF, "samples", s), dst)
+        os.chmod(dst, 0o644)
+        rgb = load_rgb(dst)
+        manifest["samples"][s] = {"file": os.path.basename(dst), "shape": list(rgb.shape), "rgb_sha256": sha(rgb)}
+    # scan2434.jpg (1280x960, not extracted): only its size and its top-left 8x8 patch matter
+    # (CimbReader not good -> colour read at (0,0), Decoder.h:107-114); keep just that.
+    scan = load_rgb(os.path.join(REF, "samples/b/scan2434.jpg"))
+    np.save(os.path.join(HERE, "b__scan2434_topleft8.npy"), scan[:8, :8].copy())
+    manifest["samples"]["b/scan2434.jpg"] = {"file": "b__scan2434_topleft8.npy", "shape": list(scan.shape), "patch": "top-left 8x8 only"}
+    for g in GOLDENS:
+        manifest["goldens"].append(dict(zip(("sample", "mode", "ecc", "bytes", "sha256", "source"), g)))
+    # OpenCV arithmetic pins on a camera frame (clean frames do not discriminate rounding variants)
+    for s in ("b/ex2434.jpg", "6bit/4_30_f0_627_extract.jpg"):
+        rgb = load_rgb(os.path.join(REF, "samples", s))
+        gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)
+        thr5 = cv2.adaptiveThreshold(gray, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, 5, 0)
+        k = np.array([[-0, -1, -0], [-1, 4.5, -1], [-0, -1, -0]], dtype=np.float32)
+        sharp = cv2.filter2D(gray, -1, k)
+        thr7 = cv2.adaptiveThreshold(sharp, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, 7, 0)
+        manifest["cv_pins"][s] = {"gray": sha(gray), "thr5": sha(thr5), "sharp": sha(sharp), "thr7_sharp": sha(thr7)}
+    with open(os.path.join(HERE, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+    print("wrote", len(manifest["samples"]), "samples")
+
+
+if __name__ == "__main__":
+    main()
