@@ -1,0 +1,142 @@
+/*
+ * cb200.h -- C ABI of libcb200.so: the B200 (sm_100a) implementation of libcimbar's per-frame decode hot path.
+ *
+ * Drop-in boundary.  The reference (sz3/libcimbar) has no plugin registry: the path sits
+ * behind header-only C++ templates (Decoder / CimbReader / CimbDecoder) and one facade C ABI (cimbard_*,
+ * src/lib/cimbar_js/cimbar_recv_js.h:11-39).  These entry points are what a binding for this path would call;
+ * each cites the reference interface it replaces (paths relative to the libcimbar checkout).  The header-compatible
+ * C++ shims that route libcimbar's own class names here are in libcimbar_b200/host/ (see INTEGRATION.md).
+ *
+ * Conventions: plain pointers and sizes, no exceptions, int return (0 = CB200_OK, negative = error, see
+ * cb200_last_error()).  A context is bound to one GPU and one CUDA stream and is NOT thread-safe -- same model as
+ * the reference's "one Decoder per thread" (thread_local Config, src/lib/cimb_translator/Config.h:11-15).
+ * Buffers are caller-owned.  `_dev` entry points take device pointers and only enqueue work on the context's
+ * stream (call cb200_sync before reading results); the others take host pointers and return when results are in
+ * host memory.  Frames are tightly packed RGB8, image_size_y rows x image_size_x px x 3 bytes, already extracted
+ * (the output of the reference's Extractor / `--no-deskew` input).
+ */
+#ifndef CB200_H
+#define CB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_OK            0
+#define CB200_ERR_ARG      -1   /* bad argument (null pointer, n out of range, ...) */
+#define CB200_ERR_CUDA     -2   /* CUDA runtime error, text in cb200_last_error() */
+#define CB200_ERR_MODE     -3   /* unknown / unsupported mode_val */
+#define CB200_ERR_NOMEM    -4
+#define CB200_ERR_NODEVICE -5   /* no usable CUDA device: the library never falls back to a CPU path */
+
+/* decode flags */
+#define CB200_FLAG_NO_FALLBACK  0x1u  /* do not run the exact flood-walk kernel on frames K1 flags as inexact (bench only) */
+#define CB200_FLAG_SHARPEN      0x2u  /* needs_sharpen / should_preprocess=true: 3x3 sharpen + block 7 (CimbReader.cpp:17-40) */
+
+/* per-frame status bits written to frame_flags[] */
+#define CB200_FRAME_FALLBACK    0x1u  /* frame was decoded by the exact flood-walk kernel (drift tracking needed) */
+#define CB200_FRAME_INEXACT     0x2u  /* K1 could not prove the drift-0 decode exact and no fallback was run */
+
+typedef struct cb200_ctx cb200_ctx;
+
+/* geometry of the active mode == the cimbar::Config accessors (src/lib/cimb_translator/Config.h:51-175) */
+typedef struct cb200_info {
+    int mode_val;            /* 68 = B, 67 = Bm, 66 = Bu, 4 = 4C, 8 = 8C (Config.h:20-43) */
+    int image_size_x, image_size_y;
+    int frame_bytes;         /* image_size_x * image_size_y * 3 */
+    int total_cells;         /* Config::total_cells() */
+    int symbol_bits, color_bits;
+    int raw_bytes;           /* Config::capacity(): bytes of cell bits per frame (9300) */
+    int raw_symbol_bytes;    /* capacity(symbol_bits): 6200; == raw_bytes for the legacy coupled modes */
+    int ecc_bytes, ecc_block_size;
+    int rs_blocks;           /* RS blocks per frame (60) */
+    int data_bytes;          /* bytes after ECC per frame (7500) */
+    int chunk_size;          /* Config::fountain_chunk_size() (625) */
+    int chunks_per_frame;    /* Config::fountain_chunks_per_frame() (12) */
+    int legacy_mode;
+    int max_frames;          /* batch capacity of this context */
+    int sm_count;
+} cb200_info;
+
+const char* cb200_last_error(void);   /* thread-local text of the last error */
+int cb200_version(void);
+
+/* Replaces: Config::update(mode_val) + Decoder::Decoder() -> CimbDecoder::CimbDecoder()/load_tiles()
+   (src/lib/cimb_translator/Config.h:46-49, src/lib/encoder/Decoder.h:40-45, CimbDecoder.cpp:57-99).
+   Allocates device workspaces for up to max_frames frames per call. device < 0: current device. */
+int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames);
+int cb200_destroy(cb200_ctx* ctx);
+int cb200_get_info(const cb200_ctx* ctx, cb200_info* out);
+/* run on a caller-provided cudaStream_t (e.g. a torch stream); NULL restores the context's own stream */
+int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream);
+int cb200_sync(cb200_ctx* ctx);
+
+/* ---- device-pointer entry points: enqueue only -------------------------------------------------------------- */
+
+/* Replaces: CimbReader::CimbReader (preprocessSymbolGrid) + Decoder::do_decode with use_ecc=false:
+   the flood walk CimbReader::read / read_color over all cells and the de-interleaved MSB-first bit packing
+   (src/lib/cimb_translator/CimbReader.cpp:30-46,:107-162; src/lib/encoder/Decoder.h:60-161).
+   d_rgb: n frames; d_raw_out: n * raw_bytes (symbol stream then colour stream; one coupled stream in legacy modes);
+   d_frame_flags: n bytes or NULL. */
+int cb200_decode_raw_dev(cb200_ctx* ctx, const uint8_t* d_rgb, int n, uint32_t flags,
+                         uint8_t* d_raw_out, uint8_t* d_frame_flags);
+
+/* Replaces: reed_solomon_stream::write + ReedSolomon::decode -> correct_reed_solomon_decode
+   (src/lib/encoder/reed_solomon_stream.h:54-76; src/third_party_lib/libcorrect/src/reed-solomon/decode.c:299-379).
+   d_raw: n * raw_bytes; d_data_out: n * data_bytes (a failed block is zero-filled, reed_solomon_stream.h:96-107);
+   d_block_ok: n * rs_blocks (1 = decoded) or NULL. */
+int cb200_rs_correct_dev(cb200_ctx* ctx, const uint8_t* d_raw, int n, uint8_t* d_data_out, uint8_t* d_block_ok);
+
+/* Replaces: Decoder::decode_fountain into an escrow_buffer_writer, kept in fixed slots
+   (src/lib/encoder/Decoder.h:171-189, aligned_stream.h:39-116, escrow_buffer_writer.h:44-60).
+   d_chunks: n * chunks_per_frame * chunk_size (slot q of frame f valid iff bit q of d_chunk_mask[f] is set:
+   a chunk is dropped when any of its RS blocks failed); d_chunk_mask: n words. */
+int cb200_decode_chunks_dev(cb200_ctx* ctx, const uint8_t* d_rgb, int n, uint32_t flags,
+                            uint8_t* d_chunks, uint32_t* d_chunk_mask, uint8_t* d_frame_flags);
+
+/* ---- host-pointer entry points: H2D + kernels + D2H, synchronous ---------------------------------------------- */
+
+/* == Decoder(false).decode(img, stream): raw cell bits (Decoder.h:163-168 with _useEcc=false) */
+int cb200_decode_raw(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* raw_out, uint8_t* frame_flags);
+/* == Decoder().decode(img, ofstream): RS-corrected bytes, zeros for failed blocks; returns good bytes per frame in
+   good_bytes[n] (may be NULL) */
+int cb200_decode(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* data_out, uint8_t* block_ok,
+                 uint8_t* frame_flags);
+/* == Decoder().decode_fountain(img, escrow_buffer_writer): per frame, the good chunks packed densely at
+   chunks_out + f * chunks_per_frame * chunk_size, their count in chunk_count[f], bit mask in chunk_mask[f] (may be
+   NULL); good bytes = count * chunk_size == the reference's return value (aligned_stream::tellp) */
+int cb200_decode_fountain(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* chunks_out,
+                          uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
+
+/* ---- single-cell entry points (CimbDecoder API parity; run one tiny kernel) ------------------------------------- */
+
+/* Replaces: CimbDecoder::decode_symbol(const bitmatrix&, drift_offset, best_distance, cooldown)
+   (src/lib/cimb_translator/CimbDecoder.cpp:142-147 -> fuzzy_ahash<8> + get_best_symbol :101-132).
+   windows: n x 10 rows of 10 bits (uint16 each, bit 9 = leftmost column), cooldown[n] (0xFE = ALL, 0xFF = none).
+   out: symbol[n], drift_offset[n], distance[n]. Host pointers. */
+int cb200_decode_symbols(cb200_ctx* ctx, const uint16_t* windows, const uint8_t* cooldown, int n,
+                         uint8_t* symbol, uint8_t* drift_offset, uint8_t* distance);
+/* Replaces: CimbDecoder::get_best_color(r, g, b, color_mode) (CimbDecoder.cpp:168-200) for integer means.
+   rgb: n x 3 bytes; out: color[n]. Host pointers. */
+int cb200_best_colors(cb200_ctx* ctx, const uint8_t* rgb_means, int n, uint8_t* color);
+
+/* ---- synthetic input (benchmark support; the inverse of the path) ---------------------------------------------- */
+
+/* cellvals: n * total_cells bytes on the device, value = (colour << symbol_bits) | symbol of linear cell i
+   (what CimbWriter::write pastes, src/lib/cimb_translator/CimbWriter.cpp:84-95); d_rgb_out: n frames. */
+int cb200_render_frames_dev(cb200_ctx* ctx, const uint8_t* d_cellvals, int n, uint8_t* d_rgb_out);
+
+/* ---- host-side helpers that need no GPU ------------------------------------------------------------------------ */
+
+/* geometry without a context (for sizing buffers before a device exists) */
+int cb200_mode_info(int mode_val, cb200_info* out);
+/* Interleave::interleave_indices (Interleave.h:8-24): slot -> linear cell index; idx has total_cells entries */
+int cb200_interleave_indices(int mode_val, uint16_t* idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CB200_H */

@@ -1,0 +1,181 @@
+"""libcimbar_b200 -- B200 (sm_100a) implementation of libcimbar's per-frame decode hot path.
+
+This Python module is only plumbing around the C ABI of lib/libcb200.so (include/cb200.h): it loads the
+shared library with ctypes and passes raw pointers (numpy host buffers or torch device pointers).  There is
+no Python or CPU decode path here: if the CUDA library is missing or no GPU is present, calls fail loudly."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libcb200.so")
+
+FLAG_NO_FALLBACK = 0x1
+FLAG_SHARPEN = 0x2
+FRAME_FALLBACK = 0x1
+FRAME_INEXACT = 0x2
+
+EXPORTS = [
+    "cb200_last_error", "cb200_version", "cb200_create", "cb200_destroy", "cb200_get_info", "cb200_set_stream",
+    "cb200_sync", "cb200_decode_raw_dev", "cb200_rs_correct_dev", "cb200_decode_chunks_dev", "cb200_decode_raw",
+    "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
+    "cb200_mode_info", "cb200_interleave_indices",
+]
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "mode_val", "image_size_x", "image_size_y", "frame_bytes", "total_cells", "symbol_bits", "color_bits",
+        "raw_bytes", "raw_symbol_bytes", "ecc_bytes", "ecc_block_size", "rs_blocks", "data_bytes", "chunk_size",
+        "chunks_per_frame", "legacy_mode", "max_frames", "sm_count")]
+
+
+class Cb200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libcb200.so (building it is __graft_entry__.build()'s / libcimbar_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Cb200Error(f"{LIB_PATH} is missing: build it with `python -m libcimbar_b200.build` "
+                         "(there is no fallback implementation)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u8p, u32p, u16p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    lib.cb200_last_error.restype = C.c_char_p
+    lib.cb200_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+    lib.cb200_destroy.argtypes = [vp]
+    lib.cb200_get_info.argtypes = [vp, C.POINTER(Info)]
+    lib.cb200_set_stream.argtypes = [vp, vp]
+    lib.cb200_sync.argtypes = [vp]
+    lib.cb200_decode_raw_dev.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u8p]
+    lib.cb200_rs_correct_dev.argtypes = [vp, u8p, C.c_int, u8p, u8p]
+    lib.cb200_decode_chunks_dev.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u32p, u8p]
+    lib.cb200_decode_raw.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u8p]
+    lib.cb200_decode.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u8p, u8p]
+    lib.cb200_decode_fountain.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u32p, u32p, u8p]
+    lib.cb200_decode_symbols.argtypes = [vp, u16p, u8p, C.c_int, u8p, u8p, u8p]
+    lib.cb200_best_colors.argtypes = [vp, u8p, C.c_int, u8p]
+    lib.cb200_render_frames_dev.argtypes = [vp, u8p, C.c_int, u8p]
+    lib.cb200_mode_info.argtypes = [C.c_int, C.POINTER(Info)]
+    lib.cb200_interleave_indices.argtypes = [C.c_int, u16p]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise Cb200Error(f"cb200 error {rc}: {load_library().cb200_last_error().decode()}")
+
+
+def mode_info(mode_val=68):
+    info = Info()
+    _check(load_library().cb200_mode_info(mode_val, C.byref(info)))
+    return info
+
+
+def interleave_indices(mode_val=68):
+    info = mode_info(mode_val)
+    idx = np.zeros(info.total_cells, dtype=np.uint16)
+    _check(load_library().cb200_interleave_indices(mode_val, idx.ctypes.data))
+    return idx
+
+
+def _hptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Context:
+    """One decode context = one GPU + one stream (cb200_create / cb200_destroy)."""
+
+    def __init__(self, mode_val=68, max_frames=64, device=-1):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        _check(self.lib.cb200_create(C.byref(self._h), device, mode_val, max_frames))
+        self.info = Info()
+        _check(self.lib.cb200_get_info(self._h, C.byref(self.info)))
+
+    def close(self):
+        if self._h:
+            self.lib.cb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib.cb200_set_stream(self._h, cuda_stream_ptr))
+
+    def sync(self):
+        _check(self.lib.cb200_sync(self._h))
+
+    # ---- host-pointer entry points (numpy in / numpy out)
+    def _frames(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if rgb.ndim == 3:
+            rgb = rgb[None]
+        n = rgb.shape[0]
+        if rgb.shape[1:] != (self.info.image_size_y, self.info.image_size_x, 3):
+            raise Cb200Error(f"frames must be {self.info.image_size_y}x{self.info.image_size_x}x3 RGB8, got {rgb.shape[1:]}")
+        return rgb, n
+
+    def decode_raw(self, rgb, flags=0):
+        rgb, n = self._frames(rgb)
+        raw = np.zeros((n, self.info.raw_bytes), dtype=np.uint8)
+        ff = np.zeros(n, dtype=np.uint8)
+        _check(self.lib.cb200_decode_raw(self._h, rgb.ctypes.data, n, flags, raw.ctypes.data, ff.ctypes.data))
+        return raw, ff
+
+    def decode(self, rgb, flags=0):
+        rgb, n = self._frames(rgb)
+        data = np.zeros((n, self.info.data_bytes), dtype=np.uint8)
+        ok = np.zeros((n, self.info.rs_blocks), dtype=np.uint8)
+        ff = np.zeros(n, dtype=np.uint8)
+        _check(self.lib.cb200_decode(self._h, rgb.ctypes.data, n, flags, data.ctypes.data, ok.ctypes.data, ff.ctypes.data))
+        return data, ok, ff
+
+    def decode_fountain(self, rgb, flags=0):
+        rgb, n = self._frames(rgb)
+        chunks = np.zeros((n, self.info.chunks_per_frame, self.info.chunk_size), dtype=np.uint8)
+        count = np.zeros(n, dtype=np.uint32)
+        mask = np.zeros(n, dtype=np.uint32)
+        ff = np.zeros(n, dtype=np.uint8)
+        _check(self.lib.cb200_decode_fountain(self._h, rgb.ctypes.data, n, flags, chunks.ctypes.data, count.ctypes.data,
+                                              mask.ctypes.data, ff.ctypes.data))
+        return chunks, count, mask, ff
+
+    def decode_symbols(self, windows, cooldown=None):
+        windows = np.ascontiguousarray(windows, dtype=np.uint16).reshape(-1, 10)
+        n = windows.shape[0]
+        cd = None if cooldown is None else np.ascontiguousarray(cooldown, dtype=np.uint8)
+        sym, off, dist = (np.zeros(n, dtype=np.uint8) for _ in range(3))
+        _check(self.lib.cb200_decode_symbols(self._h, windows.ctypes.data, _hptr(cd), n, sym.ctypes.data, off.ctypes.data, dist.ctypes.data))
+        return sym, off, dist
+
+    def best_colors(self, rgb_means):
+        rgb_means = np.ascontiguousarray(rgb_means, dtype=np.uint8).reshape(-1, 3)
+        out = np.zeros(rgb_means.shape[0], dtype=np.uint8)
+        _check(self.lib.cb200_best_colors(self._h, rgb_means.ctypes.data, rgb_means.shape[0], out.ctypes.data))
+        return out
+
+    # ---- device-pointer entry points (raw device addresses, e.g. torch.Tensor.data_ptr())
+    def decode_raw_dev(self, d_rgb, n, d_raw_out, d_flags=None, flags=0):
+        _check(self.lib.cb200_decode_raw_dev(self._h, d_rgb, n, flags, d_raw_out, d_flags))
+
+    def rs_correct_dev(self, d_raw, n, d_data_out, d_ok=None):
+        _check(self.lib.cb200_rs_correct_dev(self._h, d_raw, n, d_data_out, d_ok))
+
+    def decode_chunks_dev(self, d_rgb, n, d_chunks, d_mask, d_flags=None, flags=0):
+        _check(self.lib.cb200_decode_chunks_dev(self._h, d_rgb, n, flags, d_chunks, d_mask, d_flags))
+
+    def render_frames_dev(self, d_cellvals, n, d_rgb_out):
+        _check(self.lib.cb200_render_frames_dev(self._h, d_cellvals, n, d_rgb_out))

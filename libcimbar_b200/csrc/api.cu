@@ -1,0 +1,479 @@
+// api.cu -- the C ABI of libcb200.so (include/cb200.h): context, tables, and the kernel pipelines.
+// There is no CPU decode path in this library: every entry point that produces decode results launches the
+// sm_100a kernels, and cb200_create fails with CB200_ERR_NODEVICE when no CUDA device is usable.
+#include "../../include/cb200.h"
+#include "cb200_common.cuh"
+#include "k1_decode.cuh"
+#include "k1x_flood.cuh"
+#include "k2_rs.cuh"
+#include "render.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace cb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail_cuda(cudaError_t e, const char* what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return CB200_ERR_CUDA;
+}
+#define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, what); } while (0)
+
+// tile dictionary = CimbDecoder::_tileHashes for symbol_bits=4, dark (src/lib/cimb_translator/CimbDecoder.cpp:87-99),
+// i.e. average_hash of bitmap/4/00..0f.png; values pinned by src/lib/image_hash/test/averageHashTest.cpp:43-50.
+const unsigned long long kTilesH[16] = {
+    0xfffefcf8f0e0c080ULL, 0x80c0e0f0f8fcfeffULL, 0xff7f3f1f0f070301ULL, 0x0103070f1f3f7fffULL,
+    0x181818ffff181818ULL, 0x66e7e70000e7e766ULL, 0x3c7ee7c3c3e77e3cULL, 0x18183c3c7e7effffULL,
+    0xc0f0fcfffffcf0c0ULL, 0xfffcf00000f0fcffULL, 0xff3f0f00000f3fffULL, 0xe7e7e7e7c3c38181ULL,
+    0x8181c3c3e7e7e7e7ULL, 0x0000c3e77e3c1800ULL, 0x0c1c387070381c0cULL, 0x1e1e38381c1c7878ULL,
+};
+
+unsigned long long brev64(unsigned long long x)
+{
+    unsigned long long r = 0;
+    for (int i = 0; i < 64; ++i) if (x & (1ULL << i)) r |= 1ULL << (63 - i);
+    return r;
+}
+
+// palettes: getColor4 / getColor8 (color_mode 1) and getColor4_old / getColor8_old (color_mode 0),
+// src/lib/cimb_translator/Common.cpp:21-85, selection :122-139
+void fill_palette(int num_colors, int color_mode, uint8_t out[8][4])
+{
+    uint8_t pal[2][8][3];
+    static const uint8_t c4[4][3] = {{0, 255, 0}, {0, 255, 255}, {255, 255, 0}, {255, 0, 255}};
+    static const uint8_t c4old[4][3] = {{0, 255, 255}, {255, 255, 0}, {255, 0, 255}, {0, 255, 0}};
+    static const uint8_t c8[8][3] = {{0, 255, 255}, {255, 255, 0}, {0x7F, 0x7F, 255}, {255, 255, 255}, {0, 255, 0}, {255, 0x9F, 0}, {255, 0, 255}, {255, 65, 65}};
+    static const uint8_t c8old[8][3] = {{0, 255, 255}, {0x7F, 0x7F, 255}, {255, 0, 255}, {255, 65, 65}, {255, 0x9F, 0}, {255, 255, 0}, {255, 255, 255}, {0, 255, 0}};
+    memset(pal, 0, 48);
+    for (int i = 0; i < 8; ++i)
+        for (int k = 0; k < 3; ++k) {
+            pal[0][i][k] = (num_colors <= 4) ? c4old[i & 3][k] : c8old[i][k];
+            pal[1][i][k] = (num_colors <= 4) ? c4[i & 3][k] : c8[i][k];
+        }
+    for (int i = 0; i < 8; ++i) { for (int k = 0; k < 3; ++k) out[i][k] = pal[color_mode ? 1 : 0][i][k]; out[i][3] = 0; }
+}
+
+// cimbar::conf table: src/lib/cimb_translator/GridConf.h:121-189, Config.h:20-43
+bool mode_init(Mode& m, int mode_val)
+{
+    memset(&m, 0, sizeof(m));
+    m.mode_val = mode_val;
+    m.color_bits = 2; m.symbol_bits = 4; m.ecc_bytes = 30; m.ecc_block = 155;
+    m.width = 1024; m.height = 1024; m.cell_offset = 8; m.cells_x = 112; m.cells_y = 112;
+    int chunks_scalar = 2;
+    switch (mode_val) {
+    case 68: break;
+    case 4: m.legacy = 1; chunks_scalar = -10; break;
+    case 8: m.color_bits = 3; m.legacy = 1; chunks_scalar = -10; break;
+    case 66: m.ecc_bytes = 33; m.ecc_block = 168; m.width = 736; m.height = 637; m.cell_offset = 9; m.cells_x = 80; m.cells_y = 69; chunks_scalar = 1; break;
+    case 67: m.ecc_bytes = 36; m.ecc_block = 179; m.width = 1024; m.height = 720; m.cell_offset = 9; m.cells_x = 112; m.cells_y = 78; chunks_scalar = 2; break;
+    default: return false;
+    }
+    m.corner = (int)lrint(54.0 / kSpacing);                                   // GridConf.h:32-40
+    m.color_mode = m.legacy ? 0 : 1;                                            // Config.h:61-64
+    m.num_cells = m.cells_x * m.cells_y - 4 * m.corner * m.corner;              // GridConf.h:42-45
+    int bpc = m.color_bits + m.symbol_bits;
+    m.cap_all = m.num_cells * bpc / 8;                                          // GridConf.h:47-52
+    m.cap_sym = m.legacy ? m.cap_all : m.num_cells * m.symbol_bits / 8;
+    m.cap_col = m.legacy ? 0 : m.num_cells * m.color_bits / 8;
+    m.msg_len = m.ecc_block - m.ecc_bytes;
+    m.nblocks = m.cap_all / m.ecc_block;
+    m.nblocks_sym = m.cap_sym / m.ecc_block;
+    m.chunks_per_frame = chunks_scalar < 0 ? -chunks_scalar : bpc * chunks_scalar;   // GridConf.h:54-61
+    m.chunk_size = m.cap_all * m.msg_len / m.ecc_block / m.chunks_per_frame;    // GridConf.h:63-72
+    m.blocks_per_chunk = m.chunk_size / m.msg_len;
+    m.data_bytes = m.nblocks * m.msg_len;
+    m.top_cells = (m.cells_x - 2 * m.corner) * m.corner;
+    m.mid_cells = m.cells_x * (m.cells_y - 2 * m.corner);
+    // layout invariants the kernels rely on (true for every 8x8 mode in GridConf.h)
+    if (m.cap_sym % m.ecc_block || m.cap_all % m.ecc_block || m.chunk_size % m.msg_len || m.width % 8 || (m.width * 3) % 16) return false;
+    if (m.nblocks * m.msg_len != m.chunks_per_frame * m.chunk_size) return false;
+    // perfect hash over the little-endian tile words: slot = (L_lo * mul) >> 28 distinct for the 16 tiles
+    uint32_t x = 0x2545F491u;
+    m.hash_mul = 0;
+    for (int trial = 0; trial < 50000000 && !m.hash_mul; ++trial) {
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        uint32_t mul = x | 1u, seen = 0;
+        bool ok = true;
+        for (int t = 0; t < 16 && ok; ++t) {
+            uint32_t slot = ((uint32_t)brev64(kTilesH[t]) * mul) >> 28;
+            if (seen & (1u << slot)) ok = false;
+            seen |= 1u << slot;
+        }
+        if (ok) m.hash_mul = mul;
+    }
+    fill_palette(1 << m.color_bits, m.color_mode, m.palette);
+    return m.hash_mul != 0;
+}
+
+void fill_info(const Mode& m, int max_frames, int sm_count, cb200_info* o)
+{
+    o->mode_val = m.mode_val; o->image_size_x = m.width; o->image_size_y = m.height; o->frame_bytes = m.width * m.height * 3;
+    o->total_cells = m.num_cells; o->symbol_bits = m.symbol_bits; o->color_bits = m.color_bits;
+    o->raw_bytes = m.cap_all; o->raw_symbol_bytes = m.cap_sym; o->ecc_bytes = m.ecc_bytes; o->ecc_block_size = m.ecc_block;
+    o->rs_blocks = m.nblocks; o->data_bytes = m.data_bytes; o->chunk_size = m.chunk_size; o->chunks_per_frame = m.chunks_per_frame;
+    o->legacy_mode = m.legacy; o->max_frames = max_frames; o->sm_count = sm_count;
+}
+
+// Interleave::interleave_indices (src/lib/cimb_translator/Interleave.h:8-24)
+void interleave_indices(const Mode& m, std::vector<uint16_t>& idx)
+{
+    unsigned size = (unsigned)m.num_cells, chunks = (unsigned)m.ecc_block, partitions = 2;
+    idx.clear();
+    unsigned psize = size / partitions;
+    for (unsigned part = 0; part < size; part += psize)
+        for (unsigned c = 0; c < chunks; ++c)
+            for (unsigned i = c; i < psize; i += chunks)
+                idx.push_back((uint16_t)(i + part));
+}
+
+}  // namespace
+
+struct cb200_ctx {
+    Mode mode;
+    int device = 0, max_frames = 0, sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device workspaces
+    uint8_t* d_rgb = nullptr;        // host-pointer entry points only: max_frames frames
+    uint8_t* d_cellvals = nullptr;   // max_frames * num_cells
+    uint32_t* d_dirty = nullptr;     // max_frames
+    uint8_t* d_raw = nullptr;        // max_frames * cap_all
+    uint8_t* d_data = nullptr;       // max_frames * data_bytes
+    uint8_t* d_ok = nullptr;         // max_frames * nblocks
+    uint32_t* d_mask = nullptr;      // max_frames
+    uint8_t* d_flags = nullptr;      // max_frames
+    uint16_t* d_idx = nullptr;       // num_cells
+    FloodWorkspace flood;            // exact-walk fallback scratch
+    // small scratch for the single-cell entry points
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    // pinned host staging for results of the host-pointer entry points
+    uint8_t* h_pinned = nullptr; size_t h_pinned_bytes = 0;
+};
+
+namespace {
+
+int ensure_scratch(cb200_ctx* c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return CB200_OK;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr; c->scratch_bytes = 0;
+    CK(cudaMalloc(&c->d_scratch, bytes), "cudaMalloc scratch");
+    c->scratch_bytes = bytes;
+    return CB200_OK;
+}
+
+int check_n(const cb200_ctx* c, int n)
+{
+    if (!c) return fail(CB200_ERR_ARG, "null context");
+    if (n < 0 || n > c->max_frames) return fail(CB200_ERR_ARG, "n exceeds the context's max_frames");
+    return CB200_OK;
+}
+
+// K1 (+ exact-walk fallback) : frames -> per-cell bytes in ctx->d_cellvals, per-frame flags in ctx->d_flags
+int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
+{
+    const Mode& m = c->mode;
+    cudaStream_t st = c->stream;
+    const bool sharpen = (flags & CB200_FLAG_SHARPEN) != 0;
+    CK(cudaMemsetAsync(c->d_dirty, 0, sizeof(uint32_t) * (size_t)n, st), "memset dirty");
+    if (!sharpen) {
+        // bands: whole frames when there are enough of them to fill the machine, else split frames into bands of cell rows
+        int ctas = c->sm_count * 3;
+        int bands = 1;
+        if (n < ctas) { bands = (ctas + n - 1) / n; if (bands > m.cells_y / 4) bands = m.cells_y / 4; if (bands < 1) bands = 1; }
+        int units = n * bands;
+        int grid = units < ctas ? units : ctas;
+        CK(k1_launch(m, d_rgb, n, bands, grid, c->d_cellvals, c->d_dirty, st), "k1 launch");
+    }
+    // the sharpen preprocessing (needs_sharpen, CimbReader.cpp:37-40) is only implemented in the exact-walk kernel
+    CK(flood_launch(m, c->flood, d_rgb, n, (flags & CB200_FLAG_NO_FALLBACK) != 0, sharpen, sharpen,
+                    c->d_cellvals, c->d_dirty, c->d_flags, st), "flood launch");
+    return CB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cb200_last_error(void) { return g_err.c_str(); }
+int cb200_version(void) { return 1; }
+
+int cb200_mode_info(int mode_val, cb200_info* out)
+{
+    if (!out) return fail(CB200_ERR_ARG, "null out");
+    Mode m;
+    if (!mode_init(m, mode_val)) return fail(CB200_ERR_MODE, "unsupported mode_val");
+    fill_info(m, 0, 0, out);
+    return CB200_OK;
+}
+
+int cb200_interleave_indices(int mode_val, uint16_t* idx)
+{
+    if (!idx) return fail(CB200_ERR_ARG, "null idx");
+    Mode m;
+    if (!mode_init(m, mode_val)) return fail(CB200_ERR_MODE, "unsupported mode_val");
+    std::vector<uint16_t> v;
+    interleave_indices(m, v);
+    memcpy(idx, v.data(), v.size() * sizeof(uint16_t));
+    return CB200_OK;
+}
+
+int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
+{
+    if (!out || max_frames < 1) return fail(CB200_ERR_ARG, "bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CB200_ERR_NODEVICE, "no CUDA device: libcb200 has no CPU fallback");
+    if (device < 0) { CK(cudaGetDevice(&device), "cudaGetDevice"); }
+    if (device >= ndev) return fail(CB200_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device), "cudaSetDevice");
+    cb200_ctx* c = new cb200_ctx();
+    if (!mode_init(c->mode, mode_val)) { delete c; return fail(CB200_ERR_MODE, "unsupported mode_val"); }
+    const Mode& m = c->mode;
+    c->device = device; c->max_frames = max_frames;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major < 10) { delete c; return fail(CB200_ERR_NODEVICE, "libcb200 is built for sm_100a only"); }
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    c->stream = c->own_stream;
+
+    // ---- tables
+    float adjust[256];
+    adjust[0] = 0.0f;
+    for (int d = 1; d < 256; ++d) adjust[d] = (float)(255.0 / (double)(float)d);   // CimbDecoder.cpp:185
+    unsigned long long tilesL[16];
+    for (int t = 0; t < 16; ++t) tilesL[t] = brev64(kTilesH[t]);
+    CK(k1_init_tables(adjust, tilesL), "k1 tables");
+    CK(render_init_tables(kTilesH), "render tables");
+    uint8_t gexp[512], glog[256];
+    {   // GF(2^8), primitive polynomial 0x187 (ReedSolomon.h:26; libcorrect field.h:26-62)
+        unsigned el = 1; gexp[0] = 1; glog[0] = 0;
+        for (unsigned i = 1; i < 512; ++i) {
+            el *= 2; if (el > 255) el ^= 0x187u;
+            gexp[i] = (uint8_t)el;
+            if (i < 256) glog[el] = (uint8_t)i;
+        }
+    }
+    CK(k2_init_tables(gexp, glog), "k2 tables");
+    CK(flood_init_tables(adjust, tilesL), "flood tables");
+
+    // ---- workspaces
+    size_t n = (size_t)max_frames;
+    CK(cudaMalloc(&c->d_cellvals, n * m.num_cells), "cudaMalloc cellvals");
+    CK(cudaMalloc(&c->d_dirty, n * sizeof(uint32_t)), "cudaMalloc dirty");
+    CK(cudaMalloc(&c->d_raw, n * m.cap_all), "cudaMalloc raw");
+    CK(cudaMalloc(&c->d_data, n * m.data_bytes), "cudaMalloc data");
+    CK(cudaMalloc(&c->d_ok, n * m.nblocks), "cudaMalloc ok");
+    CK(cudaMalloc(&c->d_mask, n * sizeof(uint32_t)), "cudaMalloc mask");
+    CK(cudaMalloc(&c->d_flags, n), "cudaMalloc flags");
+    std::vector<uint16_t> idx;
+    interleave_indices(m, idx);
+    CK(cudaMalloc(&c->d_idx, idx.size() * sizeof(uint16_t)), "cudaMalloc idx");
+    CK(cudaMemcpy(c->d_idx, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "upload idx");
+    CK(flood_workspace_create(m, c->sm_count, &c->flood), "flood workspace");
+    *out = c;
+    return CB200_OK;
+}
+
+int cb200_destroy(cb200_ctx* c)
+{
+    if (!c) return CB200_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_rgb); cudaFree(c->d_cellvals); cudaFree(c->d_dirty); cudaFree(c->d_raw); cudaFree(c->d_data);
+    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_scratch);
+    flood_workspace_destroy(&c->flood);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return CB200_OK;
+}
+
+int cb200_get_info(const cb200_ctx* c, cb200_info* out)
+{
+    if (!c || !out) return fail(CB200_ERR_ARG, "null argument");
+    fill_info(c->mode, c->max_frames, c->sm_count, out);
+    return CB200_OK;
+}
+
+int cb200_set_stream(cb200_ctx* c, void* cuda_stream)
+{
+    if (!c) return fail(CB200_ERR_ARG, "null context");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return CB200_OK;
+}
+
+int cb200_sync(cb200_ctx* c)
+{
+    if (!c) return fail(CB200_ERR_ARG, "null context");
+    CK(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+    return CB200_OK;
+}
+
+int cb200_decode_raw_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, uint8_t* d_raw_out, uint8_t* d_frame_flags)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!d_rgb || !d_raw_out) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
+    CK(k2_pack_launch(c->mode, c->d_cellvals, c->d_idx, n, d_raw_out, c->stream), "pack launch");
+    if (d_frame_flags) CK(cudaMemcpyAsync(d_frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToDevice, c->stream), "copy flags");
+    return CB200_OK;
+}
+
+int cb200_rs_correct_dev(cb200_ctx* c, const uint8_t* d_raw, int n, uint8_t* d_data_out, uint8_t* d_block_ok)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!d_raw || !d_data_out) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    uint8_t* ok = d_block_ok ? d_block_ok : c->d_ok;
+    CK(k2_rs_launch(c->mode, d_raw, n, d_data_out, ok, c->sm_count * 16, c->stream), "rs launch");
+    return CB200_OK;
+}
+
+int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, uint8_t* d_chunks, uint32_t* d_chunk_mask, uint8_t* d_frame_flags)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!d_rgb || !d_chunks || !d_chunk_mask) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
+    CK(k2_pack_launch(c->mode, c->d_cellvals, c->d_idx, n, c->d_raw, c->stream), "pack launch");
+    CK(k2_rs_launch(c->mode, c->d_raw, n, d_chunks, c->d_ok, c->sm_count * 16, c->stream), "rs launch");
+    CK(k2_mask_launch(c->mode, c->d_ok, n, d_chunk_mask, c->stream), "mask launch");
+    if (d_frame_flags) CK(cudaMemcpyAsync(d_frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToDevice, c->stream), "copy flags");
+    return CB200_OK;
+}
+
+// ---- host-pointer entry points
+static int upload_frames(cb200_ctx* c, const uint8_t* rgb, int n)
+{
+    const Mode& m = c->mode;
+    size_t fb = (size_t)m.width * m.height * 3;
+    if (!c->d_rgb) CK(cudaMalloc(&c->d_rgb, fb * (size_t)c->max_frames), "cudaMalloc rgb staging");
+    CK(cudaMemcpyAsync(c->d_rgb, rgb, fb * (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D frames");
+    return CB200_OK;
+}
+
+int cb200_decode_raw(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* raw_out, uint8_t* frame_flags)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!rgb || !raw_out) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    rc = upload_frames(c, rgb, n); if (rc) return rc;
+    rc = cb200_decode_raw_dev(c, c->d_rgb, n, flags, c->d_raw, nullptr); if (rc) return rc;
+    CK(cudaMemcpyAsync(raw_out, c->d_raw, (size_t)n * c->mode.cap_all, cudaMemcpyDeviceToHost, c->stream), "D2H raw");
+    if (frame_flags) CK(cudaMemcpyAsync(frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H flags");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    return CB200_OK;
+}
+
+int cb200_decode(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* data_out, uint8_t* block_ok, uint8_t* frame_flags)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!rgb || !data_out) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    rc = upload_frames(c, rgb, n); if (rc) return rc;
+    rc = cb200_decode_chunks_dev(c, c->d_rgb, n, flags, c->d_data, c->d_mask, nullptr); if (rc) return rc;
+    CK(cudaMemcpyAsync(data_out, c->d_data, (size_t)n * c->mode.data_bytes, cudaMemcpyDeviceToHost, c->stream), "D2H data");
+    if (block_ok) CK(cudaMemcpyAsync(block_ok, c->d_ok, (size_t)n * c->mode.nblocks, cudaMemcpyDeviceToHost, c->stream), "D2H ok");
+    if (frame_flags) CK(cudaMemcpyAsync(frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H flags");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    return CB200_OK;
+}
+
+int cb200_decode_fountain(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* chunks_out, uint32_t* chunk_count,
+                          uint32_t* chunk_mask, uint8_t* frame_flags)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!rgb || !chunks_out || !chunk_count) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    const Mode& m = c->mode;
+    rc = upload_frames(c, rgb, n); if (rc) return rc;
+    rc = cb200_decode_chunks_dev(c, c->d_rgb, n, flags, c->d_data, c->d_mask, nullptr); if (rc) return rc;
+    size_t need = (size_t)n * m.data_bytes + (size_t)n * sizeof(uint32_t);
+    if (c->h_pinned_bytes < need) {
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        c->h_pinned = nullptr; c->h_pinned_bytes = 0;
+        CK(cudaMallocHost(&c->h_pinned, need), "cudaMallocHost");
+        c->h_pinned_bytes = need;
+    }
+    uint32_t* h_mask = reinterpret_cast<uint32_t*>(c->h_pinned);
+    uint8_t* h_data = c->h_pinned + (size_t)n * sizeof(uint32_t);
+    CK(cudaMemcpyAsync(h_data, c->d_data, (size_t)n * m.data_bytes, cudaMemcpyDeviceToHost, c->stream), "D2H chunks");
+    CK(cudaMemcpyAsync(h_mask, c->d_mask, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream), "D2H mask");
+    if (frame_flags) CK(cudaMemcpyAsync(frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H flags");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    // escrow_buffer_writer order: good chunks appended densely (src/lib/encoder/escrow_buffer_writer.h:44-60)
+    for (int f = 0; f < n; ++f) {
+        uint8_t* dst = chunks_out + (size_t)f * m.data_bytes;
+        const uint8_t* src = h_data + (size_t)f * m.data_bytes;
+        uint32_t cnt = 0;
+        for (int q = 0; q < m.chunks_per_frame; ++q)
+            if (h_mask[f] & (1u << q)) { memcpy(dst + (size_t)cnt * m.chunk_size, src + (size_t)q * m.chunk_size, (size_t)m.chunk_size); ++cnt; }
+        chunk_count[f] = cnt;
+        if (chunk_mask) chunk_mask[f] = h_mask[f];
+    }
+    return CB200_OK;
+}
+
+int cb200_decode_symbols(cb200_ctx* c, const uint16_t* windows, const uint8_t* cooldown, int n, uint8_t* symbol, uint8_t* drift_offset, uint8_t* distance)
+{
+    if (!c || !windows || !symbol || !drift_offset || !distance || n < 0) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    size_t wb = (size_t)n * 10 * sizeof(uint16_t);
+    int rc = ensure_scratch(c, wb + 4 * (size_t)n + 64); if (rc) return rc;
+    uint8_t* base = static_cast<uint8_t*>(c->d_scratch);
+    uint16_t* d_win = reinterpret_cast<uint16_t*>(base);
+    uint8_t* d_cd = base + wb; uint8_t* d_sym = d_cd + n; uint8_t* d_off = d_sym + n; uint8_t* d_dist = d_off + n;
+    CK(cudaMemcpyAsync(d_win, windows, wb, cudaMemcpyHostToDevice, c->stream), "H2D windows");
+    if (cooldown) CK(cudaMemcpyAsync(d_cd, cooldown, (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D cooldown");
+    CK(k1_symbols_launch(d_win, cooldown ? d_cd : nullptr, n, d_sym, d_off, d_dist, c->stream), "symbols launch");
+    CK(cudaMemcpyAsync(symbol, d_sym, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H");
+    CK(cudaMemcpyAsync(drift_offset, d_off, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H");
+    CK(cudaMemcpyAsync(distance, d_dist, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    return CB200_OK;
+}
+
+int cb200_best_colors(cb200_ctx* c, const uint8_t* rgb_means, int n, uint8_t* color)
+{
+    if (!c || !rgb_means || !color || n < 0) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    int rc = ensure_scratch(c, 4 * (size_t)n + 64); if (rc) return rc;
+    uint8_t* d_in = static_cast<uint8_t*>(c->d_scratch); uint8_t* d_out = d_in + 3 * (size_t)n;
+    CK(cudaMemcpyAsync(d_in, rgb_means, 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D");
+    CK(k1_colors_launch(c->mode, d_in, n, d_out, c->stream), "colors launch");
+    CK(cudaMemcpyAsync(color, d_out, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    return CB200_OK;
+}
+
+int cb200_render_frames_dev(cb200_ctx* c, const uint8_t* d_cellvals, int n, uint8_t* d_rgb_out)
+{
+    if (!c || !d_cellvals || !d_rgb_out || n < 0) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(render_launch(c->mode, d_cellvals, n, d_rgb_out, c->stream), "render launch");
+    return CB200_OK;
+}
+
+}  // extern "C"

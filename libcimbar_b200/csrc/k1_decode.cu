@@ -1,0 +1,436 @@
+// k1_decode.cu -- K1: fused preprocess + average-hash + colour kernel for clean (drift-0) frames, sm_100a.
+//
+// Replaces, for one RGB8 frame resident in HBM (reference file:line relative to /root/reference/):
+//   P1  preprocessSymbolGrid            src/lib/cimb_translator/CimbReader.cpp:30-46  (cvtColor + adaptiveThreshold(5, C=0))
+//   P5  fuzzy_ahash<8>(bitmatrix)       src/lib/image_hash/average_hash.h:63-75, ahash_result.h:70-106
+//   P6  CimbDecoder::get_best_symbol    src/lib/cimb_translator/CimbDecoder.cpp:101-132
+//   P8  Cell::mean_rgb_continuous       src/lib/cimb_translator/Cell.h:30-62 (inner 6x6, CimbDecoder.cpp:202-209)
+//   P9  CimbDecoder::get_best_color     src/lib/cimb_translator/CimbDecoder.cpp:168-200
+// for every cell at drift (0,0).  The reference walks cells serially in heap order and lets drift propagate
+// (FloodDecodePositions.cpp:49-134); that walk provably degenerates to this embarrassingly parallel pass when the
+// centre hash wins for every cell.  A cell where it does not sets bit 7 of its result
+// byte and the frame's dirty flag; such frames are re-done by the exact flood-walk kernel (k1x_flood.cu).
+//
+// Data flow per CTA (128 consumer threads + 1 TMA producer warp, 3 CTAs/SM):
+//   HBM --cp.async.bulk (TMA, 9 full-width rows = 27 KB per stage, 2 stages, mbarrier full/empty)--> smem
+//   phase A: 8 px/thread: gray = (19596R+38470G+7470B+32768)>>16 via 2x IDP.2A per px, packed 2x16 bit
+//   phase B: separable 5x5 box sum in packed-16 SIMD (5 IADD3 + 4 PRMT per 8 px), rolling vertical sum in
+//            registers, threshold 25*g > sum+12 as ONE IMAD per pixel pair, 1-bit raster row -> smem
+//   phase C: one thread per cell: 8x8 hash by funnel shifts from the raster, perfect-hash exact match against
+//            the 16-tile dictionary (full 5/9-way popcount search only when inexact), 6x6 RGB mean via IDP.4A
+//            from the staged raw rows, colour classification, one result byte per cell -> HBM
+// Every HBM byte of the frame is read exactly once (plus 4 warm-up rows per band).
+#include "cb200_common.cuh"
+#include "k1_decode.cuh"
+
+namespace cb200 {
+
+constexpr int kConsumers = 128;
+constexpr int kK1Threads = 160;
+constexpr int kStageRows = 9;
+constexpr int kMaxW = 1024;
+constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
+constexpr int kRastWords = kRastPitch / 4;
+
+struct __align__(128) K1Smem {
+    uint8_t stage[2][kStageRows * kMaxW * 3];
+    uint32_t edgeL[kStageRows][kConsumers];   // (g0,g1) of each thread's 8-px run
+    uint32_t edgeR[kStageRows][kConsumers];   // (g6,g7)
+    uint32_t raster[10][kRastWords];
+    uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
+    uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
+    float adjust[256];                        // copy of c_adjust: indexed per lane, so not read through the constant cache
+    unsigned long long full_bar[2];
+    unsigned long long empty_bar[2];
+};
+
+__constant__ float c_adjust[256];             // (float)(255.0 / (double)d), d = max-min (CimbDecoder.cpp:185)
+__constant__ unsigned long long c_tiles_L[16]; // tile dictionary, bit (8r+c) = pixel(r,c)  (bit-reversed reference hash)
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync()   // named barrier: the 128 consumer threads only
+{
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- colour
+// P9 get_best_color with integer inputs (no CCM): float32 arithmetic restated op for op (CimbDecoder.cpp:168-200)
+__device__ __forceinline__ uint32_t fix_single_color(float c, float adjust, float down)
+{
+    c = __fsub_rn(c, down);
+    c = __fmul_rn(c, adjust);
+    if (c > __fsub_rn(245.0f, down)) c = 255.0f;
+    if (c < 0.0f) c = 0.0f;
+    return __float2uint_rz(c);   // (uchar)c
+}
+
+__device__ __forceinline__ uint32_t best_color(const float* adjust_tab, const Mode& m, uint32_t ri, uint32_t gi, uint32_t bi, int num_colors)
+{
+    float r = (float)ri, g = (float)gi, b = (float)bi;
+    float mx = fmaxf(fmaxf(r, g), fmaxf(b, 1.0f));
+    float mn = fminf(fminf(r, g), fminf(b, 48.0f));
+    if (mn >= mx) mn = 0.0f;
+    float adjust = adjust_tab[(int)(mx - mn)];
+    int cr = (int)fix_single_color(r, adjust, mn);
+    int cg = (int)fix_single_color(g, adjust, mn);
+    int cb = (int)fix_single_color(b, adjust, mn);
+    int a0 = cr - cg, a1 = cg - cb, a2 = cb - cr;
+    uint32_t best = 0, best_d = 0x7fffffffu;   // reference: float 1000000 > any reachable distance (<= 780300)
+    for (int i = 0; i < num_colors; ++i) {
+        int pr = m.palette[i][0], pg = m.palette[i][1], pb = m.palette[i][2];
+        int d0 = a0 - (pr - pg), d1 = a1 - (pg - pb), d2 = a2 - (pb - pr);
+        uint32_t d = (uint32_t)(d0 * d0 + d1 * d1 + d2 * d2);
+        if (d < best_d) { best_d = d; best = (uint32_t)i; }
+    }
+    return best;
+}
+
+// sum of R,G,B over 6 consecutive pixels starting at pixel x of one staged raw row (P8, one row of the 6x6)
+__device__ __forceinline__ void rgb_row6(const uint8_t* row, int x, uint32_t& R, uint32_t& G, uint32_t& B)
+{
+    uint32_t bo = 3u * (uint32_t)x;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + (bo >> 2);
+    uint32_t sh = (bo & 3u) * 8u;
+    uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5];
+    // realign so that a0 starts at the first pixel's R byte
+    uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+    uint32_t a3 = __funnelshift_r(w3, w4, sh), a4 = __funnelshift_r(w4, w5, sh);
+    // a0 = R0 G0 B0 R1 | a1 = G1 B1 R2 G2 | a2 = B2 R3 G3 B3 | a3 = R4 G4 B4 R5 | a4 = G5 B5 x x
+    R = __dp4a(a0, 0x01000001u, R); R = __dp4a(a1, 0x00010000u, R); R = __dp4a(a2, 0x00000100u, R); R = __dp4a(a3, 0x01000001u, R);
+    G = __dp4a(a0, 0x00000100u, G); G = __dp4a(a1, 0x01000001u, G); G = __dp4a(a2, 0x00010000u, G); G = __dp4a(a3, 0x00000100u, G);
+    G = __dp4a(a4, 0x00000001u, G);
+    B = __dp4a(a0, 0x00010000u, B); B = __dp4a(a1, 0x00000100u, B); B = __dp4a(a2, 0x01000001u, B); B = __dp4a(a3, 0x00010000u, B);
+    B = __dp4a(a4, 0x00000100u, B);
+}
+
+// ---------------------------------------------------------------------------------------------- symbols
+// 32 raster bits starting at pixel `o` of window row `r`
+__device__ __forceinline__ uint32_t raster_bits(const K1Smem& s, int r, uint32_t o)
+{
+    uint32_t idx = o >> 5;
+    return __funnelshift_r(s.raster[r][idx], s.raster[r][idx + 1], o & 31u);
+}
+
+// full P5+P6 search at drift 0: FAST = ids {4,5,7,3,1}, ALL adds {8,0,2,6} (ahash_result.h:26), tiles 0..15,
+// strict '<' keeps the first minimum (the early return on distance 0 cannot change the result).
+__device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t o, bool all, uint32_t& drift_offset, uint32_t& dist_out)
+{
+    uint32_t win[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) win[r] = raster_bits(s, r, o) & 0x3FFu;
+    const int order[9] = {4, 5, 7, 3, 1, 8, 0, 2, 6};
+    uint32_t best = 1000, best_sym = 0, best_id = 0;
+    int n = all ? 9 : 5;
+    for (int q = 0; q < n; ++q) {
+        int id = order[q];
+        int r0 = id / 3, c0 = id % 3;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lo |= ((win[r0 + k] >> c0) & 0xFFu) << (8 * k);
+            hi |= ((win[r0 + 4 + k] >> c0) & 0xFFu) << (8 * k);
+        }
+        for (int t = 0; t < 16; ++t) {
+            uint2 tl = s.tiles_by_sym[t];
+            uint32_t d = __popc(lo ^ tl.x) + __popc(hi ^ tl.y);
+            if (d < best) { best = d; best_sym = (uint32_t)t; best_id = (uint32_t)id; }
+        }
+    }
+    drift_offset = best_id;
+    dist_out = best;
+    return best_sym;
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kK1Threads, 3)
+k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands,
+                 uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int W = m.width;
+    const uint32_t row_bytes = (uint32_t)W * 3u;
+    const uint32_t stage_bytes = row_bytes * kStageRows;
+    const size_t frame_bytes = (size_t)row_bytes * (size_t)m.height;
+    const int n_units = n_frames * bands;
+
+    if (tid == 0) {
+        mbar_init(&s.full_bar[0], 1); mbar_init(&s.full_bar[1], 1);
+        mbar_init(&s.empty_bar[0], 4); mbar_init(&s.empty_bar[1], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 16) {
+        unsigned long long L = c_tiles_L[tid];
+        uint32_t lo = (uint32_t)L, hi = (uint32_t)(L >> 32);
+        s.tiles_by_sym[tid] = make_uint2(lo, hi);
+        s.tiles_by_slot[(lo * m.hash_mul) >> 28] = make_uint4(lo, hi, (uint32_t)tid, 0u);
+    }
+    for (int i = tid; i < 256; i += kK1Threads) s.adjust[i] = c_adjust[i];
+    __syncthreads();
+
+    // ------------------------------------------------------------------ producer warp: TMA bulk loads
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int f = u / bands, b = u - f * bands;
+                int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
+                const uint8_t* frame = rgb + (size_t)f * frame_bytes;
+                for (int k = k0 - 1; k < k1; ++k, ++it) {
+                    uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+                    mbar_wait(&s.empty_bar[buf], ph ^ 1u);
+                    int row0 = m.cell_offset + kSpacing * k + 2;          // rows [y_k+2, y_k+10]
+                    mbar_expect_tx(&s.full_bar[buf], stage_bytes);
+                    tma_bulk_g2s(s.stage[buf], frame + (size_t)row0 * row_bytes, stage_bytes, &s.full_bar[buf]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------------------------------------------ consumers
+    const int t = tid;                          // owns pixels 8t .. 8t+7 of every row
+    const bool px_active = (8 * t) < W;
+    const int tl = (t + kConsumers - 1) & (kConsumers - 1), tr = (t + 1) & (kConsumers - 1);
+    const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
+    const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
+    const int num_colors = 1 << m.color_bits;
+
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int f = u / bands, b = u - f * bands;
+        int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
+        uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells;
+
+        uint32_t hprev[5][4], Pprev[2][4], nV[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nV[j] = kBias;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) hprev[i][j] = 0;
+            Pprev[0][j] = Pprev[1][j] = 0;
+        }
+        uint32_t carryR = 0, carryG = 0, carryB = 0;   // colour sums of row y+1 of the upcoming cell row
+        bool any_dirty = false;
+
+        for (int k = k0 - 1; k < k1; ++k, ++it) {
+            const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+            const uint8_t* sb = s.stage[buf];
+            mbar_wait(&s.full_bar[buf], ph);
+
+            // ---------------- phase A: gray, packed pairs P[r][j] = (g[j], g[j+4])
+            uint32_t P[kStageRows][4];
+            if (px_active) {
+#pragma unroll
+                for (int r = 0; r < kStageRows; ++r) {
+                    const uint2* rp = reinterpret_cast<const uint2*>(sb + (uint32_t)r * row_bytes) + 3 * t;
+                    uint2 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+                    uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
+                    n0 = __dp2a_lo(cRG, q0.x, 32768u); n0 = __dp2a_hi(cB0, q0.x, n0);
+                    n1 = __dp2a_hi(c0R, q0.x, 32768u); n1 = __dp2a_lo(cGB, q0.y, n1);
+                    n2 = __dp2a_hi(cRG, q0.y, 32768u); n2 = __dp2a_lo(cB0, q1.x, n2);
+                    n3 = __dp2a_lo(c0R, q1.x, 32768u); n3 = __dp2a_hi(cGB, q1.x, n3);
+                    n4 = __dp2a_lo(cRG, q1.y, 32768u); n4 = __dp2a_hi(cB0, q1.y, n4);
+                    n5 = __dp2a_hi(c0R, q1.y, 32768u); n5 = __dp2a_lo(cGB, q2.x, n5);
+                    n6 = __dp2a_hi(cRG, q2.x, 32768u); n6 = __dp2a_lo(cB0, q2.y, n6);
+                    n7 = __dp2a_lo(c0R, q2.y, 32768u); n7 = __dp2a_hi(cGB, q2.y, n7);
+                    P[r][0] = __byte_perm(n0, n4, 0x7632); P[r][1] = __byte_perm(n1, n5, 0x7632);
+                    P[r][2] = __byte_perm(n2, n6, 0x7632); P[r][3] = __byte_perm(n3, n7, 0x7632);
+                    s.edgeL[r][t] = __byte_perm(P[r][0], P[r][1], 0x5410);   // (g0, g1)
+                    s.edgeR[r][t] = __byte_perm(P[r][2], P[r][3], 0x7632);   // (g6, g7)
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kStageRows; ++r) { P[r][0] = P[r][1] = P[r][2] = P[r][3] = 0; }
+            }
+            consumer_sync();
+
+            // ---------------- phase B: 5x5 box sum, threshold, raster rows 1..9 (row 0 = previous row 9)
+            if (px_active) {
+                uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[0][0]);
+                rast8[t] = rast8[9 * kRastPitch + t];
+                uint32_t h[kStageRows][4];
+#pragma unroll
+                for (int r = 0; r < kStageRows; ++r) {
+                    uint32_t lR = s.edgeR[r][tl], rL = s.edgeL[r][tr];
+                    uint32_t Pm2 = __byte_perm(lR, P[r][2], 0x5410), Pm1 = __byte_perm(lR, P[r][3], 0x5432);
+                    uint32_t P4 = __byte_perm(P[r][0], rL, 0x5432), P5 = __byte_perm(P[r][1], rL, 0x7632);
+                    h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P[r][2];
+                    h[r][1] = h[r][0] - Pm2 + P[r][3];
+                    h[r][2] = h[r][1] - Pm1 + P4;
+                    h[r][3] = h[r][2] - P[r][0] + P5;
+                    uint32_t byte = 0;
+                    uint32_t tj[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t hold = (r < 5) ? hprev[r][j] : h[r - 5][j];
+                        nV[j] = nV[j] + hold - h[r][j];
+                        uint32_t Pc = (r < 2) ? Pprev[r][j] : P[r - 2][j];
+                        tj[j] = 25u * Pc + nV[j];             // bit15 / bit31 = (25 g > boxsum + 12)
+                    }
+                    byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
+                           ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
+                    byte = (byte | (byte >> 12)) & 0xFFu;
+                    rast8[(r + 1) * kRastPitch + t] = (uint8_t)byte;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) hprev[i][j] = h[4 + i][j];
+                    Pprev[0][j] = P[7][j]; Pprev[1][j] = P[8][j];
+                }
+            }
+            consumer_sync();
+
+            // ---------------- phase C: cells of row k
+            if (k >= k0) {
+                int base, ncols, x0;
+                cell_row_geom(m, k, base, ncols, x0);
+                if (t < ncols) {
+                    const int x = x0 + kSpacing * t;
+                    const int cell = base + t;
+                    // --- symbol: centre hash rows 1..8, cols 1..8 of the 10x10 window at (x-1, y-1)
+                    const uint32_t o = (uint32_t)x;          // window col 1 == pixel x
+                    uint32_t lo = 0, hi = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        lo |= (raster_bits(s, 1 + q, o) & 0xFFu) << (8 * q);
+                        hi |= (raster_bits(s, 5 + q, o) & 0xFFu) << (8 * q);
+                    }
+                    uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
+                    uint32_t sym, dirty = 0;
+                    if (te.x == lo && te.y == hi) {
+                        sym = te.z;
+                    } else {
+                        const int narrow = m.cells_x - 2 * m.corner, last = m.num_cells - 1, fm = m.top_cells;
+                        bool seed = (cell == 0) | (cell == narrow - 1) | (cell == last) | (cell == last - (narrow - 1)) |
+                                    (cell == fm) | (cell == fm + m.cells_x - 1) | (cell == last - fm) | (cell == last - (fm + m.cells_x - 1));
+                        uint32_t doff, dist;
+                        sym = full_symbol_search(s, o - 1u, seed, doff, dist);
+                        if (doff != 4u) { dirty = kCellDirty; any_dirty = true; }
+                    }
+                    // --- colour: inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
+                    uint32_t R = carryR, G = carryG, B = carryB;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) rgb_row6(sb + (uint32_t)r * row_bytes, x + 1, R, G, B);
+                    uint32_t col = 0;
+                    if (num_colors > 1) col = best_color(s.adjust, m, R / 36u, G / 36u, B / 36u, num_colors);
+                    out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
+                }
+            }
+            // colour carry for cell row k+1: its row y'+1 = last row of this stage
+            carryR = carryG = carryB = 0;
+            if (k + 1 < k1) {
+                int base, ncols, x0;
+                cell_row_geom(m, k + 1, base, ncols, x0);
+                if (t < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty_bar[buf]);
+        }
+        if (any_dirty) atomicOr(&dirty_flags[f], (uint32_t)kFrameDirtyK1);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------- single-cell API
+// CimbDecoder::decode_symbol(bitmatrix) for a batch of pre-thresholded 10x10 windows (rows MSB-first, bit 9 = col 0)
+__global__ void k_decode_symbols(const uint16_t* __restrict__ windows, const uint8_t* __restrict__ cooldown, int n,
+                                 uint8_t* __restrict__ symbol, uint8_t* __restrict__ drift_offset, uint8_t* __restrict__ distance)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t rows[10];
+    for (int r = 0; r < 10; ++r) rows[r] = windows[(size_t)i * 10 + r] & 0x3FFu;
+    uint32_t cd = cooldown ? cooldown[i] : 0xFFu;
+    const int order[9] = {4, 5, 7, 3, 1, 8, 0, 2, 6};
+    int nids = (cd == 0xFEu) ? 9 : 5;                          // CimbDecoder.cpp:144
+    uint32_t best = 1000, best_sym = 0, best_id = 0;
+    for (int q = 0; q < nids; ++q) {
+        int id = order[q];
+        if ((uint32_t)id == cd && id != 4) continue;           // CimbDecoder.cpp:116
+        int r0 = id / 3, c0 = id % 3;
+        unsigned long long H = 0;
+        for (int k = 0; k < 8; ++k) H = (H << 8) | ((rows[r0 + k] >> (2 - c0)) & 0xFFu);
+        unsigned long long L = __brevll(H);
+        for (int t = 0; t < 16; ++t) {
+            uint32_t d = __popcll(L ^ c_tiles_L[t]);
+            if (d < best) { best = d; best_sym = (uint32_t)t; best_id = (uint32_t)id; }
+        }
+    }
+    symbol[i] = (uint8_t)best_sym; drift_offset[i] = (uint8_t)best_id; distance[i] = (uint8_t)best;
+}
+
+__global__ void k_best_colors(const Mode m, const uint8_t* __restrict__ rgb, int n, uint8_t* __restrict__ color)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    color[i] = (uint8_t)best_color(c_adjust, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1 << m.color_bits);
+}
+
+cudaError_t k1_symbols_launch(const uint16_t* d_windows, const uint8_t* d_cooldown, int n, uint8_t* d_sym, uint8_t* d_off, uint8_t* d_dist, cudaStream_t st)
+{
+    k_decode_symbols<<<(n + 127) / 128, 128, 0, st>>>(d_windows, d_cooldown, n, d_sym, d_off, d_dist);
+    return cudaGetLastError();
+}
+cudaError_t k1_colors_launch(const Mode& m, const uint8_t* d_rgb, int n, uint8_t* d_color, cudaStream_t st)
+{
+    k_best_colors<<<(n + 127) / 128, 128, 0, st>>>(m, d_rgb, n, d_color);
+    return cudaGetLastError();
+}
+
+size_t k1_smem_bytes() { return sizeof(K1Smem); }
+
+cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* tiles_L16)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_adjust, adjust256, sizeof(float) * 256);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k1_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+}
+
+cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid,
+                      uint8_t* d_cellvals, uint32_t* d_dirty, cudaStream_t stream)
+{
+    k1_decode_kernel<<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, d_cellvals, d_dirty);
+    return cudaGetLastError();
+}
+
+}  // namespace cb200

@@ -1,0 +1,22 @@
+// k1x_flood.cuh -- host-side entry points of the exact flood-walk kernel (k1x_flood.cu)
+#pragma once
+#include "cb200_common.cuh"
+#include <cstring>
+
+namespace cb200 {
+
+struct FloodWorkspace {
+    int slots;                 // concurrent frames (one CTA each)
+    size_t heap_cap;           // heap entries per slot
+    uint8_t* gray; uint8_t* gray2; uint16_t* hsum; uint32_t* raster; uint32_t* heap;
+};
+
+cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16);
+cudaError_t flood_workspace_create(const Mode& m, int sm_count, FloodWorkspace* ws);
+void flood_workspace_destroy(FloodWorkspace* ws);
+// writes d_flags[f] for every frame: 0 = K1 result stands, CB200_FRAME_FALLBACK = re-decoded here,
+// CB200_FRAME_INEXACT = needed but skipped (no_fallback)
+cudaError_t flood_launch(const Mode& m, const FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
+                         bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, cudaStream_t st);
+
+}  // namespace cb200

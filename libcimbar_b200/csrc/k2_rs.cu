@@ -1,0 +1,308 @@
+// k2_rs.cu -- K2: de-interleave/bit-pack + Reed-Solomon block correction + fountain-chunk masks, sm_100a.
+//
+// Replaces (reference file:line relative to /root/reference/):
+//   P7/P10 Decoder::do_decode bit packing     src/lib/encoder/Decoder.h:77-117 (:121-161 coupled), Interleave.h:8-36,
+//                                              bit_file/bitbuffer.h:62-84 (MSB-first)
+//   P11    reed_solomon_stream::write         src/lib/encoder/reed_solomon_stream.h:54-76
+//   P12    correct_reed_solomon_decode        src/third_party_lib/libcorrect/src/reed-solomon/decode.c:299-379
+//          (GF(2^8) poly 0x187, roots alpha^1..alpha^parity; Berlekamp-Massey decode.c:30-116, Chien :120-143,
+//           locations :198-222, Forney :163-194; no syndrome re-check, x/0 = 0, success iff #roots == locator order)
+//   P13    aligned_stream chunk acceptance    src/lib/encoder/aligned_stream.h:39-116 (+ reed_solomon_stream.h:109-114)
+//
+// One warp per RS block.  Syndromes: lane j runs Horner with the constant alpha^(j+1) through exp/log LUTs in shared
+// memory; Berlekamp-Massey keeps one locator coefficient per lane-slot in shared memory and updates them lane-parallel
+// in libcorrect's exact operation order (its output for uncorrectable blocks depends on that order); Chien search
+// evaluates the locator at 8 field elements per lane; Forney evaluates one error value per lane.
+#include "cb200_common.cuh"
+#include "k2_rs.cuh"
+
+namespace cb200 {
+
+constexpr int kRsWarps = 4;
+constexpr int kMaxParity = 64;
+
+__constant__ uint8_t c_gf_exp[512];
+__constant__ uint8_t c_gf_log[256];
+
+// ---------------------------------------------------------------------------------------------- pack
+// value of interleave slot s in a given stream: 0 = symbols, 1 = colours, 2 = coupled (colour << symbol_bits | symbol)
+__device__ __forceinline__ uint32_t slot_value(const uint8_t* __restrict__ cells, const uint16_t* __restrict__ idx,
+                                               uint32_t s, int stream, int symbol_bits)
+{
+    uint32_t v = cells[idx[s]] & 0x7Fu;
+    uint32_t sym_mask = (1u << symbol_bits) - 1u;
+    if (stream == 0) return v & sym_mask;
+    if (stream == 1) return v >> symbol_bits;
+    return v;
+}
+
+// byte B of a bit stream made of w-bit slots written MSB-first (bitbuffer::write)
+__device__ __forceinline__ uint32_t stream_byte(const uint8_t* __restrict__ cells, const uint16_t* __restrict__ idx,
+                                                uint32_t B, int w, int stream, int symbol_bits, uint32_t nslots)
+{
+    uint32_t bit0 = 8u * B;
+    uint32_t s = bit0 / (uint32_t)w;
+    uint32_t skip = bit0 - s * (uint32_t)w;
+    uint32_t acc = 0, nbits = 0;
+    while (nbits < skip + 8u) {
+        uint32_t v = (s < nslots) ? slot_value(cells, idx, s, stream, symbol_bits) : 0u;
+        acc = (acc << w) | v;
+        nbits += (uint32_t)w;
+        ++s;
+    }
+    return (acc >> (nbits - skip - 8u)) & 0xFFu;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_raw(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* __restrict__ idx, int n_frames,
+           uint8_t* __restrict__ raw)
+{
+    int B = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = blockIdx.y;
+    if (B >= m.cap_all || f >= n_frames) return;
+    const uint8_t* cells = cellvals + (size_t)f * m.num_cells;
+    uint32_t v;
+    if (m.legacy) v = stream_byte(cells, idx, (uint32_t)B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
+    else if (B < m.cap_sym) v = stream_byte(cells, idx, (uint32_t)B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
+    else v = stream_byte(cells, idx, (uint32_t)(B - m.cap_sym), m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
+    raw[(size_t)f * m.cap_all + B] = (uint8_t)v;
+}
+
+// ---------------------------------------------------------------------------------------------- GF(256) helpers
+struct RsSmem {
+    uint8_t exp[512];
+    uint8_t log[256];
+    struct PerWarp {
+        uint8_t enc[256];
+        uint8_t synd[kMaxParity];
+        uint8_t loc[kMaxParity + 8];
+        uint8_t last[kMaxParity + 8];
+        uint8_t omega[kMaxParity];
+        uint8_t roots[kMaxParity + 8];
+    } w[kRsWarps];
+};
+
+__device__ __forceinline__ uint32_t gf_mul(const RsSmem& s, uint32_t a, uint32_t b)
+{   // field_mul, libcorrect field.h:92-110
+    if (a == 0 || b == 0) return 0;
+    return s.exp[(uint32_t)s.log[a] + (uint32_t)s.log[b]];
+}
+__device__ __forceinline__ uint32_t gf_div(const RsSmem& s, uint32_t a, uint32_t b)
+{   // field_div, field.h:112-129 (x / 0 == 0)
+    if (a == 0 || b == 0) return 0;
+    return s.exp[255u + (uint32_t)s.log[a] - (uint32_t)s.log[b]];
+}
+__device__ __forceinline__ uint32_t warp_xor(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------- RS decode
+// one warp per block; raw: n_frames * cap_all bytes (symbol stream blocks then colour stream blocks);
+// data_out: n_frames * nblocks * msg_len (zeros for failed blocks, reed_solomon_stream.h:96-107); ok: n_frames * nblocks
+__global__ void __launch_bounds__(kRsWarps * 32)
+k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, int n_frames, uint8_t* __restrict__ data_out,
+            uint8_t* __restrict__ block_ok)
+{
+    __shared__ RsSmem s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 512; i += blockDim.x) s.exp[i] = c_gf_exp[i];
+    for (int i = tid; i < 256; i += blockDim.x) s.log[i] = c_gf_log[i];
+    __syncthreads();
+
+    const int md = m.ecc_bytes, blk = m.ecc_block, msg_len = m.msg_len;
+    const long total_blocks = (long)n_frames * m.nblocks;
+    RsSmem::PerWarp& w = s.w[warp];
+
+    for (long gb = (long)blockIdx.x * kRsWarps + warp; gb < total_blocks; gb += (long)gridDim.x * kRsWarps) {
+        const int f = (int)(gb / m.nblocks), b = (int)(gb - (long)f * m.nblocks);
+        // Symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
+        // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks.
+        const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
+        uint8_t* out = data_out + ((size_t)f * m.nblocks + b) * msg_len;
+        __syncwarp();
+        for (int i = lane; i < blk; i += 32) w.enc[i] = enc_g[i];
+        __syncwarp();
+
+        // ---- syndromes S_j = r(alpha^(j+1)), Horner from the highest coefficient = enc[0]  (decode.c:12-28)
+        uint32_t nz = 0;
+        for (int j = lane; j < md; j += 32) {
+            uint32_t acc = 0;
+            const uint32_t lg = (uint32_t)(j + 1);
+            for (int i = 0; i < blk; ++i) {
+                uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + lg] : 0u;
+                acc = t ^ w.enc[i];
+            }
+            w.synd[j] = (uint8_t)acc;
+            nz |= acc;
+        }
+        nz = __ballot_sync(0xffffffffu, nz != 0);
+        __syncwarp();
+        if (nz == 0) {  // clean block: copy out (decode.c:337-343)
+            for (int i = lane; i < msg_len; i += 32) out[i] = w.enc[i];
+            if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
+            continue;
+        }
+
+        // ---- Berlekamp-Massey (decode.c:30-116), coefficients in shared memory, updated lane-parallel
+        for (int j = lane; j < kMaxParity + 8; j += 32) { w.loc[j] = (j == 0); w.last[j] = (j == 0); }
+        __syncwarp();
+        uint32_t numerrors = 0, loc_order = 0, last_order = 0, last_disc = 1, delay = 1;
+        for (uint32_t i = 0; i < (uint32_t)md; ++i) {
+            uint32_t part = 0;
+            for (uint32_t j = 1 + lane; j <= numerrors; j += 32) part ^= gf_mul(s, w.loc[j], w.synd[i - j]);
+            uint32_t disc = warp_xor(part) ^ w.synd[i];
+            if (disc == 0) { delay++; continue; }
+            if (2 * numerrors <= i) {
+                // last <- x^delay * (disc/last_disc) * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
+                uint32_t top = last_order + delay;
+                uint32_t sh[3], lc[3];
+                int q = 0;
+                for (uint32_t j = lane; j <= top; j += 32, ++q) {
+                    sh[q] = (j < delay) ? 0u : gf_div(s, gf_mul(s, w.last[j - delay], disc), last_disc);
+                    lc[q] = w.loc[j];
+                }
+                __syncwarp();
+                q = 0;
+                for (uint32_t j = lane; j <= top; j += 32, ++q) {
+                    w.loc[j] = (uint8_t)(lc[q] ^ sh[q]);
+                    w.last[j] = (uint8_t)lc[q];
+                }
+                __syncwarp();
+                uint32_t tmp = loc_order;
+                loc_order = top; last_order = tmp;
+                numerrors = i + 1 - numerrors;
+                last_disc = disc;
+                delay = 1;
+                continue;
+            }
+            // no length change: loc[j+delay] ^= (disc/last_disc) * last[j]
+            for (uint32_t j = lane; j <= last_order; j += 32)
+                w.loc[j + delay] ^= (uint8_t)gf_div(s, gf_mul(s, w.last[j], disc), last_disc);
+            __syncwarp();
+            if (last_order + delay > loc_order) loc_order = last_order + delay;
+            delay++;
+        }
+        const uint32_t order = loc_order;
+
+        // ---- Chien search over all field elements in increasing order (decode.c:120-143); element 0 is never a
+        //      root (loc[0] == 1); root count must equal the locator order, else the block fails
+        uint32_t myroots = 0;   // bit k set: element lane*8+k is a root
+        for (int k = 0; k < 8; ++k) {
+            uint32_t e = (uint32_t)lane * 8u + (uint32_t)k;
+            if (e == 0) continue;
+            uint32_t le = s.log[e];
+            uint32_t acc = w.loc[order];
+            for (int i = (int)order - 1; i >= 0; --i) {
+                uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + le] : 0u;
+                acc = t ^ w.loc[i];
+            }
+            if (acc == 0) myroots |= 1u << k;
+        }
+        uint32_t cnt = __popc(myroots);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total != order || order == 0) {   // order==0 cannot happen with nonzero syndromes; guarded for safety
+            if (order == 0 && total == 0) {
+                // libcorrect would "succeed" with no corrections; unreachable because S != 0 forces order >= 1
+            }
+            for (int i = lane; i < msg_len; i += 32) out[i] = 0;
+            if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 0;
+            continue;
+        }
+        {
+            uint32_t pos = incl - cnt;
+            for (int k = 0; k < 8; ++k) if (myroots & (1u << k)) w.roots[pos++] = (uint8_t)(lane * 8 + k);
+        }
+        // ---- error evaluator omega = S(x) * loc(x) mod x^md  (decode.c:146-161, polynomial.c:17-31)
+        for (int k = lane; k < md; k += 32) {
+            uint32_t acc = 0;
+            int lim = (int)order < k ? (int)order : k;
+            for (int i = 0; i <= lim; ++i) acc ^= gf_mul(s, w.loc[i], w.synd[k - i]);
+            w.omega[k] = (uint8_t)acc;
+        }
+        __syncwarp();
+        // ---- Forney (decode.c:163-194) + apply (decode.c:369-372); one root per lane-slot
+        for (uint32_t q = lane; q < order; q += 32) {
+            uint32_t X = w.roots[q];
+            uint32_t lx = s.log[X];
+            // omega(X) and loc'(X) by Horner; loc'[i] = loc[i+1] for even i, 0 for odd i (polynomial.c:97-111)
+            uint32_t num = 0;
+            for (int i = md - 1; i >= 0; --i) {
+                uint32_t t = num ? (uint32_t)s.exp[(uint32_t)s.log[num] + lx] : 0u;
+                num = t ^ w.omega[i];
+            }
+            uint32_t den = 0;
+            for (int i = (int)order - 1; i >= 0; --i) {
+                uint32_t t = den ? (uint32_t)s.exp[(uint32_t)s.log[den] + lx] : 0u;
+                uint32_t c = ((i & 1) == 0) ? (uint32_t)w.loc[i + 1] : 0u;
+                den = t ^ c;
+            }
+            uint32_t err = gf_div(s, num, den);          // X^(fcr-1) = 1 for fcr = 1
+            uint32_t inv = s.exp[510u - lx];             // field_div(1, X): log[1] = 255
+            uint32_t location = s.log[inv];              // coefficient index (255 when inv == 1: out of range in libcorrect)
+            if (location >= (uint32_t)md && location < (uint32_t)blk)
+                w.enc[blk - 1 - (int)location] ^= (uint8_t)err;
+        }
+        __syncwarp();
+        for (int i = lane; i < msg_len; i += 32) out[i] = w.enc[i];
+        if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- chunk masks (P13)
+// chunk q is emitted iff all of its RS blocks decoded and the last block of chunk q-1 was not bad: a bad block sets
+// aligned_stream::_badChunk, which is only cleared when a later good write crosses a chunk boundary
+// (aligned_stream.h:66-73, :97-104); if the bad block is the chunk's last one, _offset wraps to 0 first and the
+// flag survives into the next chunk.
+__global__ void k_chunk_mask(const Mode m, const uint8_t* __restrict__ block_ok, int n_frames, uint32_t* __restrict__ mask)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const uint8_t* ok = block_ok + (size_t)f * m.nblocks;
+    uint32_t out = 0;
+    bool carry = false;
+    for (int q = 0; q < m.chunks_per_frame; ++q) {
+        bool all = true;
+        for (int k = 0; k < m.blocks_per_chunk; ++k) all = all && (ok[q * m.blocks_per_chunk + k] != 0);
+        if (all && !carry) out |= 1u << q;
+        carry = ok[q * m.blocks_per_chunk + m.blocks_per_chunk - 1] == 0;
+    }
+    mask[f] = out;
+}
+
+cudaError_t k2_init_tables(const uint8_t* exp512, const uint8_t* log256)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_gf_exp, exp512, 512);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_gf_log, log256, 256);
+}
+
+cudaError_t k2_pack_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_raw, cudaStream_t st)
+{
+    dim3 grid((m.cap_all + 255) / 256, n_frames);
+    k_pack_raw<<<grid, 256, 0, st>>>(m, d_cellvals, d_idx, n_frames, d_raw);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint8_t* d_data, uint8_t* d_ok, int max_ctas, cudaStream_t st)
+{
+    long total = (long)n_frames * m.nblocks;
+    long ctas = (total + kRsWarps - 1) / kRsWarps;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (ctas < 1) ctas = 1;
+    k_rs_decode<<<(int)ctas, kRsWarps * 32, 0, st>>>(m, d_raw, n_frames, d_data, d_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_mask_launch(const Mode& m, const uint8_t* d_ok, int n_frames, uint32_t* d_mask, cudaStream_t st)
+{
+    k_chunk_mask<<<(n_frames + 127) / 128, 128, 0, st>>>(m, d_ok, n_frames, d_mask);
+    return cudaGetLastError();
+}
+
+}  // namespace cb200

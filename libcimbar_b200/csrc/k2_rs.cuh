@@ -1,0 +1,10 @@
+// k2_rs.cuh -- host-side entry points of the pack / Reed-Solomon / chunk-mask kernels (k2_rs.cu)
+#pragma once
+#include "cb200_common.cuh"
+
+namespace cb200 {
+cudaError_t k2_init_tables(const uint8_t* exp512, const uint8_t* log256);
+cudaError_t k2_pack_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_raw, cudaStream_t st);
+cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint8_t* d_data, uint8_t* d_ok, int max_ctas, cudaStream_t st);
+cudaError_t k2_mask_launch(const Mode& m, const uint8_t* d_ok, int n_frames, uint32_t* d_mask, cudaStream_t st);
+}  // namespace cb200

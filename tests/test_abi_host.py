@@ -1,0 +1,58 @@
+"""CPU-side checks of the product's host surface: the C-ABI library loads and exports every symbol include/cb200.h
+declares, its mode table and interleave map agree with the oracle, and it refuses to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import libcimbar_b200 as cb
+from libcimbar_b200 import build as cbbuild
+from oracle_lib import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORA = Oracle()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    cbbuild.build()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(cb.EXPORTS)
+    lib = cb.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cb200_version() >= 1
+
+
+@pytest.mark.parametrize("mode_val", [68, 4, 8, 67, 66])
+def test_mode_table_matches_oracle(mode_val):
+    i, m = cb.mode_info(mode_val), ORA.mode(mode_val)
+    assert (i.image_size_x, i.image_size_y, i.total_cells) == (m.image_size_x, m.image_size_y, m.total_cells)
+    assert (i.symbol_bits, i.color_bits, i.ecc_bytes, i.ecc_block_size) == (m.symbol_bits, m.color_bits, m.ecc_bytes, m.ecc_block_size)
+    assert i.raw_bytes == ORA.capacity(m) and i.chunk_size == m.chunk_size and i.chunks_per_frame == m.chunks_per_frame
+    assert i.legacy_mode == m.legacy_mode
+    assert i.data_bytes == (i.raw_bytes // i.ecc_block_size) * (i.ecc_block_size - i.ecc_bytes)
+    idx = cb.interleave_indices(mode_val)
+    want = np.zeros(m.total_cells, np.uint32)
+    ORA.lib.cbo_interleave_indices(m.total_cells, m.interleave_blocks, m.interleave_partitions, want.ctypes.data_as(C.POINTER(C.c_uint)))
+    assert np.array_equal(idx.astype(np.uint32), want)
+
+
+def test_unknown_mode_is_an_error():
+    with pytest.raises(cb.Cb200Error):
+        cb.mode_info(999)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(cb.Cb200Error) as e:
+        cb.Context(68, max_frames=1)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)

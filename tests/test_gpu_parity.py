@@ -1,0 +1,298 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of libcb200.so and is
+compared bit for bit with the CPU oracle (itself pinned to the reference's goldens, tests/test_oracle_goldens.py),
+with the reference's SHA-256 goldens directly, and with size-independent round-trip properties."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle, load_sample, manifest, _ptr
+
+pytestmark = pytest.mark.gpu
+
+ORA = Oracle()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import libcimbar_b200 as cb
+    return cb
+
+
+def synth_frames(mode_val, n, seed, error_rate=0.0, noise_tiles=False):
+    """payload -> RS-encoded cells -> frames, optionally replacing a fraction of cells with a different valid tile
+    (keeps the drift-0 pass exact) or with random 8x8 noise."""
+    m = ORA.mode(mode_val)
+    rng = np.random.default_rng(seed)
+    nbytes = (ORA.capacity(m) // m.ecc_block_size) * (m.ecc_block_size - m.ecc_bytes)
+    payloads = rng.integers(0, 256, (n, nbytes), dtype=np.uint8)
+    frames = np.zeros((n, m.image_size_y, m.image_size_x, 3), dtype=np.uint8)
+    for f in range(n):
+        cells = ORA.payload_to_cells(m, payloads[f])
+        k = int(round(error_rate * m.total_cells))
+        bad = rng.choice(m.total_cells, k, replace=False) if k else np.zeros(0, dtype=np.int64)
+        if k and not noise_tiles:
+            nvals = 1 << (m.symbol_bits + m.color_bits)
+            cells[bad] = (cells[bad] + rng.integers(1, nvals, k, dtype=np.uint8)) % nvals
+        frames[f] = ORA.render_frame(m, cells)
+        if k and noise_tiles:
+            xs, ys = np.zeros(m.total_cells, np.int32), np.zeros(m.total_cells, np.int32)
+            ORA.lib.cbo_cell_positions(C.byref(m), 0, _ptr(xs, C.c_int), _ptr(ys, C.c_int))
+            for i in bad:
+                frames[f, ys[i]:ys[i] + 8, xs[i]:xs[i] + 8] = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+    return m, payloads, frames
+
+
+# ------------------------------------------------------------------------------------------------ goldens
+@pytest.mark.parametrize("g", [g for g in manifest()["goldens"] if g["sample"] != "b/scan2434.jpg"],
+                         ids=lambda g: f"{g['sample']}-m{g['mode']}-ecc{int(g['ecc'])}")
+def test_reference_sha256_goldens_on_gpu(cb, g):
+    # src/lib/encoder/test/DecoderTest.cpp:26-106, including the camera JPEG that needs the exact flood walk
+    ctx = cb.Context(g["mode"], max_frames=1)
+    rgb = load_sample(g["sample"])
+    if g["ecc"]:
+        data, ok, ff = ctx.decode(rgb)
+        out = data[0]
+    else:
+        raw, ff = ctx.decode_raw(rgb)
+        out = raw[0]
+    assert out.size == g["bytes"]
+    assert sha(out) == g["sha256"], g["source"]
+    if g["sample"].endswith(".jpg"):
+        assert ff[0] & cb.FRAME_FALLBACK
+    ctx.close()
+
+
+def test_camera_frame_mode_b_matches_oracle(cb):
+    ctx = cb.Context(68, max_frames=1)
+    rgb = load_sample("b/ex2434.jpg")
+    raw, ff = ctx.decode_raw(rgb)
+    assert ff[0] & cb.FRAME_FALLBACK
+    assert np.array_equal(raw[0], ORA.decode_raw(ORA.mode(68), rgb))
+    data, ok, _ = ctx.decode(rgb)
+    odata, ook = ORA.decode(ORA.mode(68), rgb)
+    assert np.array_equal(data[0], odata) and np.array_equal(ok[0], ook)
+    ctx.close()
+
+
+def test_sharpen_flag_matches_oracle(cb):
+    ctx = cb.Context(68, max_frames=1)
+    for name in ("b/ex2434.jpg", "b/tr_0.png"):
+        rgb = load_sample(name)
+        raw, ff = ctx.decode_raw(rgb, flags=cb.FLAG_SHARPEN)
+        assert np.array_equal(raw[0], ORA.decode_raw(ORA.mode(68), rgb, sharpen=True)), name
+    ctx.close()
+
+
+def test_sample_stream_chunks(cb):
+    # samples/b/tr_0..3.png: every chunk decodes; headers carry encode_id 0, size 23586, distinct block ids
+    ctx = cb.Context(68, max_frames=4)
+    frames = np.stack([load_sample(f"b/tr_{k}.png") for k in range(4)])
+    chunks, count, mask, ff = ctx.decode_fountain(frames)
+    assert count.tolist() == [12] * 4 and mask.tolist() == [0xFFF] * 4 and not ff.any()
+    m = ORA.mode(68)
+    for k in range(4):
+        good, ochunks, omask = ORA.decode_fountain(m, frames[k])
+        assert good == 7500 and np.array_equal(chunks[k], ochunks)
+    ids = sorted(int(c[4]) << 8 | int(c[5]) for c in chunks.reshape(-1, 625))
+    assert len(set(ids)) == 48
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ synthetic frames
+@pytest.mark.parametrize("mode_val", [68, 4, 8, 67, 66])
+def test_clean_synthetic_frames_all_modes(cb, mode_val):
+    m, payloads, frames = synth_frames(mode_val, 3, seed=mode_val)
+    ctx = cb.Context(mode_val, max_frames=3)
+    raw, ff = ctx.decode_raw(frames)
+    assert not ff.any()
+    for f in range(3):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f])), (mode_val, f)
+    data, ok, _ = ctx.decode(frames)
+    assert ok.all() and np.array_equal(data, payloads)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 200])
+def test_band_splitting_is_invisible(cb, n):
+    # few frames are split into bands of cell rows, many frames are processed whole: same bits either way
+    m, payloads, frames = synth_frames(68, min(n, 8), seed=100 + n)
+    reps = (n + frames.shape[0] - 1) // frames.shape[0]
+    big = np.concatenate([frames] * reps)[:n]
+    ctx = cb.Context(68, max_frames=n)
+    raw, ff = ctx.decode_raw(big)
+    assert not ff.any()
+    want = np.stack([ORA.decode_raw(m, fr) for fr in frames])
+    for f in range(n):
+        assert np.array_equal(raw[f], want[f % frames.shape[0]]), f
+    ctx.close()
+
+
+def test_one_percent_tile_errors_config3(cb):
+    # BASELINE config 3: 1 % of cells replaced by a different valid tile -> RS repairs everything
+    m, payloads, frames = synth_frames(68, 6, seed=7, error_rate=0.01)
+    ctx = cb.Context(68, max_frames=6)
+    raw, ff = ctx.decode_raw(frames)
+    data, ok, _ = ctx.decode(frames)
+    for f in range(6):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f]))
+        odata, ook = ORA.decode(m, frames[f])
+        assert np.array_equal(data[f], odata) and np.array_equal(ok[f], ook)
+    assert ok.all() and np.array_equal(data, payloads)
+    ctx.close()
+
+
+@pytest.mark.parametrize("rate", [0.01, 0.08])
+def test_noise_tiles_and_rs_failures_match_oracle(cb, rate):
+    # noise tiles may break the centre-wins proof (-> exact walk) and, at 8 %, overwhelm RS: good/bad masks must match
+    m, payloads, frames = synth_frames(68, 4, seed=11, error_rate=rate, noise_tiles=True)
+    ctx = cb.Context(68, max_frames=4)
+    raw, ff = ctx.decode_raw(frames)
+    data, ok, _ = ctx.decode(frames)
+    chunks, count, mask, _ = ctx.decode_fountain(frames)
+    for f in range(4):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f])), f
+        odata, ook = ORA.decode(m, frames[f])
+        assert np.array_equal(ok[f], ook) and np.array_equal(data[f], odata)
+        good, ochunks, omask = ORA.decode_fountain(m, frames[f])
+        assert mask[f] == omask and count[f] * m.chunk_size == good
+        assert np.array_equal(chunks[f][:count[f]], ochunks[:count[f]])
+    ctx.close()
+
+
+def test_large_batch_round_trip_property(cb):
+    # size-independent property at scale: encode -> render on device -> decode == payload for every frame
+    import torch
+    n = 1024
+    m = ORA.mode(68)
+    rng = np.random.default_rng(5)
+    payloads = rng.integers(0, 256, (n, 7500), dtype=np.uint8)
+    cells = np.stack([ORA.payload_to_cells(m, p) for p in payloads])
+    ctx = cb.Context(68, max_frames=n)
+    d_cells = torch.from_numpy(cells).cuda()
+    d_rgb = torch.empty((n, 1024, 1024, 3), dtype=torch.uint8, device="cuda")
+    d_chunks = torch.empty((n, 7500), dtype=torch.uint8, device="cuda")
+    d_mask = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.render_frames_dev(d_cells.data_ptr(), n, d_rgb.data_ptr())
+    ctx.decode_chunks_dev(d_rgb.data_ptr(), n, d_chunks.data_ptr(), d_mask.data_ptr(), d_flags.data_ptr())
+    torch.cuda.synchronize()
+    assert (d_mask.cpu().numpy() == 0xFFF).all() and not d_flags.cpu().numpy().any()
+    assert np.array_equal(d_chunks.cpu().numpy(), payloads)
+    # the device renderer is the oracle's renderer
+    assert np.array_equal(d_rgb[3].cpu().numpy(), ORA.render_frame(m, cells[3]))
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ Reed-Solomon
+@pytest.mark.parametrize("mode_val", [68, 4, 67, 66])
+def test_rs_kernel_matches_libcorrect_semantics(cb, mode_val):
+    import torch
+    m = ORA.mode(mode_val)
+    rng = np.random.default_rng(mode_val + 1)
+    cap, block, parity = ORA.capacity(m), m.ecc_block_size, m.ecc_bytes
+    msg, nblocks = block - parity, ORA.capacity(m) // m.ecc_block_size
+    n = 24
+    raws = np.zeros((n, cap), np.uint8)
+    rs = ORA.lib.cbo_rs_create(parity)
+    enc = np.zeros(255, np.uint8)
+    t = parity // 2
+    for f in range(n):
+        for b in range(nblocks):
+            p = rng.integers(0, 256, msg, dtype=np.uint8)
+            ORA.lib.cbo_rs_encode(rs, _ptr(p), msg, _ptr(enc))
+            blk = enc[:block].copy()
+            kind = (f * nblocks + b) % 7
+            nerr = [0, 1, t, t + 1, int(rng.integers(0, parity + 6)), t - 1, int(rng.integers(0, 4))][kind]
+            pos = rng.choice(block, nerr, replace=False)
+            blk[pos] ^= rng.integers(1, 256, nerr, dtype=np.uint8)
+            if (f * nblocks + b) % 53 == 0:
+                blk = rng.integers(0, 256, block, dtype=np.uint8)
+            raws[f, b * block:(b + 1) * block] = blk
+    ORA.lib.cbo_rs_destroy(rs)
+    ctx = cb.Context(mode_val, max_frames=n)
+    d_raw = torch.from_numpy(raws).cuda()
+    d_data = torch.zeros((n, nblocks * msg), dtype=torch.uint8, device="cuda")
+    d_ok = torch.zeros((n, nblocks), dtype=torch.uint8, device="cuda")
+    ctx.rs_correct_dev(d_raw.data_ptr(), n, d_data.data_ptr(), d_ok.data_ptr())
+    ctx.sync()
+    data, ok = d_data.cpu().numpy(), d_ok.cpu().numpy()
+    nfail = 0
+    for f in range(n):
+        if m.legacy_mode:
+            odata, ook = ORA.rs_stream(parity, block, raws[f])
+        else:
+            cs = ORA.capacity(m, m.symbol_bits)
+            o1, k1 = ORA.rs_stream(parity, block, raws[f, :cs])
+            o2, k2 = ORA.rs_stream(parity, block, raws[f, cs:])
+            odata, ook = np.concatenate([o1, o2]), np.concatenate([k1, k2])
+        assert np.array_equal(ok[f], ook), f
+        assert np.array_equal(data[f], odata), f
+        nfail += int((ook == 0).sum())
+    assert nfail > 0
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ single-cell API
+def test_decode_symbols_matches_oracle(cb):
+    rng = np.random.default_rng(3)
+    n = 4000
+    windows = rng.integers(0, 1024, (n, 10), dtype=np.uint16)
+    # half of the windows: exact tiles embedded with a random drift, the rest pure noise
+    ORA.lib.cbo_tile_hashes.restype = C.POINTER(C.c_uint64)
+    T = ORA.lib.cbo_tile_hashes()
+    for i in range(0, n, 2):
+        t = int(T[int(rng.integers(0, 16))])
+        dx, dy = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        rows = [int(rng.integers(0, 1024)) for _ in range(10)]
+        for r in range(8):
+            byte = (t >> (8 * (7 - r))) & 0xFF
+            rows[dy + r] = (rows[dy + r] & ~(0xFF << (2 - dx))) | (byte << (2 - dx))
+        windows[i] = rows
+    cooldown = rng.choice(np.array([0xFF, 0xFE, 1, 3, 4, 5, 7], dtype=np.uint8), n)
+    ctx = cb.Context(68, max_frames=1)
+    sym, off, dist = ctx.decode_symbols(windows, cooldown)
+    hashes = (C.c_uint64 * 9)()
+    doff, ddist = C.c_uint(0), C.c_uint(0)
+    for i in range(n):
+        # build a 10x10 MSB-first bit buffer (row pitch 16 bits) and run the oracle's fuzzy_ahash + best_symbol
+        buf = np.zeros(24, np.uint8)
+        for r in range(10):
+            v = int(windows[i, r]) << 6
+            buf[2 * r], buf[2 * r + 1] = v >> 8, v & 0xFF
+        all_ = int(cooldown[i] == 0xFE)
+        ORA.lib.cbo_fuzzy_ahash(_ptr(buf), 16, 0, 0, all_, hashes)
+        s = ORA.lib.cbo_best_symbol(hashes, all_, 16, int(cooldown[i]), C.byref(doff), C.byref(ddist))
+        assert (sym[i], off[i], dist[i]) == (s, doff.value, ddist.value), i
+    ctx.close()
+
+
+def test_best_colors_matches_oracle(cb):
+    rng = np.random.default_rng(4)
+    means = rng.integers(0, 256, (20000, 3), dtype=np.uint8)
+    for mode_val in (68, 4, 8):
+        m = ORA.mode(mode_val)
+        ctx = cb.Context(mode_val, max_frames=1)
+        got = ctx.best_colors(means)
+        want = np.array([ORA.lib.cbo_best_color(float(r), float(g), float(b), 1 << m.color_bits, m.color_mode, None)
+                         for r, g, b in means], dtype=np.uint8)
+        assert np.array_equal(got, want), mode_val
+        ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ errors
+def test_argument_errors(cb):
+    ctx = cb.Context(68, max_frames=2)
+    with pytest.raises(cb.Cb200Error):
+        ctx.decode_raw(np.zeros((3, 1024, 1024, 3), np.uint8))      # n > max_frames
+    with pytest.raises(cb.Cb200Error):
+        ctx.decode_raw(np.zeros((1, 512, 512, 3), np.uint8))        # wrong geometry
+    with pytest.raises(cb.Cb200Error):
+        cb.Context(12345, max_frames=1)                             # unknown mode
+    ctx.close()
