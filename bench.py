@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded cimbar frames/s (1024x1024 mode B) on N B200s, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference ...                      (the CPU restatement of the reference on the host cores)
+
+One "step" = one pass of the decode hot path over one batch of synthetic frames resident in HBM:
+  K1 fused preprocess+ahash+colour -> K1x exact-walk check -> bit pack -> RS(155,125) -> fountain-chunk masks,
+  then (N>1) one NCCL gather of the decoded chunk records to rank 0.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of every field."""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decoded cimbar frames/sec (1024x1024 mode-B)"
+UNIT = "frames/s"
+K1_READ_BYTES = 1024 * 1024 * 3          # the RGB8 frame, read once
+K1_WRITE_BYTES = 12400                   # one result byte per cell
+K1_ALGO_BYTES = K1_READ_BYTES + K1_WRITE_BYTES
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=10000, help="frames per GPU per step (BASELINE config: 10k)")
+    ap.add_argument("--workload", default="clean", choices=["clean", "errors1pct"],
+                    help="clean = BASELINE configs[1] frames; errors1pct = configs[2] (1%% wrong tiles, RS repairs)")
+    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0, help="frames per step for --impl reference (0 = auto)")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def k1_traffic_bytes():
+    """dram bytes per K1 launch from the committed ncu capture, scaled per frame; None until one exists."""
+    p = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import libcimbar_b200 as cb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the decode path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, K, W = args.frames, args.steps, max(args.warmup, 0)
+
+    ctx = cb.Context(68, max_frames=max(B, args.e2e_frames), device=local)
+    info = ctx.info
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # ---- synthetic input, generated on the device: payload -> RS(155,125) -> interleaved cells -> RGB8 frames
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC1B4 + rank)
+    payload = torch.randint(0, 256, (B, info.data_bytes), dtype=torch.uint8, device=dev, generator=g)
+    cells = torch.empty((B, info.total_cells), dtype=torch.uint8, device=dev)
+    ctx.encode_cells_dev(payload.data_ptr(), B, cells.data_ptr())
+    if args.workload == "errors1pct":
+        # replace 1 % of the cells (124 per frame) by a different valid tile/colour: RS must repair them
+        k = info.total_cells // 100
+        pos = torch.rand((B, info.total_cells), device=dev, generator=g).argsort(dim=1)[:, :k]
+        delta = torch.randint(1, 64, (B, k), dtype=torch.uint8, device=dev, generator=g)
+        cells.scatter_(1, pos, (cells.gather(1, pos) + delta) % 64)
+    frames = torch.empty((B, info.image_size_y, info.image_size_x, 3), dtype=torch.uint8, device=dev)
+    ctx.render_frames_dev(cells.data_ptr(), B, frames.data_ptr())
+    chunks = torch.empty((B, info.data_bytes), dtype=torch.uint8, device=dev)
+    mask = torch.empty(B, dtype=torch.int32, device=dev)
+    fflags = torch.empty(B, dtype=torch.uint8, device=dev)
+    gather_chunks = gather_mask = None
+    if world > 1 and rank == 0:
+        gather_chunks = [torch.empty_like(chunks) for _ in range(world)]
+        gather_mask = [torch.empty_like(mask) for _ in range(world)]
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr())
+        if world > 1:   # the one exchange of the path: decoded fountain chunk records -> rank 0 (wirehair ingest side)
+            dist.gather(chunks, gather_chunks, dst=0)
+            dist.gather(mask, gather_mask, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.set_timing(False)
+    for _ in range(max(W, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ctx.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    elapsed_ms = e0.elapsed_time(e1)
+    k_ms = [ctx.get_timing(i) for i in range(min(K, 64))]          # per launch, launch order [K1, K1x, pack, RS, mask]
+    ctx.set_timing(False)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    sampler.join(timeout=1.0)
+
+    # ---- parity of what was just timed (outside the timed region): every chunk decoded, bytes == payload
+    ok_mask = bool((mask == (1 << info.chunks_per_frame) - 1).all().item())
+    ok_data = bool(torch.equal(chunks, payload))
+    ok_flags = not bool(fflags.any().item())
+    parity = "bit-exact: %d frames/rank, all %d chunks/frame == payload" % (B, info.chunks_per_frame) \
+        if (ok_mask and ok_data) else "MISMATCH mask_ok=%s data_ok=%s" % (ok_mask, ok_data)
+
+    # ---- end to end through the host-pointer C ABI: pinned host frames -> cb200_decode_fountain -> host chunks
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_frames, B)
+        host_frames = torch.empty((ne, info.image_size_y, info.image_size_x, 3), dtype=torch.uint8, pin_memory=True)
+        host_frames.copy_(frames[:ne])
+        torch.cuda.synchronize()
+        hf = host_frames.numpy()
+        ctx.set_stream(None)
+        ctx.decode_fountain(hf)                      # warm-up (allocates the staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        esteps = max(3, min(K, 10))
+        for _ in range(esteps):
+            ch, cnt, mk, ff = ctx.decode_fountain(hf)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_ok = bool((cnt == info.chunks_per_frame).all()) and np.array_equal(ch.reshape(ne, -1), payload[:ne].cpu().numpy())
+        e2e = {"value": world * ne * esteps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": ne * info.frame_bytes,
+               "d2h_bytes_per_step": ne * (info.data_bytes + 4 + 1),
+               "frames_per_step": ne, "steps": esteps, "api": "cb200_decode_fountain (host pointers, pinned input)",
+               "parity": "ok" if e2e_ok else "MISMATCH"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    k1_ms = sum(r[0] for r in k_ms) / len(k_ms)
+    stage_ms = [sum(r[i] for r in k_ms) / len(k_ms) for i in range(len(k_ms[0]))]
+    peak, peak_src = measured_peak_gbs()
+    achieved = B * K1_ALGO_BYTES / (k1_ms * 1e-3) / 1e9
+    traffic = k1_traffic_bytes()
+    out = {
+        "metric": METRIC, "value": world * B * K / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 (integer/bitwise; float32 only in the colour classifier, bit-exact vs reference)",
+        "data": "synthetic (device-generated: random payload -> RS(155,125) -> interleaved tiles -> RGB8 frames)",
+        "config": {"workload": ("BASELINE configs[1]" if args.workload == "clean" else "BASELINE configs[2] (1% wrong tiles)") +
+                   ": %d synthetic 1024x1024 mode-B frames per GPU per step through the full decode "
+                   "(K1 fused threshold+ahash+colour, K1x exact-walk check, pack, RS(155,125), chunk masks)" % B,
+                   "mode": "B (68)", "frames_per_gpu_per_step": B,
+                   "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
+                   "parallelism": "frames sharded one-per-GPU (dp%d), NCCL gather of chunk records to rank 0" % world},
+        "parity": parity + ("" if ok_flags else " (some frames used the exact-walk kernel)"),
+        "gpu_launches": 5 * K * world,
+        "kernel_ms_per_step": {"k1_decode": stage_ms[0], "k1x_flood_check": stage_ms[1], "pack": stage_ms[2], "rs": stage_ms[3], "chunk_mask": stage_ms[4]},
+        "roofline": {"kernel": "k1_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": B * K1_ALGO_BYTES,
+                     "traffic": (traffic["dram_bytes_per_frame"] * B if traffic else None),
+                     "traffic_source": (traffic["source"] if traffic else None)},
+        "clocks": sampler.summary(),
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_from_device_frames(frames, info)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_from_device_frames(frames, info):
+    """the oracle (CPU port of the reference decode) timed on the host cores on a bounded sample of the same frames"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    ora = Oracle()
+    cores = len(os.sched_getaffinity(0))
+    S = int(min(frames.shape[0], max(64, 16 * cores)))
+    host = frames[:S].cpu().numpy()
+    ora.bench_decode(68, host[:cores], cores, 1)      # warm the per-thread malloc arenas
+    secs, _ = ora.bench_decode(68, host, cores, 1)
+    secs1, _ = ora.bench_decode(68, host[:max(8, S // cores)], 1, 1)
+    return {"value": S / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the same synthetic frames, full decode incl. RS, %d threads (one decoder per thread); "
+                      "single thread: %.1f frames/s" % (S, cores, max(8, S // cores) / secs1)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    ora = Oracle()
+    m = ora.mode(68)
+    cores = len(os.sched_getaffinity(0))
+    S = args.ref_sample or int(max(64, 8 * cores))
+    rng = np.random.default_rng(0xC1B4)
+    base = min(S, 64)
+    uniq = np.stack([ora.render_frame(m, ora.payload_to_cells(m, rng.integers(0, 256, 7500, dtype=np.uint8))) for _ in range(base)])
+    frames = np.concatenate([uniq] * ((S + base - 1) // base))[:S]
+    K, W = args.steps, max(args.warmup, 1)
+    for _ in range(W):
+        ora.bench_decode(68, frames, cores, 1)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        ora.bench_decode(68, frames, cores, 1)
+    dt = time.perf_counter() - t0
+    value = S * K / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic (same generator family: random payload -> RS(155,125) -> tiles -> RGB8 frames)",
+        "config": {"workload": "BASELINE configs[1]: synthetic 1024x1024 mode-B frames through the full CPU decode "
+                               "(threshold, flood walk, colour, RS) -- bounded sample of %d frames per step" % S,
+                   "mode": "B (68)", "frames_per_step": S},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d frames per step, %d threads, one decoder per thread (the reference's own threading model); "
+                                   "the reference's ./cimbar cannot be built here (needs C++ OpenCV), this is its CPU restatement "
+                                   "pinned to its SHA-256 goldens" % (S, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -129,6 +129,18 @@ int cb200_best_colors(cb200_ctx* ctx, const uint8_t* rgb_means, int n, uint8_t* 
    (what CimbWriter::write pastes, src/lib/cimb_translator/CimbWriter.cpp:84-95); d_rgb_out: n frames. */
 int cb200_render_frames_dev(cb200_ctx* ctx, const uint8_t* d_cellvals, int n, uint8_t* d_rgb_out);
 
+/* payload: n * data_bytes bytes on the device -> RS-encoded (correct_reed_solomon_encode, libcorrect encode.c:3-35),
+   bit-striped (Encoder::encode_next, src/lib/encoder/Encoder.h:69-129) and interleaved cell values, n * total_cells. */
+int cb200_encode_cells_dev(cb200_ctx* ctx, const uint8_t* d_payload, int n, uint8_t* d_cellvals);
+
+/* ---- per-kernel timing (measurement support) --------------------------------------------------------------------- */
+
+/* when enabled, CUDA events are recorded on the context's stream around every kernel of every pipeline call (a ring of
+   the last 64 calls).  cb200_get_timing returns the milliseconds of the call `calls_back` calls ago (0 = last) in launch
+   order: [0] K1 fused decode, [1] K1x exact-walk kernel, [2] pack, [3] RS, [4] chunk mask (decode_raw_dev stops after [2]) */
+int cb200_set_timing(cb200_ctx* ctx, int enable);
+int cb200_get_timing(cb200_ctx* ctx, int calls_back, float* ms, int max_entries, int* n_entries);
+
 /* ---- host-side helpers that need no GPU ------------------------------------------------------------------------ */
 
 /* geometry without a context (for sizing buffers before a device exists) */

@@ -20,7 +20,7 @@ EXPORTS = [
     "cb200_last_error", "cb200_version", "cb200_create", "cb200_destroy", "cb200_get_info", "cb200_set_stream",
     "cb200_sync", "cb200_decode_raw_dev", "cb200_rs_correct_dev", "cb200_decode_chunks_dev", "cb200_decode_raw",
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
-    "cb200_mode_info", "cb200_interleave_indices",
+    "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing",
 ]
 
 
@@ -63,6 +63,9 @@ def load_library():
     lib.cb200_decode_symbols.argtypes = [vp, u16p, u8p, C.c_int, u8p, u8p, u8p]
     lib.cb200_best_colors.argtypes = [vp, u8p, C.c_int, u8p]
     lib.cb200_render_frames_dev.argtypes = [vp, u8p, C.c_int, u8p]
+    lib.cb200_encode_cells_dev.argtypes = [vp, u8p, C.c_int, u8p]
+    lib.cb200_set_timing.argtypes = [vp, C.c_int]
+    lib.cb200_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     lib.cb200_mode_info.argtypes = [C.c_int, C.POINTER(Info)]
     lib.cb200_interleave_indices.argtypes = [C.c_int, u16p]
     _lib = lib
@@ -176,6 +179,19 @@ class Context:
 
     def decode_chunks_dev(self, d_rgb, n, d_chunks, d_mask, d_flags=None, flags=0):
         _check(self.lib.cb200_decode_chunks_dev(self._h, d_rgb, n, flags, d_chunks, d_mask, d_flags))
+
+    def encode_cells_dev(self, d_payload, n, d_cellvals):
+        _check(self.lib.cb200_encode_cells_dev(self._h, d_payload, n, d_cellvals))
+
+    def set_timing(self, enable=True):
+        _check(self.lib.cb200_set_timing(self._h, int(enable)))
+
+    def get_timing(self, calls_back=0):
+        """ms per kernel of the pipeline call `calls_back` calls ago: [K1, K1x, pack, RS, mask]"""
+        ms = (C.c_float * 8)()
+        n = C.c_int(0)
+        _check(self.lib.cb200_get_timing(self._h, calls_back, ms, 8, C.byref(n)))
+        return [ms[i] for i in range(n.value)]
 
     def render_frames_dev(self, d_cellvals, n, d_rgb_out):
         _check(self.lib.cb200_render_frames_dev(self._h, d_cellvals, n, d_rgb_out))

@@ -7,6 +7,7 @@
 #include "k1x_flood.cuh"
 #include "k2_rs.cuh"
 #include "render.cuh"
+#include "encode.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -152,7 +153,16 @@ struct cb200_ctx {
     uint8_t* d_ok = nullptr;         // max_frames * nblocks
     uint32_t* d_mask = nullptr;      // max_frames
     uint8_t* d_flags = nullptr;      // max_frames
-    uint16_t* d_idx = nullptr;       // num_cells
+    uint16_t* d_idx = nullptr;       // num_cells: slot -> cell (Interleave::interleave_indices)
+    uint16_t* d_inv = nullptr;       // num_cells: cell -> slot (Interleave::interleave_reverse)
+    uint8_t* d_gen = nullptr;        // RS generator polynomial, ecc_bytes+1 coefficients
+    // per-kernel timing (cb200_set_timing): events around every launch of the last pipeline call
+    bool timing = false;
+    static constexpr int kEvSets = 64;
+    cudaEvent_t ev[kEvSets][8] = {};
+    int ev_count[kEvSets] = {};
+    long calls = 0;                  // pipeline calls since timing was enabled
+    int cur = 0;                     // event set of the call in progress
     FloodWorkspace flood;            // exact-walk fallback scratch
     // small scratch for the single-cell entry points
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -172,6 +182,11 @@ int ensure_scratch(cb200_ctx* c, size_t bytes)
     return CB200_OK;
 }
 
+void mark(cb200_ctx* c)
+{
+    if (c->timing && c->ev_count[c->cur] < 8) cudaEventRecord(c->ev[c->cur][c->ev_count[c->cur]++], c->stream);
+}
+
 int check_n(const cb200_ctx* c, int n)
 {
     if (!c) return fail(CB200_ERR_ARG, "null context");
@@ -186,6 +201,8 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
     cudaStream_t st = c->stream;
     const bool sharpen = (flags & CB200_FLAG_SHARPEN) != 0;
     CK(cudaMemsetAsync(c->d_dirty, 0, sizeof(uint32_t) * (size_t)n, st), "memset dirty");
+    if (c->timing) { c->cur = (int)(c->calls % cb200_ctx::kEvSets); c->calls++; c->ev_count[c->cur] = 0; }
+    mark(c);                                   // ev0: before K1
     if (!sharpen) {
         // bands: whole frames when there are enough of them to fill the machine, else split frames into bands of cell rows
         int ctas = c->sm_count * 3;
@@ -195,9 +212,11 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
         int grid = units < ctas ? units : ctas;
         CK(k1_launch(m, d_rgb, n, bands, grid, c->d_cellvals, c->d_dirty, st), "k1 launch");
     }
+    mark(c);                                   // ev1: after K1
     // the sharpen preprocessing (needs_sharpen, CimbReader.cpp:37-40) is only implemented in the exact-walk kernel
     CK(flood_launch(m, c->flood, d_rgb, n, (flags & CB200_FLAG_NO_FALLBACK) != 0, sharpen, sharpen,
                     c->d_cellvals, c->d_dirty, c->d_flags, st), "flood launch");
+    mark(c);                                   // ev2: after K1x
     return CB200_OK;
 }
 
@@ -273,7 +292,7 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
     size_t n = (size_t)max_frames;
     CK(cudaMalloc(&c->d_cellvals, n * m.num_cells), "cudaMalloc cellvals");
     CK(cudaMalloc(&c->d_dirty, n * sizeof(uint32_t)), "cudaMalloc dirty");
-    CK(cudaMalloc(&c->d_raw, n * m.cap_all), "cudaMalloc raw");
+    CK(cudaMalloc(&c->d_raw, n * m.cap_all + 16), "cudaMalloc raw");
     CK(cudaMalloc(&c->d_data, n * m.data_bytes), "cudaMalloc data");
     CK(cudaMalloc(&c->d_ok, n * m.nblocks), "cudaMalloc ok");
     CK(cudaMalloc(&c->d_mask, n * sizeof(uint32_t)), "cudaMalloc mask");
@@ -282,6 +301,25 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
     interleave_indices(m, idx);
     CK(cudaMalloc(&c->d_idx, idx.size() * sizeof(uint16_t)), "cudaMalloc idx");
     CK(cudaMemcpy(c->d_idx, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "upload idx");
+    {
+        std::vector<uint16_t> inv(idx.size());
+        for (size_t sidx = 0; sidx < idx.size(); ++sidx) inv[idx[sidx]] = (uint16_t)sidx;
+        CK(cudaMalloc(&c->d_inv, inv.size() * sizeof(uint16_t)), "cudaMalloc inv");
+        CK(cudaMemcpy(c->d_inv, inv.data(), inv.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "upload inv");
+        // generator polynomial prod_{i=1..parity} (x + alpha^i) (libcorrect reed-solomon.c:5-12, polynomial.c:215-262)
+        std::vector<uint8_t> g(1, 1);
+        auto mul = [&](uint8_t a, uint8_t b) -> uint8_t { return (a && b) ? gexp[glog[a] + glog[b]] : 0; };
+        for (int i = 1; i <= m.ecc_bytes; ++i) {
+            uint8_t root = gexp[i % 255];
+            std::vector<uint8_t> ng(g.size() + 1, 0);
+            for (size_t k = 0; k < g.size(); ++k) { ng[k + 1] ^= g[k]; ng[k] ^= mul(g[k], root); }
+            g.swap(ng);
+        }
+        CK(cudaMalloc(&c->d_gen, g.size()), "cudaMalloc gen");
+        CK(cudaMemcpy(c->d_gen, g.data(), g.size(), cudaMemcpyHostToDevice), "upload gen");
+        CK(encode_init_tables(gexp, glog), "encode tables");
+        for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[k][i]), "cudaEventCreate");
+    }
     CK(flood_workspace_create(m, c->sm_count, &c->flood), "flood workspace");
     *out = c;
     return CB200_OK;
@@ -292,7 +330,8 @@ int cb200_destroy(cb200_ctx* c)
     if (!c) return CB200_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_rgb); cudaFree(c->d_cellvals); cudaFree(c->d_dirty); cudaFree(c->d_raw); cudaFree(c->d_data);
-    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_scratch);
+    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_scratch);
+    for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) if (c->ev[k][i]) cudaEventDestroy(c->ev[k][i]);
     flood_workspace_destroy(&c->flood);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -329,6 +368,7 @@ int cb200_decode_raw_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t fla
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
     CK(k2_pack_launch(c->mode, c->d_cellvals, c->d_idx, n, d_raw_out, c->stream), "pack launch");
+    mark(c);                                   // ev3: after pack
     if (d_frame_flags) CK(cudaMemcpyAsync(d_frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToDevice, c->stream), "copy flags");
     return CB200_OK;
 }
@@ -352,8 +392,11 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
     CK(k2_pack_launch(c->mode, c->d_cellvals, c->d_idx, n, c->d_raw, c->stream), "pack launch");
+    mark(c);                                   // ev3: after pack
     CK(k2_rs_launch(c->mode, c->d_raw, n, d_chunks, c->d_ok, c->sm_count * 16, c->stream), "rs launch");
+    mark(c);                                   // ev4: after RS
     CK(k2_mask_launch(c->mode, c->d_ok, n, d_chunk_mask, c->stream), "mask launch");
+    mark(c);                                   // ev5: after chunk mask
     if (d_frame_flags) CK(cudaMemcpyAsync(d_frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToDevice, c->stream), "copy flags");
     return CB200_OK;
 }
@@ -464,6 +507,38 @@ int cb200_best_colors(cb200_ctx* c, const uint8_t* rgb_means, int n, uint8_t* co
     CK(k1_colors_launch(c->mode, d_in, n, d_out, c->stream), "colors launch");
     CK(cudaMemcpyAsync(color, d_out, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H");
     CK(cudaStreamSynchronize(c->stream), "sync");
+    return CB200_OK;
+}
+
+int cb200_encode_cells_dev(cb200_ctx* c, const uint8_t* d_payload, int n, uint8_t* d_cellvals)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!d_payload || !d_cellvals) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(encode_launch(c->mode, c->d_gen, c->d_inv, d_payload, n, c->d_raw, d_cellvals, c->stream), "encode launch");
+    return CB200_OK;
+}
+
+int cb200_set_timing(cb200_ctx* c, int enable)
+{
+    if (!c) return fail(CB200_ERR_ARG, "null context");
+    c->timing = enable != 0;
+    c->calls = 0; c->cur = 0;
+    for (int k = 0; k < cb200_ctx::kEvSets; ++k) c->ev_count[k] = 0;
+    return CB200_OK;
+}
+
+int cb200_get_timing(cb200_ctx* c, int calls_back, float* ms, int max_entries, int* n_entries)
+{
+    if (!c || !ms || !n_entries || calls_back < 0) return fail(CB200_ERR_ARG, "bad argument");
+    if (calls_back >= cb200_ctx::kEvSets || calls_back >= c->calls) return fail(CB200_ERR_ARG, "no such timed call");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    int set = (int)((c->calls - 1 - calls_back) % cb200_ctx::kEvSets);
+    int n = c->ev_count[set] > 0 ? c->ev_count[set] - 1 : 0;
+    if (n > max_entries) n = max_entries;
+    for (int i = 0; i < n; ++i) CK(cudaEventElapsedTime(&ms[i], c->ev[set][i], c->ev[set][i + 1]), "cudaEventElapsedTime");
+    *n_entries = n;
     return CB200_OK;
 }
 

@@ -230,33 +230,49 @@ void cbo_sharpen(const uint8_t* gray, int w, int h, uint8_t* out)
 
 void cbo_adaptive_threshold(const uint8_t* gray, int w, int h, int block, uint8_t* out)
 {
+    /* separable box sum with replicate border (boxFilter BORDER_REPLICATE inside cv::adaptiveThreshold), done with
+       running sums: a ring of `block` rows of horizontal sums and one array of column sums */
     int r = block / 2;
-    int area = block * block;
-    /* separable box sum with replicate border */
-    uint16_t* hs = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * h);
+    unsigned area = (unsigned)(block * block);
+    uint16_t* ring = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * (size_t)block);
+    uint32_t* col = (uint32_t*)calloc((size_t)w, sizeof(uint32_t));
+    /* horizontal sums of row yy (clamped) into ring slot */
+#define HROW(dst, yy) do { \
+        const uint8_t* row_ = gray + (size_t)(yy) * w; uint16_t* d_ = (dst); \
+        unsigned s_ = 0; \
+        for (int d = -r; d <= r; ++d) { int xx = d < 0 ? 0 : (d >= w ? w - 1 : d); s_ += row_[xx]; } \
+        d_[0] = (uint16_t)s_; \
+        for (int x = 1; x < w; ++x) { \
+            int xin = x + r; if (xin >= w) xin = w - 1; \
+            int xout = x - r - 1; if (xout < 0) xout = 0; \
+            s_ += row_[xin]; s_ -= row_[xout]; d_[x] = (uint16_t)s_; } \
+    } while (0)
+    /* prime: rows -r..r (clamped) */
+    for (int d = -r; d <= r; ++d) {
+        int yy = d < 0 ? 0 : (d >= h ? h - 1 : d);
+        uint16_t* slot = ring + (size_t)((d + r) % block) * w;
+        HROW(slot, yy);
+        for (int x = 0; x < w; ++x) col[x] += slot[x];
+    }
+    int next_slot = 0;   /* slot holding the oldest row (y - r) */
     for (int y = 0; y < h; ++y) {
-        const uint8_t* row = gray + (size_t)y * w;
+        const uint8_t* g = gray + (size_t)y * w;
+        uint8_t* o = out + (size_t)y * w;
         for (int x = 0; x < w; ++x) {
-            unsigned s = 0;
-            for (int d = -r; d <= r; ++d) {
-                int xx = x + d; if (xx < 0) xx = 0; if (xx >= w) xx = w - 1;
-                s += row[xx];
-            }
-            hs[(size_t)y * w + x] = (uint16_t)s;
+            unsigned mean = (2 * col[x] + area) / (2u * area);  /* round to nearest (never a tie: area odd) */
+            o[x] = (g[x] > mean) ? 255 : 0;
+        }
+        if (y + 1 < h) {   /* slide: drop row (y - r) clamped, add row (y + 1 + r) clamped */
+            uint16_t* slot = ring + (size_t)next_slot * w;
+            for (int x = 0; x < w; ++x) col[x] -= slot[x];
+            int yin = y + 1 + r; if (yin >= h) yin = h - 1;
+            HROW(slot, yin);
+            for (int x = 0; x < w; ++x) col[x] += slot[x];
+            next_slot = (next_slot + 1) % block;
         }
     }
-    for (int y = 0; y < h; ++y) {
-        for (int x = 0; x < w; ++x) {
-            unsigned s = 0;
-            for (int d = -r; d <= r; ++d) {
-                int yy = y + d; if (yy < 0) yy = 0; if (yy >= h) yy = h - 1;
-                s += hs[(size_t)yy * w + x];
-            }
-            unsigned mean = (2 * s + (unsigned)area) / (2u * (unsigned)area);  /* round to nearest (never a tie: area odd) */
-            out[(size_t)y * w + x] = (gray[(size_t)y * w + x] > mean) ? 255 : 0;
-        }
-    }
-    free(hs);
+#undef HROW
+    free(ring); free(col);
 }
 
 void cbo_pack_bits(const uint8_t* thr, size_t npix, uint8_t* bits)

@@ -7,6 +7,7 @@
 #define _POSIX_C_SOURCE 200809L
 #include "cimbar_oracle.h"
 
+#include <malloc.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -50,6 +51,11 @@ double cbo_bench_decode(int mode_val, const uint8_t* frames, int nframes, int w,
 {
     cbo_mode mode; cbo_mode_init(&mode, mode_val);
     if (nthreads < 1) nthreads = 1;
+    /* keep the per-frame MB-sized scratch buffers inside the per-thread malloc arenas: with the default
+       thresholds every frame mmaps/munmaps ~5 MB, and the munmap TLB shootdowns serialise the threads */
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_ARENA_MAX, 256);
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
     job_t* jobs = (job_t*)calloc((size_t)nthreads, sizeof(job_t));
     double t0 = now_s();
