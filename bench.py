@@ -122,7 +122,9 @@ def run_ours(args):
 
     ctx = cb.Context(68, max_frames=max(B, args.e2e_frames), device=local)
     info = ctx.info
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)           # a real (non-default) stream: handle 0 would mean "context's own"
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
 
     # ---- synthetic input, generated on the device: payload -> RS(155,125) -> interleaved cells -> RGB8 frames
     g = torch.Generator(device=dev)

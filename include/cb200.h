@@ -70,7 +70,8 @@ int cb200_version(void);
 int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames);
 int cb200_destroy(cb200_ctx* ctx);
 int cb200_get_info(const cb200_ctx* ctx, cb200_info* out);
-/* run on a caller-provided cudaStream_t (e.g. a torch stream); NULL restores the context's own stream */
+/* run on a caller-provided cudaStream_t (e.g. a torch stream); NULL restores the context's own stream
+   (to select the legacy default stream pass cudaStreamLegacy = (void*)0x1, not 0) */
 int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream);
 int cb200_sync(cb200_ctx* ctx);
 

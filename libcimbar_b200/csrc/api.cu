@@ -157,6 +157,7 @@ struct cb200_ctx {
     uint16_t* d_inv = nullptr;       // num_cells: cell -> slot (Interleave::interleave_reverse)
     uint8_t* d_gen = nullptr;        // RS generator polynomial, ecc_bytes+1 coefficients
     // per-kernel timing (cb200_set_timing): events around every launch of the last pipeline call
+    int l2_ahead = 4;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)
     bool timing = false;
     static constexpr int kEvSets = 64;
     cudaEvent_t ev[kEvSets][8] = {};
@@ -210,7 +211,7 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
         if (n < ctas) { bands = (ctas + n - 1) / n; if (bands > m.cells_y / 4) bands = m.cells_y / 4; if (bands < 1) bands = 1; }
         int units = n * bands;
         int grid = units < ctas ? units : ctas;
-        CK(k1_launch(m, d_rgb, n, bands, grid, c->d_cellvals, c->d_dirty, st), "k1 launch");
+        CK(k1_launch(m, d_rgb, n, bands, grid, c->l2_ahead, c->d_cellvals, c->d_dirty, st), "k1 launch");
     }
     mark(c);                                   // ev1: after K1
     // the sharpen preprocessing (needs_sharpen, CimbReader.cpp:37-40) is only implemented in the exact-walk kernel
@@ -261,6 +262,7 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
     if (!mode_init(c->mode, mode_val)) { delete c; return fail(CB200_ERR_MODE, "unsupported mode_val"); }
     const Mode& m = c->mode;
     c->device = device; c->max_frames = max_frames;
+    if (const char* e = getenv("CB200_K1_L2_AHEAD")) c->l2_ahead = atoi(e);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
     if (prop.major < 10) { delete c; return fail(CB200_ERR_NODEVICE, "libcb200 is built for sm_100a only"); }

@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// TMA prefetch of a linear global range into L2 (no shared memory needed): keeps DRAM requests in flight several stages
+// ahead of the shared-memory ring (SASS: UBLKPF)
+__device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void consumer_sync()   // named barrier: the 128 consumer threads only
 {
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -177,7 +183,7 @@ __device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t o,
 
 // ---------------------------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kK1Threads, 3)
-k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands,
+k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -207,17 +213,35 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     // ------------------------------------------------------------------ producer warp: TMA bulk loads
     if (warp == 4) {
         if (lane == 0) {
+            // Stage sequence of this CTA: (unit, cell row k = k0-1 .. k1-1).  Shared-memory loads run at most two stages
+            // ahead of the consumers (the ring has two slots); L2 prefetches run `l2_ahead` stages further ahead.
             uint32_t it = 0;
+            int pu = blockIdx.x, pk = 0;          // prefetch cursor (unit, row); pk initialised below
+            bool pvalid = pu < n_units;
+            if (pvalid) { int pb = pu % bands; pk = (m.cells_y * pb) / bands - 1; }
+            auto stage_src = [&](int u, int k) -> const uint8_t* {
+                int f = u / bands;
+                return rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * k + 2) * row_bytes;   // rows [y_k+2, y_k+10]
+            };
+            auto advance = [&](int& u, int& k, bool& valid) {
+                int b = u % bands;
+                int k1 = (m.cells_y * (b + 1)) / bands;
+                if (++k >= k1) {
+                    u += gridDim.x;
+                    valid = u < n_units;
+                    if (valid) { int nb = u % bands; k = (m.cells_y * nb) / bands - 1; }
+                }
+            };
+            for (int i = 0; i < l2_ahead && pvalid; ++i) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                int f = u / bands, b = u - f * bands;
+                int b = u % bands;
                 int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
-                const uint8_t* frame = rgb + (size_t)f * frame_bytes;
                 for (int k = k0 - 1; k < k1; ++k, ++it) {
+                    if (pvalid) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
                     uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
                     mbar_wait(&s.empty_bar[buf], ph ^ 1u);
-                    int row0 = m.cell_offset + kSpacing * k + 2;          // rows [y_k+2, y_k+10]
                     mbar_expect_tx(&s.full_bar[buf], stage_bytes);
-                    tma_bulk_g2s(s.stage[buf], frame + (size_t)row0 * row_bytes, stage_bytes, &s.full_bar[buf]);
+                    tma_bulk_g2s(s.stage[buf], stage_src(u, k), stage_bytes, &s.full_bar[buf]);
                 }
             }
         }
@@ -426,10 +450,10 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     return cudaFuncSetAttribute(k1_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
 }
 
-cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid,
+cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead,
                       uint8_t* d_cellvals, uint32_t* d_dirty, cudaStream_t stream)
 {
-    k1_decode_kernel<<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, d_cellvals, d_dirty);
+    k1_decode_kernel<<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
     return cudaGetLastError();
 }
 

@@ -179,7 +179,9 @@ def test_large_batch_round_trip_property(cb):
     d_chunks = torch.empty((n, 7500), dtype=torch.uint8, device="cuda")
     d_mask = torch.empty(n, dtype=torch.int32, device="cuda")
     d_flags = torch.empty(n, dtype=torch.uint8, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     ctx.render_frames_dev(d_cells.data_ptr(), n, d_rgb.data_ptr())
     ctx.decode_chunks_dev(d_rgb.data_ptr(), n, d_chunks.data_ptr(), d_mask.data_ptr(), d_flags.data_ptr())
     torch.cuda.synchronize()
