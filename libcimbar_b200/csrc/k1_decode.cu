@@ -11,7 +11,7 @@
 // centre hash wins for every cell.  A cell where it does not sets bit 7 of its result
 // byte and the frame's dirty flag; such frames are re-done by the exact flood-walk kernel (k1x_flood.cu).
 //
-// Data flow per CTA (128 consumer threads + 1 TMA producer warp, 3 CTAs/SM):
+// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 3 CTAs/SM):
 //   HBM --cp.async.bulk (TMA, 9 full-width rows = 27 KB per stage, 2 stages, mbarrier full/empty)--> smem
 //   phase A: 8 px/thread: gray = (19596R+38470G+7470B+32768)>>16 via 2x IDP.2A per px, packed 2x16 bit
 //   phase B: separable 5x5 box sum in packed-16 SIMD (5 IADD3 + 4 PRMT per 8 px), rolling vertical sum in
@@ -26,7 +26,7 @@
 namespace cb200 {
 
 constexpr int kConsumers = 128;
-constexpr int kK1Threads = 160;
+constexpr int kK1Threads = 128;
 constexpr int kStageRows = 9;
 constexpr int kMaxW = 1024;
 constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
@@ -41,7 +41,6 @@ struct __align__(128) K1Smem {
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
     float adjust[256];                        // copy of c_adjust: indexed per lane, so not read through the constant cache
     unsigned long long full_bar[2];
-    unsigned long long empty_bar[2];
 };
 
 __constant__ float c_adjust[256];             // (float)(255.0 / (double)d), d = max-min (CimbDecoder.cpp:185)
@@ -88,10 +87,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t b
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void consumer_sync()   // named barrier: the 128 consumer threads only
-{
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-}
+__device__ __forceinline__ void consumer_sync() { __syncthreads(); }
 
 // ---------------------------------------------------------------------------------------------- colour
 // P9 get_best_color with integer inputs (no CCM): float32 arithmetic restated op for op (CimbDecoder.cpp:168-200)
@@ -189,7 +185,6 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
     const int W = m.width;
     const uint32_t row_bytes = (uint32_t)W * 3u;
     const uint32_t stage_bytes = row_bytes * kStageRows;
@@ -198,7 +193,6 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
 
     if (tid == 0) {
         mbar_init(&s.full_bar[0], 1); mbar_init(&s.full_bar[1], 1);
-        mbar_init(&s.empty_bar[0], 4); mbar_init(&s.empty_bar[1], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 16) {
@@ -210,44 +204,6 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     for (int i = tid; i < 256; i += kK1Threads) s.adjust[i] = c_adjust[i];
     __syncthreads();
 
-    // ------------------------------------------------------------------ producer warp: TMA bulk loads
-    if (warp == 4) {
-        if (lane == 0) {
-            // Stage sequence of this CTA: (unit, cell row k = k0-1 .. k1-1).  Shared-memory loads run at most two stages
-            // ahead of the consumers (the ring has two slots); L2 prefetches run `l2_ahead` stages further ahead.
-            uint32_t it = 0;
-            int pu = blockIdx.x, pk = 0;          // prefetch cursor (unit, row); pk initialised below
-            bool pvalid = pu < n_units;
-            if (pvalid) { int pb = pu % bands; pk = (m.cells_y * pb) / bands - 1; }
-            auto stage_src = [&](int u, int k) -> const uint8_t* {
-                int f = u / bands;
-                return rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * k + 2) * row_bytes;   // rows [y_k+2, y_k+10]
-            };
-            auto advance = [&](int& u, int& k, bool& valid) {
-                int b = u % bands;
-                int k1 = (m.cells_y * (b + 1)) / bands;
-                if (++k >= k1) {
-                    u += gridDim.x;
-                    valid = u < n_units;
-                    if (valid) { int nb = u % bands; k = (m.cells_y * nb) / bands - 1; }
-                }
-            };
-            for (int i = 0; i < l2_ahead && pvalid; ++i) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                int b = u % bands;
-                int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
-                for (int k = k0 - 1; k < k1; ++k, ++it) {
-                    if (pvalid) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
-                    uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-                    mbar_wait(&s.empty_bar[buf], ph ^ 1u);
-                    mbar_expect_tx(&s.full_bar[buf], stage_bytes);
-                    tma_bulk_g2s(s.stage[buf], stage_src(u, k), stage_bytes, &s.full_bar[buf]);
-                }
-            }
-        }
-        return;
-    }
-
     // ------------------------------------------------------------------ consumers
     const int t = tid;                          // owns pixels 8t .. 8t+7 of every row
     const bool px_active = (8 * t) < W;
@@ -255,6 +211,34 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
     const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
     const int num_colors = 1 << m.color_bits;
+
+    // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1), rows [y_k+2, y_k+10] of the unit's frame.
+    // Thread 0 is the TMA producer: the shared-memory load of stage i+1 is issued right after the barrier that ends
+    // phase A of stage i (every thread has then finished reading that slot in phase C of stage i-1), and an L2
+    // prefetch runs `l2_ahead` stages further ahead.  No dedicated producer warp, no empty-barriers, no spinning.
+    auto stage_src = [&](int u, int k) -> const uint8_t* {
+        int f = u / bands;
+        return rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * k + 2) * row_bytes;
+    };
+    auto advance = [&](int& u, int& k, bool& valid) {
+        int b = u % bands;
+        int k1 = (m.cells_y * (b + 1)) / bands;
+        if (++k >= k1) {
+            u += gridDim.x;
+            valid = u < n_units;
+            if (valid) { int nb = u % bands; k = (m.cells_y * nb) / bands - 1; }
+        }
+    };
+    int nu = blockIdx.x, nk = 0; bool nvalid = nu < n_units;      // next stage to load into shared memory
+    int pu = nu, pk = 0; bool pvalid = nvalid;                     // next stage to prefetch into L2
+    if (tid == 0 && nvalid) {
+        nk = pk = (m.cells_y * (nu % bands)) / bands - 1;
+        mbar_expect_tx(&s.full_bar[0], stage_bytes);
+        tma_bulk_g2s(s.stage[0], stage_src(nu, nk), stage_bytes, &s.full_bar[0]);
+        advance(nu, nk, nvalid);
+        advance(pu, pk, pvalid);
+        for (int i = 0; i < l2_ahead && pvalid; ++i) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
+    }
 
     uint32_t it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -304,6 +288,14 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 for (int r = 0; r < kStageRows; ++r) { P[r][0] = P[r][1] = P[r][2] = P[r][3] = 0; }
             }
             consumer_sync();
+            if (tid == 0) {
+                if (nvalid) {   // slot buf^1 was last read in phase C of the previous stage: free since the barrier above
+                    mbar_expect_tx(&s.full_bar[buf ^ 1u], stage_bytes);
+                    tma_bulk_g2s(s.stage[buf ^ 1u], stage_src(nu, nk), stage_bytes, &s.full_bar[buf ^ 1u]);
+                    advance(nu, nk, nvalid);
+                }
+                if (pvalid) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
+            }
 
             // ---------------- phase B: 5x5 box sum, threshold, raster rows 1..9 (row 0 = previous row 9)
             if (px_active) {
@@ -385,8 +377,6 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 cell_row_geom(m, k + 1, base, ncols, x0);
                 if (t < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.empty_bar[buf]);
         }
         if (any_dirty) atomicOr(&dirty_flags[f], (uint32_t)kFrameDirtyK1);
     }
