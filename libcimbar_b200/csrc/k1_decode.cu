@@ -34,9 +34,8 @@ constexpr int kRastWords = kRastPitch / 4;
 
 struct __align__(128) K1Smem {
     uint8_t stage[2][kStageRows * kMaxW * 3];
-    uint32_t edgeL[kStageRows][kConsumers];   // (g0,g1) of each thread's 8-px run
-    uint32_t edgeR[kStageRows][kConsumers];   // (g6,g7)
-    uint32_t raster[10][kRastWords];
+    uint32_t edge[2][kStageRows][kConsumers]; // bytes (g0,g1,g6,g7) of each thread's 8-px run, double-buffered by stage
+    uint32_t raster[2][10][kRastWords];       // 1-bit threshold rows of the current / previous stage
     uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
     float adjust[256];                        // copy of c_adjust: indexed per lane, so not read through the constant cache
@@ -141,19 +140,19 @@ __device__ __forceinline__ void rgb_row6(const uint8_t* row, int x, uint32_t& R,
 
 // ---------------------------------------------------------------------------------------------- symbols
 // 32 raster bits starting at pixel `o` of window row `r`
-__device__ __forceinline__ uint32_t raster_bits(const K1Smem& s, int r, uint32_t o)
+__device__ __forceinline__ uint32_t raster_bits(const K1Smem& s, uint32_t rbuf, int r, uint32_t o)
 {
     uint32_t idx = o >> 5;
-    return __funnelshift_r(s.raster[r][idx], s.raster[r][idx + 1], o & 31u);
+    return __funnelshift_r(s.raster[rbuf][r][idx], s.raster[rbuf][r][idx + 1], o & 31u);
 }
 
 // full P5+P6 search at drift 0: FAST = ids {4,5,7,3,1}, ALL adds {8,0,2,6} (ahash_result.h:26), tiles 0..15,
 // strict '<' keeps the first minimum (the early return on distance 0 cannot change the result).
-__device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t o, bool all, uint32_t& drift_offset, uint32_t& dist_out)
+__device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t rbuf, uint32_t o, bool all, uint32_t& drift_offset, uint32_t& dist_out)
 {
     uint32_t win[10];
 #pragma unroll
-    for (int r = 0; r < 10; ++r) win[r] = raster_bits(s, r, o) & 0x3FFu;
+    for (int r = 0; r < 10; ++r) win[r] = raster_bits(s, rbuf, r, o) & 0x3FFu;
     const int order[9] = {4, 5, 7, 3, 1, 8, 0, 2, 6};
     uint32_t best = 1000, best_sym = 0, best_id = 0;
     int n = all ? 9 : 5;
@@ -178,6 +177,13 @@ __device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t o,
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+// One barrier per stage.  Iteration for stage `it` (cell row k, raw rows [y_k+2, y_k+10] in ring slot it&1):
+//   wait full[it&1]
+//   A(k):   gray of the 9 rows -> packed pairs in registers, edge grays -> edge[it&1]
+//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static)
+//   ---- __syncthreads ----  (slot it&1 is now dead: thread 0 issues the TMA of stage it+2 into it)
+//   B(k):   box sums, threshold -> raster[it&1]
+//   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
 __global__ void __launch_bounds__(kK1Threads, 3)
 k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
@@ -204,18 +210,15 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     for (int i = tid; i < 256; i += kK1Threads) s.adjust[i] = c_adjust[i];
     __syncthreads();
 
-    // ------------------------------------------------------------------ consumers
-    const int t = tid;                          // owns pixels 8t .. 8t+7 of every row
+    const int t = tid;                          // owns pixels 8t .. 8t+7 of every row, and cell t of every cell row
     const bool px_active = (8 * t) < W;
     const int tl = (t + kConsumers - 1) & (kConsumers - 1), tr = (t + 1) & (kConsumers - 1);
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
     const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
     const int num_colors = 1 << m.color_bits;
+    const int narrow = m.cells_x - 2 * m.corner, last_cell = m.num_cells - 1, first_mid = m.top_cells;
 
-    // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1), rows [y_k+2, y_k+10] of the unit's frame.
-    // Thread 0 is the TMA producer: the shared-memory load of stage i+1 is issued right after the barrier that ends
-    // phase A of stage i (every thread has then finished reading that slot in phase C of stage i-1), and an L2
-    // prefetch runs `l2_ahead` stages further ahead.  No dedicated producer warp, no empty-barriers, no spinning.
+    // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1).  Thread 0 is the TMA producer.
     auto stage_src = [&](int u, int k) -> const uint8_t* {
         int f = u / bands;
         return rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * k + 2) * row_bytes;
@@ -233,12 +236,44 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     int pu = nu, pk = 0; bool pvalid = nvalid;                     // next stage to prefetch into L2
     if (tid == 0 && nvalid) {
         nk = pk = (m.cells_y * (nu % bands)) / bands - 1;
-        mbar_expect_tx(&s.full_bar[0], stage_bytes);
-        tma_bulk_g2s(s.stage[0], stage_src(nu, nk), stage_bytes, &s.full_bar[0]);
-        advance(nu, nk, nvalid);
-        advance(pu, pk, pvalid);
+        for (int i = 0; i < 2 && nvalid; ++i) {
+            mbar_expect_tx(&s.full_bar[i], stage_bytes);
+            tma_bulk_g2s(s.stage[i], stage_src(nu, nk), stage_bytes, &s.full_bar[i]);
+            advance(nu, nk, nvalid);
+            advance(pu, pk, pvalid);
+        }
         for (int i = 0; i < l2_ahead && pvalid; ++i) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
     }
+
+    // symbol stage for one cell row from a finished raster (P5/P6 at drift 0) + the colour decided earlier
+    auto symbol_stage = [&](int k, uint32_t rbuf, uint32_t col, uint8_t* out, bool& any_dirty) {
+        int base, ncols, x0;
+        cell_row_geom(m, k, base, ncols, x0);
+        if (t >= ncols) return;
+        const uint32_t (*rast)[kRastWords] = s.raster[rbuf];
+        const uint32_t o = (uint32_t)(x0 + kSpacing * t);     // window col 1 == pixel x
+        const int cell = base + t;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t idx = o >> 5, sh = o & 31u;
+            lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+            hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+        }
+        uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
+        uint32_t sym, dirty = 0;
+        if (te.x == lo && te.y == hi) {
+            sym = te.z;
+        } else {
+            bool seed = (cell == 0) | (cell == narrow - 1) | (cell == last_cell) | (cell == last_cell - (narrow - 1)) |
+                        (cell == first_mid) | (cell == first_mid + m.cells_x - 1) | (cell == last_cell - first_mid) |
+                        (cell == last_cell - (first_mid + m.cells_x - 1));
+            uint32_t doff, dist;
+            sym = full_symbol_search(s, rbuf, o - 1u, seed, doff, dist);
+            if (doff != 4u) { dirty = kCellDirty; any_dirty = true; }
+        }
+        out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
+    };
 
     uint32_t it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -255,6 +290,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
             Pprev[0][j] = Pprev[1][j] = 0;
         }
         uint32_t carryR = 0, carryG = 0, carryB = 0;   // colour sums of row y+1 of the upcoming cell row
+        uint32_t col_prev = 0;                         // colour of this thread's cell in the row whose symbols are pending
         bool any_dirty = false;
 
         for (int k = k0 - 1; k < k1; ++k, ++it) {
@@ -262,7 +298,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
             const uint8_t* sb = s.stage[buf];
             mbar_wait(&s.full_bar[buf], ph);
 
-            // ---------------- phase A: gray, packed pairs P[r][j] = (g[j], g[j+4])
+            // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+4]); edge bytes (g0,g1,g6,g7)
             uint32_t P[kStageRows][4];
             if (px_active) {
 #pragma unroll
@@ -280,38 +316,59 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                     n7 = __dp2a_lo(c0R, q2.y, 32768u); n7 = __dp2a_hi(cGB, q2.y, n7);
                     P[r][0] = __byte_perm(n0, n4, 0x7632); P[r][1] = __byte_perm(n1, n5, 0x7632);
                     P[r][2] = __byte_perm(n2, n6, 0x7632); P[r][3] = __byte_perm(n3, n7, 0x7632);
-                    s.edgeL[r][t] = __byte_perm(P[r][0], P[r][1], 0x5410);   // (g0, g1)
-                    s.edgeR[r][t] = __byte_perm(P[r][2], P[r][3], 0x7632);   // (g6, g7)
+                    // gray is byte 2 of each numerator: E = (g0, g1, g6, g7)
+                    s.edge[buf][r][t] = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n6, n7, 0x6200), 0x7610);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) { P[r][0] = P[r][1] = P[r][2] = P[r][3] = 0; }
             }
-            consumer_sync();
+
+            // ---------------- col(k): inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
+            uint32_t col = 0;
+            {
+                int base, ncols, x0;
+                if (k >= k0) {
+                    cell_row_geom(m, k, base, ncols, x0);
+                    if (t < ncols && num_colors > 1) {
+                        const int x = x0 + kSpacing * t;
+                        uint32_t R = carryR, G = carryG, B = carryB;
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) rgb_row6(sb + (uint32_t)r * row_bytes, x + 1, R, G, B);
+                        col = best_color(s.adjust, m, R / 36u, G / 36u, B / 36u, num_colors);
+                    }
+                }
+                carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
+                if (k + 1 < k1) {
+                    cell_row_geom(m, k + 1, base, ncols, x0);
+                    if (t < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                }
+            }
+            __syncthreads();
             if (tid == 0) {
-                if (nvalid) {   // slot buf^1 was last read in phase C of the previous stage: free since the barrier above
-                    mbar_expect_tx(&s.full_bar[buf ^ 1u], stage_bytes);
-                    tma_bulk_g2s(s.stage[buf ^ 1u], stage_src(nu, nk), stage_bytes, &s.full_bar[buf ^ 1u]);
+                if (nvalid) {   // slot `buf` is dead (all threads are past their reads of it): refill with stage it+2
+                    mbar_expect_tx(&s.full_bar[buf], stage_bytes);
+                    tma_bulk_g2s(s.stage[buf], stage_src(nu, nk), stage_bytes, &s.full_bar[buf]);
                     advance(nu, nk, nvalid);
                 }
-                if (pvalid) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
+                if (pvalid && l2_ahead > 0) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
             }
 
-            // ---------------- phase B: 5x5 box sum, threshold, raster rows 1..9 (row 0 = previous row 9)
+            // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
             if (px_active) {
-                uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[0][0]);
-                rast8[t] = rast8[9 * kRastPitch + t];
+                uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[buf][0][0]);
+                const uint8_t* prev8 = reinterpret_cast<const uint8_t*>(&s.raster[buf ^ 1u][0][0]);
+                rast8[t] = prev8[9 * kRastPitch + t];
                 uint32_t h[kStageRows][4];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    uint32_t lR = s.edgeR[r][tl], rL = s.edgeL[r][tr];
-                    uint32_t Pm2 = __byte_perm(lR, P[r][2], 0x5410), Pm1 = __byte_perm(lR, P[r][3], 0x5432);
-                    uint32_t P4 = __byte_perm(P[r][0], rL, 0x5432), P5 = __byte_perm(P[r][1], rL, 0x7632);
+                    uint32_t lE = s.edge[buf][r][tl], rE = s.edge[buf][r][tr];
+                    uint32_t Pm2 = __byte_perm(lE, P[r][2], 0x5452), Pm1 = __byte_perm(lE, P[r][3], 0x5453);
+                    uint32_t P4 = __byte_perm(P[r][0], rE, 0x3432), P5 = __byte_perm(P[r][1], rE, 0x3532);
                     h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P[r][2];
                     h[r][1] = h[r][0] - Pm2 + P[r][3];
                     h[r][2] = h[r][1] - Pm1 + P4;
                     h[r][3] = h[r][2] - P[r][0] + P5;
-                    uint32_t byte = 0;
                     uint32_t tj[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -320,8 +377,8 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                         uint32_t Pc = (r < 2) ? Pprev[r][j] : P[r - 2][j];
                         tj[j] = 25u * Pc + nV[j];             // bit15 / bit31 = (25 g > boxsum + 12)
                     }
-                    byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
-                           ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
+                    uint32_t byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
+                                    ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
                     byte = (byte | (byte >> 12)) & 0xFFu;
                     rast8[(r + 1) * kRastPitch + t] = (uint8_t)byte;
                 }
@@ -332,56 +389,17 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                     Pprev[0][j] = P[7][j]; Pprev[1][j] = P[8][j];
                 }
             }
-            consumer_sync();
 
-            // ---------------- phase C: cells of row k
-            if (k >= k0) {
-                int base, ncols, x0;
-                cell_row_geom(m, k, base, ncols, x0);
-                if (t < ncols) {
-                    const int x = x0 + kSpacing * t;
-                    const int cell = base + t;
-                    // --- symbol: centre hash rows 1..8, cols 1..8 of the 10x10 window at (x-1, y-1)
-                    const uint32_t o = (uint32_t)x;          // window col 1 == pixel x
-                    uint32_t lo = 0, hi = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        lo |= (raster_bits(s, 1 + q, o) & 0xFFu) << (8 * q);
-                        hi |= (raster_bits(s, 5 + q, o) & 0xFFu) << (8 * q);
-                    }
-                    uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
-                    uint32_t sym, dirty = 0;
-                    if (te.x == lo && te.y == hi) {
-                        sym = te.z;
-                    } else {
-                        const int narrow = m.cells_x - 2 * m.corner, last = m.num_cells - 1, fm = m.top_cells;
-                        bool seed = (cell == 0) | (cell == narrow - 1) | (cell == last) | (cell == last - (narrow - 1)) |
-                                    (cell == fm) | (cell == fm + m.cells_x - 1) | (cell == last - fm) | (cell == last - (fm + m.cells_x - 1));
-                        uint32_t doff, dist;
-                        sym = full_symbol_search(s, o - 1u, seed, doff, dist);
-                        if (doff != 4u) { dirty = kCellDirty; any_dirty = true; }
-                    }
-                    // --- colour: inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
-                    uint32_t R = carryR, G = carryG, B = carryB;
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) rgb_row6(sb + (uint32_t)r * row_bytes, x + 1, R, G, B);
-                    uint32_t col = 0;
-                    if (num_colors > 1) col = best_color(s.adjust, m, R / 36u, G / 36u, B / 36u, num_colors);
-                    out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
-                }
-            }
-            // colour carry for cell row k+1: its row y'+1 = last row of this stage
-            carryR = carryG = carryB = 0;
-            if (k + 1 < k1) {
-                int base, ncols, x0;
-                cell_row_geom(m, k + 1, base, ncols, x0);
-                if (t < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
-            }
+            // ---------------- S(k-1): its raster was finished by every thread before the barrier above
+            if (k - 1 >= k0) symbol_stage(k - 1, buf ^ 1u, col_prev, out, any_dirty);
+            col_prev = col;
         }
+        // the last cell row of the unit still needs its symbols: one more barrier to see its complete raster
+        __syncthreads();
+        symbol_stage(k1 - 1, (it - 1u) & 1u, col_prev, out, any_dirty);
         if (any_dirty) atomicOr(&dirty_flags[f], (uint32_t)kFrameDirtyK1);
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------- single-cell API
 // CimbDecoder::decode_symbol(bitmatrix) for a batch of pre-thresholded 10x10 windows (rows MSB-first, bit 9 = col 0)
