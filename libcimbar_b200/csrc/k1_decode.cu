@@ -99,7 +99,8 @@ __device__ __forceinline__ uint32_t fix_single_color(float c, float adjust, floa
     return __float2uint_rz(c);   // (uchar)c
 }
 
-__device__ __forceinline__ uint32_t best_color(const float* adjust_tab, const Mode& m, uint32_t ri, uint32_t gi, uint32_t bi, int num_colors)
+template <int NC>
+__device__ __forceinline__ uint32_t best_color(const float* adjust_tab, const Mode& m, uint32_t ri, uint32_t gi, uint32_t bi)
 {
     float r = (float)ri, g = (float)gi, b = (float)bi;
     float mx = fmaxf(fmaxf(r, g), fmaxf(b, 1.0f));
@@ -111,7 +112,8 @@ __device__ __forceinline__ uint32_t best_color(const float* adjust_tab, const Mo
     int cb = (int)fix_single_color(b, adjust, mn);
     int a0 = cr - cg, a1 = cg - cb, a2 = cb - cr;
     uint32_t best = 0, best_d = 0x7fffffffu;   // reference: float 1000000 > any reachable distance (<= 780300)
-    for (int i = 0; i < num_colors; ++i) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
         int pr = m.palette[i][0], pg = m.palette[i][1], pb = m.palette[i][2];
         int d0 = a0 - (pr - pg), d1 = a1 - (pg - pb), d2 = a2 - (pb - pr);
         uint32_t d = (uint32_t)(d0 * d0 + d1 * d1 + d2 * d2);
@@ -146,34 +148,30 @@ __device__ __forceinline__ uint32_t raster_bits(const K1Smem& s, uint32_t rbuf, 
     return __funnelshift_r(s.raster[rbuf][r][idx], s.raster[rbuf][r][idx + 1], o & 31u);
 }
 
-// full P5+P6 search at drift 0: FAST = ids {4,5,7,3,1}, ALL adds {8,0,2,6} (ahash_result.h:26), tiles 0..15,
-// strict '<' keeps the first minimum (the early return on distance 0 cannot change the result).
-__device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t rbuf, uint32_t o, bool all, uint32_t& drift_offset, uint32_t& dist_out)
+// full P5+P6 search at drift 0 for ONE cell, done by the whole warp: FAST = ids {4,5,7,3,1}, ALL adds {8,0,2,6}
+// (ahash_result.h:26), tiles 0..15; the reference keeps the first minimum in that iteration order (strict '<'; its early
+// return on distance 0 cannot change the result), which is the minimum of key = dist<<8 | order<<4 | tile.
+// o = pixel x of window column 0.  Every lane returns the same key.
+__device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t rbuf, uint32_t o, bool all, int lane)
 {
-    uint32_t win[10];
-#pragma unroll
-    for (int r = 0; r < 10; ++r) win[r] = raster_bits(s, rbuf, r, o) & 0x3FFu;
-    const int order[9] = {4, 5, 7, 3, 1, 8, 0, 2, 6};
-    uint32_t best = 1000, best_sym = 0, best_id = 0;
-    int n = all ? 9 : 5;
-    for (int q = 0; q < n; ++q) {
-        int id = order[q];
-        int r0 = id / 3, c0 = id % 3;
+    const int ncand = (all ? 9 : 5) * 16;
+    uint32_t best_key = 0xFFFFFFFFu;
+    for (int p = lane; p < ncand; p += 32) {
+        const uint32_t q = (uint32_t)p >> 4, tile = (uint32_t)p & 15u;
+        const uint32_t id = (uint32_t)(0x620813754ULL >> (4 * q)) & 0xFu;     // order 4,5,7,3,1,8,0,2,6
+        const uint32_t r0 = id / 3u, c0 = id - 3u * r0;
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            lo |= ((win[r0 + k] >> c0) & 0xFFu) << (8 * k);
-            hi |= ((win[r0 + 4 + k] >> c0) & 0xFFu) << (8 * k);
+            lo |= (raster_bits(s, rbuf, (int)r0 + k, o + c0) & 0xFFu) << (8 * k);
+            hi |= (raster_bits(s, rbuf, (int)r0 + 4 + k, o + c0) & 0xFFu) << (8 * k);
         }
-        for (int t = 0; t < 16; ++t) {
-            uint2 tl = s.tiles_by_sym[t];
-            uint32_t d = __popc(lo ^ tl.x) + __popc(hi ^ tl.y);
-            if (d < best) { best = d; best_sym = (uint32_t)t; best_id = (uint32_t)id; }
-        }
+        uint2 tl = s.tiles_by_sym[tile];
+        uint32_t d = __popc(lo ^ tl.x) + __popc(hi ^ tl.y);
+        uint32_t key = (d << 8) | (q << 4) | tile;
+        best_key = key < best_key ? key : best_key;
     }
-    drift_offset = best_id;
-    dist_out = best;
-    return best_sym;
+    return __reduce_min_sync(0xffffffffu, best_key);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -184,6 +182,7 @@ __device__ __noinline__ uint32_t full_symbol_search(const K1Smem& s, uint32_t rb
 //   ---- __syncthreads ----  (slot it&1 is now dead: thread 0 issues the TMA of stage it+2 into it)
 //   B(k):   box sums, threshold -> raster[it&1]
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
+template <int NC>
 __global__ void __launch_bounds__(kK1Threads, 3)
 k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
@@ -215,7 +214,6 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     const int tl = (t + kConsumers - 1) & (kConsumers - 1), tr = (t + 1) & (kConsumers - 1);
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
     const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
-    const int num_colors = 1 << m.color_bits;
     const int narrow = m.cells_x - 2 * m.corner, last_cell = m.num_cells - 1, first_mid = m.top_cells;
 
     // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1).  Thread 0 is the TMA producer.
@@ -245,34 +243,48 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
         for (int i = 0; i < l2_ahead && pvalid; ++i) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
     }
 
-    // symbol stage for one cell row from a finished raster (P5/P6 at drift 0) + the colour decided earlier
+    // symbol stage for one cell row from a finished raster (P5/P6 at drift 0) + the colour decided earlier.
+    // Exact dictionary hits are resolved per thread through the perfect hash; the rare inexact cells (threshold edge
+    // artefacts, ~1 % of a clean frame) are searched one at a time by the whole warp, so no lane waits on a 700-instruction
+    // private search.
     auto symbol_stage = [&](int k, uint32_t rbuf, uint32_t col, uint8_t* out, bool& any_dirty) {
         int base, ncols, x0;
         cell_row_geom(m, k, base, ncols, x0);
-        if (t >= ncols) return;
+        const bool active = t < ncols;
         const uint32_t (*rast)[kRastWords] = s.raster[rbuf];
         const uint32_t o = (uint32_t)(x0 + kSpacing * t);     // window col 1 == pixel x
         const int cell = base + t;
-        uint32_t lo = 0, hi = 0;
+        uint32_t sym = 0, dirty = 0;
+        bool exact = true;
+        if (active) {
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t idx = o >> 5, sh = o & 31u;
-            lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
-            hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
-        }
-        uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
-        uint32_t sym, dirty = 0;
-        if (te.x == lo && te.y == hi) {
+            for (int q = 0; q < 4; ++q) {
+                uint32_t idx = o >> 5, sh = o & 31u;
+                lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+                hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+            }
+            uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
+            exact = (te.x == lo) & (te.y == hi);
             sym = te.z;
-        } else {
-            bool seed = (cell == 0) | (cell == narrow - 1) | (cell == last_cell) | (cell == last_cell - (narrow - 1)) |
-                        (cell == first_mid) | (cell == first_mid + m.cells_x - 1) | (cell == last_cell - first_mid) |
-                        (cell == last_cell - (first_mid + m.cells_x - 1));
-            uint32_t doff, dist;
-            sym = full_symbol_search(s, rbuf, o - 1u, seed, doff, dist);
-            if (doff != 4u) { dirty = kCellDirty; any_dirty = true; }
         }
-        out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
+        uint32_t need = __ballot_sync(0xffffffffu, !exact);
+        const int lane = tid & 31;
+        while (need) {
+            const int leader = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t lo_ = __shfl_sync(0xffffffffu, o, leader);
+            const int lcell = __shfl_sync(0xffffffffu, cell, leader);
+            const bool seed = (lcell == 0) | (lcell == narrow - 1) | (lcell == last_cell) | (lcell == last_cell - (narrow - 1)) |
+                              (lcell == first_mid) | (lcell == first_mid + m.cells_x - 1) | (lcell == last_cell - first_mid) |
+                              (lcell == last_cell - (first_mid + m.cells_x - 1));
+            const uint32_t key = warp_symbol_search(s, rbuf, lo_ - 1u, seed, lane);
+            if (lane == leader) {
+                sym = key & 15u;
+                if (((key >> 4) & 15u) != 0u) { dirty = kCellDirty; any_dirty = true; }   // order index 0 == centre hash (id 4)
+            }
+        }
+        if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
     };
 
     uint32_t it = 0;
@@ -330,12 +342,12 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 int base, ncols, x0;
                 if (k >= k0) {
                     cell_row_geom(m, k, base, ncols, x0);
-                    if (t < ncols && num_colors > 1) {
+                    if (t < ncols && NC > 1) {
                         const int x = x0 + kSpacing * t;
                         uint32_t R = carryR, G = carryG, B = carryB;
 #pragma unroll
                         for (int r = 0; r < 5; ++r) rgb_row6(sb + (uint32_t)r * row_bytes, x + 1, R, G, B);
-                        col = best_color(s.adjust, m, R / 36u, G / 36u, B / 36u, num_colors);
+                        col = best_color<NC>(s.adjust, m, R / 36u, G / 36u, B / 36u);
                     }
                 }
                 carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
@@ -433,7 +445,8 @@ __global__ void k_best_colors(const Mode m, const uint8_t* __restrict__ rgb, int
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    color[i] = (uint8_t)best_color(c_adjust, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1 << m.color_bits);
+    color[i] = (uint8_t)((m.color_bits == 3) ? best_color<8>(c_adjust, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2])
+                                              : best_color<4>(c_adjust, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
 }
 
 cudaError_t k1_symbols_launch(const uint16_t* d_windows, const uint8_t* d_cooldown, int n, uint8_t* d_sym, uint8_t* d_off, uint8_t* d_dist, cudaStream_t st)
@@ -455,13 +468,16 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k1_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    e = cudaFuncSetAttribute(k1_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k1_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
 }
 
 cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead,
                       uint8_t* d_cellvals, uint32_t* d_dirty, cudaStream_t stream)
 {
-    k1_decode_kernel<<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+    if (m.color_bits == 3) k1_decode_kernel<8><<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+    else k1_decode_kernel<4><<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
     return cudaGetLastError();
 }
 
