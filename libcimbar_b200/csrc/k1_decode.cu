@@ -89,34 +89,32 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t b
 __device__ __forceinline__ void consumer_sync() { __syncthreads(); }
 
 // ---------------------------------------------------------------------------------------------- colour
-// P9 get_best_color with integer inputs (no CCM): float32 arithmetic restated op for op (CimbDecoder.cpp:168-200)
-__device__ __forceinline__ uint32_t fix_single_color(float c, float adjust, float down)
-{
-    c = __fsub_rn(c, down);
-    c = __fmul_rn(c, adjust);
-    if (c > __fsub_rn(245.0f, down)) c = 255.0f;
-    if (c < 0.0f) c = 0.0f;
-    return __float2uint_rz(c);   // (uchar)c
-}
-
+// P9 get_best_color with integer inputs (no CCM): float32 arithmetic restated op for op (CimbDecoder.cpp:27-36, :168-200)
 template <int NC>
 __device__ __forceinline__ uint32_t best_color(const float* adjust_tab, const Mode& m, uint32_t ri, uint32_t gi, uint32_t bi)
 {
-    float r = (float)ri, g = (float)gi, b = (float)bi;
-    float mx = fmaxf(fmaxf(r, g), fmaxf(b, 1.0f));
-    float mn = fminf(fminf(r, g), fminf(b, 48.0f));
-    if (mn >= mx) mn = 0.0f;
-    float adjust = adjust_tab[(int)(mx - mn)];
-    int cr = (int)fix_single_color(r, adjust, mn);
-    int cg = (int)fix_single_color(g, adjust, mn);
-    int cb = (int)fix_single_color(b, adjust, mn);
-    int a0 = cr - cg, a1 = cg - cb, a2 = cb - cr;
-    uint32_t best = 0, best_d = 0x7fffffffu;   // reference: float 1000000 > any reachable distance (<= 780300)
+    // max/min with the floors 1 and 48 on integers (exact: the inputs are integer means); if (min >= max) min = 0
+    uint32_t mxi = max(max(ri, gi), max(bi, 1u));
+    uint32_t mni = min(min(ri, gi), min(bi, 48u));
+    if (mni >= mxi) mni = 0;
+    const float adjust = adjust_tab[mxi - mni];
+    const float mn = (float)mni;
+    const float hi_thr = __fsub_rn(245.0f, mn);
+    // fix_single_color: c -= down; c *= adjustUp; if (c > 245 - down) c = 255; (c < 0 cannot happen: down <= c); (uchar)c
+    float fr = __fmul_rn((float)(ri - mni), adjust), fg = __fmul_rn((float)(gi - mni), adjust), fb = __fmul_rn((float)(bi - mni), adjust);
+    int cr = (fr > hi_thr) ? 255 : (int)__float2uint_rz(fr);
+    int cg = (fg > hi_thr) ? 255 : (int)__float2uint_rz(fg);
+    int cb = (fb > hi_thr) ? 255 : (int)__float2uint_rz(fb);
+    const int a0 = cr - cg, a1 = cg - cb, a2 = cb - cr;
+    // color_diff = sum_j (a_j - p_ij)^2 = |a|^2 + (|p_i|^2 - 2 a.p_i): the first term is common, so the strict-'<' argmin
+    // over i of the bracket is the reference's argmin (same ties)
+    uint32_t best = 0;
+    int best_d = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        int pr = m.palette[i][0], pg = m.palette[i][1], pb = m.palette[i][2];
-        int d0 = a0 - (pr - pg), d1 = a1 - (pg - pb), d2 = a2 - (pb - pr);
-        uint32_t d = (uint32_t)(d0 * d0 + d1 * d1 + d2 * d2);
+        const int p0 = (int)m.palette[i][0] - (int)m.palette[i][1], p1 = (int)m.palette[i][1] - (int)m.palette[i][2],
+                  p2 = (int)m.palette[i][2] - (int)m.palette[i][0];
+        const int d = (p0 * p0 + p1 * p1 + p2 * p2) - 2 * (a0 * p0 + a1 * p1 + a2 * p2);
         if (d < best_d) { best_d = d; best = (uint32_t)i; }
     }
     return best;
@@ -217,30 +215,32 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     const int narrow = m.cells_x - 2 * m.corner, last_cell = m.num_cells - 1, first_mid = m.top_cells;
 
     // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1).  Thread 0 is the TMA producer.
-    auto stage_src = [&](int u, int k) -> const uint8_t* {
-        int f = u / bands;
-        return rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * k + 2) * row_bytes;
+    struct Cursor { int u, k, kend; const uint8_t* src; bool valid; };
+    auto cursor_unit = [&](Cursor& c) {          // position at the first (virtual) stage of unit c.u
+        c.valid = c.u < n_units;
+        if (!c.valid) return;
+        int f = c.u / bands, b = c.u - f * bands;
+        c.k = (m.cells_y * b) / bands - 1;
+        c.kend = (m.cells_y * (b + 1)) / bands;
+        c.src = rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * c.k + 2) * row_bytes;
     };
-    auto advance = [&](int& u, int& k, bool& valid) {
-        int b = u % bands;
-        int k1 = (m.cells_y * (b + 1)) / bands;
-        if (++k >= k1) {
-            u += gridDim.x;
-            valid = u < n_units;
-            if (valid) { int nb = u % bands; k = (m.cells_y * nb) / bands - 1; }
-        }
+    auto cursor_next = [&](Cursor& c) {
+        if (++c.k < c.kend) { c.src += stage_bytes; return; }   // consecutive stages are contiguous in the frame
+        c.u += gridDim.x;
+        cursor_unit(c);
     };
-    int nu = blockIdx.x, nk = 0; bool nvalid = nu < n_units;      // next stage to load into shared memory
-    int pu = nu, pk = 0; bool pvalid = nvalid;                     // next stage to prefetch into L2
-    if (tid == 0 && nvalid) {
-        nk = pk = (m.cells_y * (nu % bands)) / bands - 1;
-        for (int i = 0; i < 2 && nvalid; ++i) {
+    Cursor nxt, pre;                              // next stage to load into shared memory / to prefetch into L2
+    nxt.u = blockIdx.x; nxt.valid = false; pre.valid = false;
+    if (tid == 0) {
+        cursor_unit(nxt);
+        pre = nxt;
+        for (int i = 0; i < 2 && nxt.valid; ++i) {
             mbar_expect_tx(&s.full_bar[i], stage_bytes);
-            tma_bulk_g2s(s.stage[i], stage_src(nu, nk), stage_bytes, &s.full_bar[i]);
-            advance(nu, nk, nvalid);
-            advance(pu, pk, pvalid);
+            tma_bulk_g2s(s.stage[i], nxt.src, stage_bytes, &s.full_bar[i]);
+            cursor_next(nxt);
+            cursor_next(pre);
         }
-        for (int i = 0; i < l2_ahead && pvalid; ++i) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
+        for (int i = 0; i < l2_ahead && pre.valid; ++i) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
     }
 
     // symbol stage for one cell row from a finished raster (P5/P6 at drift 0) + the colour decided earlier.
@@ -358,12 +358,12 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
             }
             __syncthreads();
             if (tid == 0) {
-                if (nvalid) {   // slot `buf` is dead (all threads are past their reads of it): refill with stage it+2
+                if (nxt.valid) {   // slot `buf` is dead (all threads are past their reads of it): refill with stage it+2
                     mbar_expect_tx(&s.full_bar[buf], stage_bytes);
-                    tma_bulk_g2s(s.stage[buf], stage_src(nu, nk), stage_bytes, &s.full_bar[buf]);
-                    advance(nu, nk, nvalid);
+                    tma_bulk_g2s(s.stage[buf], nxt.src, stage_bytes, &s.full_bar[buf]);
+                    cursor_next(nxt);
                 }
-                if (pvalid && l2_ahead > 0) { tma_prefetch_l2(stage_src(pu, pk), stage_bytes); advance(pu, pk, pvalid); }
+                if (l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
             }
 
             // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
