@@ -22,6 +22,7 @@
 // Every HBM byte of the frame is read exactly once (plus 4 warm-up rows per band).
 #include "cb200_common.cuh"
 #include "k1_decode.cuh"
+#include <cstdlib>
 
 namespace cb200 {
 
@@ -468,7 +469,7 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k1_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    e = cudaFuncSetAttribute(k1_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem) + 40 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k1_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
 }
@@ -476,8 +477,9 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
 cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead,
                       uint8_t* d_cellvals, uint32_t* d_dirty, cudaStream_t stream)
 {
+    const int extra = getenv("CB200_K1_EXTRA_SMEM") ? atoi(getenv("CB200_K1_EXTRA_SMEM")) : 0;   // tuning only: lowers CTAs/SM
     if (m.color_bits == 3) k1_decode_kernel<8><<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
-    else k1_decode_kernel<4><<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+    else k1_decode_kernel<4><<<grid, kK1Threads, sizeof(K1Smem) + extra, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
     return cudaGetLastError();
 }
 
