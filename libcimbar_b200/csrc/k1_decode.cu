@@ -26,8 +26,8 @@
 
 namespace cb200 {
 
-constexpr int kConsumers = 128;
-constexpr int kK1Threads = 128;
+constexpr int kPx = 4;                     // pixels per thread and row
+constexpr int kK1Threads = 256;            // 256 threads x 4 px = one full 1024-px row
 constexpr int kStageRows = 9;
 constexpr int kMaxW = 1024;
 constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
@@ -35,7 +35,6 @@ constexpr int kRastWords = kRastPitch / 4;
 
 struct __align__(128) K1Smem {
     uint8_t stage[2][kStageRows * kMaxW * 3];
-    uint32_t edge[2][kStageRows][kConsumers]; // bytes (g0,g1,g6,g7) of each thread's 8-px run, double-buffered by stage
     uint32_t raster[2][10][kRastWords];       // 1-bit threshold rows of the current / previous stage
     uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
@@ -174,11 +173,15 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+// 256 threads, 3 CTAs/SM (24 warps/SM: the kernel is latency-bound per warp, throughput scales with resident warps).
 // One barrier per stage.  Iteration for stage `it` (cell row k, raw rows [y_k+2, y_k+10] in ring slot it&1):
 //   wait full[it&1]
-//   A(k):   gray of the 9 rows -> packed pairs in registers, edge grays -> edge[it&1]
-//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static)
-//   ---- __syncthreads ----  (slot it&1 is now dead: thread 0 issues the TMA of stage it+2 into it)
+//   A(k):   gray of the thread's 4 px in each of the 9 rows -> packed pairs in registers; the four grays of every row
+//           (one word E_r) are parked in the thread's OWN 36 raw bytes of rows 5..7 (dead after the gray loads, never
+//           read by the colour pass) so that neighbours can fetch the box-filter halo after the barrier
+//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static); a lane
+//           pair shares a cell: three rows each, combined with one shuffle
+//   ---- __syncthreads ----   thread 0: TMA of stage it+1 into slot (it+1)&1 (dead since B(k-1)), L2 prefetch of it+2
 //   B(k):   box sums, threshold -> raster[it&1]
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
 template <int NC>
@@ -189,8 +192,10 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const int W = m.width;
     const uint32_t row_bytes = (uint32_t)W * 3u;
+    const uint32_t row_words = row_bytes >> 2;
     const uint32_t stage_bytes = row_bytes * kStageRows;
     const size_t frame_bytes = (size_t)row_bytes * (size_t)m.height;
     const int n_units = n_frames * bands;
@@ -208,9 +213,11 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     for (int i = tid; i < 256; i += kK1Threads) s.adjust[i] = c_adjust[i];
     __syncthreads();
 
-    const int t = tid;                          // owns pixels 8t .. 8t+7 of every row, and cell t of every cell row
-    const bool px_active = (8 * t) < W;
-    const int tl = (t + kConsumers - 1) & (kConsumers - 1), tr = (t + 1) & (kConsumers - 1);
+    const int t = tid;                          // owns pixels 4t .. 4t+3 of every row
+    const int nthr_px = W / kPx;                // threads that own pixels
+    const bool px_active = t < nthr_px;
+    const int tl = (t == 0) ? 0 : t - 1, tr = (t + 1 < nthr_px) ? t + 1 : t;   // halo sources (clamped: frame borders are never used)
+    const int ct = t >> 1, half = t & 1;        // cell of the row shared by the lane pair (2c, 2c+1)
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
     const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
     const int narrow = m.cells_x - 2 * m.corner, last_cell = m.num_cells - 1, first_mid = m.top_cells;
@@ -235,9 +242,9 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     if (tid == 0) {
         cursor_unit(nxt);
         pre = nxt;
-        for (int i = 0; i < 2 && nxt.valid; ++i) {
-            mbar_expect_tx(&s.full_bar[i], stage_bytes);
-            tma_bulk_g2s(s.stage[i], nxt.src, stage_bytes, &s.full_bar[i]);
+        if (nxt.valid) {
+            mbar_expect_tx(&s.full_bar[0], stage_bytes);
+            tma_bulk_g2s(s.stage[0], nxt.src, stage_bytes, &s.full_bar[0]);
             cursor_next(nxt);
             cursor_next(pre);
         }
@@ -245,32 +252,30 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     }
 
     // symbol stage for one cell row from a finished raster (P5/P6 at drift 0) + the colour decided earlier.
-    // Exact dictionary hits are resolved per thread through the perfect hash; the rare inexact cells (threshold edge
-    // artefacts, ~1 % of a clean frame) are searched one at a time by the whole warp, so no lane waits on a 700-instruction
-    // private search.
+    // A lane pair shares a cell: the even lane extracts hash rows 0-3, the odd lane rows 4-7.  Exact dictionary hits are
+    // resolved through the perfect hash; the rare inexact cells (threshold edge artefacts, ~1 % of a clean frame) are
+    // searched one at a time by the whole warp.
     auto symbol_stage = [&](int k, uint32_t rbuf, uint32_t col, uint8_t* out, bool& any_dirty) {
         int base, ncols, x0;
         cell_row_geom(m, k, base, ncols, x0);
-        const bool active = t < ncols;
+        const bool active = ct < ncols;
         const uint32_t (*rast)[kRastWords] = s.raster[rbuf];
-        const uint32_t o = (uint32_t)(x0 + kSpacing * t);     // window col 1 == pixel x
-        const int cell = base + t;
-        uint32_t sym = 0, dirty = 0;
-        bool exact = true;
+        const uint32_t o = (uint32_t)(x0 + kSpacing * ct);    // window col 1 == pixel x
+        const int cell = base + ct;
+        uint32_t mine = 0;
         if (active) {
-            uint32_t lo = 0, hi = 0;
+            const uint32_t idx = o >> 5, sh = o & 31u;
+            const int r0 = 1 + 4 * half;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t idx = o >> 5, sh = o & 31u;
-                lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
-                hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
-            }
-            uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
-            exact = (te.x == lo) & (te.y == hi);
-            sym = te.z;
+            for (int q = 0; q < 4; ++q)
+                mine |= (__funnelshift_r(rast[r0 + q][idx], rast[r0 + q][idx + 1], sh) & 0xFFu) << (8 * q);
         }
-        uint32_t need = __ballot_sync(0xffffffffu, !exact);
-        const int lane = tid & 31;
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+        const uint32_t lo = half ? other : mine, hi = half ? mine : other;
+        const uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
+        const bool exact = !active || ((te.x == lo) & (te.y == hi));
+        uint32_t sym = te.z, dirty = 0;
+        uint32_t need = __ballot_sync(0xffffffffu, !exact && half == 0);
         while (need) {
             const int leader = __ffs(need) - 1;
             need &= need - 1;
@@ -285,7 +290,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 if (((key >> 4) & 15u) != 0u) { dirty = kCellDirty; any_dirty = true; }   // order index 0 == centre hash (id 4)
             }
         }
-        if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
+        if (active && half == 0) out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
     };
 
     uint32_t it = 0;
@@ -294,109 +299,126 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
         int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
         uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells;
 
-        uint32_t hprev[5][4], Pprev[2][4], nV[4];
+        uint32_t hprev[5][2], Pprev[2][2], nV[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             nV[j] = kBias;
 #pragma unroll
             for (int i = 0; i < 5; ++i) hprev[i][j] = 0;
             Pprev[0][j] = Pprev[1][j] = 0;
         }
-        uint32_t carryR = 0, carryG = 0, carryB = 0;   // colour sums of row y+1 of the upcoming cell row
-        uint32_t col_prev = 0;                         // colour of this thread's cell in the row whose symbols are pending
+        uint32_t carryR = 0, carryG = 0, carryB = 0;   // (even lanes) colour sums of row y+1 of the upcoming cell row
+        uint32_t col_prev = 0;                         // colour of this lane pair's cell in the row whose symbols are pending
         bool any_dirty = false;
 
         for (int k = k0 - 1; k < k1; ++k, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            const uint8_t* sb = s.stage[buf];
+            uint8_t* sb = s.stage[buf];
+            uint32_t* sw = reinterpret_cast<uint32_t*>(sb);
             mbar_wait(&s.full_bar[buf], ph);
 
-            // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+4]); edge bytes (g0,g1,g6,g7)
-            uint32_t P[kStageRows][4];
-            if (px_active) {
+            // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+2]); E_r = (g0,g1,g2,g3)
+            uint32_t P[kStageRows][2];
+            {   // (threads beyond the row width of the narrower modes compute on in-bounds garbage; only their stores are masked)
+                uint32_t E[kStageRows];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    const uint2* rp = reinterpret_cast<const uint2*>(sb + (uint32_t)r * row_bytes) + 3 * t;
-                    uint2 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-                    uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
-                    n0 = __dp2a_lo(cRG, q0.x, 32768u); n0 = __dp2a_hi(cB0, q0.x, n0);
-                    n1 = __dp2a_hi(c0R, q0.x, 32768u); n1 = __dp2a_lo(cGB, q0.y, n1);
-                    n2 = __dp2a_hi(cRG, q0.y, 32768u); n2 = __dp2a_lo(cB0, q1.x, n2);
-                    n3 = __dp2a_lo(c0R, q1.x, 32768u); n3 = __dp2a_hi(cGB, q1.x, n3);
-                    n4 = __dp2a_lo(cRG, q1.y, 32768u); n4 = __dp2a_hi(cB0, q1.y, n4);
-                    n5 = __dp2a_hi(c0R, q1.y, 32768u); n5 = __dp2a_lo(cGB, q2.x, n5);
-                    n6 = __dp2a_hi(cRG, q2.x, 32768u); n6 = __dp2a_lo(cB0, q2.y, n6);
-                    n7 = __dp2a_lo(c0R, q2.y, 32768u); n7 = __dp2a_hi(cGB, q2.y, n7);
-                    P[r][0] = __byte_perm(n0, n4, 0x7632); P[r][1] = __byte_perm(n1, n5, 0x7632);
-                    P[r][2] = __byte_perm(n2, n6, 0x7632); P[r][3] = __byte_perm(n3, n7, 0x7632);
-                    // gray is byte 2 of each numerator: E = (g0, g1, g6, g7)
-                    s.edge[buf][r][t] = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n6, n7, 0x6200), 0x7610);
+                    const uint32_t* rp = sw + (uint32_t)r * row_words + 3 * t;
+                    uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
+                    uint32_t n0, n1, n2, n3;
+                    n0 = __dp2a_lo(cRG, w0, 32768u); n0 = __dp2a_hi(cB0, w0, n0);
+                    n1 = __dp2a_hi(c0R, w0, 32768u); n1 = __dp2a_lo(cGB, w1, n1);
+                    n2 = __dp2a_hi(cRG, w1, 32768u); n2 = __dp2a_lo(cB0, w2, n2);
+                    n3 = __dp2a_lo(c0R, w2, 32768u); n3 = __dp2a_hi(cGB, w2, n3);
+                    P[r][0] = __byte_perm(n0, n2, 0x7632);         // gray = byte 2 of the numerator
+                    P[r][1] = __byte_perm(n1, n3, 0x7632);
+                    E[r] = __byte_perm(P[r][0], P[r][1], 0x6240);
                 }
-            } else {
+                // park E_0..E_8 in this thread's own (already consumed) raw words of rows 5, 6, 7
+                if (px_active) {
 #pragma unroll
-                for (int r = 0; r < kStageRows; ++r) { P[r][0] = P[r][1] = P[r][2] = P[r][3] = 0; }
+                    for (int r = 0; r < kStageRows; ++r) sw[(uint32_t)(5 + r / 3) * row_words + 3 * t + (r % 3)] = E[r];
+                }
             }
 
-            // ---------------- col(k): inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
+            // ---------------- col(k): inner 6x6 = rows y+1..y+6, px x+1..x+6.  even lane: row y+1 (carried from the
+            // previous stage) + stage rows 0,1 and next row's carry (stage row 8); odd lane: stage rows 2,3,4.
             uint32_t col = 0;
             {
                 int base, ncols, x0;
+                uint32_t R = 0, G = 0, B = 0;
+                bool cact = false;
                 if (k >= k0) {
                     cell_row_geom(m, k, base, ncols, x0);
-                    if (t < ncols && NC > 1) {
-                        const int x = x0 + kSpacing * t;
-                        uint32_t R = carryR, G = carryG, B = carryB;
-#pragma unroll
-                        for (int r = 0; r < 5; ++r) rgb_row6(sb + (uint32_t)r * row_bytes, x + 1, R, G, B);
-                        col = best_color<NC>(s.adjust, m, R / 36u, G / 36u, B / 36u);
+                    cact = (ct < ncols) && NC > 1;
+                    if (cact) {
+                        const int x = x0 + kSpacing * ct + 1;
+                        if (half == 0) {
+                            R = carryR; G = carryG; B = carryB;
+                            rgb_row6(sb, x, R, G, B);
+                            rgb_row6(sb + row_bytes, x, R, G, B);
+                        } else {
+                            rgb_row6(sb + 2u * row_bytes, x, R, G, B);
+                            rgb_row6(sb + 3u * row_bytes, x, R, G, B);
+                            rgb_row6(sb + 4u * row_bytes, x, R, G, B);
+                        }
                     }
                 }
-                carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
-                if (k + 1 < k1) {
+                carryR = carryG = carryB = 0;
+                if (k + 1 < k1 && half == 0) {
                     cell_row_geom(m, k + 1, base, ncols, x0);
-                    if (t < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                    if (ct < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * ct + 1, carryR, carryG, carryB);
+                }
+                // pack the three sums (each <= 6*6*255 < 2^14) into one shuffle
+                uint32_t packed = R | (G << 16);
+                uint32_t op = __shfl_xor_sync(0xffffffffu, packed, 1);
+                uint32_t ob = __shfl_xor_sync(0xffffffffu, B, 1);
+                if (cact) {
+                    R = (packed & 0xFFFFu) + (op & 0xFFFFu); G = (packed >> 16) + (op >> 16); B += ob;
+                    col = best_color<NC>(s.adjust, m, R / 36u, G / 36u, B / 36u);
                 }
             }
             __syncthreads();
             if (tid == 0) {
-                if (nxt.valid) {   // slot `buf` is dead (all threads are past their reads of it): refill with stage it+2
-                    mbar_expect_tx(&s.full_bar[buf], stage_bytes);
-                    tma_bulk_g2s(s.stage[buf], nxt.src, stage_bytes, &s.full_bar[buf]);
+                // slot buf^1 held stage it-1: its last readers (B(k-1): parked halo words) finished before this barrier
+                if (nxt.valid) {
+                    mbar_expect_tx(&s.full_bar[buf ^ 1u], stage_bytes);
+                    tma_bulk_g2s(s.stage[buf ^ 1u], nxt.src, stage_bytes, &s.full_bar[buf ^ 1u]);
                     cursor_next(nxt);
                 }
                 if (l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
             }
 
             // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
-            if (px_active) {
+            {
                 uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[buf][0][0]);
                 const uint8_t* prev8 = reinterpret_cast<const uint8_t*>(&s.raster[buf ^ 1u][0][0]);
-                rast8[t] = prev8[9 * kRastPitch + t];
-                uint32_t h[kStageRows][4];
+                const bool rstore = px_active && half == 0;
+                if (rstore) rast8[ct] = prev8[9 * kRastPitch + ct];
+                uint32_t h[kStageRows][2];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    uint32_t lE = s.edge[buf][r][tl], rE = s.edge[buf][r][tr];
-                    uint32_t Pm2 = __byte_perm(lE, P[r][2], 0x5452), Pm1 = __byte_perm(lE, P[r][3], 0x5453);
-                    uint32_t P4 = __byte_perm(P[r][0], rE, 0x3432), P5 = __byte_perm(P[r][1], rE, 0x3532);
-                    h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P[r][2];
-                    h[r][1] = h[r][0] - Pm2 + P[r][3];
-                    h[r][2] = h[r][1] - Pm1 + P4;
-                    h[r][3] = h[r][2] - P[r][0] + P5;
-                    uint32_t tj[4];
+                    const uint32_t eoff = (uint32_t)(5 + r / 3) * row_words + (r % 3);
+                    uint32_t lE = sw[eoff + 3 * tl], rE = sw[eoff + 3 * tr];
+                    uint32_t Pm2 = __byte_perm(lE, P[r][0], 0x5452), Pm1 = __byte_perm(lE, P[r][1], 0x5453);
+                    uint32_t P2 = __byte_perm(P[r][0], rE, 0x3432), P3 = __byte_perm(P[r][1], rE, 0x3532);
+                    h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P2;
+                    h[r][1] = h[r][0] - Pm2 + P3;
+                    uint32_t tj[2];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 2; ++j) {
                         uint32_t hold = (r < 5) ? hprev[r][j] : h[r - 5][j];
                         nV[j] = nV[j] + hold - h[r][j];
                         uint32_t Pc = (r < 2) ? Pprev[r][j] : P[r - 2][j];
                         tj[j] = 25u * Pc + nV[j];             // bit15 / bit31 = (25 g > boxsum + 12)
                     }
-                    uint32_t byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
-                                    ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
-                    byte = (byte | (byte >> 12)) & 0xFFu;
-                    rast8[(r + 1) * kRastPitch + t] = (uint8_t)byte;
+                    uint32_t wv = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u);
+                    uint32_t nib = (wv | (wv >> 14)) & 0xFu;  // px 0..3 of this thread
+                    uint32_t onib = __shfl_down_sync(0xffffffffu, nib, 1);
+                    if (rstore) rast8[(r + 1) * kRastPitch + ct] = (uint8_t)(nib | (onib << 4));
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) hprev[i][j] = h[4 + i][j];
                     Pprev[0][j] = P[7][j]; Pprev[1][j] = P[8][j];
