@@ -157,7 +157,8 @@ struct cb200_ctx {
     uint16_t* d_inv = nullptr;       // num_cells: cell -> slot (Interleave::interleave_reverse)
     uint8_t* d_gen = nullptr;        // RS generator polynomial, ecc_bytes+1 coefficients
     // per-kernel timing (cb200_set_timing): events around every launch of the last pipeline call
-    int l2_ahead = 4;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)
+    int l2_ahead = 2;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)
+    int k1_ctas_per_sm = 4;          // K1: resident CTAs per SM the grid is sized for (CB200_K1_CTAS_PER_SM, tuning only)
     bool timing = false;
     static constexpr int kEvSets = 64;
     cudaEvent_t ev[kEvSets][8] = {};
@@ -206,7 +207,7 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
     mark(c);                                   // ev0: before K1
     if (!sharpen) {
         // bands: whole frames when there are enough of them to fill the machine, else split frames into bands of cell rows
-        int ctas = c->sm_count * 3;
+        int ctas = c->sm_count * c->k1_ctas_per_sm;
         int bands = 1;
         if (n < ctas) { bands = (ctas + n - 1) / n; if (bands > m.cells_y / 4) bands = m.cells_y / 4; if (bands < 1) bands = 1; }
         int units = n * bands;
@@ -263,6 +264,7 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
     const Mode& m = c->mode;
     c->device = device; c->max_frames = max_frames;
     if (const char* e = getenv("CB200_K1_L2_AHEAD")) c->l2_ahead = atoi(e);
+    if (const char* e = getenv("CB200_K1_CTAS_PER_SM")) c->k1_ctas_per_sm = atoi(e);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
     if (prop.major < 10) { delete c; return fail(CB200_ERR_NODEVICE, "libcb200 is built for sm_100a only"); }

@@ -11,8 +11,8 @@
 // centre hash wins for every cell.  A cell where it does not sets bit 7 of its result
 // byte and the frame's dirty flag; such frames are re-done by the exact flood-walk kernel (k1x_flood.cu).
 //
-// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 3 CTAs/SM):
-//   HBM --cp.async.bulk (TMA, 9 full-width rows = 27 KB per stage, 2 stages, mbarrier full/empty)--> smem
+// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 4 CTAs/SM):
+//   HBM --cp.async.bulk (TMA, 3 full-width rows = 9 KB per copy, ring of 15 rows, one mbarrier per 9-row stage)--> smem
 //   phase A: 8 px/thread: gray = (19596R+38470G+7470B+32768)>>16 via 2x IDP.2A per px, packed 2x16 bit
 //   phase B: separable 5x5 box sum in packed-16 SIMD (5 IADD3 + 4 PRMT per 8 px), rolling vertical sum in
 //            registers, threshold 25*g > sum+12 as ONE IMAD per pixel pair, 1-bit raster row -> smem
@@ -26,15 +26,16 @@
 
 namespace cb200 {
 
-constexpr int kPx = 4;                     // pixels per thread and row
-constexpr int kK1Threads = 256;            // 256 threads x 4 px = one full 1024-px row
-constexpr int kStageRows = 9;
+constexpr int kK1Threads = 128;            // 128 threads x 8 px = one full 1024-px row
+constexpr int kStageRows = 9;              // raw rows per cell row (stage)
+constexpr int kUnitRows = 3;               // TMA granularity: one ring unit = 3 raw rows
+constexpr int kRingUnits = 5;              // 15 rows of ring: a stage occupies 3 consecutive units (mod 5)
 constexpr int kMaxW = 1024;
 constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
 constexpr int kRastWords = kRastPitch / 4;
 
 struct __align__(128) K1Smem {
-    uint8_t stage[2][kStageRows * kMaxW * 3];
+    uint8_t ring[kRingUnits][kUnitRows * kMaxW * 3];   // raw RGB rows, filled by TMA
     uint32_t raster[2][10][kRastWords];       // 1-bit threshold rows of the current / previous stage
     uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
@@ -173,29 +174,31 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// 256 threads, 3 CTAs/SM (24 warps/SM: the kernel is latency-bound per warp, throughput scales with resident warps).
-// One barrier per stage.  Iteration for stage `it` (cell row k, raw rows [y_k+2, y_k+10] in ring slot it&1):
+// 128 threads (8 px each), 4 CTAs/SM.  The kernel is latency-bound per warp (no pipe is saturated; throughput scales
+// linearly with resident CTAs), so shared memory per CTA is kept to ~50 KB: the raw rows live in a ring of five 3-row
+// units (a 9-row stage = 3 consecutive units mod 5), and the box-filter halo words are parked in raw words that are
+// already dead instead of in a separate exchange buffer.
+// One barrier per stage.  Iteration for stage `it` (cell row k, raw rows [y_k+2, y_k+10]):
 //   wait full[it&1]
-//   A(k):   gray of the thread's 4 px in each of the 9 rows -> packed pairs in registers; the four grays of every row
-//           (one word E_r) are parked in the thread's OWN 36 raw bytes of rows 5..7 (dead after the gray loads, never
-//           read by the colour pass) so that neighbours can fetch the box-filter halo after the barrier
-//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static); a lane
-//           pair shares a cell: three rows each, combined with one shuffle
-//   ---- __syncthreads ----   thread 0: TMA of stage it+1 into slot (it+1)&1 (dead since B(k-1)), L2 prefetch of it+2
+//   A(k):   gray of the thread's 8 px in each of the 9 rows -> packed pairs in registers; one halo word E_r per row
+//           (bytes g0,g1,g6,g7) is parked in the thread's OWN raw words of stage rows 5..7 (consumed by then, and
+//           never read by the colour pass)
+//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static)
+//   ---- __syncthreads ----   thread 0: TMA of stage it+1 (its 3 units land on stage it-1's units 1,2 and stage it's
+//                             unit 0, all dead now), L2 prefetch further ahead
 //   B(k):   box sums, threshold -> raster[it&1]
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
 template <int NC>
-__global__ void __launch_bounds__(kK1Threads, 3)
+__global__ void __launch_bounds__(kK1Threads, 4)
 k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
     const int W = m.width;
     const uint32_t row_bytes = (uint32_t)W * 3u;
-    const uint32_t row_words = row_bytes >> 2;
+    const uint32_t unit_bytes = row_bytes * kUnitRows;
     const uint32_t stage_bytes = row_bytes * kStageRows;
     const size_t frame_bytes = (size_t)row_bytes * (size_t)m.height;
     const int n_units = n_frames * bands;
@@ -213,11 +216,10 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     for (int i = tid; i < 256; i += kK1Threads) s.adjust[i] = c_adjust[i];
     __syncthreads();
 
-    const int t = tid;                          // owns pixels 4t .. 4t+3 of every row
-    const int nthr_px = W / kPx;                // threads that own pixels
+    const int t = tid;                          // owns pixels 8t .. 8t+7 of every row, and cell t of every cell row
+    const int nthr_px = W / 8;
     const bool px_active = t < nthr_px;
-    const int tl = (t == 0) ? 0 : t - 1, tr = (t + 1 < nthr_px) ? t + 1 : t;   // halo sources (clamped: frame borders are never used)
-    const int ct = t >> 1, half = t & 1;        // cell of the row shared by the lane pair (2c, 2c+1)
+    const int tl = (t == 0) ? 0 : t - 1, tr = (t + 1 < nthr_px) ? t + 1 : t;   // halo sources (frame borders are never used)
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
     const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
     const int narrow = m.cells_x - 2 * m.corner, last_cell = m.num_cells - 1, first_mid = m.top_cells;
@@ -237,45 +239,52 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
         c.u += gridDim.x;
         cursor_unit(c);
     };
+    // stage `i` occupies ring units (3i, 3i+1, 3i+2) mod 5; one mbarrier transaction covers its three bulk copies
+    auto issue_stage = [&](const Cursor& c, uint32_t i) {
+        unsigned long long* bar = &s.full_bar[i & 1u];
+        mbar_expect_tx(bar, stage_bytes);
+        uint32_t p = (3u * i) % kRingUnits;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            tma_bulk_g2s(s.ring[p], c.src + (size_t)q * unit_bytes, unit_bytes, bar);
+            p = (p + 1u == kRingUnits) ? 0u : p + 1u;
+        }
+    };
     Cursor nxt, pre;                              // next stage to load into shared memory / to prefetch into L2
     nxt.u = blockIdx.x; nxt.valid = false; pre.valid = false;
     if (tid == 0) {
         cursor_unit(nxt);
         pre = nxt;
-        if (nxt.valid) {
-            mbar_expect_tx(&s.full_bar[0], stage_bytes);
-            tma_bulk_g2s(s.stage[0], nxt.src, stage_bytes, &s.full_bar[0]);
-            cursor_next(nxt);
-            cursor_next(pre);
-        }
+        if (nxt.valid) { issue_stage(nxt, 0u); cursor_next(nxt); cursor_next(pre); }
         for (int i = 0; i < l2_ahead && pre.valid; ++i) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
     }
 
     // symbol stage for one cell row from a finished raster (P5/P6 at drift 0) + the colour decided earlier.
-    // A lane pair shares a cell: the even lane extracts hash rows 0-3, the odd lane rows 4-7.  Exact dictionary hits are
-    // resolved through the perfect hash; the rare inexact cells (threshold edge artefacts, ~1 % of a clean frame) are
-    // searched one at a time by the whole warp.
+    // Exact dictionary hits are resolved per thread through the perfect hash; the rare inexact cells (threshold edge
+    // artefacts, ~1 % of a clean frame) are searched one at a time by the whole warp.
     auto symbol_stage = [&](int k, uint32_t rbuf, uint32_t col, uint8_t* out, bool& any_dirty) {
         int base, ncols, x0;
         cell_row_geom(m, k, base, ncols, x0);
-        const bool active = ct < ncols;
+        const bool active = t < ncols;
         const uint32_t (*rast)[kRastWords] = s.raster[rbuf];
-        const uint32_t o = (uint32_t)(x0 + kSpacing * ct);    // window col 1 == pixel x
-        const int cell = base + ct;
-        uint32_t mine = 0;
+        const uint32_t o = (uint32_t)(x0 + kSpacing * t);     // window col 1 == pixel x
+        const int cell = base + t;
+        uint32_t sym = 0, dirty = 0;
+        bool exact = true;
         if (active) {
-            const uint32_t idx = o >> 5, sh = o & 31u;
-            const int r0 = 1 + 4 * half;
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                mine |= (__funnelshift_r(rast[r0 + q][idx], rast[r0 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+            for (int q = 0; q < 4; ++q) {
+                uint32_t idx = o >> 5, sh = o & 31u;
+                lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+                hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+            }
+            uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
+            exact = (te.x == lo) & (te.y == hi);
+            sym = te.z;
         }
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-        const uint32_t lo = half ? other : mine, hi = half ? mine : other;
-        const uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
-        const bool exact = !active || ((te.x == lo) & (te.y == hi));
-        uint32_t sym = te.z, dirty = 0;
-        uint32_t need = __ballot_sync(0xffffffffu, !exact && half == 0);
+        uint32_t need = __ballot_sync(0xffffffffu, !exact);
+        const int lane = tid & 31;
         while (need) {
             const int leader = __ffs(need) - 1;
             need &= need - 1;
@@ -290,7 +299,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 if (((key >> 4) & 15u) != 0u) { dirty = kCellDirty; any_dirty = true; }   // order index 0 == centre hash (id 4)
             }
         }
-        if (active && half == 0) out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
+        if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
     };
 
     uint32_t it = 0;
@@ -299,93 +308,87 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
         int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
         uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells;
 
-        uint32_t hprev[5][2], Pprev[2][2], nV[2];
+        uint32_t hprev[5][4], Pprev[2][4], nV[4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
             nV[j] = kBias;
 #pragma unroll
             for (int i = 0; i < 5; ++i) hprev[i][j] = 0;
             Pprev[0][j] = Pprev[1][j] = 0;
         }
-        uint32_t carryR = 0, carryG = 0, carryB = 0;   // (even lanes) colour sums of row y+1 of the upcoming cell row
-        uint32_t col_prev = 0;                         // colour of this lane pair's cell in the row whose symbols are pending
+        uint32_t carryR = 0, carryG = 0, carryB = 0;   // colour sums of row y+1 of the upcoming cell row
+        uint32_t col_prev = 0;                         // colour of this thread's cell in the row whose symbols are pending
         bool any_dirty = false;
 
         for (int k = k0 - 1; k < k1; ++k, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            uint8_t* sb = s.stage[buf];
-            uint32_t* sw = reinterpret_cast<uint32_t*>(sb);
+            // the three ring units of this stage: rows 0-2, 3-5, 6-8
+            const uint32_t p0 = (3u * it) % kRingUnits;
+            const uint32_t p1 = (p0 + 1u == kRingUnits) ? 0u : p0 + 1u;
+            const uint32_t p2 = (p1 + 1u == kRingUnits) ? 0u : p1 + 1u;
+            uint8_t* ub[3] = {s.ring[p0], s.ring[p1], s.ring[p2]};
             mbar_wait(&s.full_bar[buf], ph);
 
-            // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+2]); E_r = (g0,g1,g2,g3)
-            uint32_t P[kStageRows][2];
-            {   // (threads beyond the row width of the narrower modes compute on in-bounds garbage; only their stores are masked)
+            // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+4]); halo word E_r = (g0,g1,g6,g7)
+            uint32_t P[kStageRows][4];
+            {   // (threads beyond the row width of the narrower modes compute on in-bounds garbage; their stores are masked)
                 uint32_t E[kStageRows];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    const uint32_t* rp = sw + (uint32_t)r * row_words + 3 * t;
-                    uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
-                    uint32_t n0, n1, n2, n3;
-                    n0 = __dp2a_lo(cRG, w0, 32768u); n0 = __dp2a_hi(cB0, w0, n0);
-                    n1 = __dp2a_hi(c0R, w0, 32768u); n1 = __dp2a_lo(cGB, w1, n1);
-                    n2 = __dp2a_hi(cRG, w1, 32768u); n2 = __dp2a_lo(cB0, w2, n2);
-                    n3 = __dp2a_lo(c0R, w2, 32768u); n3 = __dp2a_hi(cGB, w2, n3);
-                    P[r][0] = __byte_perm(n0, n2, 0x7632);         // gray = byte 2 of the numerator
-                    P[r][1] = __byte_perm(n1, n3, 0x7632);
-                    E[r] = __byte_perm(P[r][0], P[r][1], 0x6240);
+                    const uint2* rp = reinterpret_cast<const uint2*>(ub[r / 3] + (uint32_t)(r % 3) * row_bytes) + 3 * t;
+                    uint2 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+                    uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
+                    n0 = __dp2a_lo(cRG, q0.x, 32768u); n0 = __dp2a_hi(cB0, q0.x, n0);
+                    n1 = __dp2a_hi(c0R, q0.x, 32768u); n1 = __dp2a_lo(cGB, q0.y, n1);
+                    n2 = __dp2a_hi(cRG, q0.y, 32768u); n2 = __dp2a_lo(cB0, q1.x, n2);
+                    n3 = __dp2a_lo(c0R, q1.x, 32768u); n3 = __dp2a_hi(cGB, q1.x, n3);
+                    n4 = __dp2a_lo(cRG, q1.y, 32768u); n4 = __dp2a_hi(cB0, q1.y, n4);
+                    n5 = __dp2a_hi(c0R, q1.y, 32768u); n5 = __dp2a_lo(cGB, q2.x, n5);
+                    n6 = __dp2a_hi(cRG, q2.x, 32768u); n6 = __dp2a_lo(cB0, q2.y, n6);
+                    n7 = __dp2a_lo(c0R, q2.y, 32768u); n7 = __dp2a_hi(cGB, q2.y, n7);
+                    P[r][0] = __byte_perm(n0, n4, 0x7632); P[r][1] = __byte_perm(n1, n5, 0x7632);
+                    P[r][2] = __byte_perm(n2, n6, 0x7632); P[r][3] = __byte_perm(n3, n7, 0x7632);
+                    // gray is byte 2 of each numerator
+                    E[r] = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n6, n7, 0x6200), 0x7610);
                 }
-                // park E_0..E_8 in this thread's own (already consumed) raw words of rows 5, 6, 7
+                // park E_0..E_8 in this thread's own (already consumed) raw words of stage rows 5, 6, 7
                 if (px_active) {
-#pragma unroll
-                    for (int r = 0; r < kStageRows; ++r) sw[(uint32_t)(5 + r / 3) * row_words + 3 * t + (r % 3)] = E[r];
+                    uint32_t* w5 = reinterpret_cast<uint32_t*>(ub[1] + 2u * row_bytes) + 6 * t;   // stage row 5 = unit 1, row 2
+                    uint32_t* w6 = reinterpret_cast<uint32_t*>(ub[2]) + 6 * t;                    // stage row 6 = unit 2, row 0
+                    uint32_t* w7 = reinterpret_cast<uint32_t*>(ub[2] + row_bytes) + 6 * t;        // stage row 7 = unit 2, row 1
+                    w5[0] = E[0]; w5[1] = E[1]; w5[2] = E[2];
+                    w6[0] = E[3]; w6[1] = E[4]; w6[2] = E[5];
+                    w7[0] = E[6]; w7[1] = E[7]; w7[2] = E[8];
                 }
             }
 
-            // ---------------- col(k): inner 6x6 = rows y+1..y+6, px x+1..x+6.  even lane: row y+1 (carried from the
-            // previous stage) + stage rows 0,1 and next row's carry (stage row 8); odd lane: stage rows 2,3,4.
+            // ---------------- col(k): inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
             uint32_t col = 0;
             {
                 int base, ncols, x0;
-                uint32_t R = 0, G = 0, B = 0;
-                bool cact = false;
                 if (k >= k0) {
                     cell_row_geom(m, k, base, ncols, x0);
-                    cact = (ct < ncols) && NC > 1;
-                    if (cact) {
-                        const int x = x0 + kSpacing * ct + 1;
-                        if (half == 0) {
-                            R = carryR; G = carryG; B = carryB;
-                            rgb_row6(sb, x, R, G, B);
-                            rgb_row6(sb + row_bytes, x, R, G, B);
-                        } else {
-                            rgb_row6(sb + 2u * row_bytes, x, R, G, B);
-                            rgb_row6(sb + 3u * row_bytes, x, R, G, B);
-                            rgb_row6(sb + 4u * row_bytes, x, R, G, B);
-                        }
+                    if (t < ncols && NC > 1) {
+                        const int x = x0 + kSpacing * t + 1;
+                        uint32_t R = carryR, G = carryG, B = carryB;
+                        rgb_row6(ub[0], x, R, G, B);
+                        rgb_row6(ub[0] + row_bytes, x, R, G, B);
+                        rgb_row6(ub[0] + 2u * row_bytes, x, R, G, B);
+                        rgb_row6(ub[1], x, R, G, B);
+                        rgb_row6(ub[1] + row_bytes, x, R, G, B);
+                        col = best_color<NC>(s.adjust, m, R / 36u, G / 36u, B / 36u);
                     }
                 }
-                carryR = carryG = carryB = 0;
-                if (k + 1 < k1 && half == 0) {
+                carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
+                if (k + 1 < k1) {
                     cell_row_geom(m, k + 1, base, ncols, x0);
-                    if (ct < ncols) rgb_row6(sb + 8u * row_bytes, x0 + kSpacing * ct + 1, carryR, carryG, carryB);
-                }
-                // pack the three sums (each <= 6*6*255 < 2^14) into one shuffle
-                uint32_t packed = R | (G << 16);
-                uint32_t op = __shfl_xor_sync(0xffffffffu, packed, 1);
-                uint32_t ob = __shfl_xor_sync(0xffffffffu, B, 1);
-                if (cact) {
-                    R = (packed & 0xFFFFu) + (op & 0xFFFFu); G = (packed >> 16) + (op >> 16); B += ob;
-                    col = best_color<NC>(s.adjust, m, R / 36u, G / 36u, B / 36u);
+                    if (t < ncols) rgb_row6(ub[2] + 2u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
                 }
             }
             __syncthreads();
             if (tid == 0) {
-                // slot buf^1 held stage it-1: its last readers (B(k-1): parked halo words) finished before this barrier
-                if (nxt.valid) {
-                    mbar_expect_tx(&s.full_bar[buf ^ 1u], stage_bytes);
-                    tma_bulk_g2s(s.stage[buf ^ 1u], nxt.src, stage_bytes, &s.full_bar[buf ^ 1u]);
-                    cursor_next(nxt);
-                }
+                // dead now: stage it-1's units 1,2 (their parked halo words were last read in B(k-1)) and this stage's unit 0
+                if (nxt.valid) { issue_stage(nxt, it + 1u); cursor_next(nxt); }
                 if (l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
             }
 
@@ -393,32 +396,36 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
             {
                 uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[buf][0][0]);
                 const uint8_t* prev8 = reinterpret_cast<const uint8_t*>(&s.raster[buf ^ 1u][0][0]);
-                const bool rstore = px_active && half == 0;
-                if (rstore) rast8[ct] = prev8[9 * kRastPitch + ct];
-                uint32_t h[kStageRows][2];
+                if (px_active) rast8[t] = prev8[9 * kRastPitch + t];
+                const uint32_t* e5 = reinterpret_cast<const uint32_t*>(ub[1] + 2u * row_bytes);
+                const uint32_t* e6 = reinterpret_cast<const uint32_t*>(ub[2]);
+                const uint32_t* e7 = reinterpret_cast<const uint32_t*>(ub[2] + row_bytes);
+                uint32_t h[kStageRows][4];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    const uint32_t eoff = (uint32_t)(5 + r / 3) * row_words + (r % 3);
-                    uint32_t lE = sw[eoff + 3 * tl], rE = sw[eoff + 3 * tr];
-                    uint32_t Pm2 = __byte_perm(lE, P[r][0], 0x5452), Pm1 = __byte_perm(lE, P[r][1], 0x5453);
-                    uint32_t P2 = __byte_perm(P[r][0], rE, 0x3432), P3 = __byte_perm(P[r][1], rE, 0x3532);
-                    h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P2;
-                    h[r][1] = h[r][0] - Pm2 + P3;
-                    uint32_t tj[2];
+                    const uint32_t* er = (r < 3) ? e5 : (r < 6 ? e6 : e7);
+                    uint32_t lE = er[6 * tl + (r % 3)], rE = er[6 * tr + (r % 3)];
+                    uint32_t Pm2 = __byte_perm(lE, P[r][2], 0x5452), Pm1 = __byte_perm(lE, P[r][3], 0x5453);
+                    uint32_t P4 = __byte_perm(P[r][0], rE, 0x3432), P5 = __byte_perm(P[r][1], rE, 0x3532);
+                    h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P[r][2];
+                    h[r][1] = h[r][0] - Pm2 + P[r][3];
+                    h[r][2] = h[r][1] - Pm1 + P4;
+                    h[r][3] = h[r][2] - P[r][0] + P5;
+                    uint32_t tj[4];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         uint32_t hold = (r < 5) ? hprev[r][j] : h[r - 5][j];
                         nV[j] = nV[j] + hold - h[r][j];
                         uint32_t Pc = (r < 2) ? Pprev[r][j] : P[r - 2][j];
                         tj[j] = 25u * Pc + nV[j];             // bit15 / bit31 = (25 g > boxsum + 12)
                     }
-                    uint32_t wv = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u);
-                    uint32_t nib = (wv | (wv >> 14)) & 0xFu;  // px 0..3 of this thread
-                    uint32_t onib = __shfl_down_sync(0xffffffffu, nib, 1);
-                    if (rstore) rast8[(r + 1) * kRastPitch + ct] = (uint8_t)(nib | (onib << 4));
+                    uint32_t byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
+                                    ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
+                    byte = (byte | (byte >> 12)) & 0xFFu;
+                    if (px_active) rast8[(r + 1) * kRastPitch + t] = (uint8_t)byte;
                 }
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) hprev[i][j] = h[4 + i][j];
                     Pprev[0][j] = P[7][j]; Pprev[1][j] = P[8][j];
@@ -491,7 +498,7 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k1_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem) + 40 * 1024);
+    e = cudaFuncSetAttribute(k1_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem) + 64 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k1_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
 }
