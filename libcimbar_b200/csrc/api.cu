@@ -157,7 +157,7 @@ struct cb200_ctx {
     uint16_t* d_inv = nullptr;       // num_cells: cell -> slot (Interleave::interleave_reverse)
     uint8_t* d_gen = nullptr;        // RS generator polynomial, ecc_bytes+1 coefficients
     // per-kernel timing (cb200_set_timing): events around every launch of the last pipeline call
-    int l2_ahead = 2;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)
+    int l2_ahead = 0;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)
     int k1_ctas_per_sm = 4;          // K1: resident CTAs per SM the grid is sized for (CB200_K1_CTAS_PER_SM, tuning only)
     bool timing = false;
     static constexpr int kEvSets = 64;
@@ -384,7 +384,7 @@ int cb200_rs_correct_dev(cb200_ctx* c, const uint8_t* d_raw, int n, uint8_t* d_d
     if (!d_raw || !d_data_out) return fail(CB200_ERR_ARG, "null buffer");
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     uint8_t* ok = d_block_ok ? d_block_ok : c->d_ok;
-    CK(k2_rs_launch(c->mode, d_raw, n, d_data_out, ok, c->sm_count * 16, c->stream), "rs launch");
+    CK(k2_rs_launch(c->mode, d_raw, n, d_data_out, ok, c->sm_count, c->stream), "rs launch");
     return CB200_OK;
 }
 
@@ -395,9 +395,8 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
     if (!d_rgb || !d_chunks || !d_chunk_mask) return fail(CB200_ERR_ARG, "null buffer");
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
-    CK(k2_pack_launch(c->mode, c->d_cellvals, c->d_idx, n, c->d_raw, c->stream), "pack launch");
-    mark(c);                                   // ev3: after pack
-    CK(k2_rs_launch(c->mode, c->d_raw, n, d_chunks, c->d_ok, c->sm_count * 16, c->stream), "rs launch");
+    mark(c);                                   // ev3: (no separate pack kernel on this path: the RS kernel gathers from the cell bytes)
+    CK(k2_rs_fused_launch(c->mode, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream), "rs launch");
     mark(c);                                   // ev4: after RS
     CK(k2_mask_launch(c->mode, c->d_ok, n, d_chunk_mask, c->stream), "mask launch");
     mark(c);                                   // ev5: after chunk mask

@@ -18,7 +18,6 @@
 
 namespace cb200 {
 
-constexpr int kRsWarps = 4;
 constexpr int kMaxParity = 64;
 
 __constant__ uint8_t c_gf_exp[512];
@@ -69,17 +68,22 @@ k_pack_raw(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* _
 }
 
 // ---------------------------------------------------------------------------------------------- GF(256) helpers
+constexpr int kRsWarpsPerCta = 16;
+
 struct RsSmem {
     uint8_t exp[512];
     uint8_t log[256];
     struct PerWarp {
-        uint8_t enc[256];
+        alignas(4) uint8_t enc[256];
         uint8_t synd[kMaxParity];
         uint8_t loc[kMaxParity + 8];
         uint8_t last[kMaxParity + 8];
         uint8_t omega[kMaxParity];
         uint8_t roots[kMaxParity + 8];
-    } w[kRsWarps];
+    } w[kRsWarpsPerCta];
+    // followed in dynamic shared memory by the syndrome multiplier table: uint32 mt[256][32*T],
+    // mt[x][j] = x * alpha^(j+1).  One 32-bit word per (x, lane): lane j always reads bank j, so the Horner step
+    // `acc = mt[acc][lane] ^ byte` is a conflict-free LDS instead of two conflicting log/exp lookups.
 };
 
 __device__ __forceinline__ uint32_t gf_mul(const RsSmem& s, uint32_t a, uint32_t b)
@@ -100,43 +104,70 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 }
 
 // ---------------------------------------------------------------------------------------------- RS decode
-// one warp per block; raw: n_frames * cap_all bytes (symbol stream blocks then colour stream blocks);
+// one warp per block.  FUSED: the block's bytes are gathered straight from K1's per-cell bytes through the interleave
+// map (P7/P10 bit packing folded in); otherwise they are read from a packed raw stream (n_frames * cap_all bytes,
+// symbol stream blocks then colour stream blocks).
 // data_out: n_frames * nblocks * msg_len (zeros for failed blocks, reed_solomon_stream.h:96-107); ok: n_frames * nblocks
-__global__ void __launch_bounds__(kRsWarps * 32)
-k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, int n_frames, uint8_t* __restrict__ data_out,
-            uint8_t* __restrict__ block_ok)
+template <int T, bool FUSED>
+__global__ void __launch_bounds__(kRsWarpsPerCta * 32)
+k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __restrict__ cellvals, const uint16_t* __restrict__ idx,
+            int n_frames, uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok)
 {
-    __shared__ RsSmem s;
+    extern __shared__ __align__(16) uint8_t rs_smem_raw[];
+    RsSmem& s = *reinterpret_cast<RsSmem*>(rs_smem_raw);
+    uint32_t* mt = reinterpret_cast<uint32_t*>(rs_smem_raw + ((sizeof(RsSmem) + 127) & ~size_t(127)));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 512; i += blockDim.x) s.exp[i] = c_gf_exp[i];
     for (int i = tid; i < 256; i += blockDim.x) s.log[i] = c_gf_log[i];
+    for (int e = tid; e < 256 * 32 * T; e += blockDim.x) {
+        int x = e / (32 * T), j = e - x * (32 * T);
+        mt[e] = x ? (uint32_t)c_gf_exp[(uint32_t)c_gf_log[x] + (uint32_t)(j + 1)] : 0u;   // j+1 <= 64: index < 512
+    }
     __syncthreads();
 
     const int md = m.ecc_bytes, blk = m.ecc_block, msg_len = m.msg_len;
     const long total_blocks = (long)n_frames * m.nblocks;
     RsSmem::PerWarp& w = s.w[warp];
 
-    for (long gb = (long)blockIdx.x * kRsWarps + warp; gb < total_blocks; gb += (long)gridDim.x * kRsWarps) {
+    for (long gb = (long)blockIdx.x * kRsWarpsPerCta + warp; gb < total_blocks; gb += (long)gridDim.x * kRsWarpsPerCta) {
         const int f = (int)(gb / m.nblocks), b = (int)(gb - (long)f * m.nblocks);
-        // Symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
-        // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks.
-        const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
         uint8_t* out = data_out + ((size_t)f * m.nblocks + b) * msg_len;
         __syncwarp();
-        for (int i = lane; i < blk; i += 32) w.enc[i] = enc_g[i];
+        if (FUSED) {
+            const uint8_t* cells = cellvals + (size_t)f * m.num_cells;
+            for (int i = lane; i < blk; i += 32) {
+                uint32_t B = (uint32_t)b * (uint32_t)blk + (uint32_t)i, v;
+                if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
+                else if ((int)B < m.cap_sym) v = stream_byte(cells, idx, B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
+                else v = stream_byte(cells, idx, B - (uint32_t)m.cap_sym, m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
+                w.enc[i] = (uint8_t)v;
+            }
+        } else {
+            // symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
+            // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks
+            const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
+            for (int i = lane; i < blk; i += 32) w.enc[i] = enc_g[i];
+        }
         __syncwarp();
 
         // ---- syndromes S_j = r(alpha^(j+1)), Horner from the highest coefficient = enc[0]  (decode.c:12-28)
         uint32_t nz = 0;
-        for (int j = lane; j < md; j += 32) {
+#pragma unroll
+        for (int q = 0; q < T; ++q) {
+            const uint32_t* col = mt + lane + 32 * q;
             uint32_t acc = 0;
-            const uint32_t lg = (uint32_t)(j + 1);
-            for (int i = 0; i < blk; ++i) {
-                uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + lg] : 0u;
-                acc = t ^ w.enc[i];
+            const uint32_t* ew = reinterpret_cast<const uint32_t*>(w.enc);
+            int i = 0;
+            for (; i + 4 <= blk; i += 4) {               // four Horner steps per 32-bit load of the block
+                const uint32_t wd = ew[i >> 2];
+                acc = col[acc * (32 * T)] ^ (wd & 0xFFu);
+                acc = col[acc * (32 * T)] ^ ((wd >> 8) & 0xFFu);
+                acc = col[acc * (32 * T)] ^ ((wd >> 16) & 0xFFu);
+                acc = col[acc * (32 * T)] ^ (wd >> 24);
             }
-            w.synd[j] = (uint8_t)acc;
-            nz |= acc;
+            for (; i < blk; ++i) acc = col[acc * (32 * T)] ^ w.enc[i];
+            const int j = lane + 32 * q;
+            if (j < md) { w.synd[j] = (uint8_t)acc; nz |= acc; }
         }
         nz = __ballot_sync(0xffffffffu, nz != 0);
         __syncwarp();
@@ -289,14 +320,37 @@ cudaError_t k2_pack_launch(const Mode& m, const uint8_t* d_cellvals, const uint1
     return cudaGetLastError();
 }
 
-cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint8_t* d_data, uint8_t* d_ok, int max_ctas, cudaStream_t st)
+template <int T, bool FUSED>
+static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames,
+                               uint8_t* d_data, uint8_t* d_ok, int sm_count, cudaStream_t st)
 {
+    const size_t smem = ((sizeof(RsSmem) + 127) & ~size_t(127)) + sizeof(uint32_t) * 256 * 32 * T;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_rs_decode<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     long total = (long)n_frames * m.nblocks;
-    long ctas = (total + kRsWarps - 1) / kRsWarps;
+    long ctas = (total + kRsWarpsPerCta - 1) / kRsWarpsPerCta;
+    long max_ctas = (long)sm_count * (T == 1 ? 4 : 2);       // persistent: the table build is amortised over many blocks
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    k_rs_decode<<<(int)ctas, kRsWarps * 32, 0, st>>>(m, d_raw, n_frames, d_data, d_ok);
+    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, d_data, d_ok);
     return cudaGetLastError();
+}
+
+cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint8_t* d_data, uint8_t* d_ok, int sm_count, cudaStream_t st)
+{
+    if (m.ecc_bytes <= 32) return rs_launch_t<1, false>(m, d_raw, nullptr, nullptr, n_frames, d_data, d_ok, sm_count, st);
+    return rs_launch_t<2, false>(m, d_raw, nullptr, nullptr, n_frames, d_data, d_ok, sm_count, st);
+}
+
+cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_data,
+                               uint8_t* d_ok, int sm_count, cudaStream_t st)
+{
+    if (m.ecc_bytes <= 32) return rs_launch_t<1, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st);
+    return rs_launch_t<2, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st);
 }
 
 cudaError_t k2_mask_launch(const Mode& m, const uint8_t* d_ok, int n_frames, uint32_t* d_mask, cudaStream_t st)
