@@ -112,6 +112,22 @@ int cb200_decode(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint
 int cb200_decode_fountain(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* chunks_out,
                           uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
 
+/* per-cell record of the exact flood walk: what CimbReader::read() hands back, step by step
+   (src/lib/cimb_translator/CimbReader.cpp:139-162, PositionData.h:4-9) */
+typedef struct cb200_cell_trace {
+    uint16_t order;        /* position of this cell in the walk order (0 = first read) */
+    int16_t  x, y;         /* drift-adjusted position = PositionData.x / .y */
+    uint8_t  drift_offset; /* winning hash id 0..8, 4 = centre */
+    uint8_t  distance;     /* best Hamming distance */
+} cb200_cell_trace;
+
+/* Replaces: the loop `while (!reader.done()) reader.read(pos)` + `reader.read_color(pos)` of a CimbReader
+   (CimbReader.cpp:133-162), always through the exact flood-walk kernel.  Host pointers.
+   cellvals_out: n * total_cells bytes (symbol | colour << symbol_bits, linear cell index);
+   trace_out: n * total_cells records indexed by cell. */
+int cb200_decode_cells(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* cellvals_out,
+                       cb200_cell_trace* trace_out);
+
 /* ---- single-cell entry points (CimbDecoder API parity; run one tiny kernel) ------------------------------------- */
 
 /* Replaces: CimbDecoder::decode_symbol(const bitmatrix&, drift_offset, best_distance, cooldown)
@@ -141,6 +157,31 @@ int cb200_encode_cells_dev(cb200_ctx* ctx, const uint8_t* d_payload, int n, uint
    order: [0] K1 fused decode, [1] K1x exact-walk kernel, [2] pack, [3] RS, [4] chunk mask (decode_raw_dev stops after [2]) */
 int cb200_set_timing(cb200_ctx* ctx, int enable);
 int cb200_get_timing(cb200_ctx* ctx, int calls_back, float* ms, int max_entries, int* n_entries);
+
+/* ---- rank-0 fountain ingest (host only, no GPU) ------------------------------------------------------------------
+
+   Replaces: fountain_decoder_sink::decode_frame -> fountain_decoder_stream::write -> FountainDecoder::decode
+   (src/lib/fountain/fountain_decoder_sink.h:133-166, fountain_decoder_stream.h:45-79, FountainDecoder.h:48-60) and the
+   FountainMetadata header parse (FountainMetadata.h:16-90).  The fountain codec is wirehair and stays what it is in the
+   reference: the four callbacks have wirehair's C API signatures (wirehair_decoder_create, wirehair_decode,
+   wirehair_recover, wirehair_free), so an integrated build passes those symbols. */
+typedef struct cb200_sink cb200_sink;
+typedef void* (*cb200_codec_create_fn)(void* reuse, uint64_t message_bytes, uint32_t block_bytes);
+typedef int (*cb200_codec_decode_fn)(void* codec, unsigned block_id, const void* block_data, uint32_t data_bytes);
+typedef int (*cb200_codec_recover_fn)(void* codec, void* message_out, uint64_t message_bytes);
+typedef void (*cb200_codec_free_fn)(void* codec);
+
+cb200_sink* cb200_sink_create(unsigned chunk_size, cb200_codec_create_fn create_fn, cb200_codec_decode_fn decode_fn,
+                              cb200_codec_recover_fn recover_fn, cb200_codec_free_fn free_fn);
+void cb200_sink_destroy(cb200_sink* sink);
+/* one chunk (6-byte header + payload): > 0 = file id (encode_id|size word) when the file completed, 0 = progress,
+   -1 = already done, -10/-11/-12 = malformed (same values as the reference) */
+int64_t cb200_sink_decode_frame(cb200_sink* sink, const uint8_t* chunk, unsigned size);
+/* the fixed-slot output of cb200_decode_chunks_dev (or the records gathered from all ranks): feeds every chunk whose
+   mask bit is set; returns the last completed file id or 0 */
+int64_t cb200_sink_ingest(cb200_sink* sink, const uint8_t* chunks, const uint32_t* masks, int n_frames, int chunks_per_frame);
+int64_t cb200_sink_file_size(const cb200_sink* sink, uint32_t id);                     /* -1 if not complete */
+int cb200_sink_file_read(const cb200_sink* sink, uint32_t id, uint8_t* out, uint64_t size);
 
 /* ---- host-side helpers that need no GPU ------------------------------------------------------------------------ */
 

@@ -20,7 +20,9 @@ EXPORTS = [
     "cb200_last_error", "cb200_version", "cb200_create", "cb200_destroy", "cb200_get_info", "cb200_set_stream",
     "cb200_sync", "cb200_decode_raw_dev", "cb200_rs_correct_dev", "cb200_decode_chunks_dev", "cb200_decode_raw",
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
-    "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing",
+    "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
+    "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
+    "cb200_sink_file_read",
 ]
 
 
@@ -29,6 +31,9 @@ class Info(C.Structure):
         "mode_val", "image_size_x", "image_size_y", "frame_bytes", "total_cells", "symbol_bits", "color_bits",
         "raw_bytes", "raw_symbol_bytes", "ecc_bytes", "ecc_block_size", "rs_blocks", "data_bytes", "chunk_size",
         "chunks_per_frame", "legacy_mode", "max_frames", "sm_count")]
+
+
+TRACE_DTYPE = np.dtype([("order", "<u2"), ("x", "<i2"), ("y", "<i2"), ("drift_offset", "u1"), ("distance", "u1")])
 
 
 class Cb200Error(RuntimeError):
@@ -60,12 +65,23 @@ def load_library():
     lib.cb200_decode_raw.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u8p]
     lib.cb200_decode.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u8p, u8p]
     lib.cb200_decode_fountain.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u32p, u32p, u8p]
+    lib.cb200_decode_cells.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, vp]
     lib.cb200_decode_symbols.argtypes = [vp, u16p, u8p, C.c_int, u8p, u8p, u8p]
     lib.cb200_best_colors.argtypes = [vp, u8p, C.c_int, u8p]
     lib.cb200_render_frames_dev.argtypes = [vp, u8p, C.c_int, u8p]
     lib.cb200_encode_cells_dev.argtypes = [vp, u8p, C.c_int, u8p]
     lib.cb200_set_timing.argtypes = [vp, C.c_int]
     lib.cb200_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
+    lib.cb200_sink_create.restype = vp
+    lib.cb200_sink_create.argtypes = [C.c_uint, vp, vp, vp, vp]
+    lib.cb200_sink_destroy.argtypes = [vp]
+    lib.cb200_sink_decode_frame.restype = C.c_int64
+    lib.cb200_sink_decode_frame.argtypes = [vp, u8p, C.c_uint]
+    lib.cb200_sink_ingest.restype = C.c_int64
+    lib.cb200_sink_ingest.argtypes = [vp, u8p, u32p, C.c_int, C.c_int]
+    lib.cb200_sink_file_size.restype = C.c_int64
+    lib.cb200_sink_file_size.argtypes = [vp, C.c_uint32]
+    lib.cb200_sink_file_read.argtypes = [vp, C.c_uint32, u8p, C.c_uint64]
     lib.cb200_mode_info.argtypes = [C.c_int, C.POINTER(Info)]
     lib.cb200_interleave_indices.argtypes = [C.c_int, u16p]
     _lib = lib
@@ -156,6 +172,14 @@ class Context:
                                               mask.ctypes.data, ff.ctypes.data))
         return chunks, count, mask, ff
 
+    def decode_cells(self, rgb, flags=0):
+        """exact flood walk with per-cell trace (order, x, y, drift_offset, distance) -- CimbReader semantics"""
+        rgb, n = self._frames(rgb)
+        cells = np.zeros((n, self.info.total_cells), dtype=np.uint8)
+        trace = np.zeros((n, self.info.total_cells), dtype=TRACE_DTYPE)
+        _check(self.lib.cb200_decode_cells(self._h, rgb.ctypes.data, n, flags, cells.ctypes.data, trace.ctypes.data))
+        return cells, trace
+
     def decode_symbols(self, windows, cooldown=None):
         windows = np.ascontiguousarray(windows, dtype=np.uint16).reshape(-1, 10)
         n = windows.shape[0]
@@ -195,3 +219,40 @@ class Context:
 
     def render_frames_dev(self, d_cellvals, n, d_rgb_out):
         _check(self.lib.cb200_render_frames_dev(self._h, d_cellvals, n, d_rgb_out))
+
+
+class FountainSink:
+    """Rank-0 fountain ingest (cb200_sink_*): header parse, de-dup and stream bookkeeping on the host, with the
+    fountain codec (wirehair) supplied by the caller as a ctypes library exposing wirehair's C API."""
+
+    def __init__(self, chunk_size, codec_lib):
+        self.lib = load_library()
+        fn = lambda name: C.cast(getattr(codec_lib, name), C.c_void_p)
+        self._h = self.lib.cb200_sink_create(chunk_size, fn("wirehair_decoder_create"), fn("wirehair_decode"),
+                                             fn("wirehair_recover"), fn("wirehair_free"))
+        if not self._h:
+            raise Cb200Error("cb200_sink_create failed")
+        self.chunk_size = chunk_size
+
+    def close(self):
+        if self._h:
+            self.lib.cb200_sink_destroy(self._h)
+            self._h = None
+
+    def decode_frame(self, chunk):
+        chunk = np.ascontiguousarray(chunk, dtype=np.uint8)
+        return self.lib.cb200_sink_decode_frame(self._h, chunk.ctypes.data, chunk.size)
+
+    def ingest(self, chunks, masks):
+        chunks = np.ascontiguousarray(chunks, dtype=np.uint8)
+        masks = np.ascontiguousarray(masks, dtype=np.uint32)
+        n = masks.size
+        return self.lib.cb200_sink_ingest(self._h, chunks.ctypes.data, masks.ctypes.data, n, chunks.size // (n * self.chunk_size))
+
+    def file(self, file_id):
+        size = self.lib.cb200_sink_file_size(self._h, file_id)
+        if size < 0:
+            return None
+        out = np.zeros(size, dtype=np.uint8)
+        _check(self.lib.cb200_sink_file_read(self._h, file_id, out.ctypes.data, size))
+        return out

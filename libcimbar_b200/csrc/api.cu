@@ -197,15 +197,16 @@ int check_n(const cb200_ctx* c, int n)
 }
 
 // K1 (+ exact-walk fallback) : frames -> per-cell bytes in ctx->d_cellvals, per-frame flags in ctx->d_flags
-int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
+int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTrace* d_trace = nullptr)
 {
     const Mode& m = c->mode;
     cudaStream_t st = c->stream;
     const bool sharpen = (flags & CB200_FLAG_SHARPEN) != 0;
+    const bool exact_only = sharpen || d_trace != nullptr;     // these go straight to the exact-walk kernel
     CK(cudaMemsetAsync(c->d_dirty, 0, sizeof(uint32_t) * (size_t)n, st), "memset dirty");
     if (c->timing) { c->cur = (int)(c->calls % cb200_ctx::kEvSets); c->calls++; c->ev_count[c->cur] = 0; }
     mark(c);                                   // ev0: before K1
-    if (!sharpen) {
+    if (!exact_only) {
         // bands: whole frames when there are enough of them to fill the machine, else split frames into bands of cell rows
         int ctas = c->sm_count * c->k1_ctas_per_sm;
         int bands = 1;
@@ -216,13 +217,23 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags)
     }
     mark(c);                                   // ev1: after K1
     // the sharpen preprocessing (needs_sharpen, CimbReader.cpp:37-40) is only implemented in the exact-walk kernel
-    CK(flood_launch(m, c->flood, d_rgb, n, (flags & CB200_FLAG_NO_FALLBACK) != 0, sharpen, sharpen,
-                    c->d_cellvals, c->d_dirty, c->d_flags, st), "flood launch");
+    CK(flood_launch(m, c->flood, d_rgb, n, (flags & CB200_FLAG_NO_FALLBACK) != 0, exact_only, sharpen,
+                    c->d_cellvals, c->d_dirty, c->d_flags, d_trace, st), "flood launch");
     mark(c);                                   // ev2: after K1x
     return CB200_OK;
 }
 
 }  // namespace
+
+int upload_frames(cb200_ctx* c, const uint8_t* rgb, int n)
+{
+    const Mode& m = c->mode;
+    size_t fb = (size_t)m.width * m.height * 3;
+    if (!c->d_rgb) CK(cudaMalloc(&c->d_rgb, fb * (size_t)c->max_frames), "cudaMalloc rgb staging");
+    CK(cudaMemcpyAsync(c->d_rgb, rgb, fb * (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D frames");
+    return CB200_OK;
+}
+
 
 extern "C" {
 
@@ -405,15 +416,6 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
 }
 
 // ---- host-pointer entry points
-static int upload_frames(cb200_ctx* c, const uint8_t* rgb, int n)
-{
-    const Mode& m = c->mode;
-    size_t fb = (size_t)m.width * m.height * 3;
-    if (!c->d_rgb) CK(cudaMalloc(&c->d_rgb, fb * (size_t)c->max_frames), "cudaMalloc rgb staging");
-    CK(cudaMemcpyAsync(c->d_rgb, rgb, fb * (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D frames");
-    return CB200_OK;
-}
-
 int cb200_decode_raw(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* raw_out, uint8_t* frame_flags)
 {
     int rc = check_n(c, n); if (rc) return rc;
@@ -476,6 +478,24 @@ int cb200_decode_fountain(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flag
         chunk_count[f] = cnt;
         if (chunk_mask) chunk_mask[f] = h_mask[f];
     }
+    return CB200_OK;
+}
+
+int cb200_decode_cells(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* cellvals_out, cb200_cell_trace* trace_out)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!rgb || !cellvals_out || !trace_out) return fail(CB200_ERR_ARG, "null buffer");
+    static_assert(sizeof(cb200_cell_trace) == sizeof(CellTrace), "trace layout");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    rc = upload_frames(c, rgb, n); if (rc) return rc;
+    size_t tb = (size_t)n * c->mode.num_cells * sizeof(CellTrace);
+    rc = ensure_scratch(c, tb); if (rc) return rc;
+    CellTrace* d_trace = static_cast<CellTrace*>(c->d_scratch);
+    rc = run_cells(c, c->d_rgb, n, flags & ~CB200_FLAG_NO_FALLBACK, d_trace); if (rc) return rc;
+    CK(cudaMemcpyAsync(cellvals_out, c->d_cellvals, (size_t)n * c->mode.num_cells, cudaMemcpyDeviceToHost, c->stream), "D2H cells");
+    CK(cudaMemcpyAsync(trace_out, d_trace, tb, cudaMemcpyDeviceToHost, c->stream), "D2H trace");
+    CK(cudaStreamSynchronize(c->stream), "sync");
     return CB200_OK;
 }
 

@@ -260,7 +260,8 @@ __device__ uint32_t flood_best_color(const float* adjust_tab, const Mode& m, uin
 __global__ void __launch_bounds__(kFloodThreads, 1)
 k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fallback, int force_all, int sharpen,
         uint8_t* __restrict__ cellvals, const uint32_t* __restrict__ dirty, uint8_t* __restrict__ frame_flags,
-        uint8_t* ws_gray, uint8_t* ws_gray2, uint16_t* ws_hsum, uint32_t* ws_raster, uint32_t* ws_heap, size_t heap_cap)
+        uint8_t* ws_gray, uint8_t* ws_gray2, uint16_t* ws_hsum, uint32_t* ws_raster, uint32_t* ws_heap, size_t heap_cap,
+        CellTrace* __restrict__ trace)
 {
     extern __shared__ __align__(16) uint8_t flood_smem_raw[];
     FloodSmem& s = *reinterpret_cast<FloodSmem*>(flood_smem_raw);
@@ -362,6 +363,12 @@ k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fall
                     if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
                     flood_update(m, s, heap, ci, ndx, ndy, dist, ncd);
                     s.instr[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
+                    if (trace) {
+                        CellTrace tr;
+                        tr.order = (uint16_t)(count - 1); tr.x = (int16_t)(x + bx); tr.y = (int16_t)(y + by);
+                        tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
+                        trace[(size_t)f * ncells + ci] = tr;
+                    }
                 }
                 __syncwarp();
             }
@@ -424,11 +431,12 @@ void flood_workspace_destroy(FloodWorkspace* ws)
 }
 
 cudaError_t flood_launch(const Mode& m, const FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
-                         bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, cudaStream_t st)
+                         bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, CellTrace* d_trace,
+                         cudaStream_t st)
 {
     int grid = n_frames < ws.slots ? n_frames : ws.slots;
     k_flood<<<grid, kFloodThreads, sizeof(FloodSmem), st>>>(m, d_rgb, n_frames, no_fallback ? 1 : 0, force_all ? 1 : 0, sharpen ? 1 : 0,
-                                                            d_cellvals, d_dirty, d_flags, ws.gray, ws.gray2, ws.hsum, ws.raster, ws.heap, ws.heap_cap);
+                                                            d_cellvals, d_dirty, d_flags, ws.gray, ws.gray2, ws.hsum, ws.raster, ws.heap, ws.heap_cap, d_trace);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,14 @@
 
 namespace cb200 {
 
+// per-cell record of the exact walk (== what CimbReader::read returns step by step, CimbReader.cpp:139-162)
+struct CellTrace {
+    uint16_t order;        // position in the flood-walk order
+    int16_t x, y;          // drift-adjusted cell position (PositionData x, y)
+    uint8_t drift_offset;  // winning hash id 0..8 (4 = centre)
+    uint8_t distance;      // best Hamming distance
+};
+
 struct FloodWorkspace {
     int slots;                 // concurrent frames (one CTA each)
     size_t heap_cap;           // heap entries per slot
@@ -17,6 +25,7 @@ void flood_workspace_destroy(FloodWorkspace* ws);
 // writes d_flags[f] for every frame: 0 = K1 result stands, CB200_FRAME_FALLBACK = re-decoded here,
 // CB200_FRAME_INEXACT = needed but skipped (no_fallback)
 cudaError_t flood_launch(const Mode& m, const FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
-                         bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, cudaStream_t st);
+                         bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, CellTrace* d_trace,
+                         cudaStream_t st);
 
 }  // namespace cb200

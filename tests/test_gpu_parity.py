@@ -298,3 +298,52 @@ def test_argument_errors(cb):
     with pytest.raises(cb.Cb200Error):
         cb.Context(12345, max_frames=1)                             # unknown mode
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ C++ shims
+def test_cpp_shims_rerun_reference_unit_tests(cb, tmp_path):
+    """libcimbar_b200/host/{Decoder,CimbReader,CimbDecoder}.h keep the reference's class/method names; tests/cpp/shim_test.cpp
+    re-runs the reference's DecoderTest / CimbReaderTest / CimbDecoderTest cases through them (and so through the kernels)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "shim_test")
+    libdir = os.path.join(root, "libcimbar_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "cpp", "shim_test.cpp"),
+                           "-L" + libdir, "-lcb200", "-Wl,-rpath," + libdir])
+    golden = {(g["sample"], g["mode"], g["ecc"]): g["sha256"] for g in manifest()["goldens"]}
+    first22 = {
+        ("6bit/4color_ecc30_fountain_0.png", 4): ("0=0 99=8 11680=3 11681=32 11900=28 11901=25 11904=12 11995=2 11996=8 11998=6 "
+                                                  "11999=54 12001=29 12004=6 12099=2 12195=57 12196=1 12200=5 12201=0 12298=32 "
+                                                  "12299=34 12300=30 12399=15"),     # CimbReaderTest.cpp:80-83 (colour mode 0)
+        ("6bit/4color_ecc30_fountain_0.png", 68): ("0=16 99=24 11680=19 11681=48 11900=44 11901=41 11904=28 11995=18 11996=24 "
+                                                   "11998=22 11999=6 12001=45 12004=22 12099=18 12195=9 12196=17 12200=21 12201=16 "
+                                                   "12298=48 12299=50 12300=46 12399=31"),  # CimbReaderTest.cpp:116-118 (colour mode 1)
+        ("6bit/4_30_f0_627_extract.jpg", 68): ("0=16 1=44 99=24 100=44 600=49 601=54 711=46 712=9 11464=5 11576=48 11577=60 "
+                                               "11687=57 11688=7 11689=48 11690=0 11798=31 11799=41 12297=62 12298=48 12299=50 "
+                                               "12300=46 12399=31"),                  # CimbReaderTest.cpp:153-155
+    }
+    for sample, mode in [("b/tr_0.png", 68), ("6bit/4color_ecc30_fountain_0.png", 4), ("6bit/4color_ecc30_fountain_0.png", 68),
+                         ("6bit/4_30_f0_627_extract.jpg", 4), ("6bit/4_30_f0_627_extract.jpg", 68)]:
+        rgb = load_sample(sample)
+        fpath = str(tmp_path / "frame.rgb")
+        rgb.tofile(fpath)
+        prefix = str(tmp_path / "out")
+        res = subprocess.run([exe, str(mode), fpath, prefix], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        raw = np.fromfile(prefix + ".raw", dtype=np.uint8)
+        ecc = np.fromfile(prefix + ".ecc", dtype=np.uint8)
+        if (sample, mode, False) in golden:
+            assert sha(raw) == golden[(sample, mode, False)]
+        if (sample, mode, True) in golden:
+            assert sha(ecc) == golden[(sample, mode, True)]
+        m = ORA.mode(mode)
+        assert np.array_equal(raw, ORA.decode_raw(m, rgb))
+        good, ochunks, omask = ORA.decode_fountain(m, rgb)
+        chunks = np.fromfile(prefix + ".chunks", dtype=np.uint8)
+        assert chunks.size == good and np.array_equal(chunks, ochunks.reshape(-1)[:good])
+        lines = open(prefix + ".first22").read().split("\n")
+        if (sample, mode) in first22:
+            assert lines[0] == first22[(sample, mode)]
+        if sample == "6bit/4color_ecc30_fountain_0.png":
+            assert lines[1] == "0 62 8"                                   # CimbReaderTest.cpp:37-58: first read
