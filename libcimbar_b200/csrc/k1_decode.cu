@@ -351,14 +351,16 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                     // gray is byte 2 of each numerator
                     E[r] = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n6, n7, 0x6200), 0x7610);
                 }
-                // park E_0..E_8 in this thread's own (already consumed) raw words of stage rows 5, 6, 7
+                // park E_0..E_8 in this thread's own (already consumed) raw words of stage rows 5, 6, 7: the thread owns words
+                // 6t..6t+5 of each row; slot 2*(r%3) + (t>>4 & 1) makes lanes t and t+16 (same 6t mod 32) hit different banks
                 if (px_active) {
-                    uint32_t* w5 = reinterpret_cast<uint32_t*>(ub[1] + 2u * row_bytes) + 6 * t;   // stage row 5 = unit 1, row 2
-                    uint32_t* w6 = reinterpret_cast<uint32_t*>(ub[2]) + 6 * t;                    // stage row 6 = unit 2, row 0
-                    uint32_t* w7 = reinterpret_cast<uint32_t*>(ub[2] + row_bytes) + 6 * t;        // stage row 7 = unit 2, row 1
-                    w5[0] = E[0]; w5[1] = E[1]; w5[2] = E[2];
-                    w6[0] = E[3]; w6[1] = E[4]; w6[2] = E[5];
-                    w7[0] = E[6]; w7[1] = E[7]; w7[2] = E[8];
+                    const uint32_t po = 6u * (uint32_t)t + (((uint32_t)t >> 4) & 1u);
+                    uint32_t* w5 = reinterpret_cast<uint32_t*>(ub[1] + 2u * row_bytes) + po;   // stage row 5 = unit 1, row 2
+                    uint32_t* w6 = reinterpret_cast<uint32_t*>(ub[2]) + po;                    // stage row 6 = unit 2, row 0
+                    uint32_t* w7 = reinterpret_cast<uint32_t*>(ub[2] + row_bytes) + po;        // stage row 7 = unit 2, row 1
+                    w5[0] = E[0]; w5[2] = E[1]; w5[4] = E[2];
+                    w6[0] = E[3]; w6[2] = E[4]; w6[4] = E[5];
+                    w7[0] = E[6]; w7[2] = E[7]; w7[4] = E[8];
                 }
             }
 
@@ -400,11 +402,12 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 const uint32_t* e5 = reinterpret_cast<const uint32_t*>(ub[1] + 2u * row_bytes);
                 const uint32_t* e6 = reinterpret_cast<const uint32_t*>(ub[2]);
                 const uint32_t* e7 = reinterpret_cast<const uint32_t*>(ub[2] + row_bytes);
+                const uint32_t pol = 6u * (uint32_t)tl + (((uint32_t)tl >> 4) & 1u), por = 6u * (uint32_t)tr + (((uint32_t)tr >> 4) & 1u);
                 uint32_t h[kStageRows][4];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
                     const uint32_t* er = (r < 3) ? e5 : (r < 6 ? e6 : e7);
-                    uint32_t lE = er[6 * tl + (r % 3)], rE = er[6 * tr + (r % 3)];
+                    uint32_t lE = er[pol + 2 * (r % 3)], rE = er[por + 2 * (r % 3)];
                     uint32_t Pm2 = __byte_perm(lE, P[r][2], 0x5452), Pm1 = __byte_perm(lE, P[r][3], 0x5453);
                     uint32_t P4 = __byte_perm(P[r][0], rE, 0x3432), P5 = __byte_perm(P[r][1], rE, 0x3532);
                     h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P[r][2];
