@@ -75,6 +75,7 @@ struct RsSmem {
     uint8_t log[256];
     struct PerWarp {
         alignas(4) uint8_t enc[256];
+        alignas(8) uint16_t encs[256];   // enc[i] * (128*T): byte offset of table row enc[i] (syndrome loop operand)
         uint8_t synd[kMaxParity];
         uint8_t loc[kMaxParity + 8];
         uint8_t last[kMaxParity + 8];
@@ -121,7 +122,8 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
     for (int i = tid; i < 256; i += blockDim.x) s.log[i] = c_gf_log[i];
     for (int e = tid; e < 256 * 32 * T; e += blockDim.x) {
         int x = e / (32 * T), j = e - x * (32 * T);
-        mt[e] = x ? (uint32_t)c_gf_exp[(uint32_t)c_gf_log[x] + (uint32_t)(j + 1)] : 0u;   // j+1 <= 64: index < 512
+        uint32_t v = x ? (uint32_t)c_gf_exp[(uint32_t)c_gf_log[x] + (uint32_t)(j + 1)] : 0u;   // j+1 <= 64: index < 512
+        mt[e] = v * (128u * T);      // stored as the byte offset of table row v: the Horner step needs no address arithmetic
     }
     __syncthreads();
 
@@ -135,18 +137,28 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         __syncwarp();
         if (FUSED) {
             const uint8_t* cells = cellvals + (size_t)f * m.num_cells;
+            const bool fast = !m.legacy && m.symbol_bits == 4 && m.color_bits == 2;
             for (int i = lane; i < blk; i += 32) {
                 uint32_t B = (uint32_t)b * (uint32_t)blk + (uint32_t)i, v;
-                if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
+                if (fast && (int)B < m.cap_sym) {          // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
+                    const uint32_t sl = *reinterpret_cast<const uint32_t*>(idx + 2u * B);
+                    v = ((uint32_t)(cells[sl & 0xFFFFu] & 15u) << 4) | (uint32_t)(cells[sl >> 16] & 15u);
+                } else if (fast) {                         // four 2-bit colours per byte (Decoder.h:112-113)
+                    const uint2 sl = *reinterpret_cast<const uint2*>(idx + 4u * (B - (uint32_t)m.cap_sym));
+                    v = ((uint32_t)((cells[sl.x & 0xFFFFu] >> 4) & 3u) << 6) | ((uint32_t)((cells[sl.x >> 16] >> 4) & 3u) << 4) |
+                        ((uint32_t)((cells[sl.y & 0xFFFFu] >> 4) & 3u) << 2) | (uint32_t)((cells[sl.y >> 16] >> 4) & 3u);
+                }
+                else if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
                 else if ((int)B < m.cap_sym) v = stream_byte(cells, idx, B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
                 else v = stream_byte(cells, idx, B - (uint32_t)m.cap_sym, m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
                 w.enc[i] = (uint8_t)v;
+                w.encs[i] = (uint16_t)(v * (128u * T));
             }
         } else {
             // symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
             // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks
             const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
-            for (int i = lane; i < blk; i += 32) w.enc[i] = enc_g[i];
+            for (int i = lane; i < blk; i += 32) { uint32_t v = enc_g[i]; w.enc[i] = (uint8_t)v; w.encs[i] = (uint16_t)(v * (128u * T)); }
         }
         __syncwarp();
 
@@ -154,18 +166,20 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         uint32_t nz = 0;
 #pragma unroll
         for (int q = 0; q < T; ++q) {
-            const uint32_t* col = mt + lane + 32 * q;
-            uint32_t acc = 0;
-            const uint32_t* ew = reinterpret_cast<const uint32_t*>(w.enc);
+            // Horner with every value kept as a table-row byte offset: off' = mt[off ^ enc_off][lane]  (one XOR, one LDS per byte)
+            const char* colb = reinterpret_cast<const char*>(mt) + 4 * (lane + 32 * q);
+            uint32_t off = 0;
+            const uint2* e4 = reinterpret_cast<const uint2*>(w.encs);
             int i = 0;
-            for (; i + 4 <= blk; i += 4) {               // four Horner steps per 32-bit load of the block
-                const uint32_t wd = ew[i >> 2];
-                acc = col[acc * (32 * T)] ^ (wd & 0xFFu);
-                acc = col[acc * (32 * T)] ^ ((wd >> 8) & 0xFFu);
-                acc = col[acc * (32 * T)] ^ ((wd >> 16) & 0xFFu);
-                acc = col[acc * (32 * T)] ^ (wd >> 24);
+            for (; i + 4 <= blk; i += 4) {
+                const uint2 e = e4[i >> 2];
+                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.x & 0xFFFFu)));
+                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.x >> 16)));
+                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.y & 0xFFFFu)));
+                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.y >> 16)));
             }
-            for (; i < blk; ++i) acc = col[acc * (32 * T)] ^ w.enc[i];
+            for (; i < blk; ++i) off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (uint32_t)w.encs[i]));
+            const uint32_t acc = off / (128u * T);
             const int j = lane + 32 * q;
             if (j < md) { w.synd[j] = (uint8_t)acc; nz |= acc; }
         }
