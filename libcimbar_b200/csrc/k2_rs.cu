@@ -166,19 +166,19 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         uint32_t nz = 0;
 #pragma unroll
         for (int q = 0; q < T; ++q) {
-            // Horner with every value kept as a table-row byte offset: off' = mt[off ^ enc_off][lane]  (one XOR, one LDS per byte)
+            // Horner with every value kept as a table-row byte offset: off' = mt[off][lane] ^ enc_off  (one LDS, one XOR per byte)
             const char* colb = reinterpret_cast<const char*>(mt) + 4 * (lane + 32 * q);
             uint32_t off = 0;
             const uint2* e4 = reinterpret_cast<const uint2*>(w.encs);
             int i = 0;
             for (; i + 4 <= blk; i += 4) {
                 const uint2 e = e4[i >> 2];
-                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.x & 0xFFFFu)));
-                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.x >> 16)));
-                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.y & 0xFFFFu)));
-                off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (e.y >> 16)));
+                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.x & 0xFFFFu);
+                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.x >> 16);
+                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.y & 0xFFFFu);
+                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.y >> 16);
             }
-            for (; i < blk; ++i) off = *reinterpret_cast<const uint32_t*>(colb + (off ^ (uint32_t)w.encs[i]));
+            for (; i < blk; ++i) off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (uint32_t)w.encs[i];
             const uint32_t acc = off / (128u * T);
             const int j = lane + 32 * q;
             if (j < md) { w.synd[j] = (uint8_t)acc; nz |= acc; }
