@@ -335,7 +335,39 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
         CK(encode_init_tables(gexp, glog), "encode tables");
         for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[k][i]), "cudaEventCreate");
     }
-    CK(flood_workspace_create(m, c->sm_count, &c->flood), "flood workspace");
+    {   // neighbour table for the exact walk: AdjacentCellFinder::find (src/lib/cimb_translator/AdjacentCellFinder.cpp:54-105),
+        // evaluated literally (position comparisons included) over the linear cell positions (CellPositions.cpp:5-50)
+        const int n_cells = m.num_cells;
+        std::vector<int> xs(n_cells);
+        for (int k = 0, i = 0; k < m.cells_y; ++k) {
+            int base, ncols, x0;
+            cell_row_geom(m, k, base, ncols, x0);
+            for (int cc = 0; cc < ncols; ++cc, ++i) xs[i] = x0 + kSpacing * cc;
+        }
+        const int first_mid = m.top_cells, first_bottom = m.top_cells + m.mid_cells;
+        auto margin = [&](int index) { return (index < first_mid) ? 1 : (index < first_bottom ? 0 : 1); };
+        auto right = [&](int index) -> int { if (index < 0 || index >= n_cells - 1) return -1; int next = index + 1; return xs[next] < xs[index] ? -1 : next; };
+        auto left = [&](int index) -> int { int next = index - 1; if (next < 0) return -1; return xs[next] > xs[index] ? -1 : next; };
+        auto bottom = [&](int index) -> int {
+            if (index < 0 || index >= n_cells) return -1;
+            int inc = m.cells_x; if (margin(index)) inc -= m.corner;
+            int next = index + inc; if (margin(next)) next -= m.corner;
+            if (next < 0 || next >= n_cells) return -1;
+            return xs[next] != xs[index] ? -1 : next;
+        };
+        auto top = [&](int index) -> int {
+            int inc = m.cells_x; if (margin(index)) inc -= m.corner;
+            int next = index - inc; if (margin(next)) next += m.corner;
+            if (next < 0) return -1;
+            return xs[next] != xs[index] ? -1 : next;
+        };
+        std::vector<uint16_t> adj((size_t)n_cells * 4);
+        for (int i = 0; i < n_cells; ++i) {
+            int v[4] = {right(i), left(i), bottom(i), top(i)};
+            for (int d = 0; d < 4; ++d) adj[(size_t)i * 4 + d] = v[d] < 0 ? (uint16_t)0xFFFF : (uint16_t)v[d];
+        }
+        CK(flood_workspace_create(m, c->sm_count, adj.data(), &c->flood), "flood workspace");
+    }
     *out = c;
     return CB200_OK;
 }

@@ -23,11 +23,13 @@ constexpr int kFloodThreads = 256;
 __constant__ float cx_adjust[256];
 __constant__ unsigned long long cx_tiles_L[16];
 
+constexpr int kHeapSmem = 14336;        // heap entries kept in shared memory (observed maximum ~9.1k); the rest spills to global
+
 struct FloodSmem {
     uint32_t instr[kMaxCells];          // before decode: dx(8) | dy(8) | prio(8) | cooldown(8); after: x(11) | y(11) | sym(4) | done
+    uint32_t heap[kHeapSmem];
     uint32_t remaining[(kMaxCells + 31) / 32];
     float adjust[256];
-    int bcast[4];
 };
 
 // ---------------------------------------------------------------------------------------------- geometry
@@ -47,79 +49,43 @@ __device__ __forceinline__ void cell_xy(const Mode& m, int index, int& x, int& y
 }
 __device__ __forceinline__ int cell_x(const Mode& m, int index) { int x, y; cell_xy(m, index, x, y); return x; }
 
-// AdjacentCellFinder.cpp:54-105 (the position comparisons are kept literally)
-__device__ __forceinline__ int adj_margin(const Mode& m, int index)
-{
-    return (index < m.top_cells) ? 1 : (index < m.top_cells + m.mid_cells ? 0 : 1);
-}
-__device__ int adj_right(const Mode& m, int index)
-{
-    if (index < 0 || index >= m.num_cells - 1) return -1;
-    int next = index + 1;
-    if (cell_x(m, next) < cell_x(m, index)) return -1;
-    return next;
-}
-__device__ int adj_left(const Mode& m, int index)
-{
-    int next = index - 1;
-    if (next < 0) return -1;
-    if (cell_x(m, next) > cell_x(m, index)) return -1;
-    return next;
-}
-__device__ int adj_bottom(const Mode& m, int index)
-{
-    if (index < 0 || index >= m.num_cells) return -1;
-    int inc = m.cells_x;
-    if (adj_margin(m, index)) inc -= m.corner;
-    int next = index + inc;
-    if (adj_margin(m, next)) next -= m.corner;
-    if (next < 0 || next >= m.num_cells) return -1;
-    if (cell_x(m, next) != cell_x(m, index)) return -1;
-    return next;
-}
-__device__ int adj_top(const Mode& m, int index)
-{
-    int inc = m.cells_x;
-    if (adj_margin(m, index)) inc -= m.corner;
-    int next = index - inc;
-    if (adj_margin(m, next)) next += m.corner;
-    if (next < 0) return -1;
-    if (cell_x(m, next) != cell_x(m, index)) return -1;
-    return next;
-}
-
 // ---------------------------------------------------------------------------------------------- heap (lane 0 only)
 // entries: prio << 16 | index.  std::priority_queue<decode_prio, vector, PrioCompare> with comp(a,b) = a.prio > b.prio
-struct Heap { uint32_t* v; int n; };
+struct Heap {
+    uint32_t* sm; uint32_t* spill; int n;
+    __device__ __forceinline__ uint32_t get(int i) const { return i < kHeapSmem ? sm[i] : spill[i - kHeapSmem]; }
+    __device__ __forceinline__ void set(int i, uint32_t v) { if (i < kHeapSmem) sm[i] = v; else spill[i - kHeapSmem] = v; }
+};
 __device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 16; }
 __device__ void heap_push(Heap& h, uint32_t idx, uint32_t prio)
 {
     int hole = h.n++;
     int parent = (hole - 1) / 2;
-    while (hole > 0 && hprio(h.v[parent]) > prio) { h.v[hole] = h.v[parent]; hole = parent; parent = (hole - 1) / 2; }
-    h.v[hole] = (prio << 16) | idx;
+    while (hole > 0 && hprio(h.get(parent)) > prio) { h.set(hole, h.get(parent)); hole = parent; parent = (hole - 1) / 2; }
+    h.set(hole, (prio << 16) | idx);
 }
 __device__ uint32_t heap_pop(Heap& h)
 {
-    uint32_t top = h.v[0];
-    uint32_t value = h.v[h.n - 1];
+    uint32_t top = h.get(0);
+    uint32_t value = h.get(h.n - 1);
     int len = --h.n;
     if (len == 0) return top;
     int hole = 0, second = 0;
     while (second < (len - 1) / 2) {
         second = 2 * (second + 1);
-        if (hprio(h.v[second]) > hprio(h.v[second - 1])) second--;
-        h.v[hole] = h.v[second];
+        uint32_t a = h.get(second), b = h.get(second - 1);
+        if (hprio(a) > hprio(b)) { second--; a = b; }
+        h.set(hole, a);
         hole = second;
     }
     if ((len & 1) == 0 && second == (len - 2) / 2) {
         second = 2 * (second + 1);
-        h.v[hole] = h.v[second - 1];
+        h.set(hole, h.get(second - 1));
         hole = second - 1;
     }
     int parent = (hole - 1) / 2;
-    while (hole > 0 && hprio(h.v[parent]) > hprio(value)) { h.v[hole] = h.v[parent]; hole = parent; parent = (hole - 1) / 2; }
-    h.v[hole] = value;
+    while (hole > 0 && hprio(h.get(parent)) > hprio(value)) { h.set(hole, h.get(parent)); hole = parent; parent = (hole - 1) / 2; }
+    h.set(hole, value);
     return top;
 }
 
@@ -142,30 +108,38 @@ __device__ void update_adjacents(FloodSmem& s, Heap& h, const int adj[4], int dx
     }
 }
 
-// FloodDecodePositions::update, FloodDecodePositions.cpp:86-129
-__device__ void flood_update(const Mode& m, FloodSmem& s, Heap& h, int index, int dx, int dy, uint32_t err, uint32_t cooldown)
+// FloodDecodePositions::update, FloodDecodePositions.cpp:86-129.  adj: per-cell neighbours (right, left, bottom, top) as
+// AdjacentCellFinder::find computes them (AdjacentCellFinder.cpp:54-105), precomputed once per context; 0xFFFF = none.
+__device__ __forceinline__ int adj_of(const ushort4* __restrict__ adj, int cell, int dir)
 {
-    int adj[4] = {adj_right(m, index), adj_left(m, index), adj_bottom(m, index), adj_top(m, index)};
-    update_adjacents(s, h, adj, dx, dy, err, cooldown);
+    ushort4 a = __ldg(&adj[cell]);
+    unsigned v = dir == 0 ? a.x : dir == 1 ? a.y : dir == 2 ? a.z : a.w;
+    return v == 0xFFFFu ? -1 : (int)v;
+}
+__device__ void flood_update(const ushort4* __restrict__ adj, FloodSmem& s, Heap& h, int index, int dx, int dy, uint32_t err, uint32_t cooldown)
+{
+    ushort4 a4 = __ldg(&adj[index]);
+    int a[4] = {a4.x == 0xFFFFu ? -1 : (int)a4.x, a4.y == 0xFFFFu ? -1 : (int)a4.y, a4.z == 0xFFFFu ? -1 : (int)a4.z, a4.w == 0xFFFFu ? -1 : (int)a4.w};
+    update_adjacents(s, h, a, dx, dy, err, cooldown);
     uint32_t self = s.instr[index];
     uint32_t prev_err = (self >> 16) & 0xFFu, prev_cd = self >> 24;
     if (prev_err < 3 && err < 3 && prev_cd == 4 && cooldown == 4) {
-        int rr = adj[0], ll = adj[1];
+        int rr = a[0], ll = a[1];
         if (rr >= 0 && ll >= 0) {
             int hz[4] = {-1, -1, -1, -1};
-            hz[0] = adj_right(m, rr);
-            if (hz[0] >= 0) hz[1] = adj_right(m, hz[0]);
-            hz[2] = adj_left(m, ll);
-            if (hz[2] >= 0) hz[3] = adj_left(m, hz[2]);
+            hz[0] = adj_of(adj, rr, 0);
+            if (hz[0] >= 0) hz[1] = adj_of(adj, hz[0], 0);
+            hz[2] = adj_of(adj, ll, 1);
+            if (hz[2] >= 0) hz[3] = adj_of(adj, hz[2], 1);
             update_adjacents(s, h, hz, dx, dy, err, cooldown);
         }
-        int uu = adj[3], dd = adj[2];
+        int uu = a[3], dd = a[2];
         if (uu >= 0 && dd >= 0) {
             int vt[4] = {-1, -1, -1, -1};
-            vt[0] = adj_top(m, uu);
-            if (vt[0] >= 0) vt[1] = adj_top(m, vt[0]);
-            vt[2] = adj_bottom(m, dd);
-            if (vt[2] >= 0) vt[3] = adj_bottom(m, vt[2]);
+            vt[0] = adj_of(adj, uu, 3);
+            if (vt[0] >= 0) vt[1] = adj_of(adj, vt[0], 3);
+            vt[2] = adj_of(adj, dd, 2);
+            if (vt[2] >= 0) vt[3] = adj_of(adj, vt[2], 2);
             update_adjacents(s, h, vt, dx, dy, err, cooldown);
         }
     }
@@ -257,11 +231,11 @@ __device__ uint32_t flood_best_color(const float* adjust_tab, const Mode& m, uin
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kFloodThreads, 1)
+__global__ void __launch_bounds__(kFloodThreads, 2)
 k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fallback, int force_all, int sharpen,
         uint8_t* __restrict__ cellvals, const uint32_t* __restrict__ dirty, uint8_t* __restrict__ frame_flags,
         uint8_t* ws_gray, uint8_t* ws_gray2, uint16_t* ws_hsum, uint32_t* ws_raster, uint32_t* ws_heap, size_t heap_cap,
-        CellTrace* __restrict__ trace)
+        const ushort4* __restrict__ adj, CellTrace* __restrict__ trace)
 {
     extern __shared__ __align__(16) uint8_t flood_smem_raw[];
     FloodSmem& s = *reinterpret_cast<FloodSmem*>(flood_smem_raw);
@@ -272,7 +246,7 @@ k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fall
     uint8_t* gray2 = ws_gray2 + (size_t)blockIdx.x * npx;
     uint16_t* hsum = ws_hsum + (size_t)blockIdx.x * npx;
     uint32_t* raster = ws_raster + (size_t)blockIdx.x * (npx / 32 + 4);
-    Heap heap; heap.v = ws_heap + (size_t)blockIdx.x * heap_cap; heap.n = 0;
+    Heap heap; heap.sm = s.heap; heap.spill = ws_heap + (size_t)blockIdx.x * heap_cap; heap.n = 0;
     for (int i = tid; i < 256; i += kFloodThreads) s.adjust[i] = cx_adjust[i];
 
     for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
@@ -361,7 +335,7 @@ k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fall
                     int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
                     uint32_t ncd;                                      // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
                     if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
-                    flood_update(m, s, heap, ci, ndx, ndy, dist, ncd);
+                    flood_update(adj, s, heap, ci, ndx, ndy, dist, ncd);
                     s.instr[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
                     if (trace) {
                         CellTrace tr;
@@ -408,12 +382,12 @@ cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* 
     return cudaFuncSetAttribute(k_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FloodSmem));
 }
 
-cudaError_t flood_workspace_create(const Mode& m, int sm_count, FloodWorkspace* ws)
+cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* adj_host, FloodWorkspace* ws)
 {
     memset(ws, 0, sizeof(*ws));
-    ws->slots = sm_count;
+    ws->slots = 2 * sm_count;   // two resident CTAs per SM (108 KB shared memory each)
     size_t npx = (size_t)m.width * m.height;
-    ws->heap_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
+    ws->heap_cap = 16 + 12 * (size_t)m.num_cells;   // spill area: every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
     if ((e = cudaMalloc(&ws->gray, npx * ws->slots)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->gray2, npx * ws->slots)) != cudaSuccess) return e;
@@ -421,12 +395,14 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, FloodWorkspace* 
     if ((e = cudaMalloc(&ws->raster, (npx / 32 + 4) * ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMemset(ws->raster, 0, (npx / 32 + 4) * ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->heap, ws->heap_cap * ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&ws->adj, (size_t)m.num_cells * 4 * sizeof(uint16_t))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(ws->adj, adj_host, (size_t)m.num_cells * 4 * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 void flood_workspace_destroy(FloodWorkspace* ws)
 {
-    cudaFree(ws->gray); cudaFree(ws->gray2); cudaFree(ws->hsum); cudaFree(ws->raster); cudaFree(ws->heap);
+    cudaFree(ws->gray); cudaFree(ws->gray2); cudaFree(ws->hsum); cudaFree(ws->raster); cudaFree(ws->heap); cudaFree(ws->adj);
     memset(ws, 0, sizeof(*ws));
 }
 
@@ -436,7 +412,8 @@ cudaError_t flood_launch(const Mode& m, const FloodWorkspace& ws, const uint8_t*
 {
     int grid = n_frames < ws.slots ? n_frames : ws.slots;
     k_flood<<<grid, kFloodThreads, sizeof(FloodSmem), st>>>(m, d_rgb, n_frames, no_fallback ? 1 : 0, force_all ? 1 : 0, sharpen ? 1 : 0,
-                                                            d_cellvals, d_dirty, d_flags, ws.gray, ws.gray2, ws.hsum, ws.raster, ws.heap, ws.heap_cap, d_trace);
+                                                            d_cellvals, d_dirty, d_flags, ws.gray, ws.gray2, ws.hsum, ws.raster, ws.heap, ws.heap_cap,
+                                                            reinterpret_cast<const ushort4*>(ws.adj), d_trace);
     return cudaGetLastError();
 }
 

@@ -17,10 +17,12 @@ struct FloodWorkspace {
     int slots;                 // concurrent frames (one CTA each)
     size_t heap_cap;           // heap entries per slot
     uint8_t* gray; uint8_t* gray2; uint16_t* hsum; uint32_t* raster; uint32_t* heap;
+    uint16_t* adj;             // [num_cells][4] neighbours right, left, bottom, top (0xFFFF = none)
 };
 
 cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16);
-cudaError_t flood_workspace_create(const Mode& m, int sm_count, FloodWorkspace* ws);
+// adj_host: [num_cells][4] = AdjacentCellFinder::find for every cell (built by the caller from the cell geometry)
+cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* adj_host, FloodWorkspace* ws);
 void flood_workspace_destroy(FloodWorkspace* ws);
 // writes d_flags[f] for every frame: 0 = K1 result stands, CB200_FRAME_FALLBACK = re-decoded here,
 // CB200_FRAME_INEXACT = needed but skipped (no_fallback)

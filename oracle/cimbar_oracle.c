@@ -497,8 +497,11 @@ static unsigned decode_color_at(const cbo_mode* m, const uint8_t* rgb, int w, in
 typedef struct { uint16_t idx; uint8_t prio; } heap_elem;
 typedef struct { heap_elem* v; int n; int cap; } heap_t;
 
+int cbo_dbg_max_heap = 0, cbo_dbg_pushes = 0;   /* instrumentation for sizing the device heap (tests only) */
 static void heap_push(heap_t* h, uint16_t idx, uint8_t prio)
 {
+    ++cbo_dbg_pushes;
+    if (h->n + 1 > cbo_dbg_max_heap) cbo_dbg_max_heap = h->n + 1;
     if (h->n == h->cap) { h->cap *= 2; h->v = (heap_elem*)realloc(h->v, sizeof(heap_elem) * (size_t)h->cap); }
     int hole = h->n++;
     int parent = (hole - 1) / 2;
