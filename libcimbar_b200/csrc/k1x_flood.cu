@@ -60,6 +60,17 @@ __device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 16; }
 __device__ void heap_push(Heap& h, uint32_t idx, uint32_t prio)
 {
     int hole = h.n++;
+    if (hole < kHeapSmem) {          // common case: the whole sift-up path lives in shared memory
+        uint32_t* v = h.sm;
+        int parent = (hole - 1) / 2;
+        while (hole > 0) {
+            uint32_t pe = v[parent];
+            if (hprio(pe) <= prio) break;
+            v[hole] = pe; hole = parent; parent = (hole - 1) / 2;
+        }
+        v[hole] = (prio << 16) | idx;
+        return;
+    }
     int parent = (hole - 1) / 2;
     while (hole > 0 && hprio(h.get(parent)) > prio) { h.set(hole, h.get(parent)); hole = parent; parent = (hole - 1) / 2; }
     h.set(hole, (prio << 16) | idx);
@@ -71,6 +82,31 @@ __device__ uint32_t heap_pop(Heap& h)
     int len = --h.n;
     if (len == 0) return top;
     int hole = 0, second = 0;
+    if (len <= kHeapSmem) {          // common case: shared memory only
+        uint32_t* v = h.sm;
+        const int lim = (len - 1) / 2;
+        while (second < lim) {
+            second = 2 * (second + 1);
+            uint32_t a = v[second], b = v[second - 1];
+            if (hprio(a) > hprio(b)) { second--; a = b; }
+            v[hole] = a;
+            hole = second;
+        }
+        if ((len & 1) == 0 && second == (len - 2) / 2) {
+            second = 2 * (second + 1);
+            v[hole] = v[second - 1];
+            hole = second - 1;
+        }
+        const uint32_t vp = hprio(value);
+        int parent = (hole - 1) / 2;
+        while (hole > 0) {
+            uint32_t pe = v[parent];
+            if (hprio(pe) <= vp) break;
+            v[hole] = pe; hole = parent; parent = (hole - 1) / 2;
+        }
+        v[hole] = value;
+        return top;
+    }
     while (second < (len - 1) / 2) {
         second = 2 * (second + 1);
         uint32_t a = h.get(second), b = h.get(second - 1);
@@ -95,55 +131,48 @@ __device__ __forceinline__ uint32_t pack_instr(int dx, int dy, uint32_t prio, ui
 }
 __device__ __forceinline__ bool is_remaining(const FloodSmem& s, int i) { return (s.remaining[i >> 5] >> (i & 31)) & 1u; }
 
-// FloodDecodePositions::update_adjacents, FloodDecodePositions.cpp:69-83
-__device__ void update_adjacents(FloodSmem& s, Heap& h, const int adj[4], int dx, int dy, uint32_t err, uint32_t cooldown)
+// FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83), done by the warp:
+// lanes 0..11 each resolve one candidate neighbour -- lanes 0-3 the direct neighbours (right, left, bottom, top), lanes
+// 4-7 the horizontal horizon (right of right, its right, left of left, its left), lanes 8-11 the vertical horizon -- and
+// test it (still remaining? stored priority > err?); lane 0 then rewrites the inherit entries and pushes the survivors
+// in the reference's order (adjacents, horizon, vert).  The candidates are distinct cells, so the tests are independent.
+// adj: per-cell neighbours as AdjacentCellFinder::find computes them (AdjacentCellFinder.cpp:54-105), 0xFFFF = none.
+__device__ __forceinline__ int adj_dir(const ushort4* __restrict__ adj, int cell, int dir)
 {
-    for (int k = 0; k < 4; ++k) {
-        int next = adj[k];
-        if (next < 0 || !is_remaining(s, next)) continue;
-        uint32_t di = s.instr[next];
-        if (((di >> 16) & 0xFFu) <= err) continue;
-        s.instr[next] = pack_instr(dx, dy, err, cooldown);
-        heap_push(h, (uint32_t)next, err);
-    }
-}
-
-// FloodDecodePositions::update, FloodDecodePositions.cpp:86-129.  adj: per-cell neighbours (right, left, bottom, top) as
-// AdjacentCellFinder::find computes them (AdjacentCellFinder.cpp:54-105), precomputed once per context; 0xFFFF = none.
-__device__ __forceinline__ int adj_of(const ushort4* __restrict__ adj, int cell, int dir)
-{
+    if (cell < 0) return -1;
     ushort4 a = __ldg(&adj[cell]);
     unsigned v = dir == 0 ? a.x : dir == 1 ? a.y : dir == 2 ? a.z : a.w;
     return v == 0xFFFFu ? -1 : (int)v;
 }
-__device__ void flood_update(const ushort4* __restrict__ adj, FloodSmem& s, Heap& h, int index, int dx, int dy, uint32_t err, uint32_t cooldown)
+__device__ void flood_update_warp(const ushort4* __restrict__ adj, FloodSmem& s, Heap& h, int lane, int index, int dx, int dy,
+                                  uint32_t err, uint32_t cooldown, uint32_t self)
 {
-    ushort4 a4 = __ldg(&adj[index]);
-    int a[4] = {a4.x == 0xFFFFu ? -1 : (int)a4.x, a4.y == 0xFFFFu ? -1 : (int)a4.y, a4.z == 0xFFFFu ? -1 : (int)a4.z, a4.w == 0xFFFFu ? -1 : (int)a4.w};
-    update_adjacents(s, h, a, dx, dy, err, cooldown);
-    uint32_t self = s.instr[index];
-    uint32_t prev_err = (self >> 16) & 0xFFu, prev_cd = self >> 24;
-    if (prev_err < 3 && err < 3 && prev_cd == 4 && cooldown == 4) {
-        int rr = a[0], ll = a[1];
-        if (rr >= 0 && ll >= 0) {
-            int hz[4] = {-1, -1, -1, -1};
-            hz[0] = adj_of(adj, rr, 0);
-            if (hz[0] >= 0) hz[1] = adj_of(adj, hz[0], 0);
-            hz[2] = adj_of(adj, ll, 1);
-            if (hz[2] >= 0) hz[3] = adj_of(adj, hz[2], 1);
-            update_adjacents(s, h, hz, dx, dy, err, cooldown);
-        }
-        int uu = a[3], dd = a[2];
-        if (uu >= 0 && dd >= 0) {
-            int vt[4] = {-1, -1, -1, -1};
-            vt[0] = adj_of(adj, uu, 3);
-            if (vt[0] >= 0) vt[1] = adj_of(adj, vt[0], 3);
-            vt[2] = adj_of(adj, dd, 2);
-            if (vt[2] >= 0) vt[3] = adj_of(adj, vt[2], 2);
-            update_adjacents(s, h, vt, dx, dy, err, cooldown);
+    const uint32_t prev_err = (self >> 16) & 0xFFu, prev_cd = self >> 24;
+    const bool horizon = prev_err < 3 && err < 3 && prev_cd == 4 && cooldown == 4;
+    int cand = -1;
+    if (lane < 4) cand = adj_dir(adj, index, lane);
+    else if (lane < 12 && horizon) {
+        const int grp = (lane - 4) >> 1;               // 0: right chain, 1: left chain, 2: top chain, 3: bottom chain
+        const int dir = grp == 0 ? 0 : grp == 1 ? 1 : grp == 2 ? 3 : 2;
+        // horizontal horizon needs BOTH right and left neighbours, vertical BOTH top and bottom (FloodDecodePositions.cpp:102, :116)
+        const int a0 = adj_dir(adj, index, grp < 2 ? 0 : 3), a1 = adj_dir(adj, index, grp < 2 ? 1 : 2);
+        if (a0 >= 0 && a1 >= 0) {
+            const int first = adj_dir(adj, dir == (grp < 2 ? 0 : 3) ? a0 : a1, dir);   // neighbour of the direct neighbour
+            cand = ((lane - 4) & 1) ? adj_dir(adj, first, dir) : first;
         }
     }
-    // prev_error / prev_cooldown are written back here in the reference; the entry is reused for the result instead
+    bool push = false;
+    if (cand >= 0 && is_remaining(s, cand)) push = ((s.instr[cand] >> 16) & 0xFFu) > err;
+    // reference order: adj = right, left, bottom, top; horizon = right+1, right+2, left+1, left+2; vert = top+1, top+2, bottom+1, bottom+2
+    // lanes: 0..3 direct; 4,5 right chain; 6,7 left chain; 8,9 top chain; 10,11 bottom chain  -> already in reference order
+    uint32_t todo = __ballot_sync(0xffffffffu, push) & 0xFFFu;
+    const uint32_t entry = pack_instr(dx, dy, err, cooldown);
+    while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int c = __shfl_sync(0xffffffffu, cand, l);
+        if (lane == 0) { s.instr[c] = entry; heap_push(h, (uint32_t)c, err); }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- preprocessing (P1)
@@ -328,20 +357,22 @@ k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fall
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best_key, o); best_key = v < best_key ? v : best_key; }
-                if (lane == 0) {
-                    uint32_t dist = best_key >> 8, q = (best_key >> 4) & 0xFu, sym = best_key & 0xFu;
-                    int id = (0x620813754ULL >> (4 * q)) & 0xF;
-                    int bx = id % 3 - 1, by = id / 3 - 1;             // CellDrift::driftPairs, CellDrift.h:13-15
-                    int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
+                {   // every lane derives the (warp-uniform) decision from the reduced key
+                    const uint32_t dist = best_key >> 8, q = (best_key >> 4) & 0xFu, sym = best_key & 0xFu;
+                    const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);
+                    const int bx = id % 3 - 1, by = id / 3 - 1;             // CellDrift::driftPairs, CellDrift.h:13-15
+                    const int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
                     uint32_t ncd;                                      // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
                     if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
-                    flood_update(adj, s, heap, ci, ndx, ndy, dist, ncd);
-                    s.instr[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
-                    if (trace) {
-                        CellTrace tr;
-                        tr.order = (uint16_t)(count - 1); tr.x = (int16_t)(x + bx); tr.y = (int16_t)(y + by);
-                        tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
-                        trace[(size_t)f * ncells + ci] = tr;
+                    flood_update_warp(adj, s, heap, lane, ci, ndx, ndy, dist, ncd, ins);
+                    if (lane == 0) {
+                        s.instr[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
+                        if (trace) {
+                            CellTrace tr;
+                            tr.order = (uint16_t)(count - 1); tr.x = (int16_t)(x + bx); tr.y = (int16_t)(y + by);
+                            tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
+                            trace[(size_t)f * ncells + ci] = tr;
+                        }
                     }
                 }
                 __syncwarp();
