@@ -187,6 +187,9 @@ int cb200_sink_file_read(const cb200_sink* sink, uint32_t id, uint8_t* out, uint
 
 /* geometry without a context (for sizing buffers before a device exists) */
 int cb200_mode_info(int mode_val, cb200_info* out);
+/* host-side consistency checks of the mode tables the kernels rely on (cell adjacency in closed form vs the literal
+   AdjacentCellFinder evaluation); 0 = consistent */
+int cb200_selfcheck(int mode_val);
 /* Interleave::interleave_indices (Interleave.h:8-24): slot -> linear cell index; idx has total_cells entries */
 int cb200_interleave_indices(int mode_val, uint16_t* idx);
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
-    "cb200_sink_file_read",
+    "cb200_sink_file_read", "cb200_selfcheck",
 ]
 
 
@@ -82,6 +82,7 @@ def load_library():
     lib.cb200_sink_file_size.restype = C.c_int64
     lib.cb200_sink_file_size.argtypes = [vp, C.c_uint32]
     lib.cb200_sink_file_read.argtypes = [vp, C.c_uint32, u8p, C.c_uint64]
+    lib.cb200_selfcheck.argtypes = [C.c_int]
     lib.cb200_mode_info.argtypes = [C.c_int, C.POINTER(Info)]
     lib.cb200_interleave_indices.argtypes = [C.c_int, u16p]
     _lib = lib

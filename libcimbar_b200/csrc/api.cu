@@ -138,6 +138,58 @@ void interleave_indices(const Mode& m, std::vector<uint16_t>& idx)
                 idx.push_back((uint16_t)(i + part));
 }
 
+// neighbour table for the exact walk: AdjacentCellFinder::find (src/lib/cimb_translator/AdjacentCellFinder.cpp:54-105),
+// evaluated literally (position comparisons included) over the linear cell positions (CellPositions.cpp:5-50)
+void build_adjacency(const Mode& m, std::vector<uint16_t>& adj)
+{
+    const int n_cells = m.num_cells;
+    std::vector<int> xs(n_cells);
+    for (int k = 0, i = 0; k < m.cells_y; ++k) {
+        int base, ncols, x0;
+        cell_row_geom(m, k, base, ncols, x0);
+        for (int cc = 0; cc < ncols; ++cc, ++i) xs[i] = x0 + kSpacing * cc;
+    }
+    const int first_mid = m.top_cells, first_bottom = m.top_cells + m.mid_cells;
+    auto margin = [&](int index) { return (index < first_mid) ? 1 : (index < first_bottom ? 0 : 1); };
+    auto right = [&](int index) -> int { if (index < 0 || index >= n_cells - 1) return -1; int next = index + 1; return xs[next] < xs[index] ? -1 : next; };
+    auto left = [&](int index) -> int { int next = index - 1; if (next < 0) return -1; return xs[next] > xs[index] ? -1 : next; };
+    auto bottom = [&](int index) -> int {
+        if (index < 0 || index >= n_cells) return -1;
+        int inc = m.cells_x; if (margin(index)) inc -= m.corner;
+        int next = index + inc; if (margin(next)) next -= m.corner;
+        if (next < 0 || next >= n_cells) return -1;
+        return xs[next] != xs[index] ? -1 : next;
+    };
+    auto top = [&](int index) -> int {
+        int inc = m.cells_x; if (margin(index)) inc -= m.corner;
+        int next = index - inc; if (margin(next)) next += m.corner;
+        if (next < 0) return -1;
+        return xs[next] != xs[index] ? -1 : next;
+    };
+    adj.assign((size_t)n_cells * 4, 0);
+    for (int i = 0; i < n_cells; ++i) {
+        int v[4] = {right(i), left(i), bottom(i), top(i)};
+        for (int d = 0; d < 4; ++d) adj[(size_t)i * 4 + d] = v[d] < 0 ? (uint16_t)0xFFFF : (uint16_t)v[d];
+    }
+}
+
+// the kernels use the (row, column) form of the same relation (cell_neighbour): the two must agree everywhere
+bool adjacency_consistent(const Mode& m, const std::vector<uint16_t>& adj)
+{
+    for (int i = 0; i < m.num_cells; ++i) {
+        int k, cc, k2, c2;
+        cell_row_col(m, i, k, cc);
+        int base, ncols, x0;
+        cell_row_geom(m, k, base, ncols, x0);
+        if (base + cc != i) return false;
+        for (int d = 0; d < 4; ++d) {
+            int v = cell_neighbour(m, k, cc, d, k2, c2);
+            if ((v < 0 ? 0xFFFF : v) != adj[(size_t)i * 4 + d]) return false;
+        }
+    }
+    return true;
+}
+
 }  // namespace
 
 struct cb200_ctx {
@@ -249,6 +301,16 @@ int cb200_mode_info(int mode_val, cb200_info* out)
     return CB200_OK;
 }
 
+int cb200_selfcheck(int mode_val)
+{
+    Mode m;
+    if (!mode_init(m, mode_val)) return fail(CB200_ERR_MODE, "unsupported mode_val");
+    std::vector<uint16_t> adj;
+    build_adjacency(m, adj);
+    if (!adjacency_consistent(m, adj)) return fail(CB200_ERR_MODE, "adjacency self-check failed");
+    return CB200_OK;
+}
+
 int cb200_interleave_indices(int mode_val, uint16_t* idx)
 {
     if (!idx) return fail(CB200_ERR_ARG, "null idx");
@@ -335,37 +397,10 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
         CK(encode_init_tables(gexp, glog), "encode tables");
         for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[k][i]), "cudaEventCreate");
     }
-    {   // neighbour table for the exact walk: AdjacentCellFinder::find (src/lib/cimb_translator/AdjacentCellFinder.cpp:54-105),
-        // evaluated literally (position comparisons included) over the linear cell positions (CellPositions.cpp:5-50)
-        const int n_cells = m.num_cells;
-        std::vector<int> xs(n_cells);
-        for (int k = 0, i = 0; k < m.cells_y; ++k) {
-            int base, ncols, x0;
-            cell_row_geom(m, k, base, ncols, x0);
-            for (int cc = 0; cc < ncols; ++cc, ++i) xs[i] = x0 + kSpacing * cc;
-        }
-        const int first_mid = m.top_cells, first_bottom = m.top_cells + m.mid_cells;
-        auto margin = [&](int index) { return (index < first_mid) ? 1 : (index < first_bottom ? 0 : 1); };
-        auto right = [&](int index) -> int { if (index < 0 || index >= n_cells - 1) return -1; int next = index + 1; return xs[next] < xs[index] ? -1 : next; };
-        auto left = [&](int index) -> int { int next = index - 1; if (next < 0) return -1; return xs[next] > xs[index] ? -1 : next; };
-        auto bottom = [&](int index) -> int {
-            if (index < 0 || index >= n_cells) return -1;
-            int inc = m.cells_x; if (margin(index)) inc -= m.corner;
-            int next = index + inc; if (margin(next)) next -= m.corner;
-            if (next < 0 || next >= n_cells) return -1;
-            return xs[next] != xs[index] ? -1 : next;
-        };
-        auto top = [&](int index) -> int {
-            int inc = m.cells_x; if (margin(index)) inc -= m.corner;
-            int next = index - inc; if (margin(next)) next += m.corner;
-            if (next < 0) return -1;
-            return xs[next] != xs[index] ? -1 : next;
-        };
-        std::vector<uint16_t> adj((size_t)n_cells * 4);
-        for (int i = 0; i < n_cells; ++i) {
-            int v[4] = {right(i), left(i), bottom(i), top(i)};
-            for (int d = 0; d < 4; ++d) adj[(size_t)i * 4 + d] = v[d] < 0 ? (uint16_t)0xFFFF : (uint16_t)v[d];
-        }
+    {
+        std::vector<uint16_t> adj;
+        build_adjacency(m, adj);
+        if (!adjacency_consistent(m, adj)) { cb200_destroy(c); return fail(CB200_ERR_MODE, "adjacency self-check failed"); }
         CK(flood_workspace_create(m, c->sm_count, adj.data(), &c->flood), "flood workspace");
     }
     *out = c;

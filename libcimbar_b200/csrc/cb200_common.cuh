@@ -45,6 +45,40 @@ __host__ __device__ inline void cell_row_geom(const Mode& m, int k, int& base, i
     else { base = m.top_cells + m.mid_cells + (k - (m.cells_y - m.corner)) * narrow; ncols = narrow; x0 = m.cell_offset + kSpacing * m.corner; }
 }
 
+// linear cell index -> (cell row k, column c within that row)
+__host__ __device__ inline void cell_row_col(const Mode& m, int index, int& k, int& c)
+{
+    int narrow = m.cells_x - 2 * m.corner;
+    if (index < m.top_cells) { k = index / narrow; c = index - k * narrow; }
+    else if (index < m.top_cells + m.mid_cells) { int q = index - m.top_cells; k = q / m.cells_x; c = q - k * m.cells_x; k += m.corner; }
+    else { int q = index - m.top_cells - m.mid_cells; k = q / narrow; c = q - k * narrow; k += m.cells_y - m.corner; }
+}
+
+// AdjacentCellFinder::find in (row, column) arithmetic -- equivalent to the reference's index/position logic
+// (src/lib/cimb_translator/AdjacentCellFinder.cpp:54-105; equivalence is asserted against the literal evaluation when a
+// context is created).  dir: 0 right, 1 left, 2 bottom, 3 top.  Returns the neighbour's linear index or -1.
+__host__ __device__ inline int cell_neighbour(const Mode& m, int k, int c, int dir, int& k2, int& c2)
+{
+    int base, ncols, x0;
+    cell_row_geom(m, k, base, ncols, x0);
+    k2 = k; c2 = c;
+    if (dir == 0) { if (c + 1 >= ncols) return -1; c2 = c + 1; return base + c2; }
+    if (dir == 1) { if (c == 0) return -1; c2 = c - 1; return base + c2; }
+    k2 = (dir == 2) ? k + 1 : k - 1;
+    if (k2 < 0 || k2 >= m.cells_y) return -1;
+    // two quirks of the reference's index arithmetic, kept because the walk order depends on them: in the marker rows the
+    // row stride is cells_x - corner, so from the second-to-last top row the last `corner` cells step INTO the first mid row
+    // (and symmetrically upwards from the second bottom row), fail the x comparison, and report no neighbour
+    // (AdjacentCellFinder.cpp:79-105)
+    if (dir == 2 && k == m.corner - 2 && c >= ncols - m.corner) return -1;
+    if (dir == 3 && k == m.cells_y - m.corner + 1 && c < m.corner) return -1;
+    int base2, ncols2, x02;
+    cell_row_geom(m, k2, base2, ncols2, x02);
+    c2 = c + (x0 - x02) / kSpacing;          // same x in the neighbouring row (rows next to the anchors are narrower)
+    if (c2 < 0 || c2 >= ncols2) return -1;
+    return base2 + c2;
+}
+
 // per-cell result byte written by K1/K1x
 constexpr uint8_t kCellDirty = 0x80;   // centre hash did not win -> frame needs the exact flood walk
 

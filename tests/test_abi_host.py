@@ -44,6 +44,13 @@ def test_mode_table_matches_oracle(mode_val):
     assert np.array_equal(idx.astype(np.uint32), want)
 
 
+@pytest.mark.parametrize("mode_val", [68, 4, 8, 67, 66])
+def test_closed_form_adjacency_matches_literal_finder(mode_val):
+    # the exact-walk kernel uses (row, column) arithmetic for AdjacentCellFinder; it must equal the literal evaluation,
+    # which in turn equals the reference's own class (tests/test_oracle_vs_ref.py::test_cell_positions_and_adjacency)
+    assert cb.load_library().cb200_selfcheck(mode_val) == 0
+
+
 def test_unknown_mode_is_an_error():
     with pytest.raises(cb.Cb200Error):
         cb.mode_info(999)
