@@ -138,28 +138,28 @@ __device__ __forceinline__ bool is_remaining(const FloodSmem& s, int i) { return
 // test it (still remaining? stored priority > err?); lane 0 then rewrites the inherit entries and pushes the survivors
 // in the reference's order (adjacents, horizon, vert).  The candidates are distinct cells, so the tests are independent.
 // adj: per-cell neighbours as AdjacentCellFinder::find computes them (AdjacentCellFinder.cpp:54-105), 0xFFFF = none.
-__device__ void flood_update_warp(const Mode& m, FloodSmem& s, Heap& h, int lane, int index, int dx, int dy,
+__device__ __forceinline__ int adj_dir(const ushort4* __restrict__ adj, int cell, int dir)
+{
+    if (cell < 0) return -1;
+    ushort4 a = __ldg(&adj[cell]);
+    unsigned v = dir == 0 ? a.x : dir == 1 ? a.y : dir == 2 ? a.z : a.w;
+    return v == 0xFFFFu ? -1 : (int)v;
+}
+__device__ void flood_update_warp(const ushort4* __restrict__ adj, FloodSmem& s, Heap& h, int lane, int index, int dx, int dy,
                                   uint32_t err, uint32_t cooldown, uint32_t self)
 {
     const uint32_t prev_err = (self >> 16) & 0xFFu, prev_cd = self >> 24;
     const bool horizon = prev_err < 3 && err < 3 && prev_cd == 4 && cooldown == 4;
-    int k, c;
-    cell_row_col(m, index, k, c);
     int cand = -1;
-    if (lane < 4) { int k2, c2; cand = cell_neighbour(m, k, c, lane, k2, c2); }
+    if (lane < 4) cand = adj_dir(adj, index, lane);
     else if (lane < 12 && horizon) {
         const int grp = (lane - 4) >> 1;               // 0: right chain, 1: left chain, 2: top chain, 3: bottom chain
         const int dir = grp == 0 ? 0 : grp == 1 ? 1 : grp == 2 ? 3 : 2;
-        // the horizontal horizon needs BOTH right and left neighbours, the vertical one BOTH top and bottom
-        // (FloodDecodePositions.cpp:102, :116)
-        int ka, ca, kb, cb;
-        const int a0 = cell_neighbour(m, k, c, grp < 2 ? 0 : 3, ka, ca), a1 = cell_neighbour(m, k, c, grp < 2 ? 1 : 2, kb, cb);
+        // horizontal horizon needs BOTH right and left neighbours, vertical BOTH top and bottom (FloodDecodePositions.cpp:102, :116)
+        const int a0 = adj_dir(adj, index, grp < 2 ? 0 : 3), a1 = adj_dir(adj, index, grp < 2 ? 1 : 2);
         if (a0 >= 0 && a1 >= 0) {
-            const bool use_a = dir == (grp < 2 ? 0 : 3);
-            int k1 = use_a ? ka : kb, c1 = use_a ? ca : cb, k2, c2;
-            int first = cell_neighbour(m, k1, c1, dir, k2, c2);          // neighbour of the direct neighbour
-            if (((lane - 4) & 1) == 0) cand = first;
-            else if (first >= 0) { int k3, c3; cand = cell_neighbour(m, k2, c2, dir, k3, c3); }
+            const int first = adj_dir(adj, dir == (grp < 2 ? 0 : 3) ? a0 : a1, dir);   // neighbour of the direct neighbour
+            cand = ((lane - 4) & 1) ? adj_dir(adj, first, dir) : first;
         }
     }
     bool push = false;
@@ -366,7 +366,7 @@ k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fall
                     const int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
                     uint32_t ncd;                                      // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
                     if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
-                    flood_update_warp(m, s, heap, lane, ci, ndx, ndy, dist, ncd, ins);
+                    flood_update_warp(adj, s, heap, lane, ci, ndx, ndy, dist, ncd, ins);
                     if (lane == 0) {
                         s.instr[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
                         if (trace) {
