@@ -191,10 +191,50 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
             continue;
         }
 
-        // ---- Berlekamp-Massey (decode.c:30-116), coefficients in shared memory, updated lane-parallel
+        // ---- Berlekamp-Massey (decode.c:30-116).  Field arithmetic is exact, so scale = disc / last_disc is applied as one
+        //      multiplication (libcorrect writes mul-then-div per coefficient: same element); what must match libcorrect is
+        //      the update rule and the order bookkeeping, because they decide the locator it reports for uncorrectable blocks.
+        uint32_t numerrors = 0, loc_order = 0, last_order = 0, last_disc = 1, delay = 1;
+        if (T == 1) {
+            // parity <= 31: coefficient j of the locator / previous locator lives in lane j, syndrome j in lane j
+            uint32_t loc = (lane == 0), last = (lane == 0);
+            const uint32_t syn = (lane < md) ? (uint32_t)w.synd[lane] : 0u;
+            const uint32_t lsyn = s.log[syn];
+            for (uint32_t i = 0; i < (uint32_t)md; ++i) {
+                // disc = S[i] ^ sum_{j=1..numerrors} loc[j] * S[i-j]
+                const uint32_t sj = __shfl_sync(0xffffffffu, syn, (int)(i - (uint32_t)lane) & 31);
+                const uint32_t lsj = __shfl_sync(0xffffffffu, lsyn, (int)(i - (uint32_t)lane) & 31);
+                uint32_t term = 0;
+                if ((uint32_t)lane >= 1u && (uint32_t)lane <= numerrors && loc != 0 && sj != 0) term = s.exp[(uint32_t)s.log[loc] + lsj];
+                const uint32_t disc = __reduce_xor_sync(0xffffffffu, term) ^ __shfl_sync(0xffffffffu, syn, (int)i);
+                if (disc == 0) { delay++; continue; }
+                const uint32_t lscale = 255u + (uint32_t)s.log[disc] - (uint32_t)s.log[last_disc];      // log(disc / last_disc), last_disc != 0
+                const uint32_t top = last_order + delay;
+                const uint32_t shifted = __shfl_up_sync(0xffffffffu, last, delay);                              // last[j - delay]
+                const uint32_t lsc = lscale >= 255u ? lscale - 255u : lscale;                                   // in [0, 254]: exp index stays < 512
+                const uint32_t sh = ((uint32_t)lane >= delay && (uint32_t)lane <= top && shifted != 0) ? (uint32_t)s.exp[(uint32_t)s.log[shifted] + lsc] : 0u;
+                if (2 * numerrors <= i) {
+                    // last <- x^delay * scale * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
+                    if ((uint32_t)lane <= top) { const uint32_t t0 = loc; loc ^= sh; last = t0; }
+                    const uint32_t tmp = loc_order;
+                    loc_order = top; last_order = tmp;
+                    numerrors = i + 1 - numerrors;
+                    last_disc = disc;
+                    delay = 1;
+                    continue;
+                }
+                // no length change: loc[j+delay] ^= scale * last[j]
+                loc ^= sh;
+                if (top > loc_order) loc_order = top;
+                delay++;
+            }
+            w.loc[lane] = (uint8_t)loc;
+            if (lane < 8) w.loc[32 + lane] = 0;
+            __syncwarp();
+        } else {
+        // coefficients in shared memory, updated lane-parallel (parity > 31 needs more than one coefficient per lane)
         for (int j = lane; j < kMaxParity + 8; j += 32) { w.loc[j] = (j == 0); w.last[j] = (j == 0); }
         __syncwarp();
-        uint32_t numerrors = 0, loc_order = 0, last_order = 0, last_disc = 1, delay = 1;
         for (uint32_t i = 0; i < (uint32_t)md; ++i) {
             uint32_t part = 0;
             for (uint32_t j = 1 + lane; j <= numerrors; j += 32) part ^= gf_mul(s, w.loc[j], w.synd[i - j]);
@@ -229,6 +269,7 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
             __syncwarp();
             if (last_order + delay > loc_order) loc_order = last_order + delay;
             delay++;
+        }
         }
         const uint32_t order = loc_order;
 

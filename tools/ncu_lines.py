@@ -15,6 +15,9 @@ import sys
 import tempfile
 
 rep, kernel, srcfile = sys.argv[1], sys.argv[2], sys.argv[3]
+# kernel may be "ncu_regex:mangled_substring" to pick one template instance in the cubin
+mangled = kernel.split(":", 1)[1] if ":" in kernel else kernel
+kernel = kernel.split(":", 1)[0]
 top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "libcimbar_b200", "lib", "libcb200.so")
@@ -35,7 +38,7 @@ for f in os.listdir(tmp):
     if not f.endswith(".cubin"):
         continue
     dis = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-    m = re.search(r"^\.text\.\S*" + kernel + r"\S*:\n", dis, re.M)
+    m = re.search(r"^\.text\.\S*" + mangled + r"\S*:\n", dis, re.M)
     if not m:
         continue
     cur = None
