@@ -347,3 +347,69 @@ def test_cpp_shims_rerun_reference_unit_tests(cb, tmp_path):
             assert lines[0] == first22[(sample, mode)]
         if sample == "6bit/4color_ecc30_fountain_0.png":
             assert lines[1] == "0 62 8"                                   # CimbReaderTest.cpp:37-58: first read
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_degenerate_frames_match_oracle(cb):
+    """all-black, all-white, pure noise, a vertical gradient: no valid tiles anywhere, every path still has to agree"""
+    m = ORA.mode(68)
+    rng = np.random.default_rng(9)
+    frames = np.zeros((4, 1024, 1024, 3), np.uint8)
+    frames[1] = 255
+    frames[2] = rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+    frames[3] = (np.arange(1024, dtype=np.uint32)[:, None, None] // 4).astype(np.uint8)
+    ctx = cb.Context(68, max_frames=4)
+    raw, ff = ctx.decode_raw(frames)
+    data, ok, _ = ctx.decode(frames)
+    chunks, count, mask, _ = ctx.decode_fountain(frames)
+    for f in range(4):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f])), f
+        odata, ook = ORA.decode(m, frames[f])
+        assert np.array_equal(ok[f], ook) and np.array_equal(data[f], odata), f
+        good, ochunks, omask = ORA.decode_fountain(m, frames[f])
+        assert mask[f] == omask and count[f] * m.chunk_size == good
+    ctx.close()
+
+
+def test_cell_trace_matches_oracle_walk(cb):
+    """cb200_decode_cells == the reference's CimbReader loop: same walk order, positions, drift offsets and distances"""
+    for sample, mode in (("b/ex2434.jpg", 68), ("6bit/4_30_f0_627_extract.jpg", 4), ("b/tr_1.png", 68)):
+        m = ORA.mode(mode)
+        rgb = load_sample(sample)
+        ctx = cb.Context(mode, max_frames=1)
+        cells, trace = ctx.decode_cells(rgb)
+        _, ocells = ORA.decode_raw(m, rgb, want_cells=True)
+        assert np.array_equal(trace[0]["order"], ocells["order"]), sample
+        assert np.array_equal(trace[0]["x"], ocells["x"]) and np.array_equal(trace[0]["y"], ocells["y"])
+        assert np.array_equal(trace[0]["drift_offset"], ocells["drift_offset"])
+        assert np.array_equal(trace[0]["distance"], ocells["distance"])
+        assert np.array_equal(cells[0] & 15, ocells["symbol"]) and np.array_equal((cells[0] >> 4) & 7, ocells["color"])
+        ctx.close()
+
+
+def test_batch_mixing_clean_and_dirty_frames(cb):
+    """a batch where only some frames need the exact walk: flags identify exactly those, every frame is bit-exact"""
+    m, payloads, frames = synth_frames(68, 6, seed=21)
+    cam = load_sample("b/ex2434.jpg")
+    batch = np.stack([frames[0], cam, frames[1], frames[2], cam, frames[3]])
+    ctx = cb.Context(68, max_frames=6)
+    raw, ff = ctx.decode_raw(batch)
+    assert [int(x & cb.FRAME_FALLBACK) for x in ff] == [0, 1, 0, 0, 1, 0]
+    for f in range(6):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, batch[f])), f
+    # NO_FALLBACK: dirty frames are reported, not silently wrong
+    raw2, ff2 = ctx.decode_raw(batch, flags=cb.FLAG_NO_FALLBACK)
+    assert [int(x) for x in ff2] == [0, cb.FRAME_INEXACT, 0, 0, cb.FRAME_INEXACT, 0]
+    ctx.close()
+
+
+def test_two_contexts_and_modes_coexist(cb):
+    """tables are per context / per launch: interleaving a mode-B and a legacy 4C context must not cross-contaminate"""
+    mb, pb, fb = synth_frames(68, 2, seed=31)
+    m4, p4, f4 = synth_frames(4, 2, seed=32)
+    cb_b, cb_4 = cb.Context(68, max_frames=2), cb.Context(4, max_frames=2)
+    for _ in range(2):
+        d4, ok4, _ = cb_4.decode(f4)
+        db, okb, _ = cb_b.decode(fb)
+        assert ok4.all() and okb.all() and np.array_equal(d4, p4) and np.array_equal(db, pb)
+    cb_b.close(); cb_4.close()
