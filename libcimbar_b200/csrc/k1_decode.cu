@@ -188,19 +188,42 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 //                             unit 0, all dead now), L2 prefetch further ahead
 //   B(k):   box sums, threshold -> raster[it&1]
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
-template <int NC>
+template <int NC, bool G1024>
 __global__ void __launch_bounds__(kK1Threads, 4)
-k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
+k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
 {
+    // G1024: the 1024x1024 / 112x112-cell geometry of modes B, 4C and 8C as compile-time constants (GridConf.h:121-141);
+    // the other modes (Bm 1024x720, Bu 736x637) take every dimension from the Mode struct
+    struct Geo {
+        const Mode& q;
+        __device__ __forceinline__ int width() const { return G1024 ? 1024 : q.width; }
+        __device__ __forceinline__ int height() const { return G1024 ? 1024 : q.height; }
+        __device__ __forceinline__ int cells_x() const { return G1024 ? 112 : q.cells_x; }
+        __device__ __forceinline__ int cells_y() const { return G1024 ? 112 : q.cells_y; }
+        __device__ __forceinline__ int corner() const { return G1024 ? 6 : q.corner; }
+        __device__ __forceinline__ int cell_offset() const { return G1024 ? 8 : q.cell_offset; }
+        __device__ __forceinline__ int num_cells() const { return G1024 ? 12400 : q.num_cells; }
+        __device__ __forceinline__ int top_cells() const { return G1024 ? 600 : q.top_cells; }
+        __device__ __forceinline__ int mid_cells() const { return G1024 ? 11200 : q.mid_cells; }
+        __device__ __forceinline__ int symbol_bits() const { return G1024 ? 4 : q.symbol_bits; }
+        __device__ __forceinline__ void row_geom(int k, int& base, int& ncols, int& x0) const
+        {
+            const int narrow = cells_x() - 2 * corner();
+            if (k < corner()) { base = k * narrow; ncols = narrow; x0 = cell_offset() + kSpacing * corner(); }
+            else if (k < cells_y() - corner()) { base = top_cells() + (k - corner()) * cells_x(); ncols = cells_x(); x0 = cell_offset(); }
+            else { base = top_cells() + mid_cells() + (k - (cells_y() - corner())) * narrow; ncols = narrow; x0 = cell_offset() + kSpacing * corner(); }
+        }
+    };
+    const Geo m{mm};
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int W = m.width;
+    const int W = m.width();
     const uint32_t row_bytes = (uint32_t)W * 3u;
     const uint32_t unit_bytes = row_bytes * kUnitRows;
     const uint32_t stage_bytes = row_bytes * kStageRows;
-    const size_t frame_bytes = (size_t)row_bytes * (size_t)m.height;
+    const size_t frame_bytes = (size_t)row_bytes * (size_t)m.height();
     const int n_units = n_frames * bands;
 
     if (tid == 0) {
@@ -211,7 +234,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
         unsigned long long L = c_tiles_L[tid];
         uint32_t lo = (uint32_t)L, hi = (uint32_t)(L >> 32);
         s.tiles_by_sym[tid] = make_uint2(lo, hi);
-        s.tiles_by_slot[(lo * m.hash_mul) >> 28] = make_uint4(lo, hi, (uint32_t)tid, 0u);
+        s.tiles_by_slot[(lo * mm.hash_mul) >> 28] = make_uint4(lo, hi, (uint32_t)tid, 0u);
     }
     for (int i = tid; i < 256; i += kK1Threads) s.adjust[i] = c_adjust[i];
     __syncthreads();
@@ -222,7 +245,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     const int tl = (t == 0) ? 0 : t - 1, tr = (t + 1 < nthr_px) ? t + 1 : t;   // halo sources (frame borders are never used)
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
     const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
-    const int narrow = m.cells_x - 2 * m.corner, last_cell = m.num_cells - 1, first_mid = m.top_cells;
+    const int narrow = m.cells_x() - 2 * m.corner(), last_cell = m.num_cells() - 1, first_mid = m.top_cells();
 
     // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1).  Thread 0 is the TMA producer.
     struct Cursor { int u, k, kend; const uint8_t* src; bool valid; };
@@ -230,9 +253,9 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
         c.valid = c.u < n_units;
         if (!c.valid) return;
         int f = c.u / bands, b = c.u - f * bands;
-        c.k = (m.cells_y * b) / bands - 1;
-        c.kend = (m.cells_y * (b + 1)) / bands;
-        c.src = rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset + kSpacing * c.k + 2) * row_bytes;
+        c.k = (m.cells_y() * b) / bands - 1;
+        c.kend = (m.cells_y() * (b + 1)) / bands;
+        c.src = rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset() + kSpacing * c.k + 2) * row_bytes;
     };
     auto cursor_next = [&](Cursor& c) {
         if (++c.k < c.kend) { c.src += stage_bytes; return; }   // consecutive stages are contiguous in the frame
@@ -264,7 +287,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
     // artefacts, ~1 % of a clean frame) are searched one at a time by the whole warp.
     auto symbol_stage = [&](int k, uint32_t rbuf, uint32_t col, uint8_t* out, bool& any_dirty) {
         int base, ncols, x0;
-        cell_row_geom(m, k, base, ncols, x0);
+        m.row_geom(k, base, ncols, x0);
         const bool active = t < ncols;
         const uint32_t (*rast)[kRastWords] = s.raster[rbuf];
         const uint32_t o = (uint32_t)(x0 + kSpacing * t);     // window col 1 == pixel x
@@ -279,7 +302,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                 lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
                 hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
             }
-            uint4 te = s.tiles_by_slot[(lo * m.hash_mul) >> 28];
+            uint4 te = s.tiles_by_slot[(lo * mm.hash_mul) >> 28];
             exact = (te.x == lo) & (te.y == hi);
             sym = te.z;
         }
@@ -291,22 +314,22 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
             const uint32_t lo_ = __shfl_sync(0xffffffffu, o, leader);
             const int lcell = __shfl_sync(0xffffffffu, cell, leader);
             const bool seed = (lcell == 0) | (lcell == narrow - 1) | (lcell == last_cell) | (lcell == last_cell - (narrow - 1)) |
-                              (lcell == first_mid) | (lcell == first_mid + m.cells_x - 1) | (lcell == last_cell - first_mid) |
-                              (lcell == last_cell - (first_mid + m.cells_x - 1));
+                              (lcell == first_mid) | (lcell == first_mid + m.cells_x() - 1) | (lcell == last_cell - first_mid) |
+                              (lcell == last_cell - (first_mid + m.cells_x() - 1));
             const uint32_t key = warp_symbol_search(s, rbuf, lo_ - 1u, seed, lane);
             if (lane == leader) {
                 sym = key & 15u;
                 if (((key >> 4) & 15u) != 0u) { dirty = kCellDirty; any_dirty = true; }   // order index 0 == centre hash (id 4)
             }
         }
-        if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits) | dirty);
+        if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits()) | dirty);
     };
 
     uint32_t it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int f = u / bands, b = u - f * bands;
-        int k0 = (m.cells_y * b) / bands, k1 = (m.cells_y * (b + 1)) / bands;
-        uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells;
+        int k0 = (m.cells_y() * b) / bands, k1 = (m.cells_y() * (b + 1)) / bands;
+        uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells();
 
         uint32_t hprev[5][4], Pprev[2][4], nV[4];
 #pragma unroll
@@ -369,7 +392,7 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
             {
                 int base, ncols, x0;
                 if (k >= k0) {
-                    cell_row_geom(m, k, base, ncols, x0);
+                    m.row_geom(k, base, ncols, x0);
                     if (t < ncols && NC > 1) {
                         const int x = x0 + kSpacing * t + 1;
                         uint32_t R = carryR, G = carryG, B = carryB;
@@ -378,12 +401,12 @@ k1_decode_kernel(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, in
                         rgb_row6(ub[0] + 2u * row_bytes, x, R, G, B);
                         rgb_row6(ub[1], x, R, G, B);
                         rgb_row6(ub[1] + row_bytes, x, R, G, B);
-                        col = best_color<NC>(s.adjust, m, R / 36u, G / 36u, B / 36u);
+                        col = best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
                     }
                 }
                 carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
                 if (k + 1 < k1) {
-                    cell_row_geom(m, k + 1, base, ncols, x0);
+                    m.row_geom(k + 1, base, ncols, x0);
                     if (t < ncols) rgb_row6(ub[2] + 2u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
                 }
             }
@@ -501,17 +524,27 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k1_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem) + 64 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k1_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+    const int smem_max = (int)sizeof(K1Smem) + 64 * 1024;
+    if ((e = cudaFuncSetAttribute(k1_decode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k1_decode_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k1_decode_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k1_decode_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
 }
 
 cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead,
                       uint8_t* d_cellvals, uint32_t* d_dirty, cudaStream_t stream)
 {
     const int extra = getenv("CB200_K1_EXTRA_SMEM") ? atoi(getenv("CB200_K1_EXTRA_SMEM")) : 0;   // tuning only: lowers CTAs/SM
-    if (m.color_bits == 3) k1_decode_kernel<8><<<grid, kK1Threads, sizeof(K1Smem), stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
-    else k1_decode_kernel<4><<<grid, kK1Threads, sizeof(K1Smem) + extra, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+    const size_t smem = sizeof(K1Smem) + extra;
+    const bool g1024 = m.width == 1024 && m.height == 1024 && m.cells_x == 112 && m.cells_y == 112 && m.corner == 6 &&
+                       m.cell_offset == 8 && m.symbol_bits == 4;
+    if (m.color_bits == 3) {
+        if (g1024) k1_decode_kernel<8, true><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+        else k1_decode_kernel<8, false><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+    } else {
+        if (g1024) k1_decode_kernel<4, true><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+        else k1_decode_kernel<4, false><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+    }
     return cudaGetLastError();
 }
 
