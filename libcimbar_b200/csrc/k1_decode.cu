@@ -35,7 +35,7 @@ constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + 
 constexpr int kRastWords = kRastPitch / 4;
 
 struct __align__(128) K1Smem {
-    uint8_t ring[kRingUnits][kUnitRows * kMaxW * 3];   // raw RGB rows, filled by TMA
+    uint8_t ring[kRingUnits * kUnitRows * kMaxW * 3];  // raw RGB rows, filled by TMA; unit p starts at p * (3 * row_bytes)
     uint32_t raster[2][10][kRastWords];       // 1-bit threshold rows of the current / previous stage
     uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
@@ -262,23 +262,21 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         c.u += gridDim.x;
         cursor_unit(c);
     };
-    // stage `i` occupies ring units (3i, 3i+1, 3i+2) mod 5; one mbarrier transaction covers its three bulk copies
-    auto issue_stage = [&](const Cursor& c, uint32_t i) {
+    // stage `i` occupies ring units (3i, 3i+1, 3i+2) mod 5 starting at unit `p`; the source rows are contiguous, so the
+    // stage is one bulk copy, or two when it wraps around the end of the ring; one mbarrier transaction covers both
+    auto issue_stage = [&](const Cursor& c, uint32_t i, uint32_t p) {
         unsigned long long* bar = &s.full_bar[i & 1u];
         mbar_expect_tx(bar, stage_bytes);
-        uint32_t p = (3u * i) % kRingUnits;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            tma_bulk_g2s(s.ring[p], c.src + (size_t)q * unit_bytes, unit_bytes, bar);
-            p = (p + 1u == kRingUnits) ? 0u : p + 1u;
-        }
+        const uint32_t first = (kRingUnits - p) < 3u ? (kRingUnits - p) : 3u;      // units before the wrap
+        tma_bulk_g2s(s.ring + p * unit_bytes, c.src, first * unit_bytes, bar);
+        if (first < 3u) tma_bulk_g2s(s.ring, c.src + (size_t)first * unit_bytes, (3u - first) * unit_bytes, bar);
     };
     Cursor nxt, pre;                              // next stage to load into shared memory / to prefetch into L2
     nxt.u = blockIdx.x; nxt.valid = false; pre.valid = false;
     if (tid == 0) {
         cursor_unit(nxt);
         pre = nxt;
-        if (nxt.valid) { issue_stage(nxt, 0u); cursor_next(nxt); cursor_next(pre); }
+        if (nxt.valid) { issue_stage(nxt, 0u, 0u); cursor_next(nxt); cursor_next(pre); }
         for (int i = 0; i < l2_ahead && pre.valid; ++i) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
     }
 
@@ -325,7 +323,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits()) | dirty);
     };
 
-    uint32_t it = 0;
+    uint32_t it = 0, ring_pos = 0;                 // ring unit of the current stage's first row: (3 * it) mod 5
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int f = u / bands, b = u - f * bands;
         int k0 = (m.cells_y() * b) / bands, k1 = (m.cells_y() * (b + 1)) / bands;
@@ -346,10 +344,10 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         for (int k = k0 - 1; k < k1; ++k, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
             // the three ring units of this stage: rows 0-2, 3-5, 6-8
-            const uint32_t p0 = (3u * it) % kRingUnits;
+            const uint32_t p0 = ring_pos;
             const uint32_t p1 = (p0 + 1u == kRingUnits) ? 0u : p0 + 1u;
             const uint32_t p2 = (p1 + 1u == kRingUnits) ? 0u : p1 + 1u;
-            uint8_t* ub[3] = {s.ring[p0], s.ring[p1], s.ring[p2]};
+            uint8_t* ub[3] = {s.ring + p0 * unit_bytes, s.ring + p1 * unit_bytes, s.ring + p2 * unit_bytes};
             mbar_wait(&s.full_bar[buf], ph);
 
             // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+4]); halo word E_r = (g0,g1,g6,g7)
@@ -413,7 +411,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
             __syncthreads();
             if (tid == 0) {
                 // dead now: stage it-1's units 1,2 (their parked halo words were last read in B(k-1)) and this stage's unit 0
-                if (nxt.valid) { issue_stage(nxt, it + 1u); cursor_next(nxt); }
+                if (nxt.valid) { issue_stage(nxt, it + 1u, p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u); cursor_next(nxt); }
                 if (l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
             }
 
@@ -461,6 +459,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
             // ---------------- S(k-1): its raster was finished by every thread before the barrier above
             if (k - 1 >= k0) symbol_stage(k - 1, buf ^ 1u, col_prev, out, any_dirty);
             col_prev = col;
+            ring_pos = p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u;
         }
         // the last cell row of the unit still needs its symbols: one more barrier to see its complete raster
         __syncthreads();
