@@ -413,3 +413,48 @@ def test_two_contexts_and_modes_coexist(cb):
         db, okb, _ = cb_b.decode(fb)
         assert ok4.all() and okb.all() and np.array_equal(d4, p4) and np.array_equal(db, pb)
     cb_b.close(); cb_4.close()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 4 (one GPU)
+def test_fountain_file_round_trip_with_frame_loss(cb):
+    """file -> wirehair blocks (the reference's own codec) -> 625-byte chunks -> RS + tiles -> frames -> GPU decode ->
+    rank-0 sink -> file, with a third of the frames lost and the rest fed in shuffled order (wirehair does not care)."""
+    import torch
+    from oracle_lib import Ref
+    try:
+        ref = Ref()
+    except (FileNotFoundError, OSError) as e:
+        pytest.skip(f"oracle/_ref not available: {e}")
+    m = ORA.mode(68)
+    rng = np.random.default_rng(44)
+    size = 300_000
+    data = rng.integers(0, 256, size, dtype=np.uint8)
+    payload = m.chunk_size - 6
+    enc = ref.lib.wirehair_encoder_create(None, data.ctypes.data, size, payload)
+    n_frames = 66                                                 # 792 blocks for N = 485
+    chunks = np.zeros((n_frames, 12, m.chunk_size), np.uint8)
+    for b in range(n_frames * 12):
+        ch = chunks[b // 12, b % 12]
+        ORA.lib.cbo_md_pack(7, size, b, _ptr(ch))
+        wrote = C.c_uint32(0)
+        assert ref.lib.wirehair_encode(enc, b, ch[6:].ctypes.data, payload, C.byref(wrote)) == 0
+    ref.lib.wirehair_free(enc)
+    ctx = cb.Context(68, max_frames=n_frames)
+    d_payload = torch.from_numpy(chunks.reshape(n_frames, -1)).cuda()
+    d_cells = torch.empty((n_frames, m.total_cells), dtype=torch.uint8, device="cuda")
+    d_rgb = torch.empty((n_frames, 1024, 1024, 3), dtype=torch.uint8, device="cuda")
+    d_chunks = torch.empty((n_frames, 7500), dtype=torch.uint8, device="cuda")
+    d_mask = torch.empty(n_frames, dtype=torch.int32, device="cuda")
+    ctx.encode_cells_dev(d_payload.data_ptr(), n_frames, d_cells.data_ptr())
+    ctx.render_frames_dev(d_cells.data_ptr(), n_frames, d_rgb.data_ptr())
+    ctx.decode_chunks_dev(d_rgb.data_ptr(), n_frames, d_chunks.data_ptr(), d_mask.data_ptr())
+    ctx.sync()
+    got, masks = d_chunks.cpu().numpy(), d_mask.cpu().numpy().astype(np.uint32)
+    assert (masks == 0xFFF).all() and np.array_equal(got, chunks.reshape(n_frames, -1))
+    keep = rng.permutation(n_frames)[: (2 * n_frames) // 3]       # lose a third of the frames, shuffle the rest
+    sink = cb.FountainSink(m.chunk_size, ref.lib)
+    fid = sink.ingest(got[keep], masks[keep])
+    assert fid > 0
+    assert np.array_equal(sink.file(fid), data)
+    sink.close()
+    ctx.close()
