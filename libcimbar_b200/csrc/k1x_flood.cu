@@ -319,6 +319,7 @@ k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fall
                         break;
                     }
                 }
+                __syncwarp();   // lane 0's writes to remaining[] / the heap are ordered before the other lanes' reads below
                 ci = __shfl_sync(0xffffffffu, ci, 0);
                 ins = __shfl_sync(0xffffffffu, ins, 0);
                 if (ci < 0) break;   // heap exhausted (cannot happen on a connected grid)
