@@ -207,8 +207,20 @@ def run_ours(args):
     ok_data = bool(torch.equal(chunks, payload))
     n_fallback = int((fflags & 1).sum().item())
     ok_flags = not bool(fflags.any().item())
-    parity = "bit-exact: %d frames/rank, all %d chunks/frame == payload" % (B, info.chunks_per_frame) \
-        if (ok_mask and ok_data) else "MISMATCH mask_ok=%s data_ok=%s" % (ok_mask, ok_data)
+    if ok_mask and ok_data:
+        parity = "bit-exact: %d frames/rank, all %d chunks/frame == payload" % (B, info.chunks_per_frame)
+    elif args.workload == "clean":
+        parity = "MISMATCH mask_ok=%s data_ok=%s" % (ok_mask, ok_data)
+    else:
+        # damaged input: RS may legitimately give up on a chunk (the reference would too; exactness against the oracle is
+        # what tests/test_gpu_parity.py checks) -- report how many chunks came through and that every one of those is right
+        cpf, cs = info.chunks_per_frame, info.data_bytes // info.chunks_per_frame
+        bits = ((mask.view(B, 1) >> torch.arange(cpf, device=dev, dtype=torch.int32).view(1, cpf)) & 1).bool()
+        same = (chunks.view(B, cpf, cs) == payload.view(B, cpf, cs)).all(dim=2)
+        good = int(bits.sum().item())
+        wrong = int((bits & ~same).sum().item())
+        parity = "%d of %d chunks decoded, %d frames complete; decoded chunks != payload: %d" % (
+            good, B * cpf, int(bits.all(dim=1).sum().item()), wrong)
 
     # ---- end to end through the host-pointer C ABI: pinned host frames -> cb200_decode_fountain -> host chunks
     e2e = None

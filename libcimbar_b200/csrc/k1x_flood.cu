@@ -9,227 +9,432 @@
 //   P4  CimbReader::read, CellDrift           src/lib/cimb_translator/CimbReader.cpp:139-162, CellDrift.cpp:23-43
 //   P5/P6 fuzzy_ahash + get_best_symbol       src/lib/image_hash/ahash_result.h:70-106, CimbDecoder.cpp:101-132
 //   P8/P9 colour at the drift-adjusted cell   src/lib/cimb_translator/Cell.h:30-62, CimbDecoder.cpp:168-217
-// One CTA per frame that needs it (clean frames cost one flag test).  The threshold raster of the whole frame is
-// built by all 256 threads in global scratch; warp 0 then runs the 12 400-step walk: lane 0 owns the heap (global
-// scratch) and the per-cell inherit table (shared memory), all 32 lanes score the 5x16 / 9x16 (hash, tile) candidates
-// of each step with popcounts and a warp min-reduction; finally all threads classify colours at the recorded positions.
+//
+// Four kernels per batch; clean batches cost four empty launches:
+//   k_flood_list    compacts the frames K1 flagged into a work list (one CTA, order-preserving)
+//   k_flood_raster  threshold raster of every listed frame, fully parallel: one CTA per 16-row band, gray / sharpen /
+//                   box sums staged in shared memory with OpenCV's border rules, 1 bit per pixel to global memory
+//   k_flood_walk    the serial 12 400-step walk, ONE WARP PER FRAME, seven frames per SM in flight (the walk is a chain
+//                   of dependent heap and window accesses, so throughput comes from walking many frames at once):
+//                   binary heap in shared memory (+ global spill), the drift/cooldown a cell inherits travels inside the
+//                   32-bit heap entry, so the only per-cell state is one priority byte in shared memory
+//   k_flood_colour  colours at the recorded drift-adjusted positions, one thread per cell
 #include "cb200_common.cuh"
 #include "k1x_flood.cuh"
 
 namespace cb200 {
 
-constexpr int kFloodThreads = 256;
+constexpr int kRasterThreads = 256;
+constexpr int kBandRows = 16;            // output rows per raster CTA
+constexpr int kFloodMaxEntries = 4096;   // listed frames whose raster/result are resident at once (one chunk)
 
 __constant__ float cx_adjust[256];
 __constant__ unsigned long long cx_tiles_L[16];
 
-constexpr int kHeapSmem = 14336;        // heap entries kept in shared memory (observed maximum ~9.1k); the rest spills to global
+// ---------------------------------------------------------------------------------------------- work list
+// order-preserving compaction of the frames that need the exact walk; also writes the per-frame flags
+__global__ void __launch_bounds__(1024)
+k_flood_list(const uint32_t* __restrict__ dirty, int n_frames, int no_fallback, int force_all, uint8_t* __restrict__ frame_flags,
+             uint32_t* __restrict__ list, uint32_t* __restrict__ counters, int n_counters)
+{
+    __shared__ uint32_t warp_off[32];
+    __shared__ uint32_t base_s, total_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    for (int i = 1 + tid; i < n_counters; i += 1024) counters[i] = 0;     // per-chunk work counters of k_flood_walk
+    __syncthreads();
+    for (int start = 0; start < n_frames; start += 1024) {
+        const int f = start + tid;
+        const bool need = f < n_frames && (force_all || (dirty[f] & kFrameDirtyK1));
+        const bool take = need && !no_fallback;
+        if (f < n_frames) frame_flags[f] = need ? (no_fallback ? 0x2 : 0x1) : 0;   // CB200_FRAME_INEXACT / CB200_FRAME_FALLBACK
+        const uint32_t b = __ballot_sync(0xffffffffu, take);
+        const uint32_t prefix = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) warp_off[warp] = __popc(b);
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = warp_off[lane], incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            warp_off[lane] = incl - v;
+            if (lane == 31) total_s = incl;
+        }
+        __syncthreads();
+        if (take) list[base_s + warp_off[warp] + prefix] = (uint32_t)f;
+        __syncthreads();
+        if (tid == 0) base_s += total_s;
+        __syncthreads();
+    }
+    if (tid == 0) counters[0] = base_s;
+}
 
-struct FloodSmem {
-    uint32_t instr[kMaxCells];          // before decode: dx(8) | dy(8) | prio(8) | cooldown(8); after: x(11) | y(11) | sym(4) | done
-    uint32_t heap[kHeapSmem];
-    uint32_t remaining[(kMaxCells + 31) / 32];
-    float adjust[256];
-    unsigned long long tiles[16];       // copy of cx_tiles_L: indexed per lane in the scoring loop
-};
+__device__ __forceinline__ int chunk_count(const uint32_t* counters, int base, int cap)
+{
+    int c = (int)counters[0] - base;
+    return c < 0 ? 0 : (c > cap ? cap : c);
+}
 
-// ---------------------------------------------------------------------------------------------- geometry
-__device__ __forceinline__ void cell_xy(const Mode& m, int index, int& x, int& y)
-{   // CellPositions::compute_linear, CellPositions.cpp:5-50
-    int narrow = m.cells_x - 2 * m.corner;
-    if (index < m.top_cells) {
-        int k = index / narrow, c = index - k * narrow;
-        x = m.cell_offset + kSpacing * (m.corner + c); y = m.cell_offset + kSpacing * k;
-    } else if (index < m.top_cells + m.mid_cells) {
-        int q = index - m.top_cells; int k = q / m.cells_x, c = q - k * m.cells_x;
-        x = m.cell_offset + kSpacing * c; y = m.cell_offset + kSpacing * (m.corner + k);
-    } else {
-        int q = index - m.top_cells - m.mid_cells; int k = q / narrow, c = q - k * narrow;
-        x = m.cell_offset + kSpacing * (m.corner + c); y = m.cell_offset + kSpacing * (m.cells_y - m.corner + k);
+// ---------------------------------------------------------------------------------------------- preprocessing (P1)
+__device__ __forceinline__ int reflect101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; return p; }
+__device__ __forceinline__ int clampi(int p, int lo, int hi) { return p < lo ? lo : (p > hi ? hi : p); }
+__device__ __forceinline__ uint32_t gray_of(uint32_t r, uint32_t g, uint32_t b)
+{   // cvtColor(RGB2GRAY), 8-bit: (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+    return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;
+}
+
+// One CTA per (listed frame, band of kBandRows rows): gray -> (optionally sharpened) gray -> horizontal box sums ->
+// threshold bits.  Everything a band needs (R rows of halo, +1 for the sharpen kernel) is staged in shared memory.
+__global__ void __launch_bounds__(kRasterThreads)
+k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
+               int base, int cap, int sharpen, uint32_t* __restrict__ ws_raster)
+{
+    extern __shared__ __align__(16) uint8_t raster_smem[];
+    const int W = m.width, H = m.height, npx = W * H;
+    const int R = sharpen ? 3 : 2;                     // block size 7 after sharpening, else 5 (CimbReader.cpp:37-45)
+    const int nb = (H + kBandRows - 1) / kBandRows;
+    const int cnt = chunk_count(counters, base, cap);
+    const int rows_h = kBandRows + 2 * R, rows_g = rows_h + (sharpen ? 2 : 0);
+    uint8_t* g = raster_smem;
+    uint8_t* g2 = g + rows_g * W;
+    uint16_t* hs = reinterpret_cast<uint16_t*>(g2 + (sharpen ? rows_h * W : 0));
+    const uint32_t area = (uint32_t)((2 * R + 1) * (2 * R + 1)), half = (area - 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wq = W / 4, nseg = W / 32;
+    constexpr int kWarps = kRasterThreads / 32;
+
+    for (int item = blockIdx.x; item < cnt * nb; item += gridDim.x) {
+        const int e = item / nb, band = item - e * nb;
+        const uint32_t f = list[base + e];
+        const uint32_t* frame32 = reinterpret_cast<const uint32_t*>(rgb + (size_t)f * npx * 3);
+        const int y0 = band * kBandRows, y1 = (y0 + kBandRows < H) ? y0 + kBandRows : H;
+        const int h0 = y0 - R > 0 ? y0 - R : 0, h1 = y1 - 1 + R < H - 1 ? y1 - 1 + R : H - 1;   // rows of box sums needed (BORDER_REPLICATE)
+        const int g0 = sharpen ? (h0 - 1 > 0 ? h0 - 1 : 0) : h0, g1 = sharpen ? (h1 + 1 < H - 1 ? h1 + 1 : H - 1) : h1;
+        __syncthreads();                                // the previous item's readers are done
+        // ---- gray rows g0..g1, four pixels (three 32-bit words) per thread
+        for (int r = warp; r <= g1 - g0; r += kWarps) {
+            const uint32_t* row = frame32 + (size_t)(g0 + r) * wq * 3;
+            uint32_t* out = reinterpret_cast<uint32_t*>(g + r * W);
+            for (int j = lane; j < wq; j += 32) {
+                const uint32_t w0 = __ldg(row + 3 * j), w1 = __ldg(row + 3 * j + 1), w2 = __ldg(row + 3 * j + 2);
+                const uint32_t p0 = gray_of(w0 & 0xFFu, (w0 >> 8) & 0xFFu, (w0 >> 16) & 0xFFu);
+                const uint32_t p1 = gray_of(w0 >> 24, w1 & 0xFFu, (w1 >> 8) & 0xFFu);
+                const uint32_t p2 = gray_of((w1 >> 16) & 0xFFu, w1 >> 24, w2 & 0xFFu);
+                const uint32_t p3 = gray_of((w2 >> 8) & 0xFFu, (w2 >> 16) & 0xFFu, w2 >> 24);
+                out[j] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+            }
+        }
+        __syncthreads();
+        const uint8_t* src = g;
+        int src0 = g0;
+        if (sharpen) {
+            // filter2D with [0 -1 0; -1 4.5 -1; 0 -1 0] (CimbReader.cpp:17-27): exact in float, cvRound = round-half-even,
+            // saturate to 8 bits, BORDER_REFLECT_101
+            for (int r = warp; r <= h1 - h0; r += kWarps) {
+                const int y = h0 + r;
+                const uint8_t* rc = g + (y - g0) * W;
+                const uint8_t* ru = g + (reflect101(y - 1, H) - g0) * W;
+                const uint8_t* rd = g + (reflect101(y + 1, H) - g0) * W;
+                for (int x = lane; x < W; x += 32) {
+                    const int c = rc[x];
+                    const int nbr = ru[x] + rd[x] + rc[reflect101(x - 1, W)] + rc[reflect101(x + 1, W)];
+                    const int twice = 9 * c - 2 * nbr;
+                    int v;
+                    if (twice & 1) { int k = (twice - 1) / 2; v = (k & 1) ? k + 1 : k; } else v = twice / 2;
+                    g2[r * W + x] = (uint8_t)clampi(v, 0, 255);
+                }
+            }
+            __syncthreads();
+            src = g2; src0 = h0;
+        }
+        // ---- horizontal box sums of rows h0..h1 (BORDER_REPLICATE)
+        for (int r = warp; r <= h1 - h0; r += kWarps) {
+            const uint8_t* row = src + (h0 + r - src0) * W;
+            for (int x = lane; x < W; x += 32) {
+                uint32_t sum = 0;
+                for (int d = -R; d <= R; ++d) sum += row[clampi(x + d, 0, W - 1)];
+                hs[r * W + x] = (uint16_t)sum;
+            }
+        }
+        __syncthreads();
+        // ---- adaptiveThreshold(MEAN_C, BINARY, bs, C=0): src > round(sum / bs^2)  <=>  bs^2 * src > sum + (bs^2 - 1) / 2
+        uint32_t* raster = ws_raster + (size_t)e * (npx / 32 + 4);
+        for (int it = warp; it < (y1 - y0) * nseg; it += kWarps) {
+            const int ry = it / nseg, seg = it - ry * nseg;
+            const int y = y0 + ry, x = seg * 32 + lane;
+            uint32_t sum = 0;
+            for (int d = -R; d <= R; ++d) sum += hs[(clampi(y + d, 0, H - 1) - h0) * W + x];
+            const bool bit = area * (uint32_t)src[(y - src0) * W + x] > sum + half;
+            const uint32_t bits = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) raster[(size_t)y * nseg + seg] = bits;   // little-endian: bit b of word w = pixel 32w + b
+        }
     }
 }
-__device__ __forceinline__ int cell_x(const Mode& m, int index) { int x, y; cell_xy(m, index, x, y); return x; }
 
 // ---------------------------------------------------------------------------------------------- heap (lane 0 only)
-// entries: prio << 16 | index.  std::priority_queue<decode_prio, vector, PrioCompare> with comp(a,b) = a.prio > b.prio
+// 32-bit entries: prio(7) << 25 | cooldown code(3) << 22 | (dy + 8)(4) << 18 | (dx + 8)(4) << 14 | cell index(14).
+// std::priority_queue<decode_prio, vector, PrioCompare> with comp(a, b) = a.prio > b.prio: only the priority is compared,
+// so the pop order of equal priorities is whatever libstdc++'s sift-up / sift-down produce; both are restated literally.
+// Element i lives at shared word i + 1 (so the children 2h+1, 2h+2 are one aligned 64-bit load) while i < hs, else in
+// the global spill area at word i - hs (hs is odd, so a pair never straddles the two).
 struct Heap {
-    uint32_t* sm; uint32_t* spill; int n;
-    __device__ __forceinline__ uint32_t get(int i) const { return i < kHeapSmem ? sm[i] : spill[i - kHeapSmem]; }
-    __device__ __forceinline__ void set(int i, uint32_t v) { if (i < kHeapSmem) sm[i] = v; else spill[i - kHeapSmem] = v; }
+    uint32_t* sm; uint32_t* spill; int n; int hs;
+    __device__ __forceinline__ uint32_t get(int i) const { return i < hs ? sm[i + 1] : spill[i - hs]; }
+    __device__ __forceinline__ void set(int i, uint32_t v) { if (i < hs) sm[i + 1] = v; else spill[i - hs] = v; }
 };
-__device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 16; }
-__device__ void heap_push(Heap& h, uint32_t idx, uint32_t prio)
+__device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 25; }
+__device__ __forceinline__ void heap_push(Heap& h, uint32_t e)
 {
     int hole = h.n++;
-    if (hole < kHeapSmem) {          // common case: the whole sift-up path lives in shared memory
-        uint32_t* v = h.sm;
-        int parent = (hole - 1) / 2;
+    const uint32_t prio = hprio(e);
+    if (hole < h.hs) {                  // common case: the whole sift-up path lives in shared memory
+        uint32_t* v = h.sm + 1;
         while (hole > 0) {
-            uint32_t pe = v[parent];
+            const int parent = (hole - 1) >> 1;
+            const uint32_t pe = v[parent];
             if (hprio(pe) <= prio) break;
-            v[hole] = pe; hole = parent; parent = (hole - 1) / 2;
+            v[hole] = pe; hole = parent;
         }
-        v[hole] = (prio << 16) | idx;
+        v[hole] = e;
         return;
     }
-    int parent = (hole - 1) / 2;
-    while (hole > 0 && hprio(h.get(parent)) > prio) { h.set(hole, h.get(parent)); hole = parent; parent = (hole - 1) / 2; }
-    h.set(hole, (prio << 16) | idx);
+    while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const uint32_t pe = h.get(parent);
+        if (hprio(pe) <= prio) break;
+        h.set(hole, pe); hole = parent;
+    }
+    h.set(hole, e);
 }
-__device__ uint32_t heap_pop(Heap& h)
+__device__ __forceinline__ uint32_t heap_pop(Heap& h)
 {
-    uint32_t top = h.get(0);
-    uint32_t value = h.get(h.n - 1);
-    int len = --h.n;
+    const uint32_t top = h.sm[1];
+    const uint32_t value = h.get(h.n - 1);
+    const int len = --h.n;
     if (len == 0) return top;
     int hole = 0, second = 0;
-    if (len <= kHeapSmem) {          // common case: shared memory only
-        uint32_t* v = h.sm;
-        const int lim = (len - 1) / 2;
+    const int lim = (len - 1) >> 1;
+    if (len <= h.hs) {                  // common case: shared memory only, both children in one load
+        uint32_t* v = h.sm + 1;
         while (second < lim) {
             second = 2 * (second + 1);
-            uint32_t a = v[second], b = v[second - 1];
-            if (hprio(a) > hprio(b)) { second--; a = b; }
+            const uint2 pr = *reinterpret_cast<const uint2*>(h.sm + second);   // .x = element second-1, .y = element second
+            uint32_t a = pr.y;
+            if (hprio(pr.y) > hprio(pr.x)) { second--; a = pr.x; }
             v[hole] = a;
             hole = second;
         }
-        if ((len & 1) == 0 && second == (len - 2) / 2) {
+        if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
             second = 2 * (second + 1);
             v[hole] = v[second - 1];
             hole = second - 1;
         }
         const uint32_t vp = hprio(value);
-        int parent = (hole - 1) / 2;
         while (hole > 0) {
-            uint32_t pe = v[parent];
+            const int parent = (hole - 1) >> 1;
+            const uint32_t pe = v[parent];
             if (hprio(pe) <= vp) break;
-            v[hole] = pe; hole = parent; parent = (hole - 1) / 2;
+            v[hole] = pe; hole = parent;
         }
         v[hole] = value;
         return top;
     }
-    while (second < (len - 1) / 2) {
+    while (second < lim) {
         second = 2 * (second + 1);
         uint32_t a = h.get(second), b = h.get(second - 1);
         if (hprio(a) > hprio(b)) { second--; a = b; }
         h.set(hole, a);
         hole = second;
     }
-    if ((len & 1) == 0 && second == (len - 2) / 2) {
+    if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
         second = 2 * (second + 1);
         h.set(hole, h.get(second - 1));
         hole = second - 1;
     }
-    int parent = (hole - 1) / 2;
-    while (hole > 0 && hprio(h.get(parent)) > hprio(value)) { h.set(hole, h.get(parent)); hole = parent; parent = (hole - 1) / 2; }
+    const uint32_t vp = hprio(value);
+    while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const uint32_t pe = h.get(parent);
+        if (hprio(pe) <= vp) break;
+        h.set(hole, pe); hole = parent;
+    }
     h.set(hole, value);
     return top;
 }
 
-__device__ __forceinline__ uint32_t pack_instr(int dx, int dy, uint32_t prio, uint32_t cooldown)
+// cooldown values (CellDrift::calculate_cooldown, CellDrift.cpp:34-43): 4, 0xFF, 0xFE (initial), or an odd drift id 1/3/5/7
+__device__ __forceinline__ uint32_t cd_code(uint32_t cd) { return cd == 4u ? 0u : cd == 0xFFu ? 1u : cd == 0xFEu ? 2u : 3u + (cd >> 1); }
+__device__ __forceinline__ uint32_t cd_value(uint32_t code) { return code == 0u ? 4u : code == 1u ? 0xFFu : code == 2u ? 0xFEu : 2u * (code - 3u) + 1u; }
+constexpr uint32_t kSeedCode = 7u;     // entry pushed by reset(): its cell's inherit record is NOT in the entry
+__device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uint32_t code, uint32_t prio)
 {
-    return ((uint32_t)(dx & 0xFF)) | ((uint32_t)(dy & 0xFF) << 8) | (prio << 16) | (cooldown << 24);
-}
-__device__ __forceinline__ bool is_remaining(const FloodSmem& s, int i) { return (s.remaining[i >> 5] >> (i & 31)) & 1u; }
-
-// FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83), done by the warp:
-// lanes 0..11 each resolve one candidate neighbour -- lanes 0-3 the direct neighbours (right, left, bottom, top), lanes
-// 4-7 the horizontal horizon (right of right, its right, left of left, its left), lanes 8-11 the vertical horizon -- and
-// test it (still remaining? stored priority > err?); lane 0 then rewrites the inherit entries and pushes the survivors
-// in the reference's order (adjacents, horizon, vert).  The candidates are distinct cells, so the tests are independent.
-// adj: per-cell neighbours as AdjacentCellFinder::find computes them (AdjacentCellFinder.cpp:54-105), 0xFFFF = none.
-__device__ __forceinline__ int adj_dir(const ushort4* __restrict__ adj, int cell, int dir)
-{
-    if (cell < 0) return -1;
-    ushort4 a = __ldg(&adj[cell]);
-    unsigned v = dir == 0 ? a.x : dir == 1 ? a.y : dir == 2 ? a.z : a.w;
-    return v == 0xFFFFu ? -1 : (int)v;
-}
-__device__ void flood_update_warp(const ushort4* __restrict__ adj, FloodSmem& s, Heap& h, int lane, int index, int dx, int dy,
-                                  uint32_t err, uint32_t cooldown, uint32_t self)
-{
-    const uint32_t prev_err = (self >> 16) & 0xFFu, prev_cd = self >> 24;
-    const bool horizon = prev_err < 3 && err < 3 && prev_cd == 4 && cooldown == 4;
-    int cand = -1;
-    if (lane < 4) cand = adj_dir(adj, index, lane);
-    else if (lane < 12 && horizon) {
-        const int grp = (lane - 4) >> 1;               // 0: right chain, 1: left chain, 2: top chain, 3: bottom chain
-        const int dir = grp == 0 ? 0 : grp == 1 ? 1 : grp == 2 ? 3 : 2;
-        // horizontal horizon needs BOTH right and left neighbours, vertical BOTH top and bottom (FloodDecodePositions.cpp:102, :116)
-        const int a0 = adj_dir(adj, index, grp < 2 ? 0 : 3), a1 = adj_dir(adj, index, grp < 2 ? 1 : 2);
-        if (a0 >= 0 && a1 >= 0) {
-            const int first = adj_dir(adj, dir == (grp < 2 ? 0 : 3) ? a0 : a1, dir);   // neighbour of the direct neighbour
-            cand = ((lane - 4) & 1) ? adj_dir(adj, first, dir) : first;
-        }
-    }
-    bool push = false;
-    if (cand >= 0 && is_remaining(s, cand)) push = ((s.instr[cand] >> 16) & 0xFFu) > err;
-    // reference order: adj = right, left, bottom, top; horizon = right+1, right+2, left+1, left+2; vert = top+1, top+2, bottom+1, bottom+2
-    // lanes: 0..3 direct; 4,5 right chain; 6,7 left chain; 8,9 top chain; 10,11 bottom chain  -> already in reference order
-    uint32_t todo = __ballot_sync(0xffffffffu, push) & 0xFFFu;
-    const uint32_t entry = pack_instr(dx, dy, err, cooldown);
-    while (todo) {
-        const int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int c = __shfl_sync(0xffffffffu, cand, l);
-        if (lane == 0) { s.instr[c] = entry; heap_push(h, (uint32_t)c, err); }
-    }
+    return (prio << 25) | (code << 22) | ((uint32_t)(dy + 8) << 18) | ((uint32_t)(dx + 8) << 14) | idx;
 }
 
-// ---------------------------------------------------------------------------------------------- preprocessing (P1)
-__device__ __forceinline__ int reflect101(int p, int n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; return p; }
-__device__ __forceinline__ int clampi(int p, int lo, int hi) { return p < lo ? lo : (p > hi ? hi : p); }
-
-// gray -> (optionally sharpened) gray -> horizontal box sums -> threshold bits; all 256 threads, global scratch
-__device__ void build_raster(const Mode& m, const uint8_t* __restrict__ frame, bool sharpen,
-                             uint8_t* gray, uint8_t* gray2, uint16_t* hsum, uint32_t* raster)
+// ---------------------------------------------------------------------------------------------- the walk
+// Shared memory of one walking warp: heap[hs + 1] words, then one byte per cell:
+//   0 = decoded (FloodDecodePositions::_remaining false), else best_prio + 1 (0xFF for the initial 0xFE).
+// Why the inherit record (drift, best_prio, cooldown; FloodDecodePositions.h:17) can ride in the heap entry: update()
+// only rewrites it when the new error is strictly lower (FloodDecodePositions.cpp:75), and pushes an entry with that
+// error, so of all entries of a cell the one that pops first is always the latest, and it carries the record as it stands.
+// The exception are the eight entries reset() seeds with priority 0/1 while the record says (0,0,0xFE,0xFE): when such an
+// entry pops, the record is the latest update still sitting in the heap (found by a warp-wide scan), else the initial one.
+__global__ void __launch_bounds__(32)
+k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
+             int heap_smem, const uint32_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
+             const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace)
 {
-    const int W = m.width, H = m.height, npx = W * H;
-    for (int i = threadIdx.x; i < npx; i += kFloodThreads) {
-        uint32_t r = frame[3 * i], g = frame[3 * i + 1], b = frame[3 * i + 2];
-        gray[i] = (uint8_t)((9798u * r + 19235u * g + 3735u * b + 16384u) >> 15);   // cvtColor(RGB2GRAY)
-    }
-    __syncthreads();
-    const uint8_t* src = gray;
-    int radius = 2;
-    if (sharpen) {
-        // filter2D with [0 -1 0; -1 4.5 -1; 0 -1 0] (CimbReader.cpp:17-27): exact in float, cvRound = round-half-even,
-        // saturate to 8 bits, BORDER_REFLECT_101; then block size 7 (CimbReader.cpp:37-40)
-        for (int i = threadIdx.x; i < npx; i += kFloodThreads) {
-            int y = i / W, x = i - y * W;
-            int c = gray[i];
-            int nb = gray[reflect101(y - 1, H) * W + x] + gray[reflect101(y + 1, H) * W + x] +
-                     gray[y * W + reflect101(x - 1, W)] + gray[y * W + reflect101(x + 1, W)];
-            int twice = 9 * c - 2 * nb, v;
-            if (twice & 1) { int k = (twice - 1) / 2; v = (k & 1) ? k + 1 : k; } else v = twice / 2;
-            gray2[i] = (uint8_t)clampi(v, 0, 255);
+    extern __shared__ __align__(16) uint8_t walk_smem[];
+    uint32_t* heap_sm = reinterpret_cast<uint32_t*>(walk_smem);
+    uint8_t* prio = walk_smem + (size_t)(heap_smem + 1) * 4;
+    const int lane = threadIdx.x;
+    const int W = m.width, npx = W * m.height, ncells = m.num_cells;
+    const int cnt = chunk_count(counters, base, cap);
+    const unsigned long long tileL = cx_tiles_L[lane & 15];
+    const int narrow = m.cells_x - 2 * m.corner;
+    const float rcp_narrow = 1.0f / (float)narrow, rcp_wide = 1.0f / (float)m.cells_x;   // exact floor for q < 2^14 (q + 0.5 trick)
+    Heap heap; heap.sm = heap_sm; heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
+
+    while (true) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(next_counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= (uint32_t)cnt) break;
+        const uint32_t f = list[base + k];
+        const uint32_t* raster = ws_raster + (size_t)k * (npx / 32 + 4);
+        uint32_t* result = ws_result + (size_t)k * ncells;
+
+        // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
+        for (int i = lane; i < (ncells + 3) / 4; i += 32) reinterpret_cast<uint32_t*>(prio)[i] = 0xFFFFFFFFu;
+        if (lane == 0) {
+            heap.n = 0;
+            const int last = ncells - 1, bmb = m.top_cells;
+            heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0)); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0));
+            heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0)); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0));
+            heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1)); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1));
+            heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1));
+            heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1));
         }
-        __syncthreads();
-        src = gray2;
-        radius = 3;
-    }
-    for (int i = threadIdx.x; i < npx; i += kFloodThreads) {
-        int y = i / W, x = i - y * W;
-        uint32_t sum = 0;
-        for (int d = -radius; d <= radius; ++d) sum += src[y * W + clampi(x + d, 0, W - 1)];   // BORDER_REPLICATE
-        hsum[i] = (uint16_t)sum;
-    }
-    __syncthreads();
-    // adaptiveThreshold(MEAN_C, BINARY, bs, C=0): src > round(sum / bs^2)  <=>  bs^2 * src > sum + (bs^2 - 1) / 2
-    const uint32_t area = (uint32_t)((2 * radius + 1) * (2 * radius + 1)), half = (area - 1) / 2;
-    const int words = npx / 32;
-    for (int wi = threadIdx.x; wi < words; wi += kFloodThreads) {
-        uint32_t bits = 0;
-        for (int b = 0; b < 32; ++b) {
-            int i = wi * 32 + b;
-            int y = i / W, x = i - y * W;
-            uint32_t sum = 0;
-            for (int d = -radius; d <= radius; ++d) sum += hsum[clampi(y + d, 0, H - 1) * W + x];
-            if (area * (uint32_t)src[i] > sum + half) bits |= 1u << b;
+        __syncwarp();
+
+        int count = 0;
+        while (count < ncells) {
+            // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67): lane 0 pops until a remaining cell shows up
+            uint32_t e = 0xFFFFFFFFu;
+            if (lane == 0) {
+                while (heap.n > 0) {
+                    const uint32_t t = heap_pop(heap);
+                    const uint32_t i = t & 0x3FFFu;
+                    if (prio[i] == 0) continue;
+                    prio[i] = 0;
+                    e = t;
+                    break;
+                }
+            }
+            __syncwarp();                                    // lane 0's heap / prio writes are ordered before the reads below
+            e = __shfl_sync(0xffffffffu, e, 0);
+            if (e == 0xFFFFFFFFu) break;                     // heap exhausted (cannot happen on a connected grid)
+            ++count;
+            const int ci = (int)(e & 0x3FFFu);
+            // neighbours: lanes 0-3 direct (right, left, bottom, top), 4-11 the horizon chains (see flood_build_cinfo)
+            uint32_t cv = 0xFFFFu;
+            if (lane < 12) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
+            uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
+            int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
+            if (code == kSeedCode) {
+                const int hn = __shfl_sync(0xffffffffu, heap.n, 0);
+                uint32_t latest = 0xFFFFFFFFu;
+                for (int i = lane; i < hn; i += 32) {
+                    const uint32_t t = heap.get(i);
+                    if ((t & 0x3FFFu) == (uint32_t)ci && ((t >> 22) & 7u) != kSeedCode && t < latest) latest = t;
+                }
+                latest = __reduce_min_sync(0xffffffffu, latest);
+                if (latest != 0xFFFFFFFFu) {
+                    code = (latest >> 22) & 7u; prev_err = latest >> 25;
+                    ddx = (int)((latest >> 14) & 15u) - 8; ddy = (int)((latest >> 18) & 15u) - 8;
+                } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
+            }
+            const uint32_t cooldown = cd_value(code);
+            // ---- cell position (CellPositions::compute_linear, CellPositions.cpp:5-50)
+            int px, py;
+            if (ci < m.top_cells) {
+                const int kk = __float2int_rz(((float)ci + 0.5f) * rcp_narrow), c = ci - kk * narrow;
+                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * kk;
+            } else if (ci < m.top_cells + m.mid_cells) {
+                const int q = ci - m.top_cells;
+                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_wide), c = q - kk * m.cells_x;
+                px = m.cell_offset + kSpacing * c; py = m.cell_offset + kSpacing * (m.corner + kk);
+            } else {
+                const int q = ci - m.top_cells - m.mid_cells;
+                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_narrow), c = q - kk * narrow;
+                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * (m.cells_y - m.corner + kk);
+            }
+            const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
+            // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r
+            uint32_t myrow = 0;
+            if (lane < 10) {
+                const uint32_t bit = (uint32_t)(y - 1 + lane) * (uint32_t)W + (uint32_t)(x - 1);
+                const uint32_t wi = bit >> 5;
+                myrow = __funnelshift_r(__ldg(raster + wi), __ldg(raster + wi + 1), bit & 31u) & 0x3FFu;   // bit i = window col i
+            }
+            uint32_t win[10];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
+            // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
+            const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
+            const int ncand = (all ? 9 : 5) * 16;
+            uint32_t best_key = 0xFFFFFFFFu;
+            for (int p = lane; p < ncand; p += 32) {
+                const int q = p >> 4;
+                const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);          // packed order table, nibble q
+                if ((uint32_t)id == cooldown && id != 4) continue;                 // CimbDecoder.cpp:116
+                const int r0 = id / 3, c0 = id % 3;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {          // rows r0 .. r0+7 of the window, selected without dynamic register indexing
+                    const uint32_t wr = r0 == 0 ? win[r] : (r0 == 1 ? win[r + 1] : win[r + 2]);
+                    const uint32_t byte = (wr >> c0) & 0xFFu;
+                    if (r < 4) lo |= byte << (8 * r); else hi |= byte << (8 * (r - 4));
+                }
+                const unsigned long long L = ((unsigned long long)hi << 32) | lo;
+                const uint32_t d = (uint32_t)__popcll(L ^ tileL);
+                const uint32_t key = (d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15);
+                best_key = key < best_key ? key : best_key;
+            }
+            best_key = __reduce_min_sync(0xffffffffu, best_key);
+            // every lane derives the (warp-uniform) decision from the reduced key
+            const uint32_t dist = best_key >> 8, q = (best_key >> 4) & 0xFu, sym = best_key & 0xFu;
+            const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);
+            const int bx = id % 3 - 1, by = id / 3 - 1;                       // CellDrift::driftPairs, CellDrift.h:13-15
+            const int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
+            uint32_t ncd;                                                     // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
+            if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
+            if (lane == 0) {
+                result[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
+                if (trace) {
+                    CellTrace tr;
+                    tr.order = (uint16_t)(count - 1); tr.x = (int16_t)(x + bx); tr.y = (int16_t)(y + by);
+                    tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
+                    trace[(size_t)f * ncells + ci] = tr;
+                }
+            }
+            // ---- FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83):
+            // lanes 0..11 test one candidate each (still remaining and stored priority > err  <=>  byte >= err + 2), lane 0
+            // then records the new priority and pushes the survivors in the reference's order (adjacents, horizon, vert).
+            const bool horizon = prev_err < 3u && dist < 3u && cooldown == 4u && ncd == 4u;
+            const int cand = (cv != 0xFFFFu && (lane < 4 || horizon)) ? (int)cv : -1;
+            const bool push = cand >= 0 && (uint32_t)prio[cand] >= dist + 2u;
+            uint32_t todo = __ballot_sync(0xffffffffu, push) & 0xFFFu;
+            const uint32_t entry = make_entry(0, ndx, ndy, cd_code(ncd), dist);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int c = __shfl_sync(0xffffffffu, cand, l);
+                if (lane == 0) { prio[c] = (uint8_t)(dist + 1u); heap_push(heap, entry | (uint32_t)c); }
+            }
+            __syncwarp();
         }
-        raster[wi] = bits;   // little-endian: bit b of word wi = pixel wi*32+b
+        __syncwarp();
     }
-    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------- colour (P8/P9)
@@ -260,194 +465,158 @@ __device__ uint32_t flood_best_color(const float* adjust_tab, const Mode& m, uin
     return best;
 }
 
-// ---------------------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kFloodThreads, 2)
-k_flood(const Mode m, const uint8_t* __restrict__ rgb, int n_frames, int no_fallback, int force_all, int sharpen,
-        uint8_t* __restrict__ cellvals, const uint32_t* __restrict__ dirty, uint8_t* __restrict__ frame_flags,
-        uint8_t* ws_gray, uint8_t* ws_gray2, uint16_t* ws_hsum, uint32_t* ws_raster, uint32_t* ws_heap, size_t heap_cap,
-        const ushort4* __restrict__ adj, CellTrace* __restrict__ trace)
+// colours at the drift-adjusted positions (CimbReader::read_color, CimbReader.cpp:133-137); one thread per cell
+__global__ void __launch_bounds__(256)
+k_flood_colour(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
+               int base, int cap, const uint32_t* __restrict__ ws_result, uint8_t* __restrict__ cellvals)
 {
-    extern __shared__ __align__(16) uint8_t flood_smem_raw[];
-    FloodSmem& s = *reinterpret_cast<FloodSmem*>(flood_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = m.width, H = m.height, npx = W * H, ncells = m.num_cells;
-    const size_t frame_bytes = (size_t)npx * 3;
-    uint8_t* gray = ws_gray + (size_t)blockIdx.x * npx;
-    uint8_t* gray2 = ws_gray2 + (size_t)blockIdx.x * npx;
-    uint16_t* hsum = ws_hsum + (size_t)blockIdx.x * npx;
-    uint32_t* raster = ws_raster + (size_t)blockIdx.x * (npx / 32 + 4);
-    Heap heap; heap.sm = s.heap; heap.spill = ws_heap + (size_t)blockIdx.x * heap_cap; heap.n = 0;
-    for (int i = tid; i < 256; i += kFloodThreads) s.adjust[i] = cx_adjust[i];
-    if (tid < 16) s.tiles[tid] = cx_tiles_L[tid];
-
-    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
-        const bool need = force_all || (dirty[f] & kFrameDirtyK1);
-        if (!need) { if (tid == 0) frame_flags[f] = 0; continue; }
-        if (no_fallback) { if (tid == 0) frame_flags[f] = 0x2; continue; }   // CB200_FRAME_INEXACT
+    __shared__ float adjust[256];
+    adjust[threadIdx.x] = cx_adjust[threadIdx.x];
+    __syncthreads();
+    const int W = m.width, ncells = m.num_cells;
+    const size_t frame_bytes = (size_t)W * m.height * 3;
+    const int cnt = chunk_count(counters, base, cap);
+    const int num_colors = 1 << m.color_bits;
+    const size_t total = (size_t)cnt * ncells;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int e = (int)(i / (size_t)ncells), ci = (int)(i - (size_t)e * ncells);
+        const uint32_t f = list[base + e];
         const uint8_t* frame = rgb + (size_t)f * frame_bytes;
-        __syncthreads();
-        build_raster(m, frame, sharpen != 0, gray, gray2, hsum, raster);
-
-        // ---- reset walk state (FloodDecodePositions::reset, FloodDecodePositions.cpp:17-42)
-        for (int i = tid; i < ncells; i += kFloodThreads) s.instr[i] = pack_instr(0, 0, 0xFE, 0xFE);
-        for (int i = tid; i < (ncells + 31) / 32; i += kFloodThreads) {
-            int rem = ncells - i * 32;
-            s.remaining[i] = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
-        }
-        __syncthreads();
-
-        if (warp == 0) {
-            if (lane == 0) {
-                heap.n = 0;
-                int small_row = m.cells_x - 2 * m.corner, last = ncells - 1, bmb = m.top_cells;
-                heap_push(heap, 0, 0); heap_push(heap, (uint32_t)(small_row - 1), 0);
-                heap_push(heap, (uint32_t)last, 0); heap_push(heap, (uint32_t)(last - (small_row - 1)), 0);
-                heap_push(heap, (uint32_t)bmb, 1); heap_push(heap, (uint32_t)(bmb + m.cells_x - 1), 1);
-                heap_push(heap, (uint32_t)(last - bmb), 1); heap_push(heap, (uint32_t)(last - (bmb + m.cells_x - 1)), 1);
+        const uint32_t rec = ws_result[i];
+        const int x = (int)(rec & 0x7FFu), y = (int)((rec >> 11) & 0x7FFu);
+        const uint32_t sym = (rec >> 22) & 0xFu;
+        uint32_t col = 0;
+        if (num_colors > 1) {
+            uint32_t R = 0, G = 0, B = 0;
+            for (int r = 1; r <= 6; ++r) {
+                const uint8_t* p = frame + ((size_t)(y + r) * W + (size_t)(x + 1)) * 3;
+                for (int c = 0; c < 6; ++c) { R += p[3 * c]; G += p[3 * c + 1]; B += p[3 * c + 2]; }
             }
-            int count = 0;
-            while (count < ncells) {
-                // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67): lane 0 pops
-                int ci = -1; uint32_t ins = 0;
-                if (lane == 0) {
-                    while (heap.n > 0) {
-                        uint32_t e = heap_pop(heap);
-                        int i = (int)(e & 0xFFFFu);
-                        if (!is_remaining(s, i)) continue;
-                        s.remaining[i >> 5] &= ~(1u << (i & 31));
-                        ci = i; ins = s.instr[i];
-                        break;
-                    }
-                }
-                __syncwarp();   // lane 0's writes to remaining[] / the heap are ordered before the other lanes' reads below
-                ci = __shfl_sync(0xffffffffu, ci, 0);
-                ins = __shfl_sync(0xffffffffu, ins, 0);
-                if (ci < 0) break;   // heap exhausted (cannot happen on a connected grid)
-                ++count;
-                const int ddx = (int)(int8_t)(ins & 0xFF), ddy = (int)(int8_t)((ins >> 8) & 0xFF);
-                const uint32_t cooldown = ins >> 24;
-                int px, py; cell_xy(m, ci, px, py);
-                const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
-                // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r
-                uint32_t myrow = 0;
-                if (lane < 10) {
-                    uint32_t bit = (uint32_t)(y - 1 + lane) * (uint32_t)W + (uint32_t)(x - 1);
-                    uint32_t wi = bit >> 5;
-                    myrow = __funnelshift_r(raster[wi], raster[wi + 1], bit & 31u) & 0x3FFu;   // bit i = window col i
-                }
-                uint32_t win[10];
-#pragma unroll
-                for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
-                // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
-                const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
-                const int ncand = (all ? 9 : 5) * 16;
-                uint32_t best_key = 0xFFFFFFFFu;
-                for (int p = lane; p < ncand; p += 32) {
-                    int q = p >> 4, t = p & 15;
-                    int id = (0x620813754ULL >> (4 * q)) & 0xF;          // packed order table, nibble q
-                    if ((uint32_t)id == cooldown && id != 4) continue; // CimbDecoder.cpp:116
-                    int r0 = id / 3, c0 = id % 3;
-                    uint32_t lo = 0, hi = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        lo |= ((win[r0 + k] >> c0) & 0xFFu) << (8 * k);
-                        hi |= ((win[r0 + 4 + k] >> c0) & 0xFFu) << (8 * k);
-                    }
-                    unsigned long long L = ((unsigned long long)hi << 32) | lo;
-                    uint32_t d = (uint32_t)__popcll(L ^ s.tiles[t]);
-                    uint32_t key = (d << 8) | ((uint32_t)q << 4) | (uint32_t)t;
-                    best_key = key < best_key ? key : best_key;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { uint32_t v = __shfl_xor_sync(0xffffffffu, best_key, o); best_key = v < best_key ? v : best_key; }
-                {   // every lane derives the (warp-uniform) decision from the reduced key
-                    const uint32_t dist = best_key >> 8, q = (best_key >> 4) & 0xFu, sym = best_key & 0xFu;
-                    const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);
-                    const int bx = id % 3 - 1, by = id / 3 - 1;             // CellDrift::driftPairs, CellDrift.h:13-15
-                    const int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
-                    uint32_t ncd;                                      // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
-                    if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
-                    flood_update_warp(adj, s, heap, lane, ci, ndx, ndy, dist, ncd, ins);
-                    if (lane == 0) {
-                        s.instr[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
-                        if (trace) {
-                            CellTrace tr;
-                            tr.order = (uint16_t)(count - 1); tr.x = (int16_t)(x + bx); tr.y = (int16_t)(y + by);
-                            tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
-                            trace[(size_t)f * ncells + ci] = tr;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
+            col = flood_best_color(adjust, m, R / 36u, G / 36u, B / 36u);
         }
-        __syncthreads();
-        // ---- colours at the drift-adjusted positions (CimbReader::read_color, CimbReader.cpp:133-137)
-        uint8_t* out = cellvals + (size_t)f * ncells;
-        const int num_colors = 1 << m.color_bits;
-        for (int i = tid; i < ncells; i += kFloodThreads) {
-            uint32_t rec = s.instr[i];
-            int x = (int)(rec & 0x7FFu), y = (int)((rec >> 11) & 0x7FFu);
-            uint32_t sym = (rec >> 22) & 0xFu;
-            uint32_t col = 0;
-            if (num_colors > 1) {
-                uint32_t R = 0, G = 0, B = 0;
-                for (int r = 1; r <= 6; ++r) {
-                    const uint8_t* p = frame + ((size_t)(y + r) * W + (size_t)(x + 1)) * 3;
-                    for (int c = 0; c < 6; ++c) { R += p[3 * c]; G += p[3 * c + 1]; B += p[3 * c + 2]; }
-                }
-                col = flood_best_color(s.adjust, m, R / 36u, G / 36u, B / 36u);
-            }
-            out[i] = (uint8_t)(sym | (col << m.symbol_bits));
-        }
-        if (tid == 0) frame_flags[f] = 0x1;   // CB200_FRAME_FALLBACK
-        __syncthreads();
+        cellvals[(size_t)f * ncells + ci] = (uint8_t)(sym | (col << m.symbol_bits));
     }
-    (void)H;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+static size_t raster_smem_bytes(const Mode& m, bool sharpen)
+{
+    const int R = sharpen ? 3 : 2, rows_h = kBandRows + 2 * R, rows_g = rows_h + (sharpen ? 2 : 0);
+    return (size_t)m.width * (size_t)(rows_g + (sharpen ? rows_h : 0) + 2 * rows_h);
+}
+
 cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16)
 {
     cudaError_t e = cudaMemcpyToSymbol(cx_adjust, adjust256, sizeof(float) * 256);
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(cx_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FloodSmem));
+    return cudaMemcpyToSymbol(cx_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
+}
+
+// per cell 16 x u16: the 12 cells FloodDecodePositions::update may touch, in the reference's push order -- 0..3 the direct
+// neighbours (right, left, bottom, top; update_adjacents), 4,5 right+1 / right+2, 6,7 left+1 / left+2 (horizontal horizon,
+// only when BOTH right and left exist, FloodDecodePositions.cpp:102), 8,9 top+1 / top+2, 10,11 bottom+1 / bottom+2 (vertical,
+// only when both top and bottom exist, :116); 0xFFFF = none.  Built from AdjacentCellFinder::find for every cell (adj_host).
+static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<uint16_t>& out)
+{
+    auto nb = [&](int cell, int dir) -> int { if (cell < 0) return -1; unsigned v = adj[(size_t)cell * 4 + dir]; return v == 0xFFFFu ? -1 : (int)v; };
+    out.assign((size_t)m.num_cells * 16, 0xFFFFu);
+    for (int i = 0; i < m.num_cells; ++i) {
+        uint16_t* o = &out[(size_t)i * 16];
+        for (int d = 0; d < 4; ++d) { int c = nb(i, d); if (c >= 0) o[d] = (uint16_t)c; }
+        const int right = nb(i, 0), left = nb(i, 1), bottom = nb(i, 2), top = nb(i, 3);
+        auto chain = [&](int first_from, int dir, int slot) {
+            int a = nb(first_from, dir), b = nb(a, dir);
+            if (a >= 0) o[slot] = (uint16_t)a;
+            if (b >= 0) o[slot + 1] = (uint16_t)b;
+        };
+        if (right >= 0 && left >= 0) { chain(right, 0, 4); chain(left, 1, 6); }
+        if (top >= 0 && bottom >= 0) { chain(top, 3, 8); chain(bottom, 2, 10); }
+    }
 }
 
 cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* adj_host, FloodWorkspace* ws)
 {
     memset(ws, 0, sizeof(*ws));
-    ws->slots = 2 * sm_count;   // two resident CTAs per SM (108 KB shared memory each)
-    size_t npx = (size_t)m.width * m.height;
-    ws->heap_cap = 16 + 12 * (size_t)m.num_cells;   // spill area: every decoded cell pushes at most 12 entries (4 + 8 horizon)
+    ws->sm_count = sm_count;
+    // shared-memory heap entries per walking warp (must be odd); the default keeps 7 walks resident per SM
+    ws->heap_smem = 4095;
+    if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
+    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)((m.num_cells + 15) / 16) * 16;
+    int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
+    if (const char* s = getenv("CB200_K1X_WALKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= per_sm) per_sm = v; }
+    ws->slots = sm_count * per_sm;
+    ws->spill_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
-    if ((e = cudaMalloc(&ws->gray, npx * ws->slots)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&ws->gray2, npx * ws->slots)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&ws->hsum, npx * ws->slots * sizeof(uint16_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&ws->raster, (npx / 32 + 4) * ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMemset(ws->raster, 0, (npx / 32 + 4) * ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&ws->heap, ws->heap_cap * ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&ws->adj, (size_t)m.num_cells * 4 * sizeof(uint16_t))) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(ws->adj, adj_host, (size_t)m.num_cells * 4 * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->walk_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_flood_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, true))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&ws->spill, ws->spill_cap * (size_t)ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
+    std::vector<uint16_t> cinfo;
+    flood_build_cinfo(m, adj_host, cinfo);
+    if ((e = cudaMalloc(&ws->cinfo, cinfo.size() * sizeof(uint16_t))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(ws->cinfo, cinfo.data(), cinfo.size() * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 void flood_workspace_destroy(FloodWorkspace* ws)
 {
-    cudaFree(ws->gray); cudaFree(ws->gray2); cudaFree(ws->hsum); cudaFree(ws->raster); cudaFree(ws->heap); cudaFree(ws->adj);
+    cudaFree(ws->spill); cudaFree(ws->cinfo); cudaFree(ws->list); cudaFree(ws->counters); cudaFree(ws->raster); cudaFree(ws->result);
     memset(ws, 0, sizeof(*ws));
 }
 
-cudaError_t flood_launch(const Mode& m, const FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
+// grows the per-batch buffers (cudaFree synchronises, so no kernel still reads the old ones)
+static cudaError_t flood_workspace_ensure(const Mode& m, FloodWorkspace& ws, int n_frames)
+{
+    cudaError_t e;
+    const size_t npx = (size_t)m.width * m.height, rw = npx / 32 + 4;
+    if (n_frames > ws.list_cap) {
+        int cap = ws.list_cap ? ws.list_cap : 256;
+        while (cap < n_frames) cap *= 2;
+        cudaFree(ws.list); cudaFree(ws.counters); ws.list = nullptr; ws.counters = nullptr; ws.list_cap = 0;
+        if ((e = cudaMalloc(&ws.list, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ws.counters, (size_t)(2 + cap / 64) * sizeof(uint32_t))) != cudaSuccess) return e;
+        ws.list_cap = cap;
+    }
+    const int want = n_frames < kFloodMaxEntries ? n_frames : kFloodMaxEntries;
+    if (want > ws.entry_cap) {
+        int cap = ws.entry_cap ? ws.entry_cap : 64;
+        while (cap < want) cap *= 2;
+        cudaFree(ws.raster); cudaFree(ws.result); ws.raster = nullptr; ws.result = nullptr; ws.entry_cap = 0;
+        if ((e = cudaMalloc(&ws.raster, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = cudaMemset(ws.raster, 0, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ws.result, (size_t)m.num_cells * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+        ws.entry_cap = cap;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
                          bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, CellTrace* d_trace,
                          cudaStream_t st)
 {
-    int grid = n_frames < ws.slots ? n_frames : ws.slots;
-    k_flood<<<grid, kFloodThreads, sizeof(FloodSmem), st>>>(m, d_rgb, n_frames, no_fallback ? 1 : 0, force_all ? 1 : 0, sharpen ? 1 : 0,
-                                                            d_cellvals, d_dirty, d_flags, ws.gray, ws.gray2, ws.hsum, ws.raster, ws.heap, ws.heap_cap,
-                                                            reinterpret_cast<const ushort4*>(ws.adj), d_trace);
+    if (n_frames <= 0) return cudaSuccess;
+    cudaError_t e = flood_workspace_ensure(m, ws, n_frames);
+    if (e != cudaSuccess) return e;
+    const int nchunks = (n_frames + ws.entry_cap - 1) / ws.entry_cap;
+    k_flood_list<<<1, 1024, 0, st>>>(d_dirty, n_frames, no_fallback ? 1 : 0, force_all ? 1 : 0, d_flags, ws.list, ws.counters, 1 + nchunks);
+    if (no_fallback) return cudaGetLastError();
+    const int nb = (m.height + kBandRows - 1) / kBandRows;
+    const size_t rs_bytes = raster_smem_bytes(m, sharpen);
+    for (int c = 0; c < nchunks; ++c) {
+        const int base = c * ws.entry_cap;
+        const int cap = n_frames - base < ws.entry_cap ? n_frames - base : ws.entry_cap;
+        long long items = (long long)cap * nb;
+        int rgrid = (int)(items < (long long)ws.sm_count * 3 ? items : (long long)ws.sm_count * 3);
+        k_flood_raster<<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, sharpen ? 1 : 0, ws.raster);
+        int wgrid = cap < ws.slots ? cap : ws.slots;
+        k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
+                                                      ws.spill, ws.spill_cap, ws.cinfo, d_trace);
+        long long cthreads = (long long)cap * m.num_cells;
+        long long cblocks = (cthreads + 255) / 256;
+        int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);
+        k_flood_colour<<<cgrid, 256, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.result, d_cellvals);
+    }
     return cudaGetLastError();
 }
 

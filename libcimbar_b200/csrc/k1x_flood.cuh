@@ -2,6 +2,8 @@
 #pragma once
 #include "cb200_common.cuh"
 #include <cstring>
+#include <cstdlib>
+#include <vector>
 
 namespace cb200 {
 
@@ -14,10 +16,15 @@ struct CellTrace {
 };
 
 struct FloodWorkspace {
-    int slots;                 // concurrent frames (one CTA each)
-    size_t heap_cap;           // heap entries per slot
-    uint8_t* gray; uint8_t* gray2; uint16_t* hsum; uint32_t* raster; uint32_t* heap;
-    uint16_t* adj;             // [num_cells][4] neighbours right, left, bottom, top (0xFFFF = none)
+    int sm_count;
+    int slots;                 // walking warps resident at once (one frame each)
+    int heap_smem;             // heap entries per walk kept in shared memory (odd)
+    size_t walk_smem;          // dynamic shared memory of one walking warp
+    size_t spill_cap;          // heap spill entries per slot
+    uint32_t* spill;           // [slots][spill_cap]
+    uint16_t* cinfo;           // [num_cells][16] update candidates in push order (0xFFFF = none)
+    int list_cap; uint32_t* list; uint32_t* counters;   // work list; counters[0] = listed frames, [1 + c] = chunk c's work counter
+    int entry_cap; uint32_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster, per-cell x | y<<11 | sym<<22
 };
 
 cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16);
@@ -26,7 +33,7 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
 void flood_workspace_destroy(FloodWorkspace* ws);
 // writes d_flags[f] for every frame: 0 = K1 result stands, CB200_FRAME_FALLBACK = re-decoded here,
 // CB200_FRAME_INEXACT = needed but skipped (no_fallback)
-cudaError_t flood_launch(const Mode& m, const FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
+cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
                          bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, CellTrace* d_trace,
                          cudaStream_t st);
 
