@@ -213,16 +213,18 @@ __device__ __forceinline__ uint32_t heap_pop(Heap& h)
     if (len == 0) return top;
     int hole = 0, second = 0;
     const int lim = (len - 1) >> 1;
-    if (len <= h.hs) {                  // common case: shared memory only, both children in one load
-        uint32_t* v = h.sm + 1;
-        while (second < lim) {
-            second = 2 * (second + 1);
-            const uint2 pr = *reinterpret_cast<const uint2*>(h.sm + second);   // .x = element second-1, .y = element second
-            uint32_t a = pr.y;
-            if (hprio(pr.y) > hprio(pr.x)) { second--; a = pr.x; }
-            v[hole] = a;
-            hole = second;
-        }
+    uint32_t* v = h.sm + 1;
+    // levels whose children both live in shared memory: one aligned 64-bit load per level
+    const int lim_sm = lim < ((h.hs - 1) >> 1) ? lim : ((h.hs - 1) >> 1);
+    while (second < lim_sm) {
+        second = 2 * (second + 1);
+        const uint2 pr = *reinterpret_cast<const uint2*>(h.sm + second);   // .x = element second-1, .y = element second
+        uint32_t a = pr.y;
+        if (hprio(pr.y) > hprio(pr.x)) { second--; a = pr.x; }
+        v[hole] = a;
+        hole = second;
+    }
+    if (len <= h.hs) {                  // common case: the rest is shared memory too
         if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
             second = 2 * (second + 1);
             v[hole] = v[second - 1];
@@ -238,10 +240,11 @@ __device__ __forceinline__ uint32_t heap_pop(Heap& h)
         v[hole] = value;
         return top;
     }
-    while (second < lim) {
+    while (second < lim) {              // the one or two levels that spilled to global memory
         second = 2 * (second + 1);
-        uint32_t a = h.get(second), b = h.get(second - 1);
-        if (hprio(a) > hprio(b)) { second--; a = b; }
+        const uint2 pr = *reinterpret_cast<const uint2*>(h.spill + (second - 1 - h.hs));
+        uint32_t a = pr.y;
+        if (hprio(pr.y) > hprio(pr.x)) { second--; a = pr.x; }
         h.set(hole, a);
         hole = second;
     }
@@ -380,24 +383,34 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
 #pragma unroll
             for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
             // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
-            const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
-            const int ncand = (all ? 9 : 5) * 16;
-            uint32_t best_key = 0xFFFFFFFFu;
-            for (int p = lane; p < ncand; p += 32) {
-                const int q = p >> 4;
-                const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);          // packed order table, nibble q
-                if ((uint32_t)id == cooldown && id != 4) continue;                 // CimbDecoder.cpp:116
-                const int r0 = id / 3, c0 = id % 3;
-                uint32_t lo = 0, hi = 0;
+            // lane q < 9 extracts the hash at drift id order[q]: the window's 8-bit columns c0..c0+7 of all ten rows form one
+            // 80-bit string, the hash at row offset r0 is bits [8 r0, 8 r0 + 64) of it (ahash_result::extract, ahash_result.h:70-106)
+            uint32_t hlo, hhi;
+            {
+                const int qq = lane < 9 ? lane : 0;
+                const int r0 = (int)((0x200201211ULL >> (4 * qq)) & 3u), c0 = (int)((0x020210121ULL >> (4 * qq)) & 3u);   // id / 3, id % 3
+                uint32_t b[10];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {          // rows r0 .. r0+7 of the window, selected without dynamic register indexing
-                    const uint32_t wr = r0 == 0 ? win[r] : (r0 == 1 ? win[r + 1] : win[r + 2]);
-                    const uint32_t byte = (wr >> c0) & 0xFFu;
-                    if (r < 4) lo |= byte << (8 * r); else hi |= byte << (8 * (r - 4));
-                }
-                const unsigned long long L = ((unsigned long long)hi << 32) | lo;
-                const uint32_t d = (uint32_t)__popcll(L ^ tileL);
-                const uint32_t key = (d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15);
+                for (int r = 0; r < 10; ++r) b[r] = (win[r] >> c0) & 0xFFu;
+                const uint32_t w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+                const uint32_t w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+                const uint32_t w2 = b[8] | (b[9] << 8);
+                hlo = __funnelshift_r(w0, w1, 8 * r0); hhi = __funnelshift_r(w1, w2, 8 * r0);
+            }
+            // every lane scores its tile (lane & 15) against the hashes q = 2 it + (lane >> 4)
+            const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
+            const int nq = all ? 9 : 5;
+            const uint32_t tile_lo = (uint32_t)tileL, tile_hi = (uint32_t)(tileL >> 32);
+            uint32_t best_key = 0xFFFFFFFFu;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                if (it >= 3 && !all) break;                       // warp-uniform
+                const int q = 2 * it + (lane >> 4);
+                const uint32_t lo = __shfl_sync(0xffffffffu, hlo, q & 15), hi = __shfl_sync(0xffffffffu, hhi, q & 15);
+                const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);          // packed order table, nibble q
+                const bool valid = q < nq && !((uint32_t)id == cooldown && id != 4);   // CimbDecoder.cpp:116
+                const uint32_t d = (uint32_t)(__popc(lo ^ tile_lo) + __popc(hi ^ tile_hi));
+                const uint32_t key = valid ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15)) : 0xFFFFFFFFu;
                 best_key = key < best_key ? key : best_key;
             }
             best_key = __reduce_min_sync(0xffffffffu, best_key);
