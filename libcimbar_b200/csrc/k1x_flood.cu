@@ -82,22 +82,32 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t r, uint32_t g, uint32_t b)
     return (9798u * r + 19235u * g + 3735u * b + 16384u) >> 15;
 }
 
+// bits of v (16 of them) moved to the even bit positions
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
 // One CTA per (listed frame, band of kBandRows rows): gray -> (optionally sharpened) gray -> horizontal box sums ->
-// threshold bits.  Everything a band needs (R rows of halo, +1 for the sharpen kernel) is staged in shared memory.
+// threshold bits.  Everything a band needs (R rows of halo, +1 for the sharpen kernel) is staged in shared memory;
+// gray and the horizontal sums handle four pixels per thread, the vertical pass slides a packed 2x16-bit column sum.
+template <bool SHARPEN>
 __global__ void __launch_bounds__(kRasterThreads)
 k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
-               int base, int cap, int sharpen, uint32_t* __restrict__ ws_raster)
+               int base, int cap, uint32_t* __restrict__ ws_raster)
 {
     extern __shared__ __align__(16) uint8_t raster_smem[];
+    constexpr int R = SHARPEN ? 3 : 2;                 // block size 7 after sharpening, else 5 (CimbReader.cpp:37-45)
+    constexpr uint32_t area = (2 * R + 1) * (2 * R + 1), half = (area - 1) / 2;
+    constexpr int rows_h = kBandRows + 2 * R, rows_g = rows_h + (SHARPEN ? 2 : 0);
     const int W = m.width, H = m.height, npx = W * H;
-    const int R = sharpen ? 3 : 2;                     // block size 7 after sharpening, else 5 (CimbReader.cpp:37-45)
     const int nb = (H + kBandRows - 1) / kBandRows;
     const int cnt = chunk_count(counters, base, cap);
-    const int rows_h = kBandRows + 2 * R, rows_g = rows_h + (sharpen ? 2 : 0);
     uint8_t* g = raster_smem;
     uint8_t* g2 = g + rows_g * W;
-    uint16_t* hs = reinterpret_cast<uint16_t*>(g2 + (sharpen ? rows_h * W : 0));
-    const uint32_t area = (uint32_t)((2 * R + 1) * (2 * R + 1)), half = (area - 1) / 2;
+    uint16_t* hs = reinterpret_cast<uint16_t*>(g2 + (SHARPEN ? rows_h * W : 0));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wq = W / 4, nseg = W / 32;
     constexpr int kWarps = kRasterThreads / 32;
@@ -108,7 +118,7 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
         const uint32_t* frame32 = reinterpret_cast<const uint32_t*>(rgb + (size_t)f * npx * 3);
         const int y0 = band * kBandRows, y1 = (y0 + kBandRows < H) ? y0 + kBandRows : H;
         const int h0 = y0 - R > 0 ? y0 - R : 0, h1 = y1 - 1 + R < H - 1 ? y1 - 1 + R : H - 1;   // rows of box sums needed (BORDER_REPLICATE)
-        const int g0 = sharpen ? (h0 - 1 > 0 ? h0 - 1 : 0) : h0, g1 = sharpen ? (h1 + 1 < H - 1 ? h1 + 1 : H - 1) : h1;
+        const int g0 = SHARPEN ? (h0 - 1 > 0 ? h0 - 1 : 0) : h0, g1 = SHARPEN ? (h1 + 1 < H - 1 ? h1 + 1 : H - 1) : h1;
         __syncthreads();                                // the previous item's readers are done
         // ---- gray rows g0..g1, four pixels (three 32-bit words) per thread
         for (int r = warp; r <= g1 - g0; r += kWarps) {
@@ -126,7 +136,7 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
         __syncthreads();
         const uint8_t* src = g;
         int src0 = g0;
-        if (sharpen) {
+        if (SHARPEN) {
             // filter2D with [0 -1 0; -1 4.5 -1; 0 -1 0] (CimbReader.cpp:17-27): exact in float, cvRound = round-half-even,
             // saturate to 8 bits, BORDER_REFLECT_101
             for (int r = warp; r <= h1 - h0; r += kWarps) {
@@ -146,26 +156,47 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
             __syncthreads();
             src = g2; src0 = h0;
         }
-        // ---- horizontal box sums of rows h0..h1 (BORDER_REPLICATE)
+        // ---- horizontal box sums of rows h0..h1 (BORDER_REPLICATE), four pixels per thread from three words
         for (int r = warp; r <= h1 - h0; r += kWarps) {
-            const uint8_t* row = src + (h0 + r - src0) * W;
-            for (int x = lane; x < W; x += 32) {
-                uint32_t sum = 0;
-                for (int d = -R; d <= R; ++d) sum += row[clampi(x + d, 0, W - 1)];
-                hs[r * W + x] = (uint16_t)sum;
+            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(src + (h0 + r - src0) * W);
+            uint2* out = reinterpret_cast<uint2*>(hs + r * W);
+            for (int j = lane; j < wq; j += 32) {
+                const uint32_t cur = r32[j];
+                const uint32_t prev = j > 0 ? r32[j - 1] : (cur & 0xFFu) * 0x01010101u;
+                const uint32_t next = j < wq - 1 ? r32[j + 1] : (cur >> 24) * 0x01010101u;
+                uint32_t b[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { b[k] = (prev >> (8 * k)) & 0xFFu; b[4 + k] = (cur >> (8 * k)) & 0xFFu; b[8 + k] = (next >> (8 * k)) & 0xFFu; }
+                uint32_t s0 = 0;
+#pragma unroll
+                for (int d = -R; d <= R; ++d) s0 += b[4 + d];
+                const uint32_t s1 = s0 - b[4 - R] + b[5 + R], s2 = s1 - b[5 - R] + b[6 + R], s3 = s2 - b[6 - R] + b[7 + R];
+                out[j] = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
             }
         }
         __syncthreads();
         // ---- adaptiveThreshold(MEAN_C, BINARY, bs, C=0): src > round(sum / bs^2)  <=>  bs^2 * src > sum + (bs^2 - 1) / 2
+        // a warp owns a 64-pixel column segment (two pixels per lane) and slides the vertical sum down the band's rows
         uint32_t* raster = ws_raster + (size_t)e * (npx / 32 + 4);
-        for (int it = warp; it < (y1 - y0) * nseg; it += kWarps) {
-            const int ry = it / nseg, seg = it - ry * nseg;
-            const int y = y0 + ry, x = seg * 32 + lane;
-            uint32_t sum = 0;
-            for (int d = -R; d <= R; ++d) sum += hs[(clampi(y + d, 0, H - 1) - h0) * W + x];
-            const bool bit = area * (uint32_t)src[(y - src0) * W + x] > sum + half;
-            const uint32_t bits = __ballot_sync(0xffffffffu, bit);
-            if (lane == 0) raster[(size_t)y * nseg + seg] = bits;   // little-endian: bit b of word w = pixel 32w + b
+        const uint32_t* hs32 = reinterpret_cast<const uint32_t*>(hs);
+        const int wh = W / 2;
+        for (int seg = warp; seg < (W + 63) / 64; seg += kWarps) {
+            const int x = seg * 64 + 2 * lane;
+            const bool act = x < W;
+            const int xh = act ? x / 2 : 0;
+            uint32_t V = 0;
+#pragma unroll
+            for (int d = -R; d <= R; ++d) V += hs32[(clampi(y0 + d, 0, H - 1) - h0) * wh + xh];
+            for (int y = y0; y < y1; ++y) {
+                const uint32_t sp = *reinterpret_cast<const uint16_t*>(src + (y - src0) * W + 2 * xh);
+                const bool b0 = act && area * (sp & 0xFFu) > (V & 0xFFFFu) + half;
+                const bool b1 = act && area * (sp >> 8) > (V >> 16) + half;
+                const uint32_t ev = __ballot_sync(0xffffffffu, b0), od = __ballot_sync(0xffffffffu, b1);
+                // little-endian raster: bit b of word w = pixel 32w + b
+                if (lane == 0) raster[(size_t)y * nseg + 2 * seg] = spread16(ev & 0xFFFFu) | (spread16(od & 0xFFFFu) << 1);
+                if (lane == 1 && seg * 64 + 32 < W) raster[(size_t)y * nseg + 2 * seg + 1] = spread16(ev >> 16) | (spread16(od >> 16) << 1);
+                if (y + 1 < y1) V += hs32[(clampi(y + R + 1, 0, H - 1) - h0) * wh + xh] - hs32[(clampi(y - R, 0, H - 1) - h0) * wh + xh];
+            }
         }
     }
 }
@@ -216,6 +247,19 @@ __device__ __forceinline__ uint32_t heap_pop(Heap& h)
     uint32_t* v = h.sm + 1;
     // levels whose children both live in shared memory: one aligned 64-bit load per level
     const int lim_sm = lim < ((h.hs - 1) >> 1) ? lim : ((h.hs - 1) >> 1);
+    // two levels per shared-memory round trip: both children and all four grandchildren (one aligned 128-bit load)
+    while (2 * (second + 1) < lim_sm) {
+        const int c2 = 2 * (second + 1);
+        const uint2 ch = *reinterpret_cast<const uint2*>(h.sm + c2);        // elements c2-1, c2
+        const uint4 gc = *reinterpret_cast<const uint4*>(h.sm + 2 * c2);    // elements 2c2-1, 2c2 (children of c2-1), 2c2+1, 2c2+2 (of c2)
+        const bool left = hprio(ch.y) > hprio(ch.x);
+        const int c = left ? c2 - 1 : c2;
+        const uint32_t g0 = left ? gc.x : gc.z, g1 = left ? gc.y : gc.w;
+        const bool left2 = hprio(g1) > hprio(g0);
+        v[hole] = left ? ch.x : ch.y;
+        v[c] = left2 ? g0 : g1;
+        hole = second = 2 * c + (left2 ? 1 : 2);
+    }
     while (second < lim_sm) {
         second = 2 * (second + 1);
         const uint2 pr = *reinterpret_cast<const uint2*>(h.sm + second);   // .x = element second-1, .y = element second
@@ -274,7 +318,8 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uin
 }
 
 // ---------------------------------------------------------------------------------------------- the walk
-// Shared memory of one walking warp: heap[hs + 1] words, then one byte per cell:
+// Shared memory of one walking warp: heap[hs + 1] words, then the _remaining bitmap (1 bit per cell).  One byte per cell
+// lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel, off the pop chain):
 //   0 = decoded (FloodDecodePositions::_remaining false), else best_prio + 1 (0xFF for the initial 0xFE).
 // Why the inherit record (drift, best_prio, cooldown; FloodDecodePositions.h:17) can ride in the heap entry: update()
 // only rewrites it when the new error is strictly lower (FloodDecodePositions.cpp:75), and pushes an entry with that
@@ -284,11 +329,12 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uin
 __global__ void __launch_bounds__(32)
 k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
              int heap_smem, const uint32_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
-             const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace)
+             uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
     uint32_t* heap_sm = reinterpret_cast<uint32_t*>(walk_smem);
-    uint8_t* prio = walk_smem + (size_t)(heap_smem + 1) * 4;
+    uint32_t* remaining = heap_sm + heap_smem + 1;
+    uint8_t* prio = ws_prio + (size_t)blockIdx.x * kMaxCells;
     const int lane = threadIdx.x;
     const int W = m.width, npx = W * m.height, ncells = m.num_cells;
     const int cnt = chunk_count(counters, base, cap);
@@ -307,7 +353,8 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
         uint32_t* result = ws_result + (size_t)k * ncells;
 
         // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
-        for (int i = lane; i < (ncells + 3) / 4; i += 32) reinterpret_cast<uint32_t*>(prio)[i] = 0xFFFFFFFFu;
+        for (int i = lane; i < kMaxCells / 16; i += 32) __stcg(reinterpret_cast<uint4*>(prio) + i, make_uint4(~0u, ~0u, ~0u, ~0u));
+        for (int i = lane; i < (ncells + 31) / 32; i += 32) remaining[i] = 0xFFFFFFFFu;
         if (lane == 0) {
             heap.n = 0;
             const int last = ncells - 1, bmb = m.top_cells;
@@ -327,8 +374,10 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 while (heap.n > 0) {
                     const uint32_t t = heap_pop(heap);
                     const uint32_t i = t & 0x3FFFu;
-                    if (prio[i] == 0) continue;
-                    prio[i] = 0;
+                    const uint32_t w = remaining[i >> 5], bit = 1u << (i & 31u);
+                    if (!(w & bit)) continue;
+                    remaining[i >> 5] = w & ~bit;
+                    __stcg(prio + i, (uint8_t)0);
                     e = t;
                     break;
                 }
@@ -379,6 +428,9 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 const uint32_t wi = bit >> 5;
                 myrow = __funnelshift_r(__ldg(raster + wi), __ldg(raster + wi + 1), bit & 31u) & 0x3FFu;   // bit i = window col i
             }
+            // the candidates' priority bytes: requested now, needed only after the scoring below
+            uint32_t pv = 0;
+            if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
             uint32_t win[10];
 #pragma unroll
             for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
@@ -435,14 +487,14 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             // then records the new priority and pushes the survivors in the reference's order (adjacents, horizon, vert).
             const bool horizon = prev_err < 3u && dist < 3u && cooldown == 4u && ncd == 4u;
             const int cand = (cv != 0xFFFFu && (lane < 4 || horizon)) ? (int)cv : -1;
-            const bool push = cand >= 0 && (uint32_t)prio[cand] >= dist + 2u;
+            const bool push = cand >= 0 && pv >= dist + 2u;
             uint32_t todo = __ballot_sync(0xffffffffu, push) & 0xFFFu;
             const uint32_t entry = make_entry(0, ndx, ndy, cd_code(ncd), dist);
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int c = __shfl_sync(0xffffffffu, cand, l);
-                if (lane == 0) { prio[c] = (uint8_t)(dist + 1u); heap_push(heap, entry | (uint32_t)c); }
+                if (lane == 0) { __stcg(prio + c, (uint8_t)(dist + 1u)); heap_push(heap, entry | (uint32_t)c); }
             }
             __syncwarp();
         }
@@ -554,7 +606,7 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     // shared-memory heap entries per walking warp (must be odd); the default keeps 7 walks resident per SM
     ws->heap_smem = 4095;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
-    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)((m.num_cells + 15) / 16) * 16;
+    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)((m.num_cells + 127) / 128) * 16;
     int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
@@ -563,8 +615,10 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     ws->spill_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->walk_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_flood_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, true))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_flood_raster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, false))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_flood_raster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, true))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->spill, ws->spill_cap * (size_t)ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&ws->prio, (size_t)kMaxCells * (size_t)ws->slots)) != cudaSuccess) return e;
     std::vector<uint16_t> cinfo;
     flood_build_cinfo(m, adj_host, cinfo);
     if ((e = cudaMalloc(&ws->cinfo, cinfo.size() * sizeof(uint16_t))) != cudaSuccess) return e;
@@ -574,7 +628,7 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
 
 void flood_workspace_destroy(FloodWorkspace* ws)
 {
-    cudaFree(ws->spill); cudaFree(ws->cinfo); cudaFree(ws->list); cudaFree(ws->counters); cudaFree(ws->raster); cudaFree(ws->result);
+    cudaFree(ws->spill); cudaFree(ws->prio); cudaFree(ws->cinfo); cudaFree(ws->list); cudaFree(ws->counters); cudaFree(ws->raster); cudaFree(ws->result);
     memset(ws, 0, sizeof(*ws));
 }
 
@@ -621,10 +675,11 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         const int cap = n_frames - base < ws.entry_cap ? n_frames - base : ws.entry_cap;
         long long items = (long long)cap * nb;
         int rgrid = (int)(items < (long long)ws.sm_count * 3 ? items : (long long)ws.sm_count * 3);
-        k_flood_raster<<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, sharpen ? 1 : 0, ws.raster);
+        if (sharpen) k_flood_raster<true><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
+        else k_flood_raster<false><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
         int wgrid = cap < ws.slots ? cap : ws.slots;
         k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
-                                                      ws.spill, ws.spill_cap, ws.cinfo, d_trace);
+                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace);
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);

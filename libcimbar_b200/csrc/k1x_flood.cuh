@@ -22,6 +22,7 @@ struct FloodWorkspace {
     size_t walk_smem;          // dynamic shared memory of one walking warp
     size_t spill_cap;          // heap spill entries per slot
     uint32_t* spill;           // [slots][spill_cap]
+    uint8_t* prio;             // [slots][kMaxCells] per-cell priority bytes of the walk in that slot
     uint16_t* cinfo;           // [num_cells][16] update candidates in push order (0xFFFF = none)
     int list_cap; uint32_t* list; uint32_t* counters;   // work list; counters[0] = listed frames, [1 + c] = chunk c's work counter
     int entry_cap; uint32_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster, per-cell x | y<<11 | sym<<22
