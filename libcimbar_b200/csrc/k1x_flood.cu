@@ -120,17 +120,29 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
         const int h0 = y0 - R > 0 ? y0 - R : 0, h1 = y1 - 1 + R < H - 1 ? y1 - 1 + R : H - 1;   // rows of box sums needed (BORDER_REPLICATE)
         const int g0 = SHARPEN ? (h0 - 1 > 0 ? h0 - 1 : 0) : h0, g1 = SHARPEN ? (h1 + 1 < H - 1 ? h1 + 1 : H - 1) : h1;
         __syncthreads();                                // the previous item's readers are done
-        // ---- gray rows g0..g1, four pixels (three 32-bit words) per thread
+        // ---- gray rows g0..g1, four pixels (three 32-bit words) per thread; a lane's loads of a row are all issued before
+        // the first one is used (the kernel is otherwise starved for memory-level parallelism)
         for (int r = warp; r <= g1 - g0; r += kWarps) {
             const uint32_t* row = frame32 + (size_t)(g0 + r) * wq * 3;
             uint32_t* out = reinterpret_cast<uint32_t*>(g + r * W);
-            for (int j = lane; j < wq; j += 32) {
-                const uint32_t w0 = __ldg(row + 3 * j), w1 = __ldg(row + 3 * j + 1), w2 = __ldg(row + 3 * j + 2);
-                const uint32_t p0 = gray_of(w0 & 0xFFu, (w0 >> 8) & 0xFFu, (w0 >> 16) & 0xFFu);
-                const uint32_t p1 = gray_of(w0 >> 24, w1 & 0xFFu, (w1 >> 8) & 0xFFu);
-                const uint32_t p2 = gray_of((w1 >> 16) & 0xFFu, w1 >> 24, w2 & 0xFFu);
-                const uint32_t p3 = gray_of((w2 >> 8) & 0xFFu, (w2 >> 16) & 0xFFu, w2 >> 24);
-                out[j] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+            for (int j0 = 0; j0 < wq; j0 += 128) {
+                uint32_t w[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    if (j < wq) { w[u][0] = __ldg(row + 3 * j); w[u][1] = __ldg(row + 3 * j + 1); w[u][2] = __ldg(row + 3 * j + 2); }
+                    else { w[u][0] = w[u][1] = w[u][2] = 0; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    const uint32_t w0 = w[u][0], w1 = w[u][1], w2 = w[u][2];
+                    const uint32_t p0 = gray_of(w0 & 0xFFu, (w0 >> 8) & 0xFFu, (w0 >> 16) & 0xFFu);
+                    const uint32_t p1 = gray_of(w0 >> 24, w1 & 0xFFu, (w1 >> 8) & 0xFFu);
+                    const uint32_t p2 = gray_of((w1 >> 16) & 0xFFu, w1 >> 24, w2 & 0xFFu);
+                    const uint32_t p3 = gray_of((w2 >> 8) & 0xFFu, (w2 >> 16) & 0xFFu, w2 >> 24);
+                    if (j < wq) out[j] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+                }
             }
         }
         __syncthreads();
@@ -368,32 +380,26 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
 
         int count = 0;
         while (count < ncells) {
-            // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67): lane 0 pops until a remaining cell shows up
-            uint32_t e = 0xFFFFFFFFu;
-            if (lane == 0) {
-                while (heap.n > 0) {
-                    const uint32_t t = heap_pop(heap);
-                    const uint32_t i = t & 0x3FFFu;
-                    const uint32_t w = remaining[i >> 5], bit = 1u << (i & 31u);
-                    if (!(w & bit)) continue;
-                    remaining[i >> 5] = w & ~bit;
-                    __stcg(prio + i, (uint8_t)0);
-                    e = t;
-                    break;
-                }
-            }
-            __syncwarp();                                    // lane 0's heap / prio writes are ordered before the reads below
-            e = __shfl_sync(0xffffffffu, e, 0);
-            if (e == 0xFFFFFFFFu) break;                     // heap exhausted (cannot happen on a connected grid)
-            ++count;
+            // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67).  The entry about to pop is the heap's first
+            // element, so every lane reads it there and the loads of the cell's window / neighbours are in flight while
+            // lane 0 runs the sift-down of the pop itself.
+            const int hn = __shfl_sync(0xffffffffu, heap.n, 0);
+            if (hn == 0) break;                              // heap exhausted (cannot happen on a connected grid)
+            const uint32_t e = heap_sm[1];
             const int ci = (int)(e & 0x3FFFu);
+            const uint32_t rem_bit = 1u << (ci & 31);
+            if (!(remaining[ci >> 5] & rem_bit)) {           // stale entry of a cell that is already decoded: skipped
+                if (lane == 0) heap_pop(heap);
+                __syncwarp();
+                continue;
+            }
+            ++count;
             // neighbours: lanes 0-3 direct (right, left, bottom, top), 4-11 the horizon chains (see flood_build_cinfo)
             uint32_t cv = 0xFFFFu;
             if (lane < 12) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
             uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
             int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
-            if (code == kSeedCode) {
-                const int hn = __shfl_sync(0xffffffffu, heap.n, 0);
+            if (code == kSeedCode) {                         // (scanned before the pop: the seed entry itself is excluded either way)
                 uint32_t latest = 0xFFFFFFFFu;
                 for (int i = lane; i < hn; i += 32) {
                     const uint32_t t = heap.get(i);
@@ -422,15 +428,25 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             }
             const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
             // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r
-            uint32_t myrow = 0;
+            uint32_t ra = 0, rb = 0, rshift = 0;
             if (lane < 10) {
                 const uint32_t bit = (uint32_t)(y - 1 + lane) * (uint32_t)W + (uint32_t)(x - 1);
                 const uint32_t wi = bit >> 5;
-                myrow = __funnelshift_r(__ldg(raster + wi), __ldg(raster + wi + 1), bit & 31u) & 0x3FFu;   // bit i = window col i
+                rshift = bit & 31u;
+                ra = __ldg(raster + wi); rb = __ldg(raster + wi + 1);
             }
+            asm volatile("" ::: "memory");
+            if (lane == 0) {
+                heap_pop(heap);
+                remaining[ci >> 5] &= ~rem_bit;
+                __stcg(prio + ci, (uint8_t)0);
+            }
+            __syncwarp();                                    // lane 0's heap / bitmap / prio writes are ordered before the reads below
+            asm volatile("" ::: "memory");
             // the candidates' priority bytes: requested now, needed only after the scoring below
             uint32_t pv = 0;
             if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
+            const uint32_t myrow = __funnelshift_r(ra, rb, rshift) & 0x3FFu;   // bit i = window col i
             uint32_t win[10];
 #pragma unroll
             for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
