@@ -389,6 +389,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             const int ci = (int)(e & 0x3FFFu);
             const uint32_t rem_bit = 1u << (ci & 31);
             if (!(remaining[ci >> 5] & rem_bit)) {           // stale entry of a cell that is already decoded: skipped
+                __syncwarp();
                 if (lane == 0) heap_pop(heap);
                 __syncwarp();
                 continue;
@@ -435,6 +436,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 rshift = bit & 31u;
                 ra = __ldg(raster + wi); rb = __ldg(raster + wi + 1);
             }
+            __syncwarp();                                    // every lane has read the heap top / bitmap before lane 0 rewrites them
             asm volatile("" ::: "memory");
             if (lane == 0) {
                 heap_pop(heap);
