@@ -114,6 +114,11 @@ bool mode_init(Mode& m, int mode_val)
         if (ok) m.hash_mul = mul;
     }
     fill_palette(1 << m.color_bits, m.color_mode, m.palette);
+    for (int i = 0; i < 8; ++i) {
+        const int p0 = (int)m.palette[i][0] - (int)m.palette[i][1], p1 = (int)m.palette[i][1] - (int)m.palette[i][2],
+                  p2 = (int)m.palette[i][2] - (int)m.palette[i][0];
+        m.pal_c[i] = p0 * p0 + p1 * p1 + p2 * p2; m.pal_u[i] = 2 * (p0 - p2); m.pal_w[i] = 2 * (p1 - p2);
+    }
     return m.hash_mul != 0;
 }
 

@@ -34,6 +34,9 @@ struct Mode {
     int mid_cells;                     // cells_x * (cells_y - 2*corner)
     uint32_t hash_mul;                 // perfect hash over the tile dictionary: slot = (L_lo * hash_mul) >> 28
     uint8_t palette[8][4];             // decode palette for (num_colors, color_mode): Common.cpp:21-85, :122-139
+    // colour distance in closed form (CimbDecoder.cpp:168-200): with p = (pr-pg, pg-pb, pb-pr) of palette entry i and
+    // a = (r-g, g-b, b-r) of the cell, |a - p|^2 = |a|^2 + pal_c[i] - (a0 * pal_u[i] + a1 * pal_w[i])  (a2 = -a0-a1)
+    int pal_c[8], pal_u[8], pal_w[8];  // |p|^2, 2 (p0 - p2), 2 (p1 - p2)
 };
 
 // cell row k (0..cells_y-1): first cell index, number of cells, x of first cell

@@ -106,16 +106,14 @@ __device__ __forceinline__ uint32_t best_color(const float* adjust_tab, const Mo
     int cr = (fr > hi_thr) ? 255 : (int)__float2uint_rz(fr);
     int cg = (fg > hi_thr) ? 255 : (int)__float2uint_rz(fg);
     int cb = (fb > hi_thr) ? 255 : (int)__float2uint_rz(fb);
-    const int a0 = cr - cg, a1 = cg - cb, a2 = cb - cr;
-    // color_diff = sum_j (a_j - p_ij)^2 = |a|^2 + (|p_i|^2 - 2 a.p_i): the first term is common, so the strict-'<' argmin
-    // over i of the bracket is the reference's argmin (same ties)
+    const int a0 = cr - cg, a1 = cg - cb;
+    // color_diff = sum_j (a_j - p_ij)^2 = |a|^2 + |p_i|^2 - 2 a.p_i, and a2 = -a0 - a1: the first term is common, so the
+    // strict-'<' argmin over i of pal_c[i] - (a0 pal_u[i] + a1 pal_w[i]) is the reference's argmin (same ties)
     uint32_t best = 0;
     int best_d = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        const int p0 = (int)m.palette[i][0] - (int)m.palette[i][1], p1 = (int)m.palette[i][1] - (int)m.palette[i][2],
-                  p2 = (int)m.palette[i][2] - (int)m.palette[i][0];
-        const int d = (p0 * p0 + p1 * p1 + p2 * p2) - 2 * (a0 * p0 + a1 * p1 + a2 * p2);
+        const int d = m.pal_c[i] - (a0 * m.pal_u[i] + a1 * m.pal_w[i]);
         if (d < best_d) { best_d = d; best = (uint32_t)i; }
     }
     return best;
@@ -153,21 +151,36 @@ __device__ __forceinline__ uint32_t raster_bits(const K1Smem& s, uint32_t rbuf, 
 // o = pixel x of window column 0.  Every lane returns the same key.
 __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t rbuf, uint32_t o, bool all, int lane)
 {
-    const int ncand = (all ? 9 : 5) * 16;
-    uint32_t best_key = 0xFFFFFFFFu;
-    for (int p = lane; p < ncand; p += 32) {
-        const uint32_t q = (uint32_t)p >> 4, tile = (uint32_t)p & 15u;
-        const uint32_t id = (uint32_t)(0x620813754ULL >> (4 * q)) & 0xFu;     // order 4,5,7,3,1,8,0,2,6
-        const uint32_t r0 = id / 3u, c0 = id - 3u * r0;
-        uint32_t lo = 0, hi = 0;
+    // lanes 0..9 fetch the ten 10-bit window rows, every lane gets all of them
+    const uint32_t myrow = raster_bits(s, rbuf, lane < 10 ? lane : 0, o) & 0x3FFu;
+    uint32_t win[10];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            lo |= (raster_bits(s, rbuf, (int)r0 + k, o + c0) & 0xFFu) << (8 * k);
-            hi |= (raster_bits(s, rbuf, (int)r0 + 4 + k, o + c0) & 0xFFu) << (8 * k);
-        }
-        uint2 tl = s.tiles_by_sym[tile];
-        uint32_t d = __popc(lo ^ tl.x) + __popc(hi ^ tl.y);
-        uint32_t key = (d << 8) | (q << 4) | tile;
+    for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
+    // lane q < 9 extracts the hash at drift id order[q]: columns c0..c0+7 of the ten rows form an 80-bit string, the hash
+    // at row offset r0 is bits [8 r0, 8 r0 + 64) of it (ahash_result::extract, ahash_result.h:70-106)
+    uint32_t hlo, hhi;
+    {
+        const int qq = lane < 9 ? lane : 0;
+        const int r0 = (int)((0x200201211ULL >> (4 * qq)) & 3u), c0 = (int)((0x020210121ULL >> (4 * qq)) & 3u);   // id / 3, id % 3
+        uint32_t b[10];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) b[r] = (win[r] >> c0) & 0xFFu;
+        const uint32_t w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        const uint32_t w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        const uint32_t w2 = b[8] | (b[9] << 8);
+        hlo = __funnelshift_r(w0, w1, 8 * r0); hhi = __funnelshift_r(w1, w2, 8 * r0);
+    }
+    // every lane scores its tile (lane & 15) against the hashes q = 2 it + (lane >> 4)
+    const uint2 tl = s.tiles_by_sym[lane & 15];
+    const int nq = all ? 9 : 5;
+    uint32_t best_key = 0xFFFFFFFFu;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        if (it >= 3 && !all) break;                       // warp-uniform
+        const int q = 2 * it + (lane >> 4);
+        const uint32_t lo = __shfl_sync(0xffffffffu, hlo, q & 15), hi = __shfl_sync(0xffffffffu, hhi, q & 15);
+        const uint32_t d = (uint32_t)(__popc(lo ^ tl.x) + __popc(hi ^ tl.y));
+        const uint32_t key = q < nq ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15)) : 0xFFFFFFFFu;
         best_key = key < best_key ? key : best_key;
     }
     return __reduce_min_sync(0xffffffffu, best_key);

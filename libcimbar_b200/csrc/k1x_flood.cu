@@ -26,7 +26,7 @@ namespace cb200 {
 
 constexpr int kRasterThreads = 256;
 constexpr int kBandRows = 16;            // output rows per raster CTA
-constexpr int kFloodMaxEntries = 4096;   // listed frames whose raster/result are resident at once (one chunk)
+constexpr int kFloodMaxEntries = 16384;  // listed frames whose raster/result are resident at once (one chunk, 181 KB each)
 
 __constant__ float cx_adjust[256];
 __constant__ unsigned long long cx_tiles_L[16];
@@ -665,8 +665,8 @@ static cudaError_t flood_workspace_ensure(const Mode& m, FloodWorkspace& ws, int
     }
     const int want = n_frames < kFloodMaxEntries ? n_frames : kFloodMaxEntries;
     if (want > ws.entry_cap) {
-        int cap = ws.entry_cap ? ws.entry_cap : 64;
-        while (cap < want) cap *= 2;
+        int cap = (want + 1023) / 1024 * 1024;          // in steps of 1024 frames (185 MB)
+        if (want <= 64) cap = 64; else if (want <= 256) cap = 256;
         cudaFree(ws.raster); cudaFree(ws.result); ws.raster = nullptr; ws.result = nullptr; ws.entry_cap = 0;
         if ((e = cudaMalloc(&ws.raster, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
         if ((e = cudaMemset(ws.raster, 0, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
