@@ -74,8 +74,8 @@ struct RsSmem {
     uint8_t exp[512];
     uint8_t log[256];
     struct PerWarp {
-        alignas(4) uint8_t enc[256];
-        alignas(8) uint16_t encs[256];   // enc[i] * (128*T): byte offset of table row enc[i] (syndrome loop operand)
+        alignas(16) uint32_t encs[256];  // block byte i as enc[i] * (128*T) = the byte offset of table row enc[i] (the syndrome
+                                         // loop's operand as is; the byte itself is encs[i] >> kRowShift)
         uint8_t synd[kMaxParity];
         uint8_t loc[kMaxParity + 8];
         uint8_t last[kMaxParity + 8];
@@ -97,6 +97,12 @@ __device__ __forceinline__ uint32_t gf_div(const RsSmem& s, uint32_t a, uint32_t
     if (a == 0 || b == 0) return 0;
     return s.exp[255u + (uint32_t)s.log[a] - (uint32_t)s.log[b]];
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 {
 #pragma unroll
@@ -110,7 +116,7 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 // symbol stream blocks then colour stream blocks).
 // data_out: n_frames * nblocks * msg_len (zeros for failed blocks, reed_solomon_stream.h:96-107); ok: n_frames * nblocks
 template <int T, bool FUSED>
-__global__ void __launch_bounds__(kRsWarpsPerCta * 32)
+__global__ void __launch_bounds__(kRsWarpsPerCta * 32, 4)
 k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __restrict__ cellvals, const uint16_t* __restrict__ idx,
             int n_frames, uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok)
 {
@@ -137,28 +143,66 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         __syncwarp();
         if (FUSED) {
             const uint8_t* cells = cellvals + (size_t)f * m.num_cells;
-            const bool fast = !m.legacy && m.symbol_bits == 4 && m.color_bits == 2;
-            for (int i = lane; i < blk; i += 32) {
-                uint32_t B = (uint32_t)b * (uint32_t)blk + (uint32_t)i, v;
-                if (fast && (int)B < m.cap_sym) {          // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
-                    const uint32_t sl = *reinterpret_cast<const uint32_t*>(idx + 2u * B);
-                    v = ((uint32_t)(cells[sl & 0xFFFFu] & 15u) << 4) | (uint32_t)(cells[sl >> 16] & 15u);
-                } else if (fast) {                         // four 2-bit colours per byte (Decoder.h:112-113)
-                    const uint2 sl = *reinterpret_cast<const uint2*>(idx + 4u * (B - (uint32_t)m.cap_sym));
-                    v = ((uint32_t)((cells[sl.x & 0xFFFFu] >> 4) & 3u) << 6) | ((uint32_t)((cells[sl.x >> 16] >> 4) & 3u) << 4) |
-                        ((uint32_t)((cells[sl.y & 0xFFFFu] >> 4) & 3u) << 2) | (uint32_t)((cells[sl.y >> 16] >> 4) & 3u);
+            const bool fast = !m.legacy && m.symbol_bits == 4 && m.color_bits == 2 && blk <= 160;
+            if (fast) {
+                // a block lies entirely in the symbol stream or in the colour stream (cap_sym is a whole number of blocks).
+                // All interleave-map words of the block are loaded first, then all cell bytes: two dependent round trips
+                // to L2 per block instead of two per 32 bytes.
+                const uint32_t B0 = (uint32_t)b * (uint32_t)blk;
+                constexpr int kU = 5;                      // 5 x 32 >= ecc_block (155 in every mode; checked at launch)
+                if ((int)B0 < m.cap_sym) {                 // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
+                    uint32_t sl[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = lane + 32 * u;
+                        sl[u] = i < blk ? *reinterpret_cast<const uint32_t*>(idx + 2u * (B0 + (uint32_t)i)) : 0u;
+                    }
+                    uint32_t c0[kU], c1[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = lane + 32 * u;
+                        if (i < blk) { c0[u] = cells[sl[u] & 0xFFFFu]; c1[u] = cells[sl[u] >> 16]; } else { c0[u] = c1[u] = 0; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = lane + 32 * u;
+                        if (i < blk) w.encs[i] = (((c0[u] & 15u) << 4) | (c1[u] & 15u)) * (128u * T);
+                    }
+                } else {                                   // four 2-bit colours per byte (Decoder.h:112-113)
+                    uint2 sl[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = lane + 32 * u;
+                        sl[u] = i < blk ? *reinterpret_cast<const uint2*>(idx + 4u * (B0 + (uint32_t)i - (uint32_t)m.cap_sym)) : make_uint2(0u, 0u);
+                    }
+                    uint32_t c0[kU], c1[kU], c2[kU], c3[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = lane + 32 * u;
+                        if (i < blk) { c0[u] = cells[sl[u].x & 0xFFFFu]; c1[u] = cells[sl[u].x >> 16]; c2[u] = cells[sl[u].y & 0xFFFFu]; c3[u] = cells[sl[u].y >> 16]; }
+                        else { c0[u] = c1[u] = c2[u] = c3[u] = 0; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = lane + 32 * u;
+                        if (i < blk)
+                            w.encs[i] = ((((c0[u] >> 4) & 3u) << 6) | (((c1[u] >> 4) & 3u) << 4) | (((c2[u] >> 4) & 3u) << 2) | ((c3[u] >> 4) & 3u)) * (128u * T);
+                    }
                 }
-                else if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
-                else if ((int)B < m.cap_sym) v = stream_byte(cells, idx, B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
-                else v = stream_byte(cells, idx, B - (uint32_t)m.cap_sym, m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
-                w.enc[i] = (uint8_t)v;
-                w.encs[i] = (uint16_t)(v * (128u * T));
+            } else {
+                for (int i = lane; i < blk; i += 32) {
+                    uint32_t B = (uint32_t)b * (uint32_t)blk + (uint32_t)i, v;
+                    if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
+                    else if ((int)B < m.cap_sym) v = stream_byte(cells, idx, B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
+                    else v = stream_byte(cells, idx, B - (uint32_t)m.cap_sym, m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
+                    w.encs[i] = v * (128u * T);
+                }
             }
         } else {
             // symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
             // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks
             const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
-            for (int i = lane; i < blk; i += 32) { uint32_t v = enc_g[i]; w.enc[i] = (uint8_t)v; w.encs[i] = (uint16_t)(v * (128u * T)); }
+            for (int i = lane; i < blk; i += 32) w.encs[i] = (uint32_t)enc_g[i] * (128u * T);
         }
         __syncwarp();
 
@@ -166,19 +210,21 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         uint32_t nz = 0;
 #pragma unroll
         for (int q = 0; q < T; ++q) {
-            // Horner with every value kept as a table-row byte offset: off' = mt[off][lane] ^ enc_off  (one LDS, one XOR per byte)
-            const char* colb = reinterpret_cast<const char*>(mt) + 4 * (lane + 32 * q);
+            // Horner with every value kept as a table-row byte offset: off' = mt[off][lane] ^ enc_off -- per byte one address
+            // add, one LDS and one XOR (32-bit shared addresses, so no generic-pointer arithmetic in the chain)
+            const uint32_t colb = (uint32_t)__cvta_generic_to_shared(mt) + 4u * (uint32_t)(lane + 32 * q);
             uint32_t off = 0;
-            const uint2* e4 = reinterpret_cast<const uint2*>(w.encs);
+            const uint4* e4 = reinterpret_cast<const uint4*>(w.encs);
             int i = 0;
+#pragma unroll 2
             for (; i + 4 <= blk; i += 4) {
-                const uint2 e = e4[i >> 2];
-                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.x & 0xFFFFu);
-                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.x >> 16);
-                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.y & 0xFFFFu);
-                off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (e.y >> 16);
+                const uint4 e = e4[i >> 2];
+                off = lds_u32(colb + off) ^ e.x;
+                off = lds_u32(colb + off) ^ e.y;
+                off = lds_u32(colb + off) ^ e.z;
+                off = lds_u32(colb + off) ^ e.w;
             }
-            for (; i < blk; ++i) off = *reinterpret_cast<const uint32_t*>(colb + off) ^ (uint32_t)w.encs[i];
+            for (; i < blk; ++i) off = lds_u32(colb + off) ^ w.encs[i];
             const uint32_t acc = off / (128u * T);
             const int j = lane + 32 * q;
             if (j < md) { w.synd[j] = (uint8_t)acc; nz |= acc; }
@@ -186,7 +232,7 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         nz = __ballot_sync(0xffffffffu, nz != 0);
         __syncwarp();
         if (nz == 0) {  // clean block: copy out (decode.c:337-343)
-            for (int i = lane; i < msg_len; i += 32) out[i] = w.enc[i];
+            for (int i = lane; i < msg_len; i += 32) out[i] = (uint8_t)(w.encs[i] / (128u * T));
             if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
             continue;
         }
@@ -332,10 +378,10 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
             uint32_t inv = s.exp[510u - lx];             // field_div(1, X): log[1] = 255
             uint32_t location = s.log[inv];              // coefficient index (255 when inv == 1: out of range in libcorrect)
             if (location >= (uint32_t)md && location < (uint32_t)blk)
-                w.enc[blk - 1 - (int)location] ^= (uint8_t)err;
+                w.encs[blk - 1 - (int)location] ^= err * (128u * T);
         }
         __syncwarp();
-        for (int i = lane; i < msg_len; i += 32) out[i] = w.enc[i];
+        for (int i = lane; i < msg_len; i += 32) out[i] = (uint8_t)(w.encs[i] / (128u * T));
         if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
     }
 }
