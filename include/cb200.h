@@ -35,6 +35,12 @@ extern "C" {
 /* decode flags */
 #define CB200_FLAG_NO_FALLBACK  0x1u  /* do not run the exact flood-walk kernel on frames K1 flags as inexact (bench only) */
 #define CB200_FLAG_SHARPEN      0x2u  /* needs_sharpen / should_preprocess=true: 3x3 sharpen + block 7 (CimbReader.cpp:17-40) */
+#define CB200_FLAG_CC_SIMPLE    0x4u  /* color_correction == 1: every frame gets the von Kries matrix of its own anchor white
+                                         before anything is read (simpleColorCorrection, CimbReader.cpp:55-93, :124-125);
+                                         afterwards the context's CCM is the last frame's, as in the reference's decoder.
+                                         Without this flag the colour pass uses the context's CCM if one is set (below);
+                                         color_correction == 2's per-frame header fit (CimbReader::init_ccm) is NOT part
+                                         of the library: compute it on the host and hand it in through cb200_set_ccm. */
 
 /* per-frame status bits written to frame_flags[] */
 #define CB200_FRAME_FALLBACK    0x1u  /* frame was decoded by the exact flood-walk kernel (drift tracking needed) */
@@ -139,6 +145,18 @@ int cb200_decode_symbols(cb200_ctx* ctx, const uint16_t* windows, const uint8_t*
 /* Replaces: CimbDecoder::get_best_color(r, g, b, color_mode) (CimbDecoder.cpp:168-200) for integer means.
    rgb: n x 3 bytes; out: color[n]. Host pointers. */
 int cb200_best_colors(cb200_ctx* ctx, const uint8_t* rgb_means, int n, uint8_t* color);
+
+/* ---- colour correction matrix (the decoder's CCM state) -------------------------------------------------------- */
+
+/* Replaces: CimbDecoder::update_color_correction(cv::Matx<float,3,3>&&) (src/lib/cimb_translator/CimbDecoder.cpp:82-85),
+   also what DecoderPlus::load_ccm feeds (src/lib/encoder/DecoderPlus.h:31-42).  m9 = 9 floats, row-major; NULL deactivates
+   the CCM (TestableCimbDecoder: internal_ccm() = color_correction()).  While a CCM is active every colour decision of this
+   context (all decode entry points and cb200_best_colors) runs color_correction::transform + get_best_color in the
+   reference's float32 operation order (chromatic_adaptation/color_correction.h:64-68, CimbDecoder.cpp:168-200). */
+int cb200_set_ccm(cb200_ctx* ctx, const float* m9);
+/* Replaces: CimbDecoder::get_ccm() (CimbDecoder.cpp:76-80): returns 1 and fills m9 when a CCM is active, else 0.
+   After a CB200_FLAG_CC_SIMPLE call this is the last frame's matrix (synchronises the context's stream). */
+int cb200_get_ccm(cb200_ctx* ctx, float* m9);
 
 /* ---- synthetic input (benchmark support; the inverse of the path) ---------------------------------------------- */
 

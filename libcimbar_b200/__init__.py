@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libcb200.so")
 
 FLAG_NO_FALLBACK = 0x1
 FLAG_SHARPEN = 0x2
+FLAG_CC_SIMPLE = 0x4
 FRAME_FALLBACK = 0x1
 FRAME_INEXACT = 0x2
 
@@ -22,7 +23,7 @@ EXPORTS = [
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
-    "cb200_sink_file_read", "cb200_selfcheck",
+    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm",
 ]
 
 
@@ -68,6 +69,8 @@ def load_library():
     lib.cb200_decode_cells.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, vp]
     lib.cb200_decode_symbols.argtypes = [vp, u16p, u8p, C.c_int, u8p, u8p, u8p]
     lib.cb200_best_colors.argtypes = [vp, u8p, C.c_int, u8p]
+    lib.cb200_set_ccm.argtypes = [vp, C.c_void_p]
+    lib.cb200_get_ccm.argtypes = [vp, C.c_void_p]
     lib.cb200_render_frames_dev.argtypes = [vp, u8p, C.c_int, u8p]
     lib.cb200_encode_cells_dev.argtypes = [vp, u8p, C.c_int, u8p]
     lib.cb200_set_timing.argtypes = [vp, C.c_int]
@@ -194,6 +197,22 @@ class Context:
         out = np.zeros(rgb_means.shape[0], dtype=np.uint8)
         _check(self.lib.cb200_best_colors(self._h, rgb_means.ctypes.data, rgb_means.shape[0], out.ctypes.data))
         return out
+
+    def set_ccm(self, m9):
+        """CimbDecoder::update_color_correction: 3x3 float32 row-major, or None to deactivate"""
+        if m9 is None:
+            _check(self.lib.cb200_set_ccm(self._h, None))
+        else:
+            a = np.ascontiguousarray(m9, dtype=np.float32).reshape(9)
+            _check(self.lib.cb200_set_ccm(self._h, a.ctypes.data))
+
+    def get_ccm(self):
+        """the active CCM as a 3x3 float32 array, or None"""
+        a = np.zeros(9, dtype=np.float32)
+        rc = self.lib.cb200_get_ccm(self._h, a.ctypes.data)
+        if rc < 0:
+            _check(rc)
+        return a.reshape(3, 3) if rc == 1 else None
 
     # ---- device-pointer entry points (raw device addresses, e.g. torch.Tensor.data_ptr())
     def decode_raw_dev(self, d_rgb, n, d_raw_out, d_flags=None, flags=0):

@@ -227,6 +227,12 @@ struct cb200_ctx {
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
     // pinned host staging for results of the host-pointer entry points
     uint8_t* h_pinned = nullptr; size_t h_pinned_bytes = 0;
+    // colour correction (the reference's thread-local CimbDecoder CCM, CimbDecoder.cpp:69-85)
+    float ccm[9] = {};               // active matrix, row-major
+    bool ccm_active = false;
+    bool ccm_pending = false;        // the last CC_SIMPLE batch's final matrix is still on its way to h_ccm
+    float* d_ccm = nullptr;          // per-frame matrices of a CC_SIMPLE batch: max_frames x 9
+    float* h_ccm = nullptr;          // pinned, 9 floats
 };
 
 namespace {
@@ -253,11 +259,42 @@ int check_n(const cb200_ctx* c, int n)
     return CB200_OK;
 }
 
+// the context's CCM as the colour kernels take it; resolves the matrix a CC_SIMPLE batch left behind
+int ccm_resolve(cb200_ctx* c)
+{
+    if (!c->ccm_pending) return CB200_OK;
+    CK(cudaStreamSynchronize(c->stream), "sync (ccm)");
+    memcpy(c->ccm, c->h_ccm, sizeof(c->ccm));
+    c->ccm_pending = false;
+    return CB200_OK;
+}
+int ccm_arg(cb200_ctx* c, CcmArg& cc)
+{
+    memset(&cc, 0, sizeof(cc));
+    int rc = ccm_resolve(c); if (rc) return rc;
+    if (c->ccm_active) { cc.active = 1; memcpy(cc.m, c->ccm, sizeof(cc.m)); }
+    return CB200_OK;
+}
+
 // K1 (+ exact-walk fallback) : frames -> per-cell bytes in ctx->d_cellvals, per-frame flags in ctx->d_flags
 int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTrace* d_trace = nullptr)
 {
     const Mode& m = c->mode;
     cudaStream_t st = c->stream;
+    CcmArg cc;
+    if ((flags & CB200_FLAG_CC_SIMPLE) && n > 0) {
+        // color_correction == 1: one matrix per frame, computed on the device before the colour pass (CimbReader.cpp:124-125)
+        if (!c->d_ccm) CK(cudaMalloc(&c->d_ccm, sizeof(float) * 9 * (size_t)c->max_frames), "cudaMalloc ccm");
+        if (!c->h_ccm) CK(cudaMallocHost(&c->h_ccm, sizeof(float) * 9), "cudaMallocHost ccm");
+        memset(&cc, 0, sizeof(cc));
+        CK(ccm_simple_launch(m, d_rgb, n, c->d_ccm, st), "ccm launch");
+        cc.per_frame = c->d_ccm; cc.active = 1;
+        // the decoder keeps the last matrix it was given (CimbDecoder.cpp:82-85)
+        CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, st), "D2H ccm");
+        c->ccm_pending = true; c->ccm_active = true;
+    } else {
+        int rc = ccm_arg(c, cc); if (rc) return rc;
+    }
     const bool sharpen = (flags & CB200_FLAG_SHARPEN) != 0;
     const bool exact_only = sharpen || d_trace != nullptr;     // these go straight to the exact-walk kernel
     CK(cudaMemsetAsync(c->d_dirty, 0, sizeof(uint32_t) * (size_t)n, st), "memset dirty");
@@ -270,12 +307,12 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTra
         if (n < ctas) { bands = (ctas + n - 1) / n; if (bands > m.cells_y / 4) bands = m.cells_y / 4; if (bands < 1) bands = 1; }
         int units = n * bands;
         int grid = units < ctas ? units : ctas;
-        CK(k1_launch(m, d_rgb, n, bands, grid, c->l2_ahead, c->d_cellvals, c->d_dirty, st), "k1 launch");
+        CK(k1_launch(m, d_rgb, n, bands, grid, c->l2_ahead, c->d_cellvals, c->d_dirty, cc, st), "k1 launch");
     }
     mark(c);                                   // ev1: after K1
     // the sharpen preprocessing (needs_sharpen, CimbReader.cpp:37-40) is only implemented in the exact-walk kernel
     CK(flood_launch(m, c->flood, d_rgb, n, (flags & CB200_FLAG_NO_FALLBACK) != 0, exact_only, sharpen,
-                    c->d_cellvals, c->d_dirty, c->d_flags, d_trace, st), "flood launch");
+                    c->d_cellvals, c->d_dirty, c->d_flags, d_trace, cc, st), "flood launch");
     mark(c);                                   // ev2: after K1x
     return CB200_OK;
 }
@@ -420,6 +457,8 @@ int cb200_destroy(cb200_ctx* c)
     cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_scratch);
     for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) if (c->ev[k][i]) cudaEventDestroy(c->ev[k][i]);
     flood_workspace_destroy(&c->flood);
+    cudaFree(c->d_ccm);
+    if (c->h_ccm) cudaFreeHost(c->h_ccm);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -599,10 +638,30 @@ int cb200_best_colors(cb200_ctx* c, const uint8_t* rgb_means, int n, uint8_t* co
     int rc = ensure_scratch(c, 4 * (size_t)n + 64); if (rc) return rc;
     uint8_t* d_in = static_cast<uint8_t*>(c->d_scratch); uint8_t* d_out = d_in + 3 * (size_t)n;
     CK(cudaMemcpyAsync(d_in, rgb_means, 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D");
-    CK(k1_colors_launch(c->mode, d_in, n, d_out, c->stream), "colors launch");
+    CcmArg cc;
+    rc = ccm_arg(c, cc); if (rc) return rc;
+    CK(k1_colors_launch(c->mode, d_in, n, d_out, cc, c->stream), "colors launch");
     CK(cudaMemcpyAsync(color, d_out, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "D2H");
     CK(cudaStreamSynchronize(c->stream), "sync");
     return CB200_OK;
+}
+
+int cb200_set_ccm(cb200_ctx* c, const float* m9)
+{
+    if (!c) return fail(CB200_ERR_ARG, "null context");
+    c->ccm_pending = false;                      // an explicit matrix replaces whatever the last batch left
+    c->ccm_active = m9 != nullptr;
+    if (m9) memcpy(c->ccm, m9, sizeof(c->ccm));
+    return CB200_OK;
+}
+
+int cb200_get_ccm(cb200_ctx* c, float* m9)
+{
+    if (!c) return fail(CB200_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    int rc = ccm_resolve(c); if (rc) return rc;
+    if (c->ccm_active && m9) memcpy(m9, c->ccm, sizeof(c->ccm));
+    return c->ccm_active ? 1 : 0;
 }
 
 int cb200_encode_cells_dev(cb200_ctx* c, const uint8_t* d_payload, int n, uint8_t* d_cellvals)

@@ -22,6 +22,7 @@
 // Every HBM byte of the frame is read exactly once (plus 4 warm-up rows per band).
 #include "cb200_common.cuh"
 #include "k1_decode.cuh"
+#include "ccm.cuh"
 #include <cstdlib>
 
 namespace cb200 {
@@ -41,6 +42,7 @@ struct __align__(128) K1Smem {
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
     float adjust[256];                        // copy of c_adjust: indexed per lane, so not read through the constant cache
     unsigned long long full_bar[2];
+    float ccm[12];                            // CCM variant only: the current frame's 3x3 colour correction matrix
 };
 
 __constant__ float c_adjust[256];             // (float)(255.0 / (double)d), d = max-min (CimbDecoder.cpp:185)
@@ -201,10 +203,12 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 //                             unit 0, all dead now), L2 prefetch further ahead
 //   B(k):   box sums, threshold -> raster[it&1]
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
-template <int NC, bool G1024>
+// CCM: the colour classifier runs the reference's float path with a 3x3 colour correction matrix (ccm.cuh) instead of the
+// integer restatement; the matrix of the frame is staged in shared memory when a CTA starts on it.
+template <int NC, bool G1024, bool CCM>
 __global__ void __launch_bounds__(kK1Threads, 4)
 k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
-                 uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags)
+                 uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags, const CcmArg cc)
 {
     // G1024: the 1024x1024 / 112x112-cell geometry of modes B, 4C and 8C as compile-time constants (GridConf.h:121-141);
     // the other modes (Bm 1024x720, Bu 736x637) take every dimension from the Mode struct
@@ -341,6 +345,10 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         int f = u / bands, b = u - f * bands;
         int k0 = (m.cells_y() * b) / bands, k1 = (m.cells_y() * (b + 1)) / bands;
         uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells();
+        if (CCM) {      // nobody reads s.ccm between the last colour pass of the previous unit and this barrier
+            if (tid < 9) s.ccm[tid] = cc.per_frame ? cc.per_frame[(size_t)f * 9 + tid] : cc.m[tid];
+            __syncthreads();
+        }
 
         uint32_t hprev[5][4], Pprev[2][4], nV[4];
 #pragma unroll
@@ -412,7 +420,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                         rgb_row6(ub[0] + 2u * row_bytes, x, R, G, B);
                         rgb_row6(ub[1], x, R, G, B);
                         rgb_row6(ub[1] + row_bytes, x, R, G, B);
-                        col = best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
+                        col = CCM ? best_color_ccm<NC>(s.ccm, mm, R / 36u, G / 36u, B / 36u) : best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
                     }
                 }
                 carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
@@ -509,10 +517,11 @@ __global__ void k_decode_symbols(const uint16_t* __restrict__ windows, const uin
     symbol[i] = (uint8_t)best_sym; drift_offset[i] = (uint8_t)best_id; distance[i] = (uint8_t)best;
 }
 
-__global__ void k_best_colors(const Mode m, const uint8_t* __restrict__ rgb, int n, uint8_t* __restrict__ color)
+__global__ void k_best_colors(const Mode m, const uint8_t* __restrict__ rgb, int n, uint8_t* __restrict__ color, const CcmArg cc)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (cc.active) { color[i] = (uint8_t)best_color_ccm<0>(cc.m, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]); return; }
     color[i] = (uint8_t)((m.color_bits == 3) ? best_color<8>(c_adjust, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2])
                                               : best_color<4>(c_adjust, m, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
 }
@@ -522,9 +531,9 @@ cudaError_t k1_symbols_launch(const uint16_t* d_windows, const uint8_t* d_cooldo
     k_decode_symbols<<<(n + 127) / 128, 128, 0, st>>>(d_windows, d_cooldown, n, d_sym, d_off, d_dist);
     return cudaGetLastError();
 }
-cudaError_t k1_colors_launch(const Mode& m, const uint8_t* d_rgb, int n, uint8_t* d_color, cudaStream_t st)
+cudaError_t k1_colors_launch(const Mode& m, const uint8_t* d_rgb, int n, uint8_t* d_color, const CcmArg& cc, cudaStream_t st)
 {
-    k_best_colors<<<(n + 127) / 128, 128, 0, st>>>(m, d_rgb, n, d_color);
+    k_best_colors<<<(n + 127) / 128, 128, 0, st>>>(m, d_rgb, n, d_color, cc);
     return cudaGetLastError();
 }
 
@@ -537,26 +546,31 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
     if (e != cudaSuccess) return e;
     const int smem_max = (int)sizeof(K1Smem) + 64 * 1024;
-    if ((e = cudaFuncSetAttribute(k1_decode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k1_decode_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k1_decode_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k1_decode_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+#define CB200_K1_ATTR(NC, G, C) \
+    if ((e = cudaFuncSetAttribute(k1_decode_kernel<NC, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
+    CB200_K1_ATTR(4, true, false) CB200_K1_ATTR(4, false, false) CB200_K1_ATTR(8, true, false) CB200_K1_ATTR(8, false, false)
+    CB200_K1_ATTR(4, true, true) CB200_K1_ATTR(4, false, true) CB200_K1_ATTR(8, true, true) CB200_K1_ATTR(8, false, true)
+#undef CB200_K1_ATTR
+    return cudaSuccess;
 }
 
 cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead,
-                      uint8_t* d_cellvals, uint32_t* d_dirty, cudaStream_t stream)
+                      uint8_t* d_cellvals, uint32_t* d_dirty, const CcmArg& cc, cudaStream_t stream)
 {
     const int extra = getenv("CB200_K1_EXTRA_SMEM") ? atoi(getenv("CB200_K1_EXTRA_SMEM")) : 0;   // tuning only: lowers CTAs/SM
     const size_t smem = sizeof(K1Smem) + extra;
     const bool g1024 = m.width == 1024 && m.height == 1024 && m.cells_x == 112 && m.cells_y == 112 && m.corner == 6 &&
                        m.cell_offset == 8 && m.symbol_bits == 4;
+    const bool ccm = cc.active != 0;
+#define CB200_K1_GO(NC, G, C) k1_decode_kernel<NC, G, C><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty, cc)
     if (m.color_bits == 3) {
-        if (g1024) k1_decode_kernel<8, true><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
-        else k1_decode_kernel<8, false><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+        if (g1024) { if (ccm) CB200_K1_GO(8, true, true); else CB200_K1_GO(8, true, false); }
+        else { if (ccm) CB200_K1_GO(8, false, true); else CB200_K1_GO(8, false, false); }
     } else {
-        if (g1024) k1_decode_kernel<4, true><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
-        else k1_decode_kernel<4, false><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty);
+        if (g1024) { if (ccm) CB200_K1_GO(4, true, true); else CB200_K1_GO(4, true, false); }
+        else { if (ccm) CB200_K1_GO(4, false, true); else CB200_K1_GO(4, false, false); }
     }
+#undef CB200_K1_GO
     return cudaGetLastError();
 }
 

@@ -21,6 +21,7 @@
 //   k_flood_colour  colours at the recorded drift-adjusted positions, one thread per cell
 #include "cb200_common.cuh"
 #include "k1x_flood.cuh"
+#include "ccm.cuh"
 
 namespace cb200 {
 
@@ -551,7 +552,7 @@ __device__ uint32_t flood_best_color(const float* adjust_tab, const Mode& m, uin
 // colours at the drift-adjusted positions (CimbReader::read_color, CimbReader.cpp:133-137); one thread per cell
 __global__ void __launch_bounds__(256)
 k_flood_colour(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
-               int base, int cap, const uint32_t* __restrict__ ws_result, uint8_t* __restrict__ cellvals)
+               int base, int cap, const uint32_t* __restrict__ ws_result, uint8_t* __restrict__ cellvals, const CcmArg cc)
 {
     __shared__ float adjust[256];
     adjust[threadIdx.x] = cx_adjust[threadIdx.x];
@@ -575,7 +576,12 @@ k_flood_colour(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
                 const uint8_t* p = frame + ((size_t)(y + r) * W + (size_t)(x + 1)) * 3;
                 for (int c = 0; c < 6; ++c) { R += p[3 * c]; G += p[3 * c + 1]; B += p[3 * c + 2]; }
             }
-            col = flood_best_color(adjust, m, R / 36u, G / 36u, B / 36u);
+            if (cc.active) {
+                float mat[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) mat[q] = cc.per_frame ? cc.per_frame[(size_t)f * 9 + q] : cc.m[q];
+                col = best_color_ccm<0>(mat, m, R / 36u, G / 36u, B / 36u);
+            } else col = flood_best_color(adjust, m, R / 36u, G / 36u, B / 36u);
         }
         cellvals[(size_t)f * ncells + ci] = (uint8_t)(sym | (col << m.symbol_bits));
     }
@@ -678,7 +684,7 @@ static cudaError_t flood_workspace_ensure(const Mode& m, FloodWorkspace& ws, int
 
 cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
                          bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, CellTrace* d_trace,
-                         cudaStream_t st)
+                         const CcmArg& cc, cudaStream_t st)
 {
     if (n_frames <= 0) return cudaSuccess;
     cudaError_t e = flood_workspace_ensure(m, ws, n_frames);
@@ -701,7 +707,7 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);
-        k_flood_colour<<<cgrid, 256, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.result, d_cellvals);
+        k_flood_colour<<<cgrid, 256, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.result, d_cellvals, cc);
     }
     return cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // k1x_flood.cuh -- host-side entry points of the exact flood-walk kernel (k1x_flood.cu)
 #pragma once
 #include "cb200_common.cuh"
+#include "ccm.cuh"
 #include <cstring>
 #include <cstdlib>
 #include <vector>
@@ -36,6 +37,6 @@ void flood_workspace_destroy(FloodWorkspace* ws);
 // CB200_FRAME_INEXACT = needed but skipped (no_fallback)
 cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb, int n_frames, bool no_fallback,
                          bool force_all, bool sharpen, uint8_t* d_cellvals, const uint32_t* d_dirty, uint8_t* d_flags, CellTrace* d_trace,
-                         cudaStream_t st);
+                         const CcmArg& cc, cudaStream_t st);
 
 }  // namespace cb200

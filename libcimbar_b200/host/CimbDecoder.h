@@ -80,6 +80,14 @@ public:
 		return get_best_color(r, g, b, color_mode);
 	}
 
+	// CimbDecoder::update_color_correction / get_ccm (CimbDecoder.cpp:76-85): get_best_color and decode_color use it while set
+	void update_color_correction(const float m9[9])
+	{
+		if (cb200_set_ccm(_ctx, m9) != CB200_OK) throw std::runtime_error(std::string("cb200_set_ccm: ") + cb200_last_error());
+	}
+	void clear_color_correction() { cb200_set_ccm(_ctx, nullptr); }
+	bool get_ccm(float m9[9]) const { return cb200_get_ccm(_ctx, m9) == 1; }
+
 	bool expects_binary_threshold() const { return _ahashThreshold >= 0xFE; }
 	unsigned symbol_bits() const { return _symbolBits; }
 

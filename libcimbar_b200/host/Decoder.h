@@ -10,14 +10,18 @@
 // Differences from the reference, by design of this round:
 //   * frames must be exactly Config::image_size_x() x image_size_y(), RGB8, continuous (the Extractor's output);
 //     a smaller image reproduces the reference's degenerate "reader not good" result (zero-filled streams);
-//   * color_correction 1/2 (CCM) is not implemented on the device yet: pass 0 (the CLI's `--color-correct 0`);
-//     any other value is decoded as 0 and reported through last_warnings().
+//   * color_correction: 0 = off, 1 = simpleColorCorrection on the device (per-frame von Kries matrix, bit-exact).
+//     2 (the per-frame header fit of CimbReader::init_ccm, an OpenCV SVD least-squares fit) is not computed by the
+//     library: the frame is decoded with whatever CCM the decoder currently holds (update_color_correction / load_ccm,
+//     exactly what the reference does for a frame whose header did not decode) and WARN_COLOR_CORRECTION_IGNORED is set
+//     in last_warnings().
 #pragma once
 #include "../../include/cb200.h"
 #include "Config.h"
 #include "streams.h"
 
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -53,6 +57,36 @@ public:
 
 	unsigned last_warnings() const { return _warnings; }
 	unsigned last_frame_flags() const { return _frameFlags; }   // CB200_FRAME_FALLBACK: the exact flood walk was needed
+
+	// The decoder's colour correction matrix: CimbDecoder::update_color_correction / get_ccm (CimbDecoder.cpp:76-85), row-major.
+	void update_color_correction(const float m9[9])
+	{
+		if (cb200_set_ccm(_ctx, m9) != CB200_OK) throw std::runtime_error(std::string("cb200_set_ccm: ") + cb200_last_error());
+	}
+	void clear_color_correction() { cb200_set_ccm(_ctx, nullptr); }   // TestableCimbDecoder: internal_ccm() = color_correction()
+	bool get_ccm(float m9[9]) const { return cb200_get_ccm(_ctx, m9) == 1; }
+	// DecoderPlus::load_ccm / save_ccm (src/lib/encoder/DecoderPlus.h:31-55): the file is the 9 float32 of the matrix
+	bool load_ccm(const std::string& filename)
+	{
+		FILE* f = fopen(filename.c_str(), "rb");
+		if (!f) return false;
+		float m[9];
+		size_t got = fread(m, 1, sizeof(m), f);
+		fclose(f);
+		if (got < sizeof(m)) return false;
+		update_color_correction(m);
+		return true;
+	}
+	bool save_ccm(const std::string& filename) const
+	{
+		float m[9];
+		if (!get_ccm(m)) return false;
+		FILE* f = fopen(filename.c_str(), "wb");
+		if (!f) return false;
+		size_t put = fwrite(m, 1, sizeof(m), f);
+		fclose(f);
+		return put == sizeof(m);
+	}
 
 	template <typename MAT, typename STREAM>
 	unsigned decode(const MAT& img, STREAM& ostream, bool should_preprocess = false, int color_correction = 2)
@@ -93,7 +127,7 @@ protected:
 	template <typename MAT>
 	bool run(const MAT& img, bool should_preprocess, int color_correction, std::vector<uint8_t>& data, std::vector<uint8_t>& ok)
 	{
-		_warnings = (color_correction != 0) ? WARN_COLOR_CORRECTION_IGNORED : 0;
+		_warnings = (color_correction != 0 and color_correction != 1) ? WARN_COLOR_CORRECTION_IGNORED : 0;
 		_frameFlags = 0;
 		if (cimbar::Config::mode_val() != _modeVal)
 			throw std::runtime_error("cb200::Decoder: Config mode changed after construction (one Decoder per mode)");
@@ -125,7 +159,7 @@ protected:
 		}
 		if (img.cols != _info.image_size_x or img.rows != _info.image_size_y or !img.isContinuous())
 			throw std::invalid_argument("cb200::Decoder: frame must be exactly image_size_x x image_size_y, continuous RGB8");
-		uint32_t flags = should_preprocess ? CB200_FLAG_SHARPEN : 0;
+		uint32_t flags = (should_preprocess ? CB200_FLAG_SHARPEN : 0) | (color_correction == 1 ? CB200_FLAG_CC_SIMPLE : 0);
 		uint8_t ff = 0;
 		int rc = _useEcc ? cb200_decode(_ctx, img.data, 1, flags, data.data(), ok.data(), &ff)
 		                 : cb200_decode_raw(_ctx, img.data, 1, flags, data.data(), &ff);

@@ -480,6 +480,74 @@ unsigned cbo_best_color(float r, float g, float b, unsigned num_colors, unsigned
     return best_fit;
 }
 
+/* CimbDecoder's thread_local color_correction (CimbDecoder.cpp:69-85): set by update_color_correction, used by every
+   get_best_color until replaced.  NULL deactivates it (TestableCimbDecoder::internal_ccm() = color_correction()). */
+static __thread float g_ccm[9];
+static __thread int g_ccm_active = 0;
+void cbo_set_ccm(const float* m9)
+{
+    g_ccm_active = m9 != NULL;
+    if (m9) memcpy(g_ccm, m9, sizeof(g_ccm));
+}
+int cbo_get_ccm(float* m9) { if (g_ccm_active && m9) memcpy(m9, g_ccm, sizeof(g_ccm)); return g_ccm_active; }
+
+/* cv::Matx<float,3,3> * cv::Matx<float,3,3> (opencv2/core/matx.hpp Matx_MatMulOp: s = 0; s += a(i,k) * b(k,j), k ascending) */
+static void matx33_mul(const float* a, const float* b, float* out)
+{
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float s = 0;
+            for (int k = 0; k < 3; ++k) s += a[3 * i + k] * b[3 * k + j];
+            out[3 * i + j] = s;
+        }
+}
+/* cv::Matx<float,3,3>::inv() (DECOMP_LU default -> the closed-form 3x3 operator of opencv2/core/operations.hpp:
+   determinant in float, d = 1 / d, cofactors * d) */
+static int matx33_inv(const float* a, float* b)
+{
+    float d = a[0] * (a[4] * a[8] - a[7] * a[5]) - a[1] * (a[3] * a[8] - a[6] * a[5]) + a[2] * (a[3] * a[7] - a[6] * a[4]);
+    if (d == 0) return 0;
+    d = 1 / d;
+    b[0] = (a[4] * a[8] - a[5] * a[7]) * d; b[1] = (a[2] * a[7] - a[1] * a[8]) * d; b[2] = (a[1] * a[5] - a[2] * a[4]) * d;
+    b[3] = (a[5] * a[6] - a[3] * a[8]) * d; b[4] = (a[0] * a[8] - a[2] * a[6]) * d; b[5] = (a[2] * a[3] - a[0] * a[5]) * d;
+    b[6] = (a[3] * a[7] - a[4] * a[6]) * d; b[7] = (a[1] * a[6] - a[0] * a[7]) * d; b[8] = (a[0] * a[4] - a[1] * a[3]) * d;
+    return 1;
+}
+/* color_correction::get_adaptation_matrix<von_kries>(actual, desired), chromatic_adaptation/color_correction.h:12-24,
+   von Kries transform adaptation_transform.h:22-33: T.inv() * diag((T*desired) / (T*actual)) * T */
+void cbo_adaptation_matrix(const float actual[3], const float desired[3], float out[9])
+{
+    static const float T[9] = {0.4002400f, 0.7076000f, -0.0808100f, -0.2263000f, 1.1653200f, 0.0457000f, 0.0000000f, 0.0000000f, 0.9182200f};
+    float m1[3], m2[3], d[9] = {0}, ti[9], tmp[9];
+    for (int i = 0; i < 3; ++i) {
+        float s1 = 0, s2 = 0;
+        for (int k = 0; k < 3; ++k) { s1 += T[3 * i + k] * actual[k]; s2 += T[3 * i + k] * desired[k]; }
+        m1[i] = s1; m2[i] = s2;
+    }
+    for (int i = 0; i < 3; ++i) d[4 * i] = m2[i] / m1[i];
+    if (!matx33_inv(T, ti)) memset(ti, 0, sizeof(ti));
+    matx33_mul(ti, d, tmp);
+    matx33_mul(tmp, T, out);
+}
+/* calculateWhite (dark) + simpleColorCorrection, CimbReader.cpp:55-93: max over three anchor 4x4 means, floor (1,1,1) */
+void cbo_simple_ccm(const cbo_mode* m, const uint8_t* rgb, int w, int h, float out[9])
+{
+    int padding = ((w - (int)m->image_size_x) < (h - (int)m->image_size_y) ? (w - (int)m->image_size_x) : (h - (int)m->image_size_y)) / 2;
+    unsigned tl = 30 + (unsigned)padding - 2;                                    /* Config::anchor_size() == 30 */
+    unsigned right = m->image_size_x + (unsigned)padding - 30 - 2, bottom = m->image_size_y + (unsigned)padding - 30 - 2;
+    unsigned ax[3] = {tl, tl, right}, ay[3] = {tl, bottom, tl};
+    float white[3] = {1, 1, 1};
+    for (int a = 0; a < 3; ++a) {
+        double sum[3] = {0, 0, 0};
+        for (unsigned y = 0; y < 4; ++y)
+            for (unsigned x = 0; x < 4; ++x)
+                for (int c = 0; c < 3; ++c) sum[c] += rgb[((size_t)(ay[a] + y) * (size_t)w + (ax[a] + x)) * 3 + c];
+        for (int c = 0; c < 3; ++c) { float v = (float)(sum[c] / 16.0); if (v > white[c]) white[c] = v; }   /* cv::mean -> double */
+    }
+    const float desired[3] = {255.0f, 255.0f, 255.0f};
+    cbo_adaptation_matrix(white, desired, out);
+}
+
 static unsigned decode_color_at(const cbo_mode* m, const uint8_t* rgb, int w, int x, int y)
 {
     /* CimbReader::read_color (CimbReader.cpp:133-137) -> CimbDecoder::decode_color (:211-217) */
@@ -487,7 +555,7 @@ static unsigned decode_color_at(const cbo_mode* m, const uint8_t* rgb, int w, in
     if (num_colors <= 1) return 0;
     uint8_t avg[3];
     cbo_avg_color(rgb, w, x, y, (int)m->cell_size, avg);
-    return cbo_best_color((float)avg[0], (float)avg[1], (float)avg[2], num_colors, m->color_mode, NULL);
+    return cbo_best_color((float)avg[0], (float)avg[1], (float)avg[2], num_colors, m->color_mode, g_ccm_active ? g_ccm : NULL);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -663,7 +731,6 @@ int cbo_flood_walk_synthetic(const cbo_mode* m, unsigned seed, unsigned noise, u
 int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen,
                    int color_correction, uint8_t* out, cbo_cell* cells)
 {
-    (void)color_correction;
     static const int DRIFT_PAIRS[9][2] = {{-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {0, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}}; /* CellDrift.h:13-15 */
     unsigned bpc = m->symbol_bits + m->color_bits;
     unsigned cap_all = cbo_capacity(m, bpc);
@@ -685,6 +752,11 @@ int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int need
     uint8_t* col_buf = m->legacy_mode ? out : out + cap_sym;
     unsigned sym_stride = m->legacy_mode ? bpc : m->symbol_bits;
 
+    if (good && color_correction == 1) {   /* CimbReader.cpp:124-125: the decoder's CCM is replaced before anything is read */
+        float ccm[9];
+        cbo_simple_ccm(m, rgb, w, h, ccm);
+        cbo_set_ccm(ccm);
+    }
     if (good) {
         int padding = ((w - (int)m->image_size_x) < (h - (int)m->image_size_y) ? (w - (int)m->image_size_x) : (h - (int)m->image_size_y)) / 2;
         cbo_cell_positions(m, padding, xs, ys);

@@ -107,7 +107,13 @@ void cbo_palette(unsigned index, unsigned num_colors, unsigned color_mode, uint8
    cells (optional) gets ncells entries indexed by cell index.  Returns bytes written
    (capacity), also when the image is too small (zero-filled, CimbReader.cpp:119,141). */
 int  cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen,
-                    int color_correction /*0 only*/, uint8_t* out, cbo_cell* cells);
+                    int color_correction /* 0, or 1 = simpleColorCorrection; 2 (header fit) is not restated */, uint8_t* out, cbo_cell* cells);
+/* the decoder's thread-local CCM (CimbDecoder::update_color_correction, CimbDecoder.cpp:82-85); NULL = inactive */
+void cbo_set_ccm(const float* m9);
+int cbo_get_ccm(float* m9);
+/* color_correction::get_adaptation_matrix<von_kries> (color_correction.h:12-24) and simpleColorCorrection (CimbReader.cpp:55-93) */
+void cbo_adaptation_matrix(const float actual[3], const float desired[3], float out[9]);
+void cbo_simple_ccm(const cbo_mode* m, const uint8_t* rgb, int w, int h, float out[9]);
 
 /* test hooks for the flood-walk / heap emulation (compared with the reference's FloodDecodePositions in oracle/_ref) */
 void cbo_synth_result(unsigned seed, unsigned i, int dx, int dy, unsigned cooldown, unsigned noise, unsigned* drift_offset, unsigned* dist);

@@ -15,7 +15,7 @@ REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 SAMPLES = [
-    "b/tr_0.png", "b/tr_1.png", "b/tr_2.png", "b/tr_3.png", "b/ex2434.jpg",
+    "b/tr_0.png", "b/tr_1.png", "b/tr_2.png", "b/tr_3.png", "b/ex2434.jpg", "b/ex380.jpg",
     "6bit/4color_ecc30_fountain_0.png", "6bit/4_30_f0_627_extract.jpg", "mycell.png",
 ]
 
@@ -27,6 +27,25 @@ GOLDENS = [  # (sample, mode, ecc, bytes, sha256, source)
     ("6bit/4_30_f0_627_extract.jpg", 4, False, 9300, "2040c157884c476def842f7854621a7655182e5f11a34ade563616d93cb93455", "src/lib/encoder/test/DecoderTest.cpp:92-106"),
     ("b/scan2434.jpg", 68, False, 9300, "ccb39ac3511a8974a8e98d3ea321d576d974d28f0b9373fc611ce6a4c83b561c", "src/lib/encoder/test/DecoderTest.cpp:50-62"),
 ]
+
+
+# colour-correction goldens: the CCM the reference's tests print (operator<< of cv::Matx<float>, "%.8g") and the colours of
+# the first six cells in flood order with that CCM active
+CCM_GOLDENS = [
+    {"sample": "b/ex2434.jpg", "mode": 68, "source": "src/lib/cimb_translator/test/CimbReaderTest.cpp:181-214",
+     "matrix": [[2.3991191, -0.41846275, -0.54654282], [-0.42976046, 2.632102, -0.76466882], [-0.54299992, -0.20199311, 2.2753253]],
+     "first_colors": [0, 1, 1, 2, 2, 2]},
+    {"sample": "b/ex2434.jpg", "mode": 68, "source": "src/lib/cimb_translator/test/CimbReaderTest.cpp:216-237 (CCM disabled)",
+     "matrix": None, "first_colors": [0, 1, 1, 2, 2, 2]},
+    {"sample": "b/ex380.jpg", "mode": 68, "source": "src/lib/cimb_translator/test/CimbReaderTest.cpp:239-272",
+     "matrix": [[1.6250746, 0.0024788622, -0.45772526], [-0.29126319, 2.2922182, -0.67037439], [-1.2192062, -2.7447209, 5.0476217]],
+     "first_colors": [0, 1, 1, 2, 2, 2]},
+]
+# color_correctionTest/testTransform (src/lib/chromatic_adaptation/test/color_correctionTest.cpp:14-30)
+ADAPTATION_GOLDEN = {"actual": [192, 255, 255], "desired": [255, 255, 255],
+                     "matrix_str": "[1.0655777, 0.2109226, -0.013239831;\n 0.023168325, 0.98723376, -0.0046780901;\n 0, 0, 1]",
+                     "transform_in": [180, 98, 255], "transform_out": [209.09822971, 99.72629027, 255.0],
+                     "source": "src/lib/chromatic_adaptation/test/color_correctionTest.cpp:14-30"}
 
 
 def load_rgb(path):
@@ -41,7 +60,8 @@ def sha(a):
 def main():
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference")
-    manifest = {"cv2": cv2.__version__, "samples": {}, "goldens": [], "cv_pins": {}}
+    manifest = {"cv2": cv2.__version__, "samples": {}, "goldens": [], "cv_pins": {}, "ccm_goldens": CCM_GOLDENS,
+                "adaptation_golden": ADAPTATION_GOLDEN}
     for s in SAMPLES:
         dst = os.path.join(HERE, s.replace("/", "__"))
         shutil.copyfile(os.path.join(REF, "samples", s), dst)

@@ -93,6 +93,10 @@ class Oracle:
         L.cbo_md_encode_id.restype = C.c_uint
         L.cbo_bench_decode.argtypes = [C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.cbo_bench_decode.restype = C.c_double
+        L.cbo_set_ccm.argtypes = [C.POINTER(C.c_float)]
+        L.cbo_get_ccm.argtypes = [C.POINTER(C.c_float)]
+        L.cbo_adaptation_matrix.argtypes = [C.POINTER(C.c_float)] * 3
+        L.cbo_simple_ccm.argtypes = [C.POINTER(Mode), u8p, C.c_int, C.c_int, C.POINTER(C.c_float)]
 
     def mode(self, mode_val=68):
         m = Mode()
@@ -102,13 +106,33 @@ class Oracle:
     def capacity(self, m, bits=0):
         return self.lib.cbo_capacity(C.byref(m), bits)
 
-    def decode_raw(self, m, rgb, sharpen=False, want_cells=False):
+    def decode_raw(self, m, rgb, sharpen=False, want_cells=False, color_correction=0):
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
         h, w = rgb.shape[:2]
         out = np.zeros(self.capacity(m), dtype=np.uint8)
         cells = np.zeros(m.total_cells, dtype=CELL_DTYPE) if want_cells else None
-        self.lib.cbo_decode_raw(C.byref(m), _ptr(rgb), w, h, int(sharpen), 0, _ptr(out), cells.ctypes.data if want_cells else None)
+        self.lib.cbo_decode_raw(C.byref(m), _ptr(rgb), w, h, int(sharpen), int(color_correction), _ptr(out),
+                                cells.ctypes.data if want_cells else None)
         return (out, cells) if want_cells else out
+
+    def set_ccm(self, m9):
+        """CimbDecoder::update_color_correction for the calling thread's oracle state; None deactivates it"""
+        if m9 is None:
+            self.lib.cbo_set_ccm(None)
+        else:
+            a = np.ascontiguousarray(m9, dtype=np.float32).reshape(9)
+            self.lib.cbo_set_ccm(_ptr(a, C.c_float))
+
+    def adaptation_matrix(self, actual, desired):
+        a, d, o = (np.asarray(actual, np.float32), np.asarray(desired, np.float32), np.zeros(9, np.float32))
+        self.lib.cbo_adaptation_matrix(_ptr(a, C.c_float), _ptr(d, C.c_float), _ptr(o, C.c_float))
+        return o.reshape(3, 3)
+
+    def simple_ccm(self, m, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        o = np.zeros(9, np.float32)
+        self.lib.cbo_simple_ccm(C.byref(m), _ptr(rgb), rgb.shape[1], rgb.shape[0], _ptr(o, C.c_float))
+        return o.reshape(3, 3)
 
     def decode(self, m, rgb, use_ecc=True, sharpen=False):
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)

@@ -458,3 +458,90 @@ def test_fountain_file_round_trip_with_frame_loss(cb):
     assert np.array_equal(sink.file(fid), data)
     sink.close()
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ colour correction (CCM)
+def _tint(frames, gains):
+    """a coloured cast: per-channel gain, the kind of error a CCM exists to undo"""
+    out = frames.astype(np.float32) * np.asarray(gains, np.float32)
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("idx", [0, 2])
+def test_ccm_reference_goldens_on_gpu(cb, idx):
+    # CimbReaderTest.cpp:181-214 / :239-272: with the printed CCM active the first six reads give colours 0,1,1,2,2,2;
+    # and every cell of the camera frame must match the oracle under the same CCM
+    g = manifest()["ccm_goldens"][idx]
+    ctx = cb.Context(g["mode"], max_frames=1)
+    rgb = load_sample(g["sample"])
+    ctx.set_ccm(g["matrix"])
+    assert np.array_equal(ctx.get_ccm(), np.asarray(g["matrix"], np.float32))
+    cells, trace = ctx.decode_cells(rgb)
+    m = ORA.mode(g["mode"])
+    order = np.argsort(trace[0]["order"])
+    assert (cells[0][order[:6]] >> m.symbol_bits).tolist() == g["first_colors"]
+    raw, ff = ctx.decode_raw(rgb)
+    ORA.set_ccm(g["matrix"])
+    try:
+        want = ORA.decode_raw(m, rgb)
+    finally:
+        ORA.set_ccm(None)
+    assert np.array_equal(raw[0], want)
+    ctx.set_ccm(None)
+    assert ctx.get_ccm() is None
+    raw0, _ = ctx.decode_raw(rgb)
+    assert np.array_equal(raw0[0], ORA.decode_raw(m, rgb))
+    if idx == 2:          # ex380 is the reference's "VeryNecessary" case; on ex2434 the CCM changes no colour
+        assert not np.array_equal(raw0[0], raw[0])
+
+
+@pytest.mark.parametrize("mode_val", [68, 8, 67])
+def test_ccm_on_clean_frames_goes_through_k1(cb, mode_val):
+    # tinted synthetic frames stay on the drift-0 kernel (K1's CCM variant); the matrix is an arbitrary strong one
+    m, payloads, frames = synth_frames(mode_val, 3, seed=41)
+    frames = _tint(frames, (0.62, 0.95, 0.8))
+    mat = np.array([[1.61, 0.02, -0.11], [-0.07, 1.05, 0.03], [-0.2, -0.15, 1.45]], np.float32)
+    ctx = cb.Context(mode_val, max_frames=3)
+    ctx.set_ccm(mat)
+    raw, ff = ctx.decode_raw(frames)
+    assert ff.tolist() == [0, 0, 0]
+    ORA.set_ccm(mat)
+    try:
+        for f in range(3):
+            assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f])), f
+    finally:
+        ORA.set_ccm(None)
+    # single-value entry point under the same CCM (CimbDecoder::get_best_color with an active CCM)
+    rng = np.random.default_rng(5)
+    means = rng.integers(0, 256, (4096, 3), dtype=np.uint8)
+    got = ctx.best_colors(means)
+    cm = (C.c_float * 9)(*mat.reshape(9).tolist())
+    want = [ORA.lib.cbo_best_color(float(r), float(g), float(b), 1 << m.color_bits, m.color_mode, cm) for r, g, b in means]
+    assert got.tolist() == want
+
+
+def test_simple_color_correction_matches_oracle(cb):
+    # color_correction == 1 (simpleColorCorrection, CimbReader.cpp:55-93): per-frame von Kries matrix from the anchors
+    m, payloads, frames = synth_frames(68, 4, seed=43)
+    frames[1] = _tint(frames[1:2], (0.7, 1.0, 0.9))[0]
+    frames[2] = _tint(frames[2:3], (1.0, 0.55, 0.8))[0]
+    frames[3] = load_sample("b/ex380.jpg")                      # camera frame: exact walk + CCM
+    ctx = cb.Context(68, max_frames=4)
+    raw, ff = ctx.decode_raw(frames, flags=cb.FLAG_CC_SIMPLE)
+    assert ff.tolist()[:3] == [0, 0, 0] and ff[3] == cb.FRAME_FALLBACK
+    try:
+        for f in range(4):
+            assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f], color_correction=1)), f
+        # the decoder keeps the last frame's matrix (CimbDecoder.cpp:82-85), bit for bit
+        assert np.array_equal(ctx.get_ccm(), ORA.simple_ccm(m, frames[3]))
+        # ... and uses it for the next call without the flag, like a reference decoder whose CCM was set earlier
+        raw2, _ = ctx.decode_raw(frames[:2])
+        ORA.set_ccm(ORA.simple_ccm(m, frames[3]))
+        for f in range(2):
+            assert np.array_equal(raw2[f], ORA.decode_raw(m, frames[f])), f
+    finally:
+        ORA.set_ccm(None)
+    # full decode with RS under color_correction == 1 still returns the payload of the tinted frames
+    ctx2 = cb.Context(68, max_frames=4)
+    data, ok, _ = ctx2.decode(frames[:3], flags=cb.FLAG_CC_SIMPLE)
+    assert ok.all() and np.array_equal(data, payloads[:3])

@@ -123,3 +123,47 @@ def test_preprocess_matches_cv2():
         thr7 = cv2.adaptiveThreshold(sharp, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, 7, 0)
         assert sha(thr7) == pins["thr7_sharp"]
         assert np.array_equal(np.unpackbits(ORA.preprocess(rgb, sharpen=True)).reshape(h, w) * 255, thr7)
+
+
+# ---------------------------------------------------------------------------------------------- colour correction
+def _fmt_matx(mat):
+    """operator<<(std::ostream&, cv::Matx<float,3,3>): "%.8g" elements, ", " / ";\n " separators"""
+    return "[" + ";\n ".join(", ".join("%.8g" % float(x) for x in row) for row in mat) + "]"
+
+
+def test_adaptation_matrix_matches_reference_string():
+    g = manifest()["adaptation_golden"]          # color_correctionTest.cpp:14-30
+    mat = ORA.adaptation_matrix(g["actual"], g["desired"])
+    assert _fmt_matx(mat) == g["matrix_str"]
+    r, gg, b = (np.float32(x) for x in g["transform_in"])
+    out = [np.float32(np.float32(np.float32(mat[i, 0] * r) + np.float32(mat[i, 1] * gg)) + np.float32(mat[i, 2] * b)) for i in range(3)]
+    assert np.allclose(out, g["transform_out"], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("idx", range(3))
+def test_ccm_goldens_first_colors(idx):
+    g = manifest()["ccm_goldens"][idx]           # CimbReaderTest.cpp:181-272: colours of the first six reads with that CCM
+    m = ORA.mode(g["mode"])
+    rgb = load_sample(g["sample"])
+    ORA.set_ccm(g["matrix"])
+    try:
+        _, cells = ORA.decode_raw(m, rgb, want_cells=True)
+    finally:
+        ORA.set_ccm(None)
+    order = np.argsort(cells["order"])
+    assert cells["color"][order[:6]].tolist() == g["first_colors"]
+
+
+def test_ccm_is_very_necessary_for_ex380():
+    """the reference names the ex380 case "VeryNecessary": without the CCM a visible share of the colours changes"""
+    g = manifest()["ccm_goldens"][2]
+    m = ORA.mode(68)
+    rgb = load_sample(g["sample"])
+    _, plain = ORA.decode_raw(m, rgb, want_cells=True)
+    ORA.set_ccm(g["matrix"])
+    try:
+        _, fixed = ORA.decode_raw(m, rgb, want_cells=True)
+    finally:
+        ORA.set_ccm(None)
+    assert np.array_equal(plain["symbol"], fixed["symbol"])
+    assert (plain["color"] != fixed["color"]).mean() > 0.02
