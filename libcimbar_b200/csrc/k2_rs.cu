@@ -211,30 +211,22 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
 #pragma unroll
         for (int q = 0; q < T; ++q) {
             // Horner with every value kept as a table-row byte offset: off' = mt[off][lane] ^ enc_off -- per byte one address
-            // add, one LDS and one XOR (32-bit shared addresses, so no generic-pointer arithmetic in the chain).  The chain is
-            // bound by the shared-memory round trip, so the block is cut in two at byte h and both halves run interleaved:
-            // r(c) = r_hi(c) * c^(blk-h) + r_lo(c), with the one multiplication done through log/exp at the end.
+            // add, one LDS and one XOR (32-bit shared addresses, so no generic-pointer arithmetic in the chain).  The floor
+            // is shared-memory bandwidth: one 32-lane table read per block byte (splitting the chain in two interleaved halves
+            // was measured and does not help).
             const uint32_t colb = (uint32_t)__cvta_generic_to_shared(mt) + 4u * (uint32_t)(lane + 32 * q);
-            const int h = ((blk / 2 + 3) & ~3) < blk ? ((blk / 2 + 3) & ~3) : blk, common = (blk - h) & ~3;
-            uint32_t off = 0, off2 = 0;
+            uint32_t off = 0;
             const uint4* e4 = reinterpret_cast<const uint4*>(w.encs);
-            const uint4* f4 = reinterpret_cast<const uint4*>(w.encs + h);
             int i = 0;
-            for (; i < common; i += 4) {
-                const uint4 e = e4[i >> 2], g = f4[i >> 2];
-                off = lds_u32(colb + off) ^ e.x; off2 = lds_u32(colb + off2) ^ g.x;
-                off = lds_u32(colb + off) ^ e.y; off2 = lds_u32(colb + off2) ^ g.y;
-                off = lds_u32(colb + off) ^ e.z; off2 = lds_u32(colb + off2) ^ g.z;
-                off = lds_u32(colb + off) ^ e.w; off2 = lds_u32(colb + off2) ^ g.w;
+#pragma unroll 2
+            for (; i + 4 <= blk; i += 4) {
+                const uint4 e = e4[i >> 2];
+                off = lds_u32(colb + off) ^ e.x;
+                off = lds_u32(colb + off) ^ e.y;
+                off = lds_u32(colb + off) ^ e.z;
+                off = lds_u32(colb + off) ^ e.w;
             }
-            for (int i1 = i; i1 < h; ++i1) off = lds_u32(colb + off) ^ w.encs[i1];
-            for (int i2 = h + i; i2 < blk; ++i2) off2 = lds_u32(colb + off2) ^ w.encs[i2];
-            {
-                const uint32_t hi = off / (128u * T);
-                const uint32_t lg = ((uint32_t)(lane + 32 * q + 1) * (uint32_t)(blk - h)) % 255u;     // log of c^(blk-h), c = alpha^(j+1)
-                const uint32_t shifted = hi ? (uint32_t)s.exp[(uint32_t)s.log[hi] + lg] : 0u;
-                off = off2 ^ (shifted * (128u * T));
-            }
+            for (; i < blk; ++i) off = lds_u32(colb + off) ^ w.encs[i];
             const uint32_t acc = off / (128u * T);
             const int j = lane + 32 * q;
             if (j < md) { w.synd[j] = (uint8_t)acc; nz |= acc; }
