@@ -8,6 +8,7 @@
  */
 #include "cimbar_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -548,6 +549,219 @@ void cbo_simple_ccm(const cbo_mode* m, const uint8_t* rgb, int w, int h, float o
     cbo_adaptation_matrix(white, desired, out);
 }
 
+/* color_correction::get_moore_penrose_lsm(actual, desired), color_correction.h:26-39: x = desired^T, y = actual^T,
+   z = cv::invert(y, DECOMP_SVD), result = x * z.  rows = N (5 or 9), row-major N x 3 floats.
+   cv::invert(DECOMP_SVD) on the 3 x N float matrix y (OpenCV modules/core/src/lapack.cpp, the build without LAPACK that the
+   reference's printed goldens come from): SVD::compute -> _SVDcompute (m < n: works on the rows of y as they are) ->
+   JacobiSVDImpl_<float> (one-sided Hestenes rotations, dot products and norms in double, c/s and the rotated values in
+   float, eps = 2 FLT_EPSILON, at most max(m, 30) sweeps, singular values sorted descending, rows normalised by 1 / w),
+   then SVD::backSubst -> SVBkSbImpl_ (x += v_i * (u_i / w_i)^T, products and sums in double, stored as float after every
+   i), then the 3 x N by N x 3 product through cv::gemm (double accumulators).  Reproduces the matrix strings of
+   color_correctionTest.cpp:32-84 digit for digit (tests/test_oracle_goldens.py). */
+static void jacobi_svd_f32(float* At, int astep, float* Wout, float* Vt, int m, int n)
+{
+    double W[16];
+    const float eps = FLT_EPSILON * 2;
+    for (int i = 0; i < n; ++i) {
+        double sd = 0;
+        for (int k = 0; k < m; ++k) { float t = At[i * astep + k]; sd += (double)t * t; }
+        W[i] = sd;
+        for (int k = 0; k < n; ++k) Vt[i * n + k] = 0;
+        Vt[i * n + i] = 1;
+    }
+    int max_iter = m > 30 ? m : 30;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        int changed = 0;
+        for (int i = 0; i < n - 1; ++i)
+            for (int j = i + 1; j < n; ++j) {
+                float *Ai = At + i * astep, *Aj = At + j * astep;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < m; ++k) p += (double)Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt((double)a * b)) continue;
+                p *= 2;
+                double beta = a - b, gamma = hypot((double)p, beta);
+                float c, sn;
+                if (beta < 0) { double delta = (gamma - beta) * 0.5; sn = (float)sqrt(delta / gamma); c = (float)(p / (gamma * sn * 2)); }
+                else { c = (float)sqrt((gamma + beta) / (gamma * 2)); sn = (float)(p / (gamma * c * 2)); }
+                a = b = 0;
+                for (int k = 0; k < m; ++k) {
+                    float t0 = c * Ai[k] + sn * Aj[k];
+                    float t1 = -sn * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += (double)t0 * t0; b += (double)t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = 1;
+                float *Vi = Vt + i * n, *Vj = Vt + j * n;
+                for (int k = 0; k < n; ++k) {
+                    float t0 = c * Vi[k] + sn * Vj[k];
+                    float t1 = -sn * Vi[k] + c * Vj[k];
+                    Vi[k] = t0; Vj[k] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < n; ++i) {
+        double sd = 0;
+        for (int k = 0; k < m; ++k) { float t = At[i * astep + k]; sd += (double)t * t; }
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < n - 1; ++i) {
+        int j = i;
+        for (int k = i + 1; k < n; ++k) if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double tw = W[i]; W[i] = W[j]; W[j] = tw;
+            for (int k = 0; k < m; ++k) { float t = At[i * astep + k]; At[i * astep + k] = At[j * astep + k]; At[j * astep + k] = t; }
+            for (int k = 0; k < n; ++k) { float t = Vt[i * n + k]; Vt[i * n + k] = Vt[j * n + k]; Vt[j * n + k] = t; }
+        }
+    }
+    for (int i = 0; i < n; ++i) Wout[i] = (float)W[i];
+    for (int i = 0; i < n; ++i) {
+        /* (singular values <= FLT_MIN would get a random unit vector from cv::RNG(0x12345678): cannot happen for 3 colour
+           columns that span the colour space; treated as zero here) */
+        double sd = W[i];
+        float s = (float)(sd > (double)FLT_MIN ? 1 / sd : 0.);
+        for (int k = 0; k < m; ++k) At[i * astep + k] *= s;
+    }
+}
+int cbo_moore_penrose_lsm(const float* actual, const float* desired, int rows, float out[9])
+{
+    if (rows < 3 || rows > 16) return 0;
+    const int N = rows;
+    float At[3 * 16], Vt[9], W[3];
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < N; ++k) At[r * 16 + k] = actual[k * 3 + r];    /* y = actual^T, 3 x N */
+    jacobi_svd_f32(At, 16, W, Vt, N, 3);
+    /* SVD of y: u = Vt^T (3 x 3), vt = At (3 x N).  backSubst with no rhs: z (N x 3) = sum_i vt_i^T * (u column i / w_i) */
+    float z[16 * 3];
+    for (int i = 0; i < N * 3; ++i) z[i] = 0;
+    double threshold = 0;
+    for (int i = 0; i < 3; ++i) threshold += W[i];
+    threshold *= (float)(FLT_EPSILON * 2);
+    for (int i = 0; i < 3; ++i) {
+        double wi = W[i];
+        if (fabs(wi) <= threshold) continue;
+        wi = 1 / wi;
+        double buffer[3];
+        for (int j = 0; j < 3; ++j) buffer[j] = Vt[i * 3 + j] * wi;         /* u(j, i) = Vt(i, j) */
+        for (int r = 0; r < N; ++r) {
+            float sv = At[i * 16 + r];
+            for (int j = 0; j < 3; ++j) z[r * 3 + j] = (float)(z[r * 3 + j] + sv * buffer[j]);
+        }
+    }
+    for (int i = 0; i < 3; ++i)                                             /* x (3 x N) * z (N x 3), x = desired^T */
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0;
+            for (int k = 0; k < N; ++k) acc += (double)desired[k * 3 + i] * z[k * 3 + j];
+            out[i * 3 + j] = (float)acc;
+        }
+    return 1;
+}
+
+/* What the aligned_stream callbacks leave in CimbReader::_fountainColorHeader after the symbol stream
+   (Decoder.h:171-189, aligned_stream.h:39-116, CimbReader::update_metadata CimbReader.cpp:269-280): the first six bytes
+   of the first good chunk, block id incremented once per chunk event from that chunk on (skipping the "radioactive" id).
+   blocks/ok = the symbol stream's RS results.  Returns 0 when no header was seen (id() == 0). */
+static void md_event(uint8_t hdr[6], int* have, unsigned* radioactive, const uint8_t* buf, unsigned len, unsigned chunk_size)
+{   /* CimbReader::update_metadata(buff, len, chunk_size), CimbReader.cpp:269-280 */
+    int id_zero = (hdr[0] | hdr[1] | hdr[2] | hdr[3]) == 0;
+    if (len == 0 && id_zero) return;
+    if (id_zero && buf) { memcpy(hdr, buf, len > 6 ? 6 : len); *have = 1; }
+    if (*radioactive == 0) { unsigned fs = cbo_md_file_size(hdr); *radioactive = (fs % chunk_size == 0) ? 0xFFFFFFFFu : fs / chunk_size; }
+    unsigned next = cbo_md_block_id(hdr) + 1;
+    if (next == *radioactive) next += 1;
+    hdr[4] = (uint8_t)((next >> 8) & 0xFF); hdr[5] = (uint8_t)(next & 0xFF);
+}
+
+int cbo_header_after_symbols(const uint8_t* blocks, const uint8_t* ok, unsigned nblocks, unsigned msg_len, unsigned chunk_size,
+                             uint8_t hdr[6], unsigned* radioactive_out)
+{
+    uint8_t* buffer = (uint8_t*)calloc(chunk_size, 1);
+    unsigned offset = 0, radioactive = 0; int bad_chunk = 0, have = 0;
+    memset(hdr, 0, 6);
+    for (unsigned b = 0; b < nblocks; ++b) {
+        const uint8_t* data = blocks + (size_t)b * msg_len;
+        if (!ok[b]) { bad_chunk = 1; offset = (offset + msg_len) % chunk_size; continue; }
+        unsigned length = msg_len;
+        while (length > 0) {
+            unsigned work = length + offset;
+            if (work >= chunk_size) {
+                unsigned write_len = chunk_size - offset;
+                if (bad_chunk) { bad_chunk = 0; offset = 0; md_event(hdr, &have, &radioactive, NULL, 0, chunk_size); }
+                else { memcpy(buffer + offset, data, write_len); offset += write_len; md_event(hdr, &have, &radioactive, buffer, offset, chunk_size); offset = 0; }
+                length -= write_len; data += write_len;
+                continue;
+            }
+            memcpy(buffer + offset, data, length);
+            offset += length; length = 0;
+        }
+    }
+    free(buffer);
+    if (radioactive_out) *radioactive_out = radioactive;
+    return have && (hdr[0] | hdr[1] | hdr[2] | hdr[3]) != 0;
+}
+
+/* CimbReader::init_ccm, CimbReader.cpp:169-267 (color_correction == 2): colours the header predicts at the head of every
+   colour-stream chunk -> per-colour average of the observed cell means -> + anchor white -> least-squares 3x3 fit.
+   hdr/radioactive as left by the symbol pass.  Returns 1 and fills out when a matrix results, 0 when the reference bails. */
+int cbo_init_ccm(const cbo_mode* m, const uint8_t* rgb, int w, int h, const uint8_t hdr_in[6], unsigned radioactive, float out[9])
+{
+    if ((hdr_in[0] | hdr_in[1] | hdr_in[2] | hdr_in[3]) == 0) return 0;
+    unsigned ncells = m->total_cells, color_bits = m->color_bits;
+    if (color_bits == 0) return 0;
+    int padding = ((w - (int)m->image_size_x) < (h - (int)m->image_size_y) ? (w - (int)m->image_size_x) : (h - (int)m->image_size_y)) / 2;
+    int* xs = (int*)malloc(sizeof(int) * ncells); int* ys = (int*)malloc(sizeof(int) * ncells);
+    unsigned* idx = (unsigned*)malloc(sizeof(unsigned) * ncells);
+    cbo_cell_positions(m, padding, xs, ys);
+    cbo_interleave_indices(ncells, m->interleave_blocks, m->interleave_partitions, idx);
+    unsigned fountain_blocks = m->chunks_per_frame;
+    unsigned end = cbo_capacity(m, color_bits) * 8 / color_bits;
+    unsigned interval = cbo_capacity(m, m->symbol_bits + color_bits) * 8 / fountain_blocks / color_bits;
+    unsigned header_len = 6 * 8 / color_bits;
+    uint8_t hdr[6]; memcpy(hdr, hdr_in, 6);
+    /* std::unordered_map<uint16_t, ...> of libstdc++: 13 buckets after the first insert, identity hash, every key of 0..7 in
+       its own bucket, a new node goes to the front of the list -> iteration runs in reverse order of first appearance */
+    unsigned order[8], norder = 0, cnt[8] = {0}, sr[8] = {0}, sg[8] = {0}, sb[8] = {0}; int seen[8] = {0};
+    for (unsigned block = 0; block < end; block += interval) {
+        for (unsigned s = block, i = 0; s < block + header_len; ++s, i += color_bits) {
+            unsigned expected = 0;
+            for (unsigned k = 0; k < color_bits; ++k) expected = (expected << 1) | ((hdr[(i + k) >> 3] >> (7 - ((i + k) & 7))) & 1u);
+            unsigned cell = idx[s];
+            uint8_t avg[3];
+            cbo_avg_color(rgb, w, xs[cell], ys[cell], (int)m->cell_size, avg);
+            if (!seen[expected]) { seen[expected] = 1; order[norder++] = expected; }
+            cnt[expected] += 1; sr[expected] += avg[0]; sg[expected] += avg[1]; sb[expected] += avg[2];
+        }
+        unsigned next = cbo_md_block_id(hdr) + 1; if (next == radioactive) next += 1;
+        hdr[4] = (uint8_t)((next >> 8) & 0xFF); hdr[5] = (uint8_t)(next & 0xFF);
+    }
+    free(xs); free(ys); free(idx);
+    float actual[16 * 3], desired[16 * 3]; int rows = 0;
+    for (int k = (int)norder - 1; k >= 0; --k) {
+        unsigned c = order[k];
+        if (cnt[c] == 0) continue;
+        actual[rows * 3] = (float)(sr[c] / cnt[c]); actual[rows * 3 + 1] = (float)(sg[c] / cnt[c]); actual[rows * 3 + 2] = (float)(sb[c] / cnt[c]);
+        uint8_t pal[3]; cbo_palette(c, 1u << color_bits, m->color_mode, pal);
+        desired[rows * 3] = pal[0]; desired[rows * 3 + 1] = pal[1]; desired[rows * 3 + 2] = pal[2];
+        ++rows;
+    }
+    if (rows < 4) return 0;
+    {   /* calculateWhite, dark (CimbReader.cpp:55-72) */
+        unsigned tl = 30 + (unsigned)padding - 2, right = m->image_size_x + (unsigned)padding - 30 - 2, bottom = m->image_size_y + (unsigned)padding - 30 - 2;
+        unsigned ax[3] = {tl, tl, right}, ay[3] = {tl, bottom, tl};
+        float white[3] = {1, 1, 1};
+        for (int a = 0; a < 3; ++a) {
+            double sum[3] = {0, 0, 0};
+            for (unsigned y = 0; y < 4; ++y) for (unsigned x = 0; x < 4; ++x) for (int c = 0; c < 3; ++c)
+                sum[c] += rgb[((size_t)(ay[a] + y) * (size_t)w + (ax[a] + x)) * 3 + c];
+            for (int c = 0; c < 3; ++c) { float v = (float)(sum[c] / 16.0); if (v > white[c]) white[c] = v; }
+        }
+        actual[rows * 3] = white[0]; actual[rows * 3 + 1] = white[1]; actual[rows * 3 + 2] = white[2];
+        desired[rows * 3] = desired[rows * 3 + 1] = desired[rows * 3 + 2] = 255.0f;
+        ++rows;
+    }
+    return cbo_moore_penrose_lsm(actual, desired, rows, out);
+}
+
 static unsigned decode_color_at(const cbo_mode* m, const uint8_t* rgb, int w, int x, int y)
 {
     /* CimbReader::read_color (CimbReader.cpp:133-137) -> CimbDecoder::decode_color (:211-217) */
@@ -728,6 +942,8 @@ int cbo_flood_walk_synthetic(const cbo_mode* m, unsigned seed, unsigned noise, u
 /* ------------------------------------------------------------------------------------------
  * Decoder::do_decode / do_decode_coupled with use_ecc = false -- Decoder.h:60-161
  * ---------------------------------------------------------------------------------------- */
+static __thread void (*g_pre_color_hook)(const cbo_mode*, const uint8_t*, int, int, int, const uint8_t*) = NULL;
+
 int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen,
                    int color_correction, uint8_t* out, cbo_cell* cells)
 {
@@ -799,6 +1015,10 @@ int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int need
         }
         free(f.heap.v); free(f.remaining); free(f.instr); free(bits);
     }
+
+    /* Decoder.h:104-105: "do color correction init, now that we (hopefully) have some fountain headers from the symbol
+       decode" -- only do_decode (not the legacy coupled layout) calls reader.init_ccm */
+    if (g_pre_color_hook && !m->legacy_mode) g_pre_color_hook(m, rgb, w, h, good, sym_buf);
 
     /* colour pass: Decoder.h:107-114 / :153-158.  colorPositions default to {i=0,x=0,y=0} when the reader
        was not good, so every entry ORs the colour at (0,0) into bit position 0. */
@@ -1137,6 +1357,49 @@ int cbo_decode(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sh
     }
     free(raw);
     return (int)total;
+}
+
+/* the symbol pass of a fountain decode with color_correction == 2: RS the symbol stream, replay the aligned_stream
+   callbacks, fit the CCM (CimbReader::init_ccm) and install it before the colour pass */
+static void fountain_ccm_hook(const cbo_mode* m, const uint8_t* rgb, int w, int h, int good, const uint8_t* sym_buf)
+{
+    if (!good || m->ecc_bytes == 0) return;
+    unsigned cap_sym = cbo_capacity(m, m->symbol_bits), msg = m->ecc_block_size - m->ecc_bytes;
+    unsigned nbs = cap_sym / m->ecc_block_size;
+    uint8_t* data = (uint8_t*)malloc((size_t)nbs * msg); uint8_t* ok = (uint8_t*)malloc(nbs);
+    cbo_rs_stream(m->ecc_bytes, m->ecc_block_size, sym_buf, cap_sym, data, ok);
+    uint8_t hdr[6]; unsigned radioactive = 0; float ccm[9];
+    if (cbo_header_after_symbols(data, ok, nbs, msg, m->chunk_size, hdr, &radioactive) &&
+        cbo_init_ccm(m, rgb, w, h, hdr, radioactive, ccm))
+        cbo_set_ccm(ccm);
+    free(data); free(ok);
+}
+
+int cbo_decode_fountain_cc(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen, int color_correction,
+                           uint8_t* chunks_out, uint32_t* mask)
+{
+    /* Decoder::decode_fountain, Decoder.h:171-189: one aligned_stream spans the symbol and colour RS streams */
+    unsigned bpc = m->symbol_bits + m->color_bits;
+    unsigned cap_all = cbo_capacity(m, bpc);
+    unsigned msg = m->ecc_block_size - m->ecc_bytes;
+    unsigned nblocks = cap_all / m->ecc_block_size;
+    uint8_t* data = (uint8_t*)malloc((size_t)nblocks * msg);
+    uint8_t* ok = (uint8_t*)malloc(nblocks);
+    uint8_t* raw = (uint8_t*)malloc(cap_all);
+    g_pre_color_hook = (color_correction == 2) ? fountain_ccm_hook : NULL;
+    cbo_decode_raw(m, rgb, w, h, needs_sharpen, color_correction, raw, NULL);
+    g_pre_color_hook = NULL;
+    if (m->legacy_mode) cbo_rs_stream(m->ecc_bytes, m->ecc_block_size, raw, cap_all, data, ok);
+    else {
+        unsigned cap_sym = cbo_capacity(m, m->symbol_bits), cap_col = cbo_capacity(m, m->color_bits);
+        unsigned nbs = cap_sym / m->ecc_block_size;
+        cbo_rs_stream(m->ecc_bytes, m->ecc_block_size, raw, cap_sym, data, ok);
+        cbo_rs_stream(m->ecc_bytes, m->ecc_block_size, raw + cap_sym, cap_col, data + (size_t)nbs * msg, ok + nbs);
+    }
+    free(raw);
+    unsigned good = cbo_align_chunks(data, ok, nblocks, msg, m->chunk_size, chunks_out, mask);
+    free(data); free(ok);
+    return (int)good;
 }
 
 int cbo_decode_fountain(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen,

@@ -114,6 +114,16 @@ int cbo_get_ccm(float* m9);
 /* color_correction::get_adaptation_matrix<von_kries> (color_correction.h:12-24) and simpleColorCorrection (CimbReader.cpp:55-93) */
 void cbo_adaptation_matrix(const float actual[3], const float desired[3], float out[9]);
 void cbo_simple_ccm(const cbo_mode* m, const uint8_t* rgb, int w, int h, float out[9]);
+/* color_correction::get_moore_penrose_lsm (color_correction.h:26-39): rows x 3 row-major inputs; returns 1 on success */
+int cbo_moore_penrose_lsm(const float* actual, const float* desired, int rows, float out[9]);
+/* CimbReader::_fountainColorHeader after the symbol stream's chunk callbacks (CimbReader.cpp:269-280) */
+int cbo_header_after_symbols(const uint8_t* blocks, const uint8_t* ok, unsigned nblocks, unsigned msg_len, unsigned chunk_size,
+                             uint8_t hdr[6], unsigned* radioactive_out);
+/* CimbReader::init_ccm (CimbReader.cpp:169-267); returns 1 when a matrix was fitted */
+int cbo_init_ccm(const cbo_mode* m, const uint8_t* rgb, int w, int h, const uint8_t hdr[6], unsigned radioactive, float out[9]);
+/* Decoder::decode_fountain(img, stream, should_preprocess, color_correction) incl. color_correction == 2 */
+int cbo_decode_fountain_cc(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen, int color_correction,
+                           uint8_t* chunks_out, uint32_t* mask);
 
 /* test hooks for the flood-walk / heap emulation (compared with the reference's FloodDecodePositions in oracle/_ref) */
 void cbo_synth_result(unsigned seed, unsigned i, int dx, int dy, unsigned cooldown, unsigned noise, unsigned* drift_offset, unsigned* dist);
