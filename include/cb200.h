@@ -38,9 +38,20 @@ extern "C" {
 #define CB200_FLAG_CC_SIMPLE    0x4u  /* color_correction == 1: every frame gets the von Kries matrix of its own anchor white
                                          before anything is read (simpleColorCorrection, CimbReader.cpp:55-93, :124-125);
                                          afterwards the context's CCM is the last frame's, as in the reference's decoder.
-                                         Without this flag the colour pass uses the context's CCM if one is set (below);
-                                         color_correction == 2's per-frame header fit (CimbReader::init_ccm) is NOT part
-                                         of the library: compute it on the host and hand it in through cb200_set_ccm. */
+                                         Without a CC flag the colour pass uses the context's CCM if one is set (below). */
+#define CB200_FLAG_CC_FIT       0x8u  /* color_correction == 2 (the reference's default) with the output stream of
+                                         Decoder::decode_fountain, whose chunk callback hands the decoder the fountain
+                                         headers (Decoder.h:171-189): honoured by the RS entry points (cb200_decode,
+                                         cb200_decode_chunks_dev, cb200_decode_fountain); a caller that mirrors
+                                         Decoder::decode on a plain stream must not set it (no callback, no fit), and the
+                                         raw entry points ignore it.  After the symbol stream's RS pass the fountain
+                                         header of the frame predicts the colours at the head of every colour-stream chunk,
+                                         a 3x3 least-squares CCM is fitted from them and the anchor white
+                                         (CimbReader::init_ccm, CimbReader.cpp:169-267; OpenCV's float Jacobi SVD restated),
+                                         and the frame's colours are decided with it.  A frame without a usable header keeps
+                                         the CCM of the frame before it (frame 0: the context's), exactly like the
+                                         reference's thread-local decoder state when frames are decoded in order; the
+                                         context's CCM afterwards is the last frame's.  Mutually exclusive with CC_SIMPLE. */
 
 /* per-frame status bits written to frame_flags[] */
 #define CB200_FRAME_FALLBACK    0x1u  /* frame was decoded by the exact flood-walk kernel (drift tracking needed) */

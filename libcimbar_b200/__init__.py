@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libcb200.so")
 FLAG_NO_FALLBACK = 0x1
 FLAG_SHARPEN = 0x2
 FLAG_CC_SIMPLE = 0x4
+FLAG_CC_FIT = 0x8
 FRAME_FALLBACK = 0x1
 FRAME_INEXACT = 0x2
 

@@ -231,8 +231,14 @@ struct cb200_ctx {
     float ccm[9] = {};               // active matrix, row-major
     bool ccm_active = false;
     bool ccm_pending = false;        // the last CC_SIMPLE batch's final matrix is still on its way to h_ccm
-    float* d_ccm = nullptr;          // per-frame matrices of a CC_SIMPLE batch: max_frames x 9
-    float* h_ccm = nullptr;          // pinned, 9 floats
+    bool ccm_pending_flag = false;   // ... and so is whether that frame had a CCM at all (CC_FIT batches)
+    float* d_ccm = nullptr;          // per-frame matrices of a CC_SIMPLE / CC_FIT batch (the ones used): max_frames x 9
+    float* h_ccm = nullptr;          // pinned: 9 floats + 1 activity byte (at float index 9)
+    // CC_FIT scratch: per-cell mean colours of the first pass, per-frame fits
+    uint32_t* d_means = nullptr;     // max_frames x num_cells
+    float* d_fit = nullptr;          // max_frames x 9
+    uint8_t* d_fit_valid = nullptr;  // max_frames
+    uint8_t* d_ccm_active = nullptr; // max_frames: the frame is decoded with d_ccm[f]
 };
 
 namespace {
@@ -265,7 +271,8 @@ int ccm_resolve(cb200_ctx* c)
     if (!c->ccm_pending) return CB200_OK;
     CK(cudaStreamSynchronize(c->stream), "sync (ccm)");
     memcpy(c->ccm, c->h_ccm, sizeof(c->ccm));
-    c->ccm_pending = false;
+    if (c->ccm_pending_flag) c->ccm_active = reinterpret_cast<const uint8_t*>(c->h_ccm + 9)[0] != 0;
+    c->ccm_pending = c->ccm_pending_flag = false;
     return CB200_OK;
 }
 int ccm_arg(cb200_ctx* c, CcmArg& cc)
@@ -277,21 +284,31 @@ int ccm_arg(cb200_ctx* c, CcmArg& cc)
 }
 
 // K1 (+ exact-walk fallback) : frames -> per-cell bytes in ctx->d_cellvals, per-frame flags in ctx->d_flags
-int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTrace* d_trace = nullptr)
+int ccm_buffers(cb200_ctx* c)
+{
+    if (!c->d_ccm) CK(cudaMalloc(&c->d_ccm, sizeof(float) * 9 * (size_t)c->max_frames), "cudaMalloc ccm");
+    if (!c->h_ccm) CK(cudaMallocHost(&c->h_ccm, sizeof(float) * 12), "cudaMallocHost ccm");
+    return CB200_OK;
+}
+
+// d_means != nullptr: first pass of a CC_FIT batch -- no colour decisions, the cells' mean colours go to d_means
+int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTrace* d_trace = nullptr, uint32_t* d_means = nullptr)
 {
     const Mode& m = c->mode;
     cudaStream_t st = c->stream;
     CcmArg cc;
-    if ((flags & CB200_FLAG_CC_SIMPLE) && n > 0) {
+    if (d_means) {
+        memset(&cc, 0, sizeof(cc));
+        cc.means = d_means;
+    } else if ((flags & CB200_FLAG_CC_SIMPLE) && n > 0) {
         // color_correction == 1: one matrix per frame, computed on the device before the colour pass (CimbReader.cpp:124-125)
-        if (!c->d_ccm) CK(cudaMalloc(&c->d_ccm, sizeof(float) * 9 * (size_t)c->max_frames), "cudaMalloc ccm");
-        if (!c->h_ccm) CK(cudaMallocHost(&c->h_ccm, sizeof(float) * 9), "cudaMallocHost ccm");
+        int rcb = ccm_buffers(c); if (rcb) return rcb;
         memset(&cc, 0, sizeof(cc));
         CK(ccm_simple_launch(m, d_rgb, n, c->d_ccm, st), "ccm launch");
         cc.per_frame = c->d_ccm; cc.active = 1;
         // the decoder keeps the last matrix it was given (CimbDecoder.cpp:82-85)
         CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, st), "D2H ccm");
-        c->ccm_pending = true; c->ccm_active = true;
+        c->ccm_pending = true; c->ccm_pending_flag = false; c->ccm_active = true;
     } else {
         int rc = ccm_arg(c, cc); if (rc) return rc;
     }
@@ -457,7 +474,7 @@ int cb200_destroy(cb200_ctx* c)
     cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_scratch);
     for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) if (c->ev[k][i]) cudaEventDestroy(c->ev[k][i]);
     flood_workspace_destroy(&c->flood);
-    cudaFree(c->d_ccm);
+    cudaFree(c->d_ccm); cudaFree(c->d_means); cudaFree(c->d_fit); cudaFree(c->d_fit_valid); cudaFree(c->d_ccm_active);
     if (c->h_ccm) cudaFreeHost(c->h_ccm);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -516,11 +533,39 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
     if (n == 0) return CB200_OK;
     if (!d_rgb || !d_chunks || !d_chunk_mask) return fail(CB200_ERR_ARG, "null buffer");
     CK(cudaSetDevice(c->device), "cudaSetDevice");
-    rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
-    mark(c);                                   // ev3: (no separate pack kernel on this path: the RS kernel gathers from the cell bytes)
-    CK(k2_rs_fused_launch(c->mode, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream), "rs launch");
+    const Mode& m = c->mode;
+    if ((flags & CB200_FLAG_CC_FIT) && (flags & CB200_FLAG_CC_SIMPLE)) return fail(CB200_ERR_ARG, "CC_SIMPLE and CC_FIT are exclusive");
+    // init_ccm is only reached from Decoder::do_decode (not the legacy coupled layout) and needs a header from the RS stream
+    const bool fit = (flags & CB200_FLAG_CC_FIT) && !m.legacy && m.ecc_bytes > 0 && m.color_bits > 0;
+    if (!fit) {
+        rc = run_cells(c, d_rgb, n, flags & ~CB200_FLAG_CC_FIT); if (rc) return rc;
+        mark(c);                               // ev3: (no separate pack kernel on this path: the RS kernel gathers from the cell bytes)
+        CK(k2_rs_fused_launch(m, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream), "rs launch");
+    } else {
+        // color_correction == 2: symbols (+ mean colours) -> RS of the symbol stream -> header -> CCM fit -> colours -> RS of
+        // the colour stream (Decoder.h:83-117)
+        rc = ccm_buffers(c); if (rc) return rc;
+        if (!c->d_means) CK(cudaMalloc(&c->d_means, sizeof(uint32_t) * (size_t)c->max_frames * m.num_cells), "cudaMalloc means");
+        if (!c->d_fit) CK(cudaMalloc(&c->d_fit, sizeof(float) * 9 * (size_t)c->max_frames), "cudaMalloc fit");
+        if (!c->d_fit_valid) CK(cudaMalloc(&c->d_fit_valid, (size_t)c->max_frames), "cudaMalloc fit flags");
+        if (!c->d_ccm_active) CK(cudaMalloc(&c->d_ccm_active, (size_t)c->max_frames), "cudaMalloc ccm flags");
+        CcmArg initial;
+        rc = ccm_arg(c, initial); if (rc) return rc;        // the decoder's CCM going into frame 0
+        rc = run_cells(c, d_rgb, n, flags & ~(CB200_FLAG_CC_FIT | CB200_FLAG_CC_SIMPLE), nullptr, c->d_means); if (rc) return rc;
+        mark(c);                               // ev3
+        CK(k2_rs_fused_launch(m, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, 0, m.nblocks_sym), "rs launch (symbols)");
+        CK(ccm_fit_launch(m, d_rgb, d_chunks, c->d_ok, c->d_idx, n, c->d_fit, c->d_fit_valid, c->stream), "ccm fit");
+        CK(ccm_carry_launch(n, c->d_fit, c->d_fit_valid, initial, c->d_ccm, c->d_ccm_active, c->stream), "ccm carry");
+        CK(ccm_apply_launch(m, c->d_means, n, c->d_ccm, c->d_ccm_active, c->d_cellvals, c->stream), "ccm apply");
+        CK(k2_rs_fused_launch(m, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, m.nblocks_sym, m.nblocks - m.nblocks_sym),
+           "rs launch (colours)");
+        // the decoder keeps the CCM of the last frame (and whether there is one at all)
+        CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, c->stream), "D2H ccm");
+        CK(cudaMemcpyAsync(c->h_ccm + 9, c->d_ccm_active + (n - 1), 1, cudaMemcpyDeviceToHost, c->stream), "D2H ccm flag");
+        c->ccm_pending = true; c->ccm_pending_flag = true;
+    }
     mark(c);                                   // ev4: after RS
-    CK(k2_mask_launch(c->mode, c->d_ok, n, d_chunk_mask, c->stream), "mask launch");
+    CK(k2_mask_launch(m, c->d_ok, n, d_chunk_mask, c->stream), "mask launch");
     mark(c);                                   // ev5: after chunk mask
     if (d_frame_flags) CK(cudaMemcpyAsync(d_frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToDevice, c->stream), "copy flags");
     return CB200_OK;
@@ -649,7 +694,7 @@ int cb200_best_colors(cb200_ctx* c, const uint8_t* rgb_means, int n, uint8_t* co
 int cb200_set_ccm(cb200_ctx* c, const float* m9)
 {
     if (!c) return fail(CB200_ERR_ARG, "null context");
-    c->ccm_pending = false;                      // an explicit matrix replaces whatever the last batch left
+    c->ccm_pending = c->ccm_pending_flag = false;    // an explicit matrix replaces whatever the last batch left
     c->ccm_active = m9 != nullptr;
     if (m9) memcpy(c->ccm, m9, sizeof(c->ccm));
     return CB200_OK;

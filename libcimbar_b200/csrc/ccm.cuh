@@ -17,7 +17,9 @@ namespace cb200 {
 // which CCM a launch uses: per_frame != nullptr -> matrix of frame f at per_frame + 9 f (color_correction == 1),
 // else the context's matrix m (CimbDecoder::update_color_correction) when active
 struct CcmArg {
-    const float* per_frame;
+    const float* per_frame;          // [n][9] or nullptr
+    const uint8_t* per_frame_active; // with per_frame: [n] 1 = use the matrix, 0 = no CCM for that frame (nullptr = all active)
+    uint32_t* means;                 // != nullptr: do not classify, store r | g << 8 | b << 16 per cell (color_correction == 2, first pass)
     float m[9];
     int active;
 };
@@ -63,5 +65,14 @@ __device__ __forceinline__ uint32_t best_color_ccm(const float* ccm, const Mode&
 }
 
 cudaError_t ccm_simple_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, float* d_ccm, cudaStream_t st);
+// color_correction == 2, after the symbol stream's RS pass: per frame the header the aligned_stream callbacks leave behind,
+// the colours it predicts, the fit (fit[f], valid[f]); then the carry (a frame without a fit keeps its predecessor's CCM,
+// frame 0 the context's) into used[f] / used_active[f]; then the colour decision of every cell from the stored means
+cudaError_t ccm_fit_launch(const Mode& m, const uint8_t* d_rgb, const uint8_t* d_data, const uint8_t* d_ok, const uint16_t* d_idx,
+                           int n_frames, float* d_fit, uint8_t* d_valid, cudaStream_t st);
+cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_valid, const CcmArg& initial, float* d_used,
+                             uint8_t* d_used_active, cudaStream_t st);
+cudaError_t ccm_apply_launch(const Mode& m, const uint32_t* d_means, int n_frames, const float* d_used, const uint8_t* d_used_active,
+                             uint8_t* d_cellvals, cudaStream_t st);
 
 }  // namespace cb200

@@ -205,7 +205,8 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
 // CCM: the colour classifier runs the reference's float path with a 3x3 colour correction matrix (ccm.cuh) instead of the
 // integer restatement; the matrix of the frame is staged in shared memory when a CTA starts on it.
-template <int NC, bool G1024, bool CCM>
+// CM = 0: integer classifier; 1: CCM classifier; 2: no decision, the cell's mean colour is stored for the fitted-CCM pass
+template <int NC, bool G1024, int CM>
 __global__ void __launch_bounds__(kK1Threads, 4)
 k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags, const CcmArg cc)
@@ -345,7 +346,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         int f = u / bands, b = u - f * bands;
         int k0 = (m.cells_y() * b) / bands, k1 = (m.cells_y() * (b + 1)) / bands;
         uint8_t* out = cellvals + (size_t)f * (size_t)m.num_cells();
-        if (CCM) {      // nobody reads s.ccm between the last colour pass of the previous unit and this barrier
+        if (CM == 1) {  // nobody reads s.ccm between the last colour pass of the previous unit and this barrier
             if (tid < 9) s.ccm[tid] = cc.per_frame ? cc.per_frame[(size_t)f * 9 + tid] : cc.m[tid];
             __syncthreads();
         }
@@ -420,7 +421,8 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                         rgb_row6(ub[0] + 2u * row_bytes, x, R, G, B);
                         rgb_row6(ub[1], x, R, G, B);
                         rgb_row6(ub[1] + row_bytes, x, R, G, B);
-                        col = CCM ? best_color_ccm<NC>(s.ccm, mm, R / 36u, G / 36u, B / 36u) : best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
+                        if (CM == 2) cc.means[(size_t)f * (size_t)m.num_cells() + (size_t)(base + t)] = (R / 36u) | ((G / 36u) << 8) | ((B / 36u) << 16);
+                        else col = CM == 1 ? best_color_ccm<NC>(s.ccm, mm, R / 36u, G / 36u, B / 36u) : best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
                     }
                 }
                 carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
@@ -548,8 +550,9 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     const int smem_max = (int)sizeof(K1Smem) + 64 * 1024;
 #define CB200_K1_ATTR(NC, G, C) \
     if ((e = cudaFuncSetAttribute(k1_decode_kernel<NC, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
-    CB200_K1_ATTR(4, true, false) CB200_K1_ATTR(4, false, false) CB200_K1_ATTR(8, true, false) CB200_K1_ATTR(8, false, false)
-    CB200_K1_ATTR(4, true, true) CB200_K1_ATTR(4, false, true) CB200_K1_ATTR(8, true, true) CB200_K1_ATTR(8, false, true)
+    CB200_K1_ATTR(4, true, 0) CB200_K1_ATTR(4, false, 0) CB200_K1_ATTR(8, true, 0) CB200_K1_ATTR(8, false, 0)
+    CB200_K1_ATTR(4, true, 1) CB200_K1_ATTR(4, false, 1) CB200_K1_ATTR(8, true, 1) CB200_K1_ATTR(8, false, 1)
+    CB200_K1_ATTR(4, true, 2) CB200_K1_ATTR(4, false, 2) CB200_K1_ATTR(8, true, 2) CB200_K1_ATTR(8, false, 2)
 #undef CB200_K1_ATTR
     return cudaSuccess;
 }
@@ -561,15 +564,12 @@ cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int ban
     const size_t smem = sizeof(K1Smem) + extra;
     const bool g1024 = m.width == 1024 && m.height == 1024 && m.cells_x == 112 && m.cells_y == 112 && m.corner == 6 &&
                        m.cell_offset == 8 && m.symbol_bits == 4;
-    const bool ccm = cc.active != 0;
+    const int cm = cc.means ? 2 : (cc.active ? 1 : 0);
 #define CB200_K1_GO(NC, G, C) k1_decode_kernel<NC, G, C><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty, cc)
-    if (m.color_bits == 3) {
-        if (g1024) { if (ccm) CB200_K1_GO(8, true, true); else CB200_K1_GO(8, true, false); }
-        else { if (ccm) CB200_K1_GO(8, false, true); else CB200_K1_GO(8, false, false); }
-    } else {
-        if (g1024) { if (ccm) CB200_K1_GO(4, true, true); else CB200_K1_GO(4, true, false); }
-        else { if (ccm) CB200_K1_GO(4, false, true); else CB200_K1_GO(4, false, false); }
-    }
+#define CB200_K1_CM(NC, G) do { if (cm == 2) CB200_K1_GO(NC, G, 2); else if (cm == 1) CB200_K1_GO(NC, G, 1); else CB200_K1_GO(NC, G, 0); } while (0)
+    if (m.color_bits == 3) { if (g1024) CB200_K1_CM(8, true); else CB200_K1_CM(8, false); }
+    else { if (g1024) CB200_K1_CM(4, true); else CB200_K1_CM(4, false); }
+#undef CB200_K1_CM
 #undef CB200_K1_GO
     return cudaGetLastError();
 }

@@ -576,7 +576,8 @@ k_flood_colour(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
                 const uint8_t* p = frame + ((size_t)(y + r) * W + (size_t)(x + 1)) * 3;
                 for (int c = 0; c < 6; ++c) { R += p[3 * c]; G += p[3 * c + 1]; B += p[3 * c + 2]; }
             }
-            if (cc.active) {
+            if (cc.means) cc.means[(size_t)f * ncells + ci] = (R / 36u) | ((G / 36u) << 8) | ((B / 36u) << 16);
+            else if (cc.active && (!cc.per_frame_active || cc.per_frame_active[f])) {
                 float mat[9];
 #pragma unroll
                 for (int q = 0; q < 9; ++q) mat[q] = cc.per_frame ? cc.per_frame[(size_t)f * 9 + q] : cc.m[q];

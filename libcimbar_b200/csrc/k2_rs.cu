@@ -118,8 +118,8 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 template <int T, bool FUSED>
 __global__ void __launch_bounds__(kRsWarpsPerCta * 32, 4)
 k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __restrict__ cellvals, const uint16_t* __restrict__ idx,
-            int n_frames, uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok)
-{
+            int n_frames, int b_begin, int b_count, uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok)
+{   // blocks [b_begin, b_begin + b_count) of every frame (all of them, or the symbol / the colour stream on their own)
     extern __shared__ __align__(16) uint8_t rs_smem_raw[];
     RsSmem& s = *reinterpret_cast<RsSmem*>(rs_smem_raw);
     uint32_t* mt = reinterpret_cast<uint32_t*>(rs_smem_raw + ((sizeof(RsSmem) + 127) & ~size_t(127)));
@@ -134,11 +134,11 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
     __syncthreads();
 
     const int md = m.ecc_bytes, blk = m.ecc_block, msg_len = m.msg_len;
-    const long total_blocks = (long)n_frames * m.nblocks;
+    const long total_blocks = (long)n_frames * b_count;
     RsSmem::PerWarp& w = s.w[warp];
 
     for (long gb = (long)blockIdx.x * kRsWarpsPerCta + warp; gb < total_blocks; gb += (long)gridDim.x * kRsWarpsPerCta) {
-        const int f = (int)(gb / m.nblocks), b = (int)(gb - (long)f * m.nblocks);
+        const int f = (int)(gb / b_count), b = b_begin + (int)(gb - (long)f * b_count);
         uint8_t* out = data_out + ((size_t)f * m.nblocks + b) * msg_len;
         __syncwarp();
         if (FUSED) {
@@ -425,8 +425,9 @@ cudaError_t k2_pack_launch(const Mode& m, const uint8_t* d_cellvals, const uint1
 
 template <int T, bool FUSED>
 static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames,
-                               uint8_t* d_data, uint8_t* d_ok, int sm_count, cudaStream_t st)
+                               uint8_t* d_data, uint8_t* d_ok, int sm_count, cudaStream_t st, int b_begin = 0, int b_count = -1)
 {
+    if (b_count < 0) b_count = m.nblocks;
     const size_t smem = ((sizeof(RsSmem) + 127) & ~size_t(127)) + sizeof(uint32_t) * 256 * 32 * T;
     static bool configured = false;
     if (!configured) {
@@ -434,12 +435,12 @@ static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    long total = (long)n_frames * m.nblocks;
+    long total = (long)n_frames * b_count;
     long ctas = (total + kRsWarpsPerCta - 1) / kRsWarpsPerCta;
     long max_ctas = (long)sm_count * (T == 1 ? 4 : 2);       // persistent: the table build is amortised over many blocks
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, d_data, d_ok);
+    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, b_begin, b_count, d_data, d_ok);
     return cudaGetLastError();
 }
 
@@ -450,10 +451,10 @@ cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint
 }
 
 cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_data,
-                               uint8_t* d_ok, int sm_count, cudaStream_t st)
+                               uint8_t* d_ok, int sm_count, cudaStream_t st, int b_begin, int b_count)
 {
-    if (m.ecc_bytes <= 32) return rs_launch_t<1, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st);
-    return rs_launch_t<2, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st);
+    if (m.ecc_bytes <= 32) return rs_launch_t<1, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st, b_begin, b_count);
+    return rs_launch_t<2, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st, b_begin, b_count);
 }
 
 cudaError_t k2_mask_launch(const Mode& m, const uint8_t* d_ok, int n_frames, uint32_t* d_mask, cudaStream_t st)

@@ -10,11 +10,10 @@
 // Differences from the reference, by design of this round:
 //   * frames must be exactly Config::image_size_x() x image_size_y(), RGB8, continuous (the Extractor's output);
 //     a smaller image reproduces the reference's degenerate "reader not good" result (zero-filled streams);
-//   * color_correction: 0 = off, 1 = simpleColorCorrection on the device (per-frame von Kries matrix, bit-exact).
-//     2 (the per-frame header fit of CimbReader::init_ccm, an OpenCV SVD least-squares fit) is not computed by the
-//     library: the frame is decoded with whatever CCM the decoder currently holds (update_color_correction / load_ccm,
-//     exactly what the reference does for a frame whose header did not decode) and WARN_COLOR_CORRECTION_IGNORED is set
-//     in last_warnings().
+//   * color_correction: 0 = off, 1 = simpleColorCorrection (per-frame von Kries matrix), 2 = the header fit of
+//     CimbReader::init_ccm -- all on the device and bit-exact.  As in the reference the fit only happens in
+//     decode_fountain (its aligned_stream hands the decoder the fountain headers); decode() with 2 uses whatever CCM the
+//     decoder holds.  Any other value is decoded as 0 and reported through last_warnings().
 #pragma once
 #include "../../include/cb200.h"
 #include "Config.h"
@@ -117,17 +116,26 @@ public:
 		{
 			null_stream devnull;
 			aligned_stream<null_stream> aligner(devnull, chunk_size, 0);
+			HeaderCallbacks on(*this);
 			return decode(img, aligner, should_preprocess, color_correction);
 		}
 		aligned_stream<FOUNTAINSTREAM> aligner(ostream, ostream.chunk_size(), 0);
+		HeaderCallbacks on(*this);   // this stream feeds CimbReader::update_metadata in the reference: color_correction 2 fits
 		return decode(img, aligner, should_preprocess, color_correction);
 	}
 
 protected:
+	struct HeaderCallbacks   // scope guard: the decode in progress is decode_fountain's (Decoder.h:171-189)
+	{
+		Decoder& d;
+		explicit HeaderCallbacks(Decoder& dec) : d(dec) { d._headerCallbacks = true; }
+		~HeaderCallbacks() { d._headerCallbacks = false; }
+	};
+
 	template <typename MAT>
 	bool run(const MAT& img, bool should_preprocess, int color_correction, std::vector<uint8_t>& data, std::vector<uint8_t>& ok)
 	{
-		_warnings = (color_correction != 0 and color_correction != 1) ? WARN_COLOR_CORRECTION_IGNORED : 0;
+		_warnings = (color_correction < 0 or color_correction > 2) ? WARN_COLOR_CORRECTION_IGNORED : 0;
 		_frameFlags = 0;
 		if (cimbar::Config::mode_val() != _modeVal)
 			throw std::runtime_error("cb200::Decoder: Config mode changed after construction (one Decoder per mode)");
@@ -159,7 +167,8 @@ protected:
 		}
 		if (img.cols != _info.image_size_x or img.rows != _info.image_size_y or !img.isContinuous())
 			throw std::invalid_argument("cb200::Decoder: frame must be exactly image_size_x x image_size_y, continuous RGB8");
-		uint32_t flags = (should_preprocess ? CB200_FLAG_SHARPEN : 0) | (color_correction == 1 ? CB200_FLAG_CC_SIMPLE : 0);
+		uint32_t flags = (should_preprocess ? CB200_FLAG_SHARPEN : 0) | (color_correction == 1 ? CB200_FLAG_CC_SIMPLE : 0) |
+		                 ((color_correction == 2 and _headerCallbacks) ? CB200_FLAG_CC_FIT : 0);
 		uint8_t ff = 0;
 		int rc = _useEcc ? cb200_decode(_ctx, img.data, 1, flags, data.data(), ok.data(), &ff)
 		                 : cb200_decode_raw(_ctx, img.data, 1, flags, data.data(), &ff);
@@ -174,6 +183,7 @@ protected:
 	bool _interleave;
 	int _modeVal;
 	cb200_ctx* _ctx = nullptr;
+	bool _headerCallbacks = false;
 	cb200_info _info;
 	unsigned _warnings = 0;
 	unsigned _frameFlags = 0;

@@ -41,6 +41,27 @@ CCM_GOLDENS = [
      "matrix": [[1.6250746, 0.0024788622, -0.45772526], [-0.29126319, 2.2922182, -0.67037439], [-1.2192062, -2.7447209, 5.0476217]],
      "first_colors": [0, 1, 1, 2, 2, 2]},
 ]
+# color_correctionTest/testComputeMoorePenrose (.2): color_correction::get_moore_penrose_lsm on explicit inputs
+MOORE_PENROSE_GOLDENS = [
+    {"actual": [[0, 142.31060606, 0], [0, 148.75, 148.75], [148.75, 148.75, 0], [148.75, 0, 148.75], [255, 255, 255]],
+     "desired": [[0, 255, 0], [0, 255, 255], [255, 255, 0], [255, 0, 255], [255, 255, 255]],
+     "matrix_str": "[1.5223049, -0.10023587, -0.19198087;\n -0.20533442, 1.6441474, -0.20533434;\n -0.19198078, -0.10023584, 1.5223049]",
+     "source": "src/lib/chromatic_adaptation/test/color_correctionTest.cpp:32-56"},
+    {"actual": [[14.58901515, 115.74431818, 39.88320707], [19.34027778, 124.4375, 115.37152778], [140.70486111, 137.45833333, 65.50694444],
+                [131.59722222, 41.22222222, 104.84027778], [171.625, 163.625, 158.875]],
+     "desired": [[0, 255, 0], [0, 255, 255], [255, 255, 0], [255, 0, 255], [255, 255, 255]],
+     "matrix_str": "[2.0261116, -0.21691091, -0.19806443;\n -0.43822661, 2.4562523, -0.41700464;\n -0.55769891, -1.1443435, 3.4819376]",
+     "source": "src/lib/chromatic_adaptation/test/color_correctionTest.cpp:58-84"},
+]
+# CimbReaderTest/testCCM(.VeryNecessary): init_ccm after update_metadata(FountainMetadata(0, 23586, 7)) -> printed matrix
+INIT_CCM_GOLDENS = [
+    {"sample": "b/ex2434.jpg", "md": [0, 23586, 7],
+     "matrix_str": "[2.3991191, -0.41846275, -0.54654282;\n -0.42976046, 2.632102, -0.76466882;\n -0.54299992, -0.20199311, 2.2753253]",
+     "source": "src/lib/cimb_translator/test/CimbReaderTest.cpp:181-199"},
+    {"sample": "b/ex380.jpg", "md": [0, 23586, 7],
+     "matrix_str": "[1.6250746, 0.0024788622, -0.45772526;\n -0.29126319, 2.2922182, -0.67037439;\n -1.2192062, -2.7447209, 5.0476217]",
+     "source": "src/lib/cimb_translator/test/CimbReaderTest.cpp:239-257"},
+]
 # color_correctionTest/testTransform (src/lib/chromatic_adaptation/test/color_correctionTest.cpp:14-30)
 ADAPTATION_GOLDEN = {"actual": [192, 255, 255], "desired": [255, 255, 255],
                      "matrix_str": "[1.0655777, 0.2109226, -0.013239831;\n 0.023168325, 0.98723376, -0.0046780901;\n 0, 0, 1]",
@@ -61,7 +82,8 @@ def main():
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference")
     manifest = {"cv2": cv2.__version__, "samples": {}, "goldens": [], "cv_pins": {}, "ccm_goldens": CCM_GOLDENS,
-                "adaptation_golden": ADAPTATION_GOLDEN}
+                "adaptation_golden": ADAPTATION_GOLDEN, "moore_penrose_goldens": MOORE_PENROSE_GOLDENS,
+                "init_ccm_goldens": INIT_CCM_GOLDENS}
     for s in SAMPLES:
         dst = os.path.join(HERE, s.replace("/", "__"))
         shutil.copyfile(os.path.join(REF, "samples", s), dst)

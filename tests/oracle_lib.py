@@ -97,6 +97,9 @@ class Oracle:
         L.cbo_get_ccm.argtypes = [C.POINTER(C.c_float)]
         L.cbo_adaptation_matrix.argtypes = [C.POINTER(C.c_float)] * 3
         L.cbo_simple_ccm.argtypes = [C.POINTER(Mode), u8p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.cbo_moore_penrose_lsm.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float)]
+        L.cbo_init_ccm.argtypes = [C.POINTER(Mode), u8p, C.c_int, C.c_int, u8p, C.c_uint, C.POINTER(C.c_float)]
+        L.cbo_decode_fountain_cc.argtypes = [C.POINTER(Mode), u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.POINTER(C.c_uint32)]
 
     def mode(self, mode_val=68):
         m = Mode()
@@ -143,13 +146,30 @@ class Oracle:
         nblocks = self.capacity(m) // m.ecc_block_size
         return out[:n].copy(), ok[:nblocks].copy()
 
-    def decode_fountain(self, m, rgb, sharpen=False):
+    def decode_fountain(self, m, rgb, sharpen=False, color_correction=0):
+        """Decoder::decode_fountain(img, stream, should_preprocess, color_correction); the CCM state is the calling thread's"""
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
         h, w = rgb.shape[:2]
         chunks = np.zeros((m.chunks_per_frame, m.chunk_size), dtype=np.uint8)
         mask = C.c_uint32(0)
-        good = self.lib.cbo_decode_fountain(C.byref(m), _ptr(rgb), w, h, int(sharpen), _ptr(chunks), C.byref(mask))
+        good = self.lib.cbo_decode_fountain_cc(C.byref(m), _ptr(rgb), w, h, int(sharpen), int(color_correction), _ptr(chunks), C.byref(mask))
         return good, chunks, mask.value
+
+    def get_ccm(self):
+        a = np.zeros(9, np.float32)
+        return a.reshape(3, 3) if self.lib.cbo_get_ccm(_ptr(a, C.c_float)) else None
+
+    def moore_penrose_lsm(self, actual, desired):
+        a = np.ascontiguousarray(actual, np.float32); d = np.ascontiguousarray(desired, np.float32); o = np.zeros(9, np.float32)
+        self.lib.cbo_moore_penrose_lsm(_ptr(a, C.c_float), _ptr(d, C.c_float), a.shape[0], _ptr(o, C.c_float))
+        return o.reshape(3, 3)
+
+    def init_ccm(self, m, rgb, hdr6, radioactive):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        h6 = np.ascontiguousarray(hdr6, dtype=np.uint8)
+        o = np.zeros(9, np.float32)
+        rc = self.lib.cbo_init_ccm(C.byref(m), _ptr(rgb), rgb.shape[1], rgb.shape[0], _ptr(h6), int(radioactive), _ptr(o, C.c_float))
+        return o.reshape(3, 3) if rc else None
 
     def preprocess(self, rgb, sharpen=False):
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8)

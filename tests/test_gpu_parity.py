@@ -545,3 +545,70 @@ def test_simple_color_correction_matches_oracle(cb):
     ctx2 = cb.Context(68, max_frames=4)
     data, ok, _ = ctx2.decode(frames[:3], flags=cb.FLAG_CC_SIMPLE)
     assert ok.all() and np.array_equal(data, payloads[:3])
+
+
+def _oracle_fountain_batch(m, frames, color_correction, initial=None):
+    """frames decoded in order by ONE reference decoder: the thread-local CCM carries from frame to frame"""
+    ORA.set_ccm(initial)
+    out = []
+    try:
+        for fr in frames:
+            good, chunks, mask = ORA.decode_fountain(m, fr, color_correction=color_correction)
+            out.append((good, chunks.copy(), mask, ORA.get_ccm()))
+    finally:
+        ORA.set_ccm(None)
+    return out
+
+
+def test_color_correction_2_fit_matches_oracle(cb):
+    # color_correction == 2 (CimbReader::init_ccm): real fountain frames (clean PNGs), a camera frame that needs both the
+    # exact walk and the CCM, tinted synthetic frames whose random "headers" still predict their own colours, a frame whose
+    # first symbol chunks are destroyed (header comes from a later chunk), and a frame with no decodable chunk at all
+    # (keeps the previous frame's CCM)
+    m, payloads, synth = synth_frames(68, 3, seed=47)
+    synth[0] = _tint(synth[0:1], (0.8, 0.6, 1.0))[0]
+    rng = np.random.default_rng(9)
+    xs, ys = np.zeros(m.total_cells, np.int32), np.zeros(m.total_cells, np.int32)
+    ORA.lib.cbo_cell_positions(C.byref(m), 0, _ptr(xs, C.c_int), _ptr(ys, C.c_int))
+    idx = np.zeros(m.total_cells, np.uint32)
+    ORA.lib.cbo_interleave_indices(m.total_cells, m.interleave_blocks, m.interleave_partitions, _ptr(idx, C.c_uint))
+    # frame 1: wreck the cells of the first two symbol chunks' RS blocks (stream slots of blocks 0..9: bytes 0..1549 -> slots 0..3099)
+    for s in rng.choice(3100, 1200, replace=False):
+        c = idx[s]
+        synth[1][ys[c]:ys[c] + 8, xs[c]:xs[c] + 8] = rng.integers(0, 256, (8, 8, 3), dtype=np.uint8)
+    # frame 2: noise everywhere -> nothing decodes
+    synth[2] = rng.integers(0, 256, synth[2].shape, dtype=np.uint8)
+    frames = np.stack([load_sample("b/tr_0.png"), load_sample("b/ex380.jpg"), synth[0], synth[1], synth[2], load_sample("b/tr_1.png")])
+    want = _oracle_fountain_batch(m, frames, 2)
+    assert want[4][3] is not None and np.array_equal(want[4][3], want[3][3])      # the scenario the carry exists for
+    ctx = cb.Context(68, max_frames=len(frames))
+    chunks, counts, masks, ff = ctx.decode_fountain(frames, flags=cb.FLAG_CC_FIT)
+    for f, (good, wchunks, wmask, wccm) in enumerate(want):
+        assert masks[f] == wmask, f
+        assert counts[f] * m.chunk_size == good, f
+        assert np.array_equal(chunks[f][:counts[f]], wchunks[:counts[f]]), f
+    assert np.array_equal(ctx.get_ccm(), want[-1][3])                             # bit-exact fit, carried to the context
+    # the block-level entry point (what the C++ Decoder mirror replays into the caller's aligned_stream) agrees
+    ctx2 = cb.Context(68, max_frames=len(frames))
+    data, ok, _ = ctx2.decode(frames, flags=cb.FLAG_CC_FIT)
+    for f in range(len(frames)):
+        for q in range(m.chunks_per_frame):
+            if masks[f] >> q & 1:
+                assert np.array_equal(data[f].reshape(m.chunks_per_frame, m.chunk_size)[q], chunks[f][bin(masks[f] & ((1 << q) - 1)).count("1")]), (f, q)
+    # a second batch starts from the CCM the first one left, like the next frames of the same reference decoder
+    again = _oracle_fountain_batch(m, frames[4:5], 2, initial=want[-1][3])
+    chunks3, counts3, masks3, _ = ctx.decode_fountain(frames[4:5], flags=cb.FLAG_CC_FIT)
+    assert masks3[0] == again[0][2] and np.array_equal(ctx.get_ccm(), again[0][3])
+
+
+@pytest.mark.parametrize("mode_val", [8, 67])
+def test_color_correction_2_other_modes(cb, mode_val):
+    m, payloads, frames = synth_frames(mode_val, 3, seed=53)
+    frames[1] = _tint(frames[1:2], (0.9, 0.7, 0.75))[0]
+    want = _oracle_fountain_batch(m, frames, 2)
+    ctx = cb.Context(mode_val, max_frames=3)
+    chunks, counts, masks, ff = ctx.decode_fountain(frames, flags=cb.FLAG_CC_FIT)
+    for f, (good, wchunks, wmask, wccm) in enumerate(want):
+        assert masks[f] == wmask and counts[f] * m.chunk_size == good, f
+        assert np.array_equal(chunks[f][:counts[f]], wchunks[:counts[f]]), f
+    assert np.array_equal(ctx.get_ccm(), want[-1][3])

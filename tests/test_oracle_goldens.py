@@ -2,6 +2,7 @@
 Sources: src/lib/encoder/test/DecoderTest.cpp:26-106 (SHA-256 of decoded bytes),
 cimb_translator/test/CimbReaderTest.cpp:37-163 (first 22 cells in flood order),
 cimb_translator/test/CimbDecoderTest.cpp:77-131 (colour known answers)."""
+import ctypes as C
 import hashlib
 
 import numpy as np
@@ -167,3 +168,42 @@ def test_ccm_is_very_necessary_for_ex380():
         ORA.set_ccm(None)
     assert np.array_equal(plain["symbol"], fixed["symbol"])
     assert (plain["color"] != fixed["color"]).mean() > 0.02
+
+
+@pytest.mark.parametrize("idx", range(2))
+def test_moore_penrose_matches_reference_strings(idx):
+    # color_correctionTest.cpp:32-84: the float Jacobi-SVD pseudo-inverse, down to its asymmetric last digits
+    g = manifest()["moore_penrose_goldens"][idx]
+    assert _fmt_matx(ORA.moore_penrose_lsm(g["actual"], g["desired"])) == g["matrix_str"]
+
+
+@pytest.mark.parametrize("idx", range(2))
+def test_init_ccm_matches_reference_strings(idx):
+    # CimbReaderTest.cpp:181-199 / :239-257: update_metadata(FountainMetadata(0, 23586, 7)) then init_ccm on a camera frame
+    g = manifest()["init_ccm_goldens"][idx]
+    m = ORA.mode(68)
+    hdr = np.zeros(6, np.uint8)
+    ORA.lib.cbo_md_pack(g["md"][0], g["md"][1], g["md"][2], hdr.ctypes.data_as(C.POINTER(C.c_uint8)))
+    size = g["md"][1]
+    radioactive = 0xFFFFFFFF if size % 625 == 0 else size // 625       # computeRadioactiveBlockId, CimbReader.cpp:99-104
+    nxt = g["md"][2] + 1                                               # update_metadata: "we always want to be +1"
+    if nxt == radioactive:
+        nxt += 1
+    hdr[4], hdr[5] = (nxt >> 8) & 0xFF, nxt & 0xFF
+    mat = ORA.init_ccm(m, load_sample(g["sample"]), hdr, radioactive)
+    assert mat is not None and _fmt_matx(mat) == g["matrix_str"]
+
+
+def test_decode_fountain_cc2_fits_from_the_frames_own_header():
+    # tr_0.png is a real fountain frame: with color_correction == 2 the decode fits a CCM from its header (a gain of ~1.5:
+    # the cell means include the tiles' black pixels) and keeps it; the chunks are the same as without
+    m = ORA.mode(68)
+    rgb = load_sample("b/tr_0.png")
+    ORA.set_ccm(None)
+    good0, chunks0, mask0 = ORA.decode_fountain(m, rgb, color_correction=0)
+    assert ORA.get_ccm() is None
+    good2, chunks2, mask2 = ORA.decode_fountain(m, rgb, color_correction=2)
+    mat = ORA.get_ccm()
+    ORA.set_ccm(None)
+    assert mat is not None and (np.diag(mat) > 1.3).all() and (np.abs(mat - np.diag(np.diag(mat))) < 0.4).all()
+    assert (good0, mask0) == (good2, mask2) and np.array_equal(chunks0, chunks2)
