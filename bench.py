@@ -35,6 +35,9 @@ def parse_args():
     ap.add_argument("--workload", default="clean", choices=["clean", "errors1pct", "noise1pct"],
                     help="clean = BASELINE configs[1] frames; errors1pct = configs[2] (1%% wrong tiles, RS repairs); "
                          "noise1pct = 1%% of the cells replaced by random pixels (forces the exact flood-walk kernel)")
+    ap.add_argument("--color-correction", type=int, default=0, choices=[0, 1, 2],
+                    help="the reference's color_correction argument (0 = headline configuration; 1 = per-frame von Kries; "
+                         "2 = per-frame header fit, the payload then carries consecutive fountain headers)")
     ap.add_argument("--e2e-frames", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -131,6 +134,20 @@ def run_ours(args):
     g = torch.Generator(device=dev)
     g.manual_seed(0xC1B4 + rank)
     payload = torch.randint(0, 256, (B, info.data_bytes), dtype=torch.uint8, device=dev, generator=g)
+    cc_flags = {0: 0, 1: cb.FLAG_CC_SIMPLE, 2: cb.FLAG_CC_FIT}[args.color_correction]
+    if args.color_correction == 2:
+        # a fountain stream: every 625-byte chunk starts with FountainMetadata(encode_id, size, block_id) and the block ids
+        # of a frame are consecutive (fountain/FountainMetadata.h:16-31) -- that is what CimbReader::init_ccm predicts from
+        cpf, cs = info.chunks_per_frame, info.data_bytes // info.chunks_per_frame
+        pv = payload.view(B, cpf, cs)
+        size = 625 * 4000                                                # a multiple of the chunk size: no "radioactive" block id
+        bid = (torch.arange(B, device=dev).view(B, 1) * cpf + torch.arange(cpf, device=dev).view(1, cpf)) % 65536
+        pv[:, :, 0] = (1 & 0x7F) | ((size >> 17) & 0x80)
+        pv[:, :, 1] = (size >> 16) & 0xFF
+        pv[:, :, 2] = (size >> 8) & 0xFF
+        pv[:, :, 3] = size & 0xFF
+        pv[:, :, 4] = (bid >> 8).to(torch.uint8)
+        pv[:, :, 5] = (bid & 0xFF).to(torch.uint8)
     cells = torch.empty((B, info.total_cells), dtype=torch.uint8, device=dev)
     ctx.encode_cells_dev(payload.data_ptr(), B, cells.data_ptr())
     if args.workload == "errors1pct":
@@ -168,7 +185,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step():
-        ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr())
+        ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr(), flags=cc_flags)
         if world > 1:   # the one exchange of the path: decoded fountain chunk records -> rank 0 (wirehair ingest side)
             dist.gather(chunks, gather_chunks, dst=0)
             dist.gather(mask, gather_mask, dst=0)
@@ -231,12 +248,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         hf = host_frames.numpy()
         ctx.set_stream(None)
-        ctx.decode_fountain(hf)                      # warm-up (allocates the staging buffers)
+        ctx.decode_fountain(hf, flags=cc_flags)      # warm-up (allocates the staging buffers)
         barrier()
         t0 = time.perf_counter()
         esteps = max(3, min(K, 10))
         for _ in range(esteps):
-            ch, cnt, mk, ff = ctx.decode_fountain(hf)
+            ch, cnt, mk, ff = ctx.decode_fountain(hf, flags=cc_flags)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device=dev)
@@ -267,7 +284,7 @@ def run_ours(args):
         "config": {"workload": ({"clean": "BASELINE configs[1]", "errors1pct": "BASELINE configs[2] (1% wrong tiles)", "noise1pct": "1% noise tiles (exact-walk path)"}[args.workload]) +
                    ": %d synthetic 1024x1024 mode-B frames per GPU per step through the full decode "
                    "(K1 fused threshold+ahash+colour, K1x exact-walk check, pack, RS(155,125), chunk masks)" % B,
-                   "mode": "B (68)", "frames_per_gpu_per_step": B,
+                   "mode": "B (68)", "frames_per_gpu_per_step": B, "color_correction": args.color_correction,
                    "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
                    "parallelism": "frames sharded one-per-GPU (dp%d), NCCL gather of chunk records to rank 0" % world},
         "parity": parity + ("" if ok_flags else " (%d of %d frames/rank went through the exact flood-walk kernel)" % (n_fallback, B)),
