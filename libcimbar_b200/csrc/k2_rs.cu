@@ -429,11 +429,9 @@ static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_
 {
     if (b_count < 0) b_count = m.nblocks;
     const size_t smem = ((sizeof(RsSmem) + 127) & ~size_t(127)) + sizeof(uint32_t) * 256 * 32 * T;
-    static bool configured = false;
-    if (!configured) {
+    {   // a per-device attribute: set on every launch (a process may hold contexts on several GPUs)
         cudaError_t e = cudaFuncSetAttribute(k_rs_decode<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     long total = (long)n_frames * b_count;
     long ctas = (total + kRsWarpsPerCta - 1) / kRsWarpsPerCta;
