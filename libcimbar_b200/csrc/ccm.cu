@@ -330,17 +330,30 @@ k_ccm_fit(const Mode m, const uint8_t* __restrict__ rgb, const uint8_t* __restri
 
 // the decoder's CCM is whatever the last successful fit left (thread-local state, CimbDecoder.cpp:69-85): frame f uses its own
 // fit if it has one, else the matrix of frame f-1 (frame 0: the context's)
-__global__ void k_ccm_carry(int n_frames, const float* __restrict__ fit, const uint8_t* __restrict__ valid, const CcmArg initial,
-                            float* __restrict__ used, uint8_t* __restrict__ used_active)
+__global__ void __launch_bounds__(1024)
+k_ccm_carry(int n_frames, const float* __restrict__ fit, const uint8_t* __restrict__ valid, const CcmArg initial,
+            float* __restrict__ used, uint8_t* __restrict__ used_active)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float cur[9];
-    for (int i = 0; i < 9; ++i) cur[i] = initial.m[i];
-    uint8_t active = initial.active ? 1 : 0;
-    for (int f = 0; f < n_frames; ++f) {
-        if (valid[f]) { for (int i = 0; i < 9; ++i) cur[i] = fit[(size_t)f * 9 + i]; active = 1; }
-        for (int i = 0; i < 9; ++i) used[(size_t)f * 9 + i] = cur[i];
-        used_active[f] = active;
+    // "index of the last frame <= f with a fit" is a running maximum: every thread scans a contiguous segment, the segment
+    // results are combined by a block-wide inclusive max scan, then every thread replays its segment with the right start
+    __shared__ int seg_last[1024];
+    const int t = threadIdx.x;
+    const int seg = (n_frames + 1023) / 1024, f0 = t * seg, f1 = min(f0 + seg, n_frames);
+    int last = -1;
+    for (int f = f0; f < f1; ++f) if (valid[f]) last = f;
+    seg_last[t] = last;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? seg_last[t - o] : -1;
+        __syncthreads();
+        if (v > seg_last[t]) seg_last[t] = v;
+        __syncthreads();
+    }
+    int cur = t > 0 ? seg_last[t - 1] : -1;
+    for (int f = f0; f < f1; ++f) {
+        if (valid[f]) cur = f;
+        for (int i = 0; i < 9; ++i) used[(size_t)f * 9 + i] = cur >= 0 ? fit[(size_t)cur * 9 + i] : initial.m[i];
+        used_active[f] = (cur >= 0 || initial.active) ? 1 : 0;
     }
 }
 
@@ -395,7 +408,7 @@ cudaError_t ccm_fit_launch(const Mode& m, const uint8_t* d_rgb, const uint8_t* d
 cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_valid, const CcmArg& initial, float* d_used,
                              uint8_t* d_used_active, cudaStream_t st)
 {
-    k_ccm_carry<<<1, 32, 0, st>>>(n_frames, d_fit, d_valid, initial, d_used, d_used_active);
+    k_ccm_carry<<<1, 1024, 0, st>>>(n_frames, d_fit, d_valid, initial, d_used, d_used_active);
     return cudaGetLastError();
 }
 cudaError_t ccm_apply_launch(const Mode& m, const uint32_t* d_means, int n_frames, const float* d_used, const uint8_t* d_used_active,

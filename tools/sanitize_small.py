@@ -22,4 +22,16 @@ data, ok, _ = ctx.decode(frames)
 assert np.array_equal(data[:3], payloads) and ff.tolist()[:3] == [0, 0, 0]
 for f in range(4):
     assert np.array_equal(raw[f], ora.decode_raw(m, frames[f]))
+# colour correction 1 (per-frame von Kries) and 2 (header fit: means pass, symbol RS, fit, carry, apply, colour RS)
+raw1, _ = ctx.decode_raw(frames, flags=cb.FLAG_CC_SIMPLE)
+for f in range(4):
+    assert np.array_equal(raw1[f], ora.decode_raw(m, frames[f], color_correction=1))
+ora.set_ccm(None)
+ctx.set_ccm(None)
+chunks, counts, masks, _ = ctx.decode_fountain(frames, flags=cb.FLAG_CC_FIT)
+for f in range(4):
+    good, wchunks, wmask = ora.decode_fountain(m, frames[f], color_correction=2)
+    assert masks[f] == wmask and np.array_equal(chunks[f][:counts[f]], wchunks[:counts[f]])
+assert np.array_equal(ctx.get_ccm(), ora.get_ccm())
+ora.set_ccm(None)
 print("sanitize_small: ok")
