@@ -288,7 +288,9 @@ def run_ours(args):
                    "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
                    "parallelism": "frames sharded one-per-GPU (dp%d), NCCL gather of chunk records to rank 0" % world},
         "parity": parity + ("" if ok_flags else " (%d of %d frames/rank went through the exact flood-walk kernel)" % (n_fallback, B)),
-        "gpu_launches": 5 * K * world,
+        # kernels of this library per step: K1, the four exact-walk-check kernels (list, raster, walk, colour), fused RS, chunk
+        # mask; color_correction 1 adds k_ccm_simple, 2 adds a second RS launch and k_ccm_fit / carry / apply
+        "gpu_launches": {0: 7, 1: 8, 2: 11}[args.color_correction] * K * world,
         "kernel_ms_per_step": {"k1_decode": stage_ms[0], "k1x_flood_check": stage_ms[1], "pack": stage_ms[2], "rs": stage_ms[3], "chunk_mask": stage_ms[4]},
         "roofline": {"kernel": "k1_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
