@@ -120,6 +120,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the decode path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, K, W = args.frames, args.steps, max(args.warmup, 0)
