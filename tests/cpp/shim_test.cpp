@@ -9,6 +9,7 @@
 #include "../../libcimbar_b200/host/Decoder.h"
 
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -53,6 +54,38 @@ int main(int argc, char** argv)
 		unsigned good = dece.decode_fountain(img, ebw, false, 0);
 		CHECK(good == ebw.buffers_in_use() * cimbar::Config::fountain_chunk_size());
 		std::ofstream(prefix + ".chunks", std::ios::binary).write(reinterpret_cast<const char*>(bufspace.data()), good);
+	}
+	{   // colour correction through the mirrors: decode_fountain's default color_correction = 2 (header fit), then 1; the
+		// fitted matrix goes through DecoderPlus::save_ccm / load_ccm's file format (9 float32)
+		std::vector<unsigned char> bufspace(cimbar::Config::fountain_chunks_per_frame() * cimbar::Config::fountain_chunk_size());
+		{
+			Decoder d2;
+			escrow_buffer_writer ebw(bufspace.data(), cimbar::Config::fountain_chunks_per_frame(), cimbar::Config::fountain_chunk_size());
+			unsigned good = d2.decode_fountain(img, ebw);
+			CHECK(d2.last_warnings() == 0);
+			std::ofstream(prefix + ".chunks_cc2", std::ios::binary).write(reinterpret_cast<const char*>(bufspace.data()), good);
+			float m9[9];
+			if (d2.get_ccm(m9))
+			{
+				CHECK(d2.save_ccm(prefix + ".ccm"));
+				Decoder d3;
+				float back[9];
+				CHECK(!d3.get_ccm(back));
+				CHECK(d3.load_ccm(prefix + ".ccm"));
+				CHECK(d3.get_ccm(back) && std::memcmp(back, m9, sizeof(m9)) == 0);
+				// Decoder::decode on a plain stream never fits (no header callbacks): it decodes with the loaded matrix
+				std::stringstream plain;
+				d3.decode(img, plain, false, 2);
+				CHECK(d3.get_ccm(back) && std::memcmp(back, m9, sizeof(m9)) == 0);
+			}
+			else std::remove((prefix + ".ccm").c_str());
+		}
+		{
+			Decoder d1;
+			escrow_buffer_writer ebw(bufspace.data(), cimbar::Config::fountain_chunks_per_frame(), cimbar::Config::fountain_chunk_size());
+			unsigned good = d1.decode_fountain(img, ebw, false, 1);
+			std::ofstream(prefix + ".chunks_cc1", std::ios::binary).write(reinterpret_cast<const char*>(bufspace.data()), good);
+		}
 	}
 	{   // CimbReaderTest: first 22 cells in flood order as "index=value" pairs, then the reader runs to exactly 12400 reads
 		CimbReader cr(img, cimbar::Config::color_mode());

@@ -342,6 +342,21 @@ def test_cpp_shims_rerun_reference_unit_tests(cb, tmp_path):
         good, ochunks, omask = ORA.decode_fountain(m, rgb)
         chunks = np.fromfile(prefix + ".chunks", dtype=np.uint8)
         assert chunks.size == good and np.array_equal(chunks, ochunks.reshape(-1)[:good])
+        # colour correction through the mirrors: 2 (decode_fountain's default) and 1, against one fresh reference decoder each
+        for cc in (2, 1):
+            ORA.set_ccm(None)
+            try:
+                good_cc, ochunks_cc, _ = ORA.decode_fountain(m, rgb, color_correction=cc)
+                want_ccm = ORA.get_ccm()
+            finally:
+                ORA.set_ccm(None)
+            got = np.fromfile(prefix + ".chunks_cc%d" % cc, dtype=np.uint8)
+            assert got.size == good_cc and np.array_equal(got, ochunks_cc.reshape(-1)[:good_cc]), (sample, mode, cc)
+            if cc == 2:
+                if want_ccm is None:
+                    assert not os.path.exists(prefix + ".ccm")
+                else:
+                    assert np.array_equal(np.fromfile(prefix + ".ccm", dtype=np.float32).reshape(3, 3), want_ccm)
         lines = open(prefix + ".first22").read().split("\n")
         if (sample, mode) in first22:
             assert lines[0] == first22[(sample, mode)]
