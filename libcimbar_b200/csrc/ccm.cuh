@@ -49,7 +49,11 @@ __device__ __forceinline__ uint32_t best_color_ccm(const float* ccm, const Mode&
     const float mx = fmaxf(fmaxf(r, g), fmaxf(b, 1.0f));
     float mn = fminf(fminf(r, g), fminf(b, 48.0f));
     if (mn >= mx) mn = 0.0f;
-    const float adjust = __double2float_rn(__ddiv_rn(255.0, (double)__fsub_rn(mx, mn)));   // float adjust = 255.0 / (max - min)
+    // float adjust = 255.0 / (max - min): a double division rounded to float in the reference.  For a float divisor d that
+    // is the correctly rounded SINGLE quotient: the double quotient could only mis-round if it sat exactly on a float
+    // midpoint M (25 significant bits) without being equal to it, i.e. 0 < |M d - 255| <= 2^-45; but M d is a multiple of
+    // 2^-41 (25 x 24 significant bits, M d ~ 255), so the product is either 255 exactly or at least 2^-41 away.
+    const float adjust = __fdiv_rn(255.0f, __fsub_rn(mx, mn));
     const int cr = (int)fix_single_color_rn(r, adjust, mn), cg = (int)fix_single_color_rn(g, adjust, mn), cb = (int)fix_single_color_rn(b, adjust, mn);
     const int a0 = cr - cg, a1 = cg - cb;
     uint32_t best = 0;
