@@ -357,28 +357,31 @@ k_ccm_carry(int n_frames, const float* __restrict__ fit, const uint8_t* __restri
     }
 }
 
-// CimbDecoder::get_best_color for every cell from the mean colours the first pass stored
+// CimbDecoder::get_best_color for every cell from the mean colours the first pass stored.  blockIdx.y walks the frames (the
+// frame's matrix sits in shared memory), blockIdx.x the cells.
 __global__ void __launch_bounds__(256)
 k_ccm_apply(const Mode m, const uint32_t* __restrict__ means, int n_frames, const float* __restrict__ used,
             const uint8_t* __restrict__ used_active, uint8_t* __restrict__ cellvals)
 {
     __shared__ float adjust[256];
+    __shared__ float mat[9];
     {   // (float)(255.0 / (double)d): the integer classifier's scale table (CimbDecoder.cpp:185)
         const int d = threadIdx.x;
         adjust[d] = d ? __double2float_rn(__ddiv_rn(255.0, (double)d)) : 0.0f;
     }
-    __syncthreads();
-    const size_t total = (size_t)n_frames * m.num_cells;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        const int f = (int)(i / (size_t)m.num_cells);
+    const int ci = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t color_mask = ((1u << m.color_bits) - 1u) << m.symbol_bits;
+    for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
+        __syncthreads();                                   // adjust[] ready; the previous frame's readers of mat[] are done
+        const bool active = used_active[f] != 0;
+        if (active && threadIdx.x < 9) mat[threadIdx.x] = used[(size_t)f * 9 + threadIdx.x];
+        __syncthreads();
+        if (ci >= m.num_cells) continue;
+        const size_t i = (size_t)f * m.num_cells + ci;
         const uint32_t v = means[i], ri = v & 0xFFu, gi = (v >> 8) & 0xFFu, bi = (v >> 16) & 0xFFu;
         uint32_t col;
-        if (used_active[f]) {
-            float mat[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) mat[q] = used[(size_t)f * 9 + q];
-            col = best_color_ccm<0>(mat, m, ri, gi, bi);
-        } else {
+        if (active) col = best_color_ccm<0>(mat, m, ri, gi, bi);
+        else {
             // integer inputs: max/min with the floors, scale through the table, same decision as the float code (k1_decode.cu)
             uint32_t mxi = max(max(ri, gi), max(bi, 1u)), mni = min(min(ri, gi), min(bi, 48u));
             if (mni >= mxi) mni = 0;
@@ -393,7 +396,7 @@ k_ccm_apply(const Mode m, const uint32_t* __restrict__ means, int n_frames, cons
                 if (d < best_d) { best_d = d; col = (uint32_t)c; }
             }
         }
-        cellvals[i] = (uint8_t)((cellvals[i] & ~(((1u << m.color_bits) - 1u) << m.symbol_bits)) | (col << m.symbol_bits));
+        cellvals[i] = (uint8_t)((cellvals[i] & ~color_mask) | (col << m.symbol_bits));
     }
 }
 
@@ -414,10 +417,8 @@ cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_
 cudaError_t ccm_apply_launch(const Mode& m, const uint32_t* d_means, int n_frames, const float* d_used, const uint8_t* d_used_active,
                              uint8_t* d_cellvals, cudaStream_t st)
 {
-    const size_t total = (size_t)n_frames * m.num_cells;
-    size_t blocks = (total + 255) / 256;
-    if (blocks > 148u * 16u) blocks = 148u * 16u;
-    k_ccm_apply<<<(int)blocks, 256, 0, st>>>(m, d_means, n_frames, d_used, d_used_active, d_cellvals);
+    dim3 grid((unsigned)((m.num_cells + 255) / 256), (unsigned)(n_frames < 32768 ? n_frames : 32768));
+    k_ccm_apply<<<grid, 256, 0, st>>>(m, d_means, n_frames, d_used, d_used_active, d_cellvals);
     return cudaGetLastError();
 }
 
