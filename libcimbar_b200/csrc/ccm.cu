@@ -363,16 +363,11 @@ __global__ void __launch_bounds__(256)
 k_ccm_apply(const Mode m, const uint32_t* __restrict__ means, int n_frames, const float* __restrict__ used,
             const uint8_t* __restrict__ used_active, uint8_t* __restrict__ cellvals)
 {
-    __shared__ float adjust[256];
     __shared__ float mat[9];
-    {   // (float)(255.0 / (double)d): the integer classifier's scale table (CimbDecoder.cpp:185)
-        const int d = threadIdx.x;
-        adjust[d] = d ? __double2float_rn(__ddiv_rn(255.0, (double)d)) : 0.0f;
-    }
     const int ci = blockIdx.x * 256 + threadIdx.x;
     const uint32_t color_mask = ((1u << m.color_bits) - 1u) << m.symbol_bits;
     for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
-        __syncthreads();                                   // adjust[] ready; the previous frame's readers of mat[] are done
+        __syncthreads();                                   // the previous frame's readers of mat[] are done
         const bool active = used_active[f] != 0;
         if (active && threadIdx.x < 9) mat[threadIdx.x] = used[(size_t)f * 9 + threadIdx.x];
         __syncthreads();
@@ -385,7 +380,8 @@ k_ccm_apply(const Mode m, const uint32_t* __restrict__ means, int n_frames, cons
             // integer inputs: max/min with the floors, scale through the table, same decision as the float code (k1_decode.cu)
             uint32_t mxi = max(max(ri, gi), max(bi, 1u)), mni = min(min(ri, gi), min(bi, 48u));
             if (mni >= mxi) mni = 0;
-            const float adj = adjust[mxi - mni], mn = (float)mni, hi_thr = __fsub_rn(245.0f, mn);
+            // (float)(255.0 / (double)d) == the single-precision quotient (see best_color_ccm)
+            const float adj = __fdiv_rn(255.0f, (float)(mxi - mni)), mn = (float)mni, hi_thr = __fsub_rn(245.0f, mn);
             const float fr = __fmul_rn((float)(ri - mni), adj), fg = __fmul_rn((float)(gi - mni), adj), fb = __fmul_rn((float)(bi - mni), adj);
             const int cr = (fr > hi_thr) ? 255 : (int)__float2uint_rz(fr), cg = (fg > hi_thr) ? 255 : (int)__float2uint_rz(fg),
                       cb = (fb > hi_thr) ? 255 : (int)__float2uint_rz(fb);
@@ -417,7 +413,7 @@ cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_
 cudaError_t ccm_apply_launch(const Mode& m, const uint32_t* d_means, int n_frames, const float* d_used, const uint8_t* d_used_active,
                              uint8_t* d_cellvals, cudaStream_t st)
 {
-    dim3 grid((unsigned)((m.num_cells + 255) / 256), (unsigned)(n_frames < 32768 ? n_frames : 32768));
+    dim3 grid((unsigned)((m.num_cells + 255) / 256), (unsigned)(n_frames < 2048 ? n_frames : 2048));
     k_ccm_apply<<<grid, 256, 0, st>>>(m, d_means, n_frames, d_used, d_used_active, d_cellvals);
     return cudaGetLastError();
 }
