@@ -207,3 +207,62 @@ def test_decode_fountain_cc2_fits_from_the_frames_own_header():
     ORA.set_ccm(None)
     assert mat is not None and (np.diag(mat) > 1.3).all() and (np.abs(mat - np.diag(np.diag(mat))) < 0.4).all()
     assert (good0, mask0) == (good2, mask2) and np.array_equal(chunks0, chunks2)
+
+
+def _header_rule_closed_form(data, ok, blocks_per_chunk, msg, chunk_size):
+    """the rule k_ccm_fit uses on the device (libcimbar_b200/csrc/ccm.cu): with whole RS blocks per chunk a chunk raises an
+    event only when its last block is good -- a flush if all its blocks are good and no bad flag is pending, else the
+    "bad chunk" callback; a bad last block passes the flag on"""
+    hdr = [0] * 6
+    radioactive, carry = 0, False
+    for q in range(len(ok) // blocks_per_chunk):
+        blk = ok[q * blocks_per_chunk:(q + 1) * blocks_per_chunk]
+        if not blk[-1]:
+            carry = True
+            continue
+        good = all(blk) and not carry
+        carry = False
+        id_zero = not any(hdr[:4])
+        if not good and id_zero:
+            continue
+        if id_zero:
+            hdr = list(data[q * blocks_per_chunk * msg:q * blocks_per_chunk * msg + 6])
+        if radioactive == 0:
+            fs = hdr[3] | (hdr[2] << 8) | (hdr[1] << 16) | ((hdr[0] & 0x80) << 17)
+            radioactive = 0xFFFFFFFF if fs % chunk_size == 0 else fs // chunk_size
+        nxt = ((hdr[4] << 8) | hdr[5]) + 1
+        if nxt == radioactive:
+            nxt += 1
+        hdr[4], hdr[5] = (nxt >> 8) & 0xFF, nxt & 0xFF
+    return hdr, radioactive, any(hdr[:4])
+
+
+def test_header_rule_closed_form_equals_stream_replay():
+    """the device derives the fountain header from per-chunk rules; the oracle replays aligned_stream byte by byte
+    (aligned_stream.h:39-116 + CimbReader::update_metadata): both must agree for every pattern of good / bad RS blocks"""
+    rng = np.random.default_rng(77)
+    L = ORA.lib
+    L.cbo_header_after_symbols.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_uint, C.c_uint, C.c_uint,
+                                           C.POINTER(C.c_uint8), C.POINTER(C.c_uint)]
+    nblocks, msg, chunk = 40, 125, 625
+    for trial in range(3000):
+        p_bad = rng.choice([0.0, 0.05, 0.3, 0.7])
+        ok = (rng.random(nblocks) >= p_bad).astype(np.uint8)
+        data = rng.integers(0, 256, nblocks * msg, dtype=np.uint8)
+        for q in range(8):                                   # headers: sometimes an all-zero id, small / aligned file sizes
+            kind = rng.integers(0, 4)
+            h = data[q * chunk:q * chunk + 6]
+            if kind == 0:
+                h[:4] = 0
+            elif kind == 1:
+                h[0] &= 0x7F; h[1] = 0; h[2] = rng.integers(0, 8); h[4] = 0; h[5] = rng.integers(0, 6)   # radioactive id nearby
+            elif kind == 2:
+                size = 625 * int(rng.integers(1, 3000)); h[0] = 1 | ((size >> 17) & 0x80); h[1] = (size >> 16) & 0xFF; h[2] = (size >> 8) & 0xFF; h[3] = size & 0xFF
+        hdr = np.zeros(6, np.uint8)
+        rad = C.c_uint(0)
+        has = L.cbo_header_after_symbols(data.ctypes.data_as(C.POINTER(C.c_uint8)), ok.ctypes.data_as(C.POINTER(C.c_uint8)), nblocks, msg, chunk,
+                                         hdr.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(rad))
+        whdr, wrad, whas = _header_rule_closed_form(data.tolist(), ok.tolist(), 5, msg, chunk)
+        assert bool(has) == bool(whas), trial
+        if has:
+            assert hdr.tolist() == whdr and rad.value == wrad, trial
