@@ -637,6 +637,8 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     if (per_sm < 1) per_sm = 1;
     if (const char* s = getenv("CB200_K1X_WALKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= per_sm) per_sm = v; }
     ws->slots = sm_count * per_sm;
+    ws->max_entries = kFloodMaxEntries;
+    if (const char* s = getenv("CB200_K1X_MAX_ENTRIES")) { int v = atoi(s); if (v >= 1 && v <= kFloodMaxEntries) ws->max_entries = v; }   // tests: force several chunks
     ws->spill_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->walk_smem)) != cudaSuccess) return e;
@@ -667,13 +669,14 @@ static cudaError_t flood_workspace_ensure(const Mode& m, FloodWorkspace& ws, int
         while (cap < n_frames) cap *= 2;
         cudaFree(ws.list); cudaFree(ws.counters); ws.list = nullptr; ws.counters = nullptr; ws.list_cap = 0;
         if ((e = cudaMalloc(&ws.list, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&ws.counters, (size_t)(2 + cap / 64) * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ws.counters, (size_t)(2 + cap) * sizeof(uint32_t))) != cudaSuccess) return e;   // 1 + one per chunk (>= 1 frame each)
         ws.list_cap = cap;
     }
-    const int want = n_frames < kFloodMaxEntries ? n_frames : kFloodMaxEntries;
+    const int want = n_frames < ws.max_entries ? n_frames : ws.max_entries;
     if (want > ws.entry_cap) {
         int cap = (want + 1023) / 1024 * 1024;          // in steps of 1024 frames (185 MB)
         if (want <= 64) cap = 64; else if (want <= 256) cap = 256;
+        if (cap > ws.max_entries) cap = ws.max_entries;
         cudaFree(ws.raster); cudaFree(ws.result); ws.raster = nullptr; ws.result = nullptr; ws.entry_cap = 0;
         if ((e = cudaMalloc(&ws.raster, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
         if ((e = cudaMemset(ws.raster, 0, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;

@@ -26,6 +26,7 @@ struct FloodWorkspace {
     uint8_t* prio;             // [slots][kMaxCells] per-cell priority bytes of the walk in that slot
     uint16_t* cinfo;           // [num_cells][16] update candidates in push order (0xFFFF = none)
     int list_cap; uint32_t* list; uint32_t* counters;   // work list; counters[0] = listed frames, [1 + c] = chunk c's work counter
+    int max_entries;           // upper bound of entry_cap (one chunk); larger work lists are processed chunk by chunk
     int entry_cap; uint32_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster, per-cell x | y<<11 | sym<<22
 };
 

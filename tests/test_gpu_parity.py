@@ -627,3 +627,21 @@ def test_color_correction_2_other_modes(cb, mode_val):
         assert masks[f] == wmask and counts[f] * m.chunk_size == good, f
         assert np.array_equal(chunks[f][:counts[f]], wchunks[:counts[f]]), f
     assert np.array_equal(ctx.get_ccm(), want[-1][3])
+
+
+def test_exact_walk_work_list_in_several_chunks(cb, monkeypatch):
+    # the exact-walk kernels keep raster/result for at most N listed frames at a time (16 384 by default) and go through
+    # longer work lists chunk by chunk; force tiny chunks so that the chunk loop, its counters and the list offsets are exercised
+    monkeypatch.setenv("CB200_K1X_MAX_ENTRIES", "3")
+    m, payloads, frames = synth_frames(68, 10, seed=61, error_rate=0.01, noise_tiles=True)
+    clean = synth_frames(68, 3, seed=62)[2]
+    batch = np.concatenate([frames[:4], clean[:2], frames[4:], clean[2:]])        # 13 frames, 10 of them need the walk
+    ctx = cb.Context(68, max_frames=len(batch))
+    monkeypatch.delenv("CB200_K1X_MAX_ENTRIES")
+    raw, ff = ctx.decode_raw(batch)
+    assert ff.tolist() == [1, 1, 1, 1, 0, 0, 1, 1, 1, 1, 1, 1, 0]
+    for f in range(len(batch)):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, batch[f])), f
+    raw2, ff2 = ctx.decode_raw(batch[::-1].copy())                                  # a second call reuses the workspace
+    for f in range(len(batch)):
+        assert np.array_equal(raw2[f], raw[len(batch) - 1 - f]), f
