@@ -133,6 +133,69 @@ def test_band_splitting_is_invisible(cb, n):
     ctx.close()
 
 
+@pytest.mark.parametrize("mode_val", [68, 4, 8, 66, 67])
+def test_whole_frame_schedule_every_mode(cb, mode_val):
+    """n >= 4 x SMs switches K1 from band-split CTAs to the persistent whole-frame schedule the bench runs in (api.cu
+    run_cells); every mode -- incl. the non-1024x1024 geometries 66 (736x637) and 67 (1024x720) and the legacy coupled
+    layouts 4C / 8C (Decoder.h:121-161, GridConf.h:144-189) -- must give the same bits there as the oracle."""
+    m, payloads, frames = synth_frames(mode_val, 5, seed=200 + mode_val)
+    n = 640                                                     # > 4 x 148 CTAs
+    big = np.concatenate([frames] * (n // 5))
+    ctx = cb.Context(mode_val, max_frames=n)
+    assert n >= 4 * ctx.info.sm_count, "test sized for <= 160 SMs"
+    raw, ff = ctx.decode_raw(big)
+    assert not ff.any()
+    want = np.stack([ORA.decode_raw(m, fr) for fr in frames])
+    assert np.array_equal(raw.reshape(n // 5, 5, -1), np.broadcast_to(want, (n // 5,) + want.shape))
+    data, ok, _ = ctx.decode(big)
+    assert ok.all() and np.array_equal(data.reshape(n // 5, 5, -1), np.broadcast_to(payloads, (n // 5,) + payloads.shape))
+    ctx.close()
+
+
+def test_config3_256_frames_match_oracle(cb):
+    """BASELINE configs[2] at a size where a systematic slip would show: 256 distinct frames with 1 % wrong (valid) tiles,
+    raw bits, RS-corrected bytes and per-block ok flags against the oracle frame by frame"""
+    n = 256
+    m, payloads, frames = synth_frames(68, n, seed=77, error_rate=0.01)
+    ctx = cb.Context(68, max_frames=n)
+    raw, ff = ctx.decode_raw(frames)
+    data, ok, _ = ctx.decode(frames)
+    chunks, count, mask, _ = ctx.decode_fountain(frames)
+    assert not ff.any()                                          # valid tiles keep the drift-0 proof intact
+    for f in range(n):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f])), f
+        odata, ook = ORA.decode(m, frames[f])
+        assert np.array_equal(ok[f], ook) and np.array_equal(data[f], odata), f
+    assert ok.all() and np.array_equal(data, payloads) and (mask == 0xFFF).all() and (count == 12).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode_val,rate", [(4, 0.01), (4, 0.045), (8, 0.01), (67, 0.01), (66, 0.01)])
+def test_other_modes_with_tile_errors_match_oracle(cb, mode_val, rate):
+    """BASELINE configs[4] (legacy 4C: coupled 6-bit layout, 10 chunks x 750 B, one RS stream) and the other modes with
+    wrong tiles: RS repairs (1 %) or gives up on some blocks (4.5 %) exactly where libcorrect does"""
+    n = 48
+    m, payloads, frames = synth_frames(mode_val, n, seed=90 + mode_val, error_rate=rate)
+    ctx = cb.Context(mode_val, max_frames=n)
+    raw, ff = ctx.decode_raw(frames)
+    data, ok, _ = ctx.decode(frames)
+    chunks, count, mask, _ = ctx.decode_fountain(frames)
+    nfail = 0
+    for f in range(n):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, frames[f])), f
+        odata, ook = ORA.decode(m, frames[f])
+        assert np.array_equal(ok[f], ook) and np.array_equal(data[f], odata), f
+        good, ochunks, omask = ORA.decode_fountain(m, frames[f])
+        assert mask[f] == omask and count[f] * m.chunk_size == good, f
+        assert np.array_equal(chunks[f][:count[f]], ochunks[:count[f]]), f
+        nfail += int((ook == 0).sum())
+    if rate <= 0.01:
+        assert ok.all() and np.array_equal(data, payloads)
+    else:
+        assert nfail > 0
+    ctx.close()
+
+
 def test_one_percent_tile_errors_config3(cb):
     # BASELINE config 3: 1 % of cells replaced by a different valid tile -> RS repairs everything
     m, payloads, frames = synth_frames(68, 6, seed=7, error_rate=0.01)
