@@ -20,9 +20,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "decoded cimbar frames/sec (1024x1024 mode-B)"
 UNIT = "frames/s"
-K1_READ_BYTES = 1024 * 1024 * 3          # the RGB8 frame, read once
-K1_WRITE_BYTES = 12400                   # one result byte per cell
-K1_ALGO_BYTES = K1_READ_BYTES + K1_WRITE_BYTES
+MODE_NAMES = {68: "B", 67: "Bm", 66: "Bu", 4: "4C", 8: "8C"}
+
+
+def metric_name(mode_val):
+    return METRIC if mode_val == 68 else "decoded cimbar frames/sec (mode %s)" % MODE_NAMES[mode_val]
 
 
 def parse_args():
@@ -35,6 +37,8 @@ def parse_args():
     ap.add_argument("--workload", default="clean", choices=["clean", "errors1pct", "noise1pct"],
                     help="clean = BASELINE configs[1] frames; errors1pct = configs[2] (1%% wrong tiles, RS repairs); "
                          "noise1pct = 1%% of the cells replaced by random pixels (forces the exact flood-walk kernel)")
+    ap.add_argument("--mode", type=int, default=68, choices=[68, 67, 66, 4, 8],
+                    help="cimbar mode_val: 68 = B (headline), 4 = legacy 4C (BASELINE configs[4]), 8 = 8C, 67 = Bm, 66 = Bu")
     ap.add_argument("--color-correction", type=int, default=0, choices=[0, 1, 2],
                     help="the reference's color_correction argument (0 = headline configuration; 1 = per-frame von Kries; "
                          "2 = per-frame header fit, the payload then carries consecutive fountain headers)")
@@ -125,8 +129,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     B, K, W = args.frames, args.steps, max(args.warmup, 0)
 
-    ctx = cb.Context(68, max_frames=max(B, args.e2e_frames), device=local)
+    MV = args.mode
+    ctx = cb.Context(MV, max_frames=max(B, args.e2e_frames), device=local)
     info = ctx.info
+    K1_ALGO_BYTES = info.frame_bytes + info.total_cells      # the RGB8 frame read once + one result byte per cell
     stream = torch.cuda.Stream(device=dev)           # a real (non-default) stream: handle 0 would mean "context's own"
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -155,10 +161,13 @@ def run_ours(args):
         # replace 1 % of the cells (124 per frame) by a different valid tile/colour: RS must repair them
         k = info.total_cells // 100
         pos = torch.rand((B, info.total_cells), device=dev, generator=g).argsort(dim=1)[:, :k]
-        delta = torch.randint(1, 64, (B, k), dtype=torch.uint8, device=dev, generator=g)
-        cells.scatter_(1, pos, (cells.gather(1, pos) + delta) % 64)
+        nvals = 1 << (info.symbol_bits + info.color_bits)
+        delta = torch.randint(1, nvals, (B, k), dtype=torch.uint8, device=dev, generator=g)
+        cells.scatter_(1, pos, (cells.gather(1, pos) + delta) % nvals)
     frames = torch.empty((B, info.image_size_y, info.image_size_x, 3), dtype=torch.uint8, device=dev)
     ctx.render_frames_dev(cells.data_ptr(), B, frames.data_ptr())
+    if args.workload == "noise1pct" and MV != 68:
+        raise SystemExit("bench.py: --workload noise1pct is only wired for mode 68")
     if args.workload == "noise1pct":
         # overwrite 124 cells per frame with uniform-noise 8x8 tiles: the centre-wins proof fails, K1x decodes the frame
         k = info.total_cells // 100
@@ -205,10 +214,12 @@ def run_ours(args):
     ctx.set_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = cb.launch_count()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
+    launches = cb.launch_count() - launches0         # counted by the library at every launch site
     barrier()
     sampler.stop_flag = True
     elapsed_ms = e0.elapsed_time(e1)
@@ -221,6 +232,10 @@ def run_ours(args):
     sampler.join(timeout=1.0)
 
     # ---- parity of what was just timed (outside the timed region): every chunk decoded, bytes == payload
+    if world > 1:
+        t = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t.item())
     ok_mask = bool((mask == (1 << info.chunks_per_frame) - 1).all().item())
     ok_data = bool(torch.equal(chunks, payload))
     n_fallback = int((fflags & 1).sum().item())
@@ -260,7 +275,10 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e_ok = bool((cnt == info.chunks_per_frame).all()) and np.array_equal(ch.reshape(ne, -1), payload[:ne].cpu().numpy())
+        if args.workload == "clean":
+            e2e_ok = bool((cnt == info.chunks_per_frame).all()) and np.array_equal(ch.reshape(ne, -1), payload[:ne].cpu().numpy())
+        else:   # damaged input: the host path must return what the device path returned for the same frames
+            e2e_ok = np.array_equal(mk, mask[:ne].cpu().numpy().astype(np.uint32))
         e2e = {"value": world * ne * esteps / dt, "unit": UNIT,
                "h2d_bytes_per_step": ne * info.frame_bytes,
                "d2h_bytes_per_step": ne * (info.data_bytes + 4 + 1),
@@ -278,20 +296,20 @@ def run_ours(args):
     achieved = B * K1_ALGO_BYTES / (k1_ms * 1e-3) / 1e9
     traffic = k1_traffic_bytes()
     out = {
-        "metric": METRIC, "value": world * B * K / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "metric": metric_name(MV), "value": world * B * K / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (integer/bitwise; float32 only in the colour classifier, bit-exact vs reference)",
         "data": "synthetic (device-generated: random payload -> RS(155,125) -> interleaved tiles -> RGB8 frames)",
         "config": {"workload": ({"clean": "BASELINE configs[1]", "errors1pct": "BASELINE configs[2] (1% wrong tiles)", "noise1pct": "1% noise tiles (exact-walk path)"}[args.workload]) +
-                   ": %d synthetic 1024x1024 mode-B frames per GPU per step through the full decode "
-                   "(K1 fused threshold+ahash+colour, K1x exact-walk check, pack, RS(155,125), chunk masks)" % B,
-                   "mode": "B (68)", "frames_per_gpu_per_step": B, "color_correction": args.color_correction,
+                   ": %d synthetic %dx%d mode-%s frames per GPU per step through the full decode "
+                   "(K1 fused threshold+ahash+colour, K1x exact-walk check, RS(%d,%d) with fused de-interleave, chunk masks)" % (
+                       B, info.image_size_x, info.image_size_y, MODE_NAMES[MV], info.ecc_block_size, info.ecc_block_size - info.ecc_bytes),
+                   "mode": "%s (%d)" % (MODE_NAMES[MV], MV), "frames_per_gpu_per_step": B, "color_correction": args.color_correction,
                    "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
                    "parallelism": "frames sharded one-per-GPU (dp%d), NCCL gather of chunk records to rank 0" % world},
         "parity": parity + ("" if ok_flags else " (%d of %d frames/rank went through the exact flood-walk kernel)" % (n_fallback, B)),
-        # kernels of this library per step: K1, the four exact-walk-check kernels (list, raster, walk, colour), fused RS, chunk
-        # mask; color_correction 1 adds k_ccm_simple, 2 adds a second RS launch and k_ccm_fit / carry / apply
-        "gpu_launches": {0: 7, 1: 8, 2: 11}[args.color_correction] * K * world,
+        # kernels of this library launched inside the timed region, all ranks (counted at the launch sites, cb200_launch_count)
+        "gpu_launches": launches,
         "kernel_ms_per_step": {"k1_decode": stage_ms[0], "k1x_flood_check": stage_ms[1], "pack": stage_ms[2], "rs": stage_ms[3], "chunk_mask": stage_ms[4]},
         "roofline": {"kernel": "k1_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
@@ -303,7 +321,7 @@ def run_ours(args):
     if e2e:
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline_from_device_frames(frames, info)
+        out["cpu_baseline"] = cpu_baseline_from_device_frames(frames, info, MV, stage_ms[3] / B)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -321,21 +339,99 @@ def usable_cores():
     return cores
 
 
-def best_thread_count(ora, host, cores):
+def best_thread_count(ora, host, cores, mode_val=68):
     """the CPU arm gets the thread count it runs fastest with on this box (oversubscribed or throttled hosts
     run slower with one thread per logical core), probed on a small sample"""
     probe = host[:min(host.shape[0], max(64, 2 * cores))]
     best, best_fps = cores, 0.0
     for t in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
-        ora.bench_decode(68, probe[:t], t, 1)
-        secs, _ = ora.bench_decode(68, probe, t, 1)
+        ora.bench_decode(mode_val, probe[:t], t, 1)
+        secs, _ = ora.bench_decode(mode_val, probe, t, 1)
         fps = probe.shape[0] / secs
         if fps > best_fps * 1.03:
             best, best_fps = t, fps
     return best
 
 
-def cpu_baseline_from_device_frames(frames, info):
+def host_description():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model, "logical_cpus": os.cpu_count(), "usable_cores": usable_cores()}
+
+
+def cpu_stage_split(ora, mode_val, host):
+    """single-thread per-stage split of the CPU restatement: ms per frame"""
+    import ctypes as C
+    import numpy as np
+    L = ora.lib
+    L.cbo_stage_timing.argtypes = [C.c_int]
+    L.cbo_stage_times.argtypes = [C.POINTER(C.c_double)]
+    m = ora.mode(mode_val)
+    n = min(host.shape[0], 24)
+    ora.decode(m, host[0])
+    L.cbo_stage_timing(1)
+    t0 = time.perf_counter()
+    for f in range(n):
+        ora.decode(m, host[f])
+    total = time.perf_counter() - t0
+    st = (C.c_double * 4)()
+    L.cbo_stage_times(st)
+    L.cbo_stage_timing(0)
+    out = {"frames": n, "threads": 1, "total_ms_per_frame": total / n * 1e3,
+           "preprocess_ms": st[0] / n * 1e3, "symbol_walk_ms": st[1] / n * 1e3, "colour_ms": st[2] / n * 1e3,
+           "rs_ms": st[3] / n * 1e3, "wirehair_ms": None}
+    try:   # what OpenCV itself (the library the reference calls for this stage) needs on this host, one thread
+        import cv2
+        cv2.setNumThreads(1)
+        def pre(img):
+            return cv2.adaptiveThreshold(cv2.cvtColor(img, cv2.COLOR_RGB2GRAY), 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, 5, 0)
+        pre(host[0])
+        t0 = time.perf_counter()
+        for f in range(n):
+            pre(host[f])
+        out["opencv_cvtColor_adaptiveThreshold_ms"] = (time.perf_counter() - t0) / n * 1e3
+    except Exception:
+        out["opencv_cvtColor_adaptiveThreshold_ms"] = None
+    return out
+
+
+def rs_standalone(ora, mode_val, host, k2_ms_per_frame):
+    """the reference's own libcorrect (oracle/_ref, compiled unmodified) on exactly the RS blocks K2 gets, next to K2"""
+    import ctypes as C
+    import numpy as np
+    try:
+        from oracle_lib import Ref, _ptr
+        ref = Ref()
+    except Exception as e:
+        return {"unavailable": str(e)[:80]}
+    m = ora.mode(mode_val)
+    n = min(host.shape[0], 16)
+    raws = [ora.decode_raw(m, host[f]) for f in range(n)]
+    cap_sym = ora.capacity(m, m.symbol_bits) if not m.legacy_mode else ora.capacity(m)
+    out = np.zeros(16384, np.uint8)
+    def run():
+        for r in raws:
+            ref.lib.ref_rs_stream(m.ecc_bytes, m.ecc_block_size, _ptr(r[:cap_sym]), cap_sym, _ptr(out))
+            if r.size > cap_sym:
+                tail = np.ascontiguousarray(r[cap_sym:])
+                ref.lib.ref_rs_stream(m.ecc_bytes, m.ecc_block_size, _ptr(tail), tail.size, _ptr(out))
+    run()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        run()
+    cpu_ms = (time.perf_counter() - t0) / (reps * n) * 1e3
+    return {"libcorrect_reference_ms_per_frame_1thread": cpu_ms, "k2_ms_per_frame": k2_ms_per_frame,
+            "frames": n, "what": "reed_solomon_stream over the frame's symbol + colour streams (oracle/_ref = libcorrect compiled unmodified)"}
+
+
+def cpu_baseline_from_device_frames(frames, info, mode_val=68, k2_ms_per_frame=None):
     """the oracle (CPU port of the reference decode) timed on the host cores on a bounded sample of the same frames"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
@@ -343,13 +439,19 @@ def cpu_baseline_from_device_frames(frames, info):
     cores = usable_cores()
     S = int(min(frames.shape[0], max(64, 16 * cores)))
     host = frames[:S].cpu().numpy()
-    cores = best_thread_count(ora, host, cores)
-    ora.bench_decode(68, host[:cores], cores, 1)      # warm the per-thread malloc arenas
-    secs, _ = ora.bench_decode(68, host, cores, 1)
-    secs1, _ = ora.bench_decode(68, host[:max(8, S // cores)], 1, 1)
+    cores = best_thread_count(ora, host, cores, mode_val)
+    ora.bench_decode(mode_val, host[:cores], cores, 1)      # warm the per-thread malloc arenas
+    secs, _ = ora.bench_decode(mode_val, host, cores, 1)
+    n1 = max(8, S // cores)
+    secs1, _ = ora.bench_decode(mode_val, host[:n1], 1, 1)
     return {"value": S / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "single_thread_value": n1 / secs1,
             "sample": "%d of the same synthetic frames, full decode incl. RS, %d threads (one decoder per thread); "
-                      "single thread: %.1f frames/s" % (S, cores, max(8, S // cores) / secs1)}
+                      "single thread: %.1f frames/s" % (S, cores, n1 / secs1),
+            "build": "gcc -O3 -march=x86-64-v3 (AVX2), fused SIMD-friendly gray/box-threshold (oracle/Makefile)",
+            "host": host_description(),
+            "stages": cpu_stage_split(ora, mode_val, host),
+            "rs_standalone": rs_standalone(ora, mode_val, host, k2_ms_per_frame)}
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
@@ -361,33 +463,39 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     ora = Oracle()
-    m = ora.mode(68)
+    MV = args.mode
+    m = ora.mode(MV)
     cores = usable_cores()
     S = args.ref_sample or int(max(64, 8 * cores))
     rng = np.random.default_rng(0xC1B4)
     base = min(S, 64)
-    uniq = np.stack([ora.render_frame(m, ora.payload_to_cells(m, rng.integers(0, 256, 7500, dtype=np.uint8))) for _ in range(base)])
+    nbytes = (ora.capacity(m) // m.ecc_block_size) * (m.ecc_block_size - m.ecc_bytes)
+    uniq = np.stack([ora.render_frame(m, ora.payload_to_cells(m, rng.integers(0, 256, nbytes, dtype=np.uint8))) for _ in range(base)])
     frames = np.concatenate([uniq] * ((S + base - 1) // base))[:S]
     K, W = args.steps, max(args.warmup, 1)
-    cores = best_thread_count(ora, frames, cores)
+    cores = best_thread_count(ora, frames, cores, MV)
     for _ in range(W):
-        ora.bench_decode(68, frames, cores, 1)
+        ora.bench_decode(MV, frames, cores, 1)
     t0 = time.perf_counter()
     for _ in range(K):
-        ora.bench_decode(68, frames, cores, 1)
+        ora.bench_decode(MV, frames, cores, 1)
     dt = time.perf_counter() - t0
     value = S * K / dt
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "impl": "reference", "metric": metric_name(MV), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic (same generator family: random payload -> RS(155,125) -> tiles -> RGB8 frames)",
-        "config": {"workload": "BASELINE configs[1]: synthetic 1024x1024 mode-B frames through the full CPU decode "
-                               "(threshold, flood walk, colour, RS) -- bounded sample of %d frames per step" % S,
-                   "mode": "B (68)", "frames_per_step": S},
+        "data": "synthetic (same generator family: random payload -> RS -> tiles -> RGB8 frames)",
+        "config": {"workload": "BASELINE configs[1]: synthetic %dx%d mode-%s frames through the full CPU decode "
+                               "(threshold, flood walk, colour, RS) -- bounded sample of %d frames per step" % (
+                                   m.image_size_x, m.image_size_y, MODE_NAMES[MV], S),
+                   "mode": "%s (%d)" % (MODE_NAMES[MV], MV), "frames_per_step": S},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d frames per step, %d threads, one decoder per thread (the reference's own threading model); "
                                    "the reference's ./cimbar cannot be built here (needs C++ OpenCV), this is its CPU restatement "
-                                   "pinned to its SHA-256 goldens" % (S, cores)},
+                                   "pinned to its SHA-256 goldens" % (S, cores),
+                         "build": "gcc -O3 -march=x86-64-v3 (AVX2), fused SIMD-friendly gray/box-threshold (oracle/Makefile)",
+                         "host": host_description(),
+                         "stages": cpu_stage_split(ora, MV, frames)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))

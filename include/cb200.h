@@ -185,6 +185,9 @@ int cb200_encode_cells_dev(cb200_ctx* ctx, const uint8_t* d_payload, int n, uint
    the last 64 calls).  cb200_get_timing returns the milliseconds of the call `calls_back` calls ago (0 = last) in launch
    order: [0] K1 fused decode, [1] K1x exact-walk kernel, [2] pack, [3] RS, [4] chunk mask (decode_raw_dev stops after [2]) */
 int cb200_set_timing(cb200_ctx* ctx, int enable);
+/* kernels launched by this library in this process so far (every launch site counts itself): bench.py reports the
+   difference across its timed region as "gpu_launches" */
+unsigned long long cb200_launch_count(void);
 int cb200_get_timing(cb200_ctx* ctx, int calls_back, float* ms, int max_entries, int* n_entries);
 
 /* ---- rank-0 fountain ingest (host only, no GPU) ------------------------------------------------------------------

@@ -24,7 +24,7 @@ EXPORTS = [
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
-    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm",
+    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count",
 ]
 
 
@@ -86,6 +86,7 @@ def load_library():
     lib.cb200_sink_file_size.restype = C.c_int64
     lib.cb200_sink_file_size.argtypes = [vp, C.c_uint32]
     lib.cb200_sink_file_read.argtypes = [vp, C.c_uint32, u8p, C.c_uint64]
+    lib.cb200_launch_count.restype = C.c_ulonglong
     lib.cb200_selfcheck.argtypes = [C.c_int]
     lib.cb200_mode_info.argtypes = [C.c_int, C.POINTER(Info)]
     lib.cb200_interleave_indices.argtypes = [C.c_int, u16p]
@@ -96,6 +97,11 @@ def load_library():
 def _check(rc):
     if rc != 0:
         raise Cb200Error(f"cb200 error {rc}: {load_library().cb200_last_error().decode()}")
+
+
+def launch_count():
+    """kernels launched by libcb200 in this process so far"""
+    return int(load_library().cb200_launch_count())
 
 
 def mode_info(mode_val=68):

@@ -2,17 +2,20 @@
 
     python -m libcimbar_b200.build [--force]
 
-nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box with the repo snapshot."""
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels to the GPU box with the repo snapshot.
+Every .cu is compiled to its own object (in parallel, only when it or a header changed) and the objects are linked."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libcb200.so")
-SOURCES = ["api.cu", "k1_decode.cu", "k1x_flood.cu", "k2_rs.cu", "render.cu", "encode.cu", "host_sink.cu", "ccm.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+SOURCES = ["api.cu", "k1_decode.cu", "k1x_flood.cu", "k2_rs.cu", "render.cu", "encode.cu", "host_sink.cu", "ccm.cu",
+           "gather.cu", "deskew.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -22,23 +25,47 @@ def _nvcc():
     return "nvcc"
 
 
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "cb200.h"))
+    hs += [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))]
+    return hs
+
+
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cb200.h")] + \
-           [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))]
+    deps = [os.path.join(CSRC, s) for s in _sources()] + _headers()
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    jobs = []
+    for s in _sources():
+        src, obj = os.path.join(CSRC, s), os.path.join(OBJ, s[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append([_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj])
     if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+        for j in jobs:
+            print(" ".join(j))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as ex:
+        for rc in ex.map(lambda j: subprocess.call(j), jobs):
+            if rc != 0:
+                raise subprocess.CalledProcessError(rc, "nvcc")
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + \
+           [os.path.join(OBJ, s[:-3] + ".o") for s in _sources()] + ["-ldl"]
+    if verbose:
+        print(" ".join(link))
+    subprocess.check_call(link)
     return LIB
 
 

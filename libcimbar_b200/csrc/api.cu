@@ -9,6 +9,7 @@
 #include "render.cuh"
 #include "encode.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@ using namespace cb200;
 namespace {
 
 thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int fail_cuda(cudaError_t e, const char* what)
@@ -197,6 +199,8 @@ bool adjacency_consistent(const Mode& m, const std::vector<uint16_t>& adj)
 
 }  // namespace
 
+namespace cb200 { void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); } }
+
 struct cb200_ctx {
     Mode mode;
     int device = 0, max_frames = 0, sm_count = 0;
@@ -349,7 +353,8 @@ int upload_frames(cb200_ctx* c, const uint8_t* rgb, int n)
 extern "C" {
 
 const char* cb200_last_error(void) { return g_err.c_str(); }
-int cb200_version(void) { return 1; }
+int cb200_version(void) { return 2; }
+unsigned long long cb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int cb200_mode_info(int mode_val, cb200_info* out)
 {

@@ -7,6 +7,9 @@
 
 namespace cb200 {
 
+// kernel launches issued by this library in this process (cb200_launch_count): every `<<<>>>` is followed by count_launch()
+void count_launch(int n = 1);
+
 constexpr int kMaxCells = 12544;   // 112*112
 constexpr int kCellSize = 8;       // Config::cell_size() is constexpr 8 (Config.h:106-110)
 constexpr int kSpacing = 9;        // every 8x8 mode uses cell_size+1 (GridConf.h:121-189)

@@ -60,7 +60,7 @@ __global__ void k_ccm_simple(const Mode m, const uint8_t* __restrict__ rgb, int 
 
 cudaError_t ccm_simple_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, float* d_ccm, cudaStream_t st)
 {
-    k_ccm_simple<<<(n_frames + 63) / 64, 64, 0, st>>>(m, d_rgb, n_frames, d_ccm);
+    k_ccm_simple<<<(n_frames + 63) / 64, 64, 0, st>>>(m, d_rgb, n_frames, d_ccm); count_launch();
     return cudaGetLastError();
 }
 
@@ -401,20 +401,20 @@ k_ccm_apply(const Mode m, const uint32_t* __restrict__ means, int n_frames, cons
 cudaError_t ccm_fit_launch(const Mode& m, const uint8_t* d_rgb, const uint8_t* d_data, const uint8_t* d_ok, const uint16_t* d_idx,
                            int n_frames, float* d_fit, uint8_t* d_valid, cudaStream_t st)
 {
-    k_ccm_fit<<<(n_frames + 3) / 4, 128, 0, st>>>(m, d_rgb, d_data, d_ok, d_idx, n_frames, d_fit, d_valid);
+    k_ccm_fit<<<(n_frames + 3) / 4, 128, 0, st>>>(m, d_rgb, d_data, d_ok, d_idx, n_frames, d_fit, d_valid); count_launch();
     return cudaGetLastError();
 }
 cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_valid, const CcmArg& initial, float* d_used,
                              uint8_t* d_used_active, cudaStream_t st)
 {
-    k_ccm_carry<<<1, 1024, 0, st>>>(n_frames, d_fit, d_valid, initial, d_used, d_used_active);
+    k_ccm_carry<<<1, 1024, 0, st>>>(n_frames, d_fit, d_valid, initial, d_used, d_used_active); count_launch();
     return cudaGetLastError();
 }
 cudaError_t ccm_apply_launch(const Mode& m, const uint32_t* d_means, int n_frames, const float* d_used, const uint8_t* d_used_active,
                              uint8_t* d_cellvals, cudaStream_t st)
 {
     dim3 grid((unsigned)((m.num_cells + 255) / 256), (unsigned)(n_frames < 2048 ? n_frames : 2048));
-    k_ccm_apply<<<grid, 256, 0, st>>>(m, d_means, n_frames, d_used, d_used_active, d_cellvals);
+    k_ccm_apply<<<grid, 256, 0, st>>>(m, d_means, n_frames, d_used, d_used_active, d_cellvals); count_launch();
     return cudaGetLastError();
 }
 

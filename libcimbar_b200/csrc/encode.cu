@@ -82,11 +82,11 @@ cudaError_t encode_launch(const Mode& m, const uint8_t* d_gen, const uint16_t* d
                           uint8_t* d_raw, uint8_t* d_cellvals, cudaStream_t st)
 {
     long total = (long)n_frames * m.nblocks;
-    k_rs_encode<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(m, d_gen, d_payload, n_frames, d_raw);
+    k_rs_encode<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(m, d_gen, d_payload, n_frames, d_raw); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 grid((m.num_cells + 255) / 256, n_frames);
-    k_unpack_cells<<<grid, 256, 0, st>>>(m, d_raw, d_inv, n_frames, d_cellvals);
+    k_unpack_cells<<<grid, 256, 0, st>>>(m, d_raw, d_inv, n_frames, d_cellvals); count_launch();
     return cudaGetLastError();
 }
 

@@ -530,12 +530,12 @@ __global__ void k_best_colors(const Mode m, const uint8_t* __restrict__ rgb, int
 
 cudaError_t k1_symbols_launch(const uint16_t* d_windows, const uint8_t* d_cooldown, int n, uint8_t* d_sym, uint8_t* d_off, uint8_t* d_dist, cudaStream_t st)
 {
-    k_decode_symbols<<<(n + 127) / 128, 128, 0, st>>>(d_windows, d_cooldown, n, d_sym, d_off, d_dist);
+    k_decode_symbols<<<(n + 127) / 128, 128, 0, st>>>(d_windows, d_cooldown, n, d_sym, d_off, d_dist); count_launch();
     return cudaGetLastError();
 }
 cudaError_t k1_colors_launch(const Mode& m, const uint8_t* d_rgb, int n, uint8_t* d_color, const CcmArg& cc, cudaStream_t st)
 {
-    k_best_colors<<<(n + 127) / 128, 128, 0, st>>>(m, d_rgb, n, d_color, cc);
+    k_best_colors<<<(n + 127) / 128, 128, 0, st>>>(m, d_rgb, n, d_color, cc); count_launch();
     return cudaGetLastError();
 }
 
@@ -571,6 +571,7 @@ cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int ban
     else { if (g1024) CB200_K1_CM(4, true); else CB200_K1_CM(4, false); }
 #undef CB200_K1_CM
 #undef CB200_K1_GO
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -694,7 +694,7 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
     cudaError_t e = flood_workspace_ensure(m, ws, n_frames);
     if (e != cudaSuccess) return e;
     const int nchunks = (n_frames + ws.entry_cap - 1) / ws.entry_cap;
-    k_flood_list<<<1, 1024, 0, st>>>(d_dirty, n_frames, no_fallback ? 1 : 0, force_all ? 1 : 0, d_flags, ws.list, ws.counters, 1 + nchunks);
+    k_flood_list<<<1, 1024, 0, st>>>(d_dirty, n_frames, no_fallback ? 1 : 0, force_all ? 1 : 0, d_flags, ws.list, ws.counters, 1 + nchunks); count_launch();
     if (no_fallback) return cudaGetLastError();
     const int nb = (m.height + kBandRows - 1) / kBandRows;
     const size_t rs_bytes = raster_smem_bytes(m, sharpen);
@@ -705,13 +705,14 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         int rgrid = (int)(items < (long long)ws.sm_count * 3 ? items : (long long)ws.sm_count * 3);
         if (sharpen) k_flood_raster<true><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
         else k_flood_raster<false><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
+        count_launch();
         int wgrid = cap < ws.slots ? cap : ws.slots;
         k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
-                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace);
+                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace); count_launch();
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);
-        k_flood_colour<<<cgrid, 256, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.result, d_cellvals, cc);
+        k_flood_colour<<<cgrid, 256, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.result, d_cellvals, cc); count_launch();
     }
     return cudaGetLastError();
 }

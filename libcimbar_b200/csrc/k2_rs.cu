@@ -419,7 +419,7 @@ cudaError_t k2_init_tables(const uint8_t* exp512, const uint8_t* log256)
 cudaError_t k2_pack_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_raw, cudaStream_t st)
 {
     dim3 grid((m.cap_all + 255) / 256, n_frames);
-    k_pack_raw<<<grid, 256, 0, st>>>(m, d_cellvals, d_idx, n_frames, d_raw);
+    k_pack_raw<<<grid, 256, 0, st>>>(m, d_cellvals, d_idx, n_frames, d_raw); count_launch();
     return cudaGetLastError();
 }
 
@@ -438,7 +438,7 @@ static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_
     long max_ctas = (long)sm_count * (T == 1 ? 4 : 2);       // persistent: the table build is amortised over many blocks
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, b_begin, b_count, d_data, d_ok);
+    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, b_begin, b_count, d_data, d_ok); count_launch();
     return cudaGetLastError();
 }
 
@@ -457,7 +457,7 @@ cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const u
 
 cudaError_t k2_mask_launch(const Mode& m, const uint8_t* d_ok, int n_frames, uint32_t* d_mask, cudaStream_t st)
 {
-    k_chunk_mask<<<(n_frames + 127) / 128, 128, 0, st>>>(m, d_ok, n_frames, d_mask);
+    k_chunk_mask<<<(n_frames + 127) / 128, 128, 0, st>>>(m, d_ok, n_frames, d_mask); count_launch();
     return cudaGetLastError();
 }
 

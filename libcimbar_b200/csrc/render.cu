@@ -52,7 +52,7 @@ cudaError_t render_launch(const Mode& m, const uint8_t* d_cellvals, int n_frames
     cudaError_t e = cudaMemsetAsync(d_rgb, 0, (size_t)n_frames * m.width * m.height * 3, st);
     if (e != cudaSuccess) return e;
     long total = (long)n_frames * m.num_cells * 8;
-    k_render<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m, d_cellvals, n_frames, d_rgb);
+    k_render<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m, d_cellvals, n_frames, d_rgb); count_launch();
     return cudaGetLastError();
 }
 

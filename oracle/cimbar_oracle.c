@@ -3,10 +3,14 @@
  *
  * TEST INFRASTRUCTURE ONLY (see cimbar_oracle.h).  Plain C99, no dependencies.
  * Every function cites the reference file:line (relative to /root/reference/) it follows.
- * Build: see oracle/Makefile (-O2 -ffp-contract=off: the colour path is float32 and must
- * not be contracted into FMAs -- the reference is built -O2 for generic x86-64, CMakeLists.txt:22).
+ * Build: see oracle/Makefile (-O3 -march=x86-64-v3 -ffp-contract=off: the colour path is float32 and must
+ * not be contracted into FMAs; the reference itself is built -O2 for generic x86-64, CMakeLists.txt:22, but its
+ * preprocessing runs in OpenCV's SIMD kernels, so the restatement is compiled to vectorise as well).
  */
+#define _POSIX_C_SOURCE 200809L
 #include "cimbar_oracle.h"
+
+#include <time.h>
 
 #include <float.h>
 #include <math.h>
@@ -293,7 +297,95 @@ void cbo_pack_bits(const uint8_t* thr, size_t npix, uint8_t* bits)
     }
 }
 
+/* The same preprocessing as the four functions above, fused row by row for speed (the CPU arm of the benchmark should
+   not be slower than OpenCV's SIMD passes by construction): gray into a padded row, horizontal box sums as 2r+1 shifted
+   adds (vectorisable), a ring of the last 2r+1 rows of horizontal sums with one running column sum, the threshold in its
+   integer form  area * g > colsum + (area-1)/2  (== g > round(colsum / area): area is odd, so there is no tie), and the
+   MSB-first bit pack eight pixels at a time.  tests/test_oracle_goldens.py asserts this equals the unfused restatement
+   (which is what is pinned against cv2) on camera frames, synthetic frames and noise. */
+static void gray_row(const uint8_t* rgb, int w, uint8_t* out)
+{
+    for (int x = 0; x < w; ++x)
+        out[x] = (uint8_t)((9798u * rgb[3 * x] + 19235u * rgb[3 * x + 1] + 3735u * rgb[3 * x + 2] + 16384u) >> 15);
+}
+
+void cbo_threshold_bits_fast(const uint8_t* gray, int w, int h, int block, uint8_t* bits)
+{
+    const int r = block / 2;
+    const unsigned area = (unsigned)(block * block), half = (area - 1) / 2;
+    const int pw = w + 2 * r;
+    uint8_t* pad = (uint8_t*)malloc((size_t)pw + 16);
+    uint16_t* ring = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)w * (size_t)block);
+    uint16_t* col = (uint16_t*)calloc((size_t)w, sizeof(uint16_t));      /* <= 49 * 255 */
+    uint8_t* thr = (uint8_t*)malloc((size_t)w + 8);
+#define HROW_FAST(dst, yy) do { \
+        const uint8_t* row_ = gray + (size_t)(yy) * w; uint16_t* d_ = (dst); \
+        memcpy(pad + r, row_, (size_t)w); \
+        for (int k_ = 0; k_ < r; ++k_) { pad[k_] = row_[0]; pad[r + w + k_] = row_[w - 1]; } \
+        for (int x = 0; x < w; ++x) d_[x] = 0; \
+        for (int d = 0; d < block; ++d) { const uint8_t* p_ = pad + d; for (int x = 0; x < w; ++x) d_[x] = (uint16_t)(d_[x] + p_[x]); } \
+    } while (0)
+    for (int d = -r; d <= r; ++d) {
+        int yy = d < 0 ? 0 : (d >= h ? h - 1 : d);
+        uint16_t* slot = ring + (size_t)((d + r) % block) * w;
+        HROW_FAST(slot, yy);
+        for (int x = 0; x < w; ++x) col[x] = (uint16_t)(col[x] + slot[x]);
+    }
+    int next_slot = 0;
+    size_t bitpos = 0;                       /* rows are packed back to back (bitmatrix over the continuous Mat) */
+    uint8_t carry = 0; int carry_n = 0;      /* w need not be a multiple of 8 in general; every mode's width is */
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* g = gray + (size_t)y * w;
+        for (int x = 0; x < w; ++x) thr[x] = (uint8_t)(area * g[x] > (unsigned)col[x] + half);
+        int x = 0;
+        if (carry_n == 0) {
+            for (; x + 8 <= w; x += 8) {
+                uint64_t v; memcpy(&v, thr + x, 8);
+                bits[bitpos >> 3] = (uint8_t)((v * 0x8040201008040201ULL) >> 56);     /* byte k (0/1) -> bit 7-k */
+                bitpos += 8;
+            }
+        }
+        for (; x < w; ++x) {                 /* generic tail */
+            carry = (uint8_t)((carry << 1) | thr[x]); ++carry_n; ++bitpos;
+            if (carry_n == 8) { bits[(bitpos >> 3) - 1] = carry; carry = 0; carry_n = 0; }
+        }
+        if (y + 1 < h) {
+            uint16_t* slot = ring + (size_t)next_slot * w;
+            for (int xx = 0; xx < w; ++xx) col[xx] = (uint16_t)(col[xx] - slot[xx]);
+            int yin = y + 1 + r; if (yin >= h) yin = h - 1;
+            HROW_FAST(slot, yin);
+            for (int xx = 0; xx < w; ++xx) col[xx] = (uint16_t)(col[xx] + slot[xx]);
+            next_slot = (next_slot + 1) % block;
+        }
+    }
+#undef HROW_FAST
+    if (carry_n) {   /* bitmatrix.h:35-45 remainder quirk: val |= (p>0) << size, size counting down from rem */
+        uint8_t v = 0; int rem = carry_n;
+        for (int k = 0; k < rem; ++k) v |= (uint8_t)(((carry >> (rem - 1 - k)) & 1) << (rem - k));
+        bits[bitpos >> 3] = v;
+    }
+    free(pad); free(ring); free(col); free(thr);
+}
+
 void cbo_preprocess(const uint8_t* rgb, int w, int h, int needs_sharpen, uint8_t* bits)
+{
+    size_t n = (size_t)w * h;
+    uint8_t* gray = (uint8_t*)malloc(n);
+    for (int y = 0; y < h; ++y) gray_row(rgb + (size_t)y * w * 3, w, gray + (size_t)y * w);
+    int block = 5;
+    if (needs_sharpen) {
+        uint8_t* sh = (uint8_t*)malloc(n);
+        cbo_sharpen(gray, w, h, sh);
+        free(gray);
+        gray = sh;
+        block = 7;
+    }
+    cbo_threshold_bits_fast(gray, w, h, block, bits);
+    free(gray);
+}
+
+/* the unfused form (cvtColor -> [filter2D] -> adaptiveThreshold -> mat_to_bitbuffer as separate passes) */
+void cbo_preprocess_unfused(const uint8_t* rgb, int w, int h, int needs_sharpen, uint8_t* bits)
 {
     size_t n = (size_t)w * h;
     uint8_t* gray = (uint8_t*)malloc(n);
@@ -942,6 +1034,15 @@ int cbo_flood_walk_synthetic(const cbo_mode* m, unsigned seed, unsigned noise, u
 /* ------------------------------------------------------------------------------------------
  * Decoder::do_decode / do_decode_coupled with use_ecc = false -- Decoder.h:60-161
  * ---------------------------------------------------------------------------------------- */
+/* per-thread stage timers (benchmark reporting only): 0 preprocess, 1 symbol walk, 2 colour pass, 3 RS */
+static __thread int g_stage_on = 0;
+static __thread double g_stage_s[4];
+static double stage_now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+void cbo_stage_timing(int enable) { g_stage_on = enable; for (int i = 0; i < 4; ++i) g_stage_s[i] = 0; }
+void cbo_stage_times(double out[4]) { for (int i = 0; i < 4; ++i) out[i] = g_stage_s[i]; }
+#define STAGE_T0() double st0_ = g_stage_on ? stage_now() : 0
+#define STAGE_ADD(i) do { if (g_stage_on) { double t_ = stage_now(); g_stage_s[i] += t_ - st0_; st0_ = t_; } } while (0)
+
 static __thread void (*g_pre_color_hook)(const cbo_mode*, const uint8_t*, int, int, int, const uint8_t*) = NULL;
 
 int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sharpen,
@@ -977,7 +1078,9 @@ int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int need
         int padding = ((w - (int)m->image_size_x) < (h - (int)m->image_size_y) ? (w - (int)m->image_size_x) : (h - (int)m->image_size_y)) / 2;
         cbo_cell_positions(m, padding, xs, ys);
         uint8_t* bits = (uint8_t*)malloc((size_t)w * h / 8 + 16);
+        STAGE_T0();
         cbo_preprocess(rgb, w, h, needs_sharpen, bits);
+        STAGE_ADD(0);
 
         flood_t f;
         f.n = (int)ncells; f.count = 0;
@@ -1013,6 +1116,7 @@ int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int need
             }
             ++order;
         }
+        STAGE_ADD(1);
         free(f.heap.v); free(f.remaining); free(f.instr); free(bits);
     }
 
@@ -1022,12 +1126,14 @@ int cbo_decode_raw(const cbo_mode* m, const uint8_t* rgb, int w, int h, int need
 
     /* colour pass: Decoder.h:107-114 / :153-158.  colorPositions default to {i=0,x=0,y=0} when the reader
        was not good, so every entry ORs the colour at (0,0) into bit position 0. */
+    STAGE_T0();
     for (unsigned i = 0; i < ncells; ++i) {
         unsigned bitpos = have_pos[i] ? inv[i] * (m->legacy_mode ? bpc : m->color_bits) : 0;
         unsigned c = decode_color_at(m, rgb, w, cx[i], cy[i]);
         bb_write(col_buf, c, bitpos, (int)m->color_bits);
         if (cells && have_pos[i]) cells[i].color = (uint8_t)c;
     }
+    STAGE_ADD(2);
     free(xs); free(ys); free(cx); free(cy); free(have_pos); free(inv);
     return (int)cap_all;
 }
@@ -1344,6 +1450,7 @@ int cbo_decode(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sh
     if (!use_ecc || m->ecc_bytes == 0) { memcpy(out, raw, cap_all); free(raw); return (int)cap_all; }
     unsigned msg = m->ecc_block_size - m->ecc_bytes;
     unsigned total = 0;
+    STAGE_T0();
     if (m->legacy_mode) {
         unsigned nb = cap_all / m->ecc_block_size;
         cbo_rs_stream(m->ecc_bytes, m->ecc_block_size, raw, cap_all, out, block_ok);
@@ -1355,6 +1462,7 @@ int cbo_decode(const cbo_mode* m, const uint8_t* rgb, int w, int h, int needs_sh
         cbo_rs_stream(m->ecc_bytes, m->ecc_block_size, raw + cap_sym, cap_col, out + (size_t)nbs * msg, block_ok ? block_ok + nbs : NULL);
         total = (nbs + nbc) * msg;
     }
+    STAGE_ADD(3);
     free(raw);
     return (int)total;
 }

@@ -86,7 +86,12 @@ void cbo_adaptive_threshold(const uint8_t* gray, int w, int h, int block, uint8_
 /* bitmatrix::mat_to_bitbuffer (bitmatrix.h:14-46): MSB-first, 8 px / byte */
 void cbo_pack_bits(const uint8_t* thr, size_t npix, uint8_t* bits);
 /* whole P1 */
-void cbo_preprocess(const uint8_t* rgb, int w, int h, int needs_sharpen, uint8_t* bits /* w*h/8 */);
+void cbo_preprocess(const uint8_t* rgb, int w, int h, int needs_sharpen, uint8_t* bits /* w*h/8 */);   /* fused, fast */
+void cbo_preprocess_unfused(const uint8_t* rgb, int w, int h, int needs_sharpen, uint8_t* bits);          /* pass by pass */
+/* per-thread stage timers for the benchmark's per-stage split: [0] preprocess, [1] symbol walk, [2] colour, [3] RS (seconds) */
+void cbo_stage_timing(int enable);
+void cbo_stage_times(double out[4]);
+void cbo_threshold_bits_fast(const uint8_t* gray, int w, int h, int block, uint8_t* bits);
 
 /* P5: fuzzy_ahash<8>(bitmatrix) + ahash_result (average_hash.h:63-75, ahash_result.h:70-106).
    window origin (wx,wy) = (x-1,y-1); hashes[9], FAST leaves corners 0 */

@@ -126,6 +126,25 @@ def test_preprocess_matches_cv2():
         assert np.array_equal(np.unpackbits(ORA.preprocess(rgb, sharpen=True)).reshape(h, w) * 255, thr7)
 
 
+def test_fused_preprocess_equals_pass_by_pass_restatement():
+    # cbo_preprocess is the fused, vectorisable form the timing legs run; cbo_preprocess_unfused is cvtColor -> [filter2D] ->
+    # adaptiveThreshold -> mat_to_bitbuffer pass by pass.  Same bits on noise, synthetic frames and every mode's geometry.
+    import ctypes as C
+    from oracle_lib import _ptr, u8p
+    ORA.lib.cbo_preprocess_unfused.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p]
+    rng = np.random.default_rng(12)
+    m = ORA.mode(68)
+    cases = [rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8), rng.integers(0, 256, (637, 736, 3), dtype=np.uint8),
+             rng.integers(0, 256, (720, 1024, 3), dtype=np.uint8), np.full((64, 64, 3), 255, np.uint8),
+             ORA.render_frame(m, rng.integers(0, 64, m.total_cells, dtype=np.uint8))]
+    for rgb in cases:
+        h, w = rgb.shape[:2]
+        for sharpen in (False, True):
+            want = np.zeros(w * h // 8 + 16, np.uint8)
+            ORA.lib.cbo_preprocess_unfused(_ptr(rgb), w, h, int(sharpen), _ptr(want))
+            assert np.array_equal(ORA.preprocess(rgb, sharpen), want[: w * h // 8]), (rgb.shape, sharpen)
+
+
 # ---------------------------------------------------------------------------------------------- colour correction
 def _fmt_matx(mat):
     """operator<<(std::ostream&, cv::Matx<float,3,3>): "%.8g" elements, ", " / ";\n " separators"""
