@@ -42,6 +42,10 @@ def parse_args():
     ap.add_argument("--color-correction", type=int, default=0, choices=[0, 1, 2],
                     help="the reference's color_correction argument (0 = headline configuration; 1 = per-frame von Kries; "
                          "2 = per-frame header fit, the payload then carries consecutive fountain headers)")
+    ap.add_argument("--gather", default="window", choices=["window", "nccl", "torch"],
+                    help="N > 1: how the chunk records reach rank 0 -- window = the RS kernels store straight into rank 0's HBM over "
+                         "NVLink (CUDA IPC peer mapping, cb200_gather_slot/publish/wait); nccl = cb200_gather_chunks (ncclSend/Recv on a "
+                         "side stream, double buffered); torch = torch.distributed.gather on the decode stream (round-1 behaviour)")
     ap.add_argument("--e2e-frames", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,16 +193,51 @@ def run_ours(args):
     mask = torch.empty(B, dtype=torch.int32, device=dev)
     fflags = torch.empty(B, dtype=torch.uint8, device=dev)
     gather_chunks = gather_mask = None
-    if world > 1 and rank == 0:
-        gather_chunks = [torch.empty_like(chunks) for _ in range(world)]
-        gather_mask = [torch.empty_like(mask) for _ in range(world)]
+    exchange, gather_kind = None, None
+    if world > 1:
+        from libcimbar_b200.dist import RecordExchange
+        gather_kind = args.gather
+        if gather_kind == "window":
+            # every rank must agree on the path: fall back to NCCL everywhere if any rank cannot map the window
+            try:
+                exchange = RecordExchange(ctx, "window", B, rank, world)
+                okw = 1
+            except cb.Cb200Error as e:
+                print("bench.py: rank %d cannot use the NVLink window (%s); falling back to --gather nccl" % (rank, e), file=sys.stderr)
+                okw = 0
+            t = torch.tensor([okw], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                exchange, gather_kind = None, "nccl"
+        if gather_kind == "nccl":
+            exchange = RecordExchange(ctx, "nccl", B, rank, world)
+        if gather_kind == "torch" and rank == 0:
+            gather_chunks = [torch.empty_like(chunks) for _ in range(world)]
+            gather_mask = [torch.empty_like(mask) for _ in range(world)]
     torch.cuda.synchronize()
+    step_no = [0]
 
     def step():
-        ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr(), flags=cc_flags)
-        if world > 1:   # the one exchange of the path: decoded fountain chunk records -> rank 0 (wirehair ingest side)
-            dist.gather(chunks, gather_chunks, dst=0)
-            dist.gather(mask, gather_mask, dst=0)
+        # the one exchange of the path: decoded fountain chunk records -> rank 0 (wirehair ingest side)
+        if exchange is None:
+            ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr(), flags=cc_flags)
+            if world > 1:
+                dist.gather(chunks, gather_chunks, dst=0)
+                dist.gather(mask, gather_mask, dst=0)
+            return
+        step_no[0] += 1
+        sidx = step_no[0]
+        pc, pm = exchange.begin(sidx)          # window: this rank's slot in rank 0's HBM; nccl: a local send buffer
+        ctx.decode_chunks_dev(frames.data_ptr(), B, pc, pm, fflags.data_ptr(), flags=cc_flags)
+        exchange.end(sidx)
+        if rank == 0 and sidx > 1:             # the records of the previous step: complete while this step decodes
+            exchange.collect(sidx - 1)
+            exchange.release(sidx - 1)
+
+    def drain():
+        if exchange is not None and rank == 0 and step_no[0] > 0:
+            exchange.collect(step_no[0])
+            exchange.release(step_no[0])
 
     def barrier():
         if world > 1:
@@ -218,6 +257,7 @@ def run_ours(args):
     e0.record()
     for _ in range(K):
         step()
+    drain()                                          # rank 0: the last step's records have arrived too
     e1.record()
     launches = cb.launch_count() - launches0         # counted by the library at every launch site
     barrier()
@@ -232,16 +272,50 @@ def run_ours(args):
     sampler.join(timeout=1.0)
 
     # ---- parity of what was just timed (outside the timed region): every chunk decoded, bytes == payload
-    if world > 1:
-        t = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        launches = int(t.item())
+    gathered_ok = None
+    if exchange is not None:
+        import ctypes
+        cudart = ctypes.CDLL("libcudart.so.12")          # the copy torch already loaded
+
+        def dev_copy(ptr, nbytes):
+            """nbytes at raw device address `ptr` (a window slot / a library-owned buffer) into a fresh torch tensor"""
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            rc = cudart.cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(nbytes), 3)   # cudaMemcpyDeviceToDevice
+            assert rc == 0, "cudaMemcpy failed: %d" % rc
+            return t
+
+        last = step_no[0]
+        payloads = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+        dist.gather(payload, payloads, dst=0)
+        if rank == 0:
+            # what arrived on rank 0 for the last step, rank by rank, against that rank's payload
+            if gather_kind == "window":
+                ctx.gather_status()
+            got = []
+            for r in range(world):
+                if gather_kind == "window":
+                    pc, pm = ctx.gather_slot(last & 1, r)
+                    got.append((dev_copy(pc, B * info.data_bytes).view(B, info.data_bytes), dev_copy(pm, 4 * B).view(torch.int32)))
+                else:
+                    got.append((exchange.recv[last & 1][0][r], exchange.recv[last & 1][1][r]))
+            chunks, mask = got[0]
+            if args.workload == "clean":
+                full = (1 << info.chunks_per_frame) - 1
+                gathered_ok = all(bool((m_ == full).all().item()) and bool(torch.equal(c_, p_)) for (c_, m_), p_ in zip(got, payloads))
+        elif gather_kind == "nccl":
+            chunks, mask = exchange.send[last & 1]
+        else:   # a peer's records live in rank 0's HBM: decode once more into local buffers for this rank's own parity line
+            ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr(), flags=cc_flags)
+            torch.cuda.synchronize()
     ok_mask = bool((mask == (1 << info.chunks_per_frame) - 1).all().item())
     ok_data = bool(torch.equal(chunks, payload))
     n_fallback = int((fflags & 1).sum().item())
     ok_flags = not bool(fflags.any().item())
     if ok_mask and ok_data:
         parity = "bit-exact: %d frames/rank, all %d chunks/frame == payload" % (B, info.chunks_per_frame)
+        if gathered_ok is not None:
+            parity += "; records of all %d ranks as gathered on rank 0 == their payloads: %s" % (world, "yes" if gathered_ok else "NO (MISMATCH)")
     elif args.workload == "clean":
         parity = "MISMATCH mask_ok=%s data_ok=%s" % (ok_mask, ok_data)
     else:
@@ -306,7 +380,10 @@ def run_ours(args):
                        B, info.image_size_x, info.image_size_y, MODE_NAMES[MV], info.ecc_block_size, info.ecc_block_size - info.ecc_bytes),
                    "mode": "%s (%d)" % (MODE_NAMES[MV], MV), "frames_per_gpu_per_step": B, "color_correction": args.color_correction,
                    "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
-                   "parallelism": "frames sharded one-per-GPU (dp%d), NCCL gather of chunk records to rank 0" % world},
+                   "parallelism": "frames sharded one-per-GPU (dp%d); chunk records to rank 0 by %s" % (world, {
+                       None: "nothing (one GPU)", "window": "direct NVLink stores of the RS kernels into rank 0's HBM (CUDA IPC window, device-side epochs)",
+                       "nccl": "ncclSend/ncclRecv on a side stream (cb200_gather_chunks), double buffered",
+                       "torch": "torch.distributed.gather on the decode stream"}[gather_kind])},
         "parity": parity + ("" if ok_flags else " (%d of %d frames/rank went through the exact flood-walk kernel)" % (n_fallback, B)),
         # kernels of this library launched inside the timed region, all ranks (counted at the launch sites, cb200_launch_count)
         "gpu_launches": launches,

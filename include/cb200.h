@@ -190,6 +190,46 @@ int cb200_set_timing(cb200_ctx* ctx, int enable);
 unsigned long long cb200_launch_count(void);
 int cb200_get_timing(cb200_ctx* ctx, int calls_back, float* ms, int max_entries, int* n_entries);
 
+/* ---- multi-GPU: the chunk records of all ranks -> rank 0 ------------------------------------------------------------
+
+   Replaces: the many-decoders -> one-sink hand-over of concurrent_fountain_decoder_sink
+   (src/lib/fountain/concurrent_fountain_decoder_sink.h:58-84), for one process per GPU (frames shard f % world).
+
+   (1) NVLink window.  Rank 0 allocates a double-buffered window in its HBM (cb200_gather_root_create) and hands the 64-byte
+   CUDA IPC handle to the other ranks by any host channel; they map it (cb200_gather_peer_open: peer access over NVLink).
+   cb200_gather_slot returns, per buffer, where THIS rank's decode must write: pass the pointers to cb200_decode_chunks_dev and
+   the RS / chunk-mask kernels store their results straight into rank 0's memory while they compute -- no separate copy or
+   collective.  After the decode a rank publishes an epoch (cb200_gather_publish: system-scope release store, enqueued on the
+   context's stream); rank 0 enqueues cb200_gather_wait(buffer, epoch) (system-scope acquire spin over all ranks, bounded by
+   timeout_s; cb200_gather_status reports a rank that never arrived) and then reads the window: cb200_gather_slot(ctx, buffer,
+   rank, ...) on rank 0 addresses any rank's records.  Frames per rank must be <= the max_frames the contexts were created with
+   (the same on every rank).  Back-pressure for the double buffer, also on the device: when rank 0 is done with buffer b of
+   epoch e it enqueues cb200_gather_release(b, e); a rank enqueues cb200_gather_acquire(b, e) before the decode that overwrites
+   buffer b (epochs are the caller's step counter, starting at 1 and increasing; step s uses buffer s & 1). */
+#define CB200_IPC_HANDLE_BYTES 64
+int cb200_gather_root_create(cb200_ctx* ctx, int nranks, uint8_t* handle_out /* CB200_IPC_HANDLE_BYTES */);
+int cb200_gather_peer_open(cb200_ctx* ctx, int nranks, int rank, const uint8_t* handle);
+int cb200_gather_slot(cb200_ctx* ctx, int buffer /* 0 | 1 */, int rank /* < 0: this rank */, uint8_t** d_chunks, uint32_t** d_mask);
+int cb200_gather_publish(cb200_ctx* ctx, int buffer, uint32_t epoch);
+int cb200_gather_wait(cb200_ctx* ctx, int buffer, uint32_t epoch, double timeout_s /* <= 0: 30 s */);
+int cb200_gather_release(cb200_ctx* ctx, int buffer, uint32_t epoch);                    /* rank 0 */
+int cb200_gather_acquire(cb200_ctx* ctx, int buffer, uint32_t epoch, double timeout_s);  /* any rank (no-op on rank 0) */
+int cb200_gather_status(cb200_ctx* ctx);   /* rank 0, synchronises: 0, or an error naming the rank that timed out */
+
+/* (2) NCCL.  cb200_gather_chunks sends n records of this rank to rank 0 (ncclSend / ncclRecv, grouped) on a side stream of
+   the context, ordered after the work already enqueued on the context's stream; the next decode can be enqueued at once and
+   overlaps the exchange.  cb200_gather_chunks_wait(buffer) makes the context's stream wait for the last exchange issued with that
+   buffer index (before its send buffers are reused / its gathered data is read): with two buffers the exchange of step s
+   overlaps the decode of step s + 1.  nccl_comm: the host's ncclComm_t, or NULL to use the communicator made by
+   cb200_comm_init (ncclGetUniqueId on rank 0 -> out-of-band broadcast -> ncclCommInitRank on every rank).  NCCL is bound at
+   run time (dlopen libnccl.so.2); d_all_chunks / d_all_masks (rank 0): nranks x n records, rank-major. */
+#define CB200_UNIQUE_ID_BYTES 128
+int cb200_comm_unique_id(uint8_t* id_out /* CB200_UNIQUE_ID_BYTES */);
+int cb200_comm_init(cb200_ctx* ctx, const uint8_t* id, int nranks, int rank);
+int cb200_gather_chunks(cb200_ctx* ctx, void* nccl_comm, int nranks, int rank, int buffer /* 0 | 1 */, const uint8_t* d_chunks,
+                        const uint32_t* d_mask, int n, uint8_t* d_all_chunks, uint32_t* d_all_masks);
+int cb200_gather_chunks_wait(cb200_ctx* ctx, int buffer);
+
 /* ---- rank-0 fountain ingest (host only, no GPU) ------------------------------------------------------------------
 
    Replaces: fountain_decoder_sink::decode_frame -> fountain_decoder_stream::write -> FountainDecoder::decode

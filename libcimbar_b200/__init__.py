@@ -25,6 +25,9 @@ EXPORTS = [
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
     "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count",
+    "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_wait",
+    "cb200_gather_release", "cb200_gather_acquire",
+    "cb200_gather_status", "cb200_comm_unique_id", "cb200_comm_init", "cb200_gather_chunks", "cb200_gather_chunks_wait",
 ]
 
 
@@ -87,6 +90,18 @@ def load_library():
     lib.cb200_sink_file_size.argtypes = [vp, C.c_uint32]
     lib.cb200_sink_file_read.argtypes = [vp, C.c_uint32, u8p, C.c_uint64]
     lib.cb200_launch_count.restype = C.c_ulonglong
+    lib.cb200_gather_root_create.argtypes = [vp, C.c_int, u8p]
+    lib.cb200_gather_peer_open.argtypes = [vp, C.c_int, C.c_int, u8p]
+    lib.cb200_gather_slot.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.cb200_gather_publish.argtypes = [vp, C.c_int, C.c_uint32]
+    lib.cb200_gather_wait.argtypes = [vp, C.c_int, C.c_uint32, C.c_double]
+    lib.cb200_gather_release.argtypes = [vp, C.c_int, C.c_uint32]
+    lib.cb200_gather_acquire.argtypes = [vp, C.c_int, C.c_uint32, C.c_double]
+    lib.cb200_gather_status.argtypes = [vp]
+    lib.cb200_comm_unique_id.argtypes = [u8p]
+    lib.cb200_comm_init.argtypes = [vp, u8p, C.c_int, C.c_int]
+    lib.cb200_gather_chunks.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, u8p, u32p, C.c_int, u8p, u32p]
+    lib.cb200_gather_chunks_wait.argtypes = [vp, C.c_int]
     lib.cb200_selfcheck.argtypes = [C.c_int]
     lib.cb200_mode_info.argtypes = [C.c_int, C.POINTER(Info)]
     lib.cb200_interleave_indices.argtypes = [C.c_int, u16p]
@@ -102,6 +117,13 @@ def _check(rc):
 def launch_count():
     """kernels launched by libcb200 in this process so far"""
     return int(load_library().cb200_launch_count())
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library's run-time NCCL binding: 128 bytes to broadcast to the other ranks"""
+    h = (C.c_uint8 * 128)()
+    _check(load_library().cb200_comm_unique_id(C.cast(h, C.c_void_p)))
+    return bytes(h)
 
 
 def mode_info(mode_val=68):
@@ -243,6 +265,47 @@ class Context:
         n = C.c_int(0)
         _check(self.lib.cb200_get_timing(self._h, calls_back, ms, 8, C.byref(n)))
         return [ms[i] for i in range(n.value)]
+
+    # ---- multi-GPU chunk-record exchange (cb200_gather_*): see include/cb200.h
+    def gather_root_create(self, nranks):
+        h = (C.c_uint8 * 64)()
+        _check(self.lib.cb200_gather_root_create(self._h, nranks, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def gather_peer_open(self, nranks, rank, handle):
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(self.lib.cb200_gather_peer_open(self._h, nranks, rank, C.cast(h, C.c_void_p)))
+
+    def gather_slot(self, buffer, rank=-1):
+        """device addresses (chunks, masks) of `rank`'s records in window buffer `buffer` (rank < 0: this rank's own slot)"""
+        pc, pm = C.c_void_p(), C.c_void_p()
+        _check(self.lib.cb200_gather_slot(self._h, buffer, rank, C.byref(pc), C.byref(pm)))
+        return pc.value, pm.value
+
+    def gather_publish(self, buffer, epoch):
+        _check(self.lib.cb200_gather_publish(self._h, buffer, epoch))
+
+    def gather_wait(self, buffer, epoch, timeout_s=30.0):
+        _check(self.lib.cb200_gather_wait(self._h, buffer, epoch, timeout_s))
+
+    def gather_release(self, buffer, epoch):
+        _check(self.lib.cb200_gather_release(self._h, buffer, epoch))
+
+    def gather_acquire(self, buffer, epoch, timeout_s=30.0):
+        _check(self.lib.cb200_gather_acquire(self._h, buffer, epoch, timeout_s))
+
+    def gather_status(self):
+        _check(self.lib.cb200_gather_status(self._h))
+
+    def comm_init(self, uid, nranks, rank):
+        h = (C.c_uint8 * 128).from_buffer_copy(uid)
+        _check(self.lib.cb200_comm_init(self._h, C.cast(h, C.c_void_p), nranks, rank))
+
+    def gather_chunks(self, nranks, rank, buffer, d_chunks, d_mask, n, d_all_chunks=None, d_all_masks=None, comm=None):
+        _check(self.lib.cb200_gather_chunks(self._h, comm, nranks, rank, buffer, d_chunks, d_mask, n, d_all_chunks, d_all_masks))
+
+    def gather_chunks_wait(self, buffer):
+        _check(self.lib.cb200_gather_chunks_wait(self._h, buffer))
 
     def render_frames_dev(self, d_cellvals, n, d_rgb_out):
         _check(self.lib.cb200_render_frames_dev(self._h, d_cellvals, n, d_rgb_out))

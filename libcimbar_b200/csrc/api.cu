@@ -1,10 +1,8 @@
 // api.cu -- the C ABI of libcb200.so (include/cb200.h): context, tables, and the kernel pipelines.
 // There is no CPU decode path in this library: every entry point that produces decode results launches the
 // sm_100a kernels, and cb200_create fails with CB200_ERR_NODEVICE when no CUDA device is usable.
-#include "../../include/cb200.h"
-#include "cb200_common.cuh"
+#include "ctx.cuh"
 #include "k1_decode.cuh"
-#include "k1x_flood.cuh"
 #include "k2_rs.cuh"
 #include "render.cuh"
 #include "encode.cuh"
@@ -24,13 +22,16 @@ namespace {
 thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
 
+}  // namespace
+namespace cb200 {
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int fail_cuda(cudaError_t e, const char* what)
 {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return CB200_ERR_CUDA;
 }
-#define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail_cuda(e__, what); } while (0)
+}  // namespace cb200
+namespace {
 
 // tile dictionary = CimbDecoder::_tileHashes for symbol_bits=4, dark (src/lib/cimb_translator/CimbDecoder.cpp:87-99),
 // i.e. average_hash of bitmap/4/00..0f.png; values pinned by src/lib/image_hash/test/averageHashTest.cpp:43-50.
@@ -101,20 +102,24 @@ bool mode_init(Mode& m, int mode_val)
     // layout invariants the kernels rely on (true for every 8x8 mode in GridConf.h)
     if (m.cap_sym % m.ecc_block || m.cap_all % m.ecc_block || m.chunk_size % m.msg_len || m.width % 8 || (m.width * 3) % 16) return false;
     if (m.nblocks * m.msg_len != m.chunks_per_frame * m.chunk_size) return false;
-    // perfect hash over the little-endian tile words: slot = (L_lo * mul) >> 28 distinct for the 16 tiles
-    uint32_t x = 0x2545F491u;
-    m.hash_mul = 0;
-    for (int trial = 0; trial < 50000000 && !m.hash_mul; ++trial) {
-        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
-        uint32_t mul = x | 1u, seen = 0;
-        bool ok = true;
-        for (int t = 0; t < 16 && ok; ++t) {
-            uint32_t slot = ((uint32_t)brev64(kTilesH[t]) * mul) >> 28;
-            if (seen & (1u << slot)) ok = false;
-            seen |= 1u << slot;
+    // perfect hash over the little-endian tile words: slot = (L_lo * mul) >> 28 distinct for the 16 tiles (the dictionary
+    // is the same in every mode: searched once per process)
+    static const uint32_t hash_mul = [] {
+        uint32_t x = 0x2545F491u;
+        for (int trial = 0; trial < 50000000; ++trial) {
+            x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+            uint32_t mul = x | 1u, seen = 0;
+            bool ok = true;
+            for (int t = 0; t < 16 && ok; ++t) {
+                uint32_t slot = ((uint32_t)brev64(kTilesH[t]) * mul) >> 28;
+                if (seen & (1u << slot)) ok = false;
+                seen |= 1u << slot;
+            }
+            if (ok) return mul;
         }
-        if (ok) m.hash_mul = mul;
-    }
+        return 0u;
+    }();
+    m.hash_mul = hash_mul;
     fill_palette(1 << m.color_bits, m.color_mode, m.palette);
     for (int i = 0; i < 8; ++i) {
         const int p0 = (int)m.palette[i][0] - (int)m.palette[i][1], p1 = (int)m.palette[i][1] - (int)m.palette[i][2],
@@ -201,50 +206,6 @@ bool adjacency_consistent(const Mode& m, const std::vector<uint16_t>& adj)
 
 namespace cb200 { void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); } }
 
-struct cb200_ctx {
-    Mode mode;
-    int device = 0, max_frames = 0, sm_count = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    // device workspaces
-    uint8_t* d_rgb = nullptr;        // host-pointer entry points only: max_frames frames
-    uint8_t* d_cellvals = nullptr;   // max_frames * num_cells
-    uint32_t* d_dirty = nullptr;     // max_frames
-    uint8_t* d_raw = nullptr;        // max_frames * cap_all
-    uint8_t* d_data = nullptr;       // max_frames * data_bytes
-    uint8_t* d_ok = nullptr;         // max_frames * nblocks
-    uint32_t* d_mask = nullptr;      // max_frames
-    uint8_t* d_flags = nullptr;      // max_frames
-    uint16_t* d_idx = nullptr;       // num_cells: slot -> cell (Interleave::interleave_indices)
-    uint16_t* d_inv = nullptr;       // num_cells: cell -> slot (Interleave::interleave_reverse)
-    uint8_t* d_gen = nullptr;        // RS generator polynomial, ecc_bytes+1 coefficients
-    // per-kernel timing (cb200_set_timing): events around every launch of the last pipeline call
-    int l2_ahead = 0;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)
-    int k1_ctas_per_sm = 4;          // K1: resident CTAs per SM the grid is sized for (CB200_K1_CTAS_PER_SM, tuning only)
-    bool timing = false;
-    static constexpr int kEvSets = 64;
-    cudaEvent_t ev[kEvSets][8] = {};
-    int ev_count[kEvSets] = {};
-    long calls = 0;                  // pipeline calls since timing was enabled
-    int cur = 0;                     // event set of the call in progress
-    FloodWorkspace flood;            // exact-walk fallback scratch
-    // small scratch for the single-cell entry points
-    void* d_scratch = nullptr; size_t scratch_bytes = 0;
-    // pinned host staging for results of the host-pointer entry points
-    uint8_t* h_pinned = nullptr; size_t h_pinned_bytes = 0;
-    // colour correction (the reference's thread-local CimbDecoder CCM, CimbDecoder.cpp:69-85)
-    float ccm[9] = {};               // active matrix, row-major
-    bool ccm_active = false;
-    bool ccm_pending = false;        // the last CC_SIMPLE batch's final matrix is still on its way to h_ccm
-    bool ccm_pending_flag = false;   // ... and so is whether that frame had a CCM at all (CC_FIT batches)
-    float* d_ccm = nullptr;          // per-frame matrices of a CC_SIMPLE / CC_FIT batch (the ones used): max_frames x 9
-    float* h_ccm = nullptr;          // pinned: 9 floats + 1 activity byte (at float index 9)
-    // CC_FIT scratch: per-cell mean colours of the first pass, per-frame fits
-    uint32_t* d_means = nullptr;     // max_frames x num_cells
-    float* d_fit = nullptr;          // max_frames x 9
-    uint8_t* d_fit_valid = nullptr;  // max_frames
-    uint8_t* d_ccm_active = nullptr; // max_frames: the frame is decoded with d_ccm[f]
-};
-
 namespace {
 
 int ensure_scratch(cb200_ctx* c, size_t bytes)
@@ -273,7 +234,8 @@ int check_n(const cb200_ctx* c, int n)
 int ccm_resolve(cb200_ctx* c)
 {
     if (!c->ccm_pending) return CB200_OK;
-    CK(cudaStreamSynchronize(c->stream), "sync (ccm)");
+    // the copies were enqueued on whatever stream was current then (cb200_set_stream may have changed it since)
+    CK(cudaEventSynchronize(c->ccm_ev), "sync (ccm)");
     memcpy(c->ccm, c->h_ccm, sizeof(c->ccm));
     if (c->ccm_pending_flag) c->ccm_active = reinterpret_cast<const uint8_t*>(c->h_ccm + 9)[0] != 0;
     c->ccm_pending = c->ccm_pending_flag = false;
@@ -292,6 +254,7 @@ int ccm_buffers(cb200_ctx* c)
 {
     if (!c->d_ccm) CK(cudaMalloc(&c->d_ccm, sizeof(float) * 9 * (size_t)c->max_frames), "cudaMalloc ccm");
     if (!c->h_ccm) CK(cudaMallocHost(&c->h_ccm, sizeof(float) * 12), "cudaMallocHost ccm");
+    if (!c->ccm_ev) CK(cudaEventCreateWithFlags(&c->ccm_ev, cudaEventDisableTiming), "cudaEventCreate ccm");
     return CB200_OK;
 }
 
@@ -312,6 +275,7 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTra
         cc.per_frame = c->d_ccm; cc.active = 1;
         // the decoder keeps the last matrix it was given (CimbDecoder.cpp:82-85)
         CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, st), "D2H ccm");
+        CK(cudaEventRecord(c->ccm_ev, st), "record ccm");
         c->ccm_pending = true; c->ccm_pending_flag = false; c->ccm_active = true;
     } else {
         int rc = ccm_arg(c, cc); if (rc) return rc;
@@ -386,25 +350,17 @@ int cb200_interleave_indices(int mode_val, uint16_t* idx)
     return CB200_OK;
 }
 
-int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
+// everything of cb200_create that can fail after the context object exists: the caller destroys `c` on any error
+static int create_impl(cb200_ctx* c, int device, int mode_val, int max_frames)
 {
-    if (!out || max_frames < 1) return fail(CB200_ERR_ARG, "bad arguments");
-    *out = nullptr;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(CB200_ERR_NODEVICE, "no CUDA device: libcb200 has no CPU fallback");
-    if (device < 0) { CK(cudaGetDevice(&device), "cudaGetDevice"); }
-    if (device >= ndev) return fail(CB200_ERR_ARG, "device index out of range");
-    CK(cudaSetDevice(device), "cudaSetDevice");
-    cb200_ctx* c = new cb200_ctx();
-    if (!mode_init(c->mode, mode_val)) { delete c; return fail(CB200_ERR_MODE, "unsupported mode_val"); }
+    if (!mode_init(c->mode, mode_val)) return fail(CB200_ERR_MODE, "unsupported mode_val");
     const Mode& m = c->mode;
     c->device = device; c->max_frames = max_frames;
     if (const char* e = getenv("CB200_K1_L2_AHEAD")) c->l2_ahead = atoi(e);
     if (const char* e = getenv("CB200_K1_CTAS_PER_SM")) c->k1_ctas_per_sm = atoi(e);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
-    if (prop.major < 10) { delete c; return fail(CB200_ERR_NODEVICE, "libcb200 is built for sm_100a only"); }
+    if (prop.major < 10) return fail(CB200_ERR_NODEVICE, "libcb200 is built for sm_100a only");
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     c->stream = c->own_stream;
@@ -459,13 +415,33 @@ int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
         CK(cudaMalloc(&c->d_gen, g.size()), "cudaMalloc gen");
         CK(cudaMemcpy(c->d_gen, g.data(), g.size(), cudaMemcpyHostToDevice), "upload gen");
         CK(encode_init_tables(gexp, glog), "encode tables");
-        for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[k][i]), "cudaEventCreate");
     }
     {
         std::vector<uint16_t> adj;
         build_adjacency(m, adj);
-        if (!adjacency_consistent(m, adj)) { cb200_destroy(c); return fail(CB200_ERR_MODE, "adjacency self-check failed"); }
+        if (!adjacency_consistent(m, adj)) return fail(CB200_ERR_MODE, "adjacency self-check failed");
         CK(flood_workspace_create(m, c->sm_count, adj.data(), &c->flood), "flood workspace");
+    }
+    return CB200_OK;
+}
+
+int cb200_create(cb200_ctx** out, int device, int mode_val, int max_frames)
+{
+    if (!out || max_frames < 1) return fail(CB200_ERR_ARG, "bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(CB200_ERR_NODEVICE, "no CUDA device: libcb200 has no CPU fallback");
+    if (device < 0) { CK(cudaGetDevice(&device), "cudaGetDevice"); }
+    if (device >= ndev) return fail(CB200_ERR_ARG, "device index out of range");
+    CK(cudaSetDevice(device), "cudaSetDevice");
+    cb200_ctx* c = new cb200_ctx();
+    c->device = device;
+    int rc = create_impl(c, device, mode_val, max_frames);
+    if (rc != CB200_OK) {            // one cleanup path: whatever was allocated so far is released (cb200_last_error keeps the cause)
+        std::string why = cb200_last_error();
+        cb200_destroy(c);
+        return fail(rc, why);
     }
     *out = c;
     return CB200_OK;
@@ -481,6 +457,9 @@ int cb200_destroy(cb200_ctx* c)
     flood_workspace_destroy(&c->flood);
     cudaFree(c->d_ccm); cudaFree(c->d_means); cudaFree(c->d_fit); cudaFree(c->d_fit_valid); cudaFree(c->d_ccm_active);
     if (c->h_ccm) cudaFreeHost(c->h_ccm);
+    if (c->ccm_ev) cudaEventDestroy(c->ccm_ev);
+    gather_destroy(c->gather);
+    deskew_destroy(c->deskew);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -567,6 +546,7 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
         // the decoder keeps the CCM of the last frame (and whether there is one at all)
         CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, c->stream), "D2H ccm");
         CK(cudaMemcpyAsync(c->h_ccm + 9, c->d_ccm_active + (n - 1), 1, cudaMemcpyDeviceToHost, c->stream), "D2H ccm flag");
+        CK(cudaEventRecord(c->ccm_ev, c->stream), "record ccm");
         c->ccm_pending = true; c->ccm_pending_flag = true;
     }
     mark(c);                                   // ev4: after RS
@@ -727,6 +707,10 @@ int cb200_encode_cells_dev(cb200_ctx* c, const uint8_t* d_payload, int n, uint8_
 int cb200_set_timing(cb200_ctx* c, int enable)
 {
     if (!c) return fail(CB200_ERR_ARG, "null context");
+    if (enable && !c->ev[0][0]) {    // the 512 events are only created for callers that measure
+        CK(cudaSetDevice(c->device), "cudaSetDevice");
+        for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[k][i]), "cudaEventCreate");
+    }
     c->timing = enable != 0;
     c->calls = 0; c->cur = 0;
     for (int k = 0; k < cb200_ctx::kEvSets; ++k) c->ev_count[k] = 0;

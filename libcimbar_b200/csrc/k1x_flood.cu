@@ -12,12 +12,17 @@
 //
 // Four kernels per batch; clean batches cost four empty launches:
 //   k_flood_list    compacts the frames K1 flagged into a work list (one CTA, order-preserving)
-//   k_flood_raster  threshold raster of every listed frame, fully parallel: one CTA per 16-row band, gray / sharpen /
-//                   box sums staged in shared memory with OpenCV's border rules, 1 bit per pixel to global memory
-//   k_flood_walk    the serial 12 400-step walk, ONE WARP PER FRAME, seven frames per SM in flight (the walk is a chain
+//   k_flood_raster_fast  threshold raster of every listed frame: one CTA per 64-row band, 8 px per thread, K1's packed-16
+//                   SIMD arithmetic (IDP.2A gray, separable 5x5 box sum, one IMAD per pixel pair) with OpenCV's replicate
+//                   borders, rolling vertical sums in registers; output in 16x16-pixel TILES (32 B = one sector each) so that
+//                   a 10x10 window of the walk touches at most four sectors.  (k_flood_raster<true> is the sharpen variant:
+//                   3x3 sharpen + block 7, staged in shared memory; same tiled output.)
+//   k_flood_walk    the serial 12 400-step walk, ONE WARP PER FRAME, up to 32 frames per SM in flight (the walk is a chain
 //                   of dependent heap and window accesses, so throughput comes from walking many frames at once):
-//                   binary heap in shared memory (+ global spill), the drift/cooldown a cell inherits travels inside the
-//                   32-bit heap entry, so the only per-cell state is one priority byte in shared memory
+//                   binary heap in shared memory (+ global spill); the sift-down of a pop resolves FIVE heap levels per
+//                   memory round trip (31 lanes load the child pairs of a 5-level subtree, one ballot, every lane checks
+//                   its ancestors' bits); the drift/cooldown a cell inherits travels inside the 32-bit heap entry, so the
+//                   only per-cell state is one priority byte in L2 and a bitmap in shared memory
 //   k_flood_colour  colours at the recorded drift-adjusted positions, one thread per cell
 #include "cb200_common.cuh"
 #include "k1x_flood.cuh"
@@ -91,13 +96,22 @@ __device__ __forceinline__ uint32_t spread16(uint32_t v)
     return v;
 }
 
+// ---------------------------------------------------------------------------------------------- tiled raster
+// 1 bit per pixel in tiles of 16 x 16 pixels: tile (ty, tx) is 16 consecutive uint16 (32 bytes, one DRAM/L2 sector), word r
+// of a tile holds row 16 ty + r, bit b of it is pixel 16 tx + b.  A 16-row band of the frame is one contiguous run of 2 W bytes.
+__host__ __device__ __forceinline__ size_t raster_words16(int W, int H) { return (size_t)(W >> 4) * (size_t)((H + 15) >> 4) * 16u + 64u; }
+__device__ __forceinline__ uint32_t raster_tile_index(int tiles_x, int x, int y)
+{
+    return ((uint32_t)(y >> 4) * (uint32_t)tiles_x + (uint32_t)(x >> 4)) * 16u + (uint32_t)(y & 15);
+}
+
 // One CTA per (listed frame, band of kBandRows rows): gray -> (optionally sharpened) gray -> horizontal box sums ->
 // threshold bits.  Everything a band needs (R rows of halo, +1 for the sharpen kernel) is staged in shared memory;
 // gray and the horizontal sums handle four pixels per thread, the vertical pass slides a packed 2x16-bit column sum.
 template <bool SHARPEN>
 __global__ void __launch_bounds__(kRasterThreads)
 k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
-               int base, int cap, uint32_t* __restrict__ ws_raster)
+               int base, int cap, uint16_t* __restrict__ ws_raster)
 {
     extern __shared__ __align__(16) uint8_t raster_smem[];
     constexpr int R = SHARPEN ? 3 : 2;                 // block size 7 after sharpening, else 5 (CimbReader.cpp:37-45)
@@ -110,7 +124,7 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
     uint8_t* g2 = g + rows_g * W;
     uint16_t* hs = reinterpret_cast<uint16_t*>(g2 + (SHARPEN ? rows_h * W : 0));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wq = W / 4, nseg = W / 32;
+    const int wq = W / 4;
     constexpr int kWarps = kRasterThreads / 32;
 
     for (int item = blockIdx.x; item < cnt * nb; item += gridDim.x) {
@@ -190,7 +204,7 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
         __syncthreads();
         // ---- adaptiveThreshold(MEAN_C, BINARY, bs, C=0): src > round(sum / bs^2)  <=>  bs^2 * src > sum + (bs^2 - 1) / 2
         // a warp owns a 64-pixel column segment (two pixels per lane) and slides the vertical sum down the band's rows
-        uint32_t* raster = ws_raster + (size_t)e * (npx / 32 + 4);
+        uint16_t* raster = ws_raster + (size_t)e * raster_words16(W, H);
         const uint32_t* hs32 = reinterpret_cast<const uint32_t*>(hs);
         const int wh = W / 2;
         for (int seg = warp; seg < (W + 63) / 64; seg += kWarps) {
@@ -205,120 +219,248 @@ k_flood_raster(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __
                 const bool b0 = act && area * (sp & 0xFFu) > (V & 0xFFFFu) + half;
                 const bool b1 = act && area * (sp >> 8) > (V >> 16) + half;
                 const uint32_t ev = __ballot_sync(0xffffffffu, b0), od = __ballot_sync(0xffffffffu, b1);
-                // little-endian raster: bit b of word w = pixel 32w + b
-                if (lane == 0) raster[(size_t)y * nseg + 2 * seg] = spread16(ev & 0xFFFFu) | (spread16(od & 0xFFFFu) << 1);
-                if (lane == 1 && seg * 64 + 32 < W) raster[(size_t)y * nseg + 2 * seg + 1] = spread16(ev >> 16) | (spread16(od >> 16) << 1);
+                // tiled little-endian raster (raster_tile_index): lane k < 4 stores the 16 pixels [64 seg + 16 k, +16)
+                if (lane < 4 && seg * 64 + 16 * lane < W) {
+                    const uint32_t word = (lane < 2) ? (spread16(ev & 0xFFFFu) | (spread16(od & 0xFFFFu) << 1))
+                                                     : (spread16(ev >> 16) | (spread16(od >> 16) << 1));
+                    raster[raster_tile_index(W >> 4, seg * 64 + 16 * lane, y)] = (uint16_t)(word >> (16 * (lane & 1)));
+                }
                 if (y + 1 < y1) V += hs32[(clampi(y + R + 1, 0, H - 1) - h0) * wh + xh] - hs32[(clampi(y - R, 0, H - 1) - h0) * wh + xh];
             }
         }
     }
 }
 
-// ---------------------------------------------------------------------------------------------- heap (lane 0 only)
+// ---------------------------------------------------------------------------------------------- fast raster (no sharpen)
+// One CTA of 128 threads per (listed frame, band of kFastBand rows).  Thread t owns pixels 8t .. 8t+7 of every row and
+// streams down the band: per input row it converts 8 pixels to gray with K1's IDP.2A form, exchanges two halo pixels with
+// its neighbours through shared memory (one barrier per row, double buffered; BORDER_REPLICATE at the frame edges by
+// clamping), forms the horizontal 5-sums in packed 2x16-bit lanes, keeps the last five of them and the last three gray rows
+// in registers, and emits one byte of threshold bits for the row two above.  16 rows of bytes are staged in shared memory
+// and written out as whole 16x16 tiles (16 bytes per thread, coalesced).  Arithmetic is K1's, so the bits are OpenCV's:
+//   gray = (9798 R + 19235 G + 3735 B + 2^14) >> 15,  bit = 25 gray > boxsum + 12  <=>  gray > round(boxsum / 25).
+constexpr int kFastThreads = 128;
+constexpr int kFastBand = 64;
+
+__device__ __forceinline__ void gray8_packed(const uint2 q0, const uint2 q1, const uint2 q2, uint32_t P[4], uint32_t& E)
+{
+    const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
+    uint32_t n0, n1, n2, n3, n4, n5, n6, n7;       // (19596 R + 38470 G + 7470 B + 2^15) : gray is byte 2
+    n0 = __dp2a_lo(cRG, q0.x, 32768u); n0 = __dp2a_hi(cB0, q0.x, n0);
+    n1 = __dp2a_hi(c0R, q0.x, 32768u); n1 = __dp2a_lo(cGB, q0.y, n1);
+    n2 = __dp2a_hi(cRG, q0.y, 32768u); n2 = __dp2a_lo(cB0, q1.x, n2);
+    n3 = __dp2a_lo(c0R, q1.x, 32768u); n3 = __dp2a_hi(cGB, q1.x, n3);
+    n4 = __dp2a_lo(cRG, q1.y, 32768u); n4 = __dp2a_hi(cB0, q1.y, n4);
+    n5 = __dp2a_hi(c0R, q1.y, 32768u); n5 = __dp2a_lo(cGB, q2.x, n5);
+    n6 = __dp2a_hi(cRG, q2.x, 32768u); n6 = __dp2a_lo(cB0, q2.y, n6);
+    n7 = __dp2a_lo(c0R, q2.y, 32768u); n7 = __dp2a_hi(cGB, q2.y, n7);
+    P[0] = __byte_perm(n0, n4, 0x7632); P[1] = __byte_perm(n1, n5, 0x7632);     // P[j] = g[j] | g[j+4] << 16
+    P[2] = __byte_perm(n2, n6, 0x7632); P[3] = __byte_perm(n3, n7, 0x7632);
+    E = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n6, n7, 0x6200), 0x7610);   // bytes (g0, g1, g6, g7)
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+k_flood_raster_fast(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
+                    int base, int cap, uint16_t* __restrict__ ws_raster)
+{
+    __shared__ uint32_t ex[2][kFastThreads];                       // halo words E of the row in flight (double buffered)
+    __shared__ __align__(16) uint8_t outb[2][16][kFastThreads];    // threshold bytes of the 16-row group being collected
+    const int W = m.width, H = m.height;
+    const int nthr = W >> 3;                                      // active threads (W / 8 <= 128)
+    const int nb = (H + kFastBand - 1) / kFastBand;
+    const int cnt = chunk_count(counters, base, cap);
+    const int t = threadIdx.x;
+    const bool act = t < nthr;
+    const int tc = act ? t : nthr - 1;                            // inactive threads shadow the last one (loads stay in bounds)
+    const size_t row_bytes = (size_t)W * 3;
+    const uint32_t kBias = 0x7FF37FF3u;                           // per half: 0x8000 - 13
+
+    for (int item = blockIdx.x; item < cnt * nb; item += gridDim.x) {
+        const int e = item / nb, band = item - e * nb;
+        const uint32_t f = list[base + e];
+        const uint8_t* frame = rgb + (size_t)f * row_bytes * (size_t)H;
+        uint16_t* raster = ws_raster + (size_t)e * raster_words16(W, H);
+        const int y0 = band * kFastBand, y1 = (y0 + kFastBand < H) ? y0 + kFastBand : H;
+        // input rows y0-2 .. y1+1 (clamped to the frame = BORDER_REPLICATE); the output row lags the input row by two
+        uint32_t hr[5][4], Pr[3][4], nV[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nV[j] = kBias;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) hr[i][j] = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Pr[i][j] = 0;
+        }
+        auto load_row = [&](int rr, uint2& a, uint2& b, uint2& c) {
+            const int yy = rr < 0 ? 0 : (rr > H - 1 ? H - 1 : rr);
+            const uint2* rp = reinterpret_cast<const uint2*>(frame + (size_t)yy * row_bytes) + 3 * tc;
+            a = __ldg(rp); b = __ldg(rp + 1); c = __ldg(rp + 2);
+        };
+        uint2 qa, qb, qc;
+        load_row(y0 - 2, qa, qb, qc);
+        __syncthreads();                                           // the previous item's last flush has been read
+        for (int rbase = y0 - 2; rbase < y1 + 2; rbase += 15) {
+#pragma unroll
+            for (int u = 0; u < 15; ++u) {
+                const int rr = rbase + u;
+                if (rr >= y1 + 2) break;
+                uint32_t (&P)[4] = Pr[u % 3];
+                uint32_t E;
+                gray8_packed(qa, qb, qc, P, E);
+                if (rr + 1 < y1 + 2) load_row(rr + 1, qa, qb, qc);   // next row's pixels fly during this row's arithmetic
+                const int par = rr & 1;
+                ex[par][t] = E;
+                __syncthreads();
+                // replicate at the frame's left / right edge: (g-2, g-1) = (g0, g0), (g8, g9) = (g7, g7)
+                const uint32_t lE = (t == 0) ? __byte_perm(E, 0, 0x0000) : ex[par][t - 1];          // bytes 2,3 used: g6,g7 of the left
+                const uint32_t rE = (t >= nthr - 1) ? __byte_perm(E, 0, 0x3333) : ex[par][t + 1];   // bytes 0,1 used: g0,g1 of the right
+                const uint32_t Pm2 = __byte_perm(lE, P[2], 0x5452), Pm1 = __byte_perm(lE, P[3], 0x5453);
+                const uint32_t P4 = __byte_perm(P[0], rE, 0x3432), P5 = __byte_perm(P[1], rE, 0x3532);
+                uint32_t h[4];
+                h[0] = Pm2 + Pm1 + P[0] + P[1] + P[2];
+                h[1] = h[0] - Pm2 + P[3];
+                h[2] = h[1] - Pm1 + P4;
+                h[3] = h[2] - P[0] + P5;
+                uint32_t tj[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    nV[j] = nV[j] + hr[u % 5][j] - h[j];              // drops row rr-5, adds row rr: window rr-4 .. rr
+                    hr[u % 5][j] = h[j];
+                    tj[j] = 25u * Pr[(u + 1) % 3][j] + nV[j];         // centre row rr-2; bit15 / bit31 = (25 g > boxsum + 12)
+                }
+                const int y = rr - 2;
+                if (y >= y0) {
+                    uint32_t byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
+                                    ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
+                    byte = (byte | (byte >> 12)) & 0xFFu;
+                    outb[(y >> 4) & 1][y & 15][t] = (uint8_t)byte;
+                    if ((y & 15) == 15 || y == y1 - 1) {
+                        __syncthreads();
+                        // 16 rows x nthr bytes -> (nthr / 2) tiles of 32 bytes, contiguous in the tiled raster: thread t writes
+                        // rows 8 (t & 1) .. +7 of tile t >> 1 as one 16-byte store
+                        if (act) {
+                            const uint16_t* ob = reinterpret_cast<const uint16_t*>(&outb[(y >> 4) & 1][0][0]);
+                            const int tile = t >> 1, r0 = 8 * (t & 1);
+                            uint32_t w[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                w[k] = (uint32_t)ob[(r0 + 2 * k) * (kFastThreads / 2) + tile] | ((uint32_t)ob[(r0 + 2 * k + 1) * (kFastThreads / 2) + tile] << 16);
+                            uint16_t* dst = raster + raster_tile_index(W >> 4, 16 * tile, (y & ~15) + r0);
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- heap (warp-uniform)
 // 32-bit entries: prio(7) << 25 | cooldown code(3) << 22 | (dy + 8)(4) << 18 | (dx + 8)(4) << 14 | cell index(14).
 // std::priority_queue<decode_prio, vector, PrioCompare> with comp(a, b) = a.prio > b.prio: only the priority is compared,
 // so the pop order of equal priorities is whatever libstdc++'s sift-up / sift-down produce; both are restated literally.
 // Element i lives at shared word i + 1 (so the children 2h+1, 2h+2 are one aligned 64-bit load) while i < hs, else in
 // the global spill area at word i - hs (hs is odd, so a pair never straddles the two).
+// Every lane of the walking warp executes push and pop with the same arguments and keeps the same `n`: loads are
+// broadcasts, stores are done by one lane, and the sift-down is spread over the lanes (below).
 struct Heap {
     uint32_t* sm; uint32_t* spill; int n; int hs;
-    __device__ __forceinline__ uint32_t get(int i) const { return i < hs ? sm[i + 1] : spill[i - hs]; }
-    __device__ __forceinline__ void set(int i, uint32_t v) { if (i < hs) sm[i + 1] = v; else spill[i - hs] = v; }
+    __device__ __forceinline__ uint32_t get(int i) const { return i < hs ? sm[i + 1] : __ldcg(spill + (i - hs)); }
+    __device__ __forceinline__ void set(int i, uint32_t v) { if (i < hs) sm[i + 1] = v; else __stcg(spill + (i - hs), v); }
+    // elements 2 node + 1 and 2 node + 2
+    __device__ __forceinline__ uint2 children(int node) const
+    {
+        const int c = 2 * node + 2;
+        if (c < hs) return *reinterpret_cast<const uint2*>(sm + c);
+        return __ldcg(reinterpret_cast<const uint2*>(spill + (c - 1 - hs)));
+    }
 };
 __device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 25; }
-__device__ __forceinline__ void heap_push(Heap& h, uint32_t e)
+
+// std::push_heap (__push_heap): append, sift up while parent.prio > prio (strict).  Warp-uniform; lane 0 stores.
+__device__ __forceinline__ void heap_push(Heap& h, uint32_t e, int lane)
 {
     int hole = h.n++;
     const uint32_t prio = hprio(e);
-    if (hole < h.hs) {                  // common case: the whole sift-up path lives in shared memory
-        uint32_t* v = h.sm + 1;
-        while (hole > 0) {
-            const int parent = (hole - 1) >> 1;
-            const uint32_t pe = v[parent];
-            if (hprio(pe) <= prio) break;
-            v[hole] = pe; hole = parent;
-        }
-        v[hole] = e;
-        return;
-    }
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
         const uint32_t pe = h.get(parent);
         if (hprio(pe) <= prio) break;
-        h.set(hole, pe); hole = parent;
+        if (lane == 0) h.set(hole, pe);
+        hole = parent;
     }
-    h.set(hole, e);
+    if (lane == 0) h.set(hole, e);
+    __syncwarp();
 }
-__device__ __forceinline__ uint32_t heap_pop(Heap& h)
+
+// per-lane constants of the five-level subtree a sift-down round works on: lane i < 31 stands for the node at depth d,
+// position j of the subtree (heap order: i = 2^d - 1 + j); anc_mask has the bits of its ancestors' lanes, anc_want the
+// value each of those bits must have ("ancestor prefers its left child") for the descent to pass through this node
+struct SubtreeLane { int d, j, dp; uint32_t anc_mask, anc_want; bool valid; };
+__device__ __forceinline__ SubtreeLane subtree_lane(int lane)
 {
-    const uint32_t top = h.sm[1];
+    SubtreeLane s;
+    s.d = 31 - __clz(lane + 1); s.j = lane + 1 - (1 << s.d);
+    s.dp = s.d > 0 ? s.d - 1 : 0; s.valid = lane < 31;
+    s.anc_mask = 0; s.anc_want = 0;
+    for (int i = lane; i > 0;) {
+        const int p = (i - 1) >> 1;
+        s.anc_mask |= 1u << p;
+        if (i & 1) s.anc_want |= 1u << p;            // odd index = left child
+        i = p;
+    }
+    if (lane == 31) { s.d = 0; s.j = 0; s.dp = 0; s.anc_mask = 0; s.anc_want = 0; }     // no node (valid == false): never on the path
+    return s;
+}
+
+// std::pop_heap + pop_back (__adjust_heap with the hole at the root, then __push_heap of the last element):
+//   while (second < (len - 1) / 2) { second = 2 (second + 1); if (v[second].prio > v[second - 1].prio) second--; v[hole] = v[second]; hole = second; }
+//   if (len even && second == (len - 2) / 2) { second = 2 (second + 1); v[hole] = v[second - 1]; hole = second - 1; }
+//   sift `value` up from the hole.
+// The descent path does not depend on `value`, only on which child each node prefers.  One round handles the 31 nodes of
+// the five-level subtree under the current hole: lane i loads the two children of its node, the preferences are collected
+// with one ballot, every lane decides from its ancestors' bits whether the descent passes through its node, and the lanes on
+// the path move their preferred child up.  13 levels cost three memory round trips instead of thirteen.
+__device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane)
+{
     const uint32_t value = h.get(h.n - 1);
     const int len = --h.n;
-    if (len == 0) return top;
-    int hole = 0, second = 0;
+    if (len == 0) return;
     const int lim = (len - 1) >> 1;
-    uint32_t* v = h.sm + 1;
-    // levels whose children both live in shared memory: one aligned 64-bit load per level
-    const int lim_sm = lim < ((h.hs - 1) >> 1) ? lim : ((h.hs - 1) >> 1);
-    // two levels per shared-memory round trip: both children and all four grandchildren (one aligned 128-bit load)
-    while (2 * (second + 1) < lim_sm) {
-        const int c2 = 2 * (second + 1);
-        const uint2 ch = *reinterpret_cast<const uint2*>(h.sm + c2);        // elements c2-1, c2
-        const uint4 gc = *reinterpret_cast<const uint4*>(h.sm + 2 * c2);    // elements 2c2-1, 2c2 (children of c2-1), 2c2+1, 2c2+2 (of c2)
-        const bool left = hprio(ch.y) > hprio(ch.x);
-        const int c = left ? c2 - 1 : c2;
-        const uint32_t g0 = left ? gc.x : gc.z, g1 = left ? gc.y : gc.w;
-        const bool left2 = hprio(g1) > hprio(g0);
-        v[hole] = left ? ch.x : ch.y;
-        v[c] = left2 ? g0 : g1;
-        hole = second = 2 * c + (left2 ? 1 : 2);
+    int hole = 0;
+    while (hole < lim) {
+        const int node = ((hole + 1) << sl.d) - 1 + sl.j;
+        const bool has2 = sl.valid && node < lim;             // both children inside the heap: the descent continues below it
+        uint2 c = make_uint2(0u, 0u);
+        if (has2) c = h.children(node);
+        const bool left = hprio(c.y) > hprio(c.x);            // right child strictly worse -> left child moves up
+        const uint32_t pref = __ballot_sync(0xffffffffu, has2 && left);
+        // the descent reaches this node iff every ancestor has two children (<=> its parent has) and points towards it
+        const bool parent_ok = (sl.d == 0) || (((hole + 1) << sl.dp) - 1 + (sl.j >> 1)) < lim;
+        const bool reached = sl.valid && parent_ok && (((pref ^ sl.anc_want) & sl.anc_mask) == 0u);
+        if (reached && has2) h.set(node, left ? c.x : c.y);
+        // where the round ends: at the first reached node without two children, or below the subtree's last level
+        const bool ends = reached && (!has2 || sl.d == 4);
+        const uint32_t eb = __ballot_sync(0xffffffffu, ends);
+        const int nxt = has2 ? 2 * node + 2 - (left ? 1 : 0) : node;
+        hole = __shfl_sync(0xffffffffu, nxt, __ffs(eb) - 1);
     }
-    while (second < lim_sm) {
-        second = 2 * (second + 1);
-        const uint2 pr = *reinterpret_cast<const uint2*>(h.sm + second);   // .x = element second-1, .y = element second
-        uint32_t a = pr.y;
-        if (hprio(pr.y) > hprio(pr.x)) { second--; a = pr.x; }
-        v[hole] = a;
-        hole = second;
-    }
-    if (len <= h.hs) {                  // common case: the rest is shared memory too
-        if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
-            second = 2 * (second + 1);
-            v[hole] = v[second - 1];
-            hole = second - 1;
-        }
-        const uint32_t vp = hprio(value);
-        while (hole > 0) {
-            const int parent = (hole - 1) >> 1;
-            const uint32_t pe = v[parent];
-            if (hprio(pe) <= vp) break;
-            v[hole] = pe; hole = parent;
-        }
-        v[hole] = value;
-        return top;
-    }
-    while (second < lim) {              // the one or two levels that spilled to global memory
-        second = 2 * (second + 1);
-        const uint2 pr = *reinterpret_cast<const uint2*>(h.spill + (second - 1 - h.hs));
-        uint32_t a = pr.y;
-        if (hprio(pr.y) > hprio(pr.x)) { second--; a = pr.x; }
-        h.set(hole, a);
-        hole = second;
-    }
-    if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
-        second = 2 * (second + 1);
-        h.set(hole, h.get(second - 1));
-        hole = second - 1;
+    __syncwarp();                                             // the moves above are visible to the reads below
+    if ((len & 1) == 0 && hole == ((len - 2) >> 1)) {         // a last node with only a left child
+        const uint32_t only = h.get(2 * hole + 1);
+        if (lane == 0) h.set(hole, only);
+        hole = 2 * hole + 1;
     }
     const uint32_t vp = hprio(value);
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
         const uint32_t pe = h.get(parent);
         if (hprio(pe) <= vp) break;
-        h.set(hole, pe); hole = parent;
+        if (lane == 0) h.set(hole, pe);
+        hole = parent;
     }
-    h.set(hole, value);
-    return top;
+    if (lane == 0) h.set(hole, value);
+    __syncwarp();
 }
 
 // cooldown values (CellDrift::calculate_cooldown, CellDrift.cpp:34-43): 4, 0xFF, 0xFE (initial), or an odd drift id 1/3/5/7
@@ -331,8 +473,9 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uin
 }
 
 // ---------------------------------------------------------------------------------------------- the walk
-// Shared memory of one walking warp: heap[hs + 1] words, then the _remaining bitmap (1 bit per cell).  One byte per cell
-// lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel, off the pop chain):
+// Shared memory of one walking warp: heap[hs + 1] words, the _remaining bitmap (1 bit per cell), the tile dictionary by
+// perfect-hash slot.  One byte per cell lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in
+// parallel, off the pop chain):
 //   0 = decoded (FloodDecodePositions::_remaining false), else best_prio + 1 (0xFF for the initial 0xFE).
 // Why the inherit record (drift, best_prio, cooldown; FloodDecodePositions.h:17) can ride in the heap entry: update()
 // only rewrites it when the new error is strictly lower (FloodDecodePositions.cpp:75), and pushes an entry with that
@@ -341,20 +484,24 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uin
 // entry pops, the record is the latest update still sitting in the heap (found by a warp-wide scan), else the initial one.
 __global__ void __launch_bounds__(32)
 k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
-             int heap_smem, const uint32_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
+             int heap_smem, const uint16_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
              uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
     uint32_t* heap_sm = reinterpret_cast<uint32_t*>(walk_smem);
     uint32_t* remaining = heap_sm + heap_smem + 1;
+    uint4* tiles_by_slot = reinterpret_cast<uint4*>(remaining + kMaxCells / 32);       // (L_lo, L_hi, symbol, 0)
     uint8_t* prio = ws_prio + (size_t)blockIdx.x * kMaxCells;
     const int lane = threadIdx.x;
-    const int W = m.width, npx = W * m.height, ncells = m.num_cells;
+    const int W = m.width, ncells = m.num_cells, tiles_x = W >> 4;
+    const size_t rwords = raster_words16(W, m.height);
     const int cnt = chunk_count(counters, base, cap);
     const unsigned long long tileL = cx_tiles_L[lane & 15];
     const int narrow = m.cells_x - 2 * m.corner;
-    const float rcp_narrow = 1.0f / (float)narrow, rcp_wide = 1.0f / (float)m.cells_x;   // exact floor for q < 2^14 (q + 0.5 trick)
+    const SubtreeLane sl = subtree_lane(lane);
     Heap heap; heap.sm = heap_sm; heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
+    if (lane < 16) tiles_by_slot[((uint32_t)tileL * m.hash_mul) >> 28] = make_uint4((uint32_t)tileL, (uint32_t)(tileL >> 32), (uint32_t)lane, 0u);
+    __syncwarp();
 
     while (true) {
         uint32_t k = 0;
@@ -362,48 +509,47 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= (uint32_t)cnt) break;
         const uint32_t f = list[base + k];
-        const uint32_t* raster = ws_raster + (size_t)k * (npx / 32 + 4);
+        const uint16_t* raster = ws_raster + (size_t)k * rwords;
         uint32_t* result = ws_result + (size_t)k * ncells;
 
         // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
         for (int i = lane; i < kMaxCells / 16; i += 32) __stcg(reinterpret_cast<uint4*>(prio) + i, make_uint4(~0u, ~0u, ~0u, ~0u));
         for (int i = lane; i < (ncells + 31) / 32; i += 32) remaining[i] = 0xFFFFFFFFu;
-        if (lane == 0) {
-            heap.n = 0;
-            const int last = ncells - 1, bmb = m.top_cells;
-            heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0)); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0));
-            heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0)); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0));
-            heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1)); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1));
-            heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1));
-            heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1));
-        }
         __syncwarp();
+        heap.n = 0;
+        {
+            const int last = ncells - 1, bmb = m.top_cells;
+            heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0), lane); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0), lane);
+            heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0), lane); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0), lane);
+            heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1), lane); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1), lane);
+            heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1), lane);
+            heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1), lane);
+        }
 
         int count = 0;
         while (count < ncells) {
             // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67).  The entry about to pop is the heap's first
             // element, so every lane reads it there and the loads of the cell's window / neighbours are in flight while
-            // lane 0 runs the sift-down of the pop itself.
-            const int hn = __shfl_sync(0xffffffffu, heap.n, 0);
-            if (hn == 0) break;                              // heap exhausted (cannot happen on a connected grid)
+            // the sift-down of the pop itself runs.
+            if (heap.n == 0) break;                          // heap exhausted (cannot happen on a connected grid)
             const uint32_t e = heap_sm[1];
             const int ci = (int)(e & 0x3FFFu);
             const uint32_t rem_bit = 1u << (ci & 31);
             if (!(remaining[ci >> 5] & rem_bit)) {           // stale entry of a cell that is already decoded: skipped
                 __syncwarp();
-                if (lane == 0) heap_pop(heap);
-                __syncwarp();
+                heap_pop(heap, sl, lane);
                 continue;
             }
             ++count;
-            // neighbours: lanes 0-3 direct (right, left, bottom, top), 4-11 the horizon chains (see flood_build_cinfo)
+            // per-cell table (flood_build_cinfo): lanes 0-3 the direct neighbours (right, left, bottom, top), 4-11 the horizon
+            // chains, 12 / 13 the cell's position (CellPositions::compute_linear, CellPositions.cpp:5-50)
             uint32_t cv = 0xFFFFu;
-            if (lane < 12) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
+            if (lane < 14) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
             uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
             int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
             if (code == kSeedCode) {                         // (scanned before the pop: the seed entry itself is excluded either way)
                 uint32_t latest = 0xFFFFFFFFu;
-                for (int i = lane; i < hn; i += 32) {
+                for (int i = lane; i < heap.n; i += 32) {
                     const uint32_t t = heap.get(i);
                     if ((t & 0x3FFFu) == (uint32_t)ci && ((t >> 22) & 7u) != kSeedCode && t < latest) latest = t;
                 }
@@ -414,77 +560,74 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
             }
             const uint32_t cooldown = cd_value(code);
-            // ---- cell position (CellPositions::compute_linear, CellPositions.cpp:5-50)
-            int px, py;
-            if (ci < m.top_cells) {
-                const int kk = __float2int_rz(((float)ci + 0.5f) * rcp_narrow), c = ci - kk * narrow;
-                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * kk;
-            } else if (ci < m.top_cells + m.mid_cells) {
-                const int q = ci - m.top_cells;
-                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_wide), c = q - kk * m.cells_x;
-                px = m.cell_offset + kSpacing * c; py = m.cell_offset + kSpacing * (m.corner + kk);
-            } else {
-                const int q = ci - m.top_cells - m.mid_cells;
-                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_narrow), c = q - kk * narrow;
-                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * (m.cells_y - m.corner + kk);
-            }
+            const int px = (int)__shfl_sync(0xffffffffu, cv, 12), py = (int)__shfl_sync(0xffffffffu, cv, 13);
             const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
-            // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r
+            // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r from (at most) two tiles
             uint32_t ra = 0, rb = 0, rshift = 0;
             if (lane < 10) {
-                const uint32_t bit = (uint32_t)(y - 1 + lane) * (uint32_t)W + (uint32_t)(x - 1);
-                const uint32_t wi = bit >> 5;
-                rshift = bit & 31u;
-                ra = __ldg(raster + wi); rb = __ldg(raster + wi + 1);
+                const uint32_t ti = raster_tile_index(tiles_x, x - 1, y - 1 + lane);
+                rshift = (uint32_t)(x - 1) & 15u;
+                ra = __ldg(raster + ti); rb = __ldg(raster + ti + 16);
             }
-            __syncwarp();                                    // every lane has read the heap top / bitmap before lane 0 rewrites them
-            asm volatile("" ::: "memory");
+            __syncwarp();                                    // every lane has read the heap top / bitmap before they are rewritten
+            heap_pop(heap, sl, lane);
             if (lane == 0) {
-                heap_pop(heap);
                 remaining[ci >> 5] &= ~rem_bit;
                 __stcg(prio + ci, (uint8_t)0);
             }
-            __syncwarp();                                    // lane 0's heap / bitmap / prio writes are ordered before the reads below
-            asm volatile("" ::: "memory");
+            __syncwarp();                                    // the bitmap / prio writes are ordered before the reads below
             // the candidates' priority bytes: requested now, needed only after the scoring below
             uint32_t pv = 0;
+            if (lane >= 12) cv = 0xFFFFu;
             if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
-            const uint32_t myrow = __funnelshift_r(ra, rb, rshift) & 0x3FFu;   // bit i = window col i
-            uint32_t win[10];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
-            // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
-            // lane q < 9 extracts the hash at drift id order[q]: the window's 8-bit columns c0..c0+7 of all ten rows form one
-            // 80-bit string, the hash at row offset r0 is bits [8 r0, 8 r0 + 64) of it (ahash_result::extract, ahash_result.h:70-106)
-            uint32_t hlo, hhi;
+            const uint32_t myrow = ((ra | (rb << 16)) >> rshift) & 0x3FFu;     // bit i = window col i
+            // ---- fast path: the centre hash (drift id 4 = rows 1..8, cols 1..8) is a dictionary tile.  The reference's search
+            // starts with id 4 and returns at once on distance 0 (CimbDecoder.cpp:101-132), whatever the cooldown.
+            uint32_t best_key;
             {
-                const int qq = lane < 9 ? lane : 0;
-                const int r0 = (int)((0x200201211ULL >> (4 * qq)) & 3u), c0 = (int)((0x020210121ULL >> (4 * qq)) & 3u);   // id / 3, id % 3
-                uint32_t b[10];
-#pragma unroll
-                for (int r = 0; r < 10; ++r) b[r] = (win[r] >> c0) & 0xFFu;
-                const uint32_t w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-                const uint32_t w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-                const uint32_t w2 = b[8] | (b[9] << 8);
-                hlo = __funnelshift_r(w0, w1, 8 * r0); hhi = __funnelshift_r(w1, w2, 8 * r0);
+                const uint32_t b = (myrow >> 1) & 0xFFu;
+                const uint32_t plo = (lane >= 1 && lane <= 4) ? b << (8 * (lane - 1)) : 0u;
+                const uint32_t phi = (lane >= 5 && lane <= 8) ? b << (8 * (lane - 5)) : 0u;
+                const uint32_t clo = __reduce_or_sync(0xffffffffu, plo), chi = __reduce_or_sync(0xffffffffu, phi);
+                const uint4 te = tiles_by_slot[(clo * m.hash_mul) >> 28];
+                best_key = (te.x == clo && te.y == chi) ? te.z : 0xFFFFFFFFu;      // key = dist << 8 | order << 4 | tile, dist = order = 0
             }
-            // every lane scores its tile (lane & 15) against the hashes q = 2 it + (lane >> 4)
-            const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
-            const int nq = all ? 9 : 5;
-            const uint32_t tile_lo = (uint32_t)tileL, tile_hi = (uint32_t)(tileL >> 32);
-            uint32_t best_key = 0xFFFFFFFFu;
+            if (best_key == 0xFFFFFFFFu) {                   // warp-uniform
+                uint32_t win[10];
 #pragma unroll
-            for (int it = 0; it < 5; ++it) {
-                if (it >= 3 && !all) break;                       // warp-uniform
-                const int q = 2 * it + (lane >> 4);
-                const uint32_t lo = __shfl_sync(0xffffffffu, hlo, q & 15), hi = __shfl_sync(0xffffffffu, hhi, q & 15);
-                const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);          // packed order table, nibble q
-                const bool valid = q < nq && !((uint32_t)id == cooldown && id != 4);   // CimbDecoder.cpp:116
-                const uint32_t d = (uint32_t)(__popc(lo ^ tile_lo) + __popc(hi ^ tile_hi));
-                const uint32_t key = valid ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15)) : 0xFFFFFFFFu;
-                best_key = key < best_key ? key : best_key;
+                for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
+                // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
+                // lane q < 9 extracts the hash at drift id order[q]: the window's 8-bit columns c0..c0+7 of all ten rows form one
+                // 80-bit string, the hash at row offset r0 is bits [8 r0, 8 r0 + 64) of it (ahash_result::extract, ahash_result.h:70-106)
+                uint32_t hlo, hhi;
+                {
+                    const int qq = lane < 9 ? lane : 0;
+                    const int r0 = (int)((0x200201211ULL >> (4 * qq)) & 3u), c0 = (int)((0x020210121ULL >> (4 * qq)) & 3u);   // id / 3, id % 3
+                    uint32_t b[10];
+#pragma unroll
+                    for (int r = 0; r < 10; ++r) b[r] = (win[r] >> c0) & 0xFFu;
+                    const uint32_t w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+                    const uint32_t w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+                    const uint32_t w2 = b[8] | (b[9] << 8);
+                    hlo = __funnelshift_r(w0, w1, 8 * r0); hhi = __funnelshift_r(w1, w2, 8 * r0);
+                }
+                // every lane scores its tile (lane & 15) against the hashes q = 2 it + (lane >> 4)
+                const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
+                const int nq = all ? 9 : 5;
+                const uint32_t tile_lo = (uint32_t)tileL, tile_hi = (uint32_t)(tileL >> 32);
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    if (it >= 3 && !all) break;                       // warp-uniform
+                    const int q = 2 * it + (lane >> 4);
+                    const uint32_t lo = __shfl_sync(0xffffffffu, hlo, q & 15), hi = __shfl_sync(0xffffffffu, hhi, q & 15);
+                    const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);          // packed order table, nibble q
+                    const bool valid = q < nq && !((uint32_t)id == cooldown && id != 4);   // CimbDecoder.cpp:116
+                    const uint32_t d = (uint32_t)(__popc(lo ^ tile_lo) + __popc(hi ^ tile_hi));
+                    const uint32_t key = valid ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15)) : 0xFFFFFFFFu;
+                    best_key = key < best_key ? key : best_key;
+                }
+                best_key = __reduce_min_sync(0xffffffffu, best_key);
             }
-            best_key = __reduce_min_sync(0xffffffffu, best_key);
             // every lane derives the (warp-uniform) decision from the reduced key
             const uint32_t dist = best_key >> 8, q = (best_key >> 4) & 0xFu, sym = best_key & 0xFu;
             const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);
@@ -502,18 +645,19 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 }
             }
             // ---- FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83):
-            // lanes 0..11 test one candidate each (still remaining and stored priority > err  <=>  byte >= err + 2), lane 0
-            // then records the new priority and pushes the survivors in the reference's order (adjacents, horizon, vert).
+            // lanes 0..11 test one candidate each (still remaining and stored priority > err  <=>  byte >= err + 2); the new
+            // priority is recorded and the survivors are pushed in the reference's order (adjacents, horizon, vert).
             const bool horizon = prev_err < 3u && dist < 3u && cooldown == 4u && ncd == 4u;
             const int cand = (cv != 0xFFFFu && (lane < 4 || horizon)) ? (int)cv : -1;
             const bool push = cand >= 0 && pv >= dist + 2u;
+            if (push) __stcg(prio + cand, (uint8_t)(dist + 1u));
             uint32_t todo = __ballot_sync(0xffffffffu, push) & 0xFFFu;
             const uint32_t entry = make_entry(0, ndx, ndy, cd_code(ncd), dist);
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int c = __shfl_sync(0xffffffffu, cand, l);
-                if (lane == 0) { __stcg(prio + c, (uint8_t)(dist + 1u)); heap_push(heap, entry | (uint32_t)c); }
+                heap_push(heap, entry | (uint32_t)c, lane);
             }
             __syncwarp();
         }
@@ -606,6 +750,7 @@ cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* 
 // neighbours (right, left, bottom, top; update_adjacents), 4,5 right+1 / right+2, 6,7 left+1 / left+2 (horizontal horizon,
 // only when BOTH right and left exist, FloodDecodePositions.cpp:102), 8,9 top+1 / top+2, 10,11 bottom+1 / bottom+2 (vertical,
 // only when both top and bottom exist, :116); 0xFFFF = none.  Built from AdjacentCellFinder::find for every cell (adj_host).
+// Slots 12, 13: the cell's top-left pixel (CellPositions::compute_linear, CellPositions.cpp:5-50).
 static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<uint16_t>& out)
 {
     auto nb = [&](int cell, int dir) -> int { if (cell < 0) return -1; unsigned v = adj[(size_t)cell * 4 + dir]; return v == 0xFFFFu ? -1 : (int)v; };
@@ -621,6 +766,11 @@ static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<ui
         };
         if (right >= 0 && left >= 0) { chain(right, 0, 4); chain(left, 1, 6); }
         if (top >= 0 && bottom >= 0) { chain(top, 3, 8); chain(bottom, 2, 10); }
+        int k, cc, rbase, ncols, x0;
+        cell_row_col(m, i, k, cc);
+        cell_row_geom(m, k, rbase, ncols, x0);
+        o[12] = (uint16_t)(x0 + kSpacing * cc);
+        o[13] = (uint16_t)(m.cell_offset + kSpacing * k);
     }
 }
 
@@ -628,12 +778,13 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
 {
     memset(ws, 0, sizeof(*ws));
     ws->sm_count = sm_count;
-    // shared-memory heap entries per walking warp (must be odd); the default keeps 7 walks resident per SM
-    ws->heap_smem = 4095;
+    // shared-memory heap entries per walking warp (must be odd): 2047 = the eleven top levels; deeper levels go to the
+    // per-slot spill area in L2.  Shared memory per walk decides how many walks an SM holds (at most 32 blocks).
+    ws->heap_smem = 2047;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
-    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)((m.num_cells + 127) / 128) * 16;
+    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + 16 * sizeof(uint4);
     int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
-    if (per_sm > 16) per_sm = 16;
+    if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
     if (const char* s = getenv("CB200_K1X_WALKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= per_sm) per_sm = v; }
     ws->slots = sm_count * per_sm;
@@ -642,7 +793,6 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     ws->spill_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->walk_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_flood_raster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, false))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_flood_raster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, true))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->spill, ws->spill_cap * (size_t)ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->prio, (size_t)kMaxCells * (size_t)ws->slots)) != cudaSuccess) return e;
@@ -663,7 +813,7 @@ void flood_workspace_destroy(FloodWorkspace* ws)
 static cudaError_t flood_workspace_ensure(const Mode& m, FloodWorkspace& ws, int n_frames)
 {
     cudaError_t e;
-    const size_t npx = (size_t)m.width * m.height, rw = npx / 32 + 4;
+    const size_t rw = raster_words16(m.width, m.height);
     if (n_frames > ws.list_cap) {
         int cap = ws.list_cap ? ws.list_cap : 256;
         while (cap < n_frames) cap *= 2;
@@ -678,8 +828,8 @@ static cudaError_t flood_workspace_ensure(const Mode& m, FloodWorkspace& ws, int
         if (want <= 64) cap = 64; else if (want <= 256) cap = 256;
         if (cap > ws.max_entries) cap = ws.max_entries;
         cudaFree(ws.raster); cudaFree(ws.result); ws.raster = nullptr; ws.result = nullptr; ws.entry_cap = 0;
-        if ((e = cudaMalloc(&ws.raster, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
-        if ((e = cudaMemset(ws.raster, 0, rw * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ws.raster, rw * (size_t)cap * sizeof(uint16_t))) != cudaSuccess) return e;
+        if ((e = cudaMemset(ws.raster, 0, rw * (size_t)cap * sizeof(uint16_t))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&ws.result, (size_t)m.num_cells * (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
         ws.entry_cap = cap;
     }
@@ -701,10 +851,15 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
     for (int c = 0; c < nchunks; ++c) {
         const int base = c * ws.entry_cap;
         const int cap = n_frames - base < ws.entry_cap ? n_frames - base : ws.entry_cap;
-        long long items = (long long)cap * nb;
-        int rgrid = (int)(items < (long long)ws.sm_count * 3 ? items : (long long)ws.sm_count * 3);
-        if (sharpen) k_flood_raster<true><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
-        else k_flood_raster<false><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
+        if (sharpen) {
+            long long items = (long long)cap * nb;
+            int rgrid = (int)(items < (long long)ws.sm_count * 3 ? items : (long long)ws.sm_count * 3);
+            k_flood_raster<true><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
+        } else {
+            long long items = (long long)cap * ((m.height + kFastBand - 1) / kFastBand);
+            int rgrid = (int)(items < (long long)ws.sm_count * 8 ? items : (long long)ws.sm_count * 8);
+            k_flood_raster_fast<<<rgrid, kFastThreads, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
+        }
         count_launch();
         int wgrid = cap < ws.slots ? cap : ws.slots;
         k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,

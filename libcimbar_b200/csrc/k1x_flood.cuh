@@ -27,7 +27,7 @@ struct FloodWorkspace {
     uint16_t* cinfo;           // [num_cells][16] update candidates in push order (0xFFFF = none)
     int list_cap; uint32_t* list; uint32_t* counters;   // work list; counters[0] = listed frames, [1 + c] = chunk c's work counter
     int max_entries;           // upper bound of entry_cap (one chunk); larger work lists are processed chunk by chunk
-    int entry_cap; uint32_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster, per-cell x | y<<11 | sym<<22
+    int entry_cap; uint16_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster in 16x16 tiles, per-cell x | y<<11 | sym<<22
 };
 
 cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16);
