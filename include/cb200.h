@@ -53,6 +53,9 @@ extern "C" {
                                          reference's thread-local decoder state when frames are decoded in order; the
                                          context's CCM afterwards is the last frame's.  Mutually exclusive with CC_SIMPLE. */
 
+#define CB200_FLAG_NO_INTERLEAVE 0x10u /* Decoder(use_ecc, interleave=false): cells map to stream slots in linear order
+                                         (Interleave::interleave_indices with num_chunks == 0, Interleave.h:10-16; Decoder.h:68) */
+
 /* per-frame status bits written to frame_flags[] */
 #define CB200_FRAME_FALLBACK    0x1u  /* frame was decoded by the exact flood-walk kernel (drift tracking needed) */
 #define CB200_FRAME_INEXACT     0x2u  /* K1 could not prove the drift-0 decode exact and no fallback was run */
@@ -145,6 +148,14 @@ typedef struct cb200_cell_trace {
 int cb200_decode_cells(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* cellvals_out,
                        cb200_cell_trace* trace_out);
 
+/* Same, for a host that mirrors CimbReader call by call: with means_out != NULL (n * total_cells words, r | g << 8 | b << 16 =
+   Cell::mean_rgb of the inner 6x6 at the cell's drift-adjusted position, Cell.h:30-62) the colours are NOT decided here --
+   cellvals_out carries the symbols only -- so that CimbReader::read_color can classify them later with the CCM the decoder
+   holds by then (after CimbReader::init_ccm): cb200_best_colors on the stored means is CimbDecoder::decode_color.
+   CB200_FLAG_CC_SIMPLE still installs the frame's von Kries matrix as the context's CCM (CimbReader.cpp:124-125). */
+int cb200_decode_cells_means(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* cellvals_out,
+                             cb200_cell_trace* trace_out, uint32_t* means_out);
+
 /* ---- single-cell entry points (CimbDecoder API parity; run one tiny kernel) ------------------------------------- */
 
 /* Replaces: CimbDecoder::decode_symbol(const bitmatrix&, drift_offset, best_distance, cooldown)
@@ -168,6 +179,19 @@ int cb200_set_ccm(cb200_ctx* ctx, const float* m9);
 /* Replaces: CimbDecoder::get_ccm() (CimbDecoder.cpp:76-80): returns 1 and fills m9 when a CCM is active, else 0.
    After a CB200_FLAG_CC_SIMPLE call this is the last frame's matrix (synchronises the context's stream). */
 int cb200_get_ccm(cb200_ctx* ctx, float* m9);
+
+/* Replaces: CimbReader::init_ccm (src/lib/cimb_translator/CimbReader.cpp:169-267) for a host that tracked the fountain header
+   itself (CimbReader::update_metadata, CimbReader.cpp:269-280): header6 = _fountainColorHeader as it stands (block id already
+   "+1"), radioactive_block_id = _radioactiveBlockId.  rgb: one frame (host pointer), or NULL = the frame the last host-pointer
+   call of this context uploaded.  flags: CB200_FLAG_NO_INTERLEAVE or 0.  Samples the header cells of every colour-stream chunk
+   and the anchor white on the device and runs the Moore-Penrose fit (OpenCV's float Jacobi SVD restated).  Returns 1 when a
+   matrix was fitted -- it is then the context's CCM and copied to m9_out (may be NULL) --, 0 when the reference would have
+   returned without one (no header, fewer than four colours seen), negative on error. */
+int cb200_fit_ccm(cb200_ctx* ctx, const uint8_t* rgb, const uint8_t* header6, uint32_t radioactive_block_id, uint32_t flags, float* m9_out);
+
+/* Replaces: CimbDecoder::get_color(i, color_mode) -> cimbar::getColor(i, num_colors, color_mode)
+   (src/lib/cimb_translator/CimbDecoder.cpp:149-152, Common.cpp:122-139): decode palette entry i for 1 << color_bits colours. */
+int cb200_palette_color(int color_bits, unsigned color_mode, int i, uint8_t* rgb_out /* 3 bytes */);
 
 /* ---- synthetic input (benchmark support; the inverse of the path) ---------------------------------------------- */
 

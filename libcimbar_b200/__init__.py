@@ -15,6 +15,7 @@ FLAG_NO_FALLBACK = 0x1
 FLAG_SHARPEN = 0x2
 FLAG_CC_SIMPLE = 0x4
 FLAG_CC_FIT = 0x8
+FLAG_NO_INTERLEAVE = 0x10
 FRAME_FALLBACK = 0x1
 FRAME_INEXACT = 0x2
 
@@ -24,7 +25,7 @@ EXPORTS = [
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
-    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count",
+    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
     "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_wait",
     "cb200_gather_release", "cb200_gather_acquire",
     "cb200_gather_status", "cb200_comm_unique_id", "cb200_comm_init", "cb200_gather_chunks", "cb200_gather_chunks_wait",
@@ -90,6 +91,9 @@ def load_library():
     lib.cb200_sink_file_size.argtypes = [vp, C.c_uint32]
     lib.cb200_sink_file_read.argtypes = [vp, C.c_uint32, u8p, C.c_uint64]
     lib.cb200_launch_count.restype = C.c_ulonglong
+    lib.cb200_decode_cells_means.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, vp, vp]
+    lib.cb200_fit_ccm.argtypes = [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.cb200_palette_color.argtypes = [C.c_int, C.c_uint, C.c_int, u8p]
     lib.cb200_gather_root_create.argtypes = [vp, C.c_int, u8p]
     lib.cb200_gather_peer_open.argtypes = [vp, C.c_int, C.c_int, u8p]
     lib.cb200_gather_slot.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
@@ -212,6 +216,28 @@ class Context:
         trace = np.zeros((n, self.info.total_cells), dtype=TRACE_DTYPE)
         _check(self.lib.cb200_decode_cells(self._h, rgb.ctypes.data, n, flags, cells.ctypes.data, trace.ctypes.data))
         return cells, trace
+
+    def decode_cells_means(self, rgb, flags=0):
+        """like decode_cells, but the colours are left undecided: returns (symbols, trace, means r|g<<8|b<<16)"""
+        rgb, n = self._frames(rgb)
+        cells = np.zeros((n, self.info.total_cells), dtype=np.uint8)
+        trace = np.zeros((n, self.info.total_cells), dtype=TRACE_DTYPE)
+        means = np.zeros((n, self.info.total_cells), dtype=np.uint32)
+        _check(self.lib.cb200_decode_cells_means(self._h, rgb.ctypes.data, n, flags, cells.ctypes.data, trace.ctypes.data, means.ctypes.data))
+        return cells, trace, means
+
+    def fit_ccm(self, rgb, header6, radioactive, flags=0):
+        """CimbReader::init_ccm with a header tracked by the caller; returns the fitted 3x3 matrix or None"""
+        hdr = np.ascontiguousarray(header6, dtype=np.uint8)
+        out = np.zeros(9, dtype=np.float32)
+        ptr = None
+        if rgb is not None:
+            rgb, _ = self._frames(rgb)
+            ptr = rgb.ctypes.data
+        rc = self.lib.cb200_fit_ccm(self._h, ptr, hdr.ctypes.data, int(radioactive) & 0xFFFFFFFF, flags, out.ctypes.data)
+        if rc < 0:
+            _check(rc)
+        return out.reshape(3, 3) if rc == 1 else None
 
     def decode_symbols(self, windows, cooldown=None):
         windows = np.ascontiguousarray(windows, dtype=np.uint16).reshape(-1, 10)

@@ -249,6 +249,22 @@ int ccm_arg(cb200_ctx* c, CcmArg& cc)
     return CB200_OK;
 }
 
+// the slot -> cell map of this call: Interleave::interleave_indices, or the identity for Decoder(use_ecc, interleave=false)
+// (Interleave.h:10-16 with num_chunks == 0)
+int idx_for(cb200_ctx* c, uint32_t flags, const uint16_t** out)
+{
+    *out = c->d_idx;
+    if (!(flags & CB200_FLAG_NO_INTERLEAVE)) return CB200_OK;
+    if (!c->d_idx_ident) {
+        std::vector<uint16_t> id((size_t)c->mode.num_cells);
+        for (size_t i = 0; i < id.size(); ++i) id[i] = (uint16_t)i;
+        CK(cudaMalloc(&c->d_idx_ident, id.size() * sizeof(uint16_t)), "cudaMalloc identity map");
+        CK(cudaMemcpy(c->d_idx_ident, id.data(), id.size() * sizeof(uint16_t), cudaMemcpyHostToDevice), "upload identity map");
+    }
+    *out = c->d_idx_ident;
+    return CB200_OK;
+}
+
 // K1 (+ exact-walk fallback) : frames -> per-cell bytes in ctx->d_cellvals, per-frame flags in ctx->d_flags
 int ccm_buffers(cb200_ctx* c)
 {
@@ -383,7 +399,7 @@ static int create_impl(cb200_ctx* c, int device, int mode_val, int max_frames)
         }
     }
     CK(k2_init_tables(gexp, glog), "k2 tables");
-    CK(flood_init_tables(adjust, tilesL), "flood tables");
+    CK(flood_init_tables(adjust, tilesL, m.hash_mul), "flood tables");
 
     // ---- workspaces
     size_t n = (size_t)max_frames;
@@ -452,7 +468,7 @@ int cb200_destroy(cb200_ctx* c)
     if (!c) return CB200_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_rgb); cudaFree(c->d_cellvals); cudaFree(c->d_dirty); cudaFree(c->d_raw); cudaFree(c->d_data);
-    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_scratch);
+    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_idx_ident); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_scratch);
     for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) if (c->ev[k][i]) cudaEventDestroy(c->ev[k][i]);
     flood_workspace_destroy(&c->flood);
     cudaFree(c->d_ccm); cudaFree(c->d_means); cudaFree(c->d_fit); cudaFree(c->d_fit_valid); cudaFree(c->d_ccm_active);
@@ -493,8 +509,10 @@ int cb200_decode_raw_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t fla
     if (n == 0) return CB200_OK;
     if (!d_rgb || !d_raw_out) return fail(CB200_ERR_ARG, "null buffer");
     CK(cudaSetDevice(c->device), "cudaSetDevice");
+    const uint16_t* idx;
+    rc = idx_for(c, flags, &idx); if (rc) return rc;
     rc = run_cells(c, d_rgb, n, flags); if (rc) return rc;
-    CK(k2_pack_launch(c->mode, c->d_cellvals, c->d_idx, n, d_raw_out, c->stream), "pack launch");
+    CK(k2_pack_launch(c->mode, c->d_cellvals, idx, n, d_raw_out, c->stream), "pack launch");
     mark(c);                                   // ev3: after pack
     if (d_frame_flags) CK(cudaMemcpyAsync(d_frame_flags, c->d_flags, (size_t)n, cudaMemcpyDeviceToDevice, c->stream), "copy flags");
     return CB200_OK;
@@ -521,10 +539,12 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
     if ((flags & CB200_FLAG_CC_FIT) && (flags & CB200_FLAG_CC_SIMPLE)) return fail(CB200_ERR_ARG, "CC_SIMPLE and CC_FIT are exclusive");
     // init_ccm is only reached from Decoder::do_decode (not the legacy coupled layout) and needs a header from the RS stream
     const bool fit = (flags & CB200_FLAG_CC_FIT) && !m.legacy && m.ecc_bytes > 0 && m.color_bits > 0;
+    const uint16_t* idx;
+    rc = idx_for(c, flags, &idx); if (rc) return rc;
     if (!fit) {
         rc = run_cells(c, d_rgb, n, flags & ~CB200_FLAG_CC_FIT); if (rc) return rc;
         mark(c);                               // ev3: (no separate pack kernel on this path: the RS kernel gathers from the cell bytes)
-        CK(k2_rs_fused_launch(m, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream), "rs launch");
+        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->sm_count, c->stream), "rs launch");
     } else {
         // color_correction == 2: symbols (+ mean colours) -> RS of the symbol stream -> header -> CCM fit -> colours -> RS of
         // the colour stream (Decoder.h:83-117)
@@ -537,11 +557,11 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
         rc = ccm_arg(c, initial); if (rc) return rc;        // the decoder's CCM going into frame 0
         rc = run_cells(c, d_rgb, n, flags & ~(CB200_FLAG_CC_FIT | CB200_FLAG_CC_SIMPLE), nullptr, c->d_means); if (rc) return rc;
         mark(c);                               // ev3
-        CK(k2_rs_fused_launch(m, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, 0, m.nblocks_sym), "rs launch (symbols)");
-        CK(ccm_fit_launch(m, d_rgb, d_chunks, c->d_ok, c->d_idx, n, c->d_fit, c->d_fit_valid, c->stream), "ccm fit");
+        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, 0, m.nblocks_sym), "rs launch (symbols)");
+        CK(ccm_fit_launch(m, d_rgb, d_chunks, c->d_ok, idx, n, c->d_fit, c->d_fit_valid, c->stream), "ccm fit");
         CK(ccm_carry_launch(n, c->d_fit, c->d_fit_valid, initial, c->d_ccm, c->d_ccm_active, c->stream), "ccm carry");
         CK(ccm_apply_launch(m, c->d_means, n, c->d_ccm, c->d_ccm_active, c->d_cellvals, c->stream), "ccm apply");
-        CK(k2_rs_fused_launch(m, c->d_cellvals, c->d_idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, m.nblocks_sym, m.nblocks - m.nblocks_sym),
+        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, m.nblocks_sym, m.nblocks - m.nblocks_sym),
            "rs launch (colours)");
         // the decoder keeps the CCM of the last frame (and whether there is one at all)
         CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, c->stream), "D2H ccm");
@@ -624,6 +644,12 @@ int cb200_decode_fountain(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flag
 
 int cb200_decode_cells(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* cellvals_out, cb200_cell_trace* trace_out)
 {
+    return cb200_decode_cells_means(c, rgb, n, flags, cellvals_out, trace_out, nullptr);
+}
+
+int cb200_decode_cells_means(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, uint8_t* cellvals_out, cb200_cell_trace* trace_out,
+                             uint32_t* means_out)
+{
     int rc = check_n(c, n); if (rc) return rc;
     if (n == 0) return CB200_OK;
     if (!rgb || !cellvals_out || !trace_out) return fail(CB200_ERR_ARG, "null buffer");
@@ -631,9 +657,21 @@ int cb200_decode_cells(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flags, 
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     rc = upload_frames(c, rgb, n); if (rc) return rc;
     size_t tb = (size_t)n * c->mode.num_cells * sizeof(CellTrace);
-    rc = ensure_scratch(c, tb); if (rc) return rc;
+    size_t mb = means_out ? (size_t)n * c->mode.num_cells * sizeof(uint32_t) : 0;
+    rc = ensure_scratch(c, tb + mb); if (rc) return rc;
     CellTrace* d_trace = static_cast<CellTrace*>(c->d_scratch);
-    rc = run_cells(c, c->d_rgb, n, flags & ~CB200_FLAG_NO_FALLBACK, d_trace); if (rc) return rc;
+    uint32_t* d_means = means_out ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(c->d_scratch) + tb) : nullptr;
+    // with means_out the colours are not decided here (the caller classifies the means later, with whatever CCM its decoder
+    // holds by then: CimbReader::read_color after init_ccm); CC_SIMPLE still installs the frame's matrix as the context's CCM
+    if (d_means && (flags & CB200_FLAG_CC_SIMPLE)) {
+        rc = ccm_buffers(c); if (rc) return rc;
+        CK(ccm_simple_launch(c->mode, c->d_rgb, n, c->d_ccm, c->stream), "ccm launch");
+        CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, c->stream), "D2H ccm");
+        CK(cudaEventRecord(c->ccm_ev, c->stream), "record ccm");
+        c->ccm_pending = true; c->ccm_pending_flag = false; c->ccm_active = true;
+    }
+    rc = run_cells(c, c->d_rgb, n, flags & ~(CB200_FLAG_NO_FALLBACK | (d_means ? CB200_FLAG_CC_SIMPLE : 0u)), d_trace, d_means); if (rc) return rc;
+    if (means_out) CK(cudaMemcpyAsync(means_out, d_means, mb, cudaMemcpyDeviceToHost, c->stream), "D2H means");
     CK(cudaMemcpyAsync(cellvals_out, c->d_cellvals, (size_t)n * c->mode.num_cells, cudaMemcpyDeviceToHost, c->stream), "D2H cells");
     CK(cudaMemcpyAsync(trace_out, d_trace, tb, cudaMemcpyDeviceToHost, c->stream), "D2H trace");
     CK(cudaStreamSynchronize(c->stream), "sync");
@@ -692,6 +730,46 @@ int cb200_get_ccm(cb200_ctx* c, float* m9)
     int rc = ccm_resolve(c); if (rc) return rc;
     if (c->ccm_active && m9) memcpy(m9, c->ccm, sizeof(c->ccm));
     return c->ccm_active ? 1 : 0;
+}
+
+int cb200_fit_ccm(cb200_ctx* c, const uint8_t* rgb, const uint8_t* header6, uint32_t radioactive_block_id, uint32_t flags, float* m9_out)
+{
+    if (!c || !header6) return fail(CB200_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    const Mode& m = c->mode;
+    if (m.color_bits == 0) return 0;
+    int rc;
+    if (rgb) { rc = upload_frames(c, rgb, 1); if (rc) return rc; }
+    else if (!c->d_rgb) return fail(CB200_ERR_ARG, "no frame in the context's staging buffer");
+    rc = ccm_buffers(c); if (rc) return rc;
+    if (!c->d_fit) CK(cudaMalloc(&c->d_fit, sizeof(float) * 9 * (size_t)c->max_frames), "cudaMalloc fit");
+    if (!c->d_fit_valid) CK(cudaMalloc(&c->d_fit_valid, (size_t)c->max_frames), "cudaMalloc fit flags");
+    const uint16_t* idx;
+    rc = idx_for(c, flags, &idx); if (rc) return rc;
+    GivenHeader g;
+    memset(&g, 0, sizeof(g));
+    memcpy(g.hdr, header6, 6); g.use = 1; g.radioactive = radioactive_block_id;
+    CK(ccm_fit_launch(m, c->d_rgb, nullptr, nullptr, idx, 1, c->d_fit, c->d_fit_valid, c->stream, &g), "ccm fit");
+    float fitm[9]; uint8_t valid = 0;
+    CK(cudaMemcpyAsync(fitm, c->d_fit, sizeof(fitm), cudaMemcpyDeviceToHost, c->stream), "D2H fit");
+    CK(cudaMemcpyAsync(&valid, c->d_fit_valid, 1, cudaMemcpyDeviceToHost, c->stream), "D2H fit flag");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    if (!valid) return 0;
+    c->ccm_pending = c->ccm_pending_flag = false;
+    c->ccm_active = true;
+    memcpy(c->ccm, fitm, sizeof(fitm));
+    if (m9_out) memcpy(m9_out, fitm, sizeof(fitm));
+    return 1;
+}
+
+int cb200_palette_color(int color_bits, unsigned color_mode, int i, uint8_t* rgb_out)
+{
+    if (color_bits < 0 || color_bits > 3 || i < 0 || !rgb_out) return fail(CB200_ERR_ARG, "bad arguments");
+    uint8_t pal[8][4];
+    fill_palette(1 << color_bits, (int)color_mode, pal);
+    if (i >= (color_bits >= 3 ? 8 : 4)) return fail(CB200_ERR_ARG, "colour index outside the palette");   // the reference indexes a 4 / 8 entry array
+    rgb_out[0] = pal[i][0]; rgb_out[1] = pal[i][1]; rgb_out[2] = pal[i][2];
+    return CB200_OK;
 }
 
 int cb200_encode_cells_dev(cb200_ctx* c, const uint8_t* d_payload, int n, uint8_t* d_cellvals)

@@ -1,5 +1,6 @@
 // ccm.cu -- color_correction == 1: one von Kries adaptation matrix per frame from the anchors' white (see ccm.cuh)
 #include "ccm.cuh"
+#include <cstring>
 
 namespace cb200 {
 
@@ -222,7 +223,7 @@ struct FitSmem {
 // one warp per frame
 __global__ void __launch_bounds__(128)
 k_ccm_fit(const Mode m, const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ data, const uint8_t* __restrict__ ok,
-          const uint16_t* __restrict__ idx, int n_frames, float* __restrict__ fit, uint8_t* __restrict__ valid)
+          const uint16_t* __restrict__ idx, int n_frames, float* __restrict__ fit, uint8_t* __restrict__ valid, const GivenHeader given)
 {
     __shared__ FitSmem sm[4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -232,7 +233,12 @@ k_ccm_fit(const Mode m, const uint8_t* __restrict__ rgb, const uint8_t* __restri
     const int W = m.width, H = m.height;
     const uint8_t* frame = rgb + (size_t)f * W * H * 3;
     if (lane < 8) { s.cnt[lane] = s.sr[lane] = s.sg[lane] = s.sb[lane] = 0; s.first[lane] = 0xFFFFFFFFu; }
-    if (lane == 0) {
+    if (lane == 0 && given.use) {
+        // CimbReader::init_ccm called by a host that kept the header itself (CimbReader::update_metadata on the host side)
+        for (int k = 0; k < 6; ++k) s.hdr[k] = given.hdr[k];
+        s.radioactive = given.radioactive;
+        s.has = (given.hdr[0] | given.hdr[1] | given.hdr[2] | given.hdr[3]) != 0;
+    } else if (lane == 0) {
         // what the symbol stream's chunk events leave in CimbReader::_fountainColorHeader (aligned_stream.h:39-116 with five
         // whole RS blocks per chunk: a chunk whose last block is bad raises no event and passes its bad flag on; otherwise the
         // event is a flush of the chunk when all its blocks are good and no flag was pending, else the "bad chunk" callback)
@@ -399,9 +405,12 @@ k_ccm_apply(const Mode m, const uint32_t* __restrict__ means, int n_frames, cons
 }  // namespace
 
 cudaError_t ccm_fit_launch(const Mode& m, const uint8_t* d_rgb, const uint8_t* d_data, const uint8_t* d_ok, const uint16_t* d_idx,
-                           int n_frames, float* d_fit, uint8_t* d_valid, cudaStream_t st)
+                           int n_frames, float* d_fit, uint8_t* d_valid, cudaStream_t st, const GivenHeader* given)
 {
-    k_ccm_fit<<<(n_frames + 3) / 4, 128, 0, st>>>(m, d_rgb, d_data, d_ok, d_idx, n_frames, d_fit, d_valid); count_launch();
+    GivenHeader g;
+    memset(&g, 0, sizeof(g));
+    if (given) g = *given;
+    k_ccm_fit<<<(n_frames + 3) / 4, 128, 0, st>>>(m, d_rgb, d_data, d_ok, d_idx, n_frames, d_fit, d_valid, g); count_launch();
     return cudaGetLastError();
 }
 cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_valid, const CcmArg& initial, float* d_used,

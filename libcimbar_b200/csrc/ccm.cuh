@@ -72,8 +72,11 @@ cudaError_t ccm_simple_launch(const Mode& m, const uint8_t* d_rgb, int n_frames,
 // color_correction == 2, after the symbol stream's RS pass: per frame the header the aligned_stream callbacks leave behind,
 // the colours it predicts, the fit (fit[f], valid[f]); then the carry (a frame without a fit keeps its predecessor's CCM,
 // frame 0 the context's) into used[f] / used_active[f]; then the colour decision of every cell from the stored means
+// given != nullptr (single frame): the header is not derived from the RS output but handed in by the caller
+// (CimbReader::init_ccm on a host that ran CimbReader::update_metadata itself); d_data / d_ok are then unused
+struct GivenHeader { uint8_t hdr[6]; uint8_t use; uint8_t pad; uint32_t radioactive; };
 cudaError_t ccm_fit_launch(const Mode& m, const uint8_t* d_rgb, const uint8_t* d_data, const uint8_t* d_ok, const uint16_t* d_idx,
-                           int n_frames, float* d_fit, uint8_t* d_valid, cudaStream_t st);
+                           int n_frames, float* d_fit, uint8_t* d_valid, cudaStream_t st, const GivenHeader* given = nullptr);
 cudaError_t ccm_carry_launch(int n_frames, const float* d_fit, const uint8_t* d_valid, const CcmArg& initial, float* d_used,
                              uint8_t* d_used_active, cudaStream_t st);
 cudaError_t ccm_apply_launch(const Mode& m, const uint32_t* d_means, int n_frames, const float* d_used, const uint8_t* d_used_active,

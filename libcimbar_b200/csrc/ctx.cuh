@@ -33,6 +33,7 @@ struct cb200_ctx {
     uint8_t* d_flags = nullptr;      // max_frames
     uint16_t* d_idx = nullptr;       // num_cells: slot -> cell (Interleave::interleave_indices)
     uint16_t* d_inv = nullptr;       // num_cells: cell -> slot (Interleave::interleave_reverse)
+    uint16_t* d_idx_ident = nullptr; // identity map for CB200_FLAG_NO_INTERLEAVE (created on first use)
     uint8_t* d_gen = nullptr;        // RS generator polynomial, ecc_bytes+1 coefficients
     // per-kernel timing (cb200_set_timing): events around every launch of the last pipeline call
     int l2_ahead = 0;                // K1: TMA L2-prefetch distance in stages (CB200_K1_L2_AHEAD overrides, tuning only)

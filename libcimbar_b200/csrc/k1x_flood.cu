@@ -36,6 +36,7 @@ constexpr int kFloodMaxEntries = 16384;  // listed frames whose raster/result ar
 
 __constant__ float cx_adjust[256];
 __constant__ unsigned long long cx_tiles_L[16];
+__constant__ uint4 cx_tiles_slot[16];            // (L_lo, L_hi, symbol, 0) at the tile's perfect-hash slot ((L_lo * hash_mul) >> 28)
 
 // ---------------------------------------------------------------------------------------------- work list
 // order-preserving compaction of the frames that need the exact walk; also writes the per-frame flags
@@ -360,19 +361,42 @@ k_flood_raster_fast(const Mode m, const uint8_t* __restrict__ rgb, const uint32_
 // std::priority_queue<decode_prio, vector, PrioCompare> with comp(a, b) = a.prio > b.prio: only the priority is compared,
 // so the pop order of equal priorities is whatever libstdc++'s sift-up / sift-down produce; both are restated literally.
 // Element i lives at shared word i + 1 (so the children 2h+1, 2h+2 are one aligned 64-bit load) while i < hs, else in
-// the global spill area at word i - hs (hs is odd, so a pair never straddles the two).
+// the global spill area at word i - hs (hs is odd, so a pair never straddles the two).  Shared memory is addressed through
+// 32-bit shared-window addresses and the shared / global choice is a predicate, not a branch.
 // Every lane of the walking warp executes push and pop with the same arguments and keeps the same `n`: loads are
 // broadcasts, stores are done by one lane, and the sift-down is spread over the lanes (below).
 struct Heap {
-    uint32_t* sm; uint32_t* spill; int n; int hs;
-    __device__ __forceinline__ uint32_t get(int i) const { return i < hs ? sm[i + 1] : __ldcg(spill + (i - hs)); }
-    __device__ __forceinline__ void set(int i, uint32_t v) { if (i < hs) sm[i + 1] = v; else __stcg(spill + (i - hs), v); }
-    // elements 2 node + 1 and 2 node + 2
-    __device__ __forceinline__ uint2 children(int node) const
+    uint32_t sm;          // shared-window byte address of word 0 (element i at sm + 4 i + 4)
+    uint32_t* spill; int n; int hs;
+    __device__ __forceinline__ uint32_t get(int i) const
+    {
+        uint32_t v;
+        const int in_sm = i < hs;
+        asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0;\n"
+                     "  @p ld.shared.u32 %0, [%1];\n"
+                     "  @!p ld.global.cg.u32 %0, [%2]; }"
+                     : "=r"(v) : "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(in_sm) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void set(int i, uint32_t v, bool doit) const
+    {
+        const int in_sm = doit && i < hs, in_gl = doit && i >= hs;
+        asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %3, 0; setp.ne.s32 q, %4, 0;\n"
+                     "  @p st.shared.u32 [%0], %2;\n"
+                     "  @q st.global.cg.u32 [%1], %2; }"
+                     :: "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(v), "r"(in_sm), "r"(in_gl) : "memory");
+    }
+    // elements 2 node + 1 and 2 node + 2 (nothing is loaded when !doit)
+    __device__ __forceinline__ uint2 children(int node, bool doit) const
     {
         const int c = 2 * node + 2;
-        if (c < hs) return *reinterpret_cast<const uint2*>(sm + c);
-        return __ldcg(reinterpret_cast<const uint2*>(spill + (c - 1 - hs)));
+        const int in_sm = doit && c < hs, in_gl = doit && c >= hs;
+        uint2 r = make_uint2(0u, 0u);
+        asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %4, 0; setp.ne.s32 q, %5, 0;\n"
+                     "  @p ld.shared.v2.u32 {%0, %1}, [%2];\n"
+                     "  @q ld.global.cg.v2.u32 {%0, %1}, [%3]; }"
+                     : "+r"(r.x), "+r"(r.y) : "r"(sm + 4u * (uint32_t)c), "l"(spill + (c - 1 - hs)), "r"(in_sm), "r"(in_gl) : "memory");
+        return r;
     }
 };
 __device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 25; }
@@ -386,10 +410,10 @@ __device__ __forceinline__ void heap_push(Heap& h, uint32_t e, int lane)
         const int parent = (hole - 1) >> 1;
         const uint32_t pe = h.get(parent);
         if (hprio(pe) <= prio) break;
-        if (lane == 0) h.set(hole, pe);
+        h.set(hole, pe, lane == 0);
         hole = parent;
     }
-    if (lane == 0) h.set(hole, e);
+    h.set(hole, e, lane == 0);
     __syncwarp();
 }
 
@@ -416,50 +440,102 @@ __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
 // std::pop_heap + pop_back (__adjust_heap with the hole at the root, then __push_heap of the last element):
 //   while (second < (len - 1) / 2) { second = 2 (second + 1); if (v[second].prio > v[second - 1].prio) second--; v[hole] = v[second]; hole = second; }
 //   if (len even && second == (len - 2) / 2) { second = 2 (second + 1); v[hole] = v[second - 1]; hole = second - 1; }
-//   sift `value` up from the hole.
-// The descent path does not depend on `value`, only on which child each node prefers.  One round handles the 31 nodes of
-// the five-level subtree under the current hole: lane i loads the two children of its node, the preferences are collected
-// with one ballot, every lane decides from its ancestors' bits whether the descent passes through its node, and the lanes on
-// the path move their preferred child up.  13 levels cost three memory round trips instead of thirteen.
-__device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane)
+//   sift `value` (the former last element) up from the hole: while (parent.prio > value.prio) { v[hole] = v[parent]; hole = parent; }
+// The descent path h_0 = 0, h_1, ..., h_L does not depend on `value`, only on which child each node prefers.  One round
+// handles the 31 nodes of the five-level subtree under the current hole: lane i loads the two children of its node, the
+// preferences are collected with one ballot, and every lane decides from its ancestors' bits whether the descent passes
+// through its node -- a dozen levels cost three memory round trips instead of a dozen.  Nothing is stored during the descent:
+// the lane of path level k keeps m_k = old v[h_(k+1)], the value that WOULD move up into h_k.  The sift-up then walks the same
+// path backwards and undoes those moves while prio(m_k) > prio(value); so with s = 1 + max { k : prio(m_k) <= prio(value) }
+// the net effect is v[h_k] = m_k for k < s, v[h_s] = value, everything below untouched -- s + 1 stores, no reads.
+constexpr int kPopRounds = 3;          // 15 levels: heaps of up to 65 535 entries (six times the largest seen); beyond: heap_pop_serial
+
+// the literal form, one level per step (only reached by heaps of more than 65 535 entries)
+__device__ __noinline__ void heap_pop_serial(Heap& h, int lane)
 {
     const uint32_t value = h.get(h.n - 1);
     const int len = --h.n;
     if (len == 0) return;
-    const int lim = (len - 1) >> 1;
-    int hole = 0;
-    while (hole < lim) {
-        const int node = ((hole + 1) << sl.d) - 1 + sl.j;
-        const bool has2 = sl.valid && node < lim;             // both children inside the heap: the descent continues below it
-        uint2 c = make_uint2(0u, 0u);
-        if (has2) c = h.children(node);
-        const bool left = hprio(c.y) > hprio(c.x);            // right child strictly worse -> left child moves up
-        const uint32_t pref = __ballot_sync(0xffffffffu, has2 && left);
-        // the descent reaches this node iff every ancestor has two children (<=> its parent has) and points towards it
-        const bool parent_ok = (sl.d == 0) || (((hole + 1) << sl.dp) - 1 + (sl.j >> 1)) < lim;
-        const bool reached = sl.valid && parent_ok && (((pref ^ sl.anc_want) & sl.anc_mask) == 0u);
-        if (reached && has2) h.set(node, left ? c.x : c.y);
-        // where the round ends: at the first reached node without two children, or below the subtree's last level
-        const bool ends = reached && (!has2 || sl.d == 4);
-        const uint32_t eb = __ballot_sync(0xffffffffu, ends);
-        const int nxt = has2 ? 2 * node + 2 - (left ? 1 : 0) : node;
-        hole = __shfl_sync(0xffffffffu, nxt, __ffs(eb) - 1);
+    int hole = 0, second = 0;
+    while (second < ((len - 1) >> 1)) {
+        second = 2 * (second + 1);
+        uint32_t a = h.get(second);
+        const uint32_t b = h.get(second - 1);
+        if (hprio(a) > hprio(b)) { second--; a = b; }
+        h.set(hole, a, lane == 0);
+        hole = second;
     }
-    __syncwarp();                                             // the moves above are visible to the reads below
-    if ((len & 1) == 0 && hole == ((len - 2) >> 1)) {         // a last node with only a left child
-        const uint32_t only = h.get(2 * hole + 1);
-        if (lane == 0) h.set(hole, only);
-        hole = 2 * hole + 1;
+    if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
+        second = 2 * (second + 1);
+        h.set(hole, h.get(second - 1), lane == 0);
+        hole = second - 1;
     }
+    __syncwarp();
     const uint32_t vp = hprio(value);
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
         const uint32_t pe = h.get(parent);
         if (hprio(pe) <= vp) break;
-        if (lane == 0) h.set(hole, pe);
+        h.set(hole, pe, lane == 0);
         hole = parent;
+        __syncwarp();
     }
-    if (lane == 0) h.set(hole, value);
+    h.set(hole, value, lane == 0);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane, int serial_above)
+{
+    if (h.n > serial_above) { heap_pop_serial(h, lane); return; }
+    const uint32_t value = h.get(h.n - 1);                    // (often in L2: in flight during the rounds, used after them)
+    const int len = --h.n;
+    if (len == 0) return;
+    const int lim = (len - 1) >> 1;
+    int hole = 0, level = 0;
+    int node_r[kPopRounds]; uint32_t m_r[kPopRounds]; int lvl_r[kPopRounds];     // lvl < 0: this lane moved nothing in that round
+#pragma unroll
+    for (int r = 0; r < kPopRounds; ++r) {
+        lvl_r[r] = -1; node_r[r] = 0; m_r[r] = 0;
+        if (hole < lim) {                                      // warp-uniform
+            const int node = ((hole + 1) << sl.d) - 1 + sl.j;
+            const bool has2 = sl.valid && node < lim;          // both children inside the heap: the descent continues below it
+            const uint2 c = h.children(node, has2);
+            const bool left = hprio(c.y) > hprio(c.x);         // right child strictly worse -> the left child moves up
+            const uint32_t pref = __ballot_sync(0xffffffffu, has2 && left);
+            // the descent reaches this node iff its parent has two children and every ancestor points towards it
+            const bool parent_ok = (sl.d == 0) || (((hole + 1) << sl.dp) - 1 + (sl.j >> 1)) < lim;
+            const bool reached = sl.valid && parent_ok && (((pref ^ sl.anc_want) & sl.anc_mask) == 0u);
+            if (reached && has2) { lvl_r[r] = level + sl.d; node_r[r] = node; m_r[r] = left ? c.x : c.y; }
+            // the round ends at the first reached node without two children, or below the subtree's last level
+            const bool ends = reached && (!has2 || sl.d == 4);
+            const uint32_t eb = __ballot_sync(0xffffffffu, ends);
+            const int nxt = has2 ? 2 * node + 2 - (left ? 1 : 0) : node;
+            const int src = __ffs(eb) - 1;
+            hole = __shfl_sync(0xffffffffu, nxt, src);
+            level += __shfl_sync(0xffffffffu, sl.d + (has2 ? 1 : 0), src);
+        }
+    }
+    // a last node with only a left child: one more level of the path (uniform)
+    const bool lone = (len & 1) == 0 && hole == ((len - 2) >> 1);
+    uint32_t m_lone = 0; int node_lone = hole;
+    if (lone) { m_lone = h.get(2 * hole + 1); hole = 2 * hole + 1; }
+    const int lvl_lone = level;                                // the lone move fills path level `level`; the final hole is one deeper
+    // ---- s = 1 + deepest path level whose moved value does not have to go back down
+    const uint32_t vp = hprio(value);
+    int kmax = -1;
+#pragma unroll
+    for (int r = 0; r < kPopRounds; ++r) if (lvl_r[r] >= 0 && hprio(m_r[r]) <= vp) kmax = max(kmax, lvl_r[r]);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lone && hprio(m_lone) <= vp) kmax = lvl_lone;          // the deepest level there is
+    const int s = kmax + 1;
+    const int last_level = level + (lone ? 1 : 0);             // level of the final hole
+#pragma unroll
+    for (int r = 0; r < kPopRounds; ++r) {
+        const bool mine = lvl_r[r] >= 0 && lvl_r[r] <= s && lvl_r[r] < last_level + 1;
+        h.set(node_r[r], lvl_r[r] == s ? value : m_r[r], mine);
+    }
+    if (lone && lvl_lone <= s) h.set(node_lone, lvl_lone == s ? value : m_lone, lane == 0);
+    if (s == last_level) h.set(hole, value, lane == 0);
     __syncwarp();
 }
 
@@ -473,24 +549,22 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uin
 }
 
 // ---------------------------------------------------------------------------------------------- the walk
-// Shared memory of one walking warp: heap[hs + 1] words, the _remaining bitmap (1 bit per cell), the tile dictionary by
-// perfect-hash slot.  One byte per cell lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in
-// parallel, off the pop chain):
+// Shared memory of one walking warp: heap[hs + 1] words, then the _remaining bitmap (1 bit per cell).  One byte per cell
+// lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel, off the pop chain):
 //   0 = decoded (FloodDecodePositions::_remaining false), else best_prio + 1 (0xFF for the initial 0xFE).
 // Why the inherit record (drift, best_prio, cooldown; FloodDecodePositions.h:17) can ride in the heap entry: update()
 // only rewrites it when the new error is strictly lower (FloodDecodePositions.cpp:75), and pushes an entry with that
 // error, so of all entries of a cell the one that pops first is always the latest, and it carries the record as it stands.
 // The exception are the eight entries reset() seeds with priority 0/1 while the record says (0,0,0xFE,0xFE): when such an
 // entry pops, the record is the latest update still sitting in the heap (found by a warp-wide scan), else the initial one.
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 32)
 k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
              int heap_smem, const uint16_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
-             uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace)
+             uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace, int serial_above)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
     uint32_t* heap_sm = reinterpret_cast<uint32_t*>(walk_smem);
     uint32_t* remaining = heap_sm + heap_smem + 1;
-    uint4* tiles_by_slot = reinterpret_cast<uint4*>(remaining + kMaxCells / 32);       // (L_lo, L_hi, symbol, 0)
     uint8_t* prio = ws_prio + (size_t)blockIdx.x * kMaxCells;
     const int lane = threadIdx.x;
     const int W = m.width, ncells = m.num_cells, tiles_x = W >> 4;
@@ -498,10 +572,9 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
     const int cnt = chunk_count(counters, base, cap);
     const unsigned long long tileL = cx_tiles_L[lane & 15];
     const int narrow = m.cells_x - 2 * m.corner;
+    const float rcp_narrow = 1.0f / (float)narrow, rcp_wide = 1.0f / (float)m.cells_x;   // exact floor for q < 2^14 (q + 0.5 trick)
     const SubtreeLane sl = subtree_lane(lane);
-    Heap heap; heap.sm = heap_sm; heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
-    if (lane < 16) tiles_by_slot[((uint32_t)tileL * m.hash_mul) >> 28] = make_uint4((uint32_t)tileL, (uint32_t)(tileL >> 32), (uint32_t)lane, 0u);
-    __syncwarp();
+    Heap heap; heap.sm = (uint32_t)__cvta_generic_to_shared(heap_sm); heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
 
     while (true) {
         uint32_t k = 0;
@@ -537,14 +610,13 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             const uint32_t rem_bit = 1u << (ci & 31);
             if (!(remaining[ci >> 5] & rem_bit)) {           // stale entry of a cell that is already decoded: skipped
                 __syncwarp();
-                heap_pop(heap, sl, lane);
+                heap_pop(heap, sl, lane, serial_above);
                 continue;
             }
             ++count;
-            // per-cell table (flood_build_cinfo): lanes 0-3 the direct neighbours (right, left, bottom, top), 4-11 the horizon
-            // chains, 12 / 13 the cell's position (CellPositions::compute_linear, CellPositions.cpp:5-50)
+            // neighbours: lanes 0-3 direct (right, left, bottom, top), 4-11 the horizon chains (see flood_build_cinfo)
             uint32_t cv = 0xFFFFu;
-            if (lane < 14) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
+            if (lane < 12) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
             uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
             int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
             if (code == kSeedCode) {                         // (scanned before the pop: the seed entry itself is excluded either way)
@@ -560,17 +632,32 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
             }
             const uint32_t cooldown = cd_value(code);
-            const int px = (int)__shfl_sync(0xffffffffu, cv, 12), py = (int)__shfl_sync(0xffffffffu, cv, 13);
+            // ---- cell position (CellPositions::compute_linear, CellPositions.cpp:5-50): arithmetic, so that the window loads
+            // do not wait for the neighbour table
+            int px, py;
+            if (ci < m.top_cells) {
+                const int kk = __float2int_rz(((float)ci + 0.5f) * rcp_narrow), c = ci - kk * narrow;
+                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * kk;
+            } else if (ci < m.top_cells + m.mid_cells) {
+                const int q = ci - m.top_cells;
+                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_wide), c = q - kk * m.cells_x;
+                px = m.cell_offset + kSpacing * c; py = m.cell_offset + kSpacing * (m.corner + kk);
+            } else {
+                const int q = ci - m.top_cells - m.mid_cells;
+                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_narrow), c = q - kk * narrow;
+                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * (m.cells_y - m.corner + kk);
+            }
             const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
-            // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r from (at most) two tiles
-            uint32_t ra = 0, rb = 0, rshift = 0;
+            // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r from (at most) two tiles; the rasters are read once
+            // per window and are far bigger than the L2: streaming loads, so that they do not evict the heaps and priority bytes
+            uint32_t ra = 0, rb = 0;
+            const uint32_t rshift = (uint32_t)(x - 1) & 15u;
             if (lane < 10) {
                 const uint32_t ti = raster_tile_index(tiles_x, x - 1, y - 1 + lane);
-                rshift = (uint32_t)(x - 1) & 15u;
-                ra = __ldg(raster + ti); rb = __ldg(raster + ti + 16);
+                ra = __ldcs(raster + ti); rb = __ldcs(raster + ti + 16);
             }
             __syncwarp();                                    // every lane has read the heap top / bitmap before they are rewritten
-            heap_pop(heap, sl, lane);
+            heap_pop(heap, sl, lane, serial_above);
             if (lane == 0) {
                 remaining[ci >> 5] &= ~rem_bit;
                 __stcg(prio + ci, (uint8_t)0);
@@ -578,21 +665,25 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             __syncwarp();                                    // the bitmap / prio writes are ordered before the reads below
             // the candidates' priority bytes: requested now, needed only after the scoring below
             uint32_t pv = 0;
-            if (lane >= 12) cv = 0xFFFFu;
             if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
             const uint32_t myrow = ((ra | (rb << 16)) >> rshift) & 0x3FFu;     // bit i = window col i
             // ---- fast path: the centre hash (drift id 4 = rows 1..8, cols 1..8) is a dictionary tile.  The reference's search
             // starts with id 4 and returns at once on distance 0 (CimbDecoder.cpp:101-132), whatever the cooldown.
-            uint32_t best_key;
+            uint32_t dist, sym, ncd;
+            int id, ndx, ndy, rx, ry;
+            bool exact;
             {
                 const uint32_t b = (myrow >> 1) & 0xFFu;
                 const uint32_t plo = (lane >= 1 && lane <= 4) ? b << (8 * (lane - 1)) : 0u;
                 const uint32_t phi = (lane >= 5 && lane <= 8) ? b << (8 * (lane - 5)) : 0u;
                 const uint32_t clo = __reduce_or_sync(0xffffffffu, plo), chi = __reduce_or_sync(0xffffffffu, phi);
-                const uint4 te = tiles_by_slot[(clo * m.hash_mul) >> 28];
-                best_key = (te.x == clo && te.y == chi) ? te.z : 0xFFFFFFFFu;      // key = dist << 8 | order << 4 | tile, dist = order = 0
+                const uint4 te = cx_tiles_slot[(clo * m.hash_mul) >> 28];          // uniform index: one constant-bank read
+                exact = te.x == clo && te.y == chi;
+                sym = te.z;
             }
-            if (best_key == 0xFFFFFFFFu) {                   // warp-uniform
+            if (exact) {                                     // warp-uniform
+                dist = 0; id = 4; ncd = 4; ndx = ddx; ndy = ddy; rx = x; ry = y;
+            } else {
                 uint32_t win[10];
 #pragma unroll
                 for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
@@ -615,31 +706,33 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
                 const int nq = all ? 9 : 5;
                 const uint32_t tile_lo = (uint32_t)tileL, tile_hi = (uint32_t)(tileL >> 32);
+                uint32_t best_key = 0xFFFFFFFFu;
 #pragma unroll
                 for (int it = 0; it < 5; ++it) {
                     if (it >= 3 && !all) break;                       // warp-uniform
                     const int q = 2 * it + (lane >> 4);
                     const uint32_t lo = __shfl_sync(0xffffffffu, hlo, q & 15), hi = __shfl_sync(0xffffffffu, hhi, q & 15);
-                    const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);          // packed order table, nibble q
-                    const bool valid = q < nq && !((uint32_t)id == cooldown && id != 4);   // CimbDecoder.cpp:116
+                    const int qid = (int)((0x620813754ULL >> (4 * q)) & 0xF);         // packed order table, nibble q
+                    const bool valid = q < nq && !((uint32_t)qid == cooldown && qid != 4);   // CimbDecoder.cpp:116
                     const uint32_t d = (uint32_t)(__popc(lo ^ tile_lo) + __popc(hi ^ tile_hi));
                     const uint32_t key = valid ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15)) : 0xFFFFFFFFu;
                     best_key = key < best_key ? key : best_key;
                 }
                 best_key = __reduce_min_sync(0xffffffffu, best_key);
+                // every lane derives the (warp-uniform) decision from the reduced key
+                dist = best_key >> 8; sym = best_key & 0xFu;
+                id = (int)((0x620813754ULL >> (4 * ((best_key >> 4) & 0xFu))) & 0xF);
+                const int bx = id % 3 - 1, by = id / 3 - 1;                       // CellDrift::driftPairs, CellDrift.h:13-15
+                ndx = clampi(ddx + bx, -7, 7); ndy = clampi(ddy + by, -7, 7);     // CellDrift.cpp:23-31
+                rx = x + bx; ry = y + by;
+                // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
+                if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
             }
-            // every lane derives the (warp-uniform) decision from the reduced key
-            const uint32_t dist = best_key >> 8, q = (best_key >> 4) & 0xFu, sym = best_key & 0xFu;
-            const int id = (int)((0x620813754ULL >> (4 * q)) & 0xF);
-            const int bx = id % 3 - 1, by = id / 3 - 1;                       // CellDrift::driftPairs, CellDrift.h:13-15
-            const int ndx = clampi(ddx + bx, -7, 7), ndy = clampi(ddy + by, -7, 7);   // CellDrift.cpp:23-31
-            uint32_t ncd;                                                     // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
-            if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
             if (lane == 0) {
-                result[ci] = ((uint32_t)(x + bx) & 0x7FFu) | (((uint32_t)(y + by) & 0x7FFu) << 11) | (sym << 22);
+                __stcs(result + ci, ((uint32_t)rx & 0x7FFu) | (((uint32_t)ry & 0x7FFu) << 11) | (sym << 22));
                 if (trace) {
                     CellTrace tr;
-                    tr.order = (uint16_t)(count - 1); tr.x = (int16_t)(x + bx); tr.y = (int16_t)(y + by);
+                    tr.order = (uint16_t)(count - 1); tr.x = (int16_t)rx; tr.y = (int16_t)ry;
                     tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
                     trace[(size_t)f * ncells + ci] = tr;
                 }
@@ -739,10 +832,16 @@ static size_t raster_smem_bytes(const Mode& m, bool sharpen)
     return (size_t)m.width * (size_t)(rows_g + (sharpen ? rows_h : 0) + 2 * rows_h);
 }
 
-cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16)
+cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16, uint32_t hash_mul)
 {
     cudaError_t e = cudaMemcpyToSymbol(cx_adjust, adjust256, sizeof(float) * 256);
     if (e != cudaSuccess) return e;
+    uint4 slots[16];
+    for (int t = 0; t < 16; ++t) {
+        const uint32_t lo = (uint32_t)tiles_L16[t], hi = (uint32_t)(tiles_L16[t] >> 32);
+        slots[(lo * hash_mul) >> 28] = make_uint4(lo, hi, (uint32_t)t, 0u);
+    }
+    if ((e = cudaMemcpyToSymbol(cx_tiles_slot, slots, sizeof(slots))) != cudaSuccess) return e;
     return cudaMemcpyToSymbol(cx_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
 }
 
@@ -750,7 +849,6 @@ cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* 
 // neighbours (right, left, bottom, top; update_adjacents), 4,5 right+1 / right+2, 6,7 left+1 / left+2 (horizontal horizon,
 // only when BOTH right and left exist, FloodDecodePositions.cpp:102), 8,9 top+1 / top+2, 10,11 bottom+1 / bottom+2 (vertical,
 // only when both top and bottom exist, :116); 0xFFFF = none.  Built from AdjacentCellFinder::find for every cell (adj_host).
-// Slots 12, 13: the cell's top-left pixel (CellPositions::compute_linear, CellPositions.cpp:5-50).
 static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<uint16_t>& out)
 {
     auto nb = [&](int cell, int dir) -> int { if (cell < 0) return -1; unsigned v = adj[(size_t)cell * 4 + dir]; return v == 0xFFFFu ? -1 : (int)v; };
@@ -766,11 +864,6 @@ static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<ui
         };
         if (right >= 0 && left >= 0) { chain(right, 0, 4); chain(left, 1, 6); }
         if (top >= 0 && bottom >= 0) { chain(top, 3, 8); chain(bottom, 2, 10); }
-        int k, cc, rbase, ncols, x0;
-        cell_row_col(m, i, k, cc);
-        cell_row_geom(m, k, rbase, ncols, x0);
-        o[12] = (uint16_t)(x0 + kSpacing * cc);
-        o[13] = (uint16_t)(m.cell_offset + kSpacing * k);
     }
 }
 
@@ -778,11 +871,11 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
 {
     memset(ws, 0, sizeof(*ws));
     ws->sm_count = sm_count;
-    // shared-memory heap entries per walking warp (must be odd): 2047 = the eleven top levels; deeper levels go to the
+    // shared-memory heap entries per walking warp (must be odd): 1023 = the ten top levels; deeper levels go to the
     // per-slot spill area in L2.  Shared memory per walk decides how many walks an SM holds (at most 32 blocks).
-    ws->heap_smem = 2047;
+    ws->heap_smem = 1023;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
-    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + 16 * sizeof(uint4);
+    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4;
     int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
@@ -790,6 +883,8 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     ws->slots = sm_count * per_sm;
     ws->max_entries = kFloodMaxEntries;
     if (const char* s = getenv("CB200_K1X_MAX_ENTRIES")) { int v = atoi(s); if (v >= 1 && v <= kFloodMaxEntries) ws->max_entries = v; }   // tests: force several chunks
+    ws->serial_above = 65536;                        // heaps beyond three five-level rounds pop one level at a time
+    if (const char* s = getenv("CB200_K1X_SERIAL_ABOVE")) ws->serial_above = atoi(s);      // tests: 0 forces the literal pop
     ws->spill_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->walk_smem)) != cudaSuccess) return e;
@@ -863,7 +958,7 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         count_launch();
         int wgrid = cap < ws.slots ? cap : ws.slots;
         k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
-                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace); count_launch();
+                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace, ws.serial_above); count_launch();
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);

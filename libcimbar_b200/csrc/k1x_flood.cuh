@@ -22,6 +22,7 @@ struct FloodWorkspace {
     int heap_smem;             // heap entries per walk kept in shared memory (odd)
     size_t walk_smem;          // dynamic shared memory of one walking warp
     size_t spill_cap;          // heap spill entries per slot
+    int serial_above;          // heap sizes above this use the one-level-per-step pop (65536; tests lower it)
     uint32_t* spill;           // [slots][spill_cap]
     uint8_t* prio;             // [slots][kMaxCells] per-cell priority bytes of the walk in that slot
     uint16_t* cinfo;           // [num_cells][16] update candidates in push order (0xFFFF = none)
@@ -30,7 +31,7 @@ struct FloodWorkspace {
     int entry_cap; uint16_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster in 16x16 tiles, per-cell x | y<<11 | sym<<22
 };
 
-cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16);
+cudaError_t flood_init_tables(const float* adjust256, const unsigned long long* tiles_L16, uint32_t hash_mul);
 // adj_host: [num_cells][4] = AdjacentCellFinder::find for every cell (built by the caller from the cell geometry)
 cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* adj_host, FloodWorkspace* ws);
 void flood_workspace_destroy(FloodWorkspace* ws);

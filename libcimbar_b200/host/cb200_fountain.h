@@ -5,6 +5,7 @@
 // (src/third_party_lib/wirehair/include/wirehair/wirehair.h), so an integrated build passes wirehair_decoder_create /
 // wirehair_decode / wirehair_recover / wirehair_free and gets the reference's behaviour chunk for chunk.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -64,19 +65,42 @@ public:
 			Stream st;
 			st.size = md.file_size();
 			st.codec = _api.decoder_create(nullptr, st.size, _chunkSize - FountainMetadata::md_size);
-			it = _streams.emplace(slot, st).first;
+			st.buffer.resize(_chunkSize);
+			it = _streams.emplace(slot, std::move(st)).first;
 		}
 		Stream& s = it->second;
 		if (s.size != md.file_size()) return -12;
-		if (!s.seen.insert(md.block_id()).second) return 0;          // FountainDecoder.h:50-52: never feed a block twice
-		int res = _api.decode(s.codec, md.block_id(), data + FountainMetadata::md_size, _chunkSize - FountainMetadata::md_size);
-		if (res != 0) return 0;
-		// complete: recover now (the reference's store() path) and drop the stream
+		// fountain_decoder_stream::write (fountain_decoder_stream.h:52-74): bytes accumulate in a chunk-sized buffer -- a short
+		// write is kept until the rest arrives, a long one spans chunks -- and every full buffer is one block for the codec
+		bool finished = false;
+		while (size > 0 and s.codec != nullptr)
+		{
+			unsigned n = std::min<unsigned>(size, _chunkSize - s.fill);
+			std::memcpy(s.buffer.data() + s.fill, data, n);
+			s.fill += n; data += n; size -= n;
+			if (s.fill == _chunkSize)
+			{
+				s.fill = 0;
+				unsigned block_id = ((unsigned)s.buffer[4] << 8) | s.buffer[5];
+				if (!s.seen.insert(block_id).second) continue;            // FountainDecoder.h:48-52: never feed a block twice
+				if (_api.decode(s.codec, block_id, s.buffer.data() + FountainMetadata::md_size, _chunkSize - FountainMetadata::md_size) == 0)
+				{
+					finished = true;
+					break;
+				}
+			}
+		}
+		if (!finished) return 0;
+		// complete: recover now (the reference's store() path with a write callback) and drop the stream.  Like the reference
+		// the return value is the file id even when recover fails (fountain_decoder_sink.h:158-166 ignores store()'s result);
+		// the file then simply is not available from file()
 		std::vector<uint8_t> bytes(s.size);
-		if (_api.recover(s.codec, bytes.data(), bytes.size()) != 0) return 0;
-		_done[md.id()] = std::move(bytes);
-		_api.free_codec(s.codec);
-		_streams.erase(it);
+		if (_api.recover(s.codec, bytes.data(), bytes.size()) == 0)
+		{
+			_done[md.id()] = std::move(bytes);
+			_api.free_codec(s.codec);
+			_streams.erase(it);
+		}
 		return (int64_t)md.id();
 	}
 
@@ -102,7 +126,7 @@ public:
 	unsigned num_done() const { return (unsigned)_done.size(); }
 
 protected:
-	struct Stream { void* codec = nullptr; unsigned size = 0; std::set<unsigned> seen; };
+	struct Stream { void* codec = nullptr; unsigned size = 0; std::set<unsigned> seen; std::vector<uint8_t> buffer; unsigned fill = 0; };
 	unsigned _chunkSize;
 	FountainCodecApi _api;
 	std::map<uint8_t, Stream> _streams;

@@ -7,6 +7,33 @@
 #include "../../libcimbar_b200/host/CimbDecoder.h"
 #include "../../libcimbar_b200/host/CimbReader.h"
 #include "../../libcimbar_b200/host/Decoder.h"
+#include "../../libcimbar_b200/host/cb200_fountain.h"
+
+// The stream classes are the caller's.  Where the reference checkout is on the include path (-I<ref>/src/lib, the CPU
+// compile check in tests/test_abi_host.py) the reference's own escrow_buffer_writer and aligned_stream are used UNMODIFIED,
+// which is the drop-in claim; on the GPU box (no reference) a local collector with the same concept stands in.
+#if defined(CB200_WITH_REFERENCE_STREAMS)
+#include "encoder/aligned_stream.h"
+#include "encoder/escrow_buffer_writer.h"
+#else
+class escrow_buffer_writer   // test-local stand-in: one buffer slot per write of exactly chunk_size bytes
+{
+public:
+	escrow_buffer_writer(unsigned char* space, unsigned slots, unsigned slot_bytes) : _space(space), _slots(slots), _slotBytes(slot_bytes) {}
+	bool good() const { return _ok; }
+	unsigned chunk_size() const { return _slotBytes; }
+	long tellp() const { return (long)_used * _slotBytes; }
+	unsigned buffers_in_use() const { return _used; }
+	escrow_buffer_writer& write(const char* data, unsigned length)
+	{
+		_ok = _ok and length == _slotBytes and _used < _slots;
+		if (_ok) { std::memcpy(_space + (size_t)_used * _slotBytes, data, length); ++_used; }
+		return *this;
+	}
+private:
+	unsigned char* _space; unsigned _slots, _slotBytes, _used = 0; bool _ok = true;
+};
+#endif
 
 #include <cstdio>
 #include <cstring>
@@ -88,7 +115,9 @@ int main(int argc, char** argv)
 		}
 	}
 	{   // CimbReaderTest: first 22 cells in flood order as "index=value" pairs, then the reader runs to exactly 12400 reads
-		CimbReader cr(img, cimbar::Config::color_mode());
+		CimbDecoder rdec(cimbar::Config::symbol_bits(), cimbar::Config::color_bits(), cimbar::Config::dark(), 0xFF);
+		rdec.clear_color_correction();
+		CimbReader cr(img, rdec, cimbar::Config::color_mode(), false, 0);     // CimbReaderTest.cpp:44 call shape
 		CHECK(!cr.done());
 		std::map<unsigned, unsigned> res;
 		int count = 0;
@@ -136,6 +165,115 @@ int main(int argc, char** argv)
 			CHECK(cd.get_best_color(0, 255, 255, 0) == 0); CHECK(cd.get_best_color(0, 255, 0, 0) == 3);
 			CHECK(cd.get_best_color(20, 200, 20, 0) == 3); CHECK(cd.get_best_color(155, 50, 155, 0) == 2);
 		}
+	}
+	{   // Decoder::do_decode restated call by call on the CimbReader / CimbDecoder mirrors with color_correction 2
+		// (Decoder.h:60-117 + :171-189): read() every cell, track the fountain header through update_metadata as the
+		// aligned_stream callbacks would, init_ccm, then read_color() -- must give the colours of Decoder::decode_fountain
+		if (!cimbar::Config::legacy_mode())
+		{
+			CimbDecoder cdec(cimbar::Config::symbol_bits(), cimbar::Config::color_bits(), cimbar::Config::dark(), 0xFF);
+			cdec.clear_color_correction();
+			CimbReader reader(img, cdec, cimbar::Config::color_mode(), false, 2);
+			std::vector<unsigned> idx(cimbar::Config::total_cells());
+			{
+				std::vector<uint16_t> m(idx.size());
+				cb200_interleave_indices(cimbar::Config::mode_val(), m.data());
+				for (size_t slot = 0; slot < m.size(); ++slot) idx[m[slot]] = (unsigned)slot;       // Interleave::interleave_reverse
+			}
+			std::vector<PositionData> colorPositions(reader.num_reads());
+			std::vector<uint8_t> symbols(reader.num_reads());
+			while (!reader.done())
+			{
+				PositionData pos;
+				unsigned bits = reader.read(pos);
+				symbols[pos.i] = (uint8_t)bits;
+				colorPositions[pos.i] = pos;
+			}
+			// the header events of the symbol stream: decode the frame once more through the Decoder mirror with ECC to get the
+			// symbol-stream chunks (the RS stage is not part of the reader) and replay them as update_metadata calls
+			Decoder plain;
+			plain.clear_color_correction();
+			std::vector<unsigned char> space(cimbar::Config::fountain_chunks_per_frame() * cimbar::Config::fountain_chunk_size());
+			std::vector<uint8_t> data(cimbar::Config::capacity() * (cimbar::Config::ecc_block_size() - cimbar::Config::ecc_bytes()) / cimbar::Config::ecc_block_size());
+			std::stringstream blocks;
+			plain.decode(img, blocks, false, 0);
+			std::string all = blocks.str();
+			const unsigned cs = cimbar::Config::fountain_chunk_size();
+			const unsigned sym_chunks = cimbar::Config::capacity(cimbar::Config::symbol_bits()) * (cimbar::Config::ecc_block_size() - cimbar::Config::ecc_bytes()) / cimbar::Config::ecc_block_size() / cs;
+			bool clean = true;     // (only frames whose symbol stream decodes completely are replayed here: zero blocks would need the bad-chunk events)
+			for (unsigned q = 0; q < sym_chunks; ++q)
+			{
+				bool zero = true;
+				for (unsigned k = 0; k < cs; ++k) zero = zero and all[(size_t)q * cs + k] == 0;
+				clean = clean and !zero;
+			}
+			if (clean)
+			{
+				for (unsigned q = 0; q < sym_chunks; ++q) reader.update_metadata(&all[(size_t)q * cs], cs, cs);
+				reader.init_ccm(cimbar::Config::color_bits(), cimbar::Config::interleave_blocks(), cimbar::Config::interleave_partitions(),
+				                cimbar::Config::fountain_chunks_per_frame());
+				std::vector<uint8_t> colors(reader.num_reads());
+				for (const PositionData& p : colorPositions) colors[p.i] = (uint8_t)reader.read_color(p);
+				std::ofstream(prefix + ".cells_cc2", std::ios::binary).write(reinterpret_cast<const char*>(colors.data()), colors.size());
+				float m9[9];
+				if (cdec.get_ccm(m9)) std::ofstream(prefix + ".ccm_reader", std::ios::binary).write(reinterpret_cast<const char*>(m9), sizeof(m9));
+			}
+			cdec.clear_color_correction();
+		}
+	}
+	{   // the thread's CCM survives the Decoder object (CimbDecoder.cpp:69-73): a fresh Decoder per frame, as in
+		// cimbar_recv_js.cpp:164, still decodes the second frame with the matrix the first one fitted; and the batched
+		// decode_fountain(span) gives the same chunks as frame-by-frame calls
+		std::vector<unsigned char> a(cimbar::Config::fountain_chunks_per_frame() * cimbar::Config::fountain_chunk_size() * 2), b(a.size());
+		unsigned good_a = 0, good_b = 0;
+		float ma[9] = {0}, mb[9] = {0};
+		bool has_a, has_b;
+		{
+			Decoder().clear_color_correction();
+			escrow_buffer_writer w(a.data(), 2 * cimbar::Config::fountain_chunks_per_frame(), cimbar::Config::fountain_chunk_size());
+			{ Decoder d; good_a += d.decode_fountain(img, w); }
+			{ Decoder d; good_a += d.decode_fountain(img, w); has_a = d.get_ccm(ma); }
+		}
+		{
+			Decoder().clear_color_correction();
+			escrow_buffer_writer w(b.data(), 2 * cimbar::Config::fountain_chunks_per_frame(), cimbar::Config::fountain_chunk_size());
+			Decoder d;
+			Image two[2] = {img, img};
+			good_b = d.decode_fountain(two, 2, w);
+			has_b = d.get_ccm(mb);
+		}
+		CHECK(good_a == good_b);
+		CHECK(std::memcmp(a.data(), b.data(), good_a) == 0);
+		CHECK(has_a == has_b and (!has_a or std::memcmp(ma, mb, sizeof(ma)) == 0));
+		Decoder().clear_color_correction();
+	}
+	{   // Decoder(use_ecc, interleave = false): cells in linear order (Interleave.h:10-16); written for the driver to compare
+		Decoder lin(false, false);
+		lin.clear_color_correction();
+		std::stringstream ss;
+		unsigned n = lin.decode(img, ss, false, 0);
+		CHECK(n == cimbar::Config::capacity());
+		std::ofstream(prefix + ".raw_nointerleave", std::ios::binary) << ss.str();
+	}
+	{   // a short write into the fountain sink is buffered until the rest of the chunk arrives (fountain_decoder_stream.h:52-74)
+		struct Fake { static void* create(void*, uint64_t, uint32_t) { return new int(0); }
+		              static int decode(void* c, unsigned, const void*, uint32_t) { return ++*static_cast<int*>(c) >= 2 ? 0 : 1; }
+		              static int recover(void*, void* out, uint64_t n) { std::memset(out, 7, n); return 0; }
+		              static void free_codec(void* c) { delete static_cast<int*>(c); } };
+		FountainCodecApi api{Fake::create, Fake::decode, Fake::recover, Fake::free_codec};
+		fountain_sink sink(625, api);
+		std::vector<char> chunk(625, 1);
+		FountainMetadata md(3, 1000, 0);
+		std::memcpy(chunk.data(), md.d, 6);
+		std::memcpy(chunk.data() + 300, md.d, 6);                          // decode_frame reads the stream id from the head of every call
+		CHECK(sink.decode_frame(chunk.data(), 5) == -10);
+		CHECK(sink.decode_frame(chunk.data(), 300) == 0);                 // kept, nothing decoded yet
+		CHECK(sink.decode_frame(chunk.data() + 300, 325) == 0);           // (header of the continuation bytes must parse: same id) -> block 0 fed
+		FountainMetadata md1(3, 1000, 1);
+		std::memcpy(chunk.data(), md1.d, 6);
+		int64_t done = sink.decode_frame(chunk.data(), 625);
+		CHECK(done == (int64_t)md1.id());
+		CHECK(sink.is_done(md1.id()) and sink.file(md1.id()) and sink.file(md1.id())->size() == 1000);
 	}
 	std::printf(fails ? "shim_test: %d failure(s)\n" : "shim_test: ok\n", fails);
 	return fails ? 1 : 0;

@@ -63,3 +63,19 @@ def test_no_gpu_means_loud_failure():
     with pytest.raises(cb.Cb200Error) as e:
         cb.Context(68, max_frames=1)
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_mirrors_compile_against_the_references_own_stream_classes():
+    """tests/cpp/shim_test.cpp drives the Decoder / CimbReader / CimbDecoder mirrors with the reference's call shapes; here it is
+    compiled (syntax only, no GPU needed) once with the test-local chunk collector and, where the reference checkout exists,
+    once against the reference's unmodified escrow_buffer_writer / aligned_stream headers"""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "shim_test.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", src])
+    ref = "/root/reference/src/lib"
+    if os.path.isdir(ref):
+        subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-DCB200_WITH_REFERENCE_STREAMS", "-I" + ref, src])
+    # nothing of the reference's stream classes is restated in the product headers
+    hosts = os.path.join(ROOT, "libcimbar_b200", "host")
+    text = "".join(open(os.path.join(hosts, f)).read() for f in os.listdir(hosts))
+    assert "class aligned_stream" not in text and "class escrow_buffer_writer" not in text

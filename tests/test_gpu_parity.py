@@ -420,6 +420,32 @@ def test_cpp_shims_rerun_reference_unit_tests(cb, tmp_path):
                     assert not os.path.exists(prefix + ".ccm")
                 else:
                     assert np.array_equal(np.fromfile(prefix + ".ccm", dtype=np.float32).reshape(3, 3), want_ccm)
+        # Decoder(false, interleave=false): cells in linear order
+        import copy
+        mlin = copy.copy(m)
+        mlin.interleave_blocks = 0
+        assert np.array_equal(np.fromfile(prefix + ".raw_nointerleave", dtype=np.uint8), ORA.decode_raw(mlin, rgb)), (sample, mode)
+        # do_decode restated on the CimbReader / CimbDecoder mirrors with color_correction 2 (read, update_metadata, init_ccm,
+        # read_color): the colours and the fitted matrix of one fresh reference decoder
+        if os.path.exists(prefix + ".cells_cc2"):
+            ORA.set_ccm(None)
+            try:
+                raw_cc2 = np.zeros(ORA.capacity(m), np.uint8)
+                ORA.decode_fountain(m, rgb, color_correction=2)
+                want_ccm2 = ORA.get_ccm()
+                # colours per cell under that matrix == what decode_raw gives with the matrix active
+                _, ocells = ORA.decode_raw(m, rgb, want_cells=True)
+            finally:
+                ORA.set_ccm(None)
+            got_cols = np.fromfile(prefix + ".cells_cc2", dtype=np.uint8)
+            assert np.array_equal(got_cols, ocells["color"]), (sample, mode)
+            if want_ccm2 is None:
+                assert not os.path.exists(prefix + ".ccm_reader")
+            else:
+                assert np.array_equal(np.fromfile(prefix + ".ccm_reader", dtype=np.float32).reshape(3, 3), want_ccm2)
+        for ext in (".cells_cc2", ".ccm_reader"):
+            if os.path.exists(prefix + ext):
+                os.remove(prefix + ext)
         lines = open(prefix + ".first22").read().split("\n")
         if (sample, mode) in first22:
             assert lines[0] == first22[(sample, mode)]
