@@ -46,6 +46,10 @@ def parse_args():
                     help="N > 1: how the chunk records reach rank 0 -- window = the RS kernels store straight into rank 0's HBM over "
                          "NVLink (CUDA IPC peer mapping, cb200_gather_slot/publish/wait); nccl = cb200_gather_chunks (ncclSend/Recv on a "
                          "side stream, double buffered); torch = torch.distributed.gather on the decode stream (round-1 behaviour)")
+    ap.add_argument("--fountain", action="store_true",
+                    help="BASELINE configs[3]: fountain-encoded file, frames sharded over the ranks, records to rank 0, wirehair "
+                         "reassembly checked by SHA-256 (libcimbar_b200/fountain_bench.py)")
+    ap.add_argument("--file-mb", type=float, default=30.0, help="--fountain: file size in MB (30 = the config)")
     ap.add_argument("--e2e-frames", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -582,6 +586,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.fountain:
+        from libcimbar_b200 import fountain_bench
+        fountain_bench.run(args)
     else:
         run_ours(args)
 

@@ -269,6 +269,10 @@ typedef void (*cb200_codec_free_fn)(void* codec);
 
 cb200_sink* cb200_sink_create(unsigned chunk_size, cb200_codec_create_fn create_fn, cb200_codec_decode_fn decode_fn,
                               cb200_codec_recover_fn recover_fn, cb200_codec_free_fn free_fn);
+/* same, with the codec taken from a shared library that exports wirehair's C API (wirehair_init_, wirehair_decoder_create,
+   wirehair_decode, wirehair_recover, wirehair_free): the reference's third-party codec compiled unmodified
+   (libcimbar_b200/build.py build_wirehair -> libcimbar_b200/lib/libwirehair.so).  NULL on failure. */
+cb200_sink* cb200_sink_create_wirehair(unsigned chunk_size, const char* wirehair_library);
 void cb200_sink_destroy(cb200_sink* sink);
 /* one chunk (6-byte header + payload): > 0 = file id (encode_id|size word) when the file completed, 0 = progress,
    -1 = already done, -10/-11/-12 = malformed (same values as the reference) */

@@ -24,7 +24,7 @@ EXPORTS = [
     "cb200_sync", "cb200_decode_raw_dev", "cb200_rs_correct_dev", "cb200_decode_chunks_dev", "cb200_decode_raw",
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
-    "cb200_sink_create", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
+    "cb200_sink_create", "cb200_sink_create_wirehair", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
     "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
     "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_wait",
     "cb200_gather_release", "cb200_gather_acquire",
@@ -82,6 +82,8 @@ def load_library():
     lib.cb200_get_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     lib.cb200_sink_create.restype = vp
     lib.cb200_sink_create.argtypes = [C.c_uint, vp, vp, vp, vp]
+    lib.cb200_sink_create_wirehair.restype = vp
+    lib.cb200_sink_create_wirehair.argtypes = [C.c_uint, C.c_char_p]
     lib.cb200_sink_destroy.argtypes = [vp]
     lib.cb200_sink_decode_frame.restype = C.c_int64
     lib.cb200_sink_decode_frame.argtypes = [vp, u8p, C.c_uint]
@@ -341,13 +343,19 @@ class FountainSink:
     """Rank-0 fountain ingest (cb200_sink_*): header parse, de-dup and stream bookkeeping on the host, with the
     fountain codec (wirehair) supplied by the caller as a ctypes library exposing wirehair's C API."""
 
-    def __init__(self, chunk_size, codec_lib):
+    def __init__(self, chunk_size, codec_lib=None):
+        """codec_lib: a ctypes library exposing wirehair's C API, or None / a path for the wirehair build that ships with the
+        package (lib/libwirehair.so, built by libcimbar_b200.build.build_wirehair)"""
         self.lib = load_library()
-        fn = lambda name: C.cast(getattr(codec_lib, name), C.c_void_p)
-        self._h = self.lib.cb200_sink_create(chunk_size, fn("wirehair_decoder_create"), fn("wirehair_decode"),
-                                             fn("wirehair_recover"), fn("wirehair_free"))
+        if codec_lib is None or isinstance(codec_lib, (str, bytes)):
+            path = codec_lib or os.path.join(HERE, "lib", "libwirehair.so")
+            self._h = self.lib.cb200_sink_create_wirehair(chunk_size, path.encode() if isinstance(path, str) else path)
+        else:
+            fn = lambda name: C.cast(getattr(codec_lib, name), C.c_void_p)
+            self._h = self.lib.cb200_sink_create(chunk_size, fn("wirehair_decoder_create"), fn("wirehair_decode"),
+                                                 fn("wirehair_recover"), fn("wirehair_free"))
         if not self._h:
-            raise Cb200Error("cb200_sink_create failed")
+            raise Cb200Error("cb200_sink_create failed (is lib/libwirehair.so built? python -m libcimbar_b200.build)")
         self.chunk_size = chunk_size
 
     def close(self):

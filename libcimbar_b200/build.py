@@ -69,5 +69,29 @@ def build(force=False, verbose=False):
     return LIB
 
 
+WIREHAIR_LIB = os.path.join(HERE, "lib", "libwirehair.so")
+WIREHAIR_SRC = "/root/reference/src/third_party_lib/wirehair"
+
+
+def build_wirehair(force=False, verbose=False):
+    """wirehair -- the reference's third-party fountain codec (P15, stays on the rank-0 host) -- as a shared library of its own:
+    its four translation units compiled UNMODIFIED from where they lie in the reference checkout (nothing is copied into this
+    repository).  Where the checkout is absent (the GPU box) the prebuilt file that travelled with the snapshot is used.
+    The product binds it at run time (cb200_sink_create_wirehair), exactly as libcimbar links it."""
+    if not os.path.isdir(WIREHAIR_SRC):
+        return WIREHAIR_LIB if os.path.exists(WIREHAIR_LIB) else None
+    srcs = [os.path.join(WIREHAIR_SRC, f) for f in ("wirehair.cpp", "gf256.cpp", "WirehairCodec.cpp", "WirehairTools.cpp")]
+    if not force and os.path.exists(WIREHAIR_LIB) and all(os.path.getmtime(x) <= os.path.getmtime(WIREHAIR_LIB) for x in srcs):
+        return WIREHAIR_LIB
+    os.makedirs(os.path.dirname(WIREHAIR_LIB), exist_ok=True)
+    cmd = ["g++", "-std=c++11", "-O3", "-mavx2", "-mssse3", "-fPIC", "-shared", "-I" + os.path.join(WIREHAIR_SRC, "include"),
+           "-I" + WIREHAIR_SRC, "-o", WIREHAIR_LIB] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return WIREHAIR_LIB
+
+
 if __name__ == "__main__":
+    print(build_wirehair(force="--force" in sys.argv, verbose=True))
     print(build(force="--force" in sys.argv, verbose=True))

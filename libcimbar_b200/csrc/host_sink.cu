@@ -3,8 +3,10 @@
 #include "../../include/cb200.h"
 #include "../host/cb200_fountain.h"
 
+#include <dlfcn.h>
 #include <cstring>
 #include <new>
+#include <string>
 
 using cb200::fountain_sink;
 using cb200::FountainCodecApi;
@@ -22,6 +24,22 @@ cb200_sink* cb200_sink_create(unsigned chunk_size, cb200_codec_create_fn create_
     if (!s) return nullptr;
     s->impl = new fountain_sink(chunk_size, api);
     return s;
+}
+
+// the reference's own fountain codec, bound at run time: wirehair's C API (wirehair/wirehair.h) from a shared library
+cb200_sink* cb200_sink_create_wirehair(unsigned chunk_size, const char* wirehair_library)
+{
+    if (chunk_size <= 6) return nullptr;
+    void* lib = dlopen(wirehair_library && *wirehair_library ? wirehair_library : "libwirehair.so", RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return nullptr;
+    typedef int (*init_fn)(int);
+    init_fn init = reinterpret_cast<init_fn>(dlsym(lib, "wirehair_init_"));
+    cb200_codec_create_fn c = reinterpret_cast<cb200_codec_create_fn>(dlsym(lib, "wirehair_decoder_create"));
+    cb200_codec_decode_fn d = reinterpret_cast<cb200_codec_decode_fn>(dlsym(lib, "wirehair_decode"));
+    cb200_codec_recover_fn r = reinterpret_cast<cb200_codec_recover_fn>(dlsym(lib, "wirehair_recover"));
+    cb200_codec_free_fn f = reinterpret_cast<cb200_codec_free_fn>(dlsym(lib, "wirehair_free"));
+    if (!init || !c || !d || !r || !f || init(2 /* WIREHAIR_VERSION */) != 0) return nullptr;
+    return cb200_sink_create(chunk_size, c, d, r, f);
 }
 
 void cb200_sink_destroy(cb200_sink* s)
