@@ -132,6 +132,31 @@ int cb200_decode(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint
 int cb200_decode_fountain(cb200_ctx* ctx, const uint8_t* rgb, int n, uint32_t flags, uint8_t* chunks_out,
                           uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
 
+/* the same with frames that are already in device memory (the output of cb200_deskew_dev): results to host memory */
+int cb200_decode_fountain_from_dev(cb200_ctx* ctx, const uint8_t* d_rgb, int n, uint32_t flags, uint8_t* chunks_out,
+                                   uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
+
+/* ---- extractor: deskew in front of the decode -------------------------------------------------------
+
+   Replaces: Deskewer::deskew (src/lib/extractor/Deskewer.h:25-40) = cv::getPerspectiveTransform(corners, outputPoints) +
+   cv::warpPerspective(img, out, transform, size, cv::INTER_LINEAR) to the mode's image size, as Extractor::extract calls it
+   with the four anchor centres Scanner found (src/lib/extractor/Extractor.h:30-46).  The anchor scan stays on the host: the
+   caller supplies the corners (order: top-left, top-right, bottom-left, bottom-right, as Corners::all()).
+   OpenCV's arithmetic is restated bit for bit (pinned against cv2 in tests/test_deskew.py). */
+
+/* cv::getPerspectiveTransform(src, dst): 4 points each (x, y pairs) -> 3x3 double, row-major.  Host only. */
+int cb200_perspective_transform(const float* src_xy, const float* dst_xy, double* m9_out);
+/* cv::warpPerspective(src, dst, M, Size(image_size_x, image_size_y), INTER_LINEAR) (border constant 0) for n source images of
+   src_w x src_h RGB8 in device memory, tightly packed; m9: n x 9 doubles on the HOST (the forward transforms, inverted here as
+   warpPerspective does); d_dst: n frames of the context's mode, ready for the cb200_decode_*_dev entry points. */
+int cb200_deskew_dev(cb200_ctx* ctx, const uint8_t* d_src, int src_w, int src_h, int n, const double* m9, uint8_t* d_dst);
+/* host pointers in and out (H2D + kernel + D2H): what Deskewer::deskew returns */
+int cb200_deskew(cb200_ctx* ctx, const uint8_t* src, int src_w, int src_h, int n, const double* m9, uint8_t* dst);
+/* Extractor's deskew + Decoder::decode_fountain in one call: camera images (host) and their four anchor centres
+   (n x 8 floats) in, fountain chunks out; the deskewed frames stay on the device.  Outputs as cb200_decode_fountain. */
+int cb200_extract_decode_fountain(cb200_ctx* ctx, const uint8_t* src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
+                                  uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
+
 /* per-cell record of the exact flood walk: what CimbReader::read() hands back, step by step
    (src/lib/cimb_translator/CimbReader.cpp:139-162, PositionData.h:4-9) */
 typedef struct cb200_cell_trace {

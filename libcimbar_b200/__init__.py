@@ -25,7 +25,8 @@ EXPORTS = [
     "cb200_decode", "cb200_decode_fountain", "cb200_decode_symbols", "cb200_best_colors", "cb200_render_frames_dev",
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_create_wirehair", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
-    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
+    "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count", "cb200_decode_fountain_from_dev", "cb200_perspective_transform", "cb200_deskew_dev", "cb200_deskew",
+    "cb200_extract_decode_fountain", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
     "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_wait",
     "cb200_gather_release", "cb200_gather_acquire",
     "cb200_gather_status", "cb200_comm_unique_id", "cb200_comm_init", "cb200_gather_chunks", "cb200_gather_chunks_wait",
@@ -93,6 +94,11 @@ def load_library():
     lib.cb200_sink_file_size.argtypes = [vp, C.c_uint32]
     lib.cb200_sink_file_read.argtypes = [vp, C.c_uint32, u8p, C.c_uint64]
     lib.cb200_launch_count.restype = C.c_ulonglong
+    lib.cb200_decode_fountain_from_dev.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, u32p, u32p, u8p]
+    lib.cb200_perspective_transform.argtypes = [vp, vp, vp]
+    lib.cb200_deskew_dev.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp, u8p]
+    lib.cb200_deskew.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp, u8p]
+    lib.cb200_extract_decode_fountain.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, u8p, u32p, u32p, u8p]
     lib.cb200_decode_cells_means.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, vp, vp]
     lib.cb200_fit_ccm.argtypes = [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.cb200_palette_color.argtypes = [C.c_int, C.c_uint, C.c_int, u8p]
@@ -130,6 +136,15 @@ def comm_unique_id():
     h = (C.c_uint8 * 128)()
     _check(load_library().cb200_comm_unique_id(C.cast(h, C.c_void_p)))
     return bytes(h)
+
+
+def perspective_transform(src_xy, dst_xy):
+    """cv::getPerspectiveTransform restated (host): 4 source and 4 destination points -> 3x3 float64"""
+    a = np.ascontiguousarray(src_xy, dtype=np.float32).reshape(8)
+    b = np.ascontiguousarray(dst_xy, dtype=np.float32).reshape(8)
+    out = np.zeros(9, dtype=np.float64)
+    _check(load_library().cb200_perspective_transform(a.ctypes.data, b.ctypes.data, out.ctypes.data))
+    return out.reshape(3, 3)
 
 
 def mode_info(mode_val=68):
@@ -209,6 +224,32 @@ class Context:
         ff = np.zeros(n, dtype=np.uint8)
         _check(self.lib.cb200_decode_fountain(self._h, rgb.ctypes.data, n, flags, chunks.ctypes.data, count.ctypes.data,
                                               mask.ctypes.data, ff.ctypes.data))
+        return chunks, count, mask, ff
+
+    def deskew(self, src, m9):
+        """cv::warpPerspective(src, M, mode size, INTER_LINEAR) on the device; src: (n, h, w, 3) or (h, w, 3) uint8, m9: (n, 3, 3) float64"""
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        if src.ndim == 3:
+            src = src[None]
+        n, h, w, _ = src.shape
+        m = np.ascontiguousarray(m9, dtype=np.float64).reshape(n, 9)
+        out = np.zeros((n, self.info.image_size_y, self.info.image_size_x, 3), dtype=np.uint8)
+        _check(self.lib.cb200_deskew(self._h, src.ctypes.data, w, h, n, m.ctypes.data, out.ctypes.data))
+        return out
+
+    def extract_decode_fountain(self, src, corners, flags=0):
+        """camera images + their four anchor centres (tl, tr, bl, br) -> fountain chunks; the deskewed frames stay on the device"""
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        if src.ndim == 3:
+            src = src[None]
+        n, h, w, _ = src.shape
+        cr = np.ascontiguousarray(corners, dtype=np.float32).reshape(n, 8)
+        chunks = np.zeros((n, self.info.chunks_per_frame, self.info.chunk_size), dtype=np.uint8)
+        count = np.zeros(n, dtype=np.uint32)
+        mask = np.zeros(n, dtype=np.uint32)
+        ff = np.zeros(n, dtype=np.uint8)
+        _check(self.lib.cb200_extract_decode_fountain(self._h, src.ctypes.data, w, h, n, cr.ctypes.data, flags, chunks.ctypes.data,
+                                                      count.ctypes.data, mask.ctypes.data, ff.ctypes.data))
         return chunks, count, mask, ff
 
     def decode_cells(self, rgb, flags=0):

@@ -430,6 +430,10 @@ static int create_impl(cb200_ctx* c, int device, int mode_val, int max_frames)
         }
         CK(cudaMalloc(&c->d_gen, g.size()), "cudaMalloc gen");
         CK(cudaMemcpy(c->d_gen, g.data(), g.size(), cudaMemcpyHostToDevice), "upload gen");
+        uint8_t rho[4 * 64];
+        k2_remainder_basis(g.data(), m.ecc_bytes, gexp, glog, rho);
+        CK(cudaMalloc(&c->d_rho, sizeof(rho)), "cudaMalloc rho");
+        CK(cudaMemcpy(c->d_rho, rho, sizeof(rho), cudaMemcpyHostToDevice), "upload rho");
         CK(encode_init_tables(gexp, glog), "encode tables");
     }
     {
@@ -468,7 +472,7 @@ int cb200_destroy(cb200_ctx* c)
     if (!c) return CB200_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_rgb); cudaFree(c->d_cellvals); cudaFree(c->d_dirty); cudaFree(c->d_raw); cudaFree(c->d_data);
-    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_idx_ident); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_scratch);
+    cudaFree(c->d_ok); cudaFree(c->d_mask); cudaFree(c->d_flags); cudaFree(c->d_idx); cudaFree(c->d_idx_ident); cudaFree(c->d_inv); cudaFree(c->d_gen); cudaFree(c->d_rho); cudaFree(c->d_scratch);
     for (int k = 0; k < cb200_ctx::kEvSets; ++k) for (int i = 0; i < 8; ++i) if (c->ev[k][i]) cudaEventDestroy(c->ev[k][i]);
     flood_workspace_destroy(&c->flood);
     cudaFree(c->d_ccm); cudaFree(c->d_means); cudaFree(c->d_fit); cudaFree(c->d_fit_valid); cudaFree(c->d_ccm_active);
@@ -525,7 +529,7 @@ int cb200_rs_correct_dev(cb200_ctx* c, const uint8_t* d_raw, int n, uint8_t* d_d
     if (!d_raw || !d_data_out) return fail(CB200_ERR_ARG, "null buffer");
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     uint8_t* ok = d_block_ok ? d_block_ok : c->d_ok;
-    CK(k2_rs_launch(c->mode, d_raw, n, d_data_out, ok, c->sm_count, c->stream), "rs launch");
+    CK(k2_rs_launch(c->mode, d_raw, n, d_data_out, ok, c->d_rho, c->sm_count, c->stream), "rs launch");
     return CB200_OK;
 }
 
@@ -544,7 +548,7 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
     if (!fit) {
         rc = run_cells(c, d_rgb, n, flags & ~CB200_FLAG_CC_FIT); if (rc) return rc;
         mark(c);                               // ev3: (no separate pack kernel on this path: the RS kernel gathers from the cell bytes)
-        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->sm_count, c->stream), "rs launch");
+        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->d_rho, c->sm_count, c->stream), "rs launch");
     } else {
         // color_correction == 2: symbols (+ mean colours) -> RS of the symbol stream -> header -> CCM fit -> colours -> RS of
         // the colour stream (Decoder.h:83-117)
@@ -557,11 +561,11 @@ int cb200_decode_chunks_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t 
         rc = ccm_arg(c, initial); if (rc) return rc;        // the decoder's CCM going into frame 0
         rc = run_cells(c, d_rgb, n, flags & ~(CB200_FLAG_CC_FIT | CB200_FLAG_CC_SIMPLE), nullptr, c->d_means); if (rc) return rc;
         mark(c);                               // ev3
-        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, 0, m.nblocks_sym), "rs launch (symbols)");
+        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->d_rho, c->sm_count, c->stream, 0, m.nblocks_sym), "rs launch (symbols)");
         CK(ccm_fit_launch(m, d_rgb, d_chunks, c->d_ok, idx, n, c->d_fit, c->d_fit_valid, c->stream), "ccm fit");
         CK(ccm_carry_launch(n, c->d_fit, c->d_fit_valid, initial, c->d_ccm, c->d_ccm_active, c->stream), "ccm carry");
         CK(ccm_apply_launch(m, c->d_means, n, c->d_ccm, c->d_ccm_active, c->d_cellvals, c->stream), "ccm apply");
-        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->sm_count, c->stream, m.nblocks_sym, m.nblocks - m.nblocks_sym),
+        CK(k2_rs_fused_launch(m, c->d_cellvals, idx, n, d_chunks, c->d_ok, c->d_rho, c->sm_count, c->stream, m.nblocks_sym, m.nblocks - m.nblocks_sym),
            "rs launch (colours)");
         // the decoder keeps the CCM of the last frame (and whether there is one at all)
         CK(cudaMemcpyAsync(c->h_ccm, c->d_ccm + 9 * (size_t)(n - 1), sizeof(float) * 9, cudaMemcpyDeviceToHost, c->stream), "D2H ccm");
@@ -613,9 +617,20 @@ int cb200_decode_fountain(cb200_ctx* c, const uint8_t* rgb, int n, uint32_t flag
     if (n == 0) return CB200_OK;
     if (!rgb || !chunks_out || !chunk_count) return fail(CB200_ERR_ARG, "null buffer");
     CK(cudaSetDevice(c->device), "cudaSetDevice");
-    const Mode& m = c->mode;
     rc = upload_frames(c, rgb, n); if (rc) return rc;
-    rc = cb200_decode_chunks_dev(c, c->d_rgb, n, flags, c->d_data, c->d_mask, nullptr); if (rc) return rc;
+    return cb200_decode_fountain_from_dev(c, c->d_rgb, n, flags, chunks_out, chunk_count, chunk_mask, frame_flags);
+}
+
+// frames already on the device (the staging buffer, or the deskew kernel's output), results to host memory
+int cb200_decode_fountain_from_dev(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, uint8_t* chunks_out, uint32_t* chunk_count,
+                                   uint32_t* chunk_mask, uint8_t* frame_flags)
+{
+    int rc = check_n(c, n); if (rc) return rc;
+    if (n == 0) return CB200_OK;
+    if (!d_rgb || !chunks_out || !chunk_count) return fail(CB200_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    const Mode& m = c->mode;
+    rc = cb200_decode_chunks_dev(c, d_rgb, n, flags, c->d_data, c->d_mask, nullptr); if (rc) return rc;
     size_t need = (size_t)n * m.data_bytes + (size_t)n * sizeof(uint32_t);
     if (c->h_pinned_bytes < need) {
         if (c->h_pinned) cudaFreeHost(c->h_pinned);

@@ -1,7 +1,257 @@
-// deskew.cu -- extractor stage in front of the decode path (filled in below)
+// deskew.cu -- the extractor's deskew in front of the decode path, sm_100a.
+//
+// Replaces (reference file:line relative to /root/reference/):
+//   Deskewer::deskew        src/lib/extractor/Deskewer.h:25-40: cv::getPerspectiveTransform(corners, outputPoints) +
+//                           cv::warpPerspective(img, output, transform, size, cv::INTER_LINEAR) to the mode's image size
+//   (Extractor::extract     src/lib/extractor/Extractor.h:30-46 calls it with the four anchor centres Scanner found; the anchor
+//                           scan itself stays on the host: the caller supplies the corners)
+// OpenCV is a third-party dependency of the reference; its arithmetic is restated here and pinned against cv2 itself
+// (tests/test_deskew.py): getPerspectiveTransform = an 8x8 LU solve in double (hal LUImpl: partial pivoting, d = -1/pivot,
+// row updates, back substitution), cv::invert(3x3) in closed form, warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) =
+//   per destination pixel, in double:  W = 32 / (M6 x + M7 y + M8);  X = cvRound((M0 x + M1 y + M2) W), Y likewise,
+//   evaluated block-wise exactly as OpenCV does (X0 = M0 bx + M1 y + M2 for the 64-pixel block origin bx, then + M0 x1);
+//   source pixel (X >> 5, Y >> 5) with 5-bit fractions ax, ay and the fixed-point bilinear weights
+//   (32-ax)(32-ay), ax(32-ay), (32-ax)ay, ax ay (x 32 = OpenCV's 15-bit table, which is exact for these fractions),
+//   result (sum + 512) >> 10, taps outside the source count as 0.
+// The output frames land in device memory in the layout cb200_decode_*_dev take: a camera frame goes H2D once and never
+// returns to the host before its chunks do.
 #include "ctx.cuh"
 
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
 namespace cb200 {
-struct DeskewState { int unused = 0; };
-void deskew_destroy(DeskewState* d) { delete d; }
+
+struct DeskewState {
+    double* d_minv = nullptr;      // n x 9 inverse maps (destination -> source)
+    int cap = 0;
+    uint8_t* d_src = nullptr;      // staging for the host-pointer entry point
+    size_t src_bytes = 0;
+    uint8_t* d_dst = nullptr;      // deskewed frames of the host-pointer entry points
+    size_t dst_bytes = 0;
+};
+
+void deskew_destroy(DeskewState* d)
+{
+    if (!d) return;
+    cudaFree(d->d_minv); cudaFree(d->d_src); cudaFree(d->d_dst);
+    delete d;
+}
+
+// hal::LU64f (modules/core/src/matrix_decomp.cpp, LUImpl<double>) for an m x m system with one right-hand side
+static bool lu_solve(double* A, int m, double* b)
+{
+    const double eps = DBL_EPSILON * 100;
+    for (int i = 0; i < m; ++i) {
+        int k = i;
+        for (int j = i + 1; j < m; ++j) if (std::fabs(A[j * m + i]) > std::fabs(A[k * m + i])) k = j;
+        if (std::fabs(A[k * m + i]) < eps) return false;
+        if (k != i) {
+            for (int j = i; j < m; ++j) { const double t = A[i * m + j]; A[i * m + j] = A[k * m + j]; A[k * m + j] = t; }
+            const double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        const double d = -1 / A[i * m + i];
+        for (int j = i + 1; j < m; ++j) {
+            const double alpha = A[j * m + i] * d;
+            for (int c = i + 1; c < m; ++c) A[j * m + c] += alpha * A[i * m + c];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = m - 1; i >= 0; --i) {
+        double s = b[i];
+        for (int c = i + 1; c < m; ++c) s -= A[i * m + c] * b[c];
+        b[i] = s / A[i * m + i];
+    }
+    return true;
+}
+
+// cv::invert for a 3x3 double matrix (modules/core/src/lapack.cpp: det3 + adjugate)
+static bool invert3(const double* S, double* t)
+{
+#define SD(r, c) S[(r) * 3 + (c)]
+    double d = SD(0, 0) * (SD(1, 1) * SD(2, 2) - SD(1, 2) * SD(2, 1)) - SD(0, 1) * (SD(1, 0) * SD(2, 2) - SD(1, 2) * SD(2, 0)) +
+               SD(0, 2) * (SD(1, 0) * SD(2, 1) - SD(1, 1) * SD(2, 0));
+    if (d == 0.) return false;
+    d = 1. / d;
+    t[0] = (SD(1, 1) * SD(2, 2) - SD(1, 2) * SD(2, 1)) * d;
+    t[1] = (SD(0, 2) * SD(2, 1) - SD(0, 1) * SD(2, 2)) * d;
+    t[2] = (SD(0, 1) * SD(1, 2) - SD(0, 2) * SD(1, 1)) * d;
+    t[3] = (SD(1, 2) * SD(2, 0) - SD(1, 0) * SD(2, 2)) * d;
+    t[4] = (SD(0, 0) * SD(2, 2) - SD(0, 2) * SD(2, 0)) * d;
+    t[5] = (SD(0, 2) * SD(1, 0) - SD(0, 0) * SD(1, 2)) * d;
+    t[6] = (SD(1, 0) * SD(2, 1) - SD(1, 1) * SD(2, 0)) * d;
+    t[7] = (SD(0, 1) * SD(2, 0) - SD(0, 0) * SD(2, 1)) * d;
+    t[8] = (SD(0, 0) * SD(1, 1) - SD(0, 1) * SD(1, 0)) * d;
+#undef SD
+    return true;
+}
+
+// one thread = four consecutive destination pixels (12 bytes = three aligned words)
+__global__ void __launch_bounds__(256)
+k_deskew(const uint8_t* __restrict__ src, int src_w, int src_h, size_t src_frame_bytes, const double* __restrict__ minv, int n,
+         int dst_w, int dst_h, int bw0, uint8_t* __restrict__ dst)
+{
+    const int quads = dst_w >> 2;
+    const size_t total = (size_t)n * dst_h * quads;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % quads);
+        const size_t row = i / quads;
+        const int y = (int)(row % dst_h), f = (int)(row / dst_h);
+        const double* M = minv + (size_t)f * 9;
+        const uint8_t* s = src + (size_t)f * src_frame_bytes;
+        const int x = 4 * q, bx = (x / bw0) * bw0;
+        // no FMA contraction: OpenCV's x86-64 code rounds after every multiply and add
+        const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], (double)bx), __dmul_rn(M[1], (double)y)), M[2]);
+        const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], (double)bx), __dmul_rn(M[4], (double)y)), M[5]);
+        const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], (double)bx), __dmul_rn(M[7], (double)y)), M[8]);
+        uint32_t px[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double x1 = (double)(x + u - bx);
+            double W = __dadd_rn(W0, __dmul_rn(M[6], x1));
+            W = W != 0. ? __ddiv_rn(32.0, W) : 0.;
+            double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], x1)), W), fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], x1)), W);
+            fX = fmax(-2147483648.0, fmin(2147483647.0, fX)); fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+            const int X = __double2int_rn(fX), Y = __double2int_rn(fY);        // cvRound: to nearest, ties to even
+            int sx = X >> 5, sy = Y >> 5;
+            sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx); sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);   // saturate_cast<short>
+            const uint32_t ax = (uint32_t)(X & 31), ay = (uint32_t)(Y & 31);
+            const uint32_t w00 = (32u - ax) * (32u - ay), w01 = ax * (32u - ay), w10 = (32u - ax) * ay, w11 = ax * ay;
+            const bool x0in = sx >= 0 && sx < src_w, x1in = sx + 1 >= 0 && sx + 1 < src_w;
+            const bool y0in = sy >= 0 && sy < src_h, y1in = sy + 1 >= 0 && sy + 1 < src_h;
+            uint32_t acc[3] = {512u, 512u, 512u};
+            if (y0in) {
+                const uint8_t* r0 = s + ((size_t)sy * src_w + sx) * 3;
+                if (x0in) { acc[0] += w00 * r0[0]; acc[1] += w00 * r0[1]; acc[2] += w00 * r0[2]; }
+                if (x1in) { acc[0] += w01 * r0[3]; acc[1] += w01 * r0[4]; acc[2] += w01 * r0[5]; }
+            }
+            if (y1in) {
+                const uint8_t* r1 = s + ((size_t)(sy + 1) * src_w + sx) * 3;
+                if (x0in) { acc[0] += w10 * r1[0]; acc[1] += w10 * r1[1]; acc[2] += w10 * r1[2]; }
+                if (x1in) { acc[0] += w11 * r1[3]; acc[1] += w11 * r1[4]; acc[2] += w11 * r1[5]; }
+            }
+            px[u][0] = acc[0] >> 10; px[u][1] = acc[1] >> 10; px[u][2] = acc[2] >> 10;
+        }
+        uint32_t* out = reinterpret_cast<uint32_t*>(dst + ((size_t)f * dst_h + y) * (size_t)dst_w * 3 + (size_t)x * 3);
+        out[0] = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[1][0] << 24);
+        out[1] = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | (px[2][1] << 24);
+        out[2] = px[2][2] | (px[3][0] << 8) | (px[3][1] << 16) | (px[3][2] << 24);
+    }
+}
+
+static DeskewState* dstate(cb200_ctx* c)
+{
+    if (!c->deskew) c->deskew = new DeskewState();
+    return c->deskew;
+}
+
 }  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_perspective_transform(const float* src_xy, const float* dst_xy, double* m9_out)
+{
+    if (!src_xy || !dst_xy || !m9_out) return fail(CB200_ERR_ARG, "null argument");
+    // cv::getPerspectiveTransform (modules/imgproc/src/imgwarp.cpp): c00*xi + c01*yi + c02 - ui*(c20*xi + c21*yi) = ui, ...
+    double a[8][8], b[8];
+    for (int i = 0; i < 4; ++i) {
+        // the points are cv::Point2f: the four products are single-precision products, as in OpenCV's source
+        const float sx = src_xy[2 * i], sy = src_xy[2 * i + 1], dx = dst_xy[2 * i], dy = dst_xy[2 * i + 1];
+        a[i][0] = a[i + 4][3] = sx;
+        a[i][1] = a[i + 4][4] = sy;
+        a[i][2] = a[i + 4][5] = 1;
+        a[i][3] = a[i][4] = a[i][5] = a[i + 4][0] = a[i + 4][1] = a[i + 4][2] = 0;
+        a[i][6] = -sx * dx;
+        a[i][7] = -sy * dx;
+        a[i + 4][6] = -sx * dy;
+        a[i + 4][7] = -sy * dy;
+        b[i] = dx;
+        b[i + 4] = dy;
+    }
+    if (!lu_solve(&a[0][0], 8, b)) {      // cv::solve returns false and leaves zeros: a degenerate quadrilateral
+        for (int i = 0; i < 8; ++i) m9_out[i] = 0;
+        m9_out[8] = 1;
+        return fail(CB200_ERR_ARG, "degenerate corner quadrilateral");
+    }
+    for (int i = 0; i < 8; ++i) m9_out[i] = b[i];
+    m9_out[8] = 1.;
+    return CB200_OK;
+}
+
+int cb200_deskew_dev(cb200_ctx* c, const uint8_t* d_src, int src_w, int src_h, int n, const double* m9, uint8_t* d_dst)
+{
+    if (!c || !d_src || !m9 || !d_dst || n < 0 || src_w < 2 || src_h < 2) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    const Mode& m = c->mode;
+    DeskewState* d = dstate(c);
+    if (n > d->cap) {
+        cudaFree(d->d_minv); d->d_minv = nullptr; d->cap = 0;
+        CK(cudaMalloc(&d->d_minv, sizeof(double) * 9 * (size_t)n), "cudaMalloc transforms");
+        d->cap = n;
+    }
+    // warpPerspective inverts the transform it is given (no WARP_INVERSE_MAP): cv::invert, DECOMP_LU; a singular matrix maps
+    // everything to (0, 0) there (invert leaves zeros) -- reported here instead
+    static thread_local std::vector<double> inv;
+    inv.resize((size_t)n * 9);
+    for (int f = 0; f < n; ++f)
+        if (!invert3(m9 + (size_t)f * 9, inv.data() + (size_t)f * 9)) return fail(CB200_ERR_ARG, "singular perspective transform");
+    CK(cudaMemcpyAsync(d->d_minv, inv.data(), sizeof(double) * 9 * (size_t)n, cudaMemcpyHostToDevice, c->stream), "H2D transforms");
+    CK(cudaStreamSynchronize(c->stream), "sync (transforms staged from a host vector)");
+    // OpenCV's block geometry (WarpPerspectiveInvoker): bh0 = min(16, H); bw0 = min(1024 / bh0, W)
+    const int bh0 = m.height < 16 ? m.height : 16;
+    int bw0 = 1024 / bh0; if (bw0 > m.width) bw0 = m.width;
+    const size_t total = (size_t)n * m.height * (m.width / 4);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap_blocks = (size_t)c->sm_count * 16;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    k_deskew<<<(unsigned)blocks, 256, 0, c->stream>>>(d_src, src_w, src_h, (size_t)src_w * src_h * 3, d->d_minv, n, m.width, m.height, bw0, d_dst);
+    count_launch();
+    CK(cudaGetLastError(), "deskew launch");
+    return CB200_OK;
+}
+
+int cb200_deskew(cb200_ctx* c, const uint8_t* src, int src_w, int src_h, int n, const double* m9, uint8_t* dst)
+{
+    if (!c || !src || !dst || n < 0 || n > c->max_frames) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    DeskewState* d = dstate(c);
+    const size_t sb = (size_t)n * src_w * src_h * 3, db = (size_t)n * c->mode.width * c->mode.height * 3;
+    if (sb > d->src_bytes) { cudaFree(d->d_src); d->d_src = nullptr; d->src_bytes = 0; CK(cudaMalloc(&d->d_src, sb), "cudaMalloc deskew source"); d->src_bytes = sb; }
+    if (db > d->dst_bytes) { cudaFree(d->d_dst); d->d_dst = nullptr; d->dst_bytes = 0; CK(cudaMalloc(&d->d_dst, db), "cudaMalloc deskew output"); d->dst_bytes = db; }
+    CK(cudaMemcpyAsync(d->d_src, src, sb, cudaMemcpyHostToDevice, c->stream), "H2D camera frames");
+    int rc = cb200_deskew_dev(c, d->d_src, src_w, src_h, n, m9, d->d_dst); if (rc) return rc;
+    CK(cudaMemcpyAsync(dst, d->d_dst, db, cudaMemcpyDeviceToHost, c->stream), "D2H frames");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    return CB200_OK;
+}
+
+int cb200_extract_decode_fountain(cb200_ctx* c, const uint8_t* src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
+                                  uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags)
+{
+    if (!c || !src || !corners || !chunks_out || !chunk_count || n < 0 || n > c->max_frames) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    const Mode& m = c->mode;
+    DeskewState* d = dstate(c);
+    // Deskewer::deskew (Deskewer.h:27-39) with padding 0: the anchor centres go to (anchor, anchor) ... (W - anchor, H - anchor)
+    const float an = 30.0f;                                     // Config::anchor_size() (Config.h)
+    const float outp[8] = {an, an, (float)m.width - an, an, an, (float)m.height - an, (float)m.width - an, (float)m.height - an};
+    std::vector<double> m9((size_t)n * 9);
+    for (int f = 0; f < n; ++f) {
+        int rc = cb200_perspective_transform(corners + (size_t)f * 8, outp, m9.data() + (size_t)f * 9); if (rc) return rc;
+    }
+    const size_t sb = (size_t)n * src_w * src_h * 3, db = (size_t)n * m.width * m.height * 3;
+    if (sb > d->src_bytes) { cudaFree(d->d_src); d->d_src = nullptr; d->src_bytes = 0; CK(cudaMalloc(&d->d_src, sb), "cudaMalloc deskew source"); d->src_bytes = sb; }
+    if (db > d->dst_bytes) { cudaFree(d->d_dst); d->d_dst = nullptr; d->dst_bytes = 0; CK(cudaMalloc(&d->d_dst, db), "cudaMalloc deskew output"); d->dst_bytes = db; }
+    CK(cudaMemcpyAsync(d->d_src, src, sb, cudaMemcpyHostToDevice, c->stream), "H2D camera frames");
+    int rc = cb200_deskew_dev(c, d->d_src, src_w, src_h, n, m9.data(), d->d_dst); if (rc) return rc;
+    // the deskewed frames never leave the device: straight into the decode
+    return cb200_decode_fountain_from_dev(c, d->d_dst, n, flags, chunks_out, chunk_count, chunk_mask, frame_flags);
+}
+
+}  // extern "C"

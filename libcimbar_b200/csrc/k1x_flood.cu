@@ -362,42 +362,25 @@ k_flood_raster_fast(const Mode m, const uint8_t* __restrict__ rgb, const uint32_
 // so the pop order of equal priorities is whatever libstdc++'s sift-up / sift-down produce; both are restated literally.
 // Element i lives at shared word i + 1 (so the children 2h+1, 2h+2 are one aligned 64-bit load) while i < hs, else in
 // the global spill area at word i - hs (hs is odd, so a pair never straddles the two).  Shared memory is addressed through
-// 32-bit shared-window addresses and the shared / global choice is a predicate, not a branch.
-// Every lane of the walking warp executes push and pop with the same arguments and keeps the same `n`: loads are
-// broadcasts, stores are done by one lane, and the sift-down is spread over the lanes (below).
+// 32-bit shared-window addresses.  Every lane of the walking warp executes push and pop with the same arguments and keeps the
+// same `n`: loads of uniform addresses are broadcasts, stores are done by one lane, the sift-down is spread over the lanes.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+
 struct Heap {
     uint32_t sm;          // shared-window byte address of word 0 (element i at sm + 4 i + 4)
+    uint32_t path;        // shared-window byte address of the pop's path scratch: 20 x (node, moved value)
     uint32_t* spill; int n; int hs;
-    __device__ __forceinline__ uint32_t get(int i) const
+    // warp-uniform element access (i is the same in every lane): a real branch, no predication
+    __device__ __forceinline__ uint32_t get_u(int i) const { return i < hs ? lds32(sm + 4u * (uint32_t)i + 4u) : __ldcg(spill + (i - hs)); }
+    __device__ __forceinline__ void set_u(int i, uint32_t v, int lane) const
     {
-        uint32_t v;
-        const int in_sm = i < hs;
-        asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0;\n"
-                     "  @p ld.shared.u32 %0, [%1];\n"
-                     "  @!p ld.global.cg.u32 %0, [%2]; }"
-                     : "=r"(v) : "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(in_sm) : "memory");
-        return v;
+        if (lane == 0) { if (i < hs) sts32(sm + 4u * (uint32_t)i + 4u, v); else __stcg(spill + (i - hs), v); }
     }
-    __device__ __forceinline__ void set(int i, uint32_t v, bool doit) const
-    {
-        const int in_sm = doit && i < hs, in_gl = doit && i >= hs;
-        asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %3, 0; setp.ne.s32 q, %4, 0;\n"
-                     "  @p st.shared.u32 [%0], %2;\n"
-                     "  @q st.global.cg.u32 [%1], %2; }"
-                     :: "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(v), "r"(in_sm), "r"(in_gl) : "memory");
-    }
-    // elements 2 node + 1 and 2 node + 2 (nothing is loaded when !doit)
-    __device__ __forceinline__ uint2 children(int node, bool doit) const
-    {
-        const int c = 2 * node + 2;
-        const int in_sm = doit && c < hs, in_gl = doit && c >= hs;
-        uint2 r = make_uint2(0u, 0u);
-        asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %4, 0; setp.ne.s32 q, %5, 0;\n"
-                     "  @p ld.shared.v2.u32 {%0, %1}, [%2];\n"
-                     "  @q ld.global.cg.v2.u32 {%0, %1}, [%3]; }"
-                     : "+r"(r.x), "+r"(r.y) : "r"(sm + 4u * (uint32_t)c), "l"(spill + (c - 1 - hs)), "r"(in_sm), "r"(in_gl) : "memory");
-        return r;
-    }
+    // per-lane element store
+    __device__ __forceinline__ void set_l(int i, uint32_t v) const { if (i < hs) sts32(sm + 4u * (uint32_t)i + 4u, v); else __stcg(spill + (i - hs), v); }
 };
 __device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 25; }
 
@@ -408,24 +391,25 @@ __device__ __forceinline__ void heap_push(Heap& h, uint32_t e, int lane)
     const uint32_t prio = hprio(e);
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
-        const uint32_t pe = h.get(parent);
+        const uint32_t pe = h.get_u(parent);
         if (hprio(pe) <= prio) break;
-        h.set(hole, pe, lane == 0);
+        h.set_u(hole, pe, lane);
         hole = parent;
     }
-    h.set(hole, e, lane == 0);
+    h.set_u(hole, e, lane);
     __syncwarp();
 }
 
 // per-lane constants of the five-level subtree a sift-down round works on: lane i < 31 stands for the node at depth d,
-// position j of the subtree (heap order: i = 2^d - 1 + j); anc_mask has the bits of its ancestors' lanes, anc_want the
-// value each of those bits must have ("ancestor prefers its left child") for the descent to pass through this node
-struct SubtreeLane { int d, j, dp; uint32_t anc_mask, anc_want; bool valid; };
+// position j of the subtree (heap order: i = 2^d - 1 + j), i.e. node = (hole + 1) * 2^d + j - 1; anc_mask has the bits of its
+// ancestors' lanes, anc_want the value each of those bits must have ("ancestor prefers its left child") for the descent to
+// pass through this node.  Lane 31 stands for no node (its index is always beyond the heap).
+struct SubtreeLane { int pow2d, jm1, d; uint32_t anc_mask, anc_want; };
 __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
 {
     SubtreeLane s;
-    s.d = 31 - __clz(lane + 1); s.j = lane + 1 - (1 << s.d);
-    s.dp = s.d > 0 ? s.d - 1 : 0; s.valid = lane < 31;
+    s.d = 31 - __clz(lane + 1);
+    s.pow2d = 1 << s.d; s.jm1 = lane - s.pow2d;
     s.anc_mask = 0; s.anc_want = 0;
     for (int i = lane; i > 0;) {
         const int p = (i - 1) >> 1;
@@ -433,8 +417,42 @@ __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
         if (i & 1) s.anc_want |= 1u << p;            // odd index = left child
         i = p;
     }
-    if (lane == 31) { s.d = 0; s.j = 0; s.dp = 0; s.anc_mask = 0; s.anc_want = 0; }     // no node (valid == false): never on the path
+    if (lane == 31) { s.d = 0; s.pow2d = 0; s.jm1 = 0x3FFFFFFF; s.anc_mask = 0; s.anc_want = 0; }
     return s;
+}
+
+// the literal form, one level per step (only reached by heaps of more than 65 535 entries, or when a test asks for it)
+__device__ __noinline__ void heap_pop_serial(Heap& h, int lane)
+{
+    const uint32_t value = h.get_u(h.n - 1);
+    const int len = --h.n;
+    if (len == 0) return;
+    int hole = 0, second = 0;
+    while (second < ((len - 1) >> 1)) {
+        second = 2 * (second + 1);
+        uint32_t a = h.get_u(second);
+        const uint32_t b = h.get_u(second - 1);
+        if (hprio(a) > hprio(b)) { second--; a = b; }
+        h.set_u(hole, a, lane);
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
+        second = 2 * (second + 1);
+        h.set_u(hole, h.get_u(second - 1), lane);
+        hole = second - 1;
+    }
+    __syncwarp();
+    const uint32_t vp = hprio(value);
+    while (hole > 0) {
+        const int parent = (hole - 1) >> 1;
+        const uint32_t pe = h.get_u(parent);
+        if (hprio(pe) <= vp) break;
+        h.set_u(hole, pe, lane);
+        hole = parent;
+        __syncwarp();
+    }
+    h.set_u(hole, value, lane);
+    __syncwarp();
 }
 
 // std::pop_heap + pop_back (__adjust_heap with the hole at the root, then __push_heap of the last element):
@@ -444,104 +462,65 @@ __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
 // The descent path h_0 = 0, h_1, ..., h_L does not depend on `value`, only on which child each node prefers.  One round
 // handles the 31 nodes of the five-level subtree under the current hole: lane i loads the two children of its node, the
 // preferences are collected with one ballot, and every lane decides from its ancestors' bits whether the descent passes
-// through its node -- a dozen levels cost three memory round trips instead of a dozen.  Nothing is stored during the descent:
-// the lane of path level k keeps m_k = old v[h_(k+1)], the value that WOULD move up into h_k.  The sift-up then walks the same
-// path backwards and undoes those moves while prio(m_k) > prio(value); so with s = 1 + max { k : prio(m_k) <= prio(value) }
-// the net effect is v[h_k] = m_k for k < s, v[h_s] = value, everything below untouched -- s + 1 stores, no reads.
-constexpr int kPopRounds = 3;          // 15 levels: heaps of up to 65 535 entries (six times the largest seen); beyond: heap_pop_serial
-
-// the literal form, one level per step (only reached by heaps of more than 65 535 entries)
-__device__ __noinline__ void heap_pop_serial(Heap& h, int lane)
-{
-    const uint32_t value = h.get(h.n - 1);
-    const int len = --h.n;
-    if (len == 0) return;
-    int hole = 0, second = 0;
-    while (second < ((len - 1) >> 1)) {
-        second = 2 * (second + 1);
-        uint32_t a = h.get(second);
-        const uint32_t b = h.get(second - 1);
-        if (hprio(a) > hprio(b)) { second--; a = b; }
-        h.set(hole, a, lane == 0);
-        hole = second;
-    }
-    if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
-        second = 2 * (second + 1);
-        h.set(hole, h.get(second - 1), lane == 0);
-        hole = second - 1;
-    }
-    __syncwarp();
-    const uint32_t vp = hprio(value);
-    while (hole > 0) {
-        const int parent = (hole - 1) >> 1;
-        const uint32_t pe = h.get(parent);
-        if (hprio(pe) <= vp) break;
-        h.set(hole, pe, lane == 0);
-        hole = parent;
-        __syncwarp();
-    }
-    h.set(hole, value, lane == 0);
-    __syncwarp();
-}
-
+// through its node -- a dozen levels cost three memory round trips instead of a dozen.  Nothing of the heap is stored during
+// the descent: the lane of path level k writes (h_k, m_k = old v[h_(k+1)], the value that WOULD move up into h_k) to a small
+// scratch.  The sift-up walks the same path backwards and undoes those moves while prio(m_k) > prio(value); so with
+// s = 1 + max { k : prio(m_k) <= prio(value) } the net effect is v[h_k] = m_k for k < s, v[h_s] = value, everything below
+// untouched: lane k stores level k -- s + 1 stores, no reads.
+constexpr int kPopRounds = 3;          // 15 levels: heaps of up to 65 535 entries (seven times the largest seen); beyond: heap_pop_serial
+constexpr int kPathSlots = 20;
 __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane, int serial_above)
 {
     if (h.n > serial_above) { heap_pop_serial(h, lane); return; }
-    const uint32_t value = h.get(h.n - 1);                    // (often in L2: in flight during the rounds, used after them)
+    const uint32_t value = h.get_u(h.n - 1);                   // (often in L2: in flight during the rounds, used after them)
     const int len = --h.n;
     if (len == 0) return;
     const int lim = (len - 1) >> 1;
-    int hole = 0, level = 0;
-    int node_r[kPopRounds]; uint32_t m_r[kPopRounds]; int lvl_r[kPopRounds];     // lvl < 0: this lane moved nothing in that round
+    int hole = 0;
 #pragma unroll
     for (int r = 0; r < kPopRounds; ++r) {
-        lvl_r[r] = -1; node_r[r] = 0; m_r[r] = 0;
         if (hole < lim) {                                      // warp-uniform
-            const int node = ((hole + 1) << sl.d) - 1 + sl.j;
-            const bool has2 = sl.valid && node < lim;          // both children inside the heap: the descent continues below it
-            const uint2 c = h.children(node, has2);
+            const int node = (hole + 1) * sl.pow2d + sl.jm1;
+            const bool has2 = node < lim;                      // both children inside the heap: the descent continues below it
+            const int ce = 2 * node + 2;                       // its right child's element index
+            uint2 c = make_uint2(0u, 0u);
+            if (has2) { if (ce < h.hs) c = lds64(h.sm + 4u * (uint32_t)ce); else c = __ldcg(reinterpret_cast<const uint2*>(h.spill + (ce - 1 - h.hs))); }
             const bool left = hprio(c.y) > hprio(c.x);         // right child strictly worse -> the left child moves up
             const uint32_t pref = __ballot_sync(0xffffffffu, has2 && left);
-            // the descent reaches this node iff its parent has two children and every ancestor points towards it
-            const bool parent_ok = (sl.d == 0) || (((hole + 1) << sl.dp) - 1 + (sl.j >> 1)) < lim;
-            const bool reached = sl.valid && parent_ok && (((pref ^ sl.anc_want) & sl.anc_mask) == 0u);
-            if (reached && has2) { lvl_r[r] = level + sl.d; node_r[r] = node; m_r[r] = left ? c.x : c.y; }
+            // the descent reaches this node iff its parent has two children ((node - 1) / 2 < lim <=> node <= 2 lim) and every
+            // ancestor points towards it
+            const bool reached = node <= 2 * lim && (((pref ^ sl.anc_want) & sl.anc_mask) == 0u);
+            if (reached && has2) {                             // path level of this node = floor(log2(node + 1))
+                const int lvl = 31 - __clz(node + 1);
+                sts64(h.path + 8u * (uint32_t)lvl, (uint32_t)node, left ? c.x : c.y);
+            }
             // the round ends at the first reached node without two children, or below the subtree's last level
-            const bool ends = reached && (!has2 || sl.d == 4);
-            const uint32_t eb = __ballot_sync(0xffffffffu, ends);
-            const int nxt = has2 ? 2 * node + 2 - (left ? 1 : 0) : node;
-            const int src = __ffs(eb) - 1;
-            hole = __shfl_sync(0xffffffffu, nxt, src);
-            level += __shfl_sync(0xffffffffu, sl.d + (has2 ? 1 : 0), src);
+            const uint32_t eb = __ballot_sync(0xffffffffu, reached && (!has2 || sl.d == 4));
+            const int nxt = has2 ? ce - (left ? 1 : 0) : node;
+            hole = __shfl_sync(0xffffffffu, nxt, __ffs(eb) - 1);
         }
     }
+    int last_level = 31 - __clz(hole + 1);                     // level of the hole the descent ends in
     // a last node with only a left child: one more level of the path (uniform)
-    const bool lone = (len & 1) == 0 && hole == ((len - 2) >> 1);
-    uint32_t m_lone = 0; int node_lone = hole;
-    if (lone) { m_lone = h.get(2 * hole + 1); hole = 2 * hole + 1; }
-    const int lvl_lone = level;                                // the lone move fills path level `level`; the final hole is one deeper
-    // ---- s = 1 + deepest path level whose moved value does not have to go back down
-    const uint32_t vp = hprio(value);
-    int kmax = -1;
-#pragma unroll
-    for (int r = 0; r < kPopRounds; ++r) if (lvl_r[r] >= 0 && hprio(m_r[r]) <= vp) kmax = max(kmax, lvl_r[r]);
-    kmax = __reduce_max_sync(0xffffffffu, kmax);
-    if (lone && hprio(m_lone) <= vp) kmax = lvl_lone;          // the deepest level there is
-    const int s = kmax + 1;
-    const int last_level = level + (lone ? 1 : 0);             // level of the final hole
-#pragma unroll
-    for (int r = 0; r < kPopRounds; ++r) {
-        const bool mine = lvl_r[r] >= 0 && lvl_r[r] <= s && lvl_r[r] < last_level + 1;
-        h.set(node_r[r], lvl_r[r] == s ? value : m_r[r], mine);
+    if ((len & 1) == 0 && hole == ((len - 2) >> 1)) {
+        const uint32_t m_lone = h.get_u(2 * hole + 1);
+        if (lane == 0) sts64(h.path + 8u * (uint32_t)last_level, (uint32_t)hole, m_lone);
+        hole = 2 * hole + 1;
+        ++last_level;
     }
-    if (lone && lvl_lone <= s) h.set(node_lone, lvl_lone == s ? value : m_lone, lane == 0);
-    if (s == last_level) h.set(hole, value, lane == 0);
+    __syncwarp();
+    // ---- lane k owns path level k: s = 1 + deepest level whose moved value does not have to go back down
+    const uint2 pm = lane < last_level ? lds64(h.path + 8u * (uint32_t)lane) : make_uint2((uint32_t)hole, 0u);
+    const uint32_t vp = hprio(value);
+    const uint32_t keep = __ballot_sync(0xffffffffu, lane < last_level && hprio(pm.y) <= vp);
+    const int s = 32 - __clz(keep);                            // = 1 + highest set bit, 0 if none
+    if (lane <= s && lane <= last_level) h.set_l((int)pm.x, lane == s ? value : pm.y);
     __syncwarp();
 }
 
 // cooldown values (CellDrift::calculate_cooldown, CellDrift.cpp:34-43): 4, 0xFF, 0xFE (initial), or an odd drift id 1/3/5/7
 __device__ __forceinline__ uint32_t cd_code(uint32_t cd) { return cd == 4u ? 0u : cd == 0xFFu ? 1u : cd == 0xFEu ? 2u : 3u + (cd >> 1); }
-__device__ __forceinline__ uint32_t cd_value(uint32_t code) { return code == 0u ? 4u : code == 1u ? 0xFFu : code == 2u ? 0xFEu : 2u * (code - 3u) + 1u; }
+__device__ __forceinline__ uint32_t cd_value(uint32_t code) { return __byte_perm(0x01FEFF04u, 0x00070503u, code); }   // byte `code` of 04 FF FE 01 03 05 07
 constexpr uint32_t kSeedCode = 7u;     // entry pushed by reset(): its cell's inherit record is NOT in the entry
 __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uint32_t code, uint32_t prio)
 {
@@ -563,8 +542,9 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
              uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace, int serial_above)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
-    uint32_t* heap_sm = reinterpret_cast<uint32_t*>(walk_smem);
-    uint32_t* remaining = heap_sm + heap_smem + 1;
+    // [heap: heap_smem + 1 words][_remaining bitmap: kMaxCells / 32 words][path scratch of the pop: kPathSlots x 2 words]
+    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(walk_smem);
+    const uint32_t rem_base = sm_base + 4u * (uint32_t)(heap_smem + 1);
     uint8_t* prio = ws_prio + (size_t)blockIdx.x * kMaxCells;
     const int lane = threadIdx.x;
     const int W = m.width, ncells = m.num_cells, tiles_x = W >> 4;
@@ -572,9 +552,9 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
     const int cnt = chunk_count(counters, base, cap);
     const unsigned long long tileL = cx_tiles_L[lane & 15];
     const int narrow = m.cells_x - 2 * m.corner;
-    const float rcp_narrow = 1.0f / (float)narrow, rcp_wide = 1.0f / (float)m.cells_x;   // exact floor for q < 2^14 (q + 0.5 trick)
     const SubtreeLane sl = subtree_lane(lane);
-    Heap heap; heap.sm = (uint32_t)__cvta_generic_to_shared(heap_sm); heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
+    Heap heap; heap.sm = sm_base; heap.path = rem_base + 4u * (uint32_t)(kMaxCells / 32);
+    heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
 
     while (true) {
         uint32_t k = 0;
@@ -587,7 +567,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
 
         // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
         for (int i = lane; i < kMaxCells / 16; i += 32) __stcg(reinterpret_cast<uint4*>(prio) + i, make_uint4(~0u, ~0u, ~0u, ~0u));
-        for (int i = lane; i < (ncells + 31) / 32; i += 32) remaining[i] = 0xFFFFFFFFu;
+        for (int i = lane; i < (ncells + 31) / 32; i += 32) sts32(rem_base + 4u * (uint32_t)i, 0xFFFFFFFFu);
         __syncwarp();
         heap.n = 0;
         {
@@ -605,24 +585,26 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             // element, so every lane reads it there and the loads of the cell's window / neighbours are in flight while
             // the sift-down of the pop itself runs.
             if (heap.n == 0) break;                          // heap exhausted (cannot happen on a connected grid)
-            const uint32_t e = heap_sm[1];
+            const uint32_t e = lds32(sm_base + 4u);
             const int ci = (int)(e & 0x3FFFu);
             const uint32_t rem_bit = 1u << (ci & 31);
-            if (!(remaining[ci >> 5] & rem_bit)) {           // stale entry of a cell that is already decoded: skipped
+            const uint32_t rem_addr = rem_base + 4u * (uint32_t)(ci >> 5);
+            const uint32_t rem_word = lds32(rem_addr);
+            if (!(rem_word & rem_bit)) {                     // stale entry of a cell that is already decoded: skipped
                 __syncwarp();
                 heap_pop(heap, sl, lane, serial_above);
                 continue;
             }
             ++count;
-            // neighbours: lanes 0-3 direct (right, left, bottom, top), 4-11 the horizon chains (see flood_build_cinfo)
-            uint32_t cv = 0xFFFFu;
-            if (lane < 12) cv = __ldg(&cinfo[(size_t)ci * 16 + lane]);
+            // per-cell table (flood_build_cinfo): lanes 0-3 the direct neighbours (right, left, bottom, top), 4-11 the horizon
+            // chains, 12 / 13 the cell's position (CellPositions::compute_linear, CellPositions.cpp:5-50)
+            uint32_t cv = __ldg(&cinfo[ci * 16 + (lane & 15)]);
             uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
             int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
             if (code == kSeedCode) {                         // (scanned before the pop: the seed entry itself is excluded either way)
                 uint32_t latest = 0xFFFFFFFFu;
                 for (int i = lane; i < heap.n; i += 32) {
-                    const uint32_t t = heap.get(i);
+                    const uint32_t t = i < heap.hs ? lds32(heap.sm + 4u * (uint32_t)i + 4u) : __ldcg(heap.spill + (i - heap.hs));
                     if ((t & 0x3FFFu) == (uint32_t)ci && ((t >> 22) & 7u) != kSeedCode && t < latest) latest = t;
                 }
                 latest = __reduce_min_sync(0xffffffffu, latest);
@@ -632,21 +614,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
             }
             const uint32_t cooldown = cd_value(code);
-            // ---- cell position (CellPositions::compute_linear, CellPositions.cpp:5-50): arithmetic, so that the window loads
-            // do not wait for the neighbour table
-            int px, py;
-            if (ci < m.top_cells) {
-                const int kk = __float2int_rz(((float)ci + 0.5f) * rcp_narrow), c = ci - kk * narrow;
-                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * kk;
-            } else if (ci < m.top_cells + m.mid_cells) {
-                const int q = ci - m.top_cells;
-                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_wide), c = q - kk * m.cells_x;
-                px = m.cell_offset + kSpacing * c; py = m.cell_offset + kSpacing * (m.corner + kk);
-            } else {
-                const int q = ci - m.top_cells - m.mid_cells;
-                const int kk = __float2int_rz(((float)q + 0.5f) * rcp_narrow), c = q - kk * narrow;
-                px = m.cell_offset + kSpacing * (m.corner + c); py = m.cell_offset + kSpacing * (m.cells_y - m.corner + kk);
-            }
+            const int px = (int)__shfl_sync(0xffffffffu, cv, 12), py = (int)__shfl_sync(0xffffffffu, cv, 13);
             const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
             // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r from (at most) two tiles; the rasters are read once
             // per window and are far bigger than the L2: streaming loads, so that they do not evict the heaps and priority bytes
@@ -659,12 +627,13 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             __syncwarp();                                    // every lane has read the heap top / bitmap before they are rewritten
             heap_pop(heap, sl, lane, serial_above);
             if (lane == 0) {
-                remaining[ci >> 5] &= ~rem_bit;
+                sts32(rem_addr, rem_word & ~rem_bit);
                 __stcg(prio + ci, (uint8_t)0);
             }
             __syncwarp();                                    // the bitmap / prio writes are ordered before the reads below
             // the candidates' priority bytes: requested now, needed only after the scoring below
             uint32_t pv = 0;
+            if (lane >= 12) cv = 0xFFFFu;
             if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
             const uint32_t myrow = ((ra | (rb << 16)) >> rshift) & 0x3FFu;     // bit i = window col i
             // ---- fast path: the centre hash (drift id 4 = rows 1..8, cols 1..8) is a dictionary tile.  The reference's search
@@ -864,6 +833,11 @@ static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<ui
         };
         if (right >= 0 && left >= 0) { chain(right, 0, 4); chain(left, 1, 6); }
         if (top >= 0 && bottom >= 0) { chain(top, 3, 8); chain(bottom, 2, 10); }
+        int k, cc, rbase, ncols, x0;                       // slots 12, 13: the cell's top-left pixel
+        cell_row_col(m, i, k, cc);
+        cell_row_geom(m, k, rbase, ncols, x0);
+        o[12] = (uint16_t)(x0 + kSpacing * cc);
+        o[13] = (uint16_t)(m.cell_offset + kSpacing * k);
     }
 }
 
@@ -875,7 +849,7 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     // per-slot spill area in L2.  Shared memory per walk decides how many walks an SM holds (at most 32 blocks).
     ws->heap_smem = 1023;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
-    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4;
+    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + (size_t)kPathSlots * 8;
     int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;

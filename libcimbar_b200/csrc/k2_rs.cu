@@ -15,6 +15,7 @@
 // evaluates the locator at 8 field elements per lane; Forney evaluates one error value per lane.
 #include "cb200_common.cuh"
 #include "k2_rs.cuh"
+#include <cstring>
 
 namespace cb200 {
 
@@ -69,30 +70,34 @@ k_pack_raw(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* _
 
 // ---------------------------------------------------------------------------------------------- GF(256) helpers
 constexpr int kRsWarpsPerCta = 16;
+constexpr int kStagePitch = 196;         // bytes per staged block: >= 1 + 179, a multiple of 4, 49 words (rows start in different banks)
 
+template <int T>
 struct RsSmem {
+    static constexpr int GL = 8 * T;     // lanes per block in the remainder stage
+    static constexpr int G = 32 / GL;    // blocks a warp takes at a time
     uint8_t exp[512];
     uint8_t log[256];
     struct PerWarp {
-        alignas(16) uint32_t encs[256];  // block byte i as enc[i] * (128*T) = the byte offset of table row enc[i] (the syndrome
-                                         // loop's operand as is; the byte itself is encs[i] >> kRowShift)
+        alignas(16) uint8_t stage[G * kStagePitch];   // the block bytes, `lead` zero bytes first so that the length is a multiple of 4
+        alignas(4) uint8_t rem[64];                   // remainder of the block being corrected (state words of its lane group)
         uint8_t synd[kMaxParity];
         uint8_t loc[kMaxParity + 8];
         uint8_t last[kMaxParity + 8];
         uint8_t omega[kMaxParity];
         uint8_t roots[kMaxParity + 8];
     } w[kRsWarpsPerCta];
-    // followed in dynamic shared memory by the syndrome multiplier table: uint32 mt[256][32*T],
-    // mt[x][j] = x * alpha^(j+1).  One 32-bit word per (x, lane): lane j always reads bank j, so the Horner step
-    // `acc = mt[acc][lane] ^ byte` is a conflict-free LDS instead of two conflicting log/exp lookups.
+    // followed in dynamic shared memory by the four remainder tables: uint32 lt[4][256][GL] (see k_rs_decode)
 };
 
-__device__ __forceinline__ uint32_t gf_mul(const RsSmem& s, uint32_t a, uint32_t b)
+template <int T>
+__device__ __forceinline__ uint32_t gf_mul(const RsSmem<T>& s, uint32_t a, uint32_t b)
 {   // field_mul, libcorrect field.h:92-110
     if (a == 0 || b == 0) return 0;
     return s.exp[(uint32_t)s.log[a] + (uint32_t)s.log[b]];
 }
-__device__ __forceinline__ uint32_t gf_div(const RsSmem& s, uint32_t a, uint32_t b)
+template <int T>
+__device__ __forceinline__ uint32_t gf_div(const RsSmem<T>& s, uint32_t a, uint32_t b)
 {   // field_div, field.h:112-129 (x / 0 == 0)
     if (a == 0 || b == 0) return 0;
     return s.exp[255u + (uint32_t)s.log[a] - (uint32_t)s.log[b]];
@@ -111,134 +116,181 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 }
 
 // ---------------------------------------------------------------------------------------------- RS decode
-// one warp per block.  FUSED: the block's bytes are gathered straight from K1's per-cell bytes through the interleave
-// map (P7/P10 bit packing folded in); otherwise they are read from a packed raw stream (n_frames * cap_all bytes,
-// symbol stream blocks then colour stream blocks).
-// data_out: n_frames * nblocks * msg_len (zeros for failed blocks, reed_solomon_stream.h:96-107); ok: n_frames * nblocks
+// FUSED: the block's bytes are gathered straight from K1's per-cell bytes through the interleave map (P7/P10 bit packing
+// folded in); otherwise they are read from a packed raw stream (n_frames * cap_all bytes, symbol stream blocks then colour
+// stream blocks).  data_out: n_frames * nblocks * msg_len (zeros for failed blocks, reed_solomon_stream.h:96-107);
+// ok: n_frames * nblocks.
+//
+// The clean-block test and the syndromes do not evaluate the received word c(x) at the parity roots one by one (libcorrect's
+// decode.c:12-28: `parity` Horner chains over all n bytes).  All syndromes vanish iff the generator g divides c, so the block is
+// first reduced modulo g: a warp takes 32 / GL blocks at a time, the GL = 8 T lanes of a group hold the remainder (4 bytes
+// each), and every step consumes FOUR input bytes ("slicing by 4"): with G(x) = x^pad g(x) of degree D = 4 Pw (a whole number
+// of words) the state obeys  S' = (S_low << 32) ^ sum_j T_j[byte j of (top word ^ input word)],  T_j[v] = v (x^(D+j) mod G),
+// i.e. one word broadcast, one lane shift and four conflict-light 32-byte table rows per four bytes and four blocks -- a
+// quarter of the shared-memory traffic of the per-root chains and half the instructions.  The final state is x^pad r' with
+// r' = c x^parity mod g: zero iff the block is clean; otherwise the syndromes libcorrect computes are
+// S_j = c(a^(j+1)) = r'(a^(j+1)) a^(-(j+1) parity), `parity` short Horner steps over r' instead of n long ones, and the decode
+// continues exactly as before (Berlekamp-Massey, Chien, Forney in libcorrect's operation order), one block per warp.
 template <int T, bool FUSED>
-__global__ void __launch_bounds__(kRsWarpsPerCta * 32, 4)
+__global__ void __launch_bounds__(kRsWarpsPerCta * 32, (T == 1 ? 4 : 2))
 k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __restrict__ cellvals, const uint16_t* __restrict__ idx,
-            int n_frames, int b_begin, int b_count, uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok)
+            int n_frames, int b_begin, int b_count, uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok,
+            const uint8_t* __restrict__ rho)
 {   // blocks [b_begin, b_begin + b_count) of every frame (all of them, or the symbol / the colour stream on their own)
+    using Smem = RsSmem<T>;
+    constexpr int GL = Smem::GL, G = Smem::G;
     extern __shared__ __align__(16) uint8_t rs_smem_raw[];
-    RsSmem& s = *reinterpret_cast<RsSmem*>(rs_smem_raw);
-    uint32_t* mt = reinterpret_cast<uint32_t*>(rs_smem_raw + ((sizeof(RsSmem) + 127) & ~size_t(127)));
+    Smem& s = *reinterpret_cast<Smem*>(rs_smem_raw);
+    uint32_t* lt = reinterpret_cast<uint32_t*>(rs_smem_raw + ((sizeof(Smem) + 127) & ~size_t(127)));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 512; i += blockDim.x) s.exp[i] = c_gf_exp[i];
     for (int i = tid; i < 256; i += blockDim.x) s.log[i] = c_gf_log[i];
-    for (int e = tid; e < 256 * 32 * T; e += blockDim.x) {
-        int x = e / (32 * T), j = e - x * (32 * T);
-        uint32_t v = x ? (uint32_t)c_gf_exp[(uint32_t)c_gf_log[x] + (uint32_t)(j + 1)] : 0u;   // j+1 <= 64: index < 512
-        mt[e] = v * (128u * T);      // stored as the byte offset of table row v: the Horner step needs no address arithmetic
+    __syncthreads();
+    for (int e = tid; e < 4 * 256 * GL; e += blockDim.x) {
+        const int j = e / (256 * GL), v = (e / GL) & 255, k = e % GL;
+        uint32_t word = 0;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) word |= gf_mul(s, (uint32_t)v, (uint32_t)rho[j * 64 + 4 * k + bb]) << (8 * bb);
+        lt[e] = word;
     }
     __syncthreads();
 
     const int md = m.ecc_bytes, blk = m.ecc_block, msg_len = m.msg_len;
+    const int Pw = (md + 3) >> 2, pad = 4 * Pw - md, lead = (4 - (blk & 3)) & 3, nsteps = (lead + blk) >> 2;
     const long total_blocks = (long)n_frames * b_count;
-    RsSmem::PerWarp& w = s.w[warp];
+    const long total_units = (total_blocks + G - 1) / G;
+    typename Smem::PerWarp& w = s.w[warp];
+    const int grp = lane / GL, k = lane % GL;
+    const uint32_t lt_lane = (uint32_t)__cvta_generic_to_shared(lt) + 4u * (uint32_t)k;
+    const uint32_t stage_lane = (uint32_t)__cvta_generic_to_shared(w.stage) + (uint32_t)(grp * kStagePitch);
 
-    for (long gb = (long)blockIdx.x * kRsWarpsPerCta + warp; gb < total_blocks; gb += (long)gridDim.x * kRsWarpsPerCta) {
-        const int f = (int)(gb / b_count), b = b_begin + (int)(gb - (long)f * b_count);
-        uint8_t* out = data_out + ((size_t)f * m.nblocks + b) * msg_len;
+    for (long unit = (long)blockIdx.x * kRsWarpsPerCta + warp; unit < total_units; unit += (long)gridDim.x * kRsWarpsPerCta) {
         __syncwarp();
-        if (FUSED) {
-            const uint8_t* cells = cellvals + (size_t)f * m.num_cells;
-            const bool fast = !m.legacy && m.symbol_bits == 4 && m.color_bits == 2 && blk <= 160;
-            if (fast) {
-                // a block lies entirely in the symbol stream or in the colour stream (cap_sym is a whole number of blocks).
-                // All interleave-map words of the block are loaded first, then all cell bytes: two dependent round trips
-                // to L2 per block instead of two per 32 bytes.
-                const uint32_t B0 = (uint32_t)b * (uint32_t)blk;
-                constexpr int kU = 5;                      // 5 x 32 >= ecc_block (155 in every mode; checked at launch)
-                if ((int)B0 < m.cap_sym) {                 // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
-                    uint32_t sl[kU];
+        // ---- stage the G blocks of this unit
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            const long gb = unit * G + g;
+            uint8_t* st = w.stage + g * kStagePitch;
+            if (lane < 4) st[lane] = 0;                       // the `lead` zero bytes (an absent block stays zero: it reads as clean)
+            if (gb >= total_blocks) { for (int i = lane; i < blk; i += 32) st[lead + i] = 0; continue; }
+            const int f = (int)(gb / b_count), b = b_begin + (int)(gb - (long)f * b_count);
+            uint8_t* enc = st + lead;
+            if (FUSED) {
+                const uint8_t* cells = cellvals + (size_t)f * m.num_cells;
+                const bool fast = !m.legacy && m.symbol_bits == 4 && m.color_bits == 2 && blk <= 160;
+                if (fast) {
+                    // a block lies entirely in the symbol stream or in the colour stream (cap_sym is a whole number of blocks).
+                    // All interleave-map words of the block are loaded first, then all cell bytes: two dependent round trips
+                    // to L2 per block instead of two per 32 bytes.
+                    const uint32_t B0 = (uint32_t)b * (uint32_t)blk;
+                    constexpr int kU = 5;                      // 5 x 32 >= ecc_block (155 in every mode; checked at launch)
+                    if ((int)B0 < m.cap_sym) {                 // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
+                        uint32_t sl[kU];
 #pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int i = lane + 32 * u;
-                        sl[u] = i < blk ? *reinterpret_cast<const uint32_t*>(idx + 2u * (B0 + (uint32_t)i)) : 0u;
+                        for (int u = 0; u < kU; ++u) {
+                            const int i = lane + 32 * u;
+                            sl[u] = i < blk ? *reinterpret_cast<const uint32_t*>(idx + 2u * (B0 + (uint32_t)i)) : 0u;
+                        }
+                        uint32_t c0[kU], c1[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const int i = lane + 32 * u;
+                            if (i < blk) { c0[u] = cells[sl[u] & 0xFFFFu]; c1[u] = cells[sl[u] >> 16]; } else { c0[u] = c1[u] = 0; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const int i = lane + 32 * u;
+                            if (i < blk) enc[i] = (uint8_t)(((c0[u] & 15u) << 4) | (c1[u] & 15u));
+                        }
+                    } else {                                   // four 2-bit colours per byte (Decoder.h:112-113)
+                        uint2 sl[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const int i = lane + 32 * u;
+                            sl[u] = i < blk ? *reinterpret_cast<const uint2*>(idx + 4u * (B0 + (uint32_t)i - (uint32_t)m.cap_sym)) : make_uint2(0u, 0u);
+                        }
+                        uint32_t c0[kU], c1[kU], c2[kU], c3[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const int i = lane + 32 * u;
+                            if (i < blk) { c0[u] = cells[sl[u].x & 0xFFFFu]; c1[u] = cells[sl[u].x >> 16]; c2[u] = cells[sl[u].y & 0xFFFFu]; c3[u] = cells[sl[u].y >> 16]; }
+                            else { c0[u] = c1[u] = c2[u] = c3[u] = 0; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            const int i = lane + 32 * u;
+                            if (i < blk)
+                                enc[i] = (uint8_t)((((c0[u] >> 4) & 3u) << 6) | (((c1[u] >> 4) & 3u) << 4) | (((c2[u] >> 4) & 3u) << 2) | ((c3[u] >> 4) & 3u));
+                        }
                     }
-                    uint32_t c0[kU], c1[kU];
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int i = lane + 32 * u;
-                        if (i < blk) { c0[u] = cells[sl[u] & 0xFFFFu]; c1[u] = cells[sl[u] >> 16]; } else { c0[u] = c1[u] = 0; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int i = lane + 32 * u;
-                        if (i < blk) w.encs[i] = (((c0[u] & 15u) << 4) | (c1[u] & 15u)) * (128u * T);
-                    }
-                } else {                                   // four 2-bit colours per byte (Decoder.h:112-113)
-                    uint2 sl[kU];
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int i = lane + 32 * u;
-                        sl[u] = i < blk ? *reinterpret_cast<const uint2*>(idx + 4u * (B0 + (uint32_t)i - (uint32_t)m.cap_sym)) : make_uint2(0u, 0u);
-                    }
-                    uint32_t c0[kU], c1[kU], c2[kU], c3[kU];
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int i = lane + 32 * u;
-                        if (i < blk) { c0[u] = cells[sl[u].x & 0xFFFFu]; c1[u] = cells[sl[u].x >> 16]; c2[u] = cells[sl[u].y & 0xFFFFu]; c3[u] = cells[sl[u].y >> 16]; }
-                        else { c0[u] = c1[u] = c2[u] = c3[u] = 0; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kU; ++u) {
-                        const int i = lane + 32 * u;
-                        if (i < blk)
-                            w.encs[i] = ((((c0[u] >> 4) & 3u) << 6) | (((c1[u] >> 4) & 3u) << 4) | (((c2[u] >> 4) & 3u) << 2) | ((c3[u] >> 4) & 3u)) * (128u * T);
+                } else {
+                    for (int i = lane; i < blk; i += 32) {
+                        uint32_t B = (uint32_t)b * (uint32_t)blk + (uint32_t)i, v;
+                        if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
+                        else if ((int)B < m.cap_sym) v = stream_byte(cells, idx, B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
+                        else v = stream_byte(cells, idx, B - (uint32_t)m.cap_sym, m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
+                        enc[i] = (uint8_t)v;
                     }
                 }
             } else {
-                for (int i = lane; i < blk; i += 32) {
-                    uint32_t B = (uint32_t)b * (uint32_t)blk + (uint32_t)i, v;
-                    if (m.legacy) v = stream_byte(cells, idx, B, m.symbol_bits + m.color_bits, 2, m.symbol_bits, (uint32_t)m.num_cells);
-                    else if ((int)B < m.cap_sym) v = stream_byte(cells, idx, B, m.symbol_bits, 0, m.symbol_bits, (uint32_t)m.num_cells);
-                    else v = stream_byte(cells, idx, B - (uint32_t)m.cap_sym, m.color_bits, 1, m.symbol_bits, (uint32_t)m.num_cells);
-                    w.encs[i] = v * (128u * T);
+                // symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
+                // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks
+                const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
+                for (int i = lane; i < blk; i += 32) enc[i] = enc_g[i];
+            }
+        }
+        __syncwarp();
+
+        // ---- remainder modulo x^pad g, four bytes per step, the G blocks of the unit side by side
+        uint32_t word = 0;
+        {
+            const int top_src = grp * GL + (Pw - 1);
+#pragma unroll 2
+            for (int t = 0; t < nsteps; ++t) {
+                const uint32_t ew = lds_u32(stage_lane + 4u * (uint32_t)t);     // first byte = highest power
+                const uint32_t tw = __shfl_sync(0xffffffffu, word, top_src);
+                const uint32_t v = tw ^ __byte_perm(ew, 0u, 0x0123);
+                const uint32_t r0 = lds_u32(lt_lane + (((v) & 0xFFu) + 0u) * (4u * GL));
+                const uint32_t r1 = lds_u32(lt_lane + (((v >> 8) & 0xFFu) + 256u) * (4u * GL));
+                const uint32_t r2 = lds_u32(lt_lane + (((v >> 16) & 0xFFu) + 512u) * (4u * GL));
+                const uint32_t r3 = lds_u32(lt_lane + ((v >> 24) + 768u) * (4u * GL));
+                uint32_t prev = __shfl_up_sync(0xffffffffu, word, 1, GL);
+                if (k == 0) prev = 0;
+                word = prev ^ r0 ^ r1 ^ r2 ^ r3;
+            }
+        }
+        const uint32_t dirty = __ballot_sync(0xffffffffu, k < Pw && word != 0u);
+
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            const long gb = unit * G + g;
+            if (gb >= total_blocks) break;                     // warp-uniform
+            const int f = (int)(gb / b_count), b = b_begin + (int)(gb - (long)f * b_count);
+            uint8_t* out = data_out + ((size_t)f * m.nblocks + b) * msg_len;
+            uint8_t* enc = w.stage + g * kStagePitch + lead;
+            if (((dirty >> (g * GL)) & ((1u << GL) - 1u)) == 0u) {   // clean block: copy out (decode.c:337-343)
+                for (int i = lane; i < msg_len; i += 32) out[i] = enc[i];
+                if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
+                continue;
+            }
+            // ---- syndromes from the remainder: S_j = r'(alpha^(j+1)) alpha^(-(j+1) parity), r'[i] = state byte pad + i
+            __syncwarp();
+            if (grp == g && k < Pw) reinterpret_cast<uint32_t*>(w.rem)[k] = word;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+                const int j = lane + 32 * q;
+                if (j < md) {
+                    uint32_t acc = 0;
+                    for (int i = md - 1; i >= 0; --i) {
+                        const uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + (uint32_t)(j + 1)] : 0u;   // j + 1 <= 64: index < 512
+                        acc = t ^ w.rem[pad + i];
+                    }
+                    if (acc) acc = s.exp[(uint32_t)s.log[acc] + 255u - (uint32_t)(((j + 1) * md) % 255)];
+                    w.synd[j] = (uint8_t)acc;
                 }
             }
-        } else {
-            // symbol-stream blocks are consecutive ecc_block pieces of the first cap_sym bytes, colour blocks of the rest
-            // (the two reed_solomon_streams of Decoder.h:100-101 and :115-117); cap_sym is a whole number of blocks
-            const uint8_t* enc_g = raw + (size_t)f * m.cap_all + (size_t)b * blk;
-            for (int i = lane; i < blk; i += 32) w.encs[i] = (uint32_t)enc_g[i] * (128u * T);
-        }
-        __syncwarp();
-
-        // ---- syndromes S_j = r(alpha^(j+1)), Horner from the highest coefficient = enc[0]  (decode.c:12-28)
-        uint32_t nz = 0;
-#pragma unroll
-        for (int q = 0; q < T; ++q) {
-            // Horner with every value kept as a table-row byte offset: off' = mt[off][lane] ^ enc_off -- per byte one address
-            // add, one LDS and one XOR (32-bit shared addresses, so no generic-pointer arithmetic in the chain).  The floor
-            // is shared-memory bandwidth: one 32-lane table read per block byte (splitting the chain in two interleaved halves
-            // was measured and does not help).
-            const uint32_t colb = (uint32_t)__cvta_generic_to_shared(mt) + 4u * (uint32_t)(lane + 32 * q);
-            uint32_t off = 0;
-            const uint4* e4 = reinterpret_cast<const uint4*>(w.encs);
-            int i = 0;
-#pragma unroll 2
-            for (; i + 4 <= blk; i += 4) {
-                const uint4 e = e4[i >> 2];
-                off = lds_u32(colb + off) ^ e.x;
-                off = lds_u32(colb + off) ^ e.y;
-                off = lds_u32(colb + off) ^ e.z;
-                off = lds_u32(colb + off) ^ e.w;
-            }
-            for (; i < blk; ++i) off = lds_u32(colb + off) ^ w.encs[i];
-            const uint32_t acc = off / (128u * T);
-            const int j = lane + 32 * q;
-            if (j < md) { w.synd[j] = (uint8_t)acc; nz |= acc; }
-        }
-        nz = __ballot_sync(0xffffffffu, nz != 0);
-        __syncwarp();
-        if (nz == 0) {  // clean block: copy out (decode.c:337-343)
-            for (int i = lane; i < msg_len; i += 32) out[i] = (uint8_t)(w.encs[i] / (128u * T));
-            if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
-            continue;
-        }
-
+            __syncwarp();
         // ---- Berlekamp-Massey (decode.c:30-116).  Field arithmetic is exact, so scale = disc / last_disc is applied as one
         //      multiplication (libcorrect writes mul-then-div per coefficient: same element); what must match libcorrect is
         //      the update rule and the order bookkeeping, because they decide the locator it reports for uncorrectable blocks.
@@ -285,7 +337,7 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         __syncwarp();
         for (uint32_t i = 0; i < (uint32_t)md; ++i) {
             uint32_t part = 0;
-            for (uint32_t j = 1 + lane; j <= numerrors; j += 32) part ^= gf_mul(s, w.loc[j], w.synd[i - j]);
+            for (uint32_t j = 1 + lane; j <= numerrors; j += 32) part ^= gf_mul<T>(s, w.loc[j], w.synd[i - j]);
             uint32_t disc = warp_xor(part) ^ w.synd[i];
             if (disc == 0) { delay++; continue; }
             if (2 * numerrors <= i) {
@@ -294,7 +346,7 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
                 uint32_t sh[3], lc[3];
                 int q = 0;
                 for (uint32_t j = lane; j <= top; j += 32, ++q) {
-                    sh[q] = (j < delay) ? 0u : gf_div(s, gf_mul(s, w.last[j - delay], disc), last_disc);
+                    sh[q] = (j < delay) ? 0u : gf_div<T>(s, gf_mul<T>(s, w.last[j - delay], disc), last_disc);
                     lc[q] = w.loc[j];
                 }
                 __syncwarp();
@@ -313,7 +365,7 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
             }
             // no length change: loc[j+delay] ^= (disc/last_disc) * last[j]
             for (uint32_t j = lane; j <= last_order; j += 32)
-                w.loc[j + delay] ^= (uint8_t)gf_div(s, gf_mul(s, w.last[j], disc), last_disc);
+                w.loc[j + delay] ^= (uint8_t)gf_div<T>(s, gf_mul<T>(s, w.last[j], disc), last_disc);
             __syncwarp();
             if (last_order + delay > loc_order) loc_order = last_order + delay;
             delay++;
@@ -356,7 +408,7 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         for (int k = lane; k < md; k += 32) {
             uint32_t acc = 0;
             int lim = (int)order < k ? (int)order : k;
-            for (int i = 0; i <= lim; ++i) acc ^= gf_mul(s, w.loc[i], w.synd[k - i]);
+            for (int i = 0; i <= lim; ++i) acc ^= gf_mul<T>(s, w.loc[i], w.synd[k - i]);
             w.omega[k] = (uint8_t)acc;
         }
         __syncwarp();
@@ -376,15 +428,16 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
                 uint32_t c = ((i & 1) == 0) ? (uint32_t)w.loc[i + 1] : 0u;
                 den = t ^ c;
             }
-            uint32_t err = gf_div(s, num, den);          // X^(fcr-1) = 1 for fcr = 1
+            uint32_t err = gf_div<T>(s, num, den);          // X^(fcr-1) = 1 for fcr = 1
             uint32_t inv = s.exp[510u - lx];             // field_div(1, X): log[1] = 255
             uint32_t location = s.log[inv];              // coefficient index (255 when inv == 1: out of range in libcorrect)
             if (location >= (uint32_t)md && location < (uint32_t)blk)
-                w.encs[blk - 1 - (int)location] ^= err * (128u * T);
+                enc[blk - 1 - (int)location] ^= (uint8_t)err;
         }
         __syncwarp();
-        for (int i = lane; i < msg_len; i += 32) out[i] = (uint8_t)(w.encs[i] / (128u * T));
+        for (int i = lane; i < msg_len; i += 32) out[i] = enc[i];
         if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
+        }
     }
 }
 
@@ -425,34 +478,56 @@ cudaError_t k2_pack_launch(const Mode& m, const uint8_t* d_cellvals, const uint1
 
 template <int T, bool FUSED>
 static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames,
-                               uint8_t* d_data, uint8_t* d_ok, int sm_count, cudaStream_t st, int b_begin = 0, int b_count = -1)
+                               uint8_t* d_data, uint8_t* d_ok, const uint8_t* d_rho, int sm_count, cudaStream_t st, int b_begin = 0, int b_count = -1)
 {
     if (b_count < 0) b_count = m.nblocks;
-    const size_t smem = ((sizeof(RsSmem) + 127) & ~size_t(127)) + sizeof(uint32_t) * 256 * 32 * T;
+    if (m.ecc_block + 4 > kStagePitch || m.ecc_bytes > 8 * T * 4) return cudaErrorInvalidValue;
+    const size_t smem = ((sizeof(RsSmem<T>) + 127) & ~size_t(127)) + sizeof(uint32_t) * 4 * 256 * 8 * T;
     {   // a per-device attribute: set on every launch (a process may hold contexts on several GPUs)
         cudaError_t e = cudaFuncSetAttribute(k_rs_decode<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    const int G = 4 / T;
     long total = (long)n_frames * b_count;
-    long ctas = (total + kRsWarpsPerCta - 1) / kRsWarpsPerCta;
+    long units = (total + G - 1) / G;
+    long ctas = (units + kRsWarpsPerCta - 1) / kRsWarpsPerCta;
     long max_ctas = (long)sm_count * (T == 1 ? 4 : 2);       // persistent: the table build is amortised over many blocks
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
-    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, b_begin, b_count, d_data, d_ok); count_launch();
+    k_rs_decode<T, FUSED><<<(int)ctas, kRsWarpsPerCta * 32, smem, st>>>(m, d_raw, d_cellvals, d_idx, n_frames, b_begin, b_count, d_data, d_ok, d_rho); count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint8_t* d_data, uint8_t* d_ok, int sm_count, cudaStream_t st)
+cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint8_t* d_data, uint8_t* d_ok, const uint8_t* d_rho, int sm_count, cudaStream_t st)
 {
-    if (m.ecc_bytes <= 32) return rs_launch_t<1, false>(m, d_raw, nullptr, nullptr, n_frames, d_data, d_ok, sm_count, st);
-    return rs_launch_t<2, false>(m, d_raw, nullptr, nullptr, n_frames, d_data, d_ok, sm_count, st);
+    if (m.ecc_bytes <= 32) return rs_launch_t<1, false>(m, d_raw, nullptr, nullptr, n_frames, d_data, d_ok, d_rho, sm_count, st);
+    return rs_launch_t<2, false>(m, d_raw, nullptr, nullptr, n_frames, d_data, d_ok, d_rho, sm_count, st);
 }
 
 cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_data,
-                               uint8_t* d_ok, int sm_count, cudaStream_t st, int b_begin, int b_count)
+                               uint8_t* d_ok, const uint8_t* d_rho, int sm_count, cudaStream_t st, int b_begin, int b_count)
 {
-    if (m.ecc_bytes <= 32) return rs_launch_t<1, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st, b_begin, b_count);
-    return rs_launch_t<2, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, sm_count, st, b_begin, b_count);
+    if (m.ecc_bytes <= 32) return rs_launch_t<1, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, sm_count, st, b_begin, b_count);
+    return rs_launch_t<2, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, sm_count, st, b_begin, b_count);
+}
+
+// rho[j][0 .. D-1] = coefficients (low to high) of x^(D + j) mod G, G = x^pad g, D = 4 ceil(parity / 4); gen = g low to high,
+// gen[parity] = 1.  64 bytes per j, zero padded.  (host)
+void k2_remainder_basis(const uint8_t* gen, int parity, const uint8_t* gexp512, const uint8_t* glog256, uint8_t* rho_out /* 4 * 64 */)
+{
+    const int Pw = (parity + 3) / 4, D = 4 * Pw, pad = D - parity;
+    uint8_t G[72] = {0};
+    for (int k = 0; k <= parity; ++k) G[pad + k] = gen[k];
+    auto mul = [&](uint8_t x, uint8_t y) -> uint8_t { return (x && y) ? gexp512[glog256[x] + glog256[y]] : 0; };
+    uint8_t r[64] = {0};
+    r[0] = 1;                                                  // x^0, multiplied by x step by step
+    for (int e = 1; e <= D + 3; ++e) {
+        const uint8_t top = r[D - 1];
+        for (int k = D - 1; k > 0; --k) r[k] = r[k - 1];
+        r[0] = 0;
+        if (top) for (int k = 0; k < D; ++k) r[k] ^= mul(top, G[k]);
+        if (e >= D) { for (int k = 0; k < 64; ++k) rho_out[(e - D) * 64 + k] = k < D ? r[k] : 0; }
+    }
 }
 
 cudaError_t k2_mask_launch(const Mode& m, const uint8_t* d_ok, int n_frames, uint32_t* d_mask, cudaStream_t st)

@@ -87,6 +87,7 @@ int main(int argc, char** argv)
 		std::vector<unsigned char> bufspace(cimbar::Config::fountain_chunks_per_frame() * cimbar::Config::fountain_chunk_size());
 		{
 			Decoder d2;
+			d2.clear_color_correction();          // one fresh reference decoder (the tests before this one may have left a CCM)
 			escrow_buffer_writer ebw(bufspace.data(), cimbar::Config::fountain_chunks_per_frame(), cimbar::Config::fountain_chunk_size());
 			unsigned good = d2.decode_fountain(img, ebw);
 			CHECK(d2.last_warnings() == 0);
@@ -97,6 +98,9 @@ int main(int argc, char** argv)
 				CHECK(d2.save_ccm(prefix + ".ccm"));
 				Decoder d3;
 				float back[9];
+				// the CCM is the thread's (CimbDecoder.cpp:69-73): a fresh Decoder still sees what d2 fitted, until it is cleared
+				CHECK(d3.get_ccm(back) && std::memcmp(back, m9, sizeof(m9)) == 0);
+				d3.clear_color_correction();
 				CHECK(!d3.get_ccm(back));
 				CHECK(d3.load_ccm(prefix + ".ccm"));
 				CHECK(d3.get_ccm(back) && std::memcmp(back, m9, sizeof(m9)) == 0);
@@ -109,6 +113,7 @@ int main(int argc, char** argv)
 		}
 		{
 			Decoder d1;
+			d1.clear_color_correction();
 			escrow_buffer_writer ebw(bufspace.data(), cimbar::Config::fountain_chunks_per_frame(), cimbar::Config::fountain_chunk_size());
 			unsigned good = d1.decode_fountain(img, ebw, false, 1);
 			std::ofstream(prefix + ".chunks_cc1", std::ios::binary).write(reinterpret_cast<const char*>(bufspace.data()), good);
