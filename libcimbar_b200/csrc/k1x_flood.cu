@@ -362,8 +362,11 @@ k_flood_raster_fast(const Mode m, const uint8_t* __restrict__ rgb, const uint32_
 // so the pop order of equal priorities is whatever libstdc++'s sift-up / sift-down produce; both are restated literally.
 // Element i lives at shared word i + 1 (so the children 2h+1, 2h+2 are one aligned 64-bit load) while i < hs, else in
 // the global spill area at word i - hs (hs is odd, so a pair never straddles the two).  Shared memory is addressed through
-// 32-bit shared-window addresses.  Every lane of the walking warp executes push and pop with the same arguments and keeps the
-// same `n`: loads of uniform addresses are broadcasts, stores are done by one lane, the sift-down is spread over the lanes.
+// 32-bit shared-window addresses.
+// Every lane of the walking warp executes push and pop with the same arguments and keeps the same `n`.  Where the address and
+// the value are the same in every lane ("uniform" accesses) EVERY lane stores: the redundant stores merge into one, no branch
+// is needed, and each lane later reads back what it wrote itself, so no warp barrier is needed either.  Only the sift-down
+// spreads different nodes over the lanes; its results are published with one barrier.
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
@@ -371,45 +374,63 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) { asm 
 
 struct Heap {
     uint32_t sm;          // shared-window byte address of word 0 (element i at sm + 4 i + 4)
-    uint32_t path;        // shared-window byte address of the pop's path scratch: 20 x (node, moved value)
+    uint32_t path;        // shared-window byte address of the pop's path scratch: kPathSlots x (node, moved value)
     uint32_t* spill; int n; int hs;
-    // warp-uniform element access (i is the same in every lane): a real branch, no predication
-    __device__ __forceinline__ uint32_t get_u(int i) const { return i < hs ? lds32(sm + 4u * (uint32_t)i + 4u) : __ldcg(spill + (i - hs)); }
-    __device__ __forceinline__ void set_u(int i, uint32_t v, int lane) const
+    // element load / store, shared or spill chosen by predicate (no branch)
+    __device__ __forceinline__ uint32_t get(int i) const
     {
-        if (lane == 0) { if (i < hs) sts32(sm + 4u * (uint32_t)i + 4u, v); else __stcg(spill + (i - hs), v); }
+        uint32_t v;
+        asm volatile("{ .reg .pred p; setp.lt.s32 p, %3, %4;\n"
+                     "  @p ld.shared.u32 %0, [%1];\n"
+                     "  @!p ld.global.cg.u32 %0, [%2]; }"
+                     : "=r"(v) : "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(i), "r"(hs));
+        return v;
     }
-    // per-lane element store
-    __device__ __forceinline__ void set_l(int i, uint32_t v) const { if (i < hs) sts32(sm + 4u * (uint32_t)i + 4u, v); else __stcg(spill + (i - hs), v); }
+    __device__ __forceinline__ void set(int i, uint32_t v) const
+    {
+        asm volatile("{ .reg .pred p; setp.lt.s32 p, %3, %4;\n"
+                     "  @p st.shared.u32 [%0], %2;\n"
+                     "  @!p st.global.cg.u32 [%1], %2; }"
+                     :: "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(v), "r"(i), "r"(hs) : "memory");
+    }
+    __device__ __forceinline__ void set_if(int i, uint32_t v, bool doit) const
+    {
+        const int in_sm = doit && i < hs, in_gl = doit && i >= hs;
+        asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %3, 0; setp.ne.s32 q, %4, 0;\n"
+                     "  @p st.shared.u32 [%0], %2;\n"
+                     "  @q st.global.cg.u32 [%1], %2; }"
+                     :: "r"(sm + 4u * (uint32_t)i + 4u), "l"(spill + (i - hs)), "r"(v), "r"(in_sm), "r"(in_gl) : "memory");
+    }
 };
 __device__ __forceinline__ uint32_t hprio(uint32_t e) { return e >> 25; }
 
-// std::push_heap (__push_heap): append, sift up while parent.prio > prio (strict).  Warp-uniform; lane 0 stores.
-__device__ __forceinline__ void heap_push(Heap& h, uint32_t e, int lane)
+// std::push_heap (__push_heap): append, sift up while parent.prio > prio (strict).  Uniform: every lane does all of it.
+// parent0 = the value of the first parent when the caller has already fetched it (parent0_of = its element index), else any.
+__device__ __forceinline__ void heap_push(Heap& h, uint32_t e, uint32_t parent0, int parent0_of)
 {
     int hole = h.n++;
     const uint32_t prio = hprio(e);
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
-        const uint32_t pe = h.get_u(parent);
+        const uint32_t pe = parent == parent0_of ? parent0 : h.get(parent);
         if (hprio(pe) <= prio) break;
-        h.set_u(hole, pe, lane);
+        h.set(hole, pe);
         hole = parent;
+        parent0_of = -1;                                       // (the fetched value is only good for the first step)
     }
-    h.set_u(hole, e, lane);
-    __syncwarp();
+    h.set(hole, e);
 }
 
 // per-lane constants of the five-level subtree a sift-down round works on: lane i < 31 stands for the node at depth d,
 // position j of the subtree (heap order: i = 2^d - 1 + j), i.e. node = (hole + 1) * 2^d + j - 1; anc_mask has the bits of its
 // ancestors' lanes, anc_want the value each of those bits must have ("ancestor prefers its left child") for the descent to
 // pass through this node.  Lane 31 stands for no node (its index is always beyond the heap).
-struct SubtreeLane { int pow2d, jm1, d; uint32_t anc_mask, anc_want; };
+struct SubtreeLane { int pow2d, jm1; bool last; uint32_t anc_mask, anc_want; };
 __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
 {
     SubtreeLane s;
-    s.d = 31 - __clz(lane + 1);
-    s.pow2d = 1 << s.d; s.jm1 = lane - s.pow2d;
+    const int d = 31 - __clz(lane + 1);
+    s.pow2d = 1 << d; s.jm1 = lane - s.pow2d; s.last = d == 4;
     s.anc_mask = 0; s.anc_want = 0;
     for (int i = lane; i > 0;) {
         const int p = (i - 1) >> 1;
@@ -417,42 +438,41 @@ __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
         if (i & 1) s.anc_want |= 1u << p;            // odd index = left child
         i = p;
     }
-    if (lane == 31) { s.d = 0; s.pow2d = 0; s.jm1 = 0x3FFFFFFF; s.anc_mask = 0; s.anc_want = 0; }
+    if (lane == 31) { s.pow2d = 0; s.jm1 = 0x3FFFFFFF; s.last = false; s.anc_mask = 0; s.anc_want = 0; }
     return s;
 }
 
-// the literal form, one level per step (only reached by heaps of more than 65 535 entries, or when a test asks for it)
-__device__ __noinline__ void heap_pop_serial(Heap& h, int lane)
+// the literal form, one level per step (only reached by heaps of more than 65 535 entries, or when a test asks for it).
+// Uniform: returns the new element count.
+__device__ __noinline__ int heap_pop_serial(Heap h)
 {
-    const uint32_t value = h.get_u(h.n - 1);
+    const uint32_t value = h.get(h.n - 1);
     const int len = --h.n;
-    if (len == 0) return;
+    if (len == 0) return len;
     int hole = 0, second = 0;
     while (second < ((len - 1) >> 1)) {
         second = 2 * (second + 1);
-        uint32_t a = h.get_u(second);
-        const uint32_t b = h.get_u(second - 1);
+        uint32_t a = h.get(second);
+        const uint32_t b = h.get(second - 1);
         if (hprio(a) > hprio(b)) { second--; a = b; }
-        h.set_u(hole, a, lane);
+        h.set(hole, a);
         hole = second;
     }
     if ((len & 1) == 0 && second == ((len - 2) >> 1)) {
         second = 2 * (second + 1);
-        h.set_u(hole, h.get_u(second - 1), lane);
+        h.set(hole, h.get(second - 1));
         hole = second - 1;
     }
-    __syncwarp();
     const uint32_t vp = hprio(value);
     while (hole > 0) {
         const int parent = (hole - 1) >> 1;
-        const uint32_t pe = h.get_u(parent);
+        const uint32_t pe = h.get(parent);
         if (hprio(pe) <= vp) break;
-        h.set_u(hole, pe, lane);
+        h.set(hole, pe);
         hole = parent;
-        __syncwarp();
     }
-    h.set_u(hole, value, lane);
-    __syncwarp();
+    h.set(hole, value);
+    return len;
 }
 
 // std::pop_heap + pop_back (__adjust_heap with the hole at the root, then __push_heap of the last element):
@@ -471,8 +491,8 @@ constexpr int kPopRounds = 3;          // 15 levels: heaps of up to 65 535 entri
 constexpr int kPathSlots = 20;
 __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane, int serial_above)
 {
-    if (h.n > serial_above) { heap_pop_serial(h, lane); return; }
-    const uint32_t value = h.get_u(h.n - 1);                   // (often in L2: in flight during the rounds, used after them)
+    if (h.n > serial_above) { h.n = heap_pop_serial(h); __syncwarp(); return; }
+    const uint32_t value = h.get(h.n - 1);                     // (often in L2: in flight during the rounds, used after them)
     const int len = --h.n;
     if (len == 0) return;
     const int lim = (len - 1) >> 1;
@@ -484,7 +504,13 @@ __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lan
             const bool has2 = node < lim;                      // both children inside the heap: the descent continues below it
             const int ce = 2 * node + 2;                       // its right child's element index
             uint2 c = make_uint2(0u, 0u);
-            if (has2) { if (ce < h.hs) c = lds64(h.sm + 4u * (uint32_t)ce); else c = __ldcg(reinterpret_cast<const uint2*>(h.spill + (ce - 1 - h.hs))); }
+            {
+                const int in_sm = has2 && ce < h.hs, in_gl = has2 && ce >= h.hs;
+                asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %4, 0; setp.ne.s32 q, %5, 0;\n"
+                             "  @p ld.shared.v2.u32 {%0, %1}, [%2];\n"
+                             "  @q ld.global.cg.v2.u32 {%0, %1}, [%3]; }"
+                             : "+r"(c.x), "+r"(c.y) : "r"(h.sm + 4u * (uint32_t)ce), "l"(h.spill + (ce - 1 - h.hs)), "r"(in_sm), "r"(in_gl));
+            }
             const bool left = hprio(c.y) > hprio(c.x);         // right child strictly worse -> the left child moves up
             const uint32_t pref = __ballot_sync(0xffffffffu, has2 && left);
             // the descent reaches this node iff its parent has two children ((node - 1) / 2 < lim <=> node <= 2 lim) and every
@@ -494,52 +520,69 @@ __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lan
                 const int lvl = 31 - __clz(node + 1);
                 sts64(h.path + 8u * (uint32_t)lvl, (uint32_t)node, left ? c.x : c.y);
             }
-            // the round ends at the first reached node without two children, or below the subtree's last level
-            const uint32_t eb = __ballot_sync(0xffffffffu, reached && (!has2 || sl.d == 4));
+            // the round ends at the first reached node without two children, or below the subtree's last level: exactly one lane
             const int nxt = has2 ? ce - (left ? 1 : 0) : node;
-            hole = __shfl_sync(0xffffffffu, nxt, __ffs(eb) - 1);
+            hole = (int)__reduce_or_sync(0xffffffffu, (reached && (!has2 || sl.last)) ? (uint32_t)nxt : 0u);
         }
     }
     int last_level = 31 - __clz(hole + 1);                     // level of the hole the descent ends in
     // a last node with only a left child: one more level of the path (uniform)
     if ((len & 1) == 0 && hole == ((len - 2) >> 1)) {
-        const uint32_t m_lone = h.get_u(2 * hole + 1);
-        if (lane == 0) sts64(h.path + 8u * (uint32_t)last_level, (uint32_t)hole, m_lone);
+        const uint32_t m_lone = h.get(2 * hole + 1);
+        sts64(h.path + 8u * (uint32_t)last_level, (uint32_t)hole, m_lone);
         hole = 2 * hole + 1;
         ++last_level;
     }
     __syncwarp();
     // ---- lane k owns path level k: s = 1 + deepest level whose moved value does not have to go back down
-    const uint2 pm = lane < last_level ? lds64(h.path + 8u * (uint32_t)lane) : make_uint2((uint32_t)hole, 0u);
+    uint2 pm = make_uint2((uint32_t)hole, 0u);
+    if (lane < last_level) pm = lds64(h.path + 8u * (uint32_t)lane);
     const uint32_t vp = hprio(value);
     const uint32_t keep = __ballot_sync(0xffffffffu, lane < last_level && hprio(pm.y) <= vp);
-    const int s = 32 - __clz(keep);                            // = 1 + highest set bit, 0 if none
-    if (lane <= s && lane <= last_level) h.set_l((int)pm.x, lane == s ? value : pm.y);
+    const int s = 32 - __clz(keep);                            // = 1 + highest set bit, 0 if none (always <= last_level)
+    h.set_if((int)pm.x, lane == s ? value : pm.y, lane <= s);
     __syncwarp();
 }
-
 // cooldown values (CellDrift::calculate_cooldown, CellDrift.cpp:34-43): 4, 0xFF, 0xFE (initial), or an odd drift id 1/3/5/7
 __device__ __forceinline__ uint32_t cd_code(uint32_t cd) { return cd == 4u ? 0u : cd == 0xFFu ? 1u : cd == 0xFEu ? 2u : 3u + (cd >> 1); }
-__device__ __forceinline__ uint32_t cd_value(uint32_t code) { return __byte_perm(0x01FEFF04u, 0x00070503u, code); }   // byte `code` of 04 FF FE 01 03 05 07
+__device__ __forceinline__ uint32_t cd_value(uint32_t code) { return __byte_perm(0x01FEFF04u, 0x00070503u, code) & 0xFFu; }   // byte `code` of 04 FF FE 01 03 05 07
 constexpr uint32_t kSeedCode = 7u;     // entry pushed by reset(): its cell's inherit record is NOT in the entry
 __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uint32_t code, uint32_t prio)
 {
     return (prio << 25) | (code << 22) | ((uint32_t)(dy + 8) << 18) | ((uint32_t)(dx + 8) << 14) | idx;
 }
 
+// top-left pixel of linear cell ci (CellPositions::compute_linear, CellPositions.cpp:5-50), branch-free
+// (everything comes from kernel parameters = constant-bank operands: no registers are tied up)
+__device__ __forceinline__ void cell_pixel(const Mode& m, float rcp_narrow, float rcp_wide, int ci, int& px, int& py)
+{
+    const int top_mid = m.top_cells + m.mid_cells;
+    const bool mid = ci >= m.top_cells && ci < top_mid, bot = ci >= top_mid;
+    const int q = ci - (mid ? m.top_cells : (bot ? top_mid : 0));
+    const int width = mid ? m.cells_x : m.cells_x - 2 * m.corner;
+    const int kk = __float2int_rz(((float)q + 0.5f) * (mid ? rcp_wide : rcp_narrow));     // exact floor for q < 2^14
+    const int c = q - kk * width;
+    px = m.cell_offset + kSpacing * (c + (mid ? 0 : m.corner));
+    py = m.cell_offset + kSpacing * (kk + (mid ? m.corner : (bot ? m.cells_y - m.corner : 0)));
+}
+
 // ---------------------------------------------------------------------------------------------- the walk
-// Shared memory of one walking warp: heap[hs + 1] words, then the _remaining bitmap (1 bit per cell).  One byte per cell
-// lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel, off the pop chain):
+// Shared memory of one walking warp: heap[hs + 1] words, the _remaining bitmap (1 bit per cell), the pop's path scratch.
+// One byte per cell lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel):
 //   0 = decoded (FloodDecodePositions::_remaining false), else best_prio + 1 (0xFF for the initial 0xFE).
 // Why the inherit record (drift, best_prio, cooldown; FloodDecodePositions.h:17) can ride in the heap entry: update()
 // only rewrites it when the new error is strictly lower (FloodDecodePositions.cpp:75), and pushes an entry with that
 // error, so of all entries of a cell the one that pops first is always the latest, and it carries the record as it stands.
 // The exception are the eight entries reset() seeds with priority 0/1 while the record says (0,0,0xFE,0xFE): when such an
 // entry pops, the record is the latest update still sitting in the heap (found by a warp-wide scan), else the initial one.
+// Memory latency is taken off the chain by running one cell ahead: as soon as a pop has settled, the NEW heap top names the
+// cell of the next iteration (unless a push with a lower priority overtakes it, which the next iteration checks), so its
+// window rows and its neighbour-table row are requested right away and arrive while the current cell is scored and pushed.
 __global__ void __launch_bounds__(32, 32)
 k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
              int heap_smem, const uint16_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
-             uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace, int serial_above)
+             uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace, int serial_above,
+             float rcp_narrow, float rcp_wide)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
     // [heap: heap_smem + 1 words][_remaining bitmap: kMaxCells / 32 words][path scratch of the pop: kPathSlots x 2 words]
@@ -572,18 +615,18 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
         heap.n = 0;
         {
             const int last = ncells - 1, bmb = m.top_cells;
-            heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0), lane); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0), lane);
-            heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0), lane); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0), lane);
-            heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1), lane); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1), lane);
-            heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1), lane);
-            heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1), lane);
+            heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0), 0u, -1); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0), 0u, -1); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1), 0u, -1); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1), 0u, -1);
         }
 
+        // what was requested ahead for the entry `ahead_e`: window words of this lane's row, neighbour-table entry
+        uint32_t ahead_e = 0xFFFFFFFFu, ahead_ra = 0, ahead_rb = 0, ahead_cv = 0;
         int count = 0;
         while (count < ncells) {
-            // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67).  The entry about to pop is the heap's first
-            // element, so every lane reads it there and the loads of the cell's window / neighbours are in flight while
-            // the sift-down of the pop itself runs.
+            // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67): the entry about to pop is the heap's first element
             if (heap.n == 0) break;                          // heap exhausted (cannot happen on a connected grid)
             const uint32_t e = lds32(sm_base + 4u);
             const int ci = (int)(e & 0x3FFFu);
@@ -591,20 +634,17 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             const uint32_t rem_addr = rem_base + 4u * (uint32_t)(ci >> 5);
             const uint32_t rem_word = lds32(rem_addr);
             if (!(rem_word & rem_bit)) {                     // stale entry of a cell that is already decoded: skipped
-                __syncwarp();
+                __syncwarp();                                // every lane has read the top before the pop rewrites it
                 heap_pop(heap, sl, lane, serial_above);
                 continue;
             }
             ++count;
-            // per-cell table (flood_build_cinfo): lanes 0-3 the direct neighbours (right, left, bottom, top), 4-11 the horizon
-            // chains, 12 / 13 the cell's position (CellPositions::compute_linear, CellPositions.cpp:5-50)
-            uint32_t cv = __ldg(&cinfo[ci * 16 + (lane & 15)]);
             uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
             int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
             if (code == kSeedCode) {                         // (scanned before the pop: the seed entry itself is excluded either way)
                 uint32_t latest = 0xFFFFFFFFu;
                 for (int i = lane; i < heap.n; i += 32) {
-                    const uint32_t t = i < heap.hs ? lds32(heap.sm + 4u * (uint32_t)i + 4u) : __ldcg(heap.spill + (i - heap.hs));
+                    const uint32_t t = heap.get(i);
                     if ((t & 0x3FFFu) == (uint32_t)ci && ((t >> 22) & 7u) != kSeedCode && t < latest) latest = t;
                 }
                 latest = __reduce_min_sync(0xffffffffu, latest);
@@ -614,27 +654,53 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
             }
             const uint32_t cooldown = cd_value(code);
-            const int px = (int)__shfl_sync(0xffffffffu, cv, 12), py = (int)__shfl_sync(0xffffffffu, cv, 13);
+            int px, py;
+            cell_pixel(m, rcp_narrow, rcp_wide, ci, px, py);
             const int x = px + ddx, y = py + ddy;                 // CimbReader.cpp:146-148
-            // ---- 10x10 window at (x-1, y-1): lane r < 10 fetches row r from (at most) two tiles; the rasters are read once
-            // per window and are far bigger than the L2: streaming loads, so that they do not evict the heaps and priority bytes
-            uint32_t ra = 0, rb = 0;
+            // ---- neighbour-table row (lanes 0-3 right / left / bottom / top, 4-11 the horizon chains, see flood_build_cinfo) and the
+            // 10x10 window at (x-1, y-1) (lane r < 10: row r from at most two tiles): taken from the look-ahead when it was for this
+            // very entry (a seed entry's drift is not in the entry: never looked ahead), else requested now.  The rasters are read
+            // once per window and are far bigger than the L2: streaming loads, so that they do not evict the heaps and priority bytes.
+            uint32_t ra, rb, cv;
             const uint32_t rshift = (uint32_t)(x - 1) & 15u;
-            if (lane < 10) {
-                const uint32_t ti = raster_tile_index(tiles_x, x - 1, y - 1 + lane);
-                ra = __ldcs(raster + ti); rb = __ldcs(raster + ti + 16);
+            if (e == ahead_e) { ra = ahead_ra; rb = ahead_rb; cv = ahead_cv; }
+            else {
+                ra = 0; rb = 0;
+                cv = lane < 12 ? (uint32_t)__ldg(&cinfo[ci * 16 + lane]) : 0xFFFFu;
+                if (lane < 10) {
+                    const uint32_t ti = raster_tile_index(tiles_x, x - 1, y - 1 + lane);
+                    ra = __ldcs(raster + ti); rb = __ldcs(raster + ti + 16);
+                }
             }
-            __syncwarp();                                    // every lane has read the heap top / bitmap before they are rewritten
-            heap_pop(heap, sl, lane, serial_above);
-            if (lane == 0) {
-                sts32(rem_addr, rem_word & ~rem_bit);
-                __stcg(prio + ci, (uint8_t)0);
-            }
-            __syncwarp();                                    // the bitmap / prio writes are ordered before the reads below
-            // the candidates' priority bytes: requested now, needed only after the scoring below
+            // every lane has read the heap top / bitmap before they are rewritten, and the priority bytes the last iteration's
+            // pushes marked (stored by other lanes) are ordered before the loads below
+            __syncwarp();
+            // the candidates' priority bytes: requested now, needed after the scoring
             uint32_t pv = 0;
-            if (lane >= 12) cv = 0xFFFFu;
             if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
+            heap_pop(heap, sl, lane, serial_above);
+            sts32(rem_addr, rem_word & ~rem_bit);
+            __stcg(prio + ci, (uint8_t)0);
+            // ---- look ahead: the new top is (most probably) the next cell
+            const uint32_t parent_of = (uint32_t)((heap.n - 1) >> 1);                 // parent of the slot the first push will take
+            const uint32_t parent_val = heap.n > 0 ? heap.get((int)parent_of) : 0u;
+            ahead_e = 0xFFFFFFFFu;
+            if (heap.n > 0) {
+                const uint32_t ne = lds32(sm_base + 4u);
+                if (((ne >> 22) & 7u) != kSeedCode) {
+                    ahead_e = ne;
+                    const int nci = (int)(ne & 0x3FFFu);
+                    int npx, npy;
+                    cell_pixel(m, rcp_narrow, rcp_wide, nci, npx, npy);
+                    const int nx = npx + (int)((ne >> 14) & 15u) - 8, ny = npy + (int)((ne >> 18) & 15u) - 8;
+                    ahead_cv = lane < 12 ? (uint32_t)__ldg(&cinfo[nci * 16 + lane]) : 0xFFFFu;
+                    ahead_ra = 0; ahead_rb = 0;
+                    if (lane < 10) {
+                        const uint32_t ti = raster_tile_index(tiles_x, nx - 1, ny - 1 + lane);
+                        ahead_ra = __ldcs(raster + ti); ahead_rb = __ldcs(raster + ti + 16);
+                    }
+                }
+            }
             const uint32_t myrow = ((ra | (rb << 16)) >> rshift) & 0x3FFu;     // bit i = window col i
             // ---- fast path: the centre hash (drift id 4 = rows 1..8, cols 1..8) is a dictionary tile.  The reference's search
             // starts with id 4 and returns at once on distance 0 (CimbDecoder.cpp:101-132), whatever the cooldown.
@@ -697,35 +763,34 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
                 if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
             }
-            if (lane == 0) {
-                __stcs(result + ci, ((uint32_t)rx & 0x7FFu) | (((uint32_t)ry & 0x7FFu) << 11) | (sym << 22));
-                if (trace) {
-                    CellTrace tr;
-                    tr.order = (uint16_t)(count - 1); tr.x = (int16_t)rx; tr.y = (int16_t)ry;
-                    tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
-                    trace[(size_t)f * ncells + ci] = tr;
-                }
+            __stcs(result + ci, ((uint32_t)rx & 0x7FFu) | (((uint32_t)ry & 0x7FFu) << 11) | (sym << 22));     // (uniform: every lane, one store)
+            if (trace && lane == 0) {
+                CellTrace tr;
+                tr.order = (uint16_t)(count - 1); tr.x = (int16_t)rx; tr.y = (int16_t)ry;
+                tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
+                trace[(size_t)f * ncells + ci] = tr;
             }
             // ---- FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83):
             // lanes 0..11 test one candidate each (still remaining and stored priority > err  <=>  byte >= err + 2); the new
             // priority is recorded and the survivors are pushed in the reference's order (adjacents, horizon, vert).
             const bool horizon = prev_err < 3u && dist < 3u && cooldown == 4u && ncd == 4u;
-            const int cand = (cv != 0xFFFFu && (lane < 4 || horizon)) ? (int)cv : -1;
-            const bool push = cand >= 0 && pv >= dist + 2u;
-            if (push) __stcg(prio + cand, (uint8_t)(dist + 1u));
-            uint32_t todo = __ballot_sync(0xffffffffu, push) & 0xFFFu;
+            const bool push = cv != 0xFFFFu && (lane < 4 || horizon) && pv >= dist + 2u;
+            if (push) __stcg(prio + cv, (uint8_t)(dist + 1u));
+            uint32_t todo = __ballot_sync(0xffffffffu, push);
             const uint32_t entry = make_entry(0, ndx, ndy, cd_code(ncd), dist);
+            int first_parent = (int)parent_of;
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int c = __shfl_sync(0xffffffffu, cand, l);
-                heap_push(heap, entry | (uint32_t)c, lane);
+                const uint32_t c = __shfl_sync(0xffffffffu, cv, l);
+                heap_push(heap, entry | c, parent_val, first_parent);
+                first_parent = -1;
             }
-            __syncwarp();
         }
         __syncwarp();
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------- colour (P8/P9)
 __device__ uint32_t flood_best_color(const float* adjust_tab, const Mode& m, uint32_t ri, uint32_t gi, uint32_t bi)
@@ -932,7 +997,8 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         count_launch();
         int wgrid = cap < ws.slots ? cap : ws.slots;
         k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
-                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace, ws.serial_above); count_launch();
+                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace, ws.serial_above,
+                                                      1.0f / (float)(m.cells_x - 2 * m.corner), 1.0f / (float)m.cells_x); count_launch();
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);

@@ -70,6 +70,7 @@ k_pack_raw(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* _
 
 // ---------------------------------------------------------------------------------------------- GF(256) helpers
 constexpr int kRsWarpsPerCta = 16;
+constexpr int kLaDim = 40;               // >= the largest parity (36)
 constexpr int kStagePitch = 196;         // bytes per staged block: >= 1 + 179, a multiple of 4, 49 words (rows start in different banks)
 
 template <int T>
@@ -81,12 +82,15 @@ struct RsSmem {
     struct PerWarp {
         alignas(16) uint8_t stage[G * kStagePitch];   // the block bytes, `lead` zero bytes first so that the length is a multiple of 4
         alignas(4) uint8_t rem[64];                   // remainder of the block being corrected (state words of its lane group)
+        alignas(2) uint16_t remlog[kMaxParity];       // per remainder byte: byte | log(byte) << 8
         uint8_t synd[kMaxParity];
         uint8_t loc[kMaxParity + 8];
         uint8_t last[kMaxParity + 8];
         uint8_t omega[kMaxParity];
         uint8_t roots[kMaxParity + 8];
     } w[kRsWarpsPerCta];
+    // la[k][j] = log of alpha^((j+1)(k - parity)): the weight of remainder byte k in syndrome j (see k_rs_decode)
+    uint8_t la[kLaDim][kLaDim];
     // followed in dynamic shared memory by the four remainder tables: uint32 lt[4][256][GL] (see k_rs_decode)
 };
 
@@ -146,6 +150,10 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
     for (int i = tid; i < 512; i += blockDim.x) s.exp[i] = c_gf_exp[i];
     for (int i = tid; i < 256; i += blockDim.x) s.log[i] = c_gf_log[i];
     __syncthreads();
+    for (int e = tid; e < m.ecc_bytes * kLaDim; e += blockDim.x) {
+        const int kk = e / kLaDim, j = e % kLaDim;
+        s.la[kk][j] = (uint8_t)((255 - ((j + 1) * (m.ecc_bytes - kk)) % 255) % 255);
+    }
     for (int e = tid; e < 4 * 256 * GL; e += blockDim.x) {
         const int j = e / (256 * GL), v = (e / GL) & 255, k = e % GL;
         uint32_t word = 0;
@@ -171,8 +179,8 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
         for (int g = 0; g < G; ++g) {
             const long gb = unit * G + g;
             uint8_t* st = w.stage + g * kStagePitch;
-            if (lane < 4) st[lane] = 0;                       // the `lead` zero bytes (an absent block stays zero: it reads as clean)
-            if (gb >= total_blocks) { for (int i = lane; i < blk; i += 32) st[lead + i] = 0; continue; }
+            if (lane < lead) st[lane] = 0;                    // the `lead` zero bytes in front (never overlap the block bytes)
+            if (gb >= total_blocks) { for (int i = lane; i < blk; i += 32) st[lead + i] = 0; continue; }   // an absent block reads as clean
             const int f = (int)(gb / b_count), b = b_begin + (int)(gb - (long)f * b_count);
             uint8_t* enc = st + lead;
             if (FUSED) {
@@ -273,20 +281,25 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
                 if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
                 continue;
             }
-            // ---- syndromes from the remainder: S_j = r'(alpha^(j+1)) alpha^(-(j+1) parity), r'[i] = state byte pad + i
+            // ---- syndromes from the remainder: S_j = r'(alpha^(j+1)) alpha^(-(j+1) parity) = sum_k r'[k] alpha^((j+1)(k - parity)),
+            // r'[k] = state byte pad + k.  A plain sum (no Horner chain): the terms are independent, log r'[k] is the same for
+            // every lane, the weights come from the la table
             __syncwarp();
             if (grp == g && k < Pw) reinterpret_cast<uint32_t*>(w.rem)[k] = word;
+            __syncwarp();
+            for (int i = lane; i < md; i += 32) { const uint32_t rb = w.rem[pad + i]; w.remlog[i] = (uint16_t)(rb | ((uint32_t)s.log[rb] << 8)); }
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < T; ++q) {
                 const int j = lane + 32 * q;
                 if (j < md) {
                     uint32_t acc = 0;
-                    for (int i = md - 1; i >= 0; --i) {
-                        const uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + (uint32_t)(j + 1)] : 0u;   // j + 1 <= 64: index < 512
-                        acc = t ^ w.rem[pad + i];
+#pragma unroll 6
+                    for (int i = 0; i < md; ++i) {
+                        const uint32_t rl = w.remlog[i];                                        // broadcast
+                        const uint32_t t = s.exp[(rl >> 8) + (uint32_t)s.la[i][j]];             // index <= 254 + 254
+                        acc ^= (rl & 0xFFu) ? t : 0u;
                     }
-                    if (acc) acc = s.exp[(uint32_t)s.log[acc] + 255u - (uint32_t)(((j + 1) * md) % 255)];
                     w.synd[j] = (uint8_t)acc;
                 }
             }
@@ -481,7 +494,7 @@ static cudaError_t rs_launch_t(const Mode& m, const uint8_t* d_raw, const uint8_
                                uint8_t* d_data, uint8_t* d_ok, const uint8_t* d_rho, int sm_count, cudaStream_t st, int b_begin = 0, int b_count = -1)
 {
     if (b_count < 0) b_count = m.nblocks;
-    if (m.ecc_block + 4 > kStagePitch || m.ecc_bytes > 8 * T * 4) return cudaErrorInvalidValue;
+    if (m.ecc_block + 4 > kStagePitch || m.ecc_bytes > 8 * T * 4 || m.ecc_bytes > kLaDim) return cudaErrorInvalidValue;
     const size_t smem = ((sizeof(RsSmem<T>) + 127) & ~size_t(127)) + sizeof(uint32_t) * 4 * 256 * 8 * T;
     {   // a per-device attribute: set on every launch (a process may hold contexts on several GPUs)
         cudaError_t e = cudaFuncSetAttribute(k_rs_decode<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
