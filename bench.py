@@ -118,6 +118,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def bind_to_gpu_numa_node(index):
+    """pin this process (and therefore its pinned staging buffers, first touched after this call) to the CPUs that are local to
+    GPU `index`: the end-to-end leg is PCIe-bound, and on a two-socket box half of the GPUs hang off the other socket"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to GPU %d" % (len(cpus), index)
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+    return "not bound"
+
+
 # ------------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import numpy as np
@@ -131,6 +150,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the decode path has no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -361,7 +381,25 @@ def run_ours(args):
                "h2d_bytes_per_step": ne * info.frame_bytes,
                "d2h_bytes_per_step": ne * (info.data_bytes + 4 + 1),
                "frames_per_step": ne, "steps": esteps, "api": "cb200_decode_fountain (host pointers, pinned input)",
+               "numa": numa,
                "parity": "ok" if e2e_ok else "MISMATCH"}
+
+    # ---- the drop-in call shape: ONE frame per call (Decoder::decode_fountain(img, sink)), pinned and pageable host memory
+    e2e_single = None
+    if not args.no_e2e and rank == 0:
+        ns = min(64, host_frames.shape[0])
+        pageable = np.array(hf[:ns])                      # an ordinary (pageable) allocation, like a cv::Mat
+        def one_by_one(arr):
+            lat = []
+            for i in range(ns):
+                t0 = time.perf_counter()
+                ctx.decode_fountain(arr[i:i + 1], flags=cc_flags)
+                lat.append(time.perf_counter() - t0)
+            lat.sort()
+            return {"median_ms": lat[len(lat) // 2] * 1e3, "p90_ms": lat[(9 * len(lat)) // 10] * 1e3, "frames_per_s": len(lat) / sum(lat)}
+        one_by_one(hf)                                    # warm-up
+        e2e_single = {"api": "cb200_decode_fountain with n = 1 per call (3.1 MB H2D + band-split K1 + RS + D2H, synchronous)",
+                      "calls": ns, "pinned": one_by_one(hf), "pageable": one_by_one(pageable)}
 
     if rank != 0:
         if world > 1:
@@ -401,6 +439,8 @@ def run_ours(args):
     }
     if e2e:
         out["e2e"] = e2e
+    if e2e_single:
+        out["e2e_single_frame"] = e2e_single
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_from_device_frames(frames, info, MV, stage_ms[3] / B)
     print(json.dumps(out))
