@@ -557,6 +557,20 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t idx, int dx, int dy, uin
     return (prio << 25) | (code << 22) | ((uint32_t)(dy + 8) << 18) | ((uint32_t)(dx + 8) << 14) | idx;
 }
 
+// top-left pixel of linear cell ci (CellPositions::compute_linear, CellPositions.cpp:5-50), branch-free
+// (everything comes from kernel parameters = constant-bank operands: no registers are tied up)
+__device__ __forceinline__ void cell_pixel(const Mode& m, float rcp_narrow, float rcp_wide, int ci, int& px, int& py)
+{
+    const int top_mid = m.top_cells + m.mid_cells;
+    const bool mid = ci >= m.top_cells && ci < top_mid, bot = ci >= top_mid;
+    const int q = ci - (mid ? m.top_cells : (bot ? top_mid : 0));
+    const int width = mid ? m.cells_x : m.cells_x - 2 * m.corner;
+    const int kk = __float2int_rz(((float)q + 0.5f) * (mid ? rcp_wide : rcp_narrow));     // exact floor for q < 2^14
+    const int c = q - kk * width;
+    px = m.cell_offset + kSpacing * (c + (mid ? 0 : m.corner));
+    py = m.cell_offset + kSpacing * (kk + (mid ? m.corner : (bot ? m.cells_y - m.corner : 0)));
+}
+
 // ---------------------------------------------------------------------------------------------- the walk
 // Shared memory of one walk (two per block): heap[hs + 1] words, the _remaining bitmap (1 bit per cell), the pop's path scratch.
 // One byte per cell lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel):
@@ -576,14 +590,13 @@ __global__ void __launch_bounds__(32, 32)
 k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
              int heap_smem, int half_bytes, const uint16_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill,
              size_t spill_cap, uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, const uint32_t* __restrict__ cellpos,
-             CellTrace* __restrict__ trace, int serial_above)
+             CellTrace* __restrict__ trace, int serial_above, float rcp_narrow, float rcp_wide)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
     const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15, hshift = 16 * grp;
     const uint32_t hm = 0xFFFFu << hshift;
-    // [heap: heap_smem + 1 words][_remaining bitmap: kMaxCells / 32 words][path scratch of the pop: kPathSlots x 2 words]
+    // [heap: heap_smem + 1 words][path scratch of the pop: kPathSlots x 2 words]
     const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(walk_smem) + (uint32_t)(grp * half_bytes);
-    const uint32_t rem_base = sm_base + 4u * (uint32_t)(heap_smem + 1);
     const size_t slot = (size_t)blockIdx.x * 2 + grp;
     uint8_t* prio = ws_prio + slot * kMaxCells;
     const int W = m.width, ncells = m.num_cells, tiles_x = W >> 4;
@@ -593,7 +606,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
     const int narrow = m.cells_x - 2 * m.corner;
     const SubtreeLane sl = subtree_lane(lane);
     if (serial_above > kPopParallelMax) serial_above = kPopParallelMax;
-    Heap heap; heap.sm = sm_base; heap.path = rem_base + 4u * (uint32_t)(kMaxCells / 32);
+    Heap heap; heap.sm = sm_base; heap.path = sm_base + 4u * (uint32_t)(heap_smem + 1);
     heap.spill = ws_spill + slot * spill_cap; heap.n = 0; heap.hs = heap_smem;
 
     bool walking = false, finished = false;
@@ -602,7 +615,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
     uint32_t* result = ws_result;
     int count = 0;
     // what was requested ahead for the entry `ahead_e`: window words of this lane's row, neighbour-table entry, the cell's position
-    uint32_t ahead_e = 0xFFFFFFFFu, ahead_ra = 0, ahead_rb = 0, ahead_cv = 0, ahead_xy = 0;
+    uint32_t ahead_e = 0xFFFFFFFFu, ahead_ra = 0, ahead_rb = 0, ahead_cv = 0, ahead_xy = 0, ahead_live = 0;
 
     while (true) {
         __syncwarp();                                        // both halves reconverge here, once per iteration
@@ -617,7 +630,6 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
                 result = ws_result + (size_t)k * ncells;
                 // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
                 for (int i = lane; i < kMaxCells / 16; i += 16) __stcg(reinterpret_cast<uint4*>(prio) + i, make_uint4(~0u, ~0u, ~0u, ~0u));
-                for (int i = lane; i < (ncells + 31) / 32; i += 16) sts32(rem_base + 4u * (uint32_t)i, 0xFFFFFFFFu);
                 __syncwarp(hm);
                 heap.n = 0;
                 const int last = ncells - 1, bmb = m.top_cells;
@@ -637,12 +649,31 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
         if (heap.n == 0) { walking = false; continue; }      // heap exhausted (cannot happen on a connected grid)
         const uint32_t e = lds32(sm_base + 4u);
         const int ci = (int)(e & 0x3FFFu);
-        const uint32_t rem_bit = 1u << (ci & 31);
-        const uint32_t rem_addr = rem_base + 4u * (uint32_t)(ci >> 5);
-        const uint32_t rem_word = lds32(rem_addr);
-        if (!(rem_word & rem_bit)) {                         // stale entry of a cell that is already decoded: skipped
+        // FloodDecodePositions::_remaining[ci] == the cell's priority byte is not 0; known from the look-ahead when that was
+        // for this entry (it cannot have changed since: only popping ci itself clears it), else read now
+        const bool live = e == ahead_e ? ahead_live != 0u : __ldcg(prio + ci) != 0;
+        if (!live) {                                         // stale entry of a cell that is already decoded: skipped
             __syncwarp(hm);                                  // every lane has read the top before the pop rewrites it
             heap_pop(heap, sl, lane, hm, hshift, serial_above);
+            ahead_e = 0xFFFFFFFFu;
+            if (heap.n > 0) {                                // look ahead at the new top (see below)
+                const uint32_t ne = lds32(sm_base + 4u);
+                if (((ne >> 22) & 7u) != kSeedCode) {
+                    ahead_e = ne;
+                    const int nci = (int)(ne & 0x3FFFu);
+                    int npx, npy;
+                    cell_pixel(m, rcp_narrow, rcp_wide, nci, npx, npy);
+                    const uint32_t nx = (uint32_t)(npx + (int)((ne >> 14) & 15u) - 8), ny = (uint32_t)(npy + (int)((ne >> 18) & 15u) - 8);
+                    ahead_xy = nx | (ny << 16);
+                    ahead_live = __ldcg(prio + nci);
+                    ahead_cv = lane < 12 ? (uint32_t)__ldg(&cinfo[nci * 16 + lane]) : 0xFFFFu;
+                    ahead_ra = 0; ahead_rb = 0;
+                    if (lane < 10) {
+                        const uint32_t ti = raster_tile_index(tiles_x, (int)nx - 1, (int)ny - 1 + lane);
+                        ahead_ra = __ldcs(raster + ti); ahead_rb = __ldcs(raster + ti + 16);
+                    }
+                }
+            }
             continue;
         }
         ++count;
@@ -669,8 +700,9 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
         uint32_t ra, rb, cv, xy;
         if (e == ahead_e) { ra = ahead_ra; rb = ahead_rb; cv = ahead_cv; xy = ahead_xy; }
         else {
-            xy = __ldg(cellpos + ci);
-            xy = ((xy & 0xFFFFu) + (uint32_t)ddx) | (((xy >> 16) + (uint32_t)ddy) << 16);          // CimbReader.cpp:146-148
+            int px, py;
+            cell_pixel(m, rcp_narrow, rcp_wide, ci, px, py);
+            xy = (uint32_t)(px + ddx) | ((uint32_t)(py + ddy) << 16);                               // CimbReader.cpp:146-148
             ra = 0; rb = 0;
             cv = lane < 12 ? (uint32_t)__ldg(&cinfo[ci * 16 + lane]) : 0xFFFFu;
             if (lane < 10) {
@@ -687,8 +719,7 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
         uint32_t pv = 0;
         if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
         heap_pop(heap, sl, lane, hm, hshift, serial_above);
-        sts32(rem_addr, rem_word & ~rem_bit);
-        __stcg(prio + ci, (uint8_t)0);
+        __stcg(prio + ci, (uint8_t)0);                       // _remaining[ci] = false
         // ---- look ahead: the new top is (most probably) the next cell
         const int parent_of = (heap.n - 1) >> 1;                                      // parent of the slot the first push will take
         const uint32_t parent_val = heap.n > 0 ? heap.get(parent_of) : 0u;
@@ -698,9 +729,11 @@ k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __
             if (((ne >> 22) & 7u) != kSeedCode) {
                 ahead_e = ne;
                 const int nci = (int)(ne & 0x3FFFu);
-                uint32_t nxy = __ldg(cellpos + nci);
-                nxy = ((nxy & 0xFFFFu) + ((ne >> 14) & 15u) - 8u) | (((nxy >> 16) + ((ne >> 18) & 15u) - 8u) << 16);
+                int npx, npy;
+                cell_pixel(m, rcp_narrow, rcp_wide, nci, npx, npy);
+                const uint32_t nxy = (uint32_t)(npx + (int)((ne >> 14) & 15u) - 8) | ((uint32_t)(npy + (int)((ne >> 18) & 15u) - 8) << 16);
                 ahead_xy = nxy;
+                ahead_live = __ldcg(prio + nci);             // (this cell's own byte was cleared above: a second entry of it reads 0)
                 ahead_cv = lane < 12 ? (uint32_t)__ldg(&cinfo[nci * 16 + lane]) : 0xFFFFu;
                 ahead_ra = 0; ahead_rb = 0;
                 if (lane < 10) {
@@ -913,7 +946,7 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     ws->heap_smem = 511;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
     // one block = one warp = two walks (one per half-warp), each with its own heap / bitmap / path scratch
-    ws->half_bytes = (int)((((size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + (size_t)kPathSlots * 8) + 15) & ~size_t(15));
+    ws->half_bytes = (int)((((size_t)(ws->heap_smem + 1) * 4 + (size_t)kPathSlots * 8) + 15) & ~size_t(15));
     ws->walk_smem = 2 * (size_t)ws->half_bytes;
     int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));        // blocks per SM
     if (per_sm > 32) per_sm = 32;
@@ -1008,7 +1041,7 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         const int walks = cap < ws.slots ? cap : ws.slots;
         k_flood_walk<<<(walks + 1) / 2, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.half_bytes,
                                                                   ws.raster, ws.result, ws.spill, ws.spill_cap, ws.prio, ws.cinfo, ws.cellpos, d_trace,
-                                                                  ws.serial_above); count_launch();
+                                                                  ws.serial_above, 1.0f / (float)(m.cells_x - 2 * m.corner), 1.0f / (float)m.cells_x); count_launch();
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);
