@@ -356,20 +356,17 @@ k_flood_raster_fast(const Mode m, const uint8_t* __restrict__ rgb, const uint32_
     }
 }
 
-// ---------------------------------------------------------------------------------------------- heap (uniform per half-warp)
-// A walking warp carries TWO frames, one per half-warp (16 lanes): every instruction that is uniform within a walk -- most of
-// them -- then serves two walks.  Below, "lane" means the lane within the half (0..15), `hm` is the half's member mask.
-//
+// ---------------------------------------------------------------------------------------------- heap (warp-uniform)
 // 32-bit entries: prio(7) << 25 | cooldown code(3) << 22 | (dy + 8)(4) << 18 | (dx + 8)(4) << 14 | cell index(14).
 // std::priority_queue<decode_prio, vector, PrioCompare> with comp(a, b) = a.prio > b.prio: only the priority is compared,
 // so the pop order of equal priorities is whatever libstdc++'s sift-up / sift-down produce; both are restated literally.
 // Element i lives at shared word i + 1 (so the children 2h+1, 2h+2 are one aligned 64-bit load) while i < hs, else in
 // the global spill area at word i - hs (hs is odd, so a pair never straddles the two).  Shared memory is addressed through
 // 32-bit shared-window addresses.
-// Every lane of a half executes push and pop with the same arguments and keeps the same `n`.  Where the address and the value
-// are the same in every lane ("uniform" accesses) EVERY lane stores: the redundant stores merge into one, no branch is
-// needed, and each lane later reads back what it wrote itself, so no barrier is needed either.  Only the sift-down spreads
-// different nodes over the lanes; its results are published with one barrier.
+// Every lane of the walking warp executes push and pop with the same arguments and keeps the same `n`.  Where the address and
+// the value are the same in every lane ("uniform" accesses) EVERY lane stores: the redundant stores merge into one, no branch
+// is needed, and each lane later reads back what it wrote itself, so no warp barrier is needed either.  Only the sift-down
+// spreads different nodes over the lanes; its results are published with one barrier.
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
@@ -424,16 +421,16 @@ __device__ __forceinline__ void heap_push(Heap& h, uint32_t e, uint32_t parent0,
     h.set(hole, e);
 }
 
-// per-lane constants of the four-level subtree a sift-down round works on: lane i < 15 stands for the node at depth d,
+// per-lane constants of the five-level subtree a sift-down round works on: lane i < 31 stands for the node at depth d,
 // position j of the subtree (heap order: i = 2^d - 1 + j), i.e. node = (hole + 1) * 2^d + j - 1; anc_mask has the bits of its
 // ancestors' lanes, anc_want the value each of those bits must have ("ancestor prefers its left child") for the descent to
-// pass through this node.  Lane 15 stands for no node (its index is always beyond the heap).
+// pass through this node.  Lane 31 stands for no node (its index is always beyond the heap).
 struct SubtreeLane { int pow2d, jm1; bool last; uint32_t anc_mask, anc_want; };
 __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
 {
     SubtreeLane s;
     const int d = 31 - __clz(lane + 1);
-    s.pow2d = 1 << d; s.jm1 = lane - s.pow2d; s.last = d == 3;
+    s.pow2d = 1 << d; s.jm1 = lane - s.pow2d; s.last = d == 4;
     s.anc_mask = 0; s.anc_want = 0;
     for (int i = lane; i > 0;) {
         const int p = (i - 1) >> 1;
@@ -441,11 +438,11 @@ __device__ __forceinline__ SubtreeLane subtree_lane(int lane)
         if (i & 1) s.anc_want |= 1u << p;            // odd index = left child
         i = p;
     }
-    if (lane == 15) { s.pow2d = 0; s.jm1 = 0x3FFFFFFF; s.last = false; s.anc_mask = 0; s.anc_want = 0; }
+    if (lane == 31) { s.pow2d = 0; s.jm1 = 0x3FFFFFFF; s.last = false; s.anc_mask = 0; s.anc_want = 0; }
     return s;
 }
 
-// the literal form, one level per step (only reached by heaps of more than 32 767 entries, or when a test asks for it).
+// the literal form, one level per step (only reached by heaps of more than 65 535 entries, or when a test asks for it).
 // Uniform: returns the new element count.
 __device__ __noinline__ int heap_pop_serial(Heap h)
 {
@@ -483,19 +480,18 @@ __device__ __noinline__ int heap_pop_serial(Heap h)
 //   if (len even && second == (len - 2) / 2) { second = 2 (second + 1); v[hole] = v[second - 1]; hole = second - 1; }
 //   sift `value` (the former last element) up from the hole: while (parent.prio > value.prio) { v[hole] = v[parent]; hole = parent; }
 // The descent path h_0 = 0, h_1, ..., h_L does not depend on `value`, only on which child each node prefers.  One round
-// handles the 15 nodes of the four-level subtree under the current hole: lane i loads the two children of its node, the
+// handles the 31 nodes of the five-level subtree under the current hole: lane i loads the two children of its node, the
 // preferences are collected with one ballot, and every lane decides from its ancestors' bits whether the descent passes
-// through its node -- a dozen levels cost three or four memory round trips instead of a dozen.  Nothing of the heap is stored
-// during the descent: the lane of path level k writes (h_k, m_k = old v[h_(k+1)], the value that WOULD move up into h_k) to a
-// small scratch.  The sift-up walks the same path backwards and undoes those moves while prio(m_k) > prio(value); so with
+// through its node -- a dozen levels cost three memory round trips instead of a dozen.  Nothing of the heap is stored during
+// the descent: the lane of path level k writes (h_k, m_k = old v[h_(k+1)], the value that WOULD move up into h_k) to a small
+// scratch.  The sift-up walks the same path backwards and undoes those moves while prio(m_k) > prio(value); so with
 // s = 1 + max { k : prio(m_k) <= prio(value) } the net effect is v[h_k] = m_k for k < s, v[h_s] = value, everything below
 // untouched: lane k stores level k -- s + 1 stores, no reads.
-constexpr int kPopRounds = 4;          // 16 levels; the finish has one lane per level, so heaps beyond 32 767 entries (four times
-constexpr int kPopParallelMax = 32767; // the largest seen) take heap_pop_serial
+constexpr int kPopRounds = 3;          // 15 levels: heaps of up to 65 535 entries (seven times the largest seen); beyond: heap_pop_serial
 constexpr int kPathSlots = 20;
-__device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane, uint32_t hm, int hshift, int serial_above)
+__device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lane, int serial_above)
 {
-    if (h.n > serial_above) { h.n = heap_pop_serial(h); __syncwarp(hm); return; }
+    if (h.n > serial_above) { h.n = heap_pop_serial(h); __syncwarp(); return; }
     const uint32_t value = h.get(h.n - 1);                     // (often in L2: in flight during the rounds, used after them)
     const int len = --h.n;
     if (len == 0) return;
@@ -503,7 +499,7 @@ __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lan
     int hole = 0;
 #pragma unroll
     for (int r = 0; r < kPopRounds; ++r) {
-        if (hole < lim) {                                      // uniform within the half
+        if (hole < lim) {                                      // warp-uniform
             const int node = (hole + 1) * sl.pow2d + sl.jm1;
             const bool has2 = node < lim;                      // both children inside the heap: the descent continues below it
             const int ce = 2 * node + 2;                       // its right child's element index
@@ -516,7 +512,7 @@ __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lan
                              : "+r"(c.x), "+r"(c.y) : "r"(h.sm + 4u * (uint32_t)ce), "l"(h.spill + (ce - 1 - h.hs)), "r"(in_sm), "r"(in_gl));
             }
             const bool left = hprio(c.y) > hprio(c.x);         // right child strictly worse -> the left child moves up
-            const uint32_t pref = __ballot_sync(hm, has2 && left) >> hshift;
+            const uint32_t pref = __ballot_sync(0xffffffffu, has2 && left);
             // the descent reaches this node iff its parent has two children ((node - 1) / 2 < lim <=> node <= 2 lim) and every
             // ancestor points towards it
             const bool reached = node <= 2 * lim && (((pref ^ sl.anc_want) & sl.anc_mask) == 0u);
@@ -526,7 +522,7 @@ __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lan
             }
             // the round ends at the first reached node without two children, or below the subtree's last level: exactly one lane
             const int nxt = has2 ? ce - (left ? 1 : 0) : node;
-            hole = (int)__reduce_or_sync(hm, (reached && (!has2 || sl.last)) ? (uint32_t)nxt : 0u);
+            hole = (int)__reduce_or_sync(0xffffffffu, (reached && (!has2 || sl.last)) ? (uint32_t)nxt : 0u);
         }
     }
     int last_level = 31 - __clz(hole + 1);                     // level of the hole the descent ends in
@@ -537,17 +533,16 @@ __device__ __forceinline__ void heap_pop(Heap& h, const SubtreeLane& sl, int lan
         hole = 2 * hole + 1;
         ++last_level;
     }
-    __syncwarp(hm);
+    __syncwarp();
     // ---- lane k owns path level k: s = 1 + deepest level whose moved value does not have to go back down
     uint2 pm = make_uint2((uint32_t)hole, 0u);
     if (lane < last_level) pm = lds64(h.path + 8u * (uint32_t)lane);
     const uint32_t vp = hprio(value);
-    const uint32_t keep = __ballot_sync(hm, lane < last_level && hprio(pm.y) <= vp) >> hshift;
-    const int s = 32 - __clz(keep);                            // = 1 + highest set bit, 0 if none (always <= last_level <= 15)
+    const uint32_t keep = __ballot_sync(0xffffffffu, lane < last_level && hprio(pm.y) <= vp);
+    const int s = 32 - __clz(keep);                            // = 1 + highest set bit, 0 if none (always <= last_level)
     h.set_if((int)pm.x, lane == s ? value : pm.y, lane <= s);
-    __syncwarp(hm);
+    __syncwarp();
 }
-
 // cooldown values (CellDrift::calculate_cooldown, CellDrift.cpp:34-43): 4, 0xFF, 0xFE (initial), or an odd drift id 1/3/5/7
 __device__ __forceinline__ uint32_t cd_code(uint32_t cd) { return cd == 4u ? 0u : cd == 0xFFu ? 1u : cd == 0xFEu ? 2u : 3u + (cd >> 1); }
 __device__ __forceinline__ uint32_t cd_value(uint32_t code) { return __byte_perm(0x01FEFF04u, 0x00070503u, code) & 0xFFu; }   // byte `code` of 04 FF FE 01 03 05 07
@@ -572,261 +567,233 @@ __device__ __forceinline__ void cell_pixel(const Mode& m, float rcp_narrow, floa
 }
 
 // ---------------------------------------------------------------------------------------------- the walk
-// Shared memory of one walk (two per block): heap[hs + 1] words, the _remaining bitmap (1 bit per cell), the pop's path scratch.
+// Shared memory of one walking warp: heap[hs + 1] words, the _remaining bitmap (1 bit per cell), the pop's path scratch.
 // One byte per cell lives in a per-slot global array (L2 resident, read by the 12 candidate lanes in parallel):
 //   0 = decoded (FloodDecodePositions::_remaining false), else best_prio + 1 (0xFF for the initial 0xFE).
 // Why the inherit record (drift, best_prio, cooldown; FloodDecodePositions.h:17) can ride in the heap entry: update()
 // only rewrites it when the new error is strictly lower (FloodDecodePositions.cpp:75), and pushes an entry with that
 // error, so of all entries of a cell the one that pops first is always the latest, and it carries the record as it stands.
 // The exception are the eight entries reset() seeds with priority 0/1 while the record says (0,0,0xFE,0xFE): when such an
-// entry pops, the record is the latest update still sitting in the heap (found by a scan over the half's lanes), else the
-// initial one.
+// entry pops, the record is the latest update still sitting in the heap (found by a warp-wide scan), else the initial one.
 // Memory latency is taken off the chain by running one cell ahead: as soon as a pop has settled, the NEW heap top names the
 // cell of the next iteration (unless a push with a lower priority overtakes it, which the next iteration checks), so its
 // window rows and its neighbour-table row are requested right away and arrive while the current cell is scored and pushed.
-// The two halves of the warp walk different frames in lock step: one iteration of the loop = one heap entry for each half, with
-// a full-warp barrier at the top so that the halves reconverge whatever they did in the iteration before.
 __global__ void __launch_bounds__(32, 32)
 k_flood_walk(const Mode m, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters, int base, int cap, uint32_t* next_counter,
-             int heap_smem, int half_bytes, const uint16_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill,
-             size_t spill_cap, uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, const uint32_t* __restrict__ cellpos,
-             CellTrace* __restrict__ trace, int serial_above, float rcp_narrow, float rcp_wide)
+             int heap_smem, const uint16_t* __restrict__ ws_raster, uint32_t* __restrict__ ws_result, uint32_t* ws_spill, size_t spill_cap,
+             uint8_t* ws_prio, const uint16_t* __restrict__ cinfo, CellTrace* __restrict__ trace, int serial_above,
+             float rcp_narrow, float rcp_wide)
 {
     extern __shared__ __align__(16) uint8_t walk_smem[];
-    const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15, hshift = 16 * grp;
-    const uint32_t hm = 0xFFFFu << hshift;
-    // [heap: heap_smem + 1 words][path scratch of the pop: kPathSlots x 2 words]
-    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(walk_smem) + (uint32_t)(grp * half_bytes);
-    const size_t slot = (size_t)blockIdx.x * 2 + grp;
-    uint8_t* prio = ws_prio + slot * kMaxCells;
+    // [heap: heap_smem + 1 words][_remaining bitmap: kMaxCells / 32 words][path scratch of the pop: kPathSlots x 2 words]
+    const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(walk_smem);
+    const uint32_t rem_base = sm_base + 4u * (uint32_t)(heap_smem + 1);
+    uint8_t* prio = ws_prio + (size_t)blockIdx.x * kMaxCells;
+    const int lane = threadIdx.x;
     const int W = m.width, ncells = m.num_cells, tiles_x = W >> 4;
     const size_t rwords = raster_words16(W, m.height);
     const int cnt = chunk_count(counters, base, cap);
-    const unsigned long long tileL = cx_tiles_L[lane];
+    const unsigned long long tileL = cx_tiles_L[lane & 15];
     const int narrow = m.cells_x - 2 * m.corner;
     const SubtreeLane sl = subtree_lane(lane);
-    if (serial_above > kPopParallelMax) serial_above = kPopParallelMax;
-    Heap heap; heap.sm = sm_base; heap.path = sm_base + 4u * (uint32_t)(heap_smem + 1);
-    heap.spill = ws_spill + slot * spill_cap; heap.n = 0; heap.hs = heap_smem;
-
-    bool walking = false, finished = false;
-    uint32_t f = 0;
-    const uint16_t* raster = ws_raster;
-    uint32_t* result = ws_result;
-    int count = 0;
-    // what was requested ahead for the entry `ahead_e`: window words of this lane's row, neighbour-table entry, the cell's position
-    uint32_t ahead_e = 0xFFFFFFFFu, ahead_ra = 0, ahead_rb = 0, ahead_cv = 0, ahead_xy = 0, ahead_live = 0;
+    Heap heap; heap.sm = sm_base; heap.path = rem_base + 4u * (uint32_t)(kMaxCells / 32);
+    heap.spill = ws_spill + (size_t)blockIdx.x * spill_cap; heap.n = 0; heap.hs = heap_smem;
 
     while (true) {
-        __syncwarp();                                        // both halves reconverge here, once per iteration
-        if (!walking && !finished) {
-            uint32_t k = 0;
-            if (lane == 0) k = atomicAdd(next_counter, 1u);
-            k = __shfl_sync(hm, k, 0, 16);
-            if (k >= (uint32_t)cnt) finished = true;
-            else {
-                f = list[base + k];
-                raster = ws_raster + (size_t)k * rwords;
-                result = ws_result + (size_t)k * ncells;
-                // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
-                for (int i = lane; i < kMaxCells / 16; i += 16) __stcg(reinterpret_cast<uint4*>(prio) + i, make_uint4(~0u, ~0u, ~0u, ~0u));
-                __syncwarp(hm);
-                heap.n = 0;
-                const int last = ncells - 1, bmb = m.top_cells;
-                heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0), 0u, -1); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0), 0u, -1);
-                heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0), 0u, -1); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0), 0u, -1);
-                heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1), 0u, -1); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1), 0u, -1);
-                heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1), 0u, -1);
-                heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1), 0u, -1);
-                count = 0; ahead_e = 0xFFFFFFFFu;
-                walking = true;
-            }
-        }
-        if (__all_sync(0xffffffffu, finished)) break;
-        if (!walking) continue;
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(next_counter, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= (uint32_t)cnt) break;
+        const uint32_t f = list[base + k];
+        const uint16_t* raster = ws_raster + (size_t)k * rwords;
+        uint32_t* result = ws_result + (size_t)k * ncells;
 
-        // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67): the entry about to pop is the heap's first element
-        if (heap.n == 0) { walking = false; continue; }      // heap exhausted (cannot happen on a connected grid)
-        const uint32_t e = lds32(sm_base + 4u);
-        const int ci = (int)(e & 0x3FFFu);
-        // FloodDecodePositions::_remaining[ci] == the cell's priority byte is not 0; known from the look-ahead when that was
-        // for this entry (it cannot have changed since: only popping ci itself clears it), else read now
-        const bool live = e == ahead_e ? ahead_live != 0u : __ldcg(prio + ci) != 0;
-        if (!live) {                                         // stale entry of a cell that is already decoded: skipped
-            __syncwarp(hm);                                  // every lane has read the top before the pop rewrites it
-            heap_pop(heap, sl, lane, hm, hshift, serial_above);
+        // ---- FloodDecodePositions::reset (FloodDecodePositions.cpp:17-42)
+        for (int i = lane; i < kMaxCells / 16; i += 32) __stcg(reinterpret_cast<uint4*>(prio) + i, make_uint4(~0u, ~0u, ~0u, ~0u));
+        for (int i = lane; i < (ncells + 31) / 32; i += 32) sts32(rem_base + 4u * (uint32_t)i, 0xFFFFFFFFu);
+        __syncwarp();
+        heap.n = 0;
+        {
+            const int last = ncells - 1, bmb = m.top_cells;
+            heap_push(heap, make_entry(0, 0, 0, kSeedCode, 0), 0u, -1); heap_push(heap, make_entry((uint32_t)(narrow - 1), 0, 0, kSeedCode, 0), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)last, 0, 0, kSeedCode, 0), 0u, -1); heap_push(heap, make_entry((uint32_t)(last - (narrow - 1)), 0, 0, kSeedCode, 0), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)bmb, 0, 0, kSeedCode, 1), 0u, -1); heap_push(heap, make_entry((uint32_t)(bmb + m.cells_x - 1), 0, 0, kSeedCode, 1), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)(last - bmb), 0, 0, kSeedCode, 1), 0u, -1);
+            heap_push(heap, make_entry((uint32_t)(last - (bmb + m.cells_x - 1)), 0, 0, kSeedCode, 1), 0u, -1);
+        }
+
+        // what was requested ahead for the entry `ahead_e`: window words of this lane's row, neighbour-table entry
+        uint32_t ahead_e = 0xFFFFFFFFu, ahead_ra = 0, ahead_rb = 0, ahead_cv = 0;
+        int ahead_x = 0, ahead_y = 0;
+        int count = 0;
+        while (count < ncells) {
+            // ---- FloodDecodePositions::next (FloodDecodePositions.cpp:49-67): the entry about to pop is the heap's first element
+            if (heap.n == 0) break;                          // heap exhausted (cannot happen on a connected grid)
+            const uint32_t e = lds32(sm_base + 4u);
+            const int ci = (int)(e & 0x3FFFu);
+            const uint32_t rem_bit = 1u << (ci & 31);
+            const uint32_t rem_addr = rem_base + 4u * (uint32_t)(ci >> 5);
+            const uint32_t rem_word = lds32(rem_addr);
+            if (!(rem_word & rem_bit)) {                     // stale entry of a cell that is already decoded: skipped
+                __syncwarp();                                // every lane has read the top before the pop rewrites it
+                heap_pop(heap, sl, lane, serial_above);
+                continue;
+            }
+            ++count;
+            uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
+            int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
+            if (code == kSeedCode) {                         // (scanned before the pop: the seed entry itself is excluded either way)
+                uint32_t latest = 0xFFFFFFFFu;
+                for (int i = lane; i < heap.n; i += 32) {
+                    const uint32_t t = heap.get(i);
+                    if ((t & 0x3FFFu) == (uint32_t)ci && ((t >> 22) & 7u) != kSeedCode && t < latest) latest = t;
+                }
+                latest = __reduce_min_sync(0xffffffffu, latest);
+                if (latest != 0xFFFFFFFFu) {
+                    code = (latest >> 22) & 7u; prev_err = latest >> 25;
+                    ddx = (int)((latest >> 14) & 15u) - 8; ddy = (int)((latest >> 18) & 15u) - 8;
+                } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
+            }
+            const uint32_t cooldown = cd_value(code);
+            // ---- neighbour-table row (lanes 0-3 right / left / bottom / top, 4-11 the horizon chains, see flood_build_cinfo) and the
+            // 10x10 window at (x-1, y-1) (lane r < 10: row r from at most two tiles): taken from the look-ahead when it was for this
+            // very entry (a seed entry's drift is not in the entry: never looked ahead), else requested now.  The rasters are read
+            // once per window and are far bigger than the L2: streaming loads, so that they do not evict the heaps and priority bytes.
+            uint32_t ra, rb, cv;
+            int x, y;                                             // CimbReader.cpp:146-148: position + drift
+            if (e == ahead_e) { ra = ahead_ra; rb = ahead_rb; cv = ahead_cv; x = ahead_x; y = ahead_y; }
+            else {
+                int px, py;
+                cell_pixel(m, rcp_narrow, rcp_wide, ci, px, py);
+                x = px + ddx; y = py + ddy;
+                ra = 0; rb = 0;
+                cv = lane < 12 ? (uint32_t)__ldg(&cinfo[ci * 16 + lane]) : 0xFFFFu;
+                if (lane < 10) {
+                    const uint32_t ti = raster_tile_index(tiles_x, x - 1, y - 1 + lane);
+                    ra = __ldcs(raster + ti); rb = __ldcs(raster + ti + 16);
+                }
+            }
+            // every lane has read the heap top / bitmap before they are rewritten, and the priority bytes the last iteration's
+            // pushes marked (stored by other lanes) are ordered before the loads below
+            __syncwarp();
+            const uint32_t rshift = (uint32_t)(x - 1) & 15u;
+            // the candidates' priority bytes: requested now, needed after the scoring
+            uint32_t pv = 0;
+            if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
+            heap_pop(heap, sl, lane, serial_above);
+            sts32(rem_addr, rem_word & ~rem_bit);
+            __stcg(prio + ci, (uint8_t)0);
+            // ---- look ahead: the new top is (most probably) the next cell
+            const uint32_t parent_of = (uint32_t)((heap.n - 1) >> 1);                 // parent of the slot the first push will take
+            const uint32_t parent_val = heap.n > 0 ? heap.get((int)parent_of) : 0u;
             ahead_e = 0xFFFFFFFFu;
-            if (heap.n > 0) {                                // look ahead at the new top (see below)
+            if (heap.n > 0) {
                 const uint32_t ne = lds32(sm_base + 4u);
                 if (((ne >> 22) & 7u) != kSeedCode) {
                     ahead_e = ne;
                     const int nci = (int)(ne & 0x3FFFu);
                     int npx, npy;
                     cell_pixel(m, rcp_narrow, rcp_wide, nci, npx, npy);
-                    const uint32_t nx = (uint32_t)(npx + (int)((ne >> 14) & 15u) - 8), ny = (uint32_t)(npy + (int)((ne >> 18) & 15u) - 8);
-                    ahead_xy = nx | (ny << 16);
-                    ahead_live = __ldcg(prio + nci);
+                    const int nx = npx + (int)((ne >> 14) & 15u) - 8, ny = npy + (int)((ne >> 18) & 15u) - 8;
+                    ahead_x = nx; ahead_y = ny;
                     ahead_cv = lane < 12 ? (uint32_t)__ldg(&cinfo[nci * 16 + lane]) : 0xFFFFu;
                     ahead_ra = 0; ahead_rb = 0;
                     if (lane < 10) {
-                        const uint32_t ti = raster_tile_index(tiles_x, (int)nx - 1, (int)ny - 1 + lane);
+                        const uint32_t ti = raster_tile_index(tiles_x, nx - 1, ny - 1 + lane);
                         ahead_ra = __ldcs(raster + ti); ahead_rb = __ldcs(raster + ti + 16);
                     }
                 }
             }
-            continue;
-        }
-        ++count;
-        uint32_t code = (e >> 22) & 7u, prev_err = e >> 25;
-        int ddx = (int)((e >> 14) & 15u) - 8, ddy = (int)((e >> 18) & 15u) - 8;
-        if (code == kSeedCode) {                             // (scanned before the pop: the seed entry itself is excluded either way)
-            uint32_t latest = 0xFFFFFFFFu;
-            for (int i = lane; i < heap.n; i += 16) {
-                const uint32_t t = heap.get(i);
-                if ((t & 0x3FFFu) == (uint32_t)ci && ((t >> 22) & 7u) != kSeedCode && t < latest) latest = t;
-            }
-            latest = __reduce_min_sync(hm, latest);
-            if (latest != 0xFFFFFFFFu) {
-                code = (latest >> 22) & 7u; prev_err = latest >> 25;
-                ddx = (int)((latest >> 14) & 15u) - 8; ddy = (int)((latest >> 18) & 15u) - 8;
-            } else { code = 2u; prev_err = 0xFEu; ddx = 0; ddy = 0; }
-        }
-        const uint32_t cooldown = cd_value(code);
-        // ---- the cell's position (CellPositions::compute_linear, CellPositions.cpp:5-50: a table), its neighbour-table row (lanes
-        // 0-3 right / left / bottom / top, 4-11 the horizon chains, see flood_build_cinfo) and the 10x10 window at (x-1, y-1)
-        // (lane r < 10: row r from at most two tiles): taken from the look-ahead when it was for this very entry (a seed entry's
-        // drift is not in the entry: never looked ahead), else requested now.  The rasters are read once per window and are far
-        // bigger than the L2: streaming loads, so that they do not evict the heaps and priority bytes.
-        uint32_t ra, rb, cv, xy;
-        if (e == ahead_e) { ra = ahead_ra; rb = ahead_rb; cv = ahead_cv; xy = ahead_xy; }
-        else {
-            int px, py;
-            cell_pixel(m, rcp_narrow, rcp_wide, ci, px, py);
-            xy = (uint32_t)(px + ddx) | ((uint32_t)(py + ddy) << 16);                               // CimbReader.cpp:146-148
-            ra = 0; rb = 0;
-            cv = lane < 12 ? (uint32_t)__ldg(&cinfo[ci * 16 + lane]) : 0xFFFFu;
-            if (lane < 10) {
-                const uint32_t ti = raster_tile_index(tiles_x, (int)(xy & 0xFFFFu) - 1, (int)(xy >> 16) - 1 + lane);
-                ra = __ldcs(raster + ti); rb = __ldcs(raster + ti + 16);
-            }
-        }
-        const int x = (int)(xy & 0xFFFFu), y = (int)(xy >> 16);
-        const uint32_t rshift = (uint32_t)(x - 1) & 15u;
-        // every lane has read the heap top / bitmap before they are rewritten, and the priority bytes the last iteration's
-        // pushes marked (stored by other lanes) are ordered before the loads below
-        __syncwarp(hm);
-        // the candidates' priority bytes: requested now, needed after the scoring
-        uint32_t pv = 0;
-        if (cv != 0xFFFFu) pv = __ldcg(prio + cv);
-        heap_pop(heap, sl, lane, hm, hshift, serial_above);
-        __stcg(prio + ci, (uint8_t)0);                       // _remaining[ci] = false
-        // ---- look ahead: the new top is (most probably) the next cell
-        const int parent_of = (heap.n - 1) >> 1;                                      // parent of the slot the first push will take
-        const uint32_t parent_val = heap.n > 0 ? heap.get(parent_of) : 0u;
-        ahead_e = 0xFFFFFFFFu;
-        if (heap.n > 0) {
-            const uint32_t ne = lds32(sm_base + 4u);
-            if (((ne >> 22) & 7u) != kSeedCode) {
-                ahead_e = ne;
-                const int nci = (int)(ne & 0x3FFFu);
-                int npx, npy;
-                cell_pixel(m, rcp_narrow, rcp_wide, nci, npx, npy);
-                const uint32_t nxy = (uint32_t)(npx + (int)((ne >> 14) & 15u) - 8) | ((uint32_t)(npy + (int)((ne >> 18) & 15u) - 8) << 16);
-                ahead_xy = nxy;
-                ahead_live = __ldcg(prio + nci);             // (this cell's own byte was cleared above: a second entry of it reads 0)
-                ahead_cv = lane < 12 ? (uint32_t)__ldg(&cinfo[nci * 16 + lane]) : 0xFFFFu;
-                ahead_ra = 0; ahead_rb = 0;
-                if (lane < 10) {
-                    const uint32_t ti = raster_tile_index(tiles_x, (int)(nxy & 0xFFFFu) - 1, (int)(nxy >> 16) - 1 + lane);
-                    ahead_ra = __ldcs(raster + ti); ahead_rb = __ldcs(raster + ti + 16);
-                }
-            }
-        }
-        const uint32_t myrow = ((ra | (rb << 16)) >> rshift) & 0x3FFu;     // bit i = window col i
-        // ---- fast path: the centre hash (drift id 4 = rows 1..8, cols 1..8) is a dictionary tile.  The reference's search
-        // starts with id 4 and returns at once on distance 0 (CimbDecoder.cpp:101-132), whatever the cooldown.
-        uint32_t dist, sym, ncd;
-        int id, ndx, ndy, rx, ry;
-        bool exact;
-        {
-            const uint32_t b = (myrow >> 1) & 0xFFu;
-            const uint32_t plo = (lane >= 1 && lane <= 4) ? b << (8 * (lane - 1)) : 0u;
-            const uint32_t phi = (lane >= 5 && lane <= 8) ? b << (8 * (lane - 5)) : 0u;
-            const uint32_t clo = __reduce_or_sync(hm, plo), chi = __reduce_or_sync(hm, phi);
-            const uint4 te = cx_tiles_slot[(clo * m.hash_mul) >> 28];
-            exact = te.x == clo && te.y == chi;
-            sym = te.z;
-        }
-        if (exact) {                                         // uniform within the half
-            dist = 0; id = 4; ncd = 4; ndx = ddx; ndy = ddy; rx = x; ry = y;
-        } else {
-            uint32_t win[10];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(hm, myrow, r, 16);
-            // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
-            // lane q < 9 extracts the hash at drift id order[q]: the window's 8-bit columns c0..c0+7 of all ten rows form one
-            // 80-bit string, the hash at row offset r0 is bits [8 r0, 8 r0 + 64) of it (ahash_result::extract, ahash_result.h:70-106)
-            uint32_t hlo, hhi;
+            const uint32_t myrow = ((ra | (rb << 16)) >> rshift) & 0x3FFu;     // bit i = window col i
+            // ---- fast path: the centre hash (drift id 4 = rows 1..8, cols 1..8) is a dictionary tile.  The reference's search
+            // starts with id 4 and returns at once on distance 0 (CimbDecoder.cpp:101-132), whatever the cooldown.
+            uint32_t dist, sym, ncd;
+            int id, ndx, ndy, rx, ry;
+            bool exact;
             {
-                const int qq = lane < 9 ? lane : 0;
-                const int r0 = (int)((0x200201211ULL >> (4 * qq)) & 3u), c0 = (int)((0x020210121ULL >> (4 * qq)) & 3u);   // id / 3, id % 3
-                uint32_t b[10];
+                const uint32_t b = (myrow >> 1) & 0xFFu;
+                const uint32_t plo = (lane >= 1 && lane <= 4) ? b << (8 * (lane - 1)) : 0u;
+                const uint32_t phi = (lane >= 5 && lane <= 8) ? b << (8 * (lane - 5)) : 0u;
+                const uint32_t clo = __reduce_or_sync(0xffffffffu, plo), chi = __reduce_or_sync(0xffffffffu, phi);
+                const uint4 te = cx_tiles_slot[(clo * m.hash_mul) >> 28];          // uniform index: one constant-bank read
+                exact = te.x == clo && te.y == chi;
+                sym = te.z;
+            }
+            if (exact) {                                     // warp-uniform
+                dist = 0; id = 4; ncd = 4; ndx = ddx; ndy = ddy; rx = x; ry = y;
+            } else {
+                uint32_t win[10];
 #pragma unroll
-                for (int r = 0; r < 10; ++r) b[r] = (win[r] >> c0) & 0xFFu;
-                const uint32_t w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-                const uint32_t w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-                const uint32_t w2 = b[8] | (b[9] << 8);
-                hlo = __funnelshift_r(w0, w1, 8 * r0); hhi = __funnelshift_r(w1, w2, 8 * r0);
+                for (int r = 0; r < 10; ++r) win[r] = __shfl_sync(0xffffffffu, myrow, r);
+                // ---- candidates (id order 4,5,7,3,1,8,0,2,6; tiles 0..15), key = dist<<8 | order<<4 | tile
+                // lane q < 9 extracts the hash at drift id order[q]: the window's 8-bit columns c0..c0+7 of all ten rows form one
+                // 80-bit string, the hash at row offset r0 is bits [8 r0, 8 r0 + 64) of it (ahash_result::extract, ahash_result.h:70-106)
+                uint32_t hlo, hhi;
+                {
+                    const int qq = lane < 9 ? lane : 0;
+                    const int r0 = (int)((0x200201211ULL >> (4 * qq)) & 3u), c0 = (int)((0x020210121ULL >> (4 * qq)) & 3u);   // id / 3, id % 3
+                    uint32_t b[10];
+#pragma unroll
+                    for (int r = 0; r < 10; ++r) b[r] = (win[r] >> c0) & 0xFFu;
+                    const uint32_t w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+                    const uint32_t w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+                    const uint32_t w2 = b[8] | (b[9] << 8);
+                    hlo = __funnelshift_r(w0, w1, 8 * r0); hhi = __funnelshift_r(w1, w2, 8 * r0);
+                }
+                // every lane scores its tile (lane & 15) against the hashes q = 2 it + (lane >> 4)
+                const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
+                const int nq = all ? 9 : 5;
+                const uint32_t tile_lo = (uint32_t)tileL, tile_hi = (uint32_t)(tileL >> 32);
+                uint32_t best_key = 0xFFFFFFFFu;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    if (it >= 3 && !all) break;                       // warp-uniform
+                    const int q = 2 * it + (lane >> 4);
+                    const uint32_t lo = __shfl_sync(0xffffffffu, hlo, q & 15), hi = __shfl_sync(0xffffffffu, hhi, q & 15);
+                    const int qid = (int)((0x620813754ULL >> (4 * q)) & 0xF);         // packed order table, nibble q
+                    const bool valid = q < nq && !((uint32_t)qid == cooldown && qid != 4);   // CimbDecoder.cpp:116
+                    const uint32_t d = (uint32_t)(__popc(lo ^ tile_lo) + __popc(hi ^ tile_hi));
+                    const uint32_t key = valid ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)(lane & 15)) : 0xFFFFFFFFu;
+                    best_key = key < best_key ? key : best_key;
+                }
+                best_key = __reduce_min_sync(0xffffffffu, best_key);
+                // every lane derives the (warp-uniform) decision from the reduced key
+                dist = best_key >> 8; sym = best_key & 0xFu;
+                id = (int)((0x620813754ULL >> (4 * ((best_key >> 4) & 0xFu))) & 0xF);
+                const int bx = id % 3 - 1, by = id / 3 - 1;                       // CellDrift::driftPairs, CellDrift.h:13-15
+                ndx = clampi(ddx + bx, -7, 7); ndy = clampi(ddy + by, -7, 7);     // CellDrift.cpp:23-31
+                rx = x + bx; ry = y + by;
+                // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
+                if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
             }
-            // lane t scores tile t against one hash per step
-            const bool all = (cooldown == 0xFEu);                 // CimbDecoder.cpp:144
-            const int nq = all ? 9 : 5;
-            const uint32_t tile_lo = (uint32_t)tileL, tile_hi = (uint32_t)(tileL >> 32);
-            uint32_t best_key = 0xFFFFFFFFu;
-            for (int q = 0; q < nq; ++q) {                        // uniform within the half
-                const uint32_t lo = __shfl_sync(hm, hlo, q, 16), hi = __shfl_sync(hm, hhi, q, 16);
-                const int qid = (int)((0x620813754ULL >> (4 * q)) & 0xF);             // packed order table, nibble q
-                const bool valid = !((uint32_t)qid == cooldown && qid != 4);           // CimbDecoder.cpp:116
-                const uint32_t d = (uint32_t)(__popc(lo ^ tile_lo) + __popc(hi ^ tile_hi));
-                const uint32_t key = valid ? ((d << 8) | ((uint32_t)q << 4) | (uint32_t)lane) : 0xFFFFFFFFu;
-                best_key = key < best_key ? key : best_key;
+            __stcs(result + ci, ((uint32_t)rx & 0x7FFu) | (((uint32_t)ry & 0x7FFu) << 11) | (sym << 22));     // (uniform: every lane, one store)
+            if (trace && lane == 0) {
+                CellTrace tr;
+                tr.order = (uint16_t)(count - 1); tr.x = (int16_t)rx; tr.y = (int16_t)ry;
+                tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
+                trace[(size_t)f * ncells + ci] = tr;
             }
-            best_key = __reduce_min_sync(hm, best_key);
-            // every lane derives the (uniform) decision from the reduced key
-            dist = best_key >> 8; sym = best_key & 0xFu;
-            id = (int)((0x620813754ULL >> (4 * ((best_key >> 4) & 0xFu))) & 0xF);
-            const int bx = id % 3 - 1, by = id / 3 - 1;                       // CellDrift::driftPairs, CellDrift.h:13-15
-            ndx = clampi(ddx + bx, -7, 7); ndy = clampi(ddy + by, -7, 7);     // CellDrift.cpp:23-31
-            rx = x + bx; ry = y + by;
-            // CellDrift::calculate_cooldown, CellDrift.cpp:34-43
-            if (id == 4) ncd = 4; else if ((id & 1) == 0) ncd = 0xFF; else if (((cooldown ^ (uint32_t)id) & 0xFFu) == 6) ncd = 0xFF; else ncd = (uint32_t)id;
+            // ---- FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83):
+            // lanes 0..11 test one candidate each (still remaining and stored priority > err  <=>  byte >= err + 2); the new
+            // priority is recorded and the survivors are pushed in the reference's order (adjacents, horizon, vert).
+            const bool horizon = prev_err < 3u && dist < 3u && cooldown == 4u && ncd == 4u;
+            const bool push = cv != 0xFFFFu && (lane < 4 || horizon) && pv >= dist + 2u;
+            if (push) __stcg(prio + cv, (uint8_t)(dist + 1u));
+            uint32_t todo = __ballot_sync(0xffffffffu, push);
+            const uint32_t entry = make_entry(0, ndx, ndy, cd_code(ncd), dist);
+            int first_parent = (int)parent_of;
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t c = __shfl_sync(0xffffffffu, cv, l);
+                heap_push(heap, entry | c, parent_val, first_parent);
+                first_parent = -1;
+            }
         }
-        __stcs(result + ci, ((uint32_t)rx & 0x7FFu) | (((uint32_t)ry & 0x7FFu) << 11) | (sym << 22));     // (uniform: every lane, one store)
-        if (trace && lane == 0) {
-            CellTrace tr;
-            tr.order = (uint16_t)(count - 1); tr.x = (int16_t)rx; tr.y = (int16_t)ry;
-            tr.drift_offset = (uint8_t)id; tr.distance = (uint8_t)dist;
-            trace[(size_t)f * ncells + ci] = tr;
-        }
-        // ---- FloodDecodePositions::update (FloodDecodePositions.cpp:86-129) with update_adjacents (:69-83):
-        // lanes 0..11 test one candidate each (still remaining and stored priority > err  <=>  byte >= err + 2); the new
-        // priority is recorded and the survivors are pushed in the reference's order (adjacents, horizon, vert).
-        const bool horizon = prev_err < 3u && dist < 3u && cooldown == 4u && ncd == 4u;
-        const bool push = cv != 0xFFFFu && (lane < 4 || horizon) && pv >= dist + 2u;
-        if (push) __stcg(prio + cv, (uint8_t)(dist + 1u));
-        uint32_t todo = __ballot_sync(hm, push) >> hshift;
-        const uint32_t entry = make_entry(0, ndx, ndy, cd_code(ncd), dist);
-        int first_parent = parent_of;
-        while (todo) {
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t c = __shfl_sync(hm, cv, l, 16);
-            heap_push(heap, entry | c, parent_val, first_parent);
-            first_parent = -1;
-        }
-        if (count >= ncells) walking = false;
+        __syncwarp();
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------- colour (P8/P9)
 __device__ uint32_t flood_best_color(const float* adjust_tab, const Mode& m, uint32_t ri, uint32_t gi, uint32_t bi)
@@ -934,6 +901,11 @@ static void flood_build_cinfo(const Mode& m, const uint16_t* adj, std::vector<ui
         };
         if (right >= 0 && left >= 0) { chain(right, 0, 4); chain(left, 1, 6); }
         if (top >= 0 && bottom >= 0) { chain(top, 3, 8); chain(bottom, 2, 10); }
+        int k, cc, rbase, ncols, x0;                       // slots 12, 13: the cell's top-left pixel
+        cell_row_col(m, i, k, cc);
+        cell_row_geom(m, k, rbase, ncols, x0);
+        o[12] = (uint16_t)(x0 + kSpacing * cc);
+        o[13] = (uint16_t)(m.cell_offset + kSpacing * k);
     }
 }
 
@@ -941,18 +913,16 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
 {
     memset(ws, 0, sizeof(*ws));
     ws->sm_count = sm_count;
-    // shared-memory heap entries per walk (must be odd): 511 = the nine top levels; deeper levels go to the per-slot spill
-    // area in L2.  Shared memory per walk decides how many walks an SM holds (two per block, at most 32 blocks).
-    ws->heap_smem = 511;
+    // shared-memory heap entries per walking warp (must be odd): 1023 = the ten top levels; deeper levels go to the
+    // per-slot spill area in L2.  Shared memory per walk decides how many walks an SM holds (at most 32 blocks).
+    ws->heap_smem = 1023;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
-    // one block = one warp = two walks (one per half-warp), each with its own heap / bitmap / path scratch
-    ws->half_bytes = (int)((((size_t)(ws->heap_smem + 1) * 4 + (size_t)kPathSlots * 8) + 15) & ~size_t(15));
-    ws->walk_smem = 2 * (size_t)ws->half_bytes;
-    int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));        // blocks per SM
+    ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + (size_t)kPathSlots * 8;
+    int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
-    if (const char* s = getenv("CB200_K1X_WALKS_PER_SM")) { int v = atoi(s) / 2; if (v >= 1 && v <= per_sm) per_sm = v; }
-    ws->slots = sm_count * per_sm * 2;
+    if (const char* s = getenv("CB200_K1X_WALKS_PER_SM")) { int v = atoi(s); if (v >= 1 && v <= per_sm) per_sm = v; }
+    ws->slots = sm_count * per_sm;
     ws->max_entries = kFloodMaxEntries;
     if (const char* s = getenv("CB200_K1X_MAX_ENTRIES")) { int v = atoi(s); if (v >= 1 && v <= kFloodMaxEntries) ws->max_entries = v; }   // tests: force several chunks
     ws->serial_above = 65536;                        // heaps beyond three five-level rounds pop one level at a time
@@ -967,22 +937,12 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     flood_build_cinfo(m, adj_host, cinfo);
     if ((e = cudaMalloc(&ws->cinfo, cinfo.size() * sizeof(uint16_t))) != cudaSuccess) return e;
     if ((e = cudaMemcpy(ws->cinfo, cinfo.data(), cinfo.size() * sizeof(uint16_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-    // top-left pixel of every cell, x | y << 16 (CellPositions::compute_linear, CellPositions.cpp:5-50)
-    std::vector<uint32_t> pos((size_t)m.num_cells);
-    for (int i = 0; i < m.num_cells; ++i) {
-        int k, cc, rbase, ncols, x0;
-        cell_row_col(m, i, k, cc);
-        cell_row_geom(m, k, rbase, ncols, x0);
-        pos[(size_t)i] = (uint32_t)(x0 + kSpacing * cc) | ((uint32_t)(m.cell_offset + kSpacing * k) << 16);
-    }
-    if ((e = cudaMalloc(&ws->cellpos, pos.size() * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMemcpy(ws->cellpos, pos.data(), pos.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 void flood_workspace_destroy(FloodWorkspace* ws)
 {
-    cudaFree(ws->spill); cudaFree(ws->prio); cudaFree(ws->cinfo); cudaFree(ws->cellpos); cudaFree(ws->list); cudaFree(ws->counters); cudaFree(ws->raster); cudaFree(ws->result);
+    cudaFree(ws->spill); cudaFree(ws->prio); cudaFree(ws->cinfo); cudaFree(ws->list); cudaFree(ws->counters); cudaFree(ws->raster); cudaFree(ws->result);
     memset(ws, 0, sizeof(*ws));
 }
 
@@ -1038,10 +998,10 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
             k_flood_raster_fast<<<rgrid, kFastThreads, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
         }
         count_launch();
-        const int walks = cap < ws.slots ? cap : ws.slots;
-        k_flood_walk<<<(walks + 1) / 2, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.half_bytes,
-                                                                  ws.raster, ws.result, ws.spill, ws.spill_cap, ws.prio, ws.cinfo, ws.cellpos, d_trace,
-                                                                  ws.serial_above, 1.0f / (float)(m.cells_x - 2 * m.corner), 1.0f / (float)m.cells_x); count_launch();
+        int wgrid = cap < ws.slots ? cap : ws.slots;
+        k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
+                                                      ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace, ws.serial_above,
+                                                      1.0f / (float)(m.cells_x - 2 * m.corner), 1.0f / (float)m.cells_x); count_launch();
         long long cthreads = (long long)cap * m.num_cells;
         long long cblocks = (cthreads + 255) / 256;
         int cgrid = (int)(cblocks < (long long)ws.sm_count * 8 ? cblocks : (long long)ws.sm_count * 8);

@@ -18,8 +18,7 @@ struct CellTrace {
 
 struct FloodWorkspace {
     int sm_count;
-    int slots;                 // walks resident at once (one frame each; two per warp, one warp per block)
-    int half_bytes;            // shared memory of one walk (half of a block's)
+    int slots;                 // walking warps resident at once (one frame each)
     int heap_smem;             // heap entries per walk kept in shared memory (odd)
     size_t walk_smem;          // dynamic shared memory of one walking warp
     size_t spill_cap;          // heap spill entries per slot
@@ -27,7 +26,6 @@ struct FloodWorkspace {
     uint32_t* spill;           // [slots][spill_cap]
     uint8_t* prio;             // [slots][kMaxCells] per-cell priority bytes of the walk in that slot
     uint16_t* cinfo;           // [num_cells][16] update candidates in push order (0xFFFF = none)
-    uint32_t* cellpos;         // [num_cells] top-left pixel x | y << 16
     int list_cap; uint32_t* list; uint32_t* counters;   // work list; counters[0] = listed frames, [1 + c] = chunk c's work counter
     int max_entries;           // upper bound of entry_cap (one chunk); larger work lists are processed chunk by chunk
     int entry_cap; uint16_t* raster; uint32_t* result;  // per listed frame of a chunk: 1-bit raster in 16x16 tiles, per-cell x | y<<11 | sym<<22
