@@ -69,6 +69,23 @@ def build(force=False, verbose=False):
     return LIB
 
 
+FACADE_LIB = os.path.join(HERE, "lib", "libcimbard_b200.so")
+
+
+def build_facade(force=False, verbose=False):
+    """lib/libcimbard_b200.so: the reference's cimbard_* receive facade (include/cimbard_b200.h) over libcb200.so."""
+    src = os.path.join(HERE, "host", "cimbard_b200.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "cb200.h")]
+    if not force and os.path.exists(FACADE_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(FACADE_LIB) for d in deps):
+        return FACADE_LIB
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", FACADE_LIB, src, "-L" + os.path.dirname(LIB), "-lcb200",
+           "-Wl,-rpath,$ORIGIN", "-ldl"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return FACADE_LIB
+
+
 WIREHAIR_LIB = os.path.join(HERE, "lib", "libwirehair.so")
 WIREHAIR_SRC = "/root/reference/src/third_party_lib/wirehair"
 
@@ -95,3 +112,4 @@ def build_wirehair(force=False, verbose=False):
 if __name__ == "__main__":
     print(build_wirehair(force="--force" in sys.argv, verbose=True))
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_facade(force="--force" in sys.argv, verbose=True))

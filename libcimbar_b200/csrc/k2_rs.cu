@@ -16,6 +16,8 @@
 #include "cb200_common.cuh"
 #include "k2_rs.cuh"
 #include <cstring>
+#include <cstdlib>
+#include <cstdint>
 
 namespace cb200 {
 
@@ -94,14 +96,14 @@ struct RsSmem {
     // followed in dynamic shared memory by the four remainder tables: uint32 lt[4][256][GL] (see k_rs_decode)
 };
 
-template <int T>
-__device__ __forceinline__ uint32_t gf_mul(const RsSmem<T>& s, uint32_t a, uint32_t b)
+template <class S>
+__device__ __forceinline__ uint32_t gf_mul(const S& s, uint32_t a, uint32_t b)
 {   // field_mul, libcorrect field.h:92-110
     if (a == 0 || b == 0) return 0;
     return s.exp[(uint32_t)s.log[a] + (uint32_t)s.log[b]];
 }
-template <int T>
-__device__ __forceinline__ uint32_t gf_div(const RsSmem<T>& s, uint32_t a, uint32_t b)
+template <class S>
+__device__ __forceinline__ uint32_t gf_div(const S& s, uint32_t a, uint32_t b)
 {   // field_div, field.h:112-129 (x / 0 == 0)
     if (a == 0 || b == 0) return 0;
     return s.exp[255u + (uint32_t)s.log[a] - (uint32_t)s.log[b]];
@@ -117,6 +119,182 @@ __device__ __forceinline__ uint32_t warp_xor(uint32_t v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---------------------------------------------------------------------------------------------- one dirty block
+// The whole warp corrects ONE block whose remainder modulo x^pad g is nonzero: enc[0 .. blk) is corrected in place; returns
+// false when libcorrect would report failure (root count != locator order).  `holds`: this lane carries state word k of the
+// block's remainder in `word`.  S: exp/log/la tables, W: the warp's scratch (rem, remlog, synd, loc, last, omega, roots).
+template <int T, class S, class W>
+__device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc, const int md, const int blk, const int pad,
+                                                 const bool holds, const uint32_t word, const int k, const int lane)
+{
+            // ---- syndromes from the remainder: S_j = r'(alpha^(j+1)) alpha^(-(j+1) parity) = sum_k r'[k] alpha^((j+1)(k - parity)),
+            // r'[k] = state byte pad + k.  A plain sum (no Horner chain): the terms are independent, log r'[k] is the same for
+            // every lane, the weights come from the la table
+            __syncwarp();
+            if (holds) reinterpret_cast<uint32_t*>(w.rem)[k] = word;
+            __syncwarp();
+            for (int i = lane; i < md; i += 32) { const uint32_t rb = w.rem[pad + i]; w.remlog[i] = (uint16_t)(rb | ((uint32_t)s.log[rb] << 8)); }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+                const int j = lane + 32 * q;
+                if (j < md) {
+                    uint32_t acc = 0;
+#pragma unroll 6
+                    for (int i = 0; i < md; ++i) {
+                        const uint32_t rl = w.remlog[i];                                        // broadcast
+                        const uint32_t t = s.exp[(rl >> 8) + (uint32_t)s.la[i][j]];             // index <= 254 + 254
+                        acc ^= (rl & 0xFFu) ? t : 0u;
+                    }
+                    w.synd[j] = (uint8_t)acc;
+                }
+            }
+            __syncwarp();
+        // ---- Berlekamp-Massey (decode.c:30-116).  Field arithmetic is exact, so scale = disc / last_disc is applied as one
+        //      multiplication (libcorrect writes mul-then-div per coefficient: same element); what must match libcorrect is
+        //      the update rule and the order bookkeeping, because they decide the locator it reports for uncorrectable blocks.
+        uint32_t numerrors = 0, loc_order = 0, last_order = 0, last_disc = 1, delay = 1;
+        if (T == 1) {
+            // parity <= 31: coefficient j of the locator / previous locator lives in lane j, syndrome j in lane j
+            uint32_t loc = (lane == 0), last = (lane == 0);
+            const uint32_t syn = (lane < md) ? (uint32_t)w.synd[lane] : 0u;
+            const uint32_t lsyn = s.log[syn];
+            for (uint32_t i = 0; i < (uint32_t)md; ++i) {
+                // disc = S[i] ^ sum_{j=1..numerrors} loc[j] * S[i-j]
+                const uint32_t sj = __shfl_sync(0xffffffffu, syn, (int)(i - (uint32_t)lane) & 31);
+                const uint32_t lsj = __shfl_sync(0xffffffffu, lsyn, (int)(i - (uint32_t)lane) & 31);
+                uint32_t term = 0;
+                if ((uint32_t)lane >= 1u && (uint32_t)lane <= numerrors && loc != 0 && sj != 0) term = s.exp[(uint32_t)s.log[loc] + lsj];
+                const uint32_t disc = __reduce_xor_sync(0xffffffffu, term) ^ __shfl_sync(0xffffffffu, syn, (int)i);
+                if (disc == 0) { delay++; continue; }
+                const uint32_t lscale = 255u + (uint32_t)s.log[disc] - (uint32_t)s.log[last_disc];      // log(disc / last_disc), last_disc != 0
+                const uint32_t top = last_order + delay;
+                const uint32_t shifted = __shfl_up_sync(0xffffffffu, last, delay);                              // last[j - delay]
+                const uint32_t lsc = lscale >= 255u ? lscale - 255u : lscale;                                   // in [0, 254]: exp index stays < 512
+                const uint32_t sh = ((uint32_t)lane >= delay && (uint32_t)lane <= top && shifted != 0) ? (uint32_t)s.exp[(uint32_t)s.log[shifted] + lsc] : 0u;
+                if (2 * numerrors <= i) {
+                    // last <- x^delay * scale * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
+                    if ((uint32_t)lane <= top) { const uint32_t t0 = loc; loc ^= sh; last = t0; }
+                    const uint32_t tmp = loc_order;
+                    loc_order = top; last_order = tmp;
+                    numerrors = i + 1 - numerrors;
+                    last_disc = disc;
+                    delay = 1;
+                    continue;
+                }
+                // no length change: loc[j+delay] ^= scale * last[j]
+                loc ^= sh;
+                if (top > loc_order) loc_order = top;
+                delay++;
+            }
+            w.loc[lane] = (uint8_t)loc;
+            if (lane < 8) w.loc[32 + lane] = 0;
+            __syncwarp();
+        } else {
+        // coefficients in shared memory, updated lane-parallel (parity > 31 needs more than one coefficient per lane)
+        for (int j = lane; j < kMaxParity + 8; j += 32) { w.loc[j] = (j == 0); w.last[j] = (j == 0); }
+        __syncwarp();
+        for (uint32_t i = 0; i < (uint32_t)md; ++i) {
+            uint32_t part = 0;
+            for (uint32_t j = 1 + lane; j <= numerrors; j += 32) part ^= gf_mul(s, w.loc[j], w.synd[i - j]);
+            uint32_t disc = warp_xor(part) ^ w.synd[i];
+            if (disc == 0) { delay++; continue; }
+            if (2 * numerrors <= i) {
+                // last <- x^delay * (disc/last_disc) * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
+                uint32_t top = last_order + delay;
+                uint32_t sh[3], lc[3];
+                int q = 0;
+                for (uint32_t j = lane; j <= top; j += 32, ++q) {
+                    sh[q] = (j < delay) ? 0u : gf_div(s, gf_mul(s, w.last[j - delay], disc), last_disc);
+                    lc[q] = w.loc[j];
+                }
+                __syncwarp();
+                q = 0;
+                for (uint32_t j = lane; j <= top; j += 32, ++q) {
+                    w.loc[j] = (uint8_t)(lc[q] ^ sh[q]);
+                    w.last[j] = (uint8_t)lc[q];
+                }
+                __syncwarp();
+                uint32_t tmp = loc_order;
+                loc_order = top; last_order = tmp;
+                numerrors = i + 1 - numerrors;
+                last_disc = disc;
+                delay = 1;
+                continue;
+            }
+            // no length change: loc[j+delay] ^= (disc/last_disc) * last[j]
+            for (uint32_t j = lane; j <= last_order; j += 32)
+                w.loc[j + delay] ^= (uint8_t)gf_div(s, gf_mul(s, w.last[j], disc), last_disc);
+            __syncwarp();
+            if (last_order + delay > loc_order) loc_order = last_order + delay;
+            delay++;
+        }
+        }
+        const uint32_t order = loc_order;
+
+        // ---- Chien search over all field elements in increasing order (decode.c:120-143); element 0 is never a
+        //      root (loc[0] == 1); root count must equal the locator order, else the block fails
+        uint32_t myroots = 0;   // bit k set: element lane*8+k is a root
+        for (int k = 0; k < 8; ++k) {
+            uint32_t e = (uint32_t)lane * 8u + (uint32_t)k;
+            if (e == 0) continue;
+            uint32_t le = s.log[e];
+            uint32_t acc = w.loc[order];
+            for (int i = (int)order - 1; i >= 0; --i) {
+                uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + le] : 0u;
+                acc = t ^ w.loc[i];
+            }
+            if (acc == 0) myroots |= 1u << k;
+        }
+        uint32_t cnt = __popc(myroots);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total != order || order == 0) {   // order==0 cannot happen with nonzero syndromes; guarded for safety
+            if (order == 0 && total == 0) {
+                // libcorrect would "succeed" with no corrections; unreachable because S != 0 forces order >= 1
+            }
+            return false;
+        }
+        {
+            uint32_t pos = incl - cnt;
+            for (int k = 0; k < 8; ++k) if (myroots & (1u << k)) w.roots[pos++] = (uint8_t)(lane * 8 + k);
+        }
+        // ---- error evaluator omega = S(x) * loc(x) mod x^md  (decode.c:146-161, polynomial.c:17-31)
+        for (int k = lane; k < md; k += 32) {
+            uint32_t acc = 0;
+            int lim = (int)order < k ? (int)order : k;
+            for (int i = 0; i <= lim; ++i) acc ^= gf_mul(s, w.loc[i], w.synd[k - i]);
+            w.omega[k] = (uint8_t)acc;
+        }
+        __syncwarp();
+        // ---- Forney (decode.c:163-194) + apply (decode.c:369-372); one root per lane-slot
+        for (uint32_t q = lane; q < order; q += 32) {
+            uint32_t X = w.roots[q];
+            uint32_t lx = s.log[X];
+            // omega(X) and loc'(X) by Horner; loc'[i] = loc[i+1] for even i, 0 for odd i (polynomial.c:97-111)
+            uint32_t num = 0;
+            for (int i = md - 1; i >= 0; --i) {
+                uint32_t t = num ? (uint32_t)s.exp[(uint32_t)s.log[num] + lx] : 0u;
+                num = t ^ w.omega[i];
+            }
+            uint32_t den = 0;
+            for (int i = (int)order - 1; i >= 0; --i) {
+                uint32_t t = den ? (uint32_t)s.exp[(uint32_t)s.log[den] + lx] : 0u;
+                uint32_t c = ((i & 1) == 0) ? (uint32_t)w.loc[i + 1] : 0u;
+                den = t ^ c;
+            }
+            uint32_t err = gf_div(s, num, den);          // X^(fcr-1) = 1 for fcr = 1
+            uint32_t inv = s.exp[510u - lx];             // field_div(1, X): log[1] = 255
+            uint32_t location = s.log[inv];              // coefficient index (255 when inv == 1: out of range in libcorrect)
+            if (location >= (uint32_t)md && location < (uint32_t)blk)
+                enc[blk - 1 - (int)location] ^= (uint8_t)err;
+        }
+        __syncwarp();
+        return true;
 }
 
 // ---------------------------------------------------------------------------------------------- RS decode
@@ -281,176 +459,197 @@ k_rs_decode(const Mode m, const uint8_t* __restrict__ raw, const uint8_t* __rest
                 if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
                 continue;
             }
-            // ---- syndromes from the remainder: S_j = r'(alpha^(j+1)) alpha^(-(j+1) parity) = sum_k r'[k] alpha^((j+1)(k - parity)),
-            // r'[k] = state byte pad + k.  A plain sum (no Horner chain): the terms are independent, log r'[k] is the same for
-            // every lane, the weights come from the la table
             __syncwarp();
-            if (grp == g && k < Pw) reinterpret_cast<uint32_t*>(w.rem)[k] = word;
+            const bool good = rs_correct_block<T>(s, w, enc, md, blk, pad, grp == g && k < Pw, word, k, lane);
             __syncwarp();
-            for (int i = lane; i < md; i += 32) { const uint32_t rb = w.rem[pad + i]; w.remlog[i] = (uint16_t)(rb | ((uint32_t)s.log[rb] << 8)); }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < T; ++q) {
-                const int j = lane + 32 * q;
-                if (j < md) {
-                    uint32_t acc = 0;
-#pragma unroll 6
-                    for (int i = 0; i < md; ++i) {
-                        const uint32_t rl = w.remlog[i];                                        // broadcast
-                        const uint32_t t = s.exp[(rl >> 8) + (uint32_t)s.la[i][j]];             // index <= 254 + 254
-                        acc ^= (rl & 0xFFu) ? t : 0u;
-                    }
-                    w.synd[j] = (uint8_t)acc;
-                }
-            }
-            __syncwarp();
-        // ---- Berlekamp-Massey (decode.c:30-116).  Field arithmetic is exact, so scale = disc / last_disc is applied as one
-        //      multiplication (libcorrect writes mul-then-div per coefficient: same element); what must match libcorrect is
-        //      the update rule and the order bookkeeping, because they decide the locator it reports for uncorrectable blocks.
-        uint32_t numerrors = 0, loc_order = 0, last_order = 0, last_disc = 1, delay = 1;
-        if (T == 1) {
-            // parity <= 31: coefficient j of the locator / previous locator lives in lane j, syndrome j in lane j
-            uint32_t loc = (lane == 0), last = (lane == 0);
-            const uint32_t syn = (lane < md) ? (uint32_t)w.synd[lane] : 0u;
-            const uint32_t lsyn = s.log[syn];
-            for (uint32_t i = 0; i < (uint32_t)md; ++i) {
-                // disc = S[i] ^ sum_{j=1..numerrors} loc[j] * S[i-j]
-                const uint32_t sj = __shfl_sync(0xffffffffu, syn, (int)(i - (uint32_t)lane) & 31);
-                const uint32_t lsj = __shfl_sync(0xffffffffu, lsyn, (int)(i - (uint32_t)lane) & 31);
-                uint32_t term = 0;
-                if ((uint32_t)lane >= 1u && (uint32_t)lane <= numerrors && loc != 0 && sj != 0) term = s.exp[(uint32_t)s.log[loc] + lsj];
-                const uint32_t disc = __reduce_xor_sync(0xffffffffu, term) ^ __shfl_sync(0xffffffffu, syn, (int)i);
-                if (disc == 0) { delay++; continue; }
-                const uint32_t lscale = 255u + (uint32_t)s.log[disc] - (uint32_t)s.log[last_disc];      // log(disc / last_disc), last_disc != 0
-                const uint32_t top = last_order + delay;
-                const uint32_t shifted = __shfl_up_sync(0xffffffffu, last, delay);                              // last[j - delay]
-                const uint32_t lsc = lscale >= 255u ? lscale - 255u : lscale;                                   // in [0, 254]: exp index stays < 512
-                const uint32_t sh = ((uint32_t)lane >= delay && (uint32_t)lane <= top && shifted != 0) ? (uint32_t)s.exp[(uint32_t)s.log[shifted] + lsc] : 0u;
-                if (2 * numerrors <= i) {
-                    // last <- x^delay * scale * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
-                    if ((uint32_t)lane <= top) { const uint32_t t0 = loc; loc ^= sh; last = t0; }
-                    const uint32_t tmp = loc_order;
-                    loc_order = top; last_order = tmp;
-                    numerrors = i + 1 - numerrors;
-                    last_disc = disc;
-                    delay = 1;
-                    continue;
-                }
-                // no length change: loc[j+delay] ^= scale * last[j]
-                loc ^= sh;
-                if (top > loc_order) loc_order = top;
-                delay++;
-            }
-            w.loc[lane] = (uint8_t)loc;
-            if (lane < 8) w.loc[32 + lane] = 0;
-            __syncwarp();
-        } else {
-        // coefficients in shared memory, updated lane-parallel (parity > 31 needs more than one coefficient per lane)
-        for (int j = lane; j < kMaxParity + 8; j += 32) { w.loc[j] = (j == 0); w.last[j] = (j == 0); }
-        __syncwarp();
-        for (uint32_t i = 0; i < (uint32_t)md; ++i) {
-            uint32_t part = 0;
-            for (uint32_t j = 1 + lane; j <= numerrors; j += 32) part ^= gf_mul<T>(s, w.loc[j], w.synd[i - j]);
-            uint32_t disc = warp_xor(part) ^ w.synd[i];
-            if (disc == 0) { delay++; continue; }
-            if (2 * numerrors <= i) {
-                // last <- x^delay * (disc/last_disc) * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
-                uint32_t top = last_order + delay;
-                uint32_t sh[3], lc[3];
-                int q = 0;
-                for (uint32_t j = lane; j <= top; j += 32, ++q) {
-                    sh[q] = (j < delay) ? 0u : gf_div<T>(s, gf_mul<T>(s, w.last[j - delay], disc), last_disc);
-                    lc[q] = w.loc[j];
-                }
-                __syncwarp();
-                q = 0;
-                for (uint32_t j = lane; j <= top; j += 32, ++q) {
-                    w.loc[j] = (uint8_t)(lc[q] ^ sh[q]);
-                    w.last[j] = (uint8_t)lc[q];
-                }
-                __syncwarp();
-                uint32_t tmp = loc_order;
-                loc_order = top; last_order = tmp;
-                numerrors = i + 1 - numerrors;
-                last_disc = disc;
-                delay = 1;
+            if (!good) {
+                for (int i = lane; i < msg_len; i += 32) out[i] = 0;
+                if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 0;
                 continue;
             }
-            // no length change: loc[j+delay] ^= (disc/last_disc) * last[j]
-            for (uint32_t j = lane; j <= last_order; j += 32)
-                w.loc[j + delay] ^= (uint8_t)gf_div<T>(s, gf_mul<T>(s, w.last[j], disc), last_disc);
-            __syncwarp();
-            if (last_order + delay > loc_order) loc_order = last_order + delay;
-            delay++;
-        }
-        }
-        const uint32_t order = loc_order;
-
-        // ---- Chien search over all field elements in increasing order (decode.c:120-143); element 0 is never a
-        //      root (loc[0] == 1); root count must equal the locator order, else the block fails
-        uint32_t myroots = 0;   // bit k set: element lane*8+k is a root
-        for (int k = 0; k < 8; ++k) {
-            uint32_t e = (uint32_t)lane * 8u + (uint32_t)k;
-            if (e == 0) continue;
-            uint32_t le = s.log[e];
-            uint32_t acc = w.loc[order];
-            for (int i = (int)order - 1; i >= 0; --i) {
-                uint32_t t = acc ? (uint32_t)s.exp[(uint32_t)s.log[acc] + le] : 0u;
-                acc = t ^ w.loc[i];
-            }
-            if (acc == 0) myroots |= 1u << k;
-        }
-        uint32_t cnt = __popc(myroots);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total != order || order == 0) {   // order==0 cannot happen with nonzero syndromes; guarded for safety
-            if (order == 0 && total == 0) {
-                // libcorrect would "succeed" with no corrections; unreachable because S != 0 forces order >= 1
-            }
-            for (int i = lane; i < msg_len; i += 32) out[i] = 0;
-            if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 0;
-            continue;
-        }
-        {
-            uint32_t pos = incl - cnt;
-            for (int k = 0; k < 8; ++k) if (myroots & (1u << k)) w.roots[pos++] = (uint8_t)(lane * 8 + k);
-        }
-        // ---- error evaluator omega = S(x) * loc(x) mod x^md  (decode.c:146-161, polynomial.c:17-31)
-        for (int k = lane; k < md; k += 32) {
-            uint32_t acc = 0;
-            int lim = (int)order < k ? (int)order : k;
-            for (int i = 0; i <= lim; ++i) acc ^= gf_mul<T>(s, w.loc[i], w.synd[k - i]);
-            w.omega[k] = (uint8_t)acc;
-        }
-        __syncwarp();
-        // ---- Forney (decode.c:163-194) + apply (decode.c:369-372); one root per lane-slot
-        for (uint32_t q = lane; q < order; q += 32) {
-            uint32_t X = w.roots[q];
-            uint32_t lx = s.log[X];
-            // omega(X) and loc'(X) by Horner; loc'[i] = loc[i+1] for even i, 0 for odd i (polynomial.c:97-111)
-            uint32_t num = 0;
-            for (int i = md - 1; i >= 0; --i) {
-                uint32_t t = num ? (uint32_t)s.exp[(uint32_t)s.log[num] + lx] : 0u;
-                num = t ^ w.omega[i];
-            }
-            uint32_t den = 0;
-            for (int i = (int)order - 1; i >= 0; --i) {
-                uint32_t t = den ? (uint32_t)s.exp[(uint32_t)s.log[den] + lx] : 0u;
-                uint32_t c = ((i & 1) == 0) ? (uint32_t)w.loc[i + 1] : 0u;
-                den = t ^ c;
-            }
-            uint32_t err = gf_div<T>(s, num, den);          // X^(fcr-1) = 1 for fcr = 1
-            uint32_t inv = s.exp[510u - lx];             // field_div(1, X): log[1] = 255
-            uint32_t location = s.log[inv];              // coefficient index (255 when inv == 1: out of range in libcorrect)
-            if (location >= (uint32_t)md && location < (uint32_t)blk)
-                enc[blk - 1 - (int)location] ^= (uint8_t)err;
-        }
-        __syncwarp();
         for (int i = lane; i < msg_len; i += 32) out[i] = enc[i];
         if (lane == 0) block_ok[(size_t)f * m.nblocks + b] = 1;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- RS decode, whole frames per CTA
+// The hot configuration (4 symbol + 2 colour bits per cell, 155-byte blocks, parity <= 32, all blocks of every frame: mode B and
+// its siblings) does not let every warp chase the interleave map through L2 on its own.  A CTA of 32 warps takes TWO frames
+// at a time:
+//   1. their per-cell bytes (K1's output, 12,400 B each) arrive in shared memory by cp.async -- issued one step ahead, so
+//      the copy overlaps the previous step's corrections;
+//   2. all 1024 threads build the de-interleaved, bit-packed RS blocks (P7/P10) in shared memory, one 4-byte word of a staged
+//      block per thread and step: the interleave map is read coalesced (it is the same for every frame: L1/L2 hits), the
+//      cell bytes come from shared memory;
+//   3. one warp per unit of four consecutive blocks: remainder modulo x^pad g (as in k_rs_decode), the rare dirty block is
+//      corrected in place by the whole warp, and the unit's four messages -- contiguous in the output -- leave as 32-bit
+//      stores.
+constexpr int kFrWarps = 32;
+constexpr int kFrFrames = 2;
+constexpr int kFrBlk = 155, kFrWords = 39, kFrPitch = 160;   // block bytes; words per staged block (1 zero byte + 155); row pitch:
+                                                             // 40 words, so the four rows of a unit start 8 banks apart
+
+struct RsFrSmem {
+    uint8_t exp[512];
+    uint8_t log[256];
+    struct PerWarp {
+        alignas(4) uint8_t rem[64];
+        alignas(2) uint16_t remlog[kMaxParity];
+        uint8_t synd[kMaxParity];
+        uint8_t loc[kMaxParity + 8];
+        uint8_t last[kMaxParity + 8];
+        uint8_t omega[kMaxParity];
+        uint8_t roots[kMaxParity + 8];
+    } w[kFrWarps];
+    uint8_t la[kLaDim][kLaDim];
+    // followed in dynamic shared memory by: uint32 lt[4][256][8]; the cell bytes of kFrFrames frames (cell_pitch each);
+    // the staged blocks of kFrFrames frames (nblocks rows of kFrPitch bytes each)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_shared, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kFrWarps * 32, 2)
+k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* __restrict__ idx, int n_frames,
+            uint8_t* __restrict__ data_out, uint8_t* __restrict__ block_ok, const uint8_t* __restrict__ rho, int cell_pitch)
+{
+    constexpr int GL = 8, G = 4;
+    extern __shared__ __align__(16) uint8_t rs_smem_raw[];
+    RsFrSmem& s = *reinterpret_cast<RsFrSmem*>(rs_smem_raw);
+    uint8_t* dyn = rs_smem_raw + ((sizeof(RsFrSmem) + 127) & ~size_t(127));
+    uint32_t* lt = reinterpret_cast<uint32_t*>(dyn);
+    uint8_t* cellbuf = dyn + sizeof(uint32_t) * 4 * 256 * GL;
+    uint8_t* rows = cellbuf + (size_t)kFrFrames * cell_pitch;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int md = m.ecc_bytes, msg_len = m.msg_len, nb = m.nblocks, upf = nb / G;
+    const int Pw = (md + 3) >> 2, pad = 4 * Pw - md;
+    const int words_per_frame = nb * kFrWords, sym_rows = m.cap_sym / kFrBlk, cell_vecs = m.num_cells >> 4;
+    const int n_groups = (n_frames + kFrFrames - 1) / kFrFrames;
+    const uint32_t cellbuf_s = (uint32_t)__cvta_generic_to_shared(cellbuf);
+
+    auto load_cells = [&](int gi) {
+        for (int fs = 0; fs < kFrFrames; ++fs) {
+            const int f = gi * kFrFrames + fs;
+            if (f >= n_frames) break;
+            const uint8_t* src = cellvals + (size_t)f * m.num_cells;
+            for (int i = tid; i < cell_vecs; i += kFrWarps * 32) cp_async16(cellbuf_s + (uint32_t)(fs * cell_pitch + 16 * i), src + 16 * i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int gi = blockIdx.x;
+    if (gi < n_groups) load_cells(gi);
+
+    for (int i = tid; i < 512; i += blockDim.x) s.exp[i] = c_gf_exp[i];
+    for (int i = tid; i < 256; i += blockDim.x) s.log[i] = c_gf_log[i];
+    __syncthreads();
+    for (int e = tid; e < md * kLaDim; e += blockDim.x) {
+        const int kk = e / kLaDim, j = e % kLaDim;
+        s.la[kk][j] = (uint8_t)((255 - ((j + 1) * (md - kk)) % 255) % 255);
+    }
+    for (int e = tid; e < 4 * 256 * GL; e += blockDim.x) {
+        const int j = e / (256 * GL), v = (e / GL) & 255, kk = e % GL;
+        uint32_t word = 0;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) word |= gf_mul(s, (uint32_t)v, (uint32_t)rho[j * 64 + 4 * kk + bb]) << (8 * bb);
+        lt[e] = word;
+    }
+
+    RsFrSmem::PerWarp& w = s.w[warp];
+    const int grp = lane / GL, k = lane % GL;
+    const uint32_t lt_lane = (uint32_t)__cvta_generic_to_shared(lt) + 4u * (uint32_t)k;
+
+    for (; gi < n_groups; gi += gridDim.x) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();        // this group's cell bytes have landed (and the tables, first time); nobody still reads the rows of the previous group
+        const int nf = (n_frames - gi * kFrFrames) < kFrFrames ? (n_frames - gi * kFrFrames) : kFrFrames;
+
+        // ---- P7/P10: staged word q of block r = stream bytes 155 r + 4 q - 1 .. + 2 (byte -1 of a block is the zero in front)
+        for (int wi = tid; wi < nf * words_per_frame; wi += kFrWarps * 32) {
+            const int fs = wi >= words_per_frame ? 1 : 0;
+            const int rem = wi - fs * words_per_frame;
+            const int r = rem / kFrWords, q = rem - r * kFrWords;
+            const uint8_t* cb = cellbuf + fs * cell_pitch;
+            uint32_t b0, b1, b2, b3;
+            if (r < sym_rows) {         // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
+                const uint32_t* ix = reinterpret_cast<const uint32_t*>(idx) + (r * kFrBlk + 4 * q);
+                const uint32_t i0 = q ? ix[-1] : ix[0], i1 = ix[0], i2 = ix[1], i3 = ix[2];
+                b0 = ((cb[i0 & 0xFFFFu] & 15u) << 4) | (cb[i0 >> 16] & 15u);
+                b1 = ((cb[i1 & 0xFFFFu] & 15u) << 4) | (cb[i1 >> 16] & 15u);
+                b2 = ((cb[i2 & 0xFFFFu] & 15u) << 4) | (cb[i2 >> 16] & 15u);
+                b3 = ((cb[i3 & 0xFFFFu] & 15u) << 4) | (cb[i3 >> 16] & 15u);
+            } else {                    // four 2-bit colours per byte (Decoder.h:112-113)
+                const uint2* ix = reinterpret_cast<const uint2*>(idx) + ((r - sym_rows) * kFrBlk + 4 * q);
+                const uint2 i0 = q ? ix[-1] : ix[0], i1 = ix[0], i2 = ix[1], i3 = ix[2];
+                auto pack = [&](const uint2 ii) {
+                    return (((uint32_t)cb[ii.x & 0xFFFFu] >> 4) & 3u) << 6 | (((uint32_t)cb[ii.x >> 16] >> 4) & 3u) << 4 |
+                           (((uint32_t)cb[ii.y & 0xFFFFu] >> 4) & 3u) << 2 | (((uint32_t)cb[ii.y >> 16] >> 4) & 3u);
+                };
+                b0 = pack(i0); b1 = pack(i1); b2 = pack(i2); b3 = pack(i3);
+            }
+            if (q == 0) b0 = 0;
+            *reinterpret_cast<uint32_t*>(rows + (size_t)(fs * nb + r) * kFrPitch + 4 * q) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        __syncthreads();        // the rows are complete; the cell buffer is free again
+        if (gi + (int)gridDim.x < n_groups) load_cells(gi + (int)gridDim.x);
+
+        if (warp >= nf * upf) continue;
+        const int fs = warp >= upf ? 1 : 0, u = warp - fs * upf, f = gi * kFrFrames + fs;
+        uint8_t* urow = rows + (size_t)(fs * nb + G * u) * kFrPitch;
+
+        // ---- remainder modulo x^pad g, four bytes per step, the four blocks of the unit side by side (see k_rs_decode)
+        uint32_t word = 0;
+        {
+            const uint32_t stage_lane = (uint32_t)__cvta_generic_to_shared(urow) + (uint32_t)(grp * kFrPitch);
+            const int top_src = grp * GL + (Pw - 1);
+#pragma unroll 3
+            for (int t = 0; t < kFrWords; ++t) {
+                const uint32_t ew = lds_u32(stage_lane + 4u * (uint32_t)t);
+                const uint32_t tw = __shfl_sync(0xffffffffu, word, top_src);
+                const uint32_t v = tw ^ __byte_perm(ew, 0u, 0x0123);
+                const uint32_t r0 = lds_u32(lt_lane + (((v) & 0xFFu) + 0u) * (4u * GL));
+                const uint32_t r1 = lds_u32(lt_lane + (((v >> 8) & 0xFFu) + 256u) * (4u * GL));
+                const uint32_t r2 = lds_u32(lt_lane + (((v >> 16) & 0xFFu) + 512u) * (4u * GL));
+                const uint32_t r3 = lds_u32(lt_lane + ((v >> 24) + 768u) * (4u * GL));
+                uint32_t prev = __shfl_up_sync(0xffffffffu, word, 1, GL);
+                if (k == 0) prev = 0;
+                word = prev ^ r0 ^ r1 ^ r2 ^ r3;
+            }
+        }
+        const uint32_t dirty = __ballot_sync(0xffffffffu, k < Pw && word != 0u);
+        uint32_t okflags = 0x01010101u;
+        if (dirty) {
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+                if (((dirty >> (g * GL)) & ((1u << GL) - 1u)) == 0u) continue;
+                uint8_t* enc = urow + g * kFrPitch + 1;
+                __syncwarp();
+                const bool good = rs_correct_block<1>(s, w, enc, md, kFrBlk, pad, grp == g && k < Pw, word, k, lane);
+                __syncwarp();
+                if (!good) {        // zeros for a failed block (reed_solomon_stream.h:96-107)
+                    for (int i = lane; i < msg_len; i += 32) enc[i] = 0;
+                    okflags &= ~(1u << (8 * g));
+                }
+            }
+            __syncwarp();
+        }
+        // ---- the unit's four messages are contiguous in the output: 4 msg_len bytes, msg_len 32-bit words
+        uint32_t* out32 = reinterpret_cast<uint32_t*>(data_out + ((size_t)f * nb + (size_t)(G * u)) * msg_len);
+        for (int wq = lane; wq < msg_len; wq += 32) {
+            int B = 4 * wq;
+            int g = (B >= msg_len) + (B >= 2 * msg_len) + (B >= 3 * msg_len);
+            int i = B - g * msg_len;
+            uint32_t val = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                val |= (uint32_t)urow[g * kFrPitch + 1 + i] << (8 * j);
+                if (++i == msg_len) { i = 0; ++g; }
+            }
+            out32[wq] = val;
+        }
+        if (lane == 0) *reinterpret_cast<uint32_t*>(block_ok + (size_t)f * nb + (size_t)(G * u)) = okflags;
     }
 }
 
@@ -520,6 +719,23 @@ cudaError_t k2_rs_launch(const Mode& m, const uint8_t* d_raw, int n_frames, uint
 cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const uint16_t* d_idx, int n_frames, uint8_t* d_data,
                                uint8_t* d_ok, const uint8_t* d_rho, int sm_count, cudaStream_t st, int b_begin, int b_count)
 {
+    if (b_count < 0) b_count = m.nblocks;
+    static const bool frames_off = getenv("CB200_K2_FRAMES") && atoi(getenv("CB200_K2_FRAMES")) == 0;   // tuning / A-B only
+    const bool whole = b_begin == 0 && b_count == m.nblocks;
+    if (!frames_off && whole && !m.legacy && m.symbol_bits == 4 && m.color_bits == 2 && m.ecc_block == kFrBlk && m.ecc_bytes <= 32 &&
+        m.ecc_bytes <= kLaDim && m.nblocks % 4 == 0 && kFrFrames * (m.nblocks / 4) <= kFrWarps && m.num_cells % 16 == 0 &&
+        m.cap_sym % kFrBlk == 0 && (m.nblocks * m.msg_len) % 4 == 0 && ((uintptr_t)d_data & 3u) == 0 && n_frames > 0) {
+        const int cell_pitch = m.num_cells;
+        const size_t smem = ((sizeof(RsFrSmem) + 127) & ~size_t(127)) + sizeof(uint32_t) * 4 * 256 * 8 +
+                            (size_t)kFrFrames * cell_pitch + (size_t)kFrFrames * m.nblocks * kFrPitch;
+        if (smem <= 113 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_rs_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int groups = (n_frames + kFrFrames - 1) / kFrFrames, ctas = groups < 2 * sm_count ? groups : 2 * sm_count;
+            k_rs_frames<<<ctas, kFrWarps * 32, smem, st>>>(m, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, cell_pitch); count_launch();
+            return cudaGetLastError();
+        }
+    }
     if (m.ecc_bytes <= 32) return rs_launch_t<1, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, sm_count, st, b_begin, b_count);
     return rs_launch_t<2, true>(m, nullptr, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, sm_count, st, b_begin, b_count);
 }
