@@ -6,7 +6,8 @@ One step = one complete transfer of the file:
   * the file (seeded random bytes, compression_level 0 so that the check is byte equality) is cut into N = ceil(size / 619)
     wirehair blocks; ONE fountain stream (encode_id 0x55) of F frames x 12 chunks carries block ids 0 .. 12 F - 1 (block ids are
     16 bit: F <= 5461; 12 F >= N + a few is needed to complete);
-  * frame f belongs to rank f % world; every rank holds its frames in HBM (generated on the device: wirehair-encoded chunks ->
+  * rank r takes the contiguous stripe of frames [r B, (r + 1) B) (so that rank order is stream order at the sink -- wirehair is
+    several times faster when the original blocks arrive in order); every rank holds its frames in HBM (generated on the device: wirehair-encoded chunks ->
     RS(155,125) -> interleaved tiles -> RGB8 frames) and decodes them with cb200_decode_chunks_dev;
   * the chunk records reach rank 0 through the library's exchange (NVLink window / NCCL, csrc/gather.cu), are copied to the host
     and fed to the fountain sink (cb200_sink_ingest -> FountainMetadata parse, de-dup, wirehair_decode ... wirehair_recover);
@@ -85,8 +86,8 @@ def run(args):
     data, chunks = make_stream(info, size, F)
     t_gen = time.perf_counter() - t0
     want_sha = hashlib.sha256(data.tobytes()).hexdigest()
-    mine = list(range(rank, F, world))
-    B = len(mine)
+    B = F // world
+    mine = list(range(rank * B, (rank + 1) * B))               # contiguous stripes: rank order == stream order at the sink
     ctx = cb.Context(68, max_frames=B, device=local)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -164,11 +165,11 @@ def run(args):
             sink = cb.FountainSink(info.chunk_size)
             fid, fed = 0, 0
             hc, hm = h_chunks.numpy(), h_mask.numpy().astype(np.uint32)
-            # feed frame by frame in stream order (frame f = rank f % world, slot f // world), stop once the file is complete
-            step_frames = 64
-            for f0 in range(0, B, step_frames):
-                f1 = min(B, f0 + step_frames)
-                for r in range(world):
+            # feed in stream order (rank r holds frames [r B, (r + 1) B)), stop once the file is complete
+            step_frames = 256
+            for r in range(world):
+                for f0 in range(0, B, step_frames):
+                    f1 = min(B, f0 + step_frames)
                     got = sink.ingest(hc[r, f0:f1], hm[r, f0:f1])
                     fed += int(sum(bin(int(x)).count("1") for x in hm[r, f0:f1]))
                     if got > 0:
