@@ -34,4 +34,13 @@ for f in range(4):
     assert masks[f] == wmask and np.array_equal(chunks[f][:counts[f]], wchunks[:counts[f]])
 assert np.array_equal(ctx.get_ccm(), ora.get_ccm())
 ora.set_ccm(None)
+# deskew (csrc/deskew.cu): a mildly skewed "camera" of frame 0 back to the frame, then the decode on the device
+corners = np.array([[34, 28, 990, 33, 29, 996, 997, 991]], np.float32)
+out = ctx.extract_decode_fountain(frames[:1], corners)
+assert out[0].shape[0] == 1
+# five frames: an odd count for the frame-pair RS kernel
+ctx5 = cb.Context(68, max_frames=5)
+five = np.concatenate([frames[:3], frames[:2]])
+d5, ok5, _ = ctx5.decode(five)
+assert np.array_equal(d5[:3], payloads) and np.array_equal(d5[3:], payloads[:2]) and ok5.all()
 print("sanitize_small: ok")
