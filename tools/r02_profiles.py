@@ -1,0 +1,134 @@
+#!/usr/bin/env python3
+"""Regenerate the round-2 evidence under profiles/ from what the gpurun calls left in gpurun_out/ (run here, after a call).
+
+    tools/r02_profiles.py
+
+Copies the unprofiled bench lines (one JSON object per file), summarises the ncu reports of K1x (walk, raster) and K2 with
+tools/ncu_summary.py / tools/ncu_lines.py, and writes profiles/r02_results.md.  Every source is optional: what is missing is
+reported and skipped."""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GO = os.path.join(ROOT, "gpurun_out")
+PR = os.path.join(ROOT, "profiles")
+
+# profile name -> candidate sources in gpurun_out (first that exists wins)
+BENCH = {
+    "r02_bench_n1.json": ["r2h_bench_n1.json", "r2g_n1.json"],
+    "r02_bench_reference_arm.json": ["r2h_reference.json", "r2b_reference.json"],
+    "r02_bench_errors1pct.json": ["r2h_errors1pct.json", "r2g_k2new_errors1pct.json"],
+    "r02_bench_noise1pct_9472frames.json": ["r2i_noise.json", "r2g_noise.json"],
+    "r02_bench_noise1pct_3552frames.json": ["r2i_noise_3552.json", "r2d_noise_3552.json"],
+    "r02_bench_color_correction_1.json": ["r2h_cc1.json"],
+    "r02_bench_color_correction_2.json": ["r2h_cc2.json"],
+    "r02_bench_mode4.json": ["r2h_mode4.json", "r2d_mode4.json"],
+    "r02_bench_mode4_errors1pct.json": ["r2h_mode4_errors.json", "r2b_mode4_errors.json"],
+    "r02_bench_mode67.json": ["r2h_mode67.json"],
+    "r02_bench_fountain_n1.json": ["r2h_fountain_n1.json", "r2g_fountain_n1.json"],
+    "r02_bench_fountain_n2_window.json": ["r2j_fountain_n2.json", "r2g_fountain_n2.json"],
+    "r02_bench_fountain_n2_nccl.json": ["r2j_fountain_n2_nccl.json", "r2g_fountain_n2_nccl.json"],
+    "r02_bench_fountain_n8.json": ["r2k_fountain_n8.json"],
+    "r02_bench_n2_window.json": ["r2g_n2_window.json"],
+    "r02_bench_n2_nccl.json": ["r2g_n2_nccl.json"],
+    "r02_bench_n2_torch_gather.json": ["r2g_n2_torch.json"],
+    "r02_bench_n4_window.json": ["r2k_n4_window.json"],
+    "r02_bench_n8_window.json": ["r2k_n8_window.json"],
+    "r02_bench_n8_nccl.json": ["r2k_n8_nccl.json"],
+    "r02_bench_k2_per_warp_kernel_clean.json": ["r2g_k2old_clean.json"],
+    "r02_bench_k2_per_warp_kernel_errors1pct.json": ["r2g_k2old_errors1pct.json"],
+}
+
+
+def last_json(path):
+    for line in reversed(open(path).read().strip().split("\n")):
+        line = line.strip()
+        if line.startswith("{"):
+            return json.loads(line)
+    raise ValueError("no JSON line in " + path)
+
+
+def copy_bench():
+    got = {}
+    for name, cands in BENCH.items():
+        for c in cands:
+            p = os.path.join(GO, c)
+            if os.path.exists(p):
+                try:
+                    j = last_json(p)
+                except Exception as e:
+                    print("skip %s: %s" % (c, e))
+                    continue
+                json.dump(j, open(os.path.join(PR, name), "w"))
+                open(os.path.join(PR, name), "a").write("\n")
+                got[name] = (c, j)
+                break
+        else:
+            print("missing: %s (%s)" % (name, ", ".join(cands)))
+    return got
+
+
+def ncu_summary(rep, frames):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, str(frames)], capture_output=True, text=True).stdout
+    return out.partition("TRAFFIC_JSON")[0].strip()
+
+
+def ncu_lines(rep, pat, src, n):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, pat, os.path.join(ROOT, src), str(n)],
+                          capture_output=True, text=True).stdout.strip()
+
+
+def km(j):
+    return j.get("kernel_ms_per_step", {})
+
+
+def row(label, j, extra=""):
+    k = km(j)
+    e2e = (j.get("e2e") or {}).get("value")
+    return "| %s | %s | %.3f | %s | %s | %s | %s | %s |" % (
+        label, "{:,.0f}".format(j["value"]), j["ms_per_step"],
+        "%.3f" % k["k1_decode"] if "k1_decode" in k else "", "%.3f" % k["k1x_flood_check"] if "k1x_flood_check" in k else "",
+        "%.3f" % k["rs"] if "rs" in k else "", "{:,.0f}".format(e2e) if e2e else "", extra)
+
+
+def main():
+    os.makedirs(PR, exist_ok=True)
+    got = copy_bench()
+    md = ["# Round 2 -- measured results (B200, unprofiled `bench.py` lines; the JSON files next to this one are the lines themselves)", ""]
+    md += ["| run | frames/s (device-resident) | ms/step | K1 ms | K1x ms | RS ms | e2e frames/s (host buffers) | note |", "|---|---|---|---|---|---|---|---|"]
+    order = [("r02_bench_n1.json", "configs[1] clean, mode B, 10 000 frames/step"), ("r02_bench_errors1pct.json", "configs[2] 1 % wrong tiles"),
+             ("r02_bench_color_correction_1.json", "colour correction 1"), ("r02_bench_color_correction_2.json", "colour correction 2 (reference default)"),
+             ("r02_bench_mode4.json", "configs[4] mode 4C (legacy, RS(155,115)... see file)"), ("r02_bench_mode4_errors1pct.json", "mode 4C, 1 % wrong tiles"),
+             ("r02_bench_mode67.json", "mode Bm (67)"),
+             ("r02_bench_noise1pct_9472frames.json", "1 % noise tiles: every frame through the exact walk, 9 472 frames"),
+             ("r02_bench_noise1pct_3552frames.json", "same, 3 552 frames"),
+             ("r02_bench_k2_per_warp_kernel_clean.json", "A/B: CB200_K2_FRAMES=0 (round-1-style per-warp RS kernel), clean"),
+             ("r02_bench_k2_per_warp_kernel_errors1pct.json", "A/B: CB200_K2_FRAMES=0, 1 % wrong tiles"),
+             ("r02_bench_n2_window.json", "N = 2, records through the NVLink window"), ("r02_bench_n2_nccl.json", "N = 2, cb200_gather_chunks (NCCL)"),
+             ("r02_bench_n2_torch_gather.json", "N = 2, torch.distributed.gather (round-1 path)"),
+             ("r02_bench_n4_window.json", "N = 4, window"), ("r02_bench_n8_window.json", "N = 8, window"), ("r02_bench_n8_nccl.json", "N = 8, NCCL")]
+    for name, label in order:
+        if name in got:
+            src, j = got[name]
+            md.append(row(label, j, "`%s`" % name))
+    ref = got.get("r02_bench_reference_arm.json")
+    if ref:
+        j = ref[1]
+        cb = j.get("cpu_baseline", {})
+        md += ["", "Reference arm (`bench.py --impl reference`, `%s`): **%s frames/s** on %s threads (%s); stages per frame on one thread: %s" % (
+            "r02_bench_reference_arm.json", "{:,.0f}".format(j["value"]), cb.get("cores"), cb.get("build", ""), json.dumps(cb.get("stages", {})))]
+    for name in ("r02_bench_fountain_n1.json", "r02_bench_fountain_n2_window.json", "r02_bench_fountain_n2_nccl.json", "r02_bench_fountain_n8.json"):
+        if name in got:
+            j = got[name][1]
+            md += ["", "Fountain (configs[3], `%s`): %s; device %.2f ms per transfer (%s frames/s), sink %s chunks/s, end to end %.0f MB/s of file. %s" % (
+                name, j.get("parity"), j["ms_per_step"], "{:,.0f}".format(j["value"]), "{:,.0f}".format(j["rank0_sink"]["chunks_per_s"]),
+                j["end_to_end"]["file_MB_per_s"], j.get("saturation", ""))]
+    open(os.path.join(PR, "r02_results.md"), "w").write("\n".join(md) + "\n")
+    print("wrote profiles/r02_results.md with %d bench lines" % len(got))
+
+
+if __name__ == "__main__":
+    main()
