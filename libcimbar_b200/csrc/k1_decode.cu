@@ -311,13 +311,14 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         uint32_t sym = 0, dirty = 0;
         bool exact = true;
         if (active) {
-            uint32_t lo = 0, hi = 0;
+            uint32_t fr[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t idx = o >> 5, sh = o & 31u;
-                lo |= (__funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh) & 0xFFu) << (8 * q);
-                hi |= (__funnelshift_r(rast[5 + q][idx], rast[5 + q][idx + 1], sh) & 0xFFu) << (8 * q);
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t idx = o >> 5, sh = o & 31u;
+                fr[q] = __funnelshift_r(rast[1 + q][idx], rast[1 + q][idx + 1], sh);      // byte 0 = hash row q
             }
+            const uint32_t lo = __byte_perm(__byte_perm(fr[0], fr[1], 0x0040), __byte_perm(fr[2], fr[3], 0x0040), 0x5410);
+            const uint32_t hi = __byte_perm(__byte_perm(fr[4], fr[5], 0x0040), __byte_perm(fr[6], fr[7], 0x0040), 0x5410);
             uint4 te = s.tiles_by_slot[(lo * mm.hash_mul) >> 28];
             exact = (te.x == lo) & (te.y == hi);
             sym = te.z;
@@ -466,9 +467,14 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                         uint32_t Pc = (r < 2) ? Pprev[r][j] : P[r - 2][j];
                         tj[j] = 25u * Pc + nV[j];             // bit15 / bit31 = (25 g > boxsum + 12)
                     }
-                    uint32_t byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
-                                    ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
-                    byte = (byte | (byte >> 12)) & 0xFFu;
+                    // the eight decisions are bit 7 of bytes 1 and 3 of tj[0..3]: px 0,4 | 1,5 | 2,6 | 3,7.  Two byte permutes put
+                    // them into two words (px 0,4,1,5 and px 2,6,3,7 at bits 7,15,23,31); the high half of a 32x32 product with a
+                    // constant that has one bit per source (bit 32 + k - s for source bit s -> result bit k) moves all four to
+                    // their places at once -- every partial product lands on its own bit, so nothing carries, and the strays
+                    // fall outside bits 32..39.  Only the low byte of the sum is stored.
+                    const uint32_t dx = __byte_perm(tj[0], tj[1], 0x7531) & 0x80808080u;
+                    const uint32_t dy = __byte_perm(tj[2], tj[3], 0x7531) & 0x80808080u;
+                    const uint32_t byte = __umulhi(dx, 0x02200440u) + __umulhi(dy, 0x08801100u);
                     if (px_active) rast8[(r + 1) * kRastPitch + t] = (uint8_t)byte;
                 }
 #pragma unroll

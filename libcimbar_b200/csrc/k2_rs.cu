@@ -549,8 +549,11 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
         const int kk = e / kLaDim, j = e % kLaDim;
         s.la[kk][j] = (uint8_t)((255 - ((j + 1) * (md - kk)) % 255) % 255);
     }
+    // the four remainder tables interleaved: row (v, j) = T_j[v] (32 bytes) at word (4 v + j) 8, i.e. table j only ever occupies
+    // banks 8 j .. 8 j + 7.  In one lookup instruction lane group g reads table i ^ g (the four rows are XORed together, so the
+    // order does not matter): four different bank octets, no conflict whatever the four byte values are.
     for (int e = tid; e < 4 * 256 * GL; e += blockDim.x) {
-        const int j = e / (256 * GL), v = (e / GL) & 255, kk = e % GL;
+        const int v = e / (4 * GL), j = (e / GL) & 3, kk = e % GL;
         uint32_t word = 0;
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) word |= gf_mul(s, (uint32_t)v, (uint32_t)rho[j * 64 + 4 * kk + bb]) << (8 * bb);
@@ -560,6 +563,10 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
     RsFrSmem::PerWarp& w = s.w[warp];
     const int grp = lane / GL, k = lane % GL;
     const uint32_t lt_lane = (uint32_t)__cvta_generic_to_shared(lt) + 4u * (uint32_t)k;
+    // byte i of __byte_perm(v, 0, vsel) = byte i ^ grp of v; lookup i of this lane goes to table i ^ grp
+    const uint32_t vsel = 0x3210u ^ (0x1111u * (uint32_t)grp);
+    const uint32_t lt0 = lt_lane + 32u * (uint32_t)(0 ^ grp), lt1 = lt_lane + 32u * (uint32_t)(1 ^ grp);
+    const uint32_t lt2 = lt_lane + 32u * (uint32_t)(2 ^ grp), lt3 = lt_lane + 32u * (uint32_t)(3 ^ grp);
 
     for (; gi < n_groups; gi += gridDim.x) {
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -608,11 +615,11 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
             for (int t = 0; t < kFrWords; ++t) {
                 const uint32_t ew = lds_u32(stage_lane + 4u * (uint32_t)t);
                 const uint32_t tw = __shfl_sync(0xffffffffu, word, top_src);
-                const uint32_t v = tw ^ __byte_perm(ew, 0u, 0x0123);
-                const uint32_t r0 = lds_u32(lt_lane + (((v) & 0xFFu) + 0u) * (4u * GL));
-                const uint32_t r1 = lds_u32(lt_lane + (((v >> 8) & 0xFFu) + 256u) * (4u * GL));
-                const uint32_t r2 = lds_u32(lt_lane + (((v >> 16) & 0xFFu) + 512u) * (4u * GL));
-                const uint32_t r3 = lds_u32(lt_lane + ((v >> 24) + 768u) * (4u * GL));
+                const uint32_t v = __byte_perm(tw ^ __byte_perm(ew, 0u, 0x0123), 0u, vsel);
+                const uint32_t r0 = lds_u32(lt0 + ((v) & 0xFFu) * 128u);
+                const uint32_t r1 = lds_u32(lt1 + ((v >> 8) & 0xFFu) * 128u);
+                const uint32_t r2 = lds_u32(lt2 + ((v >> 16) & 0xFFu) * 128u);
+                const uint32_t r3 = lds_u32(lt3 + (v >> 24) * 128u);
                 uint32_t prev = __shfl_up_sync(0xffffffffu, word, 1, GL);
                 if (k == 0) prev = 0;
                 word = prev ^ r0 ^ r1 ^ r2 ^ r3;
@@ -637,15 +644,23 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
         }
         // ---- the unit's four messages are contiguous in the output: 4 msg_len bytes, msg_len 32-bit words
         uint32_t* out32 = reinterpret_cast<uint32_t*>(data_out + ((size_t)f * nb + (size_t)(G * u)) * msg_len);
+        const uint32_t urow_s = (uint32_t)__cvta_generic_to_shared(urow);
         for (int wq = lane; wq < msg_len; wq += 32) {
-            int B = 4 * wq;
+            const int B = 4 * wq;
             int g = (B >= msg_len) + (B >= 2 * msg_len) + (B >= 3 * msg_len);
             int i = B - g * msg_len;
-            uint32_t val = 0;
+            uint32_t val;
+            if (i + 4 <= msg_len) {                           // the four bytes lie in one block: two aligned words, one funnel shift
+                const uint32_t a = (uint32_t)(g * kFrPitch + 1 + i);
+                const uint32_t w0 = lds_u32(urow_s + (a & ~3u)), w1 = lds_u32(urow_s + (a & ~3u) + 4u);   // (w1 stays inside the row: a + 3 <= 125)
+                val = __funnelshift_r(w0, w1, 8u * (a & 3u));
+            } else {                                          // the three words of a unit that straddle two blocks
+                val = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                val |= (uint32_t)urow[g * kFrPitch + 1 + i] << (8 * j);
-                if (++i == msg_len) { i = 0; ++g; }
+                for (int j = 0; j < 4; ++j) {
+                    val |= (uint32_t)urow[g * kFrPitch + 1 + i] << (8 * j);
+                    if (++i == msg_len) { i = 0; ++g; }
+                }
             }
             out32[wq] = val;
         }

@@ -35,7 +35,10 @@ for f in range(4):
 assert np.array_equal(ctx.get_ccm(), ora.get_ccm())
 ora.set_ccm(None)
 # deskew (csrc/deskew.cu): a mildly skewed "camera" of frame 0 back to the frame, then the decode on the device
-corners = np.array([[34, 28, 990, 33, 29, 996, 997, 991]], np.float32)
+# (SANITIZE_CAMERA=0: the anchor centres where Deskewer puts them = an identity warp, so that the frame stays clean and the run
+#  never enters the exact flood walk -- racecheck of everything but K1x)
+corners = (np.array([[34, 28, 990, 33, 29, 996, 997, 991]], np.float32) if os.environ.get("SANITIZE_CAMERA", "1") == "1"
+           else np.array([[30, 30, 994, 30, 30, 994, 994, 994]], np.float32))
 out = ctx.extract_decode_fountain(frames[:1], corners)
 assert out[0].shape[0] == 1
 # five frames: an odd count for the frame-pair RS kernel
