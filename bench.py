@@ -381,6 +381,8 @@ def run_ours(args):
                "h2d_bytes_per_step": ne * info.frame_bytes,
                "d2h_bytes_per_step": ne * (info.data_bytes + 4 + 1),
                "frames_per_step": ne, "steps": esteps, "api": "cb200_decode_fountain (host pointers, pinned input)",
+               "h2d_gbytes_per_s_per_gpu": ne * info.frame_bytes * esteps / dt / 1e9,
+               "bound": "the host-to-device copy of the frames (3.1 MB each) over PCIe; the decode of a step takes ~1 % of the step",
                "numa": numa,
                "parity": "ok" if e2e_ok else "MISMATCH"}
 

@@ -128,6 +128,53 @@ def main():
                 j["end_to_end"]["file_MB_per_s"], j.get("saturation", ""))]
     open(os.path.join(PR, "r02_results.md"), "w").write("\n".join(md) + "\n")
     print("wrote profiles/r02_results.md with %d bench lines" % len(got))
+    ncu_docs()
+
+
+def first(*names):
+    for n in names:
+        p = os.path.join(GO, n)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def ncu_docs():
+    """K1 / K2 / K1x summaries of the `ncu --set full` captures (numbers under ncu are never bench values)"""
+    k1 = first("r2l_k1.ncu-rep", "r2i_k1.ncu-rep")
+    k2 = first("r2l_k2.ncu-rep", "r2i_k2.ncu-rep", "r2h_k2.ncu-rep")
+    k2e = first("r2l_k2_err.ncu-rep", "r2h_k2_err.ncu-rep")
+    walk = first("r2l_walk.ncu-rep", "r2d_walk.ncu-rep")
+    rast = first("r2l_raster.ncu-rep", "r2a_raster.ncu-rep")
+    out = ["# Round 2 -- ncu evidence (B200, `ncu --set full --clock-control none --import-source on`, one launch each;",
+           "summaries by `tools/ncu_summary.py` / `tools/ncu_lines.py`; the unprofiled numbers are in `r02_results.md`)", ""]
+    if k1:
+        body = ncu_summary(k1, 4144)
+        out += ["## K1 `k1_decode_kernel<4,true,0>` (4 144 frames in the launch) -- `%s`" % os.path.basename(k1), body, "", "```",
+                ncu_lines(k1, "k1_decode:k1_decode_kernelILi4ELb1E", "libcimbar_b200/csrc/k1_decode.cu", 14), "```", ""]
+        tj = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), k1, "4144"], capture_output=True, text=True).stdout.partition("TRAFFIC_JSON")[2].strip()
+        if tj:
+            t = json.loads(tj)
+            t["source"] = ("profiles/r02_ncu_summary.md (ncu --set full --clock-control none, k1_decode_kernel<4,true,0>, 4144 frames in the "
+                           "launch: dram__bytes_read.sum + dram__bytes_write.sum)")
+            json.dump(t, open(os.path.join(PR, "k1_traffic.json"), "w"), indent=1)
+    if k2:
+        out += ["## K2 `k_rs_frames`, clean frames (4 144 in the launch) -- `%s`" % os.path.basename(k2), ncu_summary(k2, 4144), "", "```",
+                ncu_lines(k2, "k_rs_frames", "libcimbar_b200/csrc/k2_rs.cu", 16), "```", ""]
+    if k2e:
+        out += ["## K2 `k_rs_frames`, 1 % wrong tiles (every block is corrected) -- `%s`" % os.path.basename(k2e), ncu_summary(k2e, 4144), "", "```",
+                ncu_lines(k2e, "k_rs_frames", "libcimbar_b200/csrc/k2_rs.cu", 16), "```", ""]
+    open(os.path.join(PR, "r02_ncu_summary.md"), "w").write("\n".join(out) + "\n")
+    w = []
+    if walk:
+        w += ["## `k_flood_walk` (4 736 frames = one wave of 32 walks per SM) -- `%s`" % os.path.basename(walk), ncu_summary(walk, 4736), "", "```",
+              ncu_lines(walk, "k_flood_walk", "libcimbar_b200/csrc/k1x_flood.cu", 24), "```", ""]
+    if rast:
+        w += ["## `k_flood_raster_fast` -- `%s`" % os.path.basename(rast), ncu_summary(rast, 1776), ""]
+    head_p = os.path.join(PR, "r02_k1x_walk_head.md")
+    head = open(head_p).read() if os.path.exists(head_p) else "# Round 2 -- K1x (exact flood walk)\n"
+    open(os.path.join(PR, "r02_k1x_walk.md"), "w").write(head + "\n" + "\n".join(w) + "\n")
+    print("wrote profiles/r02_ncu_summary.md, profiles/r02_k1x_walk.md")
 
 
 if __name__ == "__main__":
