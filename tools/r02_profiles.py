@@ -162,7 +162,7 @@ def ncu_docs():
         out += ["## K2 `k_rs_frames`, clean frames (4 144 in the launch) -- `%s`" % os.path.basename(k2), ncu_summary(k2, 4144), "", "```",
                 ncu_lines(k2, "k_rs_frames", "libcimbar_b200/csrc/k2_rs.cu", 16), "```", ""]
     if k2e:
-        out += ["## K2 `k_rs_frames`, 1 % wrong tiles (every block is corrected) -- `%s`" % os.path.basename(k2e), ncu_summary(k2e, 4144), "", "```",
+        out += ["## K2 `k_rs_frames`, 1 %% wrong tiles (every block is corrected) -- `%s`" % os.path.basename(k2e), ncu_summary(k2e, 4144), "", "```",
                 ncu_lines(k2e, "k_rs_frames", "libcimbar_b200/csrc/k2_rs.cu", 16), "```", ""]
     open(os.path.join(PR, "r02_ncu_summary.md"), "w").write("\n".join(out) + "\n")
     w = []
