@@ -208,7 +208,7 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 // CM = 0: integer classifier; 1: CCM classifier; 2: no decision, the cell's mean colour is stored for the fitted-CCM pass
 template <int NC, bool G1024, int CM>
 __global__ void __launch_bounds__(kK1Threads, 4)
-k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead,
+k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead_arg,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags, const CcmArg cc)
 {
     // G1024: the 1024x1024 / 112x112-cell geometry of modes B, 4C and 8C as compile-time constants (GridConf.h:121-141);
@@ -289,12 +289,23 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         tma_bulk_g2s(s.ring + p * unit_bytes, c.src, first * unit_bytes, bar);
         if (first < 3u) tma_bulk_g2s(s.ring, c.src + (size_t)first * unit_bytes, (3u - first) * unit_bytes, bar);
     };
+    // two cursors over that stream, each owned by one thread: thread 0 feeds the shared-memory ring (TMA), the first thread of
+    // warp 1 runs l2_ahead stages further ahead and only prefetches into L2 -- the per-stage cursor arithmetic is spread over
+    // two warps, so no warp arrives at the stage barrier much later than the others.
+    // (l2_ahead carries two tuning bits: 0x1000 = copy only, no decode: the ceiling of the load pipeline; 0x2000 = both cursors
+    //  in thread 0, as in round 1)
+    const bool load_only = (l2_ahead_arg & 0x1000) != 0;
+    const int l2_ahead = l2_ahead_arg & 0xFFF;
+    const int pf_tid = (l2_ahead_arg & 0x2000) ? 0 : 32;
     Cursor nxt, pre;                              // next stage to load into shared memory / to prefetch into L2
-    nxt.u = blockIdx.x; nxt.valid = false; pre.valid = false;
+    nxt.u = blockIdx.x; nxt.valid = false; pre.u = blockIdx.x; pre.valid = false;
     if (tid == 0) {
         cursor_unit(nxt);
-        pre = nxt;
-        if (nxt.valid) { issue_stage(nxt, 0u, 0u); cursor_next(nxt); cursor_next(pre); }
+        if (nxt.valid) { issue_stage(nxt, 0u, 0u); cursor_next(nxt); }
+    }
+    if (tid == pf_tid && l2_ahead > 0) {
+        cursor_unit(pre);
+        if (pre.valid) cursor_next(pre);
         for (int i = 0; i < l2_ahead && pre.valid; ++i) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
     }
 
@@ -372,6 +383,14 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
             const uint32_t p2 = (p1 + 1u == kRingUnits) ? 0u : p1 + 1u;
             uint8_t* ub[3] = {s.ring + p0 * unit_bytes, s.ring + p1 * unit_bytes, s.ring + p2 * unit_bytes};
             mbar_wait(&s.full_bar[buf], ph);
+            if (load_only) {                               // tuning only: the stage is dropped as soon as it has landed
+                __syncthreads();
+                const uint32_t p3 = p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u;
+                if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u, p3); cursor_next(nxt); }
+                if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
+                ring_pos = p3;
+                continue;
+            }
 
             // ---------------- A(k): gray, packed pairs P[r][j] = (g[j], g[j+4]); halo word E_r = (g0,g1,g6,g7)
             uint32_t P[kStageRows][4];
@@ -433,11 +452,9 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                // dead now: stage it-1's units 1,2 (their parked halo words were last read in B(k-1)) and this stage's unit 0
-                if (nxt.valid) { issue_stage(nxt, it + 1u, p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u); cursor_next(nxt); }
-                if (l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
-            }
+            // dead now: stage it-1's units 1,2 (their parked halo words were last read in B(k-1)) and this stage's unit 0
+            if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u, p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u); cursor_next(nxt); }
+            if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
 
             // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
             {
@@ -492,6 +509,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         }
         // the last cell row of the unit still needs its symbols: one more barrier to see its complete raster
         __syncthreads();
+        if (load_only) continue;
         symbol_stage(k1 - 1, (it - 1u) & 1u, col_prev, out, any_dirty);
         if (any_dirty) atomicOr(&dirty_flags[f], (uint32_t)kFrameDirtyK1);
     }

@@ -157,17 +157,17 @@ __device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc,
         //      the update rule and the order bookkeeping, because they decide the locator it reports for uncorrectable blocks.
         uint32_t numerrors = 0, loc_order = 0, last_order = 0, last_disc = 1, delay = 1;
         if (T == 1) {
-            // parity <= 31: coefficient j of the locator / previous locator lives in lane j, syndrome j in lane j
-            uint32_t loc = (lane == 0), last = (lane == 0);
+            // parity <= 32: coefficient j of the locator / previous locator lives in lane j, syndrome j in lane j (value and log
+            // packed in one word so that one shuffle moves both); lloc = log(loc) is refreshed only when loc changes
+            uint32_t loc = (lane == 0), last = (lane == 0), lloc = 0;
             const uint32_t syn = (lane < md) ? (uint32_t)w.synd[lane] : 0u;
-            const uint32_t lsyn = s.log[syn];
+            const uint32_t spk = syn | ((uint32_t)s.log[syn] << 8);
             for (uint32_t i = 0; i < (uint32_t)md; ++i) {
-                // disc = S[i] ^ sum_{j=1..numerrors} loc[j] * S[i-j]
-                const uint32_t sj = __shfl_sync(0xffffffffu, syn, (int)(i - (uint32_t)lane) & 31);
-                const uint32_t lsj = __shfl_sync(0xffffffffu, lsyn, (int)(i - (uint32_t)lane) & 31);
+                // disc = S[i] ^ sum_{j=1..numerrors} loc[j] * S[i-j]; lane 0 contributes loc[0] * S[i] = S[i] (loc[0] stays 1)
+                const uint32_t p = __shfl_sync(0xffffffffu, spk, (int)(i - (uint32_t)lane) & 31);
                 uint32_t term = 0;
-                if ((uint32_t)lane >= 1u && (uint32_t)lane <= numerrors && loc != 0 && sj != 0) term = s.exp[(uint32_t)s.log[loc] + lsj];
-                const uint32_t disc = __reduce_xor_sync(0xffffffffu, term) ^ __shfl_sync(0xffffffffu, syn, (int)i);
+                if ((uint32_t)lane <= numerrors && loc != 0 && (p & 0xFFu) != 0) term = s.exp[lloc + (p >> 8)];
+                const uint32_t disc = __reduce_xor_sync(0xffffffffu, term);
                 if (disc == 0) { delay++; continue; }
                 const uint32_t lscale = 255u + (uint32_t)s.log[disc] - (uint32_t)s.log[last_disc];      // log(disc / last_disc), last_disc != 0
                 const uint32_t top = last_order + delay;
@@ -177,6 +177,7 @@ __device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc,
                 if (2 * numerrors <= i) {
                     // last <- x^delay * scale * last ; then loc, last <- loc - last, loc   over [0, last_order+delay]
                     if ((uint32_t)lane <= top) { const uint32_t t0 = loc; loc ^= sh; last = t0; }
+                    lloc = s.log[loc];
                     const uint32_t tmp = loc_order;
                     loc_order = top; last_order = tmp;
                     numerrors = i + 1 - numerrors;
@@ -186,6 +187,7 @@ __device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc,
                 }
                 // no length change: loc[j+delay] ^= scale * last[j]
                 loc ^= sh;
+                lloc = s.log[loc];
                 if (top > loc_order) loc_order = top;
                 delay++;
             }
@@ -271,26 +273,26 @@ __device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc,
             w.omega[k] = (uint8_t)acc;
         }
         __syncwarp();
-        // ---- Forney (decode.c:163-194) + apply (decode.c:369-372); one root per lane-slot
-        for (uint32_t q = lane; q < order; q += 32) {
-            uint32_t X = w.roots[q];
-            uint32_t lx = s.log[X];
-            // omega(X) and loc'(X) by Horner; loc'[i] = loc[i+1] for even i, 0 for odd i (polynomial.c:97-111)
-            uint32_t num = 0;
-            for (int i = md - 1; i >= 0; --i) {
-                uint32_t t = num ? (uint32_t)s.exp[(uint32_t)s.log[num] + lx] : 0u;
-                num = t ^ w.omega[i];
+        // ---- Forney (decode.c:163-194) + apply (decode.c:369-372).  libcorrect evaluates omega(X) and loc'(X) by Horner, one root
+        //      after the other; field arithmetic is exact, so the same elements come out of the plain sums
+        //      omega(X) = sum_i omega[i] X^i and loc'(X) = sum_{i even, i < order} loc[i+1] X^i (polynomial.c:97-111: the formal
+        //      derivative keeps the odd coefficients) -- one term per lane, one XOR reduction per root
+        for (uint32_t q = 0; q < order; ++q) {
+            const uint32_t X = w.roots[q];
+            const uint32_t lx = s.log[X];
+            uint32_t tn = 0, td = 0;
+#pragma unroll
+            for (int qq = 0; qq < T; ++qq) {
+                const uint32_t i = (uint32_t)lane + 32u * (uint32_t)qq;
+                const uint32_t ex = (i * lx) % 255u;                     // log(X^i)
+                if (i < (uint32_t)md) { const uint32_t o = w.omega[i]; if (o) tn ^= s.exp[(uint32_t)s.log[o] + ex]; }
+                if (i < order && (i & 1u) == 0u) { const uint32_t c = w.loc[i + 1]; if (c) td ^= s.exp[(uint32_t)s.log[c] + ex]; }
             }
-            uint32_t den = 0;
-            for (int i = (int)order - 1; i >= 0; --i) {
-                uint32_t t = den ? (uint32_t)s.exp[(uint32_t)s.log[den] + lx] : 0u;
-                uint32_t c = ((i & 1) == 0) ? (uint32_t)w.loc[i + 1] : 0u;
-                den = t ^ c;
-            }
-            uint32_t err = gf_div(s, num, den);          // X^(fcr-1) = 1 for fcr = 1
-            uint32_t inv = s.exp[510u - lx];             // field_div(1, X): log[1] = 255
-            uint32_t location = s.log[inv];              // coefficient index (255 when inv == 1: out of range in libcorrect)
-            if (location >= (uint32_t)md && location < (uint32_t)blk)
+            const uint32_t num = __reduce_xor_sync(0xffffffffu, tn), den = __reduce_xor_sync(0xffffffffu, td);
+            const uint32_t err = gf_div(s, num, den);      // X^(fcr-1) = 1 for fcr = 1
+            const uint32_t inv = s.exp[510u - lx];       // field_div(1, X): log[1] = 255
+            const uint32_t location = s.log[inv];        // coefficient index (255 when inv == 1: out of range in libcorrect)
+            if (lane == 0 && location >= (uint32_t)md && location < (uint32_t)blk)
                 enc[blk - 1 - (int)location] ^= (uint8_t)err;
         }
         __syncwarp();
