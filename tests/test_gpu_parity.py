@@ -734,3 +734,23 @@ def test_exact_walk_work_list_in_several_chunks(cb, monkeypatch):
     raw2, ff2 = ctx.decode_raw(batch[::-1].copy())                                  # a second call reuses the workspace
     for f in range(len(batch)):
         assert np.array_equal(raw2[f], raw[len(batch) - 1 - f]), f
+
+
+@pytest.mark.gpu
+def test_exact_walk_with_the_literal_pop_forced(cb, monkeypatch):
+    # K1x pops through a lane-parallel sift-down (three five-level rounds); heaps beyond 65 535 entries fall back to the literal
+    # one-level-per-step __adjust_heap.  No real frame gets there, so the fallback is forced here and must give the same walk:
+    # cell trace of a camera frame against the oracle's, and a noisy synthetic frame's raw bytes
+    monkeypatch.setenv("CB200_K1X_SERIAL_ABOVE", "0")
+    ctx = cb.Context(68, max_frames=2)
+    monkeypatch.delenv("CB200_K1X_SERIAL_ABOVE")
+    cam = load_sample("b/ex2434.jpg")
+    m = ORA.mode(68)
+    want_raw, want_cells = ORA.decode_raw(m, cam, want_cells=True)
+    raw, ff = ctx.decode_raw(cam[None])
+    assert (ff[0] & cb.FRAME_FALLBACK) and np.array_equal(raw[0], want_raw)
+    _, _, noisy = synth_frames(68, 2, seed=77, error_rate=0.01, noise_tiles=True)
+    raw2, ff2 = ctx.decode_raw(noisy)
+    assert all(int(x) & cb.FRAME_FALLBACK for x in ff2)
+    for f in range(2):
+        assert np.array_equal(raw2[f], ORA.decode_raw(m, noisy[f]))
