@@ -11,8 +11,8 @@
 // centre hash wins for every cell.  A cell where it does not sets bit 7 of its result
 // byte and the frame's dirty flag; such frames are re-done by the exact flood-walk kernel (k1x_flood.cu).
 //
-// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 4 CTAs/SM):
-//   HBM --cp.async.bulk (TMA, 3 full-width rows = 9 KB per copy, ring of 15 rows, one mbarrier per 9-row stage)--> smem
+// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 5 CTAs/SM):
+//   HBM --cp.async.bulk (TMA, one copy of 9 full-width rows = 27 KB per stage, one mbarrier per stage)--> smem
 //   phase A: 8 px/thread: gray = (19596R+38470G+7470B+32768)>>16 via 2x IDP.2A per px, packed 2x16 bit
 //   phase B: separable 5x5 box sum in packed-16 SIMD (5 IADD3 + 4 PRMT per 8 px), rolling vertical sum in
 //            registers, threshold 25*g > sum+12 as ONE IMAD per pixel pair, 1-bit raster row -> smem
@@ -29,14 +29,13 @@ namespace cb200 {
 
 constexpr int kK1Threads = 128;            // 128 threads x 8 px = one full 1024-px row
 constexpr int kStageRows = 9;              // raw rows per cell row (stage)
-constexpr int kUnitRows = 3;               // TMA granularity: one ring unit = 3 raw rows
-constexpr int kRingUnits = 5;              // 15 rows of ring: a stage occupies 3 consecutive units (mod 5)
 constexpr int kMaxW = 1024;
 constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
 constexpr int kRastWords = kRastPitch / 4;
 
 struct __align__(128) K1Smem {
-    uint8_t ring[kRingUnits * kUnitRows * kMaxW * 3];  // raw RGB rows, filled by TMA; unit p starts at p * (3 * row_bytes)
+    uint8_t ring[kStageRows * kMaxW * 3];     // the raw RGB rows of ONE stage, filled by TMA (row r at r * row_bytes)
+    uint32_t halo[2][kStageRows][kK1Threads]; // per row and thread: gray of px 0,1,6,7 of its eight (what the neighbours' box sums need)
     uint32_t raster[2][10][kRastWords];       // 1-bit threshold rows of the current / previous stage
     uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
@@ -189,25 +188,26 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// 128 threads (8 px each), 4 CTAs/SM.  The kernel is latency-bound per warp (no pipe is saturated; throughput scales
-// linearly with resident CTAs), so shared memory per CTA is kept to ~50 KB: the raw rows live in a ring of five 3-row
-// units (a 9-row stage = 3 consecutive units mod 5), and the box-filter halo words are parked in raw words that are
-// already dead instead of in a separate exchange buffer.
+// 128 threads (8 px each), 5 CTAs/SM.  The kernel is bound by instruction issue and dependency latency, not by HBM (the same
+// TMA pipeline with the decode switched off copies at 7.5 TB/s, CB200_K1_L2_AHEAD=4096), so what counts is resident warps:
+// shared memory per CTA is 41 KB -- the raw rows of exactly one stage (every raw byte is consumed before the stage barrier,
+// so the next stage can land in the same place while the box sums and the symbols run) plus a 9 KB exchange array for the
+// box-filter halo words -- and registers are capped at 96.
 // One barrier per stage.  Iteration for stage `it` (cell row k, raw rows [y_k+2, y_k+10]):
 //   wait full[it&1]
 //   A(k):   gray of the thread's 8 px in each of the 9 rows -> packed pairs in registers; one halo word E_r per row
-//           (bytes g0,g1,g6,g7) is parked in the thread's OWN raw words of stage rows 5..7 (consumed by then, and
-//           never read by the colour pass)
-//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static)
-//   ---- __syncthreads ----   thread 0: TMA of stage it+1 (its 3 units land on stage it-1's units 1,2 and stage it's
-//                             unit 0, all dead now), L2 prefetch further ahead
+//           (bytes g0,g1,g6,g7) goes to a small double-buffered exchange array
+//   col(k): 6x6 RGB means of cell row k straight from the staged raw rows (drift 0: positions are static), and the
+//           first row of cell row k+1's window (its other rows come with the next stage)
+//   ---- __syncthreads ----   nobody reads the raw rows any more: thread 0 issues the TMA of stage it+1 into the same
+//                             27 KB, it lands while B and S run
 //   B(k):   box sums, threshold -> raster[it&1]
 //   S(k-1): symbols of cell row k-1 from raster[(it-1)&1] (complete since this barrier) + col(k-1) -> result bytes
 // CCM: the colour classifier runs the reference's float path with a 3x3 colour correction matrix (ccm.cuh) instead of the
 // integer restatement; the matrix of the frame is staged in shared memory when a CTA starts on it.
 // CM = 0: integer classifier; 1: CCM classifier; 2: no decision, the cell's mean colour is stored for the fitted-CCM pass
 template <int NC, bool G1024, int CM>
-__global__ void __launch_bounds__(kK1Threads, 4)
+__global__ void __launch_bounds__(kK1Threads, 5)
 k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead_arg,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags, const CcmArg cc)
 {
@@ -239,7 +239,6 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
     const int tid = threadIdx.x;
     const int W = m.width();
     const uint32_t row_bytes = (uint32_t)W * 3u;
-    const uint32_t unit_bytes = row_bytes * kUnitRows;
     const uint32_t stage_bytes = row_bytes * kStageRows;
     const size_t frame_bytes = (size_t)row_bytes * (size_t)m.height();
     const int n_units = n_frames * bands;
@@ -280,14 +279,11 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         c.u += gridDim.x;
         cursor_unit(c);
     };
-    // stage `i` occupies ring units (3i, 3i+1, 3i+2) mod 5 starting at unit `p`; the source rows are contiguous, so the
-    // stage is one bulk copy, or two when it wraps around the end of the ring; one mbarrier transaction covers both
-    auto issue_stage = [&](const Cursor& c, uint32_t i, uint32_t p) {
+    // the nine source rows of a stage are contiguous in the frame: one bulk copy into the (single-stage) ring
+    auto issue_stage = [&](const Cursor& c, uint32_t i) {
         unsigned long long* bar = &s.full_bar[i & 1u];
         mbar_expect_tx(bar, stage_bytes);
-        const uint32_t first = (kRingUnits - p) < 3u ? (kRingUnits - p) : 3u;      // units before the wrap
-        tma_bulk_g2s(s.ring + p * unit_bytes, c.src, first * unit_bytes, bar);
-        if (first < 3u) tma_bulk_g2s(s.ring, c.src + (size_t)first * unit_bytes, (3u - first) * unit_bytes, bar);
+        tma_bulk_g2s(s.ring, c.src, stage_bytes, bar);
     };
     // two cursors over that stream, each owned by one thread: thread 0 feeds the shared-memory ring (TMA), the first thread of
     // warp 1 runs l2_ahead stages further ahead and only prefetches into L2 -- the per-stage cursor arithmetic is spread over
@@ -301,7 +297,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
     nxt.u = blockIdx.x; nxt.valid = false; pre.u = blockIdx.x; pre.valid = false;
     if (tid == 0) {
         cursor_unit(nxt);
-        if (nxt.valid) { issue_stage(nxt, 0u, 0u); cursor_next(nxt); }
+        if (nxt.valid) { issue_stage(nxt, 0u); cursor_next(nxt); }
     }
     if (tid == pf_tid && l2_ahead > 0) {
         cursor_unit(pre);
@@ -353,7 +349,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         if (active) out[cell] = (uint8_t)(sym | (col << m.symbol_bits()) | dirty);
     };
 
-    uint32_t it = 0, ring_pos = 0;                 // ring unit of the current stage's first row: (3 * it) mod 5
+    uint32_t it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int f = u / bands, b = u - f * bands;
         int k0 = (m.cells_y() * b) / bands, k1 = (m.cells_y() * (b + 1)) / bands;
@@ -377,18 +373,12 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
 
         for (int k = k0 - 1; k < k1; ++k, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            // the three ring units of this stage: rows 0-2, 3-5, 6-8
-            const uint32_t p0 = ring_pos;
-            const uint32_t p1 = (p0 + 1u == kRingUnits) ? 0u : p0 + 1u;
-            const uint32_t p2 = (p1 + 1u == kRingUnits) ? 0u : p1 + 1u;
-            uint8_t* ub[3] = {s.ring + p0 * unit_bytes, s.ring + p1 * unit_bytes, s.ring + p2 * unit_bytes};
+            uint8_t* const ub[3] = {s.ring, s.ring + 3u * row_bytes, s.ring + 6u * row_bytes};   // stage rows 0-2, 3-5, 6-8
             mbar_wait(&s.full_bar[buf], ph);
             if (load_only) {                               // tuning only: the stage is dropped as soon as it has landed
                 __syncthreads();
-                const uint32_t p3 = p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u;
-                if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u, p3); cursor_next(nxt); }
+                if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u); cursor_next(nxt); }
                 if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
-                ring_pos = p3;
                 continue;
             }
 
@@ -414,17 +404,9 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                     // gray is byte 2 of each numerator
                     E[r] = __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n6, n7, 0x6200), 0x7610);
                 }
-                // park E_0..E_8 in this thread's own (already consumed) raw words of stage rows 5, 6, 7: the thread owns words
-                // 6t..6t+5 of each row; slot 2*(r%3) + (t>>4 & 1) makes lanes t and t+16 (same 6t mod 32) hit different banks
-                if (px_active) {
-                    const uint32_t po = 6u * (uint32_t)t + (((uint32_t)t >> 4) & 1u);
-                    uint32_t* w5 = reinterpret_cast<uint32_t*>(ub[1] + 2u * row_bytes) + po;   // stage row 5 = unit 1, row 2
-                    uint32_t* w6 = reinterpret_cast<uint32_t*>(ub[2]) + po;                    // stage row 6 = unit 2, row 0
-                    uint32_t* w7 = reinterpret_cast<uint32_t*>(ub[2] + row_bytes) + po;        // stage row 7 = unit 2, row 1
-                    w5[0] = E[0]; w5[2] = E[1]; w5[4] = E[2];
-                    w6[0] = E[3]; w6[2] = E[4]; w6[4] = E[5];
-                    w7[0] = E[6]; w7[2] = E[7]; w7[4] = E[8];
-                }
+                // E_0..E_8 go to the halo buffer of this stage (double buffered: a warp may start A(k+1) while another is still in B(k))
+#pragma unroll
+                for (int r = 0; r < kStageRows; ++r) s.halo[buf][r][t] = E[r];
             }
 
             // ---------------- col(k): inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
@@ -452,8 +434,8 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 }
             }
             __syncthreads();
-            // dead now: stage it-1's units 1,2 (their parked halo words were last read in B(k-1)) and this stage's unit 0
-            if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u, p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u); cursor_next(nxt); }
+            // the raw rows are dead now (gray is in registers, the colour sums are taken): the next stage may overwrite them
+            if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u); cursor_next(nxt); }
             if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
 
             // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
@@ -461,15 +443,10 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[buf][0][0]);
                 const uint8_t* prev8 = reinterpret_cast<const uint8_t*>(&s.raster[buf ^ 1u][0][0]);
                 if (px_active) rast8[t] = prev8[9 * kRastPitch + t];
-                const uint32_t* e5 = reinterpret_cast<const uint32_t*>(ub[1] + 2u * row_bytes);
-                const uint32_t* e6 = reinterpret_cast<const uint32_t*>(ub[2]);
-                const uint32_t* e7 = reinterpret_cast<const uint32_t*>(ub[2] + row_bytes);
-                const uint32_t pol = 6u * (uint32_t)tl + (((uint32_t)tl >> 4) & 1u), por = 6u * (uint32_t)tr + (((uint32_t)tr >> 4) & 1u);
                 uint32_t h[kStageRows][4];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    const uint32_t* er = (r < 3) ? e5 : (r < 6 ? e6 : e7);
-                    uint32_t lE = er[pol + 2 * (r % 3)], rE = er[por + 2 * (r % 3)];
+                    const uint32_t lE = s.halo[buf][r][tl], rE = s.halo[buf][r][tr];
                     uint32_t Pm2 = __byte_perm(lE, P[r][2], 0x5452), Pm1 = __byte_perm(lE, P[r][3], 0x5453);
                     uint32_t P4 = __byte_perm(P[r][0], rE, 0x3432), P5 = __byte_perm(P[r][1], rE, 0x3532);
                     h[r][0] = Pm2 + Pm1 + P[r][0] + P[r][1] + P[r][2];
@@ -505,7 +482,6 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
             // ---------------- S(k-1): its raster was finished by every thread before the barrier above
             if (k - 1 >= k0) symbol_stage(k - 1, buf ^ 1u, col_prev, out, any_dirty);
             col_prev = col;
-            ring_pos = p0 + 3u >= kRingUnits ? p0 + 3u - kRingUnits : p0 + 3u;
         }
         // the last cell row of the unit still needs its symbols: one more barrier to see its complete raster
         __syncthreads();
