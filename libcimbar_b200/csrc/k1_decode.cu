@@ -28,6 +28,9 @@
 namespace cb200 {
 
 constexpr int kK1Threads = 128;            // 128 threads x 8 px = one full 1024-px row
+#ifndef CB200_K1_MIN_CTAS
+#define CB200_K1_MIN_CTAS 5                // resident CTAs per SM the register allocation is capped for (5 -> 96 registers, 4 -> 128)
+#endif
 constexpr int kStageRows = 9;              // raw rows per cell row (stage)
 constexpr int kMaxW = 1024;
 constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
@@ -207,7 +210,7 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 // integer restatement; the matrix of the frame is staged in shared memory when a CTA starts on it.
 // CM = 0: integer classifier; 1: CCM classifier; 2: no decision, the cell's mean colour is stored for the fitted-CCM pass
 template <int NC, bool G1024, int CM>
-__global__ void __launch_bounds__(kK1Threads, 5)
+__global__ void __launch_bounds__(kK1Threads, CB200_K1_MIN_CTAS)
 k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead_arg,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags, const CcmArg cc)
 {
