@@ -11,7 +11,7 @@
 // centre hash wins for every cell.  A cell where it does not sets bit 7 of its result
 // byte and the frame's dirty flag; such frames are re-done by the exact flood-walk kernel (k1x_flood.cu).
 //
-// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 5 CTAs/SM):
+// Data flow per CTA (128 threads, thread 0 doubles as the TMA producer; 4 CTAs/SM):
 //   HBM --cp.async.bulk (TMA, one copy of 9 full-width rows = 27 KB per stage, one mbarrier per stage)--> smem
 //   phase A: 8 px/thread: gray = (19596R+38470G+7470B+32768)>>16 via 2x IDP.2A per px, packed 2x16 bit
 //   phase B: separable 5x5 box sum in packed-16 SIMD (5 IADD3 + 4 PRMT per 8 px), rolling vertical sum in
@@ -29,7 +29,7 @@ namespace cb200 {
 
 constexpr int kK1Threads = 128;            // 128 threads x 8 px = one full 1024-px row
 #ifndef CB200_K1_MIN_CTAS
-#define CB200_K1_MIN_CTAS 5                // resident CTAs per SM the register allocation is capped for (5 -> 96 registers, 4 -> 128)
+#define CB200_K1_MIN_CTAS 4                // resident CTAs per SM the register allocation is capped for (4 -> 128 registers, 5 -> 96)
 #endif
 constexpr int kStageRows = 9;              // raw rows per cell row (stage)
 constexpr int kMaxW = 1024;
@@ -191,11 +191,12 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-// 128 threads (8 px each), 5 CTAs/SM.  The kernel is bound by instruction issue and dependency latency, not by HBM (the same
-// TMA pipeline with the decode switched off copies at 7.5 TB/s, CB200_K1_L2_AHEAD=4096), so what counts is resident warps:
-// shared memory per CTA is 41 KB -- the raw rows of exactly one stage (every raw byte is consumed before the stage barrier,
-// so the next stage can land in the same place while the box sums and the symbols run) plus a 9 KB exchange array for the
-// box-filter halo words -- and registers are capped at 96.
+// 128 threads (8 px each), 4 CTAs/SM.  The kernel is bound by instruction issue and dependency latency, not by HBM: the same
+// TMA pipeline with the decode switched off copies at 7.4-7.5 TB/s (CB200_K1_L2_AHEAD=4096), with it 5.6 TB/s.  Shared memory
+// per CTA is 41 KB -- the raw rows of exactly one stage (every raw byte is consumed before the stage barrier, so the next
+// stage lands in the same place while the box sums and the symbols run) plus a 9 KB exchange array for the box-filter halo
+// words -- which would admit five CTAs per SM; measured, five CTAs at the 96 registers that requires lose to four at 128
+// (5.96 vs 5.63 ms per 10 000 frames: the scheduler needs the registers to keep a stage's loads in flight), so the cap is 128.
 // One barrier per stage.  Iteration for stage `it` (cell row k, raw rows [y_k+2, y_k+10]):
 //   wait full[it&1]
 //   A(k):   gray of the thread's 8 px in each of the 9 rows -> packed pairs in registers; one halo word E_r per row
