@@ -537,7 +537,7 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
             const int f = gi * kFrFrames + fs;
             if (f >= n_frames) break;
             const uint8_t* src = cellvals + (size_t)f * m.num_cells;
-            for (int i = tid; i < cell_vecs; i += kFrWarps * 32) cp_async16(cellbuf_s + (uint32_t)(fs * cell_pitch + 16 * i), src + 16 * i);
+            for (int i = tid; i < cell_vecs; i += (int)blockDim.x) cp_async16(cellbuf_s + (uint32_t)(fs * cell_pitch + 16 * i), src + 16 * i);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -576,7 +576,7 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
         const int nf = (n_frames - gi * kFrFrames) < kFrFrames ? (n_frames - gi * kFrFrames) : kFrFrames;
 
         // ---- P7/P10: staged word q of block r = stream bytes 155 r + 4 q - 1 .. + 2 (byte -1 of a block is the zero in front)
-        for (int wi = tid; wi < nf * words_per_frame; wi += kFrWarps * 32) {
+        for (int wi = tid; wi < nf * words_per_frame; wi += (int)blockDim.x) {
             const int fs = wi >= words_per_frame ? 1 : 0;
             const int rem = wi - fs * words_per_frame;
             const int r = rem / kFrWords, q = rem - r * kFrWords;
@@ -749,7 +749,8 @@ cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const u
             cudaError_t e = cudaFuncSetAttribute(k_rs_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             int groups = (n_frames + kFrFrames - 1) / kFrFrames, ctas = groups < 2 * sm_count ? groups : 2 * sm_count;
-            k_rs_frames<<<ctas, kFrWarps * 32, smem, st>>>(m, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, cell_pitch); count_launch();
+            // one warp per unit of the two frames a CTA holds (30 for mode B): no warp sits out the correction phase
+            k_rs_frames<<<ctas, 32 * kFrFrames * (m.nblocks / 4), smem, st>>>(m, d_cellvals, d_idx, n_frames, d_data, d_ok, d_rho, cell_pitch); count_launch();
             return cudaGetLastError();
         }
     }
