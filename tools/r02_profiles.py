@@ -18,17 +18,17 @@ PR = os.path.join(ROOT, "profiles")
 
 # profile name -> candidate sources in gpurun_out (first that exists wins)
 BENCH = {
-    "r02_bench_n1.json": ["r2h_bench_n1.json", "r2g_n1.json"],
-    "r02_bench_reference_arm.json": ["r2h_reference.json", "r2b_reference.json"],
-    "r02_bench_errors1pct.json": ["r2h_errors1pct.json", "r2g_k2new_errors1pct.json"],
-    "r02_bench_noise1pct_9472frames.json": ["r2i_noise.json", "r2g_noise.json"],
-    "r02_bench_noise1pct_3552frames.json": ["r2i_noise_3552.json", "r2d_noise_3552.json"],
-    "r02_bench_color_correction_1.json": ["r2h_cc1.json"],
-    "r02_bench_color_correction_2.json": ["r2h_cc2.json"],
-    "r02_bench_mode4.json": ["r2h_mode4.json", "r2d_mode4.json"],
-    "r02_bench_mode4_errors1pct.json": ["r2h_mode4_errors.json", "r2b_mode4_errors.json"],
-    "r02_bench_mode67.json": ["r2h_mode67.json"],
-    "r02_bench_fountain_n1.json": ["r2h_fountain_n1.json", "r2g_fountain_n1.json"],
+    "r02_bench_n1.json": ["r2o_bench_n1.json", "r2h_bench_n1.json", "r2g_n1.json"],
+    "r02_bench_reference_arm.json": ["r2o_reference.json", "r2h_reference.json", "r2b_reference.json"],
+    "r02_bench_errors1pct.json": ["r2o_errors1pct.json", "r2h_errors1pct.json", "r2g_k2new_errors1pct.json"],
+    "r02_bench_noise1pct_9472frames.json": ["r2o_noise.json", "r2i_noise.json", "r2g_noise.json"],
+    "r02_bench_noise1pct_3552frames.json": ["r2o_noise_3552.json", "r2i_noise_3552.json", "r2d_noise_3552.json"],
+    "r02_bench_color_correction_1.json": ["r2o_cc1.json", "r2h_cc1.json"],
+    "r02_bench_color_correction_2.json": ["r2o_cc2.json", "r2h_cc2.json"],
+    "r02_bench_mode4.json": ["r2o_mode4.json", "r2h_mode4.json", "r2d_mode4.json"],
+    "r02_bench_mode4_errors1pct.json": ["r2o_mode4_errors.json", "r2h_mode4_errors.json", "r2b_mode4_errors.json"],
+    "r02_bench_mode67.json": ["r2o_mode67.json", "r2h_mode67.json"],
+    "r02_bench_fountain_n1.json": ["r2o_fountain_n1.json", "r2h_fountain_n1.json", "r2g_fountain_n1.json"],
     "r02_bench_fountain_n2_window.json": ["r2j_fountain_n2.json", "r2g_fountain_n2.json"],
     "r02_bench_fountain_n2_nccl.json": ["r2j_fountain_n2_nccl.json", "r2g_fountain_n2_nccl.json"],
     "r02_bench_fountain_n8.json": ["r2k_fountain_n8.json"],
@@ -141,11 +141,11 @@ def first(*names):
 
 def ncu_docs():
     """K1 / K2 / K1x summaries of the `ncu --set full` captures (numbers under ncu are never bench values)"""
-    k1 = first("r2l_k1.ncu-rep", "r2i_k1.ncu-rep")
-    k2 = first("r2l_k2.ncu-rep", "r2i_k2.ncu-rep", "r2h_k2.ncu-rep")
-    k2e = first("r2l_k2_err.ncu-rep", "r2h_k2_err.ncu-rep")
-    walk = first("r2l_walk.ncu-rep", "r2d_walk.ncu-rep")
-    rast = first("r2l_raster.ncu-rep", "r2a_raster.ncu-rep")
+    k1 = first("r2o_k1.ncu-rep", "r2i_k1.ncu-rep")
+    k2 = first("r2o_k2.ncu-rep", "r2i_k2.ncu-rep", "r2h_k2.ncu-rep")
+    k2e = first("r2o_k2_err.ncu-rep", "r2h_k2_err.ncu-rep")
+    walk = first("r2o_walk.ncu-rep", "r2d_walk.ncu-rep")
+    rast = first("r2o_raster.ncu-rep", "r2a_raster.ncu-rep")
     out = ["# Round 2 -- ncu evidence (B200, `ncu --set full --clock-control none --import-source on`, one launch each;",
            "summaries by `tools/ncu_summary.py` / `tools/ncu_lines.py`; the unprofiled numbers are in `r02_results.md`)", ""]
     if k1:
