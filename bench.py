@@ -42,10 +42,12 @@ def parse_args():
     ap.add_argument("--color-correction", type=int, default=0, choices=[0, 1, 2],
                     help="the reference's color_correction argument (0 = headline configuration; 1 = per-frame von Kries; "
                          "2 = per-frame header fit, the payload then carries consecutive fountain headers)")
-    ap.add_argument("--gather", default="window", choices=["window", "nccl", "torch"],
-                    help="N > 1: how the chunk records reach rank 0 -- window = the RS kernels store straight into rank 0's HBM over "
-                         "NVLink (CUDA IPC peer mapping, cb200_gather_slot/publish/wait); nccl = cb200_gather_chunks (ncclSend/Recv on a "
-                         "side stream, double buffered); torch = torch.distributed.gather on the decode stream (round-1 behaviour)")
+    ap.add_argument("--gather", default="window", choices=["window", "window-direct", "nccl", "torch"],
+                    help="N > 1: how the chunk records reach rank 0 -- window = a window in rank 0's HBM mapped by every rank over NVLink "
+                         "(CUDA IPC), filled by copy-engine pushes on a side stream (cb200_gather_push / wait / release); window-direct = "
+                         "the RS kernels store straight into that window (cb200_gather_slot / publish); nccl = cb200_gather_chunks "
+                         "(ncclSend/Recv on a side stream, double buffered); torch = torch.distributed.gather on the decode stream "
+                         "(round-1 behaviour)")
     ap.add_argument("--fountain", action="store_true",
                     help="BASELINE configs[3]: fountain-encoded file, frames sharded over the ranks, records to rank 0, wirehair "
                          "reassembly checked by SHA-256 (libcimbar_b200/fountain_bench.py)")
@@ -221,10 +223,10 @@ def run_ours(args):
     if world > 1:
         from libcimbar_b200.dist import RecordExchange
         gather_kind = args.gather
-        if gather_kind == "window":
+        if gather_kind in ("window", "window-direct"):
             # every rank must agree on the path: fall back to NCCL everywhere if any rank cannot map the window
             try:
-                exchange = RecordExchange(ctx, "window", B, rank, world)
+                exchange = RecordExchange(ctx, gather_kind, B, rank, world)
                 okw = 1
             except cb.Cb200Error as e:
                 print("bench.py: rank %d cannot use the NVLink window (%s); falling back to --gather nccl" % (rank, e), file=sys.stderr)
@@ -314,11 +316,11 @@ def run_ours(args):
         dist.gather(payload, payloads, dst=0)
         if rank == 0:
             # what arrived on rank 0 for the last step, rank by rank, against that rank's payload
-            if gather_kind == "window":
+            if gather_kind in ("window", "window-direct"):
                 ctx.gather_status()
             got = []
             for r in range(world):
-                if gather_kind == "window":
+                if gather_kind in ("window", "window-direct"):
                     pc, pm = ctx.gather_slot(last & 1, r)
                     got.append((dev_copy(pc, B * info.data_bytes).view(B, info.data_bytes), dev_copy(pm, 4 * B).view(torch.int32)))
                 else:
@@ -327,7 +329,7 @@ def run_ours(args):
             if args.workload == "clean":
                 full = (1 << info.chunks_per_frame) - 1
                 gathered_ok = all(bool((m_ == full).all().item()) and bool(torch.equal(c_, p_)) for (c_, m_), p_ in zip(got, payloads))
-        elif gather_kind == "nccl":
+        elif exchange.send is not None:
             chunks, mask = exchange.send[last & 1]
         else:   # a peer's records live in rank 0's HBM: decode once more into local buffers for this rank's own parity line
             ctx.decode_chunks_dev(frames.data_ptr(), B, chunks.data_ptr(), mask.data_ptr(), fflags.data_ptr(), flags=cc_flags)
@@ -425,7 +427,8 @@ def run_ours(args):
                    "mode": "%s (%d)" % (MODE_NAMES[MV], MV), "frames_per_gpu_per_step": B, "color_correction": args.color_correction,
                    "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
                    "parallelism": "frames sharded one-per-GPU (dp%d); chunk records to rank 0 by %s" % (world, {
-                       None: "nothing (one GPU)", "window": "direct NVLink stores of the RS kernels into rank 0's HBM (CUDA IPC window, device-side epochs)",
+                       None: "nothing (one GPU)", "window": "copy-engine pushes into a window in rank 0's HBM (CUDA IPC peer mapping over NVLink, device-side epochs, side stream: overlaps the next decode)",
+                       "window-direct": "direct NVLink stores of the RS kernels into rank 0's HBM (CUDA IPC window, device-side epochs)",
                        "nccl": "ncclSend/ncclRecv on a side stream (cb200_gather_chunks), double buffered",
                        "torch": "torch.distributed.gather on the decode stream"}[gather_kind])},
         "parity": parity + ("" if ok_flags else " (%d of %d frames/rank went through the exact flood-walk kernel)" % (n_fallback, B)),

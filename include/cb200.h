@@ -260,6 +260,12 @@ int cb200_gather_root_create(cb200_ctx* ctx, int nranks, uint8_t* handle_out /* 
 int cb200_gather_peer_open(cb200_ctx* ctx, int nranks, int rank, const uint8_t* handle);
 int cb200_gather_slot(cb200_ctx* ctx, int buffer /* 0 | 1 */, int rank /* < 0: this rank */, uint8_t** d_chunks, uint32_t** d_mask);
 int cb200_gather_publish(cb200_ctx* ctx, int buffer, uint32_t epoch);
+/* the push form: n records that the decode wrote into LOCAL buffers travel to this rank's slot by a copy-engine transfer on a
+   side stream (ordered after everything enqueued on the context's stream so far, and -- acquire_epoch != 0 -- after rank 0 has
+   released that slot up to acquire_epoch), then the epoch is published from the side stream.  The decode stream does not
+   wait; before the local buffers are written again: cb200_gather_chunks_wait(ctx, buffer). */
+int cb200_gather_push(cb200_ctx* ctx, int buffer, const uint8_t* d_chunks, const uint32_t* d_mask, int n, uint32_t epoch,
+                      uint32_t acquire_epoch);
 int cb200_gather_wait(cb200_ctx* ctx, int buffer, uint32_t epoch, double timeout_s /* <= 0: 30 s */);
 int cb200_gather_release(cb200_ctx* ctx, int buffer, uint32_t epoch);                    /* rank 0 */
 int cb200_gather_acquire(cb200_ctx* ctx, int buffer, uint32_t epoch, double timeout_s);  /* any rank (no-op on rank 0) */

@@ -27,7 +27,7 @@ EXPORTS = [
     "cb200_sink_create", "cb200_sink_create_wirehair", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
     "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count", "cb200_decode_fountain_from_dev", "cb200_perspective_transform", "cb200_deskew_dev", "cb200_deskew",
     "cb200_extract_decode_fountain", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
-    "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_wait",
+    "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_push", "cb200_gather_wait",
     "cb200_gather_release", "cb200_gather_acquire",
     "cb200_gather_status", "cb200_comm_unique_id", "cb200_comm_init", "cb200_gather_chunks", "cb200_gather_chunks_wait",
 ]
@@ -106,6 +106,7 @@ def load_library():
     lib.cb200_gather_peer_open.argtypes = [vp, C.c_int, C.c_int, u8p]
     lib.cb200_gather_slot.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.cb200_gather_publish.argtypes = [vp, C.c_int, C.c_uint32]
+    lib.cb200_gather_push.argtypes = [vp, C.c_int, u8p, u32p, C.c_int, C.c_uint32, C.c_uint32]
     lib.cb200_gather_wait.argtypes = [vp, C.c_int, C.c_uint32, C.c_double]
     lib.cb200_gather_release.argtypes = [vp, C.c_int, C.c_uint32]
     lib.cb200_gather_acquire.argtypes = [vp, C.c_int, C.c_uint32, C.c_double]
@@ -353,6 +354,10 @@ class Context:
 
     def gather_publish(self, buffer, epoch):
         _check(self.lib.cb200_gather_publish(self._h, buffer, epoch))
+
+    def gather_push(self, buffer, d_chunks, d_mask, n, epoch, acquire_epoch=0):
+        """records in local buffers -> this rank's window slot by a copy-engine transfer on the side stream, then publish"""
+        _check(self.lib.cb200_gather_push(self._h, buffer, d_chunks, d_mask, n, epoch, acquire_epoch))
 
     def gather_wait(self, buffer, epoch, timeout_s=30.0):
         _check(self.lib.cb200_gather_wait(self._h, buffer, epoch, timeout_s))

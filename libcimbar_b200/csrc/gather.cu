@@ -4,12 +4,18 @@
 // src/lib/fountain/concurrent_fountain_decoder_sink.h:58-84: decoder threads push chunks, one thread drains them into the
 // fountain_decoder_sink) for one process per GPU on an NVLink / NVSwitch box.
 //
-// Primary path -- a window in rank 0's HBM that every rank maps (CUDA IPC, NVLink peer access): the RS kernel of rank r
-// writes its corrected bytes, and the chunk-mask kernel its masks, STRAIGHT INTO rank 0's memory through the peer mapping
-// (cb200_gather_slot gives the pointers to hand to cb200_decode_chunks_dev), so the transfer happens tile by tile while the
-// decode runs and there is no separate collective pass.  A rank then publishes an epoch with a system-scope release store
-// into a flag word of the window; rank 0 waits for the epochs of all ranks with a system-scope acquire spin (bounded).
-// The window is double buffered: rank 0 may still be draining buffer b while everybody decodes into buffer b ^ 1.
+// Primary path -- a window in rank 0's HBM that every rank maps (CUDA IPC, NVLink peer access).  A rank's records reach its
+// slot of the window in one of two ways:
+//   push   (cb200_gather_push, the default of the drivers): the decode writes into local buffers, and a copy-engine transfer on
+//          a side stream of the context moves them through the peer mapping -- no SM is involved, the transfer of step i runs
+//          under the decode of step i + 1, and eight ranks finishing their RS kernels at the same moment do not pile their
+//          stores up on rank 0's NVLink ingress (measured on 8 GPUs: the direct stores below cost 1 ms per 6 ms step);
+//   direct (cb200_gather_slot gives the pointers to hand to cb200_decode_chunks_dev): the RS kernel of rank r writes its
+//          corrected bytes, and the chunk-mask kernel its masks, STRAIGHT INTO rank 0's memory, tile by tile while the decode
+//          runs.  Fine for two to four ranks.
+// Either way the rank then publishes an epoch with a system-scope release store into a flag word of the window; rank 0 waits
+// for the epochs of all ranks with a system-scope acquire spin (bounded).  The window is double buffered: rank 0 may still be
+// draining buffer b while everybody works on buffer b ^ 1; a rank re-uses a slot only after rank 0 has released it.
 //
 // Second path -- cb200_gather_chunks(ctx, ncclComm_t, ...): ncclSend / ncclRecv (grouped) on a side stream of the context,
 // ordered after the decode by an event, so that the exchange of step i overlaps the decode of step i + 1.  NCCL is bound at
@@ -82,6 +88,15 @@ static GatherState* state(cb200_ctx* c)
 {
     if (!c->gather) c->gather = new GatherState();
     return c->gather;
+}
+
+static cudaError_t ensure_side(GatherState* g)
+{
+    if (g->side) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_ready, cudaEventDisableTiming);
+    for (cudaEvent_t& ev : g->ev_done) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    return e;
 }
 
 static void layout(GatherState* g, const cb200_ctx* c, int nranks)
@@ -223,6 +238,31 @@ int cb200_gather_acquire(cb200_ctx* c, int buffer, uint32_t epoch, double timeou
     return CB200_OK;
 }
 
+int cb200_gather_push(cb200_ctx* c, int buffer, const uint8_t* d_chunks, const uint32_t* d_mask, int n, uint32_t epoch, uint32_t acquire_epoch)
+{
+    if (!c || !c->gather || !c->gather->win || buffer < 0 || buffer > 1 || !d_chunks || !d_mask || n < 0 || n > c->max_frames)
+        return fail(CB200_ERR_ARG, "no gather window / bad arguments");
+    GatherState* g = c->gather;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    CK(ensure_side(g), "side stream (gather)");
+    uint32_t* flags = reinterpret_cast<uint32_t*>(g->win + g->flags_off);
+    // after everything enqueued on the decode stream so far ...
+    CK(cudaEventRecord(g->ev_ready, c->stream), "record");
+    CK(cudaStreamWaitEvent(g->side, g->ev_ready, 0), "wait");
+    // ... and after rank 0 has let go of what this slot held two steps ago
+    if (!g->win_owner && acquire_epoch) {
+        k_gather_wait<<<1, 32, 0, g->side>>>(flags + 65 + buffer, 1, acquire_epoch, 30000000000ull, flags + 64); count_launch();
+        CK(cudaGetLastError(), "acquire launch");
+    }
+    uint8_t* base = g->win + (size_t)buffer * g->buffer_bytes + (size_t)g->rank * g->slot_bytes;
+    CK(cudaMemcpyAsync(base, d_chunks, (size_t)n * (size_t)c->mode.data_bytes, cudaMemcpyDeviceToDevice, g->side), "push chunks (peer copy)");
+    CK(cudaMemcpyAsync(base + g->chunk_bytes, d_mask, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, g->side), "push masks (peer copy)");
+    k_gather_publish<<<1, 1, 0, g->side>>>(flags + buffer * 32 + g->rank, epoch); count_launch();
+    CK(cudaGetLastError(), "publish launch");
+    CK(cudaEventRecord(g->ev_done[buffer], g->side), "record");
+    return CB200_OK;
+}
+
 int cb200_gather_status(cb200_ctx* c)
 {
     if (!c || !c->gather || !c->gather->win || !c->gather->win_owner) return fail(CB200_ERR_ARG, "no gather window");
@@ -274,11 +314,7 @@ int cb200_gather_chunks(cb200_ctx* c, void* nccl_comm, int nranks, int rank, int
     if (const char* e = nccl_load(g->nccl)) return fail(CB200_ERR_CUDA, e);
     void* comm = nccl_comm ? nccl_comm : g->own_comm;
     if (!comm) return fail(CB200_ERR_ARG, "no communicator: pass an ncclComm_t or call cb200_comm_init");
-    if (!g->side) {
-        CK(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking), "cudaStreamCreate (gather)");
-        CK(cudaEventCreateWithFlags(&g->ev_ready, cudaEventDisableTiming), "cudaEventCreate");
-        for (cudaEvent_t& e : g->ev_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-    }
+    CK(ensure_side(g), "side stream (gather)");
     // the exchange runs on the side stream, after everything enqueued on the decode stream so far
     CK(cudaEventRecord(g->ev_ready, c->stream), "record");
     CK(cudaStreamWaitEvent(g->side, g->ev_ready, 0), "wait");

@@ -77,6 +77,7 @@ constexpr int kStagePitch = 196;         // bytes per staged block: >= 1 + 179, 
 
 template <int T>
 struct RsSmem {
+    static constexpr bool kSynTable = false;
     static constexpr int GL = 8 * T;     // lanes per block in the remainder stage
     static constexpr int G = 32 / GL;    // blocks a warp takes at a time
     uint8_t exp[512];
@@ -135,6 +136,26 @@ __device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc,
             __syncwarp();
             if (holds) reinterpret_cast<uint32_t*>(w.rem)[k] = word;
             __syncwarp();
+            if constexpr (S::kSynTable) {
+                // (parity <= 32) multiplication by the constant c = alpha^((j+1)(i - parity)) is linear over GF(2): r c = XOR over the set
+                // bits b of r of c 2^b.  wsyn[i][j] holds those eight products, masks[i] has byte b = 0xFF iff bit b of r'[i] is set
+                // (the same for every lane): two 64-bit loads and two AND-XORs per remainder byte, no log/exp chain
+                if (lane < md) {
+                    const uint32_t rb = w.rem[pad + lane];
+                    w.masks[lane] = make_uint2((((rb & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu, (((rb >> 4) * 0x00204081u) & 0x01010101u) * 0xFFu);
+                }
+                __syncwarp();
+                uint32_t ax = 0, ay = 0;
+#pragma unroll 6
+                for (int i = 0; i < md; ++i) {
+                    const uint2 mk = w.masks[i];                                                // broadcast
+                    const uint2 tw = s.wsyn[i][lane];
+                    ax ^= tw.x & mk.x; ay ^= tw.y & mk.y;
+                }
+                uint32_t x = ax ^ ay;
+                x ^= x >> 16; x ^= x >> 8;
+                if (lane < md) w.synd[lane] = (uint8_t)x;
+            } else {
             for (int i = lane; i < md; i += 32) { const uint32_t rb = w.rem[pad + i]; w.remlog[i] = (uint16_t)(rb | ((uint32_t)s.log[rb] << 8)); }
             __syncwarp();
 #pragma unroll
@@ -150,6 +171,7 @@ __device__ __forceinline__ bool rs_correct_block(const S& s, W& w, uint8_t* enc,
                     }
                     w.synd[j] = (uint8_t)acc;
                 }
+            }
             }
             __syncwarp();
         // ---- Berlekamp-Massey (decode.c:30-116).  Field arithmetic is exact, so scale = disc / last_disc is applied as one
@@ -493,9 +515,11 @@ constexpr int kFrBlk = 155, kFrWords = 39, kFrPitch = 160;   // block bytes; wor
                                                              // 40 words, so the four rows of a unit start 8 banks apart
 
 struct RsFrSmem {
+    static constexpr bool kSynTable = true;
     uint8_t exp[512];
     uint8_t log[256];
     struct PerWarp {
+        alignas(8) uint2 masks[32];           // per remainder byte: byte b = 0xFF iff its bit b is set (syndromes of a dirty block)
         alignas(4) uint8_t rem[64];
         alignas(2) uint16_t remlog[kMaxParity];
         uint8_t synd[kMaxParity];
@@ -505,6 +529,8 @@ struct RsFrSmem {
         uint8_t roots[kMaxParity + 8];
     } w[kFrWarps];
     uint8_t la[kLaDim][kLaDim];
+    // wsyn[i][j] byte b = alpha^((j+1)(i - parity)) * 2^b: the weight of bit b of remainder byte i in syndrome j
+    alignas(8) uint2 wsyn[32][32];
     // followed in dynamic shared memory by: uint32 lt[4][256][8]; the cell bytes of kFrFrames frames (cell_pitch each);
     // the staged blocks of kFrFrames frames (nblocks rows of kFrPitch bytes each)
 };
@@ -550,6 +576,16 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
     for (int e = tid; e < md * kLaDim; e += blockDim.x) {
         const int kk = e / kLaDim, j = e % kLaDim;
         s.la[kk][j] = (uint8_t)((255 - ((j + 1) * (md - kk)) % 255) % 255);
+    }
+    for (int e = tid; e < 32 * 32; e += blockDim.x) {
+        const int i = e >> 5, j = e & 31;
+        uint2 t = make_uint2(0u, 0u);
+        if (i < md && j < md) {
+            const uint32_t l = (uint32_t)((255 - ((j + 1) * (md - i)) % 255) % 255);
+            t.x = (uint32_t)s.exp[l] | ((uint32_t)s.exp[l + 1] << 8) | ((uint32_t)s.exp[l + 2] << 16) | ((uint32_t)s.exp[l + 3] << 24);
+            t.y = (uint32_t)s.exp[l + 4] | ((uint32_t)s.exp[l + 5] << 8) | ((uint32_t)s.exp[l + 6] << 16) | ((uint32_t)s.exp[l + 7] << 24);
+        }
+        s.wsyn[i][j] = t;
     }
     // the four remainder tables interleaved: row (v, j) = T_j[v] (32 bytes) at word (4 v + j) 8, i.e. table j only ever occupies
     // banks 8 j .. 8 j + 7.  In one lookup instruction lane group g reads table i ^ g (the four rows are XORed together, so the

@@ -49,11 +49,16 @@ class RecordExchange:
         self.world = dist.get_world_size() if world is None else world
         info = ctx.info
         self.rec_bytes = info.data_bytes
-        if kind == "window":
+        self.send = None
+        if kind in ("window", "window-direct"):
             box = [ctx.gather_root_create(self.world) if self.rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             if self.rank != 0:
                 ctx.gather_peer_open(self.world, self.rank, box[0])
+                if kind == "window":       # push form: the decode writes locally, a copy engine moves the records to rank 0
+                    dev = torch.device("cuda", torch.cuda.current_device())
+                    self.send = [(torch.empty((n, self.rec_bytes), dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.int32, device=dev))
+                                 for _ in range(2)]
         elif kind == "nccl":
             box = [cb.comm_unique_id() if self.rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
@@ -65,11 +70,16 @@ class RecordExchange:
                           torch.empty((self.world, n), dtype=torch.int32, device=dev)) if self.rank == 0 else (None, None)
                          for _ in range(2)]
         else:
-            raise ValueError("kind must be 'window' or 'nccl'")
+            raise ValueError("kind must be 'window', 'window-direct' or 'nccl'")
 
     def begin(self, step):
         b = step & 1
-        if self.kind == "window":
+        if self.kind == "window" and self.rank != 0:
+            if step > 2:
+                self.ctx.gather_chunks_wait(b)                 # the transfer of step - 2 out of these local buffers is done
+            c, m = self.send[b]
+            return c.data_ptr(), m.data_ptr()
+        if self.kind in ("window", "window-direct"):
             if step > 2:
                 self.ctx.gather_acquire(b, step - 2)           # rank 0 has let go of the records of step - 2
             return self.ctx.gather_slot(b)
@@ -80,7 +90,10 @@ class RecordExchange:
 
     def end(self, step):
         b = step & 1
-        if self.kind == "window":
+        if self.kind == "window" and self.rank != 0:
+            c, m = self.send[b]
+            self.ctx.gather_push(b, c.data_ptr(), m.data_ptr(), self.n, step, step - 2 if step > 2 else 0)
+        elif self.kind in ("window", "window-direct"):
             self.ctx.gather_publish(b, step)
         else:
             c, m = self.send[b]
@@ -91,7 +104,7 @@ class RecordExchange:
     def collect(self, step):
         """rank 0: make the context's stream wait for every rank's records of `step`; returns their device addresses"""
         b = step & 1
-        if self.kind == "window":
+        if self.kind in ("window", "window-direct"):
             self.ctx.gather_wait(b, step)
             return self.ctx.gather_slot(b, 0)                  # rank r's records: + r * slot stride (ctx.gather_slot(b, r))
         self.ctx.gather_chunks_wait(b)
@@ -99,5 +112,5 @@ class RecordExchange:
         return ac.data_ptr(), am.data_ptr()
 
     def release(self, step):
-        if self.kind == "window" and self.rank == 0:
+        if self.kind in ("window", "window-direct") and self.rank == 0:
             self.ctx.gather_release(step & 1, step)
