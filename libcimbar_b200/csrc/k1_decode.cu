@@ -32,21 +32,18 @@ constexpr int kK1Threads = 128;            // 128 threads x 8 px = one full 1024
 #define CB200_K1_MIN_CTAS 4                // resident CTAs per SM the register allocation is capped for (4 -> 128 registers, 5 -> 96)
 #endif
 constexpr int kStageRows = 9;              // raw rows per cell row (stage)
-constexpr int kFrontRows = 4;              // rows of a stage that are requested a whole stage ahead (the other five at the stage barrier)
 constexpr int kMaxW = 1024;
 constexpr int kRastPitch = 144;            // bytes per raster row: 1024 bits + funnel-shift overread pad
 constexpr int kRastWords = kRastPitch / 4;
 
 struct __align__(128) K1Smem {
-    uint8_t ring[kStageRows * kMaxW * 3];     // the raw RGB rows of one stage, filled by TMA (row r at r * row_bytes)
-    uint8_t front2[kFrontRows * kMaxW * 3];   // rows 0..3 of the odd stages (those of the even stages are ring rows 0..3)
+    uint8_t ring[kStageRows * kMaxW * 3];     // the raw RGB rows of ONE stage, filled by TMA (row r at r * row_bytes)
     uint32_t halo[2][kStageRows][kK1Threads]; // per row and thread: gray of px 0,1,6,7 of its eight (what the neighbours' box sums need)
     uint32_t raster[2][10][kRastWords];       // 1-bit threshold rows of the current / previous stage
     uint4 tiles_by_slot[16];                  // (L_lo, L_hi, symbol, 0), indexed by the perfect hash
     uint2 tiles_by_sym[16];                   // (L_lo, L_hi), indexed by symbol (tie-break order of the full search)
     float adjust[256];                        // copy of c_adjust: indexed per lane, so not read through the constant cache
-    unsigned long long full_bar[2];           // front rows of the even / odd stages have landed
-    unsigned long long back_bar[2];           // rows 4..8 of the even / odd stages have landed
+    unsigned long long full_bar[2];
     float ccm[12];                            // CCM variant only: the current frame's 3x3 colour correction matrix
 };
 
@@ -252,7 +249,6 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
 
     if (tid == 0) {
         mbar_init(&s.full_bar[0], 1); mbar_init(&s.full_bar[1], 1);
-        mbar_init(&s.back_bar[0], 1); mbar_init(&s.back_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 16) {
@@ -287,20 +283,11 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         c.u += gridDim.x;
         cursor_unit(c);
     };
-    // the nine source rows of a stage are contiguous in the frame.  They arrive in two bulk copies: rows 0..3 ("front") are
-    // requested at the top of the stage before -- into the buffer the stage two back has finished with -- and rows 4..8
-    // ("back") at the barrier of the stage before, into ring rows 4..8, which are dead from then on.  The front has a whole
-    // stage to arrive, the back the second half of one stage plus the time the next stage spends on its front rows.
-    const uint32_t front_bytes = row_bytes * kFrontRows, back_bytes = stage_bytes - front_bytes;
-    auto issue_front = [&](const Cursor& c, uint32_t i) {
+    // the nine source rows of a stage are contiguous in the frame: one bulk copy into the (single-stage) ring
+    auto issue_stage = [&](const Cursor& c, uint32_t i) {
         unsigned long long* bar = &s.full_bar[i & 1u];
-        mbar_expect_tx(bar, front_bytes);
-        tma_bulk_g2s((i & 1u) ? s.front2 : s.ring, c.src, front_bytes, bar);
-    };
-    auto issue_back = [&](const Cursor& c, uint32_t i) {
-        unsigned long long* bar = &s.back_bar[i & 1u];
-        mbar_expect_tx(bar, back_bytes);
-        tma_bulk_g2s(s.ring + front_bytes, c.src + front_bytes, back_bytes, bar);
+        mbar_expect_tx(bar, stage_bytes);
+        tma_bulk_g2s(s.ring, c.src, stage_bytes, bar);
     };
     // two cursors over that stream, each owned by one thread: thread 0 feeds the shared-memory ring (TMA), the first thread of
     // warp 1 runs l2_ahead stages further ahead and only prefetches into L2 -- the per-stage cursor arithmetic is spread over
@@ -314,7 +301,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
     nxt.u = blockIdx.x; nxt.valid = false; pre.u = blockIdx.x; pre.valid = false;
     if (tid == 0) {
         cursor_unit(nxt);
-        if (nxt.valid) { issue_front(nxt, 0u); issue_back(nxt, 0u); cursor_next(nxt); }
+        if (nxt.valid) { issue_stage(nxt, 0u); cursor_next(nxt); }
     }
     if (tid == pf_tid && l2_ahead > 0) {
         cursor_unit(pre);
@@ -390,14 +377,11 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
 
         for (int k = k0 - 1; k < k1; ++k, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            uint8_t* const frontp = buf ? s.front2 : s.ring;                 // stage rows 0..3
-            auto rowp = [&](int r) -> uint8_t* { return (r < kFrontRows ? frontp : s.ring) + (uint32_t)r * row_bytes; };
+            uint8_t* const ub[3] = {s.ring, s.ring + 3u * row_bytes, s.ring + 6u * row_bytes};   // stage rows 0-2, 3-5, 6-8
             mbar_wait(&s.full_bar[buf], ph);
-            if (tid == 0 && nxt.valid) issue_front(nxt, it + 1u);        // its buffer was last read before the previous barrier
             if (load_only) {                               // tuning only: the stage is dropped as soon as it has landed
-                mbar_wait(&s.back_bar[buf], ph);
                 __syncthreads();
-                if (tid == 0 && nxt.valid) { issue_back(nxt, it + 1u); cursor_next(nxt); }
+                if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u); cursor_next(nxt); }
                 if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
                 continue;
             }
@@ -408,8 +392,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 uint32_t E[kStageRows];
 #pragma unroll
                 for (int r = 0; r < kStageRows; ++r) {
-                    if (r == kFrontRows) mbar_wait(&s.back_bar[buf], ph);
-                    const uint2* rp = reinterpret_cast<const uint2*>(rowp(r)) + 3 * t;
+                    const uint2* rp = reinterpret_cast<const uint2*>(ub[r / 3] + (uint32_t)(r % 3) * row_bytes) + 3 * t;
                     uint2 q0 = rp[0], q1 = rp[1], q2 = rp[2];
                     uint32_t n0, n1, n2, n3, n4, n5, n6, n7;
                     n0 = __dp2a_lo(cRG, q0.x, 32768u); n0 = __dp2a_hi(cB0, q0.x, n0);
@@ -439,11 +422,11 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                     if (t < ncols && NC > 1) {
                         const int x = x0 + kSpacing * t + 1;
                         uint32_t R = carryR, G = carryG, B = carryB;
-                        rgb_row6(rowp(0), x, R, G, B);
-                        rgb_row6(rowp(1), x, R, G, B);
-                        rgb_row6(rowp(2), x, R, G, B);
-                        rgb_row6(rowp(3), x, R, G, B);
-                        rgb_row6(rowp(4), x, R, G, B);
+                        rgb_row6(ub[0], x, R, G, B);
+                        rgb_row6(ub[0] + row_bytes, x, R, G, B);
+                        rgb_row6(ub[0] + 2u * row_bytes, x, R, G, B);
+                        rgb_row6(ub[1], x, R, G, B);
+                        rgb_row6(ub[1] + row_bytes, x, R, G, B);
                         if (CM == 2) cc.means[(size_t)f * (size_t)m.num_cells() + (size_t)(base + t)] = (R / 36u) | ((G / 36u) << 8) | ((B / 36u) << 16);
                         else col = CM == 1 ? best_color_ccm<NC>(s.ccm, mm, R / 36u, G / 36u, B / 36u) : best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
                     }
@@ -451,12 +434,12 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
                 if (k + 1 < k1) {
                     m.row_geom(k + 1, base, ncols, x0);
-                    if (t < ncols) rgb_row6(rowp(8), x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                    if (t < ncols) rgb_row6(ub[2] + 2u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
                 }
             }
             __syncthreads();
             // the raw rows are dead now (gray is in registers, the colour sums are taken): the next stage may overwrite them
-            if (tid == 0 && nxt.valid) { issue_back(nxt, it + 1u); cursor_next(nxt); }
+            if (tid == 0 && nxt.valid) { issue_stage(nxt, it + 1u); cursor_next(nxt); }
             if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
 
             // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
