@@ -139,6 +139,71 @@ def first(*names):
     return None
 
 
+def launch_lists():
+    import collections, csv, re
+    out = []
+    for src, dst, title in (("r2o_launches.csv", "r02_launch_list_ncu.csv", "bench.py --steps 2 --warmup 1 (clean frames)"),
+                            ("r2o_launches_noise.csv", "r02_launch_list_k1x_noise1pct.csv", "bench.py --workload noise1pct --frames 4736 --steps 1 --warmup 1"),
+                            ("r2i_launches.csv", "r02_launch_list_ncu.csv", "bench.py --steps 2 --warmup 1 (clean frames)"),
+                            ("r2i_launches_noise.csv", "r02_launch_list_k1x_noise1pct.csv", "bench.py --workload noise1pct --frames 4736 --steps 1 --warmup 1")):
+        p = os.path.join(GO, src)
+        if not os.path.exists(p) or any(dst in o for o in out):
+            continue
+        rows = [l for l in open(p) if l.startswith('"')]
+        open(os.path.join(PR, dst), "w").write("".join(rows))
+        rd = list(csv.reader(rows))
+        hdr, rd = rd[0], rd[1:]
+        ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+        agg = collections.OrderedDict()
+        for r in rd:
+            n = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("cb200::", "")
+            agg.setdefault(n, []).append(float(r[vi].replace(",", "")) / 1e6)
+        dec = [k for k in agg if k.startswith(("k1_decode", "k_flood", "k_rs_", "k_chunk_mask", "k_pack"))]
+        if not dec:
+            continue
+        steps = max(len(agg[k]) for k in dec)
+        tot = sum(sum(agg[k]) for k in dec) / steps
+        tab = "### `%s` -- %s\n\n| kernel | launches | avg ms (cold, serialised under ncu) | share of the decode step |\n|---|---|---|---|\n" % (dst, title)
+        for k in dec:
+            a = sum(agg[k]) / steps
+            tab += "| %s | %d | %.3f | %.1f %% |\n" % (k, len(agg[k]), a, 100 * a / tot)
+        out.append(tab)
+    return "\n".join(out)
+
+
+def sass_evidence():
+    lib = os.path.join(ROOT, "libcimbar_b200", "lib", "libcb200.so")
+    if not os.path.exists(lib):
+        return ""
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    import collections, re
+    cur, per = None, collections.OrderedDict()
+    pats = ["UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "IDP.2A", "IDP.4A", "IMAD.HI", "REDUX", "POPC", "PRMT", "SHFL", "MATCH", "VOTE", "BAR.SYNC", "STL", "LDL",
+            "HMMA", "UTMALDG", "UTCMMA"]
+    for line in txt.split("\n"):
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = collections.Counter()
+            continue
+        if cur:
+            for p in pats:
+                if re.search(r"\b" + re.escape(p), line):
+                    per[cur][p] += 1
+    want = ["k1_decode_kernelILi4ELb1ELi0", "k_rs_frames", "k_rs_decodeILi1ELb1", "k_flood_walk", "k_flood_raster_fast", "k_deskew", "k_gather_publish", "k_gather_wait"]
+    out = ["## SASS evidence (`cuobjdump -sass libcimbar_b200/lib/libcb200.so`, instruction counts per kernel)", "",
+           "| kernel | " + " | ".join(pats) + " |", "|---|" + "---|" * len(pats)]
+    for fn, c in per.items():
+        if any(w in fn for w in want):
+            short = re.sub(r"^_ZN5cb200\d+", "", fn)[:44]
+            out.append("| `%s` | " % short + " | ".join(str(c.get(p, 0)) for p in pats) + " |")
+    out += ["", "`UBLKCP` = `cp.async.bulk` (TMA bulk copy, K1's stage loads); `SYNCS` = mbarrier operations; `LDGSTS` = `cp.async` (K2's cell-byte",
+            "staging); `IDP.2A/4A` = integer dot products (gray conversion, colour sums); `IMAD.HI` = the bit gather of the threshold",
+            "bits; `REDUX` = warp reductions (heap pop, Berlekamp-Massey, Forney). No tensor-core instruction (`HMMA`/`UTCMMA`) and no",
+            "tensor-map TMA (`UTMALDG`): the path is byte/bit work whose loads are contiguous rows."]
+    return "\n".join(out)
+
+
 def ncu_docs():
     """K1 / K2 / K1x summaries of the `ncu --set full` captures (numbers under ncu are never bench values)"""
     k1 = first("r2o_k1.ncu-rep", "r2i_k1.ncu-rep")
@@ -164,6 +229,10 @@ def ncu_docs():
     if k2e:
         out += ["## K2 `k_rs_frames`, 1 %% wrong tiles (every block is corrected) -- `%s`" % os.path.basename(k2e), ncu_summary(k2e, 4144), "", "```",
                 ncu_lines(k2e, "k_rs_frames", "libcimbar_b200/csrc/k2_rs.cu", 16), "```", ""]
+    ll = launch_lists()
+    if ll:
+        out += ["## Launch lists (`ncu --metrics gpu__time_duration.sum --clock-control none`: every launch of the command)", "", ll, ""]
+    out += [sass_evidence(), ""]
     open(os.path.join(PR, "r02_ncu_summary.md"), "w").write("\n".join(out) + "\n")
     w = []
     if walk:
