@@ -29,14 +29,16 @@ BENCH = {
     "r02_bench_mode4_errors1pct.json": ["r2o_mode4_errors.json", "r2h_mode4_errors.json", "r2b_mode4_errors.json"],
     "r02_bench_mode67.json": ["r2o_mode67.json", "r2h_mode67.json"],
     "r02_bench_fountain_n1.json": ["r2o_fountain_n1.json", "r2h_fountain_n1.json", "r2g_fountain_n1.json"],
-    "r02_bench_fountain_n2_window.json": ["r2j_fountain_n2.json", "r2g_fountain_n2.json"],
+    "r02_bench_fountain_n2_window.json": ["r2p_fountain_n2.json", "r2g_fountain_n2.json"],
     "r02_bench_fountain_n2_nccl.json": ["r2j_fountain_n2_nccl.json", "r2g_fountain_n2_nccl.json"],
-    "r02_bench_fountain_n8.json": ["r2k_fountain_n8.json"],
-    "r02_bench_n2_window.json": ["r2g_n2_window.json"],
-    "r02_bench_n2_nccl.json": ["r2g_n2_nccl.json"],
+    "r02_bench_fountain_n8.json": ["r2q_fountain_n8.json", "r2k_fountain_n8.json"],
+    "r02_bench_n2_window.json": ["r2p_n2_window.json"],
+    "r02_bench_n2_window_direct.json": ["r2p_n2_window-direct.json", "r2g_n2_window.json"],
+    "r02_bench_n2_nccl.json": ["r2p_n2_nccl.json", "r2g_n2_nccl.json"],
     "r02_bench_n2_torch_gather.json": ["r2g_n2_torch.json"],
-    "r02_bench_n4_window.json": ["r2k_n4_window.json"],
-    "r02_bench_n8_window.json": ["r2k_n8_window.json"],
+    "r02_bench_n4_window_direct.json": ["r2k_n4_window.json"],
+    "r02_bench_n8_window.json": ["r2q_n8_window.json"],
+    "r02_bench_n8_window_direct.json": ["r2q_n8_window_direct.json", "r2k_n8_window.json"],
     "r02_bench_n8_nccl.json": ["r2k_n8_nccl.json"],
     "r02_bench_k2_per_warp_kernel_clean.json": ["r2g_k2old_clean.json"],
     "r02_bench_k2_per_warp_kernel_errors1pct.json": ["r2g_k2old_errors1pct.json"],
@@ -107,9 +109,12 @@ def main():
              ("r02_bench_noise1pct_3552frames.json", "same, 3 552 frames"),
              ("r02_bench_k2_per_warp_kernel_clean.json", "A/B: CB200_K2_FRAMES=0 (round-1-style per-warp RS kernel), clean"),
              ("r02_bench_k2_per_warp_kernel_errors1pct.json", "A/B: CB200_K2_FRAMES=0, 1 % wrong tiles"),
-             ("r02_bench_n2_window.json", "N = 2, records through the NVLink window"), ("r02_bench_n2_nccl.json", "N = 2, cb200_gather_chunks (NCCL)"),
+             ("r02_bench_n2_window.json", "N = 2, window, copy-engine push (default)"), ("r02_bench_n2_window_direct.json", "N = 2, window, direct stores of the RS kernel"),
+             ("r02_bench_n2_nccl.json", "N = 2, cb200_gather_chunks (NCCL)"),
              ("r02_bench_n2_torch_gather.json", "N = 2, torch.distributed.gather (round-1 path)"),
-             ("r02_bench_n4_window.json", "N = 4, window"), ("r02_bench_n8_window.json", "N = 8, window"), ("r02_bench_n8_nccl.json", "N = 8, NCCL")]
+             ("r02_bench_n4_window_direct.json", "N = 4, window, direct stores"),
+             ("r02_bench_n8_window.json", "N = 8, window, copy-engine push (default)"), ("r02_bench_n8_window_direct.json", "N = 8, window, direct stores"),
+             ("r02_bench_n8_nccl.json", "N = 8, NCCL")]
     for name, label in order:
         if name in got:
             src, j = got[name]
