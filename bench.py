@@ -439,7 +439,10 @@ def run_ours(args):
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": B * K1_ALGO_BYTES,
                      "traffic": (traffic["dram_bytes_per_frame"] * B if traffic else None),
-                     "traffic_source": (traffic["source"] if traffic else None)},
+                     "traffic_source": (traffic["source"] if traffic else None),
+                     "note": "K1 is bound by instruction issue and dependency latency, not by HBM: the same TMA pipeline with the decode "
+                             "switched off (CB200_K1_L2_AHEAD=4096, tools/k1_sweep.py) copies at 7.4-7.5 TB/s on this GPU "
+                             "(profiles/r02_results.md)"},
         "clocks": sampler.summary(),
     }
     if e2e:
