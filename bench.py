@@ -404,6 +404,22 @@ def run_ours(args):
         one_by_one(hf)                                    # warm-up
         e2e_single = {"api": "cb200_decode_fountain with n = 1 per call (3.1 MB H2D + band-split K1 + RS + D2H, synchronous)",
                       "calls": ns, "pinned": one_by_one(hf), "pageable": one_by_one(pageable)}
+        if MV == 68 and args.workload == "clean" and args.color_correction == 0:
+            # the same call on a frame that needs the exact flood walk (one noise tile, as a camera frame would have many): the walk
+            # is ONE warp per frame -- its throughput comes from thousands of frames in flight, a lone frame pays its whole latency
+            nw = 8
+            walk = np.array(hf[:nw])
+            walk[:, 8:16, 512:520, :] = np.random.default_rng(5).integers(0, 256, (nw, 8, 8, 3), dtype=np.uint8)     # cell 50 of the top row
+            lat, used = [], 0
+            for i in range(nw + 1):
+                t0 = time.perf_counter()
+                _, _, _, ffw = ctx.decode_fountain(walk[i % nw:i % nw + 1])
+                if i:
+                    lat.append(time.perf_counter() - t0)
+                    used += int(ffw[0]) & 1
+            lat.sort()
+            e2e_single["exact_walk_frame"] = {"median_ms": lat[len(lat) // 2] * 1e3, "calls": len(lat), "frames_through_the_walk": used,
+                                              "note": "latency of one frame through K1x; batches: see --workload noise1pct"}
 
     if rank != 0:
         if world > 1:
