@@ -555,6 +555,7 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
     const int md = m.ecc_bytes, msg_len = m.msg_len, nb = m.nblocks, upf = nb / G;
     const int Pw = (md + 3) >> 2, pad = 4 * Pw - md;
     const int words_per_frame = nb * kFrWords, sym_rows = m.cap_sym / kFrBlk, cell_vecs = m.num_cells >> 4;
+    const bool coupled6 = m.legacy != 0;          // (launch condition: symbol_bits + color_bits == 6)
     const int n_groups = (n_frames + kFrFrames - 1) / kFrFrames;
     const uint32_t cellbuf_s = (uint32_t)__cvta_generic_to_shared(cellbuf);
 
@@ -618,7 +619,16 @@ k_rs_frames(const Mode m, const uint8_t* __restrict__ cellvals, const uint16_t* 
             const int r = rem / kFrWords, q = rem - r * kFrWords;
             const uint8_t* cb = cellbuf + fs * cell_pitch;
             uint32_t b0, b1, b2, b3;
-            if (r < sym_rows) {         // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
+            if (coupled6) {             // legacy modes: ONE stream of 6-bit values colour << 4 | symbol (Decoder.h:121-161), MSB first:
+                // stream byte B = bits [8 B, 8 B + 8) of the slot sequence; it always lies inside the two slots s = 8 B / 6, s + 1
+                auto byte6 = [&](const int B) -> uint32_t {
+                    const uint32_t bit0 = 8u * (uint32_t)B, sl = bit0 / 6u, skip = bit0 - 6u * sl;
+                    const uint32_t v0 = cb[idx[sl]] & 63u, v1 = cb[idx[sl + 1]] & 63u;
+                    return (((v0 << 6) | v1) >> (4u - skip)) & 0xFFu;
+                };
+                const int B0 = r * kFrBlk + 4 * q - 1;
+                b0 = q ? byte6(B0) : 0u; b1 = byte6(B0 + 1); b2 = byte6(B0 + 2); b3 = byte6(B0 + 3);
+            } else if (r < sym_rows) {  // two 4-bit symbols per byte, MSB first (Decoder.h:91-92)
                 const uint32_t* ix = reinterpret_cast<const uint32_t*>(idx) + (r * kFrBlk + 4 * q);
                 const uint32_t i0 = q ? ix[-1] : ix[0], i1 = ix[0], i2 = ix[1], i3 = ix[2];
                 b0 = ((cb[i0 & 0xFFFFu] & 15u) << 4) | (cb[i0 >> 16] & 15u);
@@ -775,7 +785,8 @@ cudaError_t k2_rs_fused_launch(const Mode& m, const uint8_t* d_cellvals, const u
     if (b_count < 0) b_count = m.nblocks;
     static const bool frames_off = getenv("CB200_K2_FRAMES") && atoi(getenv("CB200_K2_FRAMES")) == 0;   // tuning / A-B only
     const bool whole = b_begin == 0 && b_count == m.nblocks;
-    if (!frames_off && whole && !m.legacy && m.symbol_bits == 4 && m.color_bits == 2 && m.ecc_block == kFrBlk && m.ecc_bytes <= 32 &&
+    const bool bits_ok = m.symbol_bits == 4 && m.color_bits == 2 && (!m.legacy || (size_t)m.num_cells * 6 == (size_t)m.cap_all * 8);
+    if (!frames_off && whole && bits_ok && m.ecc_block == kFrBlk && m.ecc_bytes <= 32 &&
         m.ecc_bytes <= kLaDim && m.nblocks % 4 == 0 && kFrFrames * (m.nblocks / 4) <= kFrWarps && m.num_cells % 16 == 0 &&
         m.cap_sym % kFrBlk == 0 && (m.nblocks * m.msg_len) % 4 == 0 && ((uintptr_t)d_data & 3u) == 0 && n_frames > 0) {
         const int cell_pitch = m.num_cells;

@@ -25,8 +25,8 @@ BENCH = {
     "r02_bench_noise1pct_3552frames.json": ["r2o_noise_3552.json", "r2i_noise_3552.json", "r2d_noise_3552.json"],
     "r02_bench_color_correction_1.json": ["r2o_cc1.json", "r2h_cc1.json"],
     "r02_bench_color_correction_2.json": ["r2o_cc2.json", "r2h_cc2.json"],
-    "r02_bench_mode4.json": ["r2o_mode4.json", "r2h_mode4.json", "r2d_mode4.json"],
-    "r02_bench_mode4_errors1pct.json": ["r2o_mode4_errors.json", "r2h_mode4_errors.json", "r2b_mode4_errors.json"],
+    "r02_bench_mode4.json": ["r2s_mode4.json", "r2o_mode4.json", "r2h_mode4.json", "r2d_mode4.json"],
+    "r02_bench_mode4_errors1pct.json": ["r2s_mode4_errors.json", "r2o_mode4_errors.json", "r2h_mode4_errors.json", "r2b_mode4_errors.json"],
     "r02_bench_mode67.json": ["r2o_mode67.json", "r2h_mode67.json"],
     "r02_bench_fountain_n1.json": ["r2o_fountain_n1.json", "r2h_fountain_n1.json", "r2g_fountain_n1.json"],
     "r02_bench_fountain_n2_window.json": ["r2p_fountain_n2.json", "r2g_fountain_n2.json"],
@@ -37,6 +37,9 @@ BENCH = {
     "r02_bench_n2_nccl.json": ["r2p_n2_nccl.json", "r2g_n2_nccl.json"],
     "r02_bench_n2_torch_gather.json": ["r2g_n2_torch.json"],
     "r02_bench_n4_window_direct.json": ["r2k_n4_window.json"],
+    "r02_bench_n4_window.json": ["r2r_n4_window.json"],
+    "r02_bench_n1_second_run_with_walk_latency.json": ["r2r_n1.json"],
+    "r02_bench_mode4_k2_per_warp_kernel.json": ["r2s_mode4_k2old.json"],
     "r02_bench_n8_window.json": ["r2q_n8_window.json"],
     "r02_bench_n8_window_direct.json": ["r2q_n8_window_direct.json", "r2k_n8_window.json"],
     "r02_bench_n8_nccl.json": ["r2k_n8_nccl.json"],
@@ -104,6 +107,7 @@ def main():
     order = [("r02_bench_n1.json", "configs[1] clean, mode B, 10 000 frames/step"), ("r02_bench_errors1pct.json", "configs[2] 1 % wrong tiles"),
              ("r02_bench_color_correction_1.json", "colour correction 1"), ("r02_bench_color_correction_2.json", "colour correction 2 (reference default)"),
              ("r02_bench_mode4.json", "configs[4] mode 4C (legacy, RS(155,115)... see file)"), ("r02_bench_mode4_errors1pct.json", "mode 4C, 1 % wrong tiles"),
+             ("r02_bench_mode4_k2_per_warp_kernel.json", "A/B: mode 4C with CB200_K2_FRAMES=0"),
              ("r02_bench_mode67.json", "mode Bm (67)"),
              ("r02_bench_noise1pct_9472frames.json", "1 % noise tiles: every frame through the exact walk, 9 472 frames"),
              ("r02_bench_noise1pct_3552frames.json", "same, 3 552 frames"),
@@ -112,7 +116,7 @@ def main():
              ("r02_bench_n2_window.json", "N = 2, window, copy-engine push (default)"), ("r02_bench_n2_window_direct.json", "N = 2, window, direct stores of the RS kernel"),
              ("r02_bench_n2_nccl.json", "N = 2, cb200_gather_chunks (NCCL)"),
              ("r02_bench_n2_torch_gather.json", "N = 2, torch.distributed.gather (round-1 path)"),
-             ("r02_bench_n4_window_direct.json", "N = 4, window, direct stores"),
+             ("r02_bench_n4_window.json", "N = 4, window, copy-engine push (default)"), ("r02_bench_n4_window_direct.json", "N = 4, window, direct stores"),
              ("r02_bench_n8_window.json", "N = 8, window, copy-engine push (default)"), ("r02_bench_n8_window_direct.json", "N = 8, window, direct stores"),
              ("r02_bench_n8_nccl.json", "N = 8, NCCL")]
     for name, label in order:
@@ -125,6 +129,12 @@ def main():
         cb = j.get("cpu_baseline", {})
         md += ["", "Reference arm (`bench.py --impl reference`, `%s`): **%s frames/s** on %s threads (%s); stages per frame on one thread: %s" % (
             "r02_bench_reference_arm.json", "{:,.0f}".format(j["value"]), cb.get("cores"), cb.get("build", ""), json.dumps(cb.get("stages", {})))]
+    lat = got.get("r02_bench_n1_second_run_with_walk_latency.json")
+    if lat and lat[1].get("e2e_single_frame"):
+        e = lat[1]["e2e_single_frame"]
+        md += ["", "One frame per call (`e2e_single_frame`, `r02_bench_n1_second_run_with_walk_latency.json`): clean frame %.3f ms median from pinned memory "
+               "(%.3f ms from pageable); a frame that needs the exact walk: **%.1f ms** -- the walk is one warp per frame, its throughput comes from "
+               "thousands of frames in flight." % (e["pinned"]["median_ms"], e["pageable"]["median_ms"], (e.get("exact_walk_frame") or {}).get("median_ms", float("nan")))]
     for name in ("r02_bench_fountain_n1.json", "r02_bench_fountain_n2_window.json", "r02_bench_fountain_n2_nccl.json", "r02_bench_fountain_n8.json"):
         if name in got:
             j = got[name][1]
