@@ -39,6 +39,8 @@ def parse_args():
                          "noise1pct = 1%% of the cells replaced by random pixels (forces the exact flood-walk kernel)")
     ap.add_argument("--mode", type=int, default=68, choices=[68, 67, 66, 4, 8],
                     help="cimbar mode_val: 68 = B (headline), 4 = legacy 4C (BASELINE configs[4]), 8 = 8C, 67 = Bm, 66 = Bu")
+    ap.add_argument("--sharpen", action="store_true",
+                    help="decode with should_preprocess=true (CimbReader.cpp:17-46: 3x3 sharpen + block-7 threshold, inside K1)")
     ap.add_argument("--color-correction", type=int, default=0, choices=[0, 1, 2],
                     help="the reference's color_correction argument (0 = headline configuration; 1 = per-frame von Kries; "
                          "2 = per-frame header fit, the payload then carries consecutive fountain headers)")
@@ -172,6 +174,8 @@ def run_ours(args):
     g.manual_seed(0xC1B4 + rank)
     payload = torch.randint(0, 256, (B, info.data_bytes), dtype=torch.uint8, device=dev, generator=g)
     cc_flags = {0: 0, 1: cb.FLAG_CC_SIMPLE, 2: cb.FLAG_CC_FIT}[args.color_correction]
+    if args.sharpen:
+        cc_flags |= cb.FLAG_SHARPEN
     if args.color_correction == 2:
         # a fountain stream: every 625-byte chunk starts with FountainMetadata(encode_id, size, block_id) and the block ids
         # of a frame are consecutive (fountain/FountainMetadata.h:16-31) -- that is what CimbReader::init_ccm predicts from
@@ -437,10 +441,11 @@ def run_ours(args):
         "dtype": "u8 (integer/bitwise; float32 only in the colour classifier, bit-exact vs reference)",
         "data": "synthetic (device-generated: random payload -> RS(155,125) -> interleaved tiles -> RGB8 frames)",
         "config": {"workload": ({"clean": "BASELINE configs[1]", "errors1pct": "BASELINE configs[2] (1% wrong tiles)", "noise1pct": "1% noise tiles (exact-walk path)"}[args.workload]) +
+                   (" with should_preprocess=true (sharpen + block-7 threshold inside K1)" if args.sharpen else "") +
                    ": %d synthetic %dx%d mode-%s frames per GPU per step through the full decode "
                    "(K1 fused threshold+ahash+colour, K1x exact-walk check, RS(%d,%d) with fused de-interleave, chunk masks)" % (
                        B, info.image_size_x, info.image_size_y, MODE_NAMES[MV], info.ecc_block_size, info.ecc_block_size - info.ecc_bytes),
-                   "mode": "%s (%d)" % (MODE_NAMES[MV], MV), "frames_per_gpu_per_step": B, "color_correction": args.color_correction,
+                   "mode": "%s (%d)" % (MODE_NAMES[MV], MV), "frames_per_gpu_per_step": B, "color_correction": args.color_correction, "sharpen": bool(args.sharpen),
                    "l2": "input %.1f GB per step >> 126 MB L2 (no flush needed)" % (B * info.frame_bytes / 1e9),
                    "parallelism": "frames sharded one-per-GPU (dp%d); chunk records to rank 0 by %s" % (world, {
                        None: "nothing (one GPU)", "window": "copy-engine pushes into a window in rank 0's HBM (CUDA IPC peer mapping over NVLink, device-side epochs, side stream: overlaps the next decode)",

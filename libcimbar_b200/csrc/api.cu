@@ -297,21 +297,24 @@ int run_cells(cb200_ctx* c, const uint8_t* d_rgb, int n, uint32_t flags, CellTra
         int rc = ccm_arg(c, cc); if (rc) return rc;
     }
     const bool sharpen = (flags & CB200_FLAG_SHARPEN) != 0;
-    const bool exact_only = sharpen || d_trace != nullptr;     // these go straight to the exact-walk kernel
+    // a cell trace needs the walk itself; CB200_K1_SHARPEN=0 (tests, A/B) sends sharpened frames straight to the exact-walk kernel
+    // as rounds 1-2 did
+    const bool k1_sharpen = !(getenv("CB200_K1_SHARPEN") && atoi(getenv("CB200_K1_SHARPEN")) == 0);
+    const bool exact_only = (sharpen && !k1_sharpen) || d_trace != nullptr;
     CK(cudaMemsetAsync(c->d_dirty, 0, sizeof(uint32_t) * (size_t)n, st), "memset dirty");
     if (c->timing) { c->cur = (int)(c->calls % cb200_ctx::kEvSets); c->calls++; c->ev_count[c->cur] = 0; }
     mark(c);                                   // ev0: before K1
     if (!exact_only) {
         // bands: whole frames when there are enough of them to fill the machine, else split frames into bands of cell rows
-        int ctas = c->sm_count * c->k1_ctas_per_sm;
+        int ctas = c->sm_count * k1_ctas_per_sm(sharpen, c->k1_ctas_per_sm);
         int bands = 1;
         if (n < ctas) { bands = (ctas + n - 1) / n; if (bands > m.cells_y / 4) bands = m.cells_y / 4; if (bands < 1) bands = 1; }
         int units = n * bands;
         int grid = units < ctas ? units : ctas;
-        CK(k1_launch(m, d_rgb, n, bands, grid, c->l2_ahead, c->d_cellvals, c->d_dirty, cc, st), "k1 launch");
+        CK(k1_launch(m, d_rgb, n, bands, grid, c->l2_ahead, sharpen, c->d_cellvals, c->d_dirty, cc, st), "k1 launch");
     }
     mark(c);                                   // ev1: after K1
-    // the sharpen preprocessing (needs_sharpen, CimbReader.cpp:37-40) is only implemented in the exact-walk kernel
+    // frames K1 flagged (or all of them when exact_only) are re-done by the exact walk on the same preprocessing (sharpen or not)
     CK(flood_launch(m, c->flood, d_rgb, n, (flags & CB200_FLAG_NO_FALLBACK) != 0, exact_only, sharpen,
                     c->d_cellvals, c->d_dirty, c->d_flags, d_trace, cc, st), "flood launch");
     mark(c);                                   // ev2: after K1x

@@ -190,6 +190,34 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
     return __reduce_min_sync(0xffffffffu, best_key);
 }
 
+// the same search done by ONE thread for its own cell (used by the sharpen variant, where most cells are inexact): identical
+// keys, so identical results.  o = pixel x of window column 0.
+__device__ __forceinline__ uint32_t thread_symbol_search(const K1Smem& s, uint32_t rbuf, uint32_t o, bool all)
+{
+    uint32_t win[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) win[r] = raster_bits(s, rbuf, r, o) & 0x3FFu;
+    uint32_t best_key = 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        if (q >= 5 && !all) break;
+        const int r0 = (int)((0x200201211ULL >> (4 * q)) & 3u), c0 = (int)((0x020210121ULL >> (4 * q)) & 3u);   // id / 3, id % 3
+        uint32_t b[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) b[r] = (win[r0 + r] >> c0) & 0xFFu;
+        const uint32_t lo = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        const uint32_t hi = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+#pragma unroll 4
+        for (int tile = 0; tile < 16; ++tile) {
+            const uint2 tl = s.tiles_by_sym[tile];
+            const uint32_t d = (uint32_t)(__popc(lo ^ tl.x) + __popc(hi ^ tl.y));
+            const uint32_t key = (d << 8) | ((uint32_t)q << 4) | (uint32_t)tile;
+            best_key = key < best_key ? key : best_key;
+        }
+    }
+    return best_key;
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 // 128 threads (8 px each), 4 CTAs/SM.  The kernel is bound by instruction issue and dependency latency, not by HBM: the same
 // TMA pipeline with the decode switched off copies at 7.4-7.5 TB/s (CB200_K1_L2_AHEAD=4096), with it 5.6 TB/s.  Shared memory
@@ -210,8 +238,16 @@ __device__ __forceinline__ uint32_t warp_symbol_search(const K1Smem& s, uint32_t
 // CCM: the colour classifier runs the reference's float path with a 3x3 colour correction matrix (ccm.cuh) instead of the
 // integer restatement; the matrix of the frame is staged in shared memory when a CTA starts on it.
 // CM = 0: integer classifier; 1: CCM classifier; 2: no decision, the cell's mean colour is stored for the fitted-CCM pass
-template <int NC, bool G1024, int CM>
-__global__ void __launch_bounds__(kK1Threads, CB200_K1_MIN_CTAS)
+// SH: needs_sharpen preprocessing (CimbReader.cpp:17-40): gray -> filter2D [0 -1 0; -1 4.5 -1; 0 -1 0] -> adaptiveThreshold
+// with block 7.  The stage then starts two rows further down (raw rows [y_k+4, y_k+12]), has a second barrier (the
+// sharpened rows' halo pixels come from the neighbours, whose sharpened values need THEIR neighbours' gray first) and keeps
+// seven rows of horizontal sums; three CTAs per SM at up to 168 registers.  Schedule per stage:
+//   A(k), col(k)  ---- barrier 1 (TMA of the next stage) ----  sharpen: S rows a0-1 .. a0+7 from gray rows a0-2 .. a0+8
+//   (two carried), their halo words (s0,s1,s2 | s5,s6,s7) -> smem  ---- barrier 2 ----  7x7 box sums, threshold rows
+//   a0-4 .. a0+4 = y_k .. y_k+8, S(k-1).  Frame borders are never reached: the cell windows stay 3 pixels inside.
+// A lane-level numpy model of exactly this schedule is checked against the oracle in tests/test_k1_sharpen_model.py.
+template <int NC, bool G1024, int CM, bool SH>
+__global__ void __launch_bounds__(kK1Threads, SH ? 3 : CB200_K1_MIN_CTAS)
 k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, int bands, int l2_ahead_arg,
                  uint8_t* __restrict__ cellvals, uint32_t* __restrict__ dirty_flags, const CcmArg cc)
 {
@@ -265,7 +301,10 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
     const bool px_active = t < nthr_px;
     const int tl = (t == 0) ? 0 : t - 1, tr = (t + 1 < nthr_px) ? t + 1 : t;   // halo sources (frame borders are never used)
     const uint32_t cRG = 19596u | (38470u << 16), cB0 = 7470u, c0R = 19596u << 16, cGB = 38470u | (7470u << 16);
-    const uint32_t kBias = 0x7FF37FF3u;         // per half: 0x8000 - 13
+    const uint32_t kBias = SH ? 0x7FE77FE7u : 0x7FF37FF3u;   // per half: 0x8000 - 13 (block 5), 0x8000 - 25 (block 7)
+    constexpr int kBox = SH ? 7 : 5;            // adaptiveThreshold block size
+    constexpr int kFirstRow = SH ? 4 : 2;       // first raw row of a stage relative to the cell row's y
+    uint32_t* const sh_hi = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K1Smem));   // SH only: [kStageRows][kK1Threads], (s5,s6,s7) halo words
     const int narrow = m.cells_x() - 2 * m.corner(), last_cell = m.num_cells() - 1, first_mid = m.top_cells();
 
     // ---- stage stream of this CTA: (unit u, cell row k = k0-1 .. k1-1).  Thread 0 is the TMA producer.
@@ -276,7 +315,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         int f = c.u / bands, b = c.u - f * bands;
         c.k = (m.cells_y() * b) / bands - 1;
         c.kend = (m.cells_y() * (b + 1)) / bands;
-        c.src = rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset() + kSpacing * c.k + 2) * row_bytes;
+        c.src = rgb + (size_t)f * frame_bytes + (size_t)(m.cell_offset() + kSpacing * c.k + kFirstRow) * row_bytes;
     };
     auto cursor_next = [&](Cursor& c) {
         if (++c.k < c.kend) { c.src += stage_bytes; return; }   // consecutive stages are contiguous in the frame
@@ -336,6 +375,22 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
         }
         uint32_t need = __ballot_sync(0xffffffffu, !exact);
         const int lane = tid & 31;
+        if constexpr (SH) {
+            // a sharpened raster rarely reproduces a dictionary tile bit for bit (five cells in six of a clean frame are
+            // inexact), so the one-cell-at-a-time warp search would dominate: with more than two inexact cells in the warp
+            // every thread searches its own cell instead (same keys, same minimum)
+            if (__popc(need) > 2) {
+                if (!exact) {
+                    const bool seed = (cell == 0) | (cell == narrow - 1) | (cell == last_cell) | (cell == last_cell - (narrow - 1)) |
+                                      (cell == first_mid) | (cell == first_mid + m.cells_x() - 1) | (cell == last_cell - first_mid) |
+                                      (cell == last_cell - (first_mid + m.cells_x() - 1));
+                    const uint32_t key = thread_symbol_search(s, rbuf, o - 1u, seed);
+                    sym = key & 15u;
+                    if (((key >> 4) & 15u) != 0u) { dirty = kCellDirty; any_dirty = true; }
+                }
+                need = 0;
+            }
+        }
         while (need) {
             const int leader = __ffs(need) - 1;
             need &= need - 1;
@@ -363,13 +418,15 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
             __syncthreads();
         }
 
-        uint32_t hprev[5][4], Pprev[2][4], nV[4];
+        uint32_t hprev[kBox][4], Pprev[2][4], nV[4];
+        uint32_t Qprev[3][4], prevL = 0, prevR = 0;    // SH: the last three sharpened rows, the halo words of the last gray row
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             nV[j] = kBias;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) hprev[i][j] = 0;
+            for (int i = 0; i < kBox; ++i) hprev[i][j] = 0;
             Pprev[0][j] = Pprev[1][j] = 0;
+            Qprev[0][j] = Qprev[1][j] = Qprev[2][j] = 0;
         }
         uint32_t carryR = 0, carryG = 0, carryB = 0;   // colour sums of row y+1 of the upcoming cell row
         uint32_t col_prev = 0;                         // colour of this thread's cell in the row whose symbols are pending
@@ -410,7 +467,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 }
                 // E_0..E_8 go to the halo buffer of this stage (double buffered: a warp may start A(k+1) while another is still in B(k))
 #pragma unroll
-                for (int r = 0; r < kStageRows; ++r) s.halo[buf][r][t] = E[r];
+                for (int r = 0; r < kStageRows; ++r) s.halo[SH ? 0u : buf][r][t] = E[r];   // (SH: single buffer, two barriers per stage)
             }
 
             // ---------------- col(k): inner 6x6 = rows y+1..y+6 (row y+1 carried from the previous stage), px x+1..x+6
@@ -425,8 +482,10 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                         rgb_row6(ub[0], x, R, G, B);
                         rgb_row6(ub[0] + row_bytes, x, R, G, B);
                         rgb_row6(ub[0] + 2u * row_bytes, x, R, G, B);
-                        rgb_row6(ub[1], x, R, G, B);
-                        rgb_row6(ub[1] + row_bytes, x, R, G, B);
+                        if (!SH) {                     // SH: rows y+1..y+3 were carried, rows y+4..y+6 are stage rows 0..2
+                            rgb_row6(ub[1], x, R, G, B);
+                            rgb_row6(ub[1] + row_bytes, x, R, G, B);
+                        }
                         if (CM == 2) cc.means[(size_t)f * (size_t)m.num_cells() + (size_t)(base + t)] = (R / 36u) | ((G / 36u) << 8) | ((B / 36u) << 16);
                         else col = CM == 1 ? best_color_ccm<NC>(s.ccm, mm, R / 36u, G / 36u, B / 36u) : best_color<NC>(s.adjust, mm, R / 36u, G / 36u, B / 36u);
                     }
@@ -434,7 +493,13 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 carryR = carryG = carryB = 0;          // colour carry for cell row k+1: its row y'+1 = last row of this stage
                 if (k + 1 < k1) {
                     m.row_geom(k + 1, base, ncols, x0);
-                    if (t < ncols) rgb_row6(ub[2] + 2u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                    if (t < ncols) {
+                        if (SH) {                      // its rows y'+1..y'+3 = stage rows 6..8
+                            rgb_row6(ub[2], x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                            rgb_row6(ub[2] + row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                        }
+                        rgb_row6(ub[2] + 2u * row_bytes, x0 + kSpacing * t + 1, carryR, carryG, carryB);
+                    }
                 }
             }
             __syncthreads();
@@ -443,7 +508,7 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
             if (tid == pf_tid && l2_ahead > 0 && pre.valid) { tma_prefetch_l2(pre.src, stage_bytes); cursor_next(pre); }
 
             // ---------------- B(k): 5x5 box sum, threshold, raster rows 1..9 (row 0 = row 9 of the previous stage)
-            {
+            if constexpr (!SH) {
                 uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[buf][0][0]);
                 const uint8_t* prev8 = reinterpret_cast<const uint8_t*>(&s.raster[buf ^ 1u][0][0]);
                 if (px_active) rast8[t] = prev8[9 * kRastPitch + t];
@@ -479,6 +544,67 @@ k1_decode_kernel(const Mode mm, const uint8_t* __restrict__ rgb, int n_frames, i
                 for (int j = 0; j < 4; ++j) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) hprev[i][j] = h[4 + i][j];
+                    Pprev[0][j] = P[7][j]; Pprev[1][j] = P[8][j];
+                }
+            } else {
+                // ---------------- sharpen: S row i = absolute row a0-1+i, Q[i][j] = (s[j], s[j+4]) like P.  Per half:
+                // twice = 9 c - 2 (up + down + left + right) = 2 x the float result; cvRound (half to even) and saturate_cast:
+                // tc = clamp(twice, 0, 510), s = (tc + ((tc >> 1) & 1)) >> 1
+                uint32_t Q[kStageRows][4];
+#pragma unroll
+                for (int i = 0; i < kStageRows; ++i) {
+                    const uint32_t* Pc = (i == 0) ? Pprev[1] : P[i > 0 ? i - 1 : 0];
+                    const uint32_t* Pu = (i == 0) ? Pprev[0] : ((i == 1) ? Pprev[1] : P[i > 1 ? i - 2 : 0]);
+                    const uint32_t* Pd = P[i];
+                    const uint32_t lE = (i == 0) ? prevL : s.halo[0][i > 0 ? i - 1 : 0][tl];
+                    const uint32_t rE = (i == 0) ? prevR : s.halo[0][i > 0 ? i - 1 : 0][tr];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t Pl = (j == 0) ? __byte_perm(lE, Pc[3], 0x5453) : Pc[j > 0 ? j - 1 : 0];   // (gL7, g3)
+                        const uint32_t Pr = (j == 3) ? __byte_perm(Pc[0], rE, 0x3432) : Pc[j < 3 ? j + 1 : 3];   // (g4, gR0)
+                        const uint32_t nbr = Pu[j] + Pd[j] + Pl + Pr;
+                        const uint32_t T = 9u * Pc[j] + (0x08000800u - 2u * nbr);                  // twice + 2048 per half
+                        const uint32_t tc = __vminu2(__vmaxu2(T, 0x08000800u), 0x09FE09FEu) - 0x08000800u;
+                        Q[i][j] = ((tc + ((tc >> 1) & 0x00010001u)) >> 1) & 0x00FF00FFu;
+                    }
+                    s.halo[1][i][t] = __byte_perm(__byte_perm(Q[i][0], Q[i][1], 0x0040), Q[i][2], 0x0410);   // bytes (s0, s1, s2, .)
+                    sh_hi[i * kK1Threads + t] = __byte_perm(__byte_perm(Q[i][1], Q[i][2], 0x0062), Q[i][3], 0x0610);   // (s5, s6, s7, .)
+                }
+                prevL = s.halo[0][kStageRows - 1][tl]; prevR = s.halo[0][kStageRows - 1][tr];
+                __syncthreads();
+                // ---------------- B(k): 7x7 box sum of the sharpened rows, threshold 49 s > sum + 24, raster rows 1..9
+                uint8_t* rast8 = reinterpret_cast<uint8_t*>(&s.raster[buf][0][0]);
+                const uint8_t* prev8 = reinterpret_cast<const uint8_t*>(&s.raster[buf ^ 1u][0][0]);
+                if (px_active) rast8[t] = prev8[9 * kRastPitch + t];
+                uint32_t h[kStageRows][4];
+#pragma unroll
+                for (int i = 0; i < kStageRows; ++i) {
+                    const uint32_t lF = sh_hi[i * kK1Threads + tl], rF = s.halo[1][i][tr];
+                    const uint32_t Qm3 = __byte_perm(lF, Q[i][1], 0x5450), Qm2 = __byte_perm(lF, Q[i][2], 0x5451), Qm1 = __byte_perm(lF, Q[i][3], 0x5452);
+                    const uint32_t Q4 = __byte_perm(Q[i][0], rF, 0x3432), Q5 = __byte_perm(Q[i][1], rF, 0x3532), Q6 = __byte_perm(Q[i][2], rF, 0x3632);
+                    h[i][0] = Qm3 + Qm2 + Qm1 + Q[i][0] + Q[i][1] + Q[i][2] + Q[i][3];
+                    h[i][1] = h[i][0] - Qm3 + Q4;
+                    h[i][2] = h[i][1] - Qm2 + Q5;
+                    h[i][3] = h[i][2] - Qm1 + Q6;
+                    uint32_t tj[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t hold = (i < 7) ? hprev[i < 7 ? i : 0][j] : h[i >= 7 ? i - 7 : 0][j];
+                        nV[j] = nV[j] + hold - h[i][j];
+                        const uint32_t Qc = (i < 3) ? Qprev[i < 3 ? i : 0][j] : Q[i >= 3 ? i - 3 : 0][j];
+                        tj[j] = 49u * Qc + nV[j];             // bit15 / bit31 = (49 s > boxsum + 24)
+                    }
+                    const uint32_t dx = __byte_perm(tj[0], tj[1], 0x7531) & 0x80808080u;
+                    const uint32_t dy = __byte_perm(tj[2], tj[3], 0x7531) & 0x80808080u;
+                    const uint32_t byte = __umulhi(dx, 0x02200440u) + __umulhi(dy, 0x08801100u);
+                    if (px_active) rast8[(i + 1) * kRastPitch + t] = (uint8_t)byte;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) hprev[i < kBox ? i : 0][j] = h[2 + i][j];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) Qprev[i][j] = Q[6 + i][j];
                     Pprev[0][j] = P[7][j]; Pprev[1][j] = P[8][j];
                 }
             }
@@ -543,7 +669,9 @@ cudaError_t k1_colors_launch(const Mode& m, const uint8_t* d_rgb, int n, uint8_t
     return cudaGetLastError();
 }
 
-size_t k1_smem_bytes() { return sizeof(K1Smem); }
+constexpr size_t kSharpenExtraSmem = sizeof(uint32_t) * kStageRows * kK1Threads;   // the second halo word of the sharpened rows
+size_t k1_smem_bytes(bool sharpen) { return sizeof(K1Smem) + (sharpen ? kSharpenExtraSmem : 0); }
+int k1_ctas_per_sm(bool sharpen, int plain) { return sharpen ? 3 : plain; }
 
 cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* tiles_L16)
 {
@@ -551,29 +679,33 @@ cudaError_t k1_init_tables(const float* adjust256, const unsigned long long* til
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_tiles_L, tiles_L16, sizeof(unsigned long long) * 16);
     if (e != cudaSuccess) return e;
-    const int smem_max = (int)sizeof(K1Smem) + 64 * 1024;
-#define CB200_K1_ATTR(NC, G, C) \
-    if ((e = cudaFuncSetAttribute(k1_decode_kernel<NC, G, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
+    const int smem_max = (int)(sizeof(K1Smem) + kSharpenExtraSmem) + 64 * 1024;
+#define CB200_K1_ATTR2(NC, G, C, S) \
+    if ((e = cudaFuncSetAttribute(k1_decode_kernel<NC, G, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) return e;
+#define CB200_K1_ATTR(NC, G, C) CB200_K1_ATTR2(NC, G, C, false) CB200_K1_ATTR2(NC, G, C, true)
     CB200_K1_ATTR(4, true, 0) CB200_K1_ATTR(4, false, 0) CB200_K1_ATTR(8, true, 0) CB200_K1_ATTR(8, false, 0)
     CB200_K1_ATTR(4, true, 1) CB200_K1_ATTR(4, false, 1) CB200_K1_ATTR(8, true, 1) CB200_K1_ATTR(8, false, 1)
     CB200_K1_ATTR(4, true, 2) CB200_K1_ATTR(4, false, 2) CB200_K1_ATTR(8, true, 2) CB200_K1_ATTR(8, false, 2)
 #undef CB200_K1_ATTR
+#undef CB200_K1_ATTR2
     return cudaSuccess;
 }
 
-cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead,
+cudaError_t k1_launch(const Mode& m, const uint8_t* d_rgb, int n_frames, int bands, int grid, int l2_ahead, bool sharpen,
                       uint8_t* d_cellvals, uint32_t* d_dirty, const CcmArg& cc, cudaStream_t stream)
 {
     const int extra = getenv("CB200_K1_EXTRA_SMEM") ? atoi(getenv("CB200_K1_EXTRA_SMEM")) : 0;   // tuning only: lowers CTAs/SM
-    const size_t smem = sizeof(K1Smem) + extra;
+    const size_t smem = k1_smem_bytes(sharpen) + extra;
     const bool g1024 = m.width == 1024 && m.height == 1024 && m.cells_x == 112 && m.cells_y == 112 && m.corner == 6 &&
                        m.cell_offset == 8 && m.symbol_bits == 4;
     const int cm = cc.means ? 2 : (cc.active ? 1 : 0);
-#define CB200_K1_GO(NC, G, C) k1_decode_kernel<NC, G, C><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty, cc)
-#define CB200_K1_CM(NC, G) do { if (cm == 2) CB200_K1_GO(NC, G, 2); else if (cm == 1) CB200_K1_GO(NC, G, 1); else CB200_K1_GO(NC, G, 0); } while (0)
+#define CB200_K1_GO(NC, G, C, S) k1_decode_kernel<NC, G, C, S><<<grid, kK1Threads, smem, stream>>>(m, d_rgb, n_frames, bands, l2_ahead, d_cellvals, d_dirty, cc)
+#define CB200_K1_SH(NC, G, C) do { if (sharpen) CB200_K1_GO(NC, G, C, true); else CB200_K1_GO(NC, G, C, false); } while (0)
+#define CB200_K1_CM(NC, G) do { if (cm == 2) CB200_K1_SH(NC, G, 2); else if (cm == 1) CB200_K1_SH(NC, G, 1); else CB200_K1_SH(NC, G, 0); } while (0)
     if (m.color_bits == 3) { if (g1024) CB200_K1_CM(8, true); else CB200_K1_CM(8, false); }
     else { if (g1024) CB200_K1_CM(4, true); else CB200_K1_CM(4, false); }
 #undef CB200_K1_CM
+#undef CB200_K1_SH
 #undef CB200_K1_GO
     count_launch();
     return cudaGetLastError();

@@ -754,3 +754,60 @@ def test_exact_walk_with_the_literal_pop_forced(cb, monkeypatch):
     assert all(int(x) & cb.FRAME_FALLBACK for x in ff2)
     for f in range(2):
         assert np.array_equal(raw2[f], ORA.decode_raw(m, noisy[f]))
+
+
+# ------------------------------------------------------------------------------------------------ sharpen inside K1
+@pytest.mark.parametrize("mode_val,n", [(68, 3), (68, 640), (4, 5), (8, 480), (67, 4), (67, 640), (66, 7), (66, 500)])
+def test_sharpen_clean_batches_stay_on_k1(cb, mode_val, n):
+    """needs_sharpen preprocessing (CimbReader.cpp:17-46: filter2D 4.5-centre kernel + adaptiveThreshold block 7) runs inside
+    K1 (template SH): clean frames keep their K1 result (no exact walk), in the band-split schedule (few frames) and in the
+    persistent whole-frame schedule (n >= 3 x SMs), for the 1024x1024 geometry and the two others."""
+    m, payloads, frames = synth_frames(mode_val, 4, seed=300 + mode_val)
+    big = np.concatenate([frames] * ((n + 3) // 4))[:n]
+    ctx = cb.Context(mode_val, max_frames=n)
+    raw, ff = ctx.decode_raw(big, flags=cb.FLAG_SHARPEN)
+    assert not ff.any()
+    want = np.stack([ORA.decode_raw(m, fr, sharpen=True) for fr in frames])
+    for f in range(n):
+        assert np.array_equal(raw[f], want[f % 4]), f
+    data, ok, _ = ctx.decode(big, flags=cb.FLAG_SHARPEN)
+    assert ok.all() and np.array_equal(data[:min(n, 4)], payloads[:min(n, 4)])
+    ctx.close()
+
+
+def test_sharpen_mixed_batch_and_the_old_route(cb, monkeypatch):
+    """camera frames in a sharpened batch are flagged by K1 and re-done by the exact walk on the sharpened raster; with
+    CB200_K1_SHARPEN=0 every frame takes that route (rounds 1-2): same bytes either way, and as the oracle's"""
+    m, payloads, frames = synth_frames(68, 3, seed=331)
+    batch = np.stack([frames[0], load_sample("b/ex2434.jpg"), frames[1], load_sample("b/ex380.jpg"), frames[2]])
+    want = [ORA.decode_raw(m, fr, sharpen=True) for fr in batch]
+    ctx = cb.Context(68, max_frames=5)
+    raw, ff = ctx.decode_raw(batch, flags=cb.FLAG_SHARPEN)
+    assert [int(x & cb.FRAME_FALLBACK) for x in ff] == [0, 1, 0, 1, 0]
+    monkeypatch.setenv("CB200_K1_SHARPEN", "0")
+    raw0, ff0 = ctx.decode_raw(batch, flags=cb.FLAG_SHARPEN)
+    monkeypatch.delenv("CB200_K1_SHARPEN")
+    assert all(int(x) & cb.FRAME_FALLBACK for x in ff0)
+    for f in range(5):
+        assert np.array_equal(raw[f], want[f]), f
+        assert np.array_equal(raw0[f], want[f]), f
+    ctx.close()
+
+
+def test_sharpen_with_noise_tiles_and_colour_correction(cb):
+    # noise tiles make some frames dirty under sharpen too; colour correction 1 goes through K1's CCM variant (CM = 1, SH)
+    m, payloads, frames = synth_frames(68, 6, seed=341, error_rate=0.01, noise_tiles=True)
+    clean = synth_frames(68, 2, seed=342)[2]
+    batch = np.concatenate([frames[:3], clean, frames[3:]])
+    ctx = cb.Context(68, max_frames=len(batch))
+    raw, ff = ctx.decode_raw(batch, flags=cb.FLAG_SHARPEN)
+    for f in range(len(batch)):
+        assert np.array_equal(raw[f], ORA.decode_raw(m, batch[f], sharpen=True)), f
+    assert not ff[3] and not ff[4]
+    raw1, ff1 = ctx.decode_raw(batch, flags=cb.FLAG_SHARPEN | cb.FLAG_CC_SIMPLE)
+    try:
+        for f in range(len(batch)):
+            assert np.array_equal(raw1[f], ORA.decode_raw(m, batch[f], sharpen=True, color_correction=1)), f
+    finally:
+        ORA.set_ccm(None)
+    ctx.close()
