@@ -10,6 +10,7 @@
  *   - FloodDecodePositions + std::priority_queue, CellPositions, AdjacentCellFinder, CellDrift
  *   - Interleave, bitbuffer, ahash_result/bit_extractor, reed_solomon_stream, aligned_stream,
  *     escrow_buffer_writer, FountainMetadata
+ *   - the extractor's OpenCV-free pieces: ScanState_114 / ScanState_122, Anchor
  * The OpenCV-dependent files (CimbReader.cpp, CimbDecoder.cpp, Cell.h, bitmatrix.h, average_hash.h,
  * Decoder.h) cannot be compiled here (no C++ OpenCV in the image); those are pinned by the
  * SHA-256 goldens instead (tests/test_oracle_goldens.py).
@@ -26,6 +27,8 @@
 #include "encoder/aligned_stream.h"
 #include "encoder/escrow_buffer_writer.h"
 #include "fountain/FountainMetadata.h"
+#include "extractor/Anchor.h"
+#include "extractor/ScanState.h"
 
 #include <cstdint>
 #include <cstring>
@@ -158,5 +161,22 @@ void ref_md_pack(uint8_t encode_id, unsigned size, uint16_t block_id, uint8_t* o
 unsigned ref_md_file_size(const uint8_t* md6) { FountainMetadata md(reinterpret_cast<const char*>(md6), 6); return md.file_size(); }
 unsigned ref_md_block_id(const uint8_t* md6) { FountainMetadata md(reinterpret_cast<const char*>(md6), 6); return md.block_id(); }
 unsigned ref_md_encode_id(const uint8_t* md6) { FountainMetadata md(reinterpret_cast<const char*>(md6), 6); return md.encode_id(); }
+
+// extractor/ScanState.h: the state machine fed with a pixel sequence; res[i] = process(active[i]), res[n] = the closing process(false)
+void ref_scanstate_run(int kind, const uint8_t* active, int n, int* res)
+{
+	if (kind == 122) { ScanState_122 s; for (int i = 0; i < n; ++i) res[i] = s.process(active[i] != 0); res[n] = s.process(false); }
+	else { ScanState_114 s; for (int i = 0; i < n; ++i) res[i] = s.process(active[i] != 0); res[n] = s.process(false); }
+}
+
+// extractor/Anchor.h: out = {xavg, yavg, xrange, yrange, max_range, size, is_mergeable(b, max_distance)}, then a.merge(b) -> a
+void ref_anchor_ops(int* a, const int* b, int max_distance, long long* out)
+{
+	Anchor A(a[0], a[1], a[2], a[3]), B(b[0], b[1], b[2], b[3]);
+	out[0] = A.xavg(); out[1] = A.yavg(); out[2] = A.xrange(); out[3] = A.yrange(); out[4] = A.max_range();
+	out[5] = (long long)A.size(); out[6] = A.max_range() != 0 ? A.is_mergeable(B, max_distance) : -1;
+	A.merge(B);
+	a[0] = A.x(); a[1] = A.xmax(); a[2] = A.y(); a[3] = A.ymax();
+}
 
 } // extern "C"

@@ -17,6 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SAMPLES = [
     "b/tr_0.png", "b/tr_1.png", "b/tr_2.png", "b/tr_3.png", "b/ex2434.jpg", "b/ex380.jpg",
     "6bit/4color_ecc30_fountain_0.png", "6bit/4_30_f0_627_extract.jpg", "mycell.png",
+    # camera pictures the reference's ScannerTest scans (not extracted: 960x1280 / 1280x960)
+    "6bit/4_30_f0_627.jpg", "6bit/4_30_f2_734.jpg", "6bit/4_30_f2_246.jpg", "6bit/4_30_f1_360.jpg",
 ]
 
 GOLDENS = [  # (sample, mode, ecc, bytes, sha256, source)
@@ -62,6 +64,36 @@ INIT_CCM_GOLDENS = [
      "matrix_str": "[1.6250746, 0.0024788622, -0.45772526;\n -0.29126319, 2.2922182, -0.67037439;\n -1.2192062, -2.7447209, 5.0476217]",
      "source": "src/lib/cimb_translator/test/CimbReaderTest.cpp:239-257"},
 ]
+# ScannerTest: Anchor strings are "xavg+-xrange,yavg+-yrange" (Anchor.h:107-111)
+SCAN_GOLDENS = [
+    {"sample": "6bit/4_30_f0_627.jpg", "source": "src/lib/extractor/test/ScannerTest.cpp:16-72, :136-147",
+     "t1_contains": ["210+-25,912+-0", "195+-25,64+-0", "1039+-23,880+-0"],
+     "t2_contains": ["210+-0,914+-24", "195+-0,61+-25", "1039+-0,887+-23"],
+     "t3_contains": ["210+-23,914+-24", "195+-25,61+-25", "1039+-22,887+-23"],
+     "piecemeal_filtered": "195+-25,61+-25 210+-25,914+-24 1039+-23,887+-23",
+     "cutoff": 1766, "primary": "210+-25,914+-24 195+-25,61+-25 1039+-23,887+-23",
+     "scan": "210+-25,914+-24 195+-25,61+-25 1039+-23,887+-23 1035+-23,68+-24"},
+    {"sample": "6bit/4color_ecc30_fountain_0.png", "source": "src/lib/extractor/test/ScannerTest.cpp:74-92, :164-176",
+     "cutoff": 2268, "primary": "29+-27,29+-27 993+-27,29+-27 29+-27,993+-27",
+     "scan": "29+-27,29+-27 993+-27,29+-27 29+-27,993+-27 993+-27,993+-27"},
+    {"sample": "6bit/4_30_f2_734.jpg", "source": "src/lib/extractor/test/ScannerTest.cpp:94-112",
+     "cutoff": 1575, "primary": "56+-24,166+-25 870+-24,133+-25 137+-20,910+-18",
+     "scan": "56+-24,166+-25 870+-24,133+-25 137+-20,910+-18 837+-18,897+-18"},
+    {"sample": "6bit/4_30_f2_246.jpg", "source": "src/lib/extractor/test/ScannerTest.cpp:114-132",
+     "cutoff": 1606, "primary": "189+-25,899+-23 157+-26,79+-25 924+-18,811+-19",
+     "scan": "189+-25,899+-23 157+-26,79+-25 924+-18,811+-19 911+-18,122+-19"},
+    {"sample": "6bit/4_30_f1_360.jpg", "source": "src/lib/extractor/test/ScannerTest.cpp:149-162",
+     "scan": "41+-24,196+-25 909+-25,183+-25 69+-23,1036+-23 896+-23,1036+-23"},
+]
+# ScannerTest/testSortTopToBottom(.2, .3): Anchor(x, xmax, y, ymax) lists in, strings out
+SORT_GOLDENS = [
+    {"in": [[300, 360, 100, 160], [300, 360, 300, 360], [100, 160, 300, 360]], "out": "330+-30,330+-30 130+-30,330+-30 330+-30,130+-30",
+     "source": "src/lib/extractor/test/ScannerTest.cpp:208-221"},
+    {"in": [[966, 1020, 966, 1020], [966, 1020, 2, 56], [2, 56, 966, 1020]], "out": "993+-27,993+-27 29+-27,993+-27 993+-27,29+-27",
+     "source": "src/lib/extractor/test/ScannerTest.cpp:223-236"},
+    {"in": [[383, 437, 994, 1048], [395, 447, 107, 157], [1250, 1296, 124, 170]], "out": "421+-26,132+-25 1273+-23,147+-23 410+-27,1021+-27",
+     "source": "src/lib/extractor/test/ScannerTest.cpp:238-251"},
+]
 # color_correctionTest/testTransform (src/lib/chromatic_adaptation/test/color_correctionTest.cpp:14-30)
 ADAPTATION_GOLDEN = {"actual": [192, 255, 255], "desired": [255, 255, 255],
                      "matrix_str": "[1.0655777, 0.2109226, -0.013239831;\n 0.023168325, 0.98723376, -0.0046780901;\n 0, 0, 1]",
@@ -83,7 +115,7 @@ def main():
         sys.exit("needs /root/reference")
     manifest = {"cv2": cv2.__version__, "samples": {}, "goldens": [], "cv_pins": {}, "ccm_goldens": CCM_GOLDENS,
                 "adaptation_golden": ADAPTATION_GOLDEN, "moore_penrose_goldens": MOORE_PENROSE_GOLDENS,
-                "init_ccm_goldens": INIT_CCM_GOLDENS}
+                "init_ccm_goldens": INIT_CCM_GOLDENS, "scan_goldens": SCAN_GOLDENS, "sort_goldens": SORT_GOLDENS}
     for s in SAMPLES:
         dst = os.path.join(HERE, s.replace("/", "__"))
         shutil.copyfile(os.path.join(REF, "samples", s), dst)
