@@ -140,8 +140,8 @@ int cb200_decode_fountain_from_dev(cb200_ctx* ctx, const uint8_t* d_rgb, int n, 
 
    Replaces: Deskewer::deskew (src/lib/extractor/Deskewer.h:25-40) = cv::getPerspectiveTransform(corners, outputPoints) +
    cv::warpPerspective(img, out, transform, size, cv::INTER_LINEAR) to the mode's image size, as Extractor::extract calls it
-   with the four anchor centres Scanner found (src/lib/extractor/Extractor.h:30-46).  The anchor scan stays on the host: the
-   caller supplies the corners (order: top-left, top-right, bottom-left, bottom-right, as Corners::all()).
+   with the four anchor centres Scanner found (src/lib/extractor/Extractor.h:30-46).  Here the caller supplies the corners
+   (cb200_scan below finds them on the device) (order: top-left, top-right, bottom-left, bottom-right, as Corners::all()).
    OpenCV's arithmetic is restated bit for bit (pinned against cv2 in tests/test_deskew.py). */
 
 /* cv::getPerspectiveTransform(src, dst): 4 points each (x, y pairs) -> 3x3 double, row-major.  Host only. */
@@ -156,6 +156,39 @@ int cb200_deskew(cb200_ctx* ctx, const uint8_t* src, int src_w, int src_h, int n
    (n x 8 floats) in, fountain chunks out; the deskewed frames stay on the device.  Outputs as cb200_decode_fountain. */
 int cb200_extract_decode_fountain(cb200_ctx* ctx, const uint8_t* src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
                                   uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
+
+/* the same with the camera images already in device memory */
+int cb200_extract_decode_fountain_dev(cb200_ctx* ctx, const uint8_t* d_src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
+                                      uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags);
+
+/* ---- extractor: the anchor scan -------------------------------------------------------------------------
+
+   Replaces: Scanner(img).scan() (src/lib/extractor/Scanner.h:168-174 constructor = preprocess_image(fast): cvtColor(RGB2GRAY) +
+   GaussianBlur + Otsu threshold, :146-166, :124-128; Scanner.cpp:182-199 scan = scan_primary + add_bottom_right_corner) for a batch
+   of n camera pictures of w x h RGB8, tightly packed.  Results in host memory:
+     anchors: n x 4 x 4 int32 = (x, xmax, y, ymax) of each Anchor (Anchor.h:13-18) in the reference's order top-left, top-right,
+              bottom-left, bottom-right; entries beyond count[i] are zero.  May be NULL.
+     count:   n int32: anchors found (0..4; Extractor::extract needs 4), or -1 if one of the scan's fixed-capacity lists
+              overflowed on that picture (thousands of pattern hits: not a photograph of a cimbar code) -- reported, never guessed
+     cutoff:  n uint32: filter_candidates' size cutoff (Scanner.cpp:83-105).  May be NULL.
+   OpenCV's arithmetic (8-bit GaussianBlur in fixed point with the 3/5/7/9-tap table, Otsu in double precision) and libstdc++'s
+   std::sort are restated bit for bit (tests/test_scan_oracle.py pins the CPU restatement to cv2 and to every golden string of
+   extractor/test/ScannerTest.cpp; tests/test_gpu_scan.py compares the device with it).  Pictures whose short side is 4500 pixels
+   or more (a 17-tap Gaussian) or less than 60 are rejected with CB200_ERR_ARG. */
+int cb200_scan(cb200_ctx* ctx, const uint8_t* pictures, int w, int h, int n, int32_t* anchors, int32_t* count, uint32_t* cutoff);
+int cb200_scan_dev(cb200_ctx* ctx, const uint8_t* d_pictures, int w, int h, int n, int32_t* anchors, int32_t* count, uint32_t* cutoff);
+/* what the last scan call of this context computed on the way: the blurred gray pictures (n x h x w bytes) and their Otsu
+   thresholds (Scanner's binarised image is blurred > threshold).  Either pointer may be NULL.  For tests and diagnostics. */
+int cb200_scan_blurred(cb200_ctx* ctx, uint8_t* blurred_out, int32_t* thresholds_out, int w, int h, int n);
+/* Extractor::extract (src/lib/extractor/Extractor.h:30-46) + Decoder::decode_fountain for n camera pictures in host memory:
+   scan -> Corners (the anchors' centres) -> deskew to the mode's frame size -> decode; one H2D copy of the pictures, nothing
+   but anchors and chunks comes back.  extract_status: n int32 with the reference's return values -- 0 FAILURE (fewer than four
+   anchors; no chunks), 1 SUCCESS, 2 NEEDS_SHARPEN (Corners::is_granular_scale false: the caller of the reference then decodes
+   with should_preprocess = true, i.e. CB200_FLAG_SHARPEN) -- or -1 for a capacity overflow (see cb200_scan).  `flags` applies
+   to the whole batch.  The other outputs are as cb200_decode_fountain. */
+int cb200_scan_extract_decode_fountain(cb200_ctx* ctx, const uint8_t* pictures, int w, int h, int n, uint32_t flags,
+                                       uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags,
+                                       int32_t* extract_status);
 
 /* per-cell record of the exact flood walk: what CimbReader::read() hands back, step by step
    (src/lib/cimb_translator/CimbReader.cpp:139-162, PositionData.h:4-9) */

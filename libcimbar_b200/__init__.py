@@ -26,7 +26,8 @@ EXPORTS = [
     "cb200_mode_info", "cb200_interleave_indices", "cb200_encode_cells_dev", "cb200_set_timing", "cb200_get_timing", "cb200_decode_cells",
     "cb200_sink_create", "cb200_sink_create_wirehair", "cb200_sink_destroy", "cb200_sink_decode_frame", "cb200_sink_ingest", "cb200_sink_file_size",
     "cb200_sink_file_read", "cb200_selfcheck", "cb200_set_ccm", "cb200_get_ccm", "cb200_launch_count", "cb200_decode_fountain_from_dev", "cb200_perspective_transform", "cb200_deskew_dev", "cb200_deskew",
-    "cb200_extract_decode_fountain", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
+    "cb200_extract_decode_fountain", "cb200_extract_decode_fountain_dev", "cb200_scan", "cb200_scan_dev", "cb200_scan_blurred",
+    "cb200_scan_extract_decode_fountain", "cb200_decode_cells_means", "cb200_fit_ccm", "cb200_palette_color",
     "cb200_gather_root_create", "cb200_gather_peer_open", "cb200_gather_slot", "cb200_gather_publish", "cb200_gather_push", "cb200_gather_wait",
     "cb200_gather_release", "cb200_gather_acquire",
     "cb200_gather_status", "cb200_comm_unique_id", "cb200_comm_init", "cb200_gather_chunks", "cb200_gather_chunks_wait",
@@ -99,6 +100,11 @@ def load_library():
     lib.cb200_deskew_dev.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp, u8p]
     lib.cb200_deskew.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp, u8p]
     lib.cb200_extract_decode_fountain.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, u8p, u32p, u32p, u8p]
+    lib.cb200_extract_decode_fountain_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, u8p, u32p, u32p, u8p]
+    lib.cb200_scan.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.cb200_scan_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.cb200_scan_blurred.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    lib.cb200_scan_extract_decode_fountain.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_uint32, vp, vp, vp, vp, vp]
     lib.cb200_decode_cells_means.argtypes = [vp, u8p, C.c_int, C.c_uint32, u8p, vp, vp]
     lib.cb200_fit_ccm.argtypes = [vp, u8p, u8p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.cb200_palette_color.argtypes = [C.c_int, C.c_uint, C.c_int, u8p]
@@ -252,6 +258,41 @@ class Context:
         _check(self.lib.cb200_extract_decode_fountain(self._h, src.ctypes.data, w, h, n, cr.ctypes.data, flags, chunks.ctypes.data,
                                                       count.ctypes.data, mask.ctypes.data, ff.ctypes.data))
         return chunks, count, mask, ff
+
+    def scan(self, pictures):
+        """Scanner(img).scan() on the device for pictures (n, h, w, 3) or (h, w, 3) uint8 ->
+        anchors (n, 4, 4) int32 rows of (x, xmax, y, ymax), count (n,) int32 (-1: capacity overflow), cutoff (n,) uint32"""
+        pics = np.ascontiguousarray(pictures, dtype=np.uint8)
+        if pics.ndim == 3:
+            pics = pics[None]
+        n, h, w, _ = pics.shape
+        anchors = np.zeros((n, 4, 4), dtype=np.int32)
+        count = np.zeros(n, dtype=np.int32)
+        cutoff = np.zeros(n, dtype=np.uint32)
+        _check(self.lib.cb200_scan(self._h, pics.ctypes.data, w, h, n, anchors.ctypes.data, count.ctypes.data, cutoff.ctypes.data))
+        return anchors, count, cutoff
+
+    def scan_blurred(self, n, h, w):
+        """the blurred gray pictures and Otsu thresholds of the last scan call"""
+        blurred = np.zeros((n, h, w), dtype=np.uint8)
+        thr = np.zeros(n, dtype=np.int32)
+        _check(self.lib.cb200_scan_blurred(self._h, blurred.ctypes.data, thr.ctypes.data, w, h, n))
+        return blurred, thr
+
+    def scan_extract_decode_fountain(self, pictures, flags=0):
+        """Extractor::extract + Decoder::decode_fountain: camera pictures in, chunks out -> (chunks, count, mask, frame_flags, extract_status)"""
+        pics = np.ascontiguousarray(pictures, dtype=np.uint8)
+        if pics.ndim == 3:
+            pics = pics[None]
+        n, h, w, _ = pics.shape
+        chunks = np.zeros((n, self.info.chunks_per_frame, self.info.chunk_size), dtype=np.uint8)
+        count = np.zeros(n, dtype=np.uint32)
+        mask = np.zeros(n, dtype=np.uint32)
+        ff = np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.int32)
+        _check(self.lib.cb200_scan_extract_decode_fountain(self._h, pics.ctypes.data, w, h, n, flags, chunks.ctypes.data, count.ctypes.data,
+                                                           mask.ctypes.data, ff.ctypes.data, status.ctypes.data))
+        return chunks, count, mask, ff, status
 
     def decode_cells(self, rgb, flags=0):
         """exact flood walk with per-cell trace (order, x, y, drift_offset, distance) -- CimbReader semantics"""

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libcb200.so")
 SOURCES = ["api.cu", "k1_decode.cu", "k1x_flood.cu", "k2_rs.cu", "render.cu", "encode.cu", "host_sink.cu", "ccm.cu",
-           "gather.cu", "deskew.cu"]
+           "gather.cu", "deskew.cu", "scan.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 NVCC_FLAGS += os.environ.get("CB200_NVCC_EXTRA", "").split()      # tuning only: -D switches of compile-time variants (A/B on the GPU box)
 

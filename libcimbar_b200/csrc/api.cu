@@ -482,7 +482,7 @@ int cb200_destroy(cb200_ctx* c)
     if (c->h_ccm) cudaFreeHost(c->h_ccm);
     if (c->ccm_ev) cudaEventDestroy(c->ccm_ev);
     gather_destroy(c->gather);
-    deskew_destroy(c->deskew);
+    deskew_destroy(c->deskew); scan_destroy(c->scan);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;

@@ -13,8 +13,10 @@ int fail(int code, const std::string& msg);
 int fail_cuda(cudaError_t e, const char* what);
 struct GatherState;      // gather.cu
 struct DeskewState;      // deskew.cu
+struct ScanScratch;      // scan.cu
 void gather_destroy(GatherState* g);
 void deskew_destroy(DeskewState* d);
+void scan_destroy(ScanScratch* s);
 }  // namespace cb200
 #define CK(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cb200::fail_cuda(e__, what); } while (0)
 
@@ -65,4 +67,5 @@ struct cb200_ctx {
     cudaEvent_t ccm_ev = nullptr;    // recorded after the D2H copies of the last batch's CCM (ccm_resolve waits on it)
     cb200::GatherState* gather = nullptr;   // multi-GPU chunk-record window (gather.cu)
     cb200::DeskewState* deskew = nullptr;   // extractor scratch (deskew.cu)
+    cb200::ScanScratch* scan = nullptr;     // anchor-scan scratch (scan.cu)
 };

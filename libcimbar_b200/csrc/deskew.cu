@@ -230,10 +230,11 @@ int cb200_deskew(cb200_ctx* c, const uint8_t* src, int src_w, int src_h, int n, 
     return CB200_OK;
 }
 
-int cb200_extract_decode_fountain(cb200_ctx* c, const uint8_t* src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
-                                  uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags)
+// the pictures are already in device memory (the scan entry points stage them once for scan + deskew)
+int cb200_extract_decode_fountain_dev(cb200_ctx* c, const uint8_t* d_src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
+                                      uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags)
 {
-    if (!c || !src || !corners || !chunks_out || !chunk_count || n < 0 || n > c->max_frames) return fail(CB200_ERR_ARG, "bad arguments");
+    if (!c || !d_src || !corners || !chunks_out || !chunk_count || n < 0 || n > c->max_frames) return fail(CB200_ERR_ARG, "bad arguments");
     if (n == 0) return CB200_OK;
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     const Mode& m = c->mode;
@@ -245,13 +246,24 @@ int cb200_extract_decode_fountain(cb200_ctx* c, const uint8_t* src, int src_w, i
     for (int f = 0; f < n; ++f) {
         int rc = cb200_perspective_transform(corners + (size_t)f * 8, outp, m9.data() + (size_t)f * 9); if (rc) return rc;
     }
-    const size_t sb = (size_t)n * src_w * src_h * 3, db = (size_t)n * m.width * m.height * 3;
-    if (sb > d->src_bytes) { cudaFree(d->d_src); d->d_src = nullptr; d->src_bytes = 0; CK(cudaMalloc(&d->d_src, sb), "cudaMalloc deskew source"); d->src_bytes = sb; }
+    const size_t db = (size_t)n * m.width * m.height * 3;
     if (db > d->dst_bytes) { cudaFree(d->d_dst); d->d_dst = nullptr; d->dst_bytes = 0; CK(cudaMalloc(&d->d_dst, db), "cudaMalloc deskew output"); d->dst_bytes = db; }
-    CK(cudaMemcpyAsync(d->d_src, src, sb, cudaMemcpyHostToDevice, c->stream), "H2D camera frames");
-    int rc = cb200_deskew_dev(c, d->d_src, src_w, src_h, n, m9.data(), d->d_dst); if (rc) return rc;
+    int rc = cb200_deskew_dev(c, d_src, src_w, src_h, n, m9.data(), d->d_dst); if (rc) return rc;
     // the deskewed frames never leave the device: straight into the decode
     return cb200_decode_fountain_from_dev(c, d->d_dst, n, flags, chunks_out, chunk_count, chunk_mask, frame_flags);
+}
+
+int cb200_extract_decode_fountain(cb200_ctx* c, const uint8_t* src, int src_w, int src_h, int n, const float* corners, uint32_t flags,
+                                  uint8_t* chunks_out, uint32_t* chunk_count, uint32_t* chunk_mask, uint8_t* frame_flags)
+{
+    if (!c || !src || !corners || !chunks_out || !chunk_count || n < 0 || n > c->max_frames) return fail(CB200_ERR_ARG, "bad arguments");
+    if (n == 0) return CB200_OK;
+    CK(cudaSetDevice(c->device), "cudaSetDevice");
+    DeskewState* d = dstate(c);
+    const size_t sb = (size_t)n * src_w * src_h * 3;
+    if (sb > d->src_bytes) { cudaFree(d->d_src); d->d_src = nullptr; d->src_bytes = 0; CK(cudaMalloc(&d->d_src, sb), "cudaMalloc deskew source"); d->src_bytes = sb; }
+    CK(cudaMemcpyAsync(d->d_src, src, sb, cudaMemcpyHostToDevice, c->stream), "H2D camera frames");
+    return cb200_extract_decode_fountain_dev(c, d->d_src, src_w, src_h, n, corners, flags, chunks_out, chunk_count, chunk_mask, frame_flags);
 }
 
 }  // extern "C"
