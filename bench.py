@@ -50,6 +50,8 @@ def parse_args():
                          "the RS kernels store straight into that window (cb200_gather_slot / publish); nccl = cb200_gather_chunks "
                          "(ncclSend/Recv on a side stream, double buffered); torch = torch.distributed.gather on the decode stream "
                          "(round-1 behaviour)")
+    ap.add_argument("--camera", action="store_true",
+                    help="the camera path: photographs -> scan -> deskew -> decode (libcimbar_b200/camera_bench.py); one GPU")
     ap.add_argument("--fountain", action="store_true",
                     help="BASELINE configs[3]: fountain-encoded file, frames sharded over the ranks, records to rank 0, wirehair "
                          "reassembly checked by SHA-256 (libcimbar_b200/fountain_bench.py)")
@@ -655,6 +657,9 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.camera:
+        from libcimbar_b200 import camera_bench
+        camera_bench.run(args, ClockSampler, measured_peak_gbs)
     elif args.fountain:
         from libcimbar_b200 import fountain_bench
         fountain_bench.run(args)

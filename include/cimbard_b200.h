@@ -3,10 +3,9 @@
    The first six declarations are the reference's own, name and signature (src/lib/cimbar_js/cimbar_recv_js.h:11-39): a
    caller that binds cimbard_* from the reference's library binds the same symbols here.  Not provided: the zstd read-back
    (cimbard_get_filename, cimbard_get_decompress_bufsize, cimbard_decompress_read -- consumers of the finished file) and
-   cimbard_get_debug.  The anchor scan is not part of this library: cimbard_scan_extract_decode decodes an
-   image that already has the mode's size (`cimbar --no-deskew`) and returns -3, the reference's "extract failed", for any
-   other; cimbard_b200_extract_decode takes the four anchor centres from the caller's scanner and does deskew + decode on the
-   GPU. */
+   cimbard_get_debug.  cimbard_scan_extract_decode scans, extracts and decodes on the GPU exactly as the reference does on
+   the CPU (Scanner + Extractor + Decoder with should_preprocess = true), -3 when fewer than four anchors are found;
+   cimbard_b200_extract_decode is for a caller with a scanner of its own, or with `cimbar --no-deskew` input. */
 #ifndef CIMBARD_B200_H
 #define CIMBARD_B200_H
 
@@ -21,7 +20,7 @@ unsigned cimbard_get_report(unsigned char* buff, unsigned maxlen);
 /* cimbar_recv_js.h:16: fountain_chunks_per_frame * fountain_chunk_size of the configured mode */
 int cimbard_get_bufsize();
 /* cimbar_recv_js.h:17: format 3 = RGB, 4 = RGBA (<= 0: 3).  Returns the good bytes written to bufspace (whole chunks, packed
-   from the front), -1 bad image size, -2 bufsize too small, -3 the image is not an extracted frame, -4 unsupported format
+   from the front), -1 bad image size, -2 bufsize too small, -3 extract failed (fewer than four anchors), -4 unsupported format
    (the YUV layouts 12 / 420), -6 GPU error (text through cimbard_get_report) */
 int cimbard_scan_extract_decode(const unsigned char* imgdata, unsigned imgw, unsigned imgh, int format, unsigned char* bufspace, unsigned bufsize);
 /* cimbar_recv_js.h:21: chunks from cimbard_scan_extract_decode; > 0 = id of a completed file, 0 = progress, negative = error
@@ -34,7 +33,8 @@ int cimbard_configure_decode(int mode_val);
 
 /* ---- additions ---- */
 /* as cimbard_scan_extract_decode, with the four anchor centres of the camera image (x, y pairs: top-left, top-right,
-   bottom-left, bottom-right) found by the caller's scanner; NULL = the image is an extracted frame */
+   bottom-left, bottom-right) found by the caller's scanner; NULL = the image is an extracted frame of the mode's size and is
+   decoded as it is (no scan, no warp; -3 for any other size) */
 int cimbard_b200_extract_decode(const unsigned char* imgdata, unsigned imgw, unsigned imgh, int format, const float* corners,
                                 unsigned char* bufspace, unsigned bufsize);
 /* the reassembled file of a completed id (size >= cimbard_get_filesize(id)): bytes copied, -1 unknown id, -2 size too small */

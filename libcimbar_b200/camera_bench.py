@@ -1,0 +1,144 @@
+"""The camera path: photographs in, fountain chunks out (the extractor in front of the decode).
+
+    python bench.py --camera [--frames B] [--steps K] [--warmup W]
+
+One step = B camera pictures (the reference's own sample photographs of mode-4C codes, 960 x 1280, tests/golden/, replicated)
+through what the reference's facade does per picture (cimbar_recv_js.cpp:152-189): Scanner::scan -> Corners -> Deskewer::deskew
+-> Decoder::decode_fountain(should_preprocess = true):
+  * `value`: pictures/s with the pictures resident in HBM -- cb200_scan_dev + cb200_extract_decode_fountain_dev, CUDA events,
+    incl. the one host round trip of 64 B of anchors per picture between scan and deskew;
+  * `e2e`: the same through cb200_scan_extract_decode_fountain with pinned HOST pictures (H2D of 3.7 MB per picture inside);
+  * `roofline`: k_scan_blur (gray + Gaussian + histogram), algorithmic 4 B per pixel (3 read, 1 written), HBM-bound;
+  * `cpu_baseline`: the CPU restatement of the scan (oracle/scan_oracle.c) on one core, per picture, next to the GPU's.
+Photographs need the exact flood walk (K1x), so the decode leg is the walk's throughput, not K1's."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def load_pictures():
+    import cv2
+    out = []
+    for name in ("6bit__4_30_f0_627.jpg", "6bit__4_30_f2_246.jpg"):
+        img = cv2.imread(os.path.join(ROOT, "tests", "golden", name), cv2.IMREAD_COLOR)
+        out.append(np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_BGR2RGB)))
+    return out
+
+
+def run(args, ClockSampler, measured_peak_gbs):
+    import torch
+    import libcimbar_b200 as cb
+    import ctypes as C
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    B = min(args.frames, 256)
+    K, W = args.steps, max(args.warmup, 3)
+    pics = load_pictures()
+    h, w = pics[0].shape[:2]
+    batch = np.stack([pics[i % len(pics)] for i in range(B)])
+    host = torch.from_numpy(batch).pin_memory()
+    d_pics = host.to(dev)
+    ctx = cb.Context(4, max_frames=B)
+    info = ctx.info
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    anchors = np.zeros((B, 4, 4), np.int32); count = np.zeros(B, np.int32); cutoff = np.zeros(B, np.uint32)
+    chunks = np.zeros((B, info.chunks_per_frame, info.chunk_size), np.uint8)
+    ccount = np.zeros(B, np.uint32); cmask = np.zeros(B, np.uint32); ff = np.zeros(B, np.uint8); status = np.zeros(B, np.int32)
+    flags = cb.FLAG_SHARPEN
+    lib, hnd = ctx.lib, ctx._h
+
+    def step_dev():
+        cb._check(lib.cb200_scan_dev(hnd, d_pics.data_ptr(), w, h, B, anchors.ctypes.data, count.ctypes.data, cutoff.ctypes.data))
+        corners = ((anchors[:, :, 0] + anchors[:, :, 1]) // 2, (anchors[:, :, 2] + anchors[:, :, 3]) // 2)
+        cr = np.ascontiguousarray(np.stack(corners, axis=2).astype(np.float32).reshape(B, 8))
+        cb._check(lib.cb200_extract_decode_fountain_dev(hnd, d_pics.data_ptr(), w, h, B, cr.ctypes.data, flags, chunks.ctypes.data,
+                                                        ccount.ctypes.data, cmask.ctypes.data, ff.ctypes.data))
+
+    def step_e2e():
+        cb._check(lib.cb200_scan_extract_decode_fountain(hnd, host.data_ptr(), w, h, B, flags, chunks.ctypes.data, ccount.ctypes.data,
+                                                         cmask.ctypes.data, ff.ctypes.data, status.ctypes.data))
+
+    for _ in range(W):
+        step_dev()
+    torch.cuda.synchronize()
+    assert (count == 4).all(), "scan did not find four anchors in every sample photograph"
+    sampler = ClockSampler(0)
+    sampler.start()
+    ctx.set_timing(True)
+    launches0 = cb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    scan_ms = []
+    for _ in range(K):
+        step_dev()
+        scan_ms.append(ctx.get_timing(1))           # the scan's event set (the decode's is the latest)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = cb.launch_count() - launches0
+    dev_ms = e0.elapsed_time(e1)
+    ctx.set_timing(False)
+    good_chunks = int(ccount.sum())
+    for _ in range(2):
+        step_e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    assert (status > 0).all()
+
+    blur_ms = sum(r[0] for r in scan_ms) / len(scan_ms)
+    otsu_ms = sum(r[1] for r in scan_ms) / len(scan_ms)
+    anch_ms = sum(r[2] for r in scan_ms) / len(scan_ms)
+    peak, peak_src = measured_peak_gbs()
+    algo = B * w * h * 4
+    achieved = algo / (blur_ms * 1e-3) / 1e9
+
+    # CPU: the restatement of the scan on one core (oracle/scan_oracle.c), a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from scan_oracle_lib import ScanOracle
+        so = ScanOracle()
+        t0 = time.perf_counter()
+        reps = 6
+        for i in range(reps):
+            a, _ = so.scan(pics[i % len(pics)])
+            assert len(a) == 4
+        cpu_s = (time.perf_counter() - t0) / reps
+        cpu = {"value": 1.0 / cpu_s, "unit": "pictures/s (scan only)", "cores": 1, "kind": "port",
+               "sample": "%d scans of the two sample photographs, oracle/scan_oracle.c (gray + blur + Otsu + scan), one thread" % reps,
+               "gpu_scan_pictures_per_s": B / ((blur_ms + otsu_ms + anch_ms) * 1e-3)}
+    out = {
+        "metric": "camera pictures/s through scan + extract + decode (mode 4C photographs, should_preprocess = true)",
+        "value": B * K / (dev_ms * 1e-3), "unit": "pictures/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 (integer; double only in Otsu and the perspective transform, bit-exact vs OpenCV)",
+        "data": "the reference's sample photographs 6bit/4_30_f0_627.jpg and 4_30_f2_246.jpg (960 x 1280), replicated",
+        "config": {"workload": "camera path (SURVEY 8f-2): %d photographs of %d x %d per step: Scanner::scan (k_scan_blur, k_scan_otsu, "
+                               "k_scan_anchors) -> corners -> k_deskew -> decode (K1 sharpen + exact walk K1x + RS)" % (B, w, h),
+                   "mode": "4C (4)", "pictures_per_step": B, "l2": "input %.2f GB per step >> 126 MB L2" % (B * w * h * 3 / 1e9)},
+        "parity": "%d of %d chunks decoded per step (tests/test_gpu_scan.py checks the bytes against the CPU pipeline)" % (good_chunks, B * info.chunks_per_frame),
+        "gpu_launches": launches,
+        "kernel_ms_per_step": {"scan_blur_hist": blur_ms, "scan_otsu": otsu_ms, "scan_anchors": anch_ms},
+        "roofline": {"kernel": "k_scan_blur", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "traffic": None,
+                     "note": "3 bytes read + 1 written per pixel; the tile halo re-reads (2R per 128 x 32 tile) hit L2"},
+        "e2e": {"value": B * K / e2e_s, "unit": "pictures/s", "h2d_bytes_per_step": int(B * w * h * 3),
+                "d2h_bytes_per_step": int(chunks.nbytes + ccount.nbytes + cmask.nbytes + ff.nbytes + anchors.nbytes + 3 * count.nbytes),
+                "note": "cb200_scan_extract_decode_fountain from pinned host pictures, wall clock around K calls"},
+        "clocks": sampler.summary(),
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))

@@ -221,6 +221,10 @@ static int scan_run(cb200_ctx* c, const uint8_t* d_pics, int w, int h, int n)
         s->ws_pics = np; s->ws_rows_cap = rc;
     }
     CK(cudaMemsetAsync(s->d_hist, 0, sizeof(unsigned) * 256 * (size_t)n, st), "memset histograms");
+    // cb200_set_timing: one event set per scan -- [blur + histogram, Otsu, anchors] through cb200_get_timing
+    auto mark = [&]() { if (c->timing && c->ev_count[c->cur] < 8) cudaEventRecord(c->ev[c->cur][c->ev_count[c->cur]++], st); };
+    if (c->timing) { c->cur = (int)(c->calls % cb200_ctx::kEvSets); c->calls++; c->ev_count[c->cur] = 0; }
+    mark();
     const dim3 bgrid((unsigned)((w + kBlurTW - 1) / kBlurTW), (unsigned)((h + kBlurTH - 1) / kBlurTH), (unsigned)n);
     switch (R) {
     case 1: k_scan_blur<1><<<bgrid, kBlurThreads, 0, st>>>(d_pics, w, h, s->d_blur, s->d_hist); break;
@@ -229,9 +233,12 @@ static int scan_run(cb200_ctx* c, const uint8_t* d_pics, int w, int h, int n)
     default: k_scan_blur<4><<<bgrid, kBlurThreads, 0, st>>>(d_pics, w, h, s->d_blur, s->d_hist); break;
     }
     count_launch();
+    mark();
     k_scan_otsu<<<(n + 63) / 64, 64, 0, st>>>(s->d_hist, n, (double)npx, s->d_thr); count_launch();
+    mark();
     k_scan_anchors<<<n, kScanThreads, 0, st>>>(s->d_blur, s->d_thr, w, h, s->ws_rows_cap, s->d_rowbuf, s->d_rowcnt, s->d_pts, s->d_res, s->d_nres,
                                                s->d_anchors, s->d_count, s->d_cutoff, s->d_status); count_launch();
+    mark();
     CK(cudaGetLastError(), "scan launch");
     CK(cudaMemcpyAsync(s->h_anchors, s->d_anchors, sizeof(int4) * 4 * (size_t)n, cudaMemcpyDeviceToHost, st), "D2H anchors");
     CK(cudaMemcpyAsync(s->h_count, s->d_count, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st), "D2H counts");

@@ -10,12 +10,13 @@
 //                                                               nonzero result; -5 on a size that is not whole chunks)
 //   cimbard_get_filesize          :219-223                     (FountainMetadata(id).file_size())
 //   cimbard_get_report            :124-131
-// What stays outside (the anchor scan is host work that was never on the path, zstd is a consumer of the
-// finished file): Scanner and the zstd read-back (cimbard_get_filename / cimbard_decompress_read).  Without a scanner of its own
-// cimbard_scan_extract_decode takes what `./cimbar --no-deskew` takes -- an image that already has the mode's size -- and
-// answers -3 ("extract failed", the reference's value) for anything else; a caller that runs the reference's Scanner passes
-// its four anchor centres to cimbard_b200_extract_decode, which does the deskew + decode on the GPU.  The recovered file is
-// read back, undecompressed, with cimbard_b200_file_read (what cimbard_get_reassembled_file_buff exposes for the tests).
+// cimbard_scan_extract_decode runs the whole of it on the GPU: cb200_scan_extract_decode_fountain = Scanner::scan + Corners +
+// Deskewer::deskew + Decoder::decode_fountain with should_preprocess = true, as the reference does for EVERY image it is given
+// (an image that already is an extracted frame is scanned and warped again there too); fewer than four anchors -> -3.
+// What stays outside: the zstd read-back (cimbard_get_filename / cimbard_decompress_read), a consumer of the finished file.
+// Additions: cimbard_b200_extract_decode takes the anchor centres from a caller that has its own scanner (or NULL for
+// `./cimbar --no-deskew` input: an image of the mode's size, decoded as it is); the recovered file is read back, undecompressed,
+// with cimbard_b200_file_read (what cimbard_get_reassembled_file_buff exposes for the tests).
 //
 // State is per process, like the reference's (file-static sink and mode); calls are not thread-safe, like the reference's.
 #include "../../include/cb200.h"
@@ -142,7 +143,24 @@ int cimbard_b200_extract_decode(const unsigned char* imgdata, unsigned imgw, uns
 
 int cimbard_scan_extract_decode(const unsigned char* imgdata, unsigned imgw, unsigned imgh, int format, unsigned char* bufspace, unsigned bufsize)
 {
-    return cimbard_b200_extract_decode(imgdata, imgw, imgh, format, nullptr, bufspace, bufsize);
+    if (format <= 0) format = 3;
+    if (imgw == 0 || imgh == 0 || !imgdata || !bufspace) return -1;
+    cb200_info info;
+    if (!mode_info(info)) return -1;
+    if (bufsize < (unsigned)(info.chunk_size * info.chunks_per_frame)) return -2;
+    const uint8_t* rgb = to_rgb(imgdata, imgw, imgh, format);
+    if (!rgb) return -4;
+    if (ensure_ctx() != 0) return -6;
+    g_chunks.resize((size_t)info.chunk_size * info.chunks_per_frame);
+    uint32_t count = 0;
+    int32_t status = 0;
+    // Extractor::extract, then decode_fountain(img, ebw, shouldPreprocess = true) (cimbar_recv_js.cpp:171-186; color_correction
+    // defaults to 2, Decoder.h:31)
+    const uint32_t flags = CB200_FLAG_SHARPEN | CB200_FLAG_CC_FIT;
+    const int rc = cb200_scan_extract_decode_fountain(g_ctx, rgb, (int)imgw, (int)imgh, 1, flags, g_chunks.data(), &count, nullptr, nullptr, &status);
+    if (rc != CB200_OK) { g_report = std::string("scan/extract/decode: ") + cb200_last_error(); return -6; }
+    if (status <= 0) return -3;                                   // Extractor::FAILURE (cimbar_recv_js.cpp:175-176)
+    return finish(info, count, bufspace);
 }
 
 int64_t cimbard_fountain_decode(const unsigned char* buffer, unsigned size)

@@ -72,6 +72,7 @@ def test_mirrors_compile_against_the_references_own_stream_classes():
     import subprocess
     src = os.path.join(ROOT, "tests", "cpp", "shim_test.cpp")
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", src])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", os.path.join(ROOT, "tests", "cpp", "extractor_test.cpp")])   # Scanner / Extractor mirrors
     ref = "/root/reference/src/lib"
     if os.path.isdir(ref):
         subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-DCB200_WITH_REFERENCE_STREAMS", "-I" + ref, src])

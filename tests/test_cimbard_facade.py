@@ -54,7 +54,9 @@ def test_facade_sizes_and_argument_errors():
     buf = np.zeros(7500, np.uint8)
     assert L.cimbard_scan_extract_decode(img.ctypes.data, 0, 64, 3, buf.ctypes.data, 7500) == -1
     assert L.cimbard_scan_extract_decode(img.ctypes.data, 64, 64, 3, buf.ctypes.data, 7499) == -2
-    assert L.cimbard_scan_extract_decode(img.ctypes.data, 64, 64, 3, buf.ctypes.data, 7500) == -3     # not an extracted frame
+    # a picture without anchors: -3 (Extractor::FAILURE) from the GPU scan; -6 where there is no GPU (the library has no CPU path)
+    assert L.cimbard_scan_extract_decode(img.ctypes.data, 64, 64, 3, buf.ctypes.data, 7500) in (-3, -6)
+    assert L.cimbard_b200_extract_decode(img.ctypes.data, 64, 64, 3, None, buf.ctypes.data, 7500) == -3   # not an extracted frame
     big = np.zeros((1024, 1024, 3), np.uint8)
     assert L.cimbard_scan_extract_decode(big.ctypes.data, 1024, 1024, 12, buf.ctypes.data, 7500) == -4   # NV12 is not restated
     assert L.cimbard_fountain_decode(buf.ctypes.data, 0) == -5
@@ -115,6 +117,15 @@ def test_facade_frames_in_file_out():
     ctx.sync()
     frames = d_rgb.cpu().numpy()
     del ctx
+    # the synthetic renderer draws no anchors; the reference scans every image it is given (cimbar_recv_js.cpp:171-177), so the
+    # four anchor squares of a real encoder frame are pasted in (they lie outside every cell's threshold support)
+    import oracle_lib as ol
+    tr, c = ol.load_sample("b/tr_0.png"), 62
+    for ys in (slice(0, c), slice(1024 - c, 1024)):
+        for xs in (slice(0, c), slice(1024 - c, 1024)):
+            frames[:, ys, xs] = tr[ys, xs]
+    blank = np.zeros((480, 640, 3), np.uint8)
+    assert L.cimbard_scan_extract_decode(blank.ctypes.data, 640, 480, 3, np.zeros(7500, np.uint8).ctypes.data, 7500) == -3
     buf = np.zeros(L.cimbard_get_bufsize(), np.uint8)
     res = 0
     for f in range(n):

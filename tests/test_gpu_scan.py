@@ -126,3 +126,36 @@ def test_scan_extract_decode_is_its_parts(cb):
         assert status[0] == 2 and mask[0] == omask and np.array_equal(chunks[0], ochunks)
         assert good > 0
     ctx.close()
+
+
+def test_cpp_extractor_mirrors_rerun_reference_tests(cb, tmp_path):
+    """libcimbar_b200/host/Extractor.h keeps the reference's Scanner / Anchor / Extractor names; tests/cpp/extractor_test.cpp runs
+    ScannerTest/testExampleScan's and ExtractorTest's call shapes through them: golden anchor strings, Extractor's status, the
+    extracted frame == what Deskewer's two OpenCV calls give for those corners, and its decode == the oracle's."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "extractor_test")
+    libdir = os.path.join(root, "libcimbar_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "cpp", "extractor_test.cpp"),
+                           "-L" + libdir, "-lcb200", "-Wl,-rpath," + libdir])
+    O = ol.Oracle()
+    m = O.mode(4)
+    for g in ol.manifest()["scan_goldens"]:
+        rgb = ol.load_sample(g["sample"])
+        h, w = rgb.shape[:2]
+        fpath, prefix = str(tmp_path / "picture.rgb"), str(tmp_path / "out")
+        rgb.tofile(fpath)
+        res = subprocess.run([exe, "4", str(w), str(h), fpath, prefix], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert open(prefix + ".anchors").read() == g["scan"], g["source"]
+        anchors, _ = SO.scan(rgb)
+        xy = SO.corners(anchors)
+        assert int(open(prefix + ".status").read()) == (1 if SO.is_granular_scale(xy, 1024, 1024) else 2)
+        src = np.array(xy, np.float32).reshape(4, 2)
+        dst = np.array([[30, 30], [994, 30], [30, 994], [994, 994]], np.float32)
+        want = cv2.warpPerspective(rgb, cv2.getPerspectiveTransform(src, dst), (1024, 1024), flags=cv2.INTER_LINEAR)
+        frame = np.fromfile(prefix + ".frame", dtype=np.uint8).reshape(1024, 1024, 3)
+        assert np.array_equal(frame, want), g["sample"]
+        odata, ook = O.decode(m, want, use_ecc=True, sharpen=True)
+        assert np.array_equal(np.fromfile(prefix + ".ecc", dtype=np.uint8), odata), g["sample"]
