@@ -356,6 +356,154 @@ k_flood_raster_fast(const Mode m, const uint8_t* __restrict__ rgb, const uint32_
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fast raster, sharpen variant
+// needs_sharpen preprocessing of the WHOLE frame with OpenCV's borders (CimbReader.cpp:17-46): gray -> filter2D with
+// [0 -1 0; -1 4.5 -1; 0 -1 0] (BORDER_REFLECT_101, cvRound, saturate) -> adaptiveThreshold(MEAN_C, block 7, C = 0, BORDER_REPLICATE).
+// Same decomposition as k_flood_raster_fast (one CTA of 128 threads per 64-row band, 8 px per thread, rows streamed, tiled
+// output), with K1's packed sharpen arithmetic (k1_decode.cu, template SH): per sharpened row sr the thread holds the gray rows
+// above / at / below it (reflected at the frame's top and bottom; one new row per step except where a clamped row repeats),
+// exchanges the gray halo (reflected at the left / right edge), forms its eight sharpened pixels, exchanges their halo
+// (replicated at the edges), keeps seven rows of horizontal 7-sums and four sharpened rows, and emits the threshold byte of
+// row sr - 3: 49 s > boxsum + 24.  Two barriers per row.  A numpy model of exactly this schedule is checked against the
+// oracle over whole frames, borders included, in tests/test_k1x_sharpen_raster_model.py.
+__global__ void __launch_bounds__(kFastThreads)
+k_flood_raster_fast_sharpen(const Mode m, const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ list, const uint32_t* __restrict__ counters,
+                            int base, int cap, uint16_t* __restrict__ ws_raster)
+{
+    __shared__ uint32_t ex[2][kFastThreads];                       // gray halo words E (double buffered by load parity)
+    __shared__ uint32_t sx[2][2][kFastThreads];                    // sharpened halo words (s0,s1,s2) / (s5,s6,s7) (by row parity)
+    __shared__ __align__(16) uint8_t outb[2][16][kFastThreads];
+    const int W = m.width, H = m.height;
+    const int nthr = W >> 3;
+    const int nb = (H + kFastBand - 1) / kFastBand;
+    const int cnt = chunk_count(counters, base, cap);
+    const int t = threadIdx.x;
+    const bool act = t < nthr;
+    const int tc = act ? t : nthr - 1;                            // inactive threads shadow the last one
+    const bool firstT = t == 0, lastT = t >= nthr - 1;
+    const int tl = t > 0 ? t - 1 : 0, tr = t < kFastThreads - 1 ? t + 1 : t;
+    const size_t row_bytes = (size_t)W * 3;
+    const uint32_t kBias = 0x7FE77FE7u;                           // per half: 0x8000 - 25
+
+    for (int item = blockIdx.x; item < cnt * nb; item += gridDim.x) {
+        const int e = item / nb, band = item - e * nb;
+        const uint32_t f = list[base + e];
+        const uint8_t* frame = rgb + (size_t)f * row_bytes * (size_t)H;
+        uint16_t* raster = ws_raster + (size_t)e * raster_words16(W, H);
+        const int y0 = band * kFastBand, y1 = (y0 + kFastBand < H) ? y0 + kFastBand : H;
+        uint32_t Gu[4], Gc[4], Gd[4], lEc = 0, rEc = 0, lEd = 0, rEd = 0;      // gray rows above / at / below the sharpened row
+        uint32_t Qr[4][4], hr[7][4], nV[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nV[j] = kBias; Gu[j] = Gc[j] = Gd[j] = 0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) hr[i][j] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Qr[i][j] = 0;
+        }
+        int have_u = -9, have_c = -9, have_d = -9;
+        unsigned ld = 0;
+        uint2 pa = make_uint2(0, 0), pb = pa, pc = pa;             // a row requested one step ahead
+        int pf_row = -9;
+        auto fetch = [&](int y, uint2& a, uint2& b, uint2& c) {
+            const uint2* rp = reinterpret_cast<const uint2*>(frame + (size_t)y * row_bytes) + 3 * tc;
+            a = __ldg(rp); b = __ldg(rp + 1); c = __ldg(rp + 2);
+        };
+        auto load = [&](int y, uint32_t (&P)[4], uint32_t& lE, uint32_t& rE) {
+            uint2 a, b, c;
+            if (y == pf_row) { a = pa; b = pb; c = pc; } else fetch(y, a, b, c);
+            uint32_t E;
+            gray8_packed(a, b, c, P, E);
+            const unsigned par = ld & 1u; ++ld;
+            ex[par][t] = E;
+            __syncthreads();
+            // filter2D's BORDER_REFLECT_101 at the frame's left / right edge: g(-1) = g(1), g(W) = g(W-2)
+            lE = firstT ? __byte_perm(E, 0, 0x1111) : ex[par][tl];      // byte 3 is used: the left neighbour's g7
+            rE = lastT ? __byte_perm(E, 0, 0x2222) : ex[par][tr];       // byte 0 is used: the right neighbour's g0
+        };
+        __syncthreads();                                           // the previous item's last flush has been read
+        const int sr0 = y0 - 3;
+        for (int srb = sr0; srb < y1 + 3; srb += 7) {
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                const int sr = srb + u;
+                if (sr >= y1 + 3) break;
+                const int s = clampi(sr, 0, H - 1);                // adaptiveThreshold's BORDER_REPLICATE: the sharpened row repeats
+                const int wu = reflect101(s - 1, H), wd = reflect101(s + 1, H);
+                if (have_c == wu && have_d == s) {                 // one row further down: the common case
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { Gu[j] = Gc[j]; Gc[j] = Gd[j]; }
+                    lEc = lEd; rEc = rEd;
+                    load(wd, Gd, lEd, rEd);
+                } else if (!(have_u == wu && have_c == s && have_d == wd)) {
+                    uint32_t dl, dr;
+                    load(wu, Gu, dl, dr); load(s, Gc, lEc, rEc); load(wd, Gd, lEd, rEd);
+                }
+                have_u = wu; have_c = s; have_d = wd;
+                {   // the row the next step will want, requested now
+                    const int ns = clampi(sr + 1, 0, H - 1);
+                    pf_row = reflect101(ns + 1, H);
+                    fetch(pf_row, pa, pb, pc);
+                }
+                // ---- sharpen (k1_decode.cu, SH): twice = 9 c - 2 (up + down + left + right); s = clamp(round-half-even(twice / 2), 0, 255)
+                uint32_t Q[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t Pl = (j == 0) ? __byte_perm(lEc, Gc[3], 0x5453) : Gc[j > 0 ? j - 1 : 0];
+                    const uint32_t Pr = (j == 3) ? __byte_perm(Gc[0], rEc, 0x3432) : Gc[j < 3 ? j + 1 : 3];
+                    const uint32_t nbr = Gu[j] + Gd[j] + Pl + Pr;
+                    const uint32_t T = 9u * Gc[j] + (0x08000800u - 2u * nbr);
+                    const uint32_t tcl = __vminu2(__vmaxu2(T, 0x08000800u), 0x09FE09FEu) - 0x08000800u;
+                    Q[j] = ((tcl + ((tcl >> 1) & 0x00010001u)) >> 1) & 0x00FF00FFu;
+                }
+                const uint32_t FL = __byte_perm(__byte_perm(Q[0], Q[1], 0x0040), Q[2], 0x0410);     // (s0, s1, s2, .)
+                const uint32_t FH = __byte_perm(__byte_perm(Q[1], Q[2], 0x0062), Q[3], 0x0610);     // (s5, s6, s7, .)
+                const unsigned par2 = (unsigned)(sr - sr0) & 1u;
+                sx[par2][0][t] = FL; sx[par2][1][t] = FH;
+                __syncthreads();
+                // the box sum replicates at the left / right edge: S(-k) = s0, S(W-1+k) = s7
+                const uint32_t lF = firstT ? __byte_perm(FL, 0, 0x0000) : sx[par2][1][tl];
+                const uint32_t rF = lastT ? __byte_perm(FH, 0, 0x2222) : sx[par2][0][tr];
+                const uint32_t Qm3 = __byte_perm(lF, Q[1], 0x5450), Qm2 = __byte_perm(lF, Q[2], 0x5451), Qm1 = __byte_perm(lF, Q[3], 0x5452);
+                const uint32_t Q4 = __byte_perm(Q[0], rF, 0x3432), Q5 = __byte_perm(Q[1], rF, 0x3532), Q6 = __byte_perm(Q[2], rF, 0x3632);
+                uint32_t h[4];
+                h[0] = Qm3 + Qm2 + Qm1 + Q[0] + Q[1] + Q[2] + Q[3];
+                h[1] = h[0] - Qm3 + Q4;
+                h[2] = h[1] - Qm2 + Q5;
+                h[3] = h[2] - Qm1 + Q6;
+                uint32_t tj[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    nV[j] = nV[j] + hr[u][j] - h[j];                // drops row sr-7, adds row sr: window sr-6 .. sr
+                    hr[u][j] = h[j];
+                    Qr[0][j] = Qr[1][j]; Qr[1][j] = Qr[2][j]; Qr[2][j] = Qr[3][j]; Qr[3][j] = Q[j];
+                    tj[j] = 49u * Qr[0][j] + nV[j];                  // centre row sr-3; bit15 / bit31 = (49 s > boxsum + 24)
+                }
+                const int y = sr - 3;
+                if (y >= y0) {
+                    uint32_t byte = ((tj[0] >> 15) & 0x00010001u) | ((tj[1] >> 14) & 0x00020002u) |
+                                    ((tj[2] >> 13) & 0x00040004u) | ((tj[3] >> 12) & 0x00080008u);
+                    byte = (byte | (byte >> 12)) & 0xFFu;
+                    outb[(y >> 4) & 1][y & 15][t] = (uint8_t)byte;
+                    if ((y & 15) == 15 || y == y1 - 1) {
+                        __syncthreads();
+                        if (act) {
+                            const uint16_t* ob = reinterpret_cast<const uint16_t*>(&outb[(y >> 4) & 1][0][0]);
+                            const int tile = t >> 1, r0 = 8 * (t & 1);
+                            uint32_t w[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                w[k] = (uint32_t)ob[(r0 + 2 * k) * (kFastThreads / 2) + tile] | ((uint32_t)ob[(r0 + 2 * k + 1) * (kFastThreads / 2) + tile] << 16);
+                            uint16_t* dst = raster + raster_tile_index(W >> 4, 16 * tile, (y & ~15) + r0);
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- heap (warp-uniform)
 // 32-bit entries: prio(7) << 25 | cooldown code(3) << 22 | (dy + 8)(4) << 18 | (dx + 8)(4) << 14 | cell index(14).
 // std::priority_queue<decode_prio, vector, PrioCompare> with comp(a, b) = a.prio > b.prio: only the priority is compared,
@@ -988,7 +1136,13 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
     for (int c = 0; c < nchunks; ++c) {
         const int base = c * ws.entry_cap;
         const int cap = n_frames - base < ws.entry_cap ? n_frames - base : ws.entry_cap;
-        if (sharpen) {
+        // CB200_K1X_SHARPEN_RASTER=0 (tests, A/B): the round-1 shared-memory sharpen raster instead of the streaming one
+        const bool fast_sharpen = !(getenv("CB200_K1X_SHARPEN_RASTER") && atoi(getenv("CB200_K1X_SHARPEN_RASTER")) == 0);
+        if (sharpen && fast_sharpen) {
+            long long items = (long long)cap * ((m.height + kFastBand - 1) / kFastBand);
+            int rgrid = (int)(items < (long long)ws.sm_count * 8 ? items : (long long)ws.sm_count * 8);
+            k_flood_raster_fast_sharpen<<<rgrid, kFastThreads, 0, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);
+        } else if (sharpen) {
             long long items = (long long)cap * nb;
             int rgrid = (int)(items < (long long)ws.sm_count * 3 ? items : (long long)ws.sm_count * 3);
             k_flood_raster<true><<<rgrid, kRasterThreads, rs_bytes, st>>>(m, d_rgb, ws.list, ws.counters, base, cap, ws.raster);

@@ -811,3 +811,28 @@ def test_sharpen_with_noise_tiles_and_colour_correction(cb):
     finally:
         ORA.set_ccm(None)
     ctx.close()
+
+
+@pytest.mark.parametrize("mode_val", [68, 66])
+def test_sharpen_raster_of_the_exact_walk(cb, mode_val, monkeypatch):
+    """K1x's streaming sharpen raster (k_flood_raster_fast_sharpen: OpenCV's borders, reflect for the filter, replicate for the
+    box sum) against the oracle and against the round-1 shared-memory kernel (CB200_K1X_SHARPEN_RASTER=0), on frames whose cells
+    reach the borders' influence (noise everywhere) and, for mode Bu, on the 736 x 637 geometry with its 61-row last band"""
+    m = ORA.mode(mode_val)
+    rng = np.random.default_rng(400 + mode_val)
+    frames = rng.integers(0, 256, (5, m.image_size_y, m.image_size_x, 3), dtype=np.uint8)
+    frames[1, :, ::3] //= 4
+    frames[2] = np.repeat(np.repeat(rng.integers(0, 256, (m.image_size_y // 4 + 1, m.image_size_x // 4 + 1, 3), dtype=np.uint8), 4, 0), 4, 1)[:m.image_size_y, :m.image_size_x]
+    if mode_val == 68:
+        frames[3] = load_sample("b/ex2434.jpg"); frames[4] = load_sample("b/ex380.jpg")
+    ctx = cb.Context(mode_val, max_frames=5)
+    raw, ff = ctx.decode_raw(frames, flags=cb.FLAG_SHARPEN)
+    monkeypatch.setenv("CB200_K1X_SHARPEN_RASTER", "0")
+    raw0, ff0 = ctx.decode_raw(frames, flags=cb.FLAG_SHARPEN)
+    monkeypatch.delenv("CB200_K1X_SHARPEN_RASTER")
+    assert all(int(x) & cb.FRAME_FALLBACK for x in ff)
+    for f in range(5):
+        want = ORA.decode_raw(m, frames[f], sharpen=True)
+        assert np.array_equal(raw[f], want), f
+        assert np.array_equal(raw0[f], want), f
+    ctx.close()
