@@ -1066,6 +1066,13 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     ws->heap_smem = 1023;
     if (const char* s = getenv("CB200_K1X_HEAP_SMEM")) { int v = atoi(s); if (v >= 255 && v <= 32767) ws->heap_smem = v | 1; }
     ws->walk_smem = (size_t)(ws->heap_smem + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + (size_t)kPathSlots * 8;
+    // few frames (the one-frame-per-call shape of the mirrors and the facade, small camera batches): nothing hides the L2 round
+    // trips of the spilled heap levels then (a photograph's heap grows to ~4 500 entries, 19 500 pushes), so each walk gets the
+    // whole heap in shared memory -- 8 191 entries, 34 KB, six walks per SM -- and the spill area is only the overflow
+    ws->heap_smem_few = ws->heap_smem < 8191 ? 8191 : ws->heap_smem;
+    if (getenv("CB200_K1X_HEAP_SMEM")) ws->heap_smem_few = ws->heap_smem;               // a forced size is used for every batch
+    ws->walk_smem_few = (size_t)(ws->heap_smem_few + 1) * 4 + (size_t)(kMaxCells / 32) * 4 + (size_t)kPathSlots * 8;
+    ws->few_frames = sm_count * (int)((227u * 1024u) / (ws->walk_smem_few + 1024));
     int per_sm = (int)((227u * 1024u) / (ws->walk_smem + 1024));
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
@@ -1077,7 +1084,8 @@ cudaError_t flood_workspace_create(const Mode& m, int sm_count, const uint16_t* 
     if (const char* s = getenv("CB200_K1X_SERIAL_ABOVE")) ws->serial_above = atoi(s);      // tests: 0 forces the literal pop
     ws->spill_cap = 16 + 12 * (size_t)m.num_cells;   // every decoded cell pushes at most 12 entries (4 + 8 horizon)
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->walk_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_flood_walk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(ws->walk_smem > ws->walk_smem_few ? ws->walk_smem : ws->walk_smem_few))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_flood_raster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)raster_smem_bytes(m, true))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->spill, ws->spill_cap * (size_t)ws->slots * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&ws->prio, (size_t)kMaxCells * (size_t)ws->slots)) != cudaSuccess) return e;
@@ -1153,7 +1161,9 @@ cudaError_t flood_launch(const Mode& m, FloodWorkspace& ws, const uint8_t* d_rgb
         }
         count_launch();
         int wgrid = cap < ws.slots ? cap : ws.slots;
-        k_flood_walk<<<wgrid, 32, ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c, ws.heap_smem, ws.raster, ws.result,
+        const bool few = cap <= ws.few_frames;              // at most one wave of big-heap walks: latency over occupancy
+        k_flood_walk<<<wgrid, 32, few ? ws.walk_smem_few : ws.walk_smem, st>>>(m, ws.list, ws.counters, base, cap, ws.counters + 1 + c,
+                                                      few ? ws.heap_smem_few : ws.heap_smem, ws.raster, ws.result,
                                                       ws.spill, ws.spill_cap, ws.prio, ws.cinfo, d_trace, ws.serial_above,
                                                       1.0f / (float)(m.cells_x - 2 * m.corner), 1.0f / (float)m.cells_x); count_launch();
         long long cthreads = (long long)cap * m.num_cells;

@@ -21,6 +21,7 @@ struct FloodWorkspace {
     int slots;                 // walking warps resident at once (one frame each)
     int heap_smem;             // heap entries per walk kept in shared memory (odd)
     size_t walk_smem;          // dynamic shared memory of one walking warp
+    int heap_smem_few; size_t walk_smem_few; int few_frames;   // batches of at most few_frames listed frames: the whole heap in shared memory
     size_t spill_cap;          // heap spill entries per slot
     int serial_above;          // heap sizes above this use the one-level-per-step pop (65536; tests lower it)
     uint32_t* spill;           // [slots][spill_cap]
