@@ -87,52 +87,65 @@ static bool invert3(const double* S, double* t)
     return true;
 }
 
-// one thread = four consecutive destination pixels (12 bytes = three aligned words)
+// one thread = four consecutive destination pixels (12 bytes = three aligned words); blockIdx.y = frame (grid-strided), so the
+// index arithmetic is 32-bit.  The four taps of a pixel are loaded unconditionally from clamped coordinates and a tap outside the
+// source gets weight 0 (== BORDER_CONSTANT 0): no branch sits between the address arithmetic and the loads, so the 48 byte loads of
+// a thread's four pixels are all in flight together.
 __global__ void __launch_bounds__(256)
 k_deskew(const uint8_t* __restrict__ src, int src_w, int src_h, size_t src_frame_bytes, const double* __restrict__ minv, int n,
          int dst_w, int dst_h, int bw0, uint8_t* __restrict__ dst)
 {
     const int quads = dst_w >> 2;
-    const size_t total = (size_t)n * dst_h * quads;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int q = (int)(i % quads);
-        const size_t row = i / quads;
-        const int y = (int)(row % dst_h), f = (int)(row / dst_h);
+    const int per_frame = dst_h * quads;
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= per_frame) return;
+    const int y = i / quads, q = i - y * quads;
+    const int x = 4 * q, bx = (x / bw0) * bw0;
+    for (int f = (int)blockIdx.y; f < n; f += (int)gridDim.y) {
         const double* M = minv + (size_t)f * 9;
         const uint8_t* s = src + (size_t)f * src_frame_bytes;
-        const int x = 4 * q, bx = (x / bw0) * bw0;
+        const double M0 = __ldg(M), M1 = __ldg(M + 1), M2 = __ldg(M + 2), M3 = __ldg(M + 3), M4 = __ldg(M + 4), M5 = __ldg(M + 5),
+                     M6 = __ldg(M + 6), M7 = __ldg(M + 7), M8 = __ldg(M + 8);
         // no FMA contraction: OpenCV's x86-64 code rounds after every multiply and add
-        const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], (double)bx), __dmul_rn(M[1], (double)y)), M[2]);
-        const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], (double)bx), __dmul_rn(M[4], (double)y)), M[5]);
-        const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], (double)bx), __dmul_rn(M[7], (double)y)), M[8]);
-        uint32_t px[4][3];
+        const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M0, (double)bx), __dmul_rn(M1, (double)y)), M2);
+        const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M3, (double)bx), __dmul_rn(M4, (double)y)), M5);
+        const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M6, (double)bx), __dmul_rn(M7, (double)y)), M8);
+        uint32_t wgt[4][4];
+        uint32_t tap[4][4];                      // byte offsets of the taps inside the source picture (< 4 GB)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const double x1 = (double)(x + u - bx);
-            double W = __dadd_rn(W0, __dmul_rn(M[6], x1));
+            double W = __dadd_rn(W0, __dmul_rn(M6, x1));
             W = W != 0. ? __ddiv_rn(32.0, W) : 0.;
-            double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], x1)), W), fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], x1)), W);
+            double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M0, x1)), W), fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M3, x1)), W);
             fX = fmax(-2147483648.0, fmin(2147483647.0, fX)); fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
             const int X = __double2int_rn(fX), Y = __double2int_rn(fY);        // cvRound: to nearest, ties to even
             int sx = X >> 5, sy = Y >> 5;
             sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx); sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);   // saturate_cast<short>
             const uint32_t ax = (uint32_t)(X & 31), ay = (uint32_t)(Y & 31);
-            const uint32_t w00 = (32u - ax) * (32u - ay), w01 = ax * (32u - ay), w10 = (32u - ax) * ay, w11 = ax * ay;
             const bool x0in = sx >= 0 && sx < src_w, x1in = sx + 1 >= 0 && sx + 1 < src_w;
             const bool y0in = sy >= 0 && sy < src_h, y1in = sy + 1 >= 0 && sy + 1 < src_h;
-            uint32_t acc[3] = {512u, 512u, 512u};
-            if (y0in) {
-                const uint8_t* r0 = s + ((size_t)sy * src_w + sx) * 3;
-                if (x0in) { acc[0] += w00 * r0[0]; acc[1] += w00 * r0[1]; acc[2] += w00 * r0[2]; }
-                if (x1in) { acc[0] += w01 * r0[3]; acc[1] += w01 * r0[4]; acc[2] += w01 * r0[5]; }
-            }
-            if (y1in) {
-                const uint8_t* r1 = s + ((size_t)(sy + 1) * src_w + sx) * 3;
-                if (x0in) { acc[0] += w10 * r1[0]; acc[1] += w10 * r1[1]; acc[2] += w10 * r1[2]; }
-                if (x1in) { acc[0] += w11 * r1[3]; acc[1] += w11 * r1[4]; acc[2] += w11 * r1[5]; }
-            }
-            px[u][0] = acc[0] >> 10; px[u][1] = acc[1] >> 10; px[u][2] = acc[2] >> 10;
+            wgt[u][0] = (x0in && y0in) ? (32u - ax) * (32u - ay) : 0u;
+            wgt[u][1] = (x1in && y0in) ? ax * (32u - ay) : 0u;
+            wgt[u][2] = (x0in && y1in) ? (32u - ax) * ay : 0u;
+            wgt[u][3] = (x1in && y1in) ? ax * ay : 0u;
+            const int cx0 = sx < 0 ? 0 : (sx >= src_w ? src_w - 1 : sx), cx1 = sx + 1 < 0 ? 0 : (sx + 1 >= src_w ? src_w - 1 : sx + 1);
+            const int cy0 = sy < 0 ? 0 : (sy >= src_h ? src_h - 1 : sy), cy1 = sy + 1 < 0 ? 0 : (sy + 1 >= src_h ? src_h - 1 : sy + 1);
+            const uint32_t r0 = (uint32_t)cy0 * (uint32_t)src_w, r1 = (uint32_t)cy1 * (uint32_t)src_w;
+            tap[u][0] = 3u * (r0 + (uint32_t)cx0); tap[u][1] = 3u * (r0 + (uint32_t)cx1);
+            tap[u][2] = 3u * (r1 + (uint32_t)cx0); tap[u][3] = 3u * (r1 + (uint32_t)cx1);
         }
+        uint32_t v[4][4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[u][k][0] = __ldg(s + tap[u][k]); v[u][k][1] = __ldg(s + tap[u][k] + 1); v[u][k][2] = __ldg(s + tap[u][k] + 2); }
+        uint32_t px[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                px[u][ch] = (512u + wgt[u][0] * v[u][0][ch] + wgt[u][1] * v[u][1][ch] + wgt[u][2] * v[u][2][ch] + wgt[u][3] * v[u][3][ch]) >> 10;
         uint32_t* out = reinterpret_cast<uint32_t*>(dst + ((size_t)f * dst_h + y) * (size_t)dst_w * 3 + (size_t)x * 3);
         out[0] = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[1][0] << 24);
         out[1] = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | (px[2][1] << 24);
@@ -184,6 +197,7 @@ int cb200_perspective_transform(const float* src_xy, const float* dst_xy, double
 int cb200_deskew_dev(cb200_ctx* c, const uint8_t* d_src, int src_w, int src_h, int n, const double* m9, uint8_t* d_dst)
 {
     if (!c || !d_src || !m9 || !d_dst || n < 0 || src_w < 2 || src_h < 2) return fail(CB200_ERR_ARG, "bad arguments");
+    if ((size_t)src_w * (size_t)src_h * 3 >= ((size_t)1 << 32)) return fail(CB200_ERR_ARG, "source picture of 4 GB or more");
     if (n == 0) return CB200_OK;
     CK(cudaSetDevice(c->device), "cudaSetDevice");
     const Mode& m = c->mode;
@@ -204,11 +218,9 @@ int cb200_deskew_dev(cb200_ctx* c, const uint8_t* d_src, int src_w, int src_h, i
     // OpenCV's block geometry (WarpPerspectiveInvoker): bh0 = min(16, H); bw0 = min(1024 / bh0, W)
     const int bh0 = m.height < 16 ? m.height : 16;
     int bw0 = 1024 / bh0; if (bw0 > m.width) bw0 = m.width;
-    const size_t total = (size_t)n * m.height * (m.width / 4);
-    size_t blocks = (total + 255) / 256;
-    const size_t cap_blocks = (size_t)c->sm_count * 16;
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    k_deskew<<<(unsigned)blocks, 256, 0, c->stream>>>(d_src, src_w, src_h, (size_t)src_w * src_h * 3, d->d_minv, n, m.width, m.height, bw0, d_dst);
+    const int per_frame = m.height * (m.width / 4);
+    const dim3 grid((unsigned)((per_frame + 255) / 256), (unsigned)(n < 32768 ? n : 32768));
+    k_deskew<<<grid, 256, 0, c->stream>>>(d_src, src_w, src_h, (size_t)src_w * src_h * 3, d->d_minv, n, m.width, m.height, bw0, d_dst);
     count_launch();
     CK(cudaGetLastError(), "deskew launch");
     return CB200_OK;
