@@ -15,5 +15,6 @@ CB200_K1X_HEAP_SMEM=1023 timeout 200 python bench.py --camera --frames 512 --ste
 timeout 200 python bench.py --steps 3 --warmup 3 --frames 592 --no-cpu-baseline --no-e2e --workload noise1pct > $O/r2w_noise592.json 2> $O/r2w_noise592.err
 CB200_K1X_HEAP_SMEM=1023 timeout 200 python bench.py --steps 3 --warmup 3 --frames 592 --no-cpu-baseline --no-e2e --workload noise1pct > $O/r2w_noise592_heap1023.json 2> $O/r2w_noise592_heap1023.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/r2w_launches_camera.csv python bench.py --camera --frames 256 --steps 1 --warmup 3 --no-cpu-baseline > $O/r2w_camera_ncu.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k 'regex:k_scan_blur|k_scan_anchors|k_deskew' -c 3 -o $O/r2w_camera_kernels python bench.py --camera --frames 256 --steps 1 --warmup 3 --no-cpu-baseline > $O/r2w_camera_kernels_ncu.log 2>&1
 tail -3 $O/r2w_pytest.log
 echo done
