@@ -88,9 +88,28 @@ static bool invert3(const double* S, double* t)
 }
 
 // one thread = four consecutive destination pixels (12 bytes = three aligned words); blockIdx.y = frame (grid-strided), so the
-// index arithmetic is 32-bit.  The four taps of a pixel are loaded unconditionally from clamped coordinates and a tap outside the
-// source gets weight 0 (== BORDER_CONSTANT 0): no branch sits between the address arithmetic and the loads, so the 48 byte loads of
-// a thread's four pixels are all in flight together.
+// index arithmetic is 32-bit.  No branch sits between the address arithmetic and the loads, so the loads of a thread's four pixels
+// are all in flight together, and the two horizontal taps of a source row -- six consecutive bytes -- are fetched as aligned 32-bit
+// words and realigned by funnel shifts: a source that lies rotated in the photograph makes every lane hit its own sector, and the
+// kernel is then bound by L1 sector look-ups (ncu: 27 sectors per request), so fewer, wider requests are what counts.
+// A tap outside the source gets weight 0 (== BORDER_CONSTANT 0); its bytes come from a clamped, valid address.
+__device__ __forceinline__ void load_row_pair(const uint8_t* __restrict__ p, const uint8_t* __restrict__ end, uint32_t& lo, uint32_t& hi)
+{   // bytes p[0..5] -> lo = p[0..3], hi = p[4..5] (upper half unspecified); `end` = one past the last readable byte
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const uint32_t a = (uint32_t)(addr & 3u);
+    const uint8_t* base = p - a;
+    if (base + 12 <= end) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(base);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+        const uint32_t w2 = (a == 3u) ? __ldg(w + 2) : 0u;           // six bytes from offset 3 reach into the third word
+        lo = __funnelshift_r(w0, w1, 8u * a);
+        hi = __funnelshift_r(w1, w2, 8u * a);
+    } else {                                                        // the last few bytes of the buffer: byte loads
+        lo = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+        hi = (uint32_t)__ldg(p + 4) | ((uint32_t)__ldg(p + 5) << 8);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_deskew(const uint8_t* __restrict__ src, int src_w, int src_h, size_t src_frame_bytes, const double* __restrict__ minv, int n,
          int dst_w, int dst_h, int bw0, uint8_t* __restrict__ dst)
@@ -101,6 +120,7 @@ k_deskew(const uint8_t* __restrict__ src, int src_w, int src_h, size_t src_frame
     if (i >= per_frame) return;
     const int y = i / quads, q = i - y * quads;
     const int x = 4 * q, bx = (x / bw0) * bw0;
+    const uint8_t* const end = src + (size_t)n * src_frame_bytes;
     for (int f = (int)blockIdx.y; f < n; f += (int)gridDim.y) {
         const double* M = minv + (size_t)f * 9;
         const uint8_t* s = src + (size_t)f * src_frame_bytes;
@@ -111,7 +131,8 @@ k_deskew(const uint8_t* __restrict__ src, int src_w, int src_h, size_t src_frame
         const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M3, (double)bx), __dmul_rn(M4, (double)y)), M5);
         const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M6, (double)bx), __dmul_rn(M7, (double)y)), M8);
         uint32_t wgt[4][4];
-        uint32_t tap[4][4];                      // byte offsets of the taps inside the source picture (< 4 GB)
+        uint32_t off[4][2];                      // byte offsets of the two row pairs inside the source picture (< 4 GB)
+        bool left[4], right[4];                  // the pair was clamped: tap x1 is the pair's first pixel / tap x0 its second
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const double x1 = (double)(x + u - bx);
@@ -129,23 +150,32 @@ k_deskew(const uint8_t* __restrict__ src, int src_w, int src_h, size_t src_frame
             wgt[u][1] = (x1in && y0in) ? ax * (32u - ay) : 0u;
             wgt[u][2] = (x0in && y1in) ? (32u - ax) * ay : 0u;
             wgt[u][3] = (x1in && y1in) ? ax * ay : 0u;
-            const int cx0 = sx < 0 ? 0 : (sx >= src_w ? src_w - 1 : sx), cx1 = sx + 1 < 0 ? 0 : (sx + 1 >= src_w ? src_w - 1 : sx + 1);
+            // the pair of source pixels (c, c + 1) that holds whichever of the taps sx, sx + 1 are inside the row
+            const int c = sx < 0 ? 0 : (sx > src_w - 2 ? src_w - 2 : sx);
+            left[u] = sx < c; right[u] = sx > c;
             const int cy0 = sy < 0 ? 0 : (sy >= src_h ? src_h - 1 : sy), cy1 = sy + 1 < 0 ? 0 : (sy + 1 >= src_h ? src_h - 1 : sy + 1);
-            const uint32_t r0 = (uint32_t)cy0 * (uint32_t)src_w, r1 = (uint32_t)cy1 * (uint32_t)src_w;
-            tap[u][0] = 3u * (r0 + (uint32_t)cx0); tap[u][1] = 3u * (r0 + (uint32_t)cx1);
-            tap[u][2] = 3u * (r1 + (uint32_t)cx0); tap[u][3] = 3u * (r1 + (uint32_t)cx1);
+            off[u][0] = 3u * ((uint32_t)cy0 * (uint32_t)src_w + (uint32_t)c);
+            off[u][1] = 3u * ((uint32_t)cy1 * (uint32_t)src_w + (uint32_t)c);
         }
-        uint32_t v[4][4][3];
+        uint32_t lo[4][2], hi[4][2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { v[u][k][0] = __ldg(s + tap[u][k]); v[u][k][1] = __ldg(s + tap[u][k] + 1); v[u][k][2] = __ldg(s + tap[u][k] + 2); }
+        for (int u = 0; u < 4; ++u) { load_row_pair(s + off[u][0], end, lo[u][0], hi[u][0]); load_row_pair(s + off[u][1], end, lo[u][1], hi[u][1]); }
         uint32_t px[4][3];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
-                px[u][ch] = (512u + wgt[u][0] * v[u][0][ch] + wgt[u][1] * v[u][1][ch] + wgt[u][2] * v[u][2][ch] + wgt[u][3] * v[u][3][ch]) >> 10;
+            for (int ch = 0; ch < 3; ++ch) {
+                uint32_t acc = 512u;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint32_t pa = (lo[u][r] >> (8 * ch)) & 0xFFu;                                   // pixel c
+                    const uint32_t pb = ch == 0 ? lo[u][r] >> 24 : (hi[u][r] >> (8 * (ch - 1))) & 0xFFu;  // pixel c + 1
+                    const uint32_t v0 = right[u] ? pb : pa, v1 = left[u] ? pa : pb;                      // taps sx, sx + 1
+                    acc += wgt[u][2 * r] * v0 + wgt[u][2 * r + 1] * v1;
+                }
+                px[u][ch] = acc >> 10;
+            }
+        }
         uint32_t* out = reinterpret_cast<uint32_t*>(dst + ((size_t)f * dst_h + y) * (size_t)dst_w * 3 + (size_t)x * 3);
         out[0] = px[0][0] | (px[0][1] << 8) | (px[0][2] << 16) | (px[1][0] << 24);
         out[1] = px[1][1] | (px[1][2] << 8) | (px[2][0] << 16) | (px[2][1] << 24);
