@@ -31,6 +31,39 @@ def load_pictures():
     return out
 
 
+def cpu_pipeline(pics, reps=6):
+    """the same path on ONE host core, a bounded sample: the CPU restatement of the scan (oracle/scan_oracle.c), OpenCV's own
+    getPerspectiveTransform + warpPerspective (what Deskewer calls), the oracle's decode_fountain with should_preprocess = true"""
+    import cv2
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from scan_oracle_lib import ScanOracle
+    so, ora = ScanOracle(), ol.Oracle()
+    m = ora.mode(4)
+    W, H, an = m.image_size_x, m.image_size_y, 30
+    dst = np.array([[an, an], [W - an, an], [an, H - an], [W - an, H - an]], np.float32)
+    t_scan = t_warp = t_dec = 0.0
+    good = 0
+    for i in range(reps):
+        rgb = pics[i % len(pics)]
+        t0 = time.perf_counter()
+        anchors, _ = so.scan(rgb)
+        t1 = time.perf_counter()
+        assert len(anchors) == 4
+        src = np.array(so.corners(anchors), np.float32).reshape(4, 2)
+        frame = cv2.warpPerspective(rgb, cv2.getPerspectiveTransform(src, dst), (W, H), flags=cv2.INTER_LINEAR)
+        t2 = time.perf_counter()
+        g, _, _ = ora.decode_fountain(m, frame, sharpen=True)
+        t3 = time.perf_counter()
+        good += g
+        t_scan += t1 - t0; t_warp += t2 - t1; t_dec += t3 - t2
+    total = t_scan + t_warp + t_dec
+    return {"value": reps / total, "unit": "pictures/s (scan + deskew + decode)", "cores": 1, "kind": "port",
+            "sample": "%d of the sample photographs on one thread: oracle scan, cv2 warpPerspective, oracle decode_fountain with sharpen" % reps,
+            "stages_ms_per_picture": {"scan": 1e3 * t_scan / reps, "deskew_cv2": 1e3 * t_warp / reps, "decode": 1e3 * t_dec / reps},
+            "scan_only_pictures_per_s": reps / t_scan, "good_bytes_per_picture": good / reps}
+
+
 def run(args, ClockSampler, measured_peak_gbs):
     import torch
     import libcimbar_b200 as cb
@@ -116,21 +149,9 @@ def run(args, ClockSampler, measured_peak_gbs):
     algo = B * w * h * 4
     achieved = algo / (blur_ms * 1e-3) / 1e9
 
-    # CPU: the restatement of the scan on one core (oracle/scan_oracle.c), a bounded sample
-    cpu = None
-    if not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from scan_oracle_lib import ScanOracle
-        so = ScanOracle()
-        t0 = time.perf_counter()
-        reps = 6
-        for i in range(reps):
-            a, _ = so.scan(pics[i % len(pics)])
-            assert len(a) == 4
-        cpu_s = (time.perf_counter() - t0) / reps
-        cpu = {"value": 1.0 / cpu_s, "unit": "pictures/s (scan only)", "cores": 1, "kind": "port",
-               "sample": "%d scans of the two sample photographs, oracle/scan_oracle.c (gray + blur + Otsu + scan), one thread" % reps,
-               "gpu_scan_pictures_per_s": B / ((blur_ms + otsu_ms + anch_ms) * 1e-3)}
+    cpu = cpu_pipeline(pics) if not args.no_cpu_baseline else None
+    if cpu:
+        cpu["gpu_scan_pictures_per_s"] = B / ((blur_ms + otsu_ms + anch_ms) * 1e-3)
     out = {
         "metric": "camera pictures/s through scan + extract + decode (mode 4C photographs, should_preprocess = true)",
         "value": B * K / (dev_ms * 1e-3), "unit": "pictures/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
