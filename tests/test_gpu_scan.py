@@ -159,3 +159,22 @@ def test_cpp_extractor_mirrors_rerun_reference_tests(cb, tmp_path):
         assert np.array_equal(frame, want), g["sample"]
         odata, ook = O.decode(m, want, use_ecc=True, sharpen=True)
         assert np.array_equal(np.fromfile(prefix + ".ecc", dtype=np.uint8), odata), g["sample"]
+
+
+def test_scan_blur_kernels_agree(cb, monkeypatch):
+    """k_scan_blur4 (four pixels per thread: aligned word loads, IDP.2A gray, IDP.4A taps) against the one-pixel-per-element kernel
+    (CB200_SCAN_BLUR=0) and the oracle, on aligned and unaligned widths and all three kernel sizes the scanner uses"""
+    ctx = cb.Context(68, max_frames=1)
+    cam = ol.load_sample("6bit/4_30_f2_734.jpg")
+    for rgb in (cam, np.ascontiguousarray(cam[:, 3:958]), cv2.resize(cam, None, fx=1.7, fy=1.7), cv2.resize(cam, None, fx=2.9, fy=2.9)[:, :2781]):
+        h, w = rgb.shape[:2]
+        a1, c1, k1 = ctx.scan(rgb)
+        b1, t1 = ctx.scan_blurred(1, h, w)
+        monkeypatch.setenv("CB200_SCAN_BLUR", "0")
+        a0, c0, k0 = ctx.scan(rgb)
+        b0, t0 = ctx.scan_blurred(1, h, w)
+        monkeypatch.delenv("CB200_SCAN_BLUR")
+        t, bin_, bl = SO.preprocess(rgb)
+        assert np.array_equal(b1[0], bl) and np.array_equal(b0[0], bl) and t1[0] == t0[0] == t
+        assert np.array_equal(a1, a0) and c1[0] == c0[0] and k1[0] == k0[0]
+    ctx.close()

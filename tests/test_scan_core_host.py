@@ -39,6 +39,7 @@ def pictures():
     out.append(("627 x0.6", cv2.resize(cam, None, fx=0.6, fy=0.6, interpolation=cv2.INTER_AREA)))
     out.append(("627 x1.7 (blur 5)", cv2.resize(cam, None, fx=1.7, fy=1.7)))
     out.append(("627 cropped (anchor cut off)", np.ascontiguousarray(cam[:, 260:])))
+    out.append(("627 odd width (1277 x 957: no 4-byte aligned rows)", np.ascontiguousarray(cam[2:959, 1:1278])))
     rng = np.random.default_rng(3)
     out.append(("noise", rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)))
     out.append(("black", np.zeros((300, 400, 3), np.uint8)))
