@@ -46,4 +46,24 @@ ctx5 = cb.Context(68, max_frames=5)
 five = np.concatenate([frames[:3], frames[:2]])
 d5, ok5, _ = ctx5.decode(five)
 assert np.array_equal(d5[:3], payloads) and np.array_equal(d5[3:], payloads[:2]) and ok5.all()
+# second half of round 2: sharpen inside K1 (two barriers per stage, extra halo array), the walk's streaming sharpen raster, the anchor
+# scan (both blur kernels, Otsu, one CTA per picture) and scan + deskew (aligned word loads) + decode in one call
+raw_s, ff_s = ctx.decode_raw(frames, flags=cb.FLAG_SHARPEN)
+for f in range(4):
+    assert np.array_equal(raw_s[f], ora.decode_raw(m, frames[f], sharpen=True))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from scan_oracle_lib import ScanOracle
+so = ScanOracle()
+pic = load_sample("6bit/4_30_f2_734.jpg")[:, 1:958]              # 1280 x 957: rows that are not word aligned
+pic2 = load_sample("6bit/4color_ecc30_fountain_0.png")
+for p_ in (pic, pic2):
+    for blur in ("1", "0"):
+        os.environ["CB200_SCAN_BLUR"] = blur
+        anchors, count, cutoff = ctx.scan(p_)
+        want, want_cutoff = so.scan(p_)
+        assert count[0] == len(want) and [tuple(int(v) for v in a) for a in anchors[0][:count[0]]] == want and cutoff[0] == want_cutoff
+    del os.environ["CB200_SCAN_BLUR"]
+ctx4 = cb.Context(4, max_frames=2)
+chunks_c, count_c, mask_c, ff_c, status_c = ctx4.scan_extract_decode_fountain(np.stack([pic2, pic2[::-1].copy()]), flags=cb.FLAG_SHARPEN)
+assert status_c[0] > 0 and count_c[0] > 0
 print("sanitize_small: ok")
