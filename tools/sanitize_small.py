@@ -48,6 +48,7 @@ d5, ok5, _ = ctx5.decode(five)
 assert np.array_equal(d5[:3], payloads) and np.array_equal(d5[3:], payloads[:2]) and ok5.all()
 # second half of round 2: sharpen inside K1 (two barriers per stage, extra halo array), the walk's streaming sharpen raster, the anchor
 # scan (both blur kernels, Otsu, one CTA per picture) and scan + deskew (aligned word loads) + decode in one call
+ctx.set_ccm(None)                                   # the CC_FIT batch above may have left a fitted matrix in the context
 raw_s, ff_s = ctx.decode_raw(frames, flags=cb.FLAG_SHARPEN)
 for f in range(4):
     assert np.array_equal(raw_s[f], ora.decode_raw(m, frames[f], sharpen=True))
