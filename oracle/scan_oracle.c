@@ -4,6 +4,7 @@
  *
  * Restates, in plain C99 (reference file:line relative to /root/reference/src/lib/extractor/):
  *   Scanner::preprocess_image (fast)   Scanner.h:146-166, :124-128   cvtColor(RGB2GRAY) + GaussianBlur(unit, sigma 0) + Otsu
+ *   ... (fast = false)                 Scanner.h:130-136              adaptiveThreshold(MEAN_C, unit' x unit', -10) on the blurred picture
  *   ScanState / _114 / _122            ScanState.h:9-122
  *   Anchor                             Anchor.h:8-112
  *   scan_horizontal/vertical/diagonal  Scanner.h:176-276
@@ -118,6 +119,48 @@ int cbo_scan_preprocess(const uint8_t* rgb, int w, int h, uint8_t* bin, uint8_t*
     free(gray);
     if (!blurred) free(bl);
     return t;
+}
+
+/* Scanner::preprocess_image(img, fast=false) (Scanner.h:130-136, :146-166): the blurred gray image through
+ * adaptiveThreshold(255, ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY, unit, -10) with unit = nextPowerOfTwoPlusOne(unsigned(min(cols, rows) * 0.05)).
+ * OpenCV: mean = boxFilter(src, unit x unit, normalised, BORDER_REPLICATE) rounded to nearest (an odd area has no ties),
+ * dst = 255 where src - mean > 10 (delta = -10: tab[src - mean + 255] with idelta = cvCeil(delta)).  Pinned against cv2 in
+ * tests/test_scan_oracle.py.  Not on Extractor::extract's path (it constructs Scanner(img), fast = true); the device scan rejects it. */
+int cbo_scan_preprocess_adaptive(const uint8_t* rgb, int w, int h, uint8_t* bin)
+{
+    const int ksize = cbo_scan_blur_size(w, h);
+    if (!blur_kernel(ksize)) return -1;
+    const size_t n = (size_t)w * (size_t)h;
+    uint8_t* gray = (uint8_t*)malloc(n);
+    uint8_t* bl = (uint8_t*)malloc(n);
+    for (size_t i = 0; i < n; ++i)
+        gray[i] = (uint8_t)((9798u * rgb[3 * i] + 19235u * rgb[3 * i + 1] + 3735u * rgb[3 * i + 2] + 16384u) >> 15);
+    cbo_scan_gaussian_blur(gray, w, h, ksize, bl);
+    unsigned unit = (unsigned)(w < h ? w : h);
+    const int bs = (int)next_pow2_plus_one((unsigned)(unit * 0.05));
+    const int r = bs / 2;
+    const long long area = (long long)bs * bs;
+    /* integral image of the replicate-padded picture */
+    const int pw = w + 2 * r, ph = h + 2 * r;
+    long long* ii = (long long*)calloc((size_t)(pw + 1) * (size_t)(ph + 1), sizeof(long long));
+    for (int y = 0; y < ph; ++y) {
+        int sy = y - r; if (sy < 0) sy = 0; if (sy > h - 1) sy = h - 1;
+        long long rowsum = 0;
+        for (int x = 0; x < pw; ++x) {
+            int sx = x - r; if (sx < 0) sx = 0; if (sx > w - 1) sx = w - 1;
+            rowsum += bl[(size_t)sy * w + sx];
+            ii[(size_t)(y + 1) * (pw + 1) + (x + 1)] = ii[(size_t)y * (pw + 1) + (x + 1)] + rowsum;
+        }
+    }
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const long long S = ii[(size_t)(y + bs) * (pw + 1) + (x + bs)] - ii[(size_t)y * (pw + 1) + (x + bs)]
+                              - ii[(size_t)(y + bs) * (pw + 1) + x] + ii[(size_t)y * (pw + 1) + x];
+            const int mean = (int)((2 * S + area) / (2 * area));
+            bin[(size_t)y * w + x] = ((int)bl[(size_t)y * w + x] - mean > 10) ? 255 : 0;
+        }
+    free(ii); free(gray); free(bl);
+    return 0;
 }
 
 /* ------------------------------------------------------------------------------------------------ Anchor (Anchor.h) */
@@ -592,6 +635,16 @@ int cbo_scan(const uint8_t* rgb, int w, int h, cbo_anchor* out, unsigned* cutoff
     uint8_t* bin = (uint8_t*)malloc((size_t)w * (size_t)h);
     int n = -1;
     if (cbo_scan_preprocess(rgb, w, h, bin, NULL) >= 0) n = cbo_scan_bin(bin, w, h, out, cutoff_out);
+    free(bin);
+    return n;
+}
+/* Scanner(img, fast).scan(): fast = 0 is the adaptive-threshold variant (ScannerTest/testExampleScan.Adaptive) */
+int cbo_scan2(const uint8_t* rgb, int w, int h, int fast, cbo_anchor* out, unsigned* cutoff_out)
+{
+    if (fast) return cbo_scan(rgb, w, h, out, cutoff_out);
+    uint8_t* bin = (uint8_t*)malloc((size_t)w * (size_t)h);
+    int n = -1;
+    if (cbo_scan_preprocess_adaptive(rgb, w, h, bin) >= 0) n = cbo_scan_bin(bin, w, h, out, cutoff_out);
     free(bin);
     return n;
 }

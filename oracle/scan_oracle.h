@@ -15,6 +15,8 @@ int cbo_scan_blur_size(int w, int h);
 int cbo_scan_gaussian_blur(const uint8_t* src, int w, int h, int ksize, uint8_t* dst);
 int cbo_scan_otsu(const uint8_t* img, size_t n);
 int cbo_scan_preprocess(const uint8_t* rgb, int w, int h, uint8_t* bin, uint8_t* blurred);
+int cbo_scan_preprocess_adaptive(const uint8_t* rgb, int w, int h, uint8_t* bin);
+int cbo_scan2(const uint8_t* rgb, int w, int h, int fast, cbo_anchor* out, unsigned* cutoff_out);
 void cbo_scanner_init(cbo_scanner* s, const uint8_t* bin, int w, int h, int skip);
 /* kind: 114 = ScanState_114, 122 = ScanState_122.  The list functions return the total count (out holds min(count, cap)). */
 int cbo_scan_t1(const cbo_scanner* s, int kind, int skip, int y, int yend, int xstart, int xend, cbo_anchor* out, int cap);

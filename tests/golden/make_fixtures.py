@@ -72,7 +72,8 @@ SCAN_GOLDENS = [
      "t3_contains": ["210+-23,914+-24", "195+-25,61+-25", "1039+-22,887+-23"],
      "piecemeal_filtered": "195+-25,61+-25 210+-25,914+-24 1039+-23,887+-23",
      "cutoff": 1766, "primary": "210+-25,914+-24 195+-25,61+-25 1039+-23,887+-23",
-     "scan": "210+-25,914+-24 195+-25,61+-25 1039+-23,887+-23 1035+-23,68+-24"},
+     "scan": "210+-25,914+-24 195+-25,61+-25 1039+-23,887+-23 1035+-23,68+-24",
+     "scan_adaptive": "210+-25,914+-24 195+-25,61+-25 1039+-23,887+-23 1035+-23,67+-24"},      # testExampleScan.Adaptive, :178-189
     {"sample": "6bit/4color_ecc30_fountain_0.png", "source": "src/lib/extractor/test/ScannerTest.cpp:74-92, :164-176",
      "cutoff": 2268, "primary": "29+-27,29+-27 993+-27,29+-27 29+-27,993+-27",
      "scan": "29+-27,29+-27 993+-27,29+-27 29+-27,993+-27 993+-27,993+-27"},

@@ -162,3 +162,21 @@ def test_upscaled_picture_uses_the_nine_tap_blur_and_still_scans():
     small = SO.scan(rgb)[0]
     for a, b in zip(anchors, small):
         assert abs((a[0] + a[1]) // 2 - 3 * ((b[0] + b[1]) // 2)) <= 6 and abs((a[2] + a[3]) // 2 - 3 * ((b[2] + b[3]) // 2)) <= 6
+
+
+def test_adaptive_scanner_variant():
+    # Scanner(img, fast=false): ScannerTest/testExampleScan.Adaptive (ScannerTest.cpp:178-189) and cv2's adaptiveThreshold on the blurred picture
+    g = GOLD[0]
+    rgb = ol.load_sample(g["sample"])
+    h, w = rgb.shape[:2]
+    bin_ = np.zeros((h, w), np.uint8)
+    SO.lib.cbo_scan_preprocess_adaptive.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    assert SO.lib.cbo_scan_preprocess_adaptive(ol._ptr(rgb), w, h, ol._ptr(bin_)) == 0
+    bl = cv2.GaussianBlur(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY), (3, 3), 0)
+    want = cv2.adaptiveThreshold(bl, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, 65, -10)      # unit: 960 * 0.05 = 48 -> 65
+    assert np.array_equal(bin_, want)
+    from scan_oracle_lib import Anchor
+    out = (Anchor * 4)(); cutoff = C.c_uint(0)
+    SO.lib.cbo_scan2.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(Anchor), C.POINTER(C.c_uint)]
+    n = SO.lib.cbo_scan2(ol._ptr(rgb), w, h, 0, out, C.byref(cutoff))
+    assert n == 4 and join([out[i].tup() for i in range(4)]) == g["scan_adaptive"]
