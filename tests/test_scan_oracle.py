@@ -180,3 +180,38 @@ def test_adaptive_scanner_variant():
     SO.lib.cbo_scan2.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(Anchor), C.POINTER(C.c_uint)]
     n = SO.lib.cbo_scan2(ol._ptr(rgb), w, h, 0, out, C.byref(cutoff))
     assert n == 4 and join([out[i].tup() for i in range(4)]) == g["scan_adaptive"]
+
+
+def _average_hash(rgb):
+    # image_hash::average_hash (image_hash/average_hash.h:19-40): gray, cv::resize to 8 x 8, threshold = Cell::mean_grayscale (floor of the mean)
+    g = cv2.resize(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY), (8, 8))
+    thr = int(g.astype(np.uint32).sum()) // 64
+    v = 0
+    for b in (g > thr).reshape(-1):
+        v = (v << 1) | int(b)
+    return v
+
+
+@pytest.mark.parametrize("sample,want", [("6bit/4_30_f0_big.jpg", 0x2cab639cfa72624), ("6bit/4_30_f2_734.jpg", 0xc7f8205e686bc02),
+                                          ("6bit/4_30_f0_627.jpg", 0x29c64eaca3356394)])
+def test_extractor_goldens(sample, want, tmp_path):
+    """ExtractorTest/testExtract, testExtractMid, testExtractUpscale (extractor/test/ExtractorTest.cpp:13-50): ExtractorPlus::extract =
+    Scanner::scan -> Corners -> Deskewer, written as JPEG, read back, average_hash.  Scan by the restatement, the two OpenCV calls of
+    Deskewer::deskew by cv2: the reference's golden hashes come out, including the 3052 x 2704 picture (9-tap blur)."""
+    import os
+    if sample in ol.manifest()["samples"]:
+        rgb = ol.load_sample(sample)
+    else:
+        path = os.path.join("/root/reference/samples", sample)                  # 2.9 MB: not copied into tests/golden
+        if not os.path.exists(path):
+            pytest.skip("needs the reference checkout")
+        rgb = np.ascontiguousarray(cv2.cvtColor(cv2.imread(path), cv2.COLOR_BGR2RGB))
+    anchors, _ = SO.scan(rgb)
+    assert len(anchors) == 4
+    src = np.array(SO.corners(anchors), np.float32).reshape(4, 2)
+    dst = np.array([[30, 30], [994, 30], [30, 994], [994, 994]], np.float32)            # Deskewer.h:27-32, padding 0
+    out = cv2.warpPerspective(rgb, cv2.getPerspectiveTransform(src, dst), (1024, 1024), flags=cv2.INTER_LINEAR)
+    p = str(tmp_path / "ex.jpg")
+    cv2.imwrite(p, cv2.cvtColor(out, cv2.COLOR_RGB2BGR))
+    back = np.ascontiguousarray(cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB))
+    assert _average_hash(back) == want
