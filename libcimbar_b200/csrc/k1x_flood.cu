@@ -15,14 +15,17 @@
 //   k_flood_raster_fast  threshold raster of every listed frame: one CTA per 64-row band, 8 px per thread, K1's packed-16
 //                   SIMD arithmetic (IDP.2A gray, separable 5x5 box sum, one IMAD per pixel pair) with OpenCV's replicate
 //                   borders, rolling vertical sums in registers; output in 16x16-pixel TILES (32 B = one sector each) so that
-//                   a 10x10 window of the walk touches at most four sectors.  (k_flood_raster<true> is the sharpen variant:
-//                   3x3 sharpen + block 7, staged in shared memory; same tiled output.)
+//                   a 10x10 window of the walk touches at most four sectors.  k_flood_raster_fast_sharpen is the same for
+//                   needs_sharpen (3x3 sharpen with reflected borders + block 7 with replicated ones, rows streamed through
+//                   registers, two barriers per row); k_flood_raster<true>, the round-1 shared-memory kernel, is its A/B.
 //   k_flood_walk    the serial 12 400-step walk, ONE WARP PER FRAME, up to 32 frames per SM in flight (the walk is a chain
 //                   of dependent heap and window accesses, so throughput comes from walking many frames at once):
 //                   binary heap in shared memory (+ global spill); the sift-down of a pop resolves FIVE heap levels per
 //                   memory round trip (31 lanes load the child pairs of a 5-level subtree, one ballot, every lane checks
 //                   its ancestors' bits); the drift/cooldown a cell inherits travels inside the 32-bit heap entry, so the
 //                   only per-cell state is one priority byte in L2 and a bitmap in shared memory
+//                   (batches of at most one wave of big-heap walks keep the WHOLE heap in shared memory: 8 191 entries,
+//                   six walks per SM -- with few walks in flight nothing hides the L2 round trips of spilled levels)
 //   k_flood_colour  colours at the recorded drift-adjusted positions, one thread per cell
 #include "cb200_common.cuh"
 #include "k1x_flood.cuh"

@@ -6,15 +6,16 @@
 //                                                                   filter_candidates, sort_top_to_bottom) + add_bottom_right_corner
 //   Extractor::extract                          Extractor.h:30-46   scan -> Corners -> Deskewer (deskew.cu) -> NEEDS_SHARPEN test
 // Three kernels:
-//   k_scan_blur<R>   gray + separable fixed-point Gaussian (OpenCV's 8-bit path: coefficients / 256 from its small-kernel
+//   k_scan_blur4<R>  (k_scan_blur<R>: the one-pixel-per-element first version, CB200_SCAN_BLUR=0)
+//                    gray + separable fixed-point Gaussian (OpenCV's 8-bit path: coefficients / 256 from its small-kernel
 //                    table, BORDER_REFLECT_101, (sum + 2^15) >> 16) in 128 x 32 tiles staged in shared memory, plus the
 //                    picture's 256-bin histogram (shared-memory atomics, one global atomic per bin and tile)
 //   k_scan_otsu      getThreshVal_Otsu_8u in double precision, one thread per picture (no FMA contraction)
 //   k_scan_anchors   one CTA per picture runs scan_core.cuh's scan_picture: the rows of a t1 pass and the confirmation chains
 //                    of its hits are spread over the threads, the order-dependent tail (on_t1_scan's shadow test, libstdc++'s
 //                    std::sort, the bottom-right window) runs on thread 0
-// The pixel work (gray/blur/histogram) is HBM-bound: 3 bytes read and 1 written per pixel; the scan itself touches ~60 rows and
-// a few hundred short lines of the blurred picture.
+// The pixel work (gray/blur/histogram) moves 3 bytes in and 1 out per pixel (measured: 0.36 of the HBM copy peak, bound by
+// instruction issue); the scan itself touches ~60 rows and a few hundred short lines of the blurred picture.
 #include "ctx.cuh"
 #include "scan_core.cuh"
 
