@@ -3,8 +3,8 @@
 // Replaces (reference file:line relative to /root/reference/):
 //   Deskewer::deskew        src/lib/extractor/Deskewer.h:25-40: cv::getPerspectiveTransform(corners, outputPoints) +
 //                           cv::warpPerspective(img, output, transform, size, cv::INTER_LINEAR) to the mode's image size
-//   (Extractor::extract     src/lib/extractor/Extractor.h:30-46 calls it with the four anchor centres Scanner found; the anchor
-//                           scan itself stays on the host: the caller supplies the corners)
+//   (Extractor::extract     src/lib/extractor/Extractor.h:30-46 calls it with the four anchor centres Scanner found: scan.cu, or
+//                           corners the caller supplies)
 // OpenCV is a third-party dependency of the reference; its arithmetic is restated here and pinned against cv2 itself
 // (tests/test_deskew.py): getPerspectiveTransform = an 8x8 LU solve in double (hal LUImpl: partial pivoting, d = -1/pivot,
 // row updates, back substitution), cv::invert(3x3) in closed form, warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) =

@@ -1,9 +1,9 @@
 // Deskewer.h -- mirror of libcimbar's Deskewer and Corners (reference: src/lib/extractor/Deskewer.h:11-40, Corners.h:9-60).
 // Same constructor, same `deskew(img, corners)`: cv::getPerspectiveTransform(corners.all(), outputPoints) followed by
 // cv::warpPerspective(..., cv::INTER_LINEAR) to the mode's image size -- both restated bit for bit and run on the GPU
-// (cb200_perspective_transform / cb200_deskew, csrc/deskew.cu).  The anchor scan that produces the corners (Scanner) is not part
-// of this cut: the caller supplies them.  For the whole camera path in one call -- deskewed frames never leave the device --
-// use cb200_extract_decode_fountain.
+// (cb200_perspective_transform / cb200_deskew, csrc/deskew.cu).  The anchor scan that produces the corners runs on the GPU too: host/Extractor.h
+// (Scanner / Extractor mirrors over cb200_scan).  For the whole camera path in one call -- the picture goes to the device once, the
+// deskewed frame never leaves it -- use cb200_scan_extract_decode_fountain (or cb200_extract_decode_fountain with corners of your own).
 #pragma once
 #include "../../include/cb200.h"
 #include "Config.h"
