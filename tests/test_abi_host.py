@@ -80,3 +80,17 @@ def test_mirrors_compile_against_the_references_own_stream_classes():
     hosts = os.path.join(ROOT, "libcimbar_b200", "host")
     text = "".join(open(os.path.join(hosts, f)).read() for f in os.listdir(hosts))
     assert "class aligned_stream" not in text and "class escrow_buffer_writer" not in text
+
+
+def test_scan_entry_points_reject_bad_arguments_without_touching_a_gpu():
+    # argument checks come before any CUDA call: a null context / null pictures is CB200_ERR_ARG (-1) on any machine
+    lib = cb.load_library()
+    cnt = (C.c_int32 * 1)()
+    buf = np.zeros(64 * 64 * 3, np.uint8)
+    assert lib.cb200_scan(None, buf.ctypes.data, 64, 64, 1, None, cnt, None) == -1
+    assert lib.cb200_scan_dev(None, None, 64, 64, 1, None, cnt, None) == -1
+    st = (C.c_int32 * 1)()
+    cc = (C.c_uint32 * 1)()
+    assert lib.cb200_scan_extract_decode_fountain(None, buf.ctypes.data, 64, 64, 1, 0, buf.ctypes.data, cc, None, None, st) == -1
+    assert lib.cb200_scan_blurred(None, None, None, 64, 64, 1) == -1
+    assert b"bad arguments" in lib.cb200_last_error() or b"scan" in lib.cb200_last_error()
