@@ -8,8 +8,8 @@ through what the reference's facade does per picture (cimbar_recv_js.cpp:152-189
   * `value`: pictures/s with the pictures resident in HBM -- cb200_scan_dev + cb200_extract_decode_fountain_dev, CUDA events,
     incl. the one host round trip of 64 B of anchors per picture between scan and deskew;
   * `e2e`: the same through cb200_scan_extract_decode_fountain with pinned HOST pictures (H2D of 3.7 MB per picture inside);
-  * `roofline`: k_scan_blur (gray + Gaussian + histogram), algorithmic 4 B per pixel (3 read, 1 written), HBM-bound;
-  * `cpu_baseline`: the CPU restatement of the scan (oracle/scan_oracle.c) on one core, per picture, next to the GPU's.
+  * `roofline`: k_scan_blur4 (gray + Gaussian + histogram), algorithmic 4 B per pixel (3 read, 1 written);
+  * `cpu_baseline`: the same per-picture pipeline on one host core (the restatement's scan, cv2's deskew, the oracle's decode).
 Photographs need the exact flood walk (K1x), so the decode leg is the walk's throughput, not K1's."""
 import json
 import os
@@ -164,7 +164,7 @@ def run(args, ClockSampler, measured_peak_gbs):
         "parity": "%d of %d chunks decoded per step (tests/test_gpu_scan.py checks the bytes against the CPU pipeline)" % (good_chunks, B * info.chunks_per_frame),
         "gpu_launches": launches,
         "kernel_ms_per_step": {"scan_blur_hist": blur_ms, "scan_otsu": otsu_ms, "scan_anchors": anch_ms},
-        "roofline": {"kernel": "k_scan_blur", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"kernel": "k_scan_blur4", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "traffic": None,
                      "note": "3 bytes read + 1 written per pixel; the tile halo re-reads (2R per 128 x 32 tile) hit L2"},
         "e2e": {"value": E * K / e2e_s, "unit": "pictures/s", "h2d_bytes_per_step": int(E * w * h * 3),
